@@ -1,0 +1,121 @@
+/*
+  tmr_capi.h -- flat C view of the TMROctForest / TMROctantArray C++ classes.
+
+  The reference exposes its forest to Python through Cython
+  (reference tmr/TMR.pyx:3270-3790, tmr/cpp_headers/TMR.pxd:370-423), which
+  needs mpi4py/tacs/paropt/egads4py and cannot be built in this image.  This
+  header is the ctypes-friendly equivalent of that binding: one C function per
+  public method the Cython layer calls, nothing else.  The SAME source
+  (tmr_b200/csrc/capi/tmr_capi.cpp) is compiled twice:
+    * against the reference's own headers/sources  -> oracle/_ref/libtmr_ref.so
+    * against this repo's drop-in TMROctForest      -> tmr_b200/lib/libtmr_b200.so
+  which is the source-level proof that the drop-in keeps the class API.
+
+  All handles are opaque; arrays are plain pointers + sizes; octant records use
+  the reference's 24-byte layout (reference src/TMROctant.h:49-53).
+*/
+#ifndef TMR_CAPI_H
+#define TMR_CAPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* byte-identical to TMROctant (reference src/TMROctant.h:49-53) */
+typedef struct {
+  int32_t block, x, y, z, tag;
+  int16_t level, info;
+} tmrc_octant;
+
+typedef void *tmrc_forest; /* TMROctForest* */
+typedef void *tmrc_interp; /* TACSBVecInterp* (recording stand-in) */
+
+/* ---- library identity ------------------------------------------------- */
+const char *tmrc_backend(void); /* "reference-cpu" or "b200-cuda" */
+
+/* ---- TMROctForest (reference src/TMROctForest.h:46-181) ---------------- */
+tmrc_forest tmrc_forest_create(int mesh_order, int interp_type);
+void tmrc_forest_destroy(tmrc_forest f);
+void tmrc_set_connectivity(tmrc_forest f, int num_nodes, const int *block_conn,
+                           int num_blocks);
+void tmrc_set_mesh_order(tmrc_forest f, int mesh_order, int interp_type);
+int tmrc_get_mesh_order(tmrc_forest f);
+int tmrc_get_interp_type(tmrc_forest f);
+void tmrc_repartition(tmrc_forest f, int max_rank);
+void tmrc_create_trees(tmrc_forest f, int refine_level);
+void tmrc_create_random_trees(tmrc_forest f, int nrand, int min_level,
+                              int max_level);
+tmrc_forest tmrc_duplicate(tmrc_forest f);
+tmrc_forest tmrc_coarsen(tmrc_forest f);
+/* refinement == NULL refines every octant by one level */
+void tmrc_refine(tmrc_forest f, const int *refinement, int min_level,
+                 int max_level);
+void tmrc_balance(tmrc_forest f, int balance_corner);
+void tmrc_create_nodes(tmrc_forest f);
+
+/* getOctants()+getArray(): number of local octants / copy of the records */
+int tmrc_num_octants(tmrc_forest f);
+void tmrc_get_octants(tmrc_forest f, tmrc_octant *out);
+/* Python's OctantArray.__setitem__ (reference tmr/TMR.pyx:3303-3317) writes
+   through the borrowed array; this is the bulk form of that write. */
+void tmrc_write_octants(tmrc_forest f, const tmrc_octant *in, int n);
+
+/* getNodeConn: borrowed pointer, valid until the next mutating call */
+void tmrc_get_node_conn(tmrc_forest f, const int **conn, int *num_elements,
+                        int *num_owned_nodes);
+int tmrc_get_dep_node_conn(tmrc_forest f, const int **ptr, const int **conn,
+                           const double **weights);
+int tmrc_get_node_numbers(tmrc_forest f, const int **node_numbers);
+int tmrc_get_owned_node_range(tmrc_forest f, const int **node_range);
+int tmrc_get_ext_pre_offset(tmrc_forest f);
+int tmrc_get_local_node_number(tmrc_forest f, int node);
+int tmrc_get_interp_knots(tmrc_forest f, const double **knots);
+
+void tmrc_get_connectivity(tmrc_forest f, int *nblocks, int *nfaces,
+                           int *nedges, int *nnodes, const int **block_conn,
+                           const int **block_face_conn,
+                           const int **block_edge_conn,
+                           const int **block_face_ids);
+void tmrc_get_inverse_connectivity(tmrc_forest f, const int **node_block_conn,
+                                   const int **node_block_ptr,
+                                   const int **edge_block_conn,
+                                   const int **edge_block_ptr,
+                                   const int **face_block_conn,
+                                   const int **face_block_ptr);
+
+/* transformNode on n records in place (edge_dir = -1 for none); the two
+   optional outputs receive the edge_reversed / src_face_id of each call */
+void tmrc_transform_nodes(tmrc_forest f, tmrc_octant *nodes, int n,
+                          int edge_dir, int *edge_reversed, int *src_face_id);
+
+/* findEnclosing for n node-octants (info = local node index); out_index[i] is
+   the index of the enclosing element in the local array or -1; out_owner the
+   mpi owner estimate */
+void tmrc_find_enclosing(tmrc_forest f, int order, const double *knots,
+                         const tmrc_octant *nodes, int n, int *out_index,
+                         int *out_owner);
+
+/* createInterpolation into a recording interp object */
+tmrc_interp tmrc_interp_create(void);
+void tmrc_interp_destroy(tmrc_interp p);
+void tmrc_create_interpolation(tmrc_forest fine, tmrc_forest coarse,
+                               tmrc_interp p);
+/* rows in call order; rowp has nrows+1 entries */
+void tmrc_interp_get(tmrc_interp p, int *nrows, int *nnz, const int **rows,
+                     const int **rowp, const int **cols, const double **vals);
+
+/* ---- TMROctantArray (reference src/TMROctant.h:65-81) ------------------ */
+/* sort()+uniq in place; returns the new size */
+int tmrc_array_sort(tmrc_octant *array, int n, int use_node_index);
+/* contains() for nq queries against a (sorted) array; out_index = position
+   of the match or -1 */
+void tmrc_array_contains(tmrc_octant *array, int n, int use_node_index,
+                         const tmrc_octant *queries, int nq, int use_position,
+                         int *out_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
