@@ -1,0 +1,140 @@
+/*
+  tmrgpu.h -- the C-ABI between the host C++ drop-in (TMROctForest /
+  TMROctantArray, tmr_b200/csrc/host/) and the sm_100a CUDA layer
+  (tmr_b200/csrc/gpu/).  Plain pointers and sizes only; every function returns
+  0 on success and non-zero after printing "TMROctForest Error: ..." to stderr
+  (the reference's error convention, e.g. src/TMROctForest.cpp:2918-2923).
+
+  Each entry point names the reference code it replaces.  Host buffers are
+  caller-owned; device state lives behind the opaque handles.  There is no CPU
+  implementation behind this interface.
+*/
+#ifndef TMRGPU_H
+#define TMRGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tmrgpu_ctx tmrgpu_ctx;       /* device + stream + scratch    */
+typedef struct tmrgpu_forest tmrgpu_forest; /* device-resident octant forest */
+
+/* byte-identical to TMROctant (reference src/TMROctant.h:49-53) */
+typedef struct {
+  int32_t block, x, y, z, tag;
+  int16_t level, info;
+} tmrgpu_octant;
+
+/* ---- context ------------------------------------------------------------ */
+/* stream: a cudaStream_t created by the caller (e.g. torch's current stream)
+   or NULL for a private stream.  Fails when no CUDA device is present. */
+int tmrgpu_ctx_create(int device, void *stream, tmrgpu_ctx **out);
+int tmrgpu_ctx_destroy(tmrgpu_ctx *ctx);
+int tmrgpu_ctx_sync(tmrgpu_ctx *ctx);
+void *tmrgpu_ctx_stream(tmrgpu_ctx *ctx);
+/* per-kernel CUDA-event timing (bench roofline): enable, reset, read as JSON
+   {"kernel": {"launches": n, "ms": t}, ...}; returns bytes needed */
+int tmrgpu_profile_enable(tmrgpu_ctx *ctx, int on);
+int tmrgpu_profile_reset(tmrgpu_ctx *ctx);
+int tmrgpu_profile_json(tmrgpu_ctx *ctx, char *buf, int buflen);
+long tmrgpu_launch_count(tmrgpu_ctx *ctx);
+
+/* ---- forest -------------------------------------------------------------- */
+int tmrgpu_forest_create(tmrgpu_ctx *ctx, tmrgpu_forest **out);
+int tmrgpu_forest_destroy(tmrgpu_forest *f);
+
+/* Super-mesh tables computed by the host class (replaces the reads of
+   TMRBlockConn in reference src/TMROctForest.h:323-410).  Arrays are copied. */
+int tmrgpu_set_connectivity(
+    tmrgpu_forest *f, int nblocks, int nnodes, int nedges, int nfaces,
+    const int *block_conn, const int *block_edge_conn,
+    const int *block_face_conn, const int *block_face_ids,
+    const int *node_block_ptr, const int *node_block_conn,
+    const int *edge_block_ptr, const int *edge_block_conn,
+    const int *face_block_ptr, const int *face_block_conn,
+    const int *node_block_owners, const int *edge_block_owners,
+    const int *face_block_owners);
+/* share src's tables with dst (duplicate()/coarsen(): reference copyData
+   src/TMROctForest.cpp:488-500) */
+int tmrgpu_share_connectivity(tmrgpu_forest *src, tmrgpu_forest *dst);
+
+/* element array <-> host records */
+int64_t tmrgpu_count(tmrgpu_forest *f);
+int tmrgpu_upload_octants(tmrgpu_forest *f, const tmrgpu_octant *recs,
+                          int64_t n);
+int tmrgpu_download_octants(tmrgpu_forest *f, tmrgpu_octant *recs);
+int tmrgpu_download_info(tmrgpu_forest *f, int16_t *info);
+
+/* sort + uniq the device element array in place (TMROctantArray::sort,
+   reference src/TMROctant.cpp:357-399, as used by createRandomTrees :1884) */
+int tmrgpu_sort_unique(tmrgpu_forest *f);
+
+/* createTrees for blocks [block_start, block_end)
+   (reference src/TMROctForest.cpp:1744-1833) */
+int tmrgpu_create_trees(tmrgpu_forest *f, int level, int block_start,
+                        int block_end);
+/* refine (reference :2169-2329); flags on the host (copied inside) or already
+   on the device; NULL = refine everything by one level */
+int tmrgpu_refine(tmrgpu_forest *f, const int *h_flags, int min_level,
+                  int max_level);
+int tmrgpu_refine_device(tmrgpu_forest *f, const int *d_flags, int min_level,
+                         int max_level);
+/* balance (reference :2917-3089) */
+int tmrgpu_balance(tmrgpu_forest *f, int balance_corner);
+/* coarsen / duplicate into an existing forest (reference :2097-2164) */
+int tmrgpu_coarsen(tmrgpu_forest *src, tmrgpu_forest *dst);
+int tmrgpu_duplicate(tmrgpu_forest *src, tmrgpu_forest *dst);
+
+/* createNodes (reference :4064-4268).  knots: `order` interpolation knots. */
+int tmrgpu_create_nodes(tmrgpu_forest *f, int order, int interp_type,
+                        const double *knots);
+int tmrgpu_free_nodes(tmrgpu_forest *f);
+/* sizes: [0] elements [1] local nodes [2] dependent nodes [3] owned nodes
+   [4] dependent nnz [5] first owned node number */
+int tmrgpu_node_sizes(tmrgpu_forest *f, int64_t sizes[6]);
+/* copy-out; any pointer may be NULL to skip that array */
+int tmrgpu_download_nodes(tmrgpu_forest *f, int *conn, int *node_numbers,
+                          int *dep_ptr, int *dep_conn, double *dep_weights);
+
+/* createInterpolation (reference :6611-6793) between two forests that both
+   have nodes.  Builds the CSR on the device; rows are emitted in the
+   reference's call order (first touch in element order). */
+int tmrgpu_create_interp(tmrgpu_forest *fine, tmrgpu_forest *coarse,
+                         int64_t *nrows, int64_t *nnz);
+int tmrgpu_download_interp(tmrgpu_forest *fine, int *rows, int *rowp,
+                           int *cols, double *vals);
+/* batched findEnclosing against this forest's elements (reference
+   :6228-6377): nodes are element records whose info = local node index */
+int tmrgpu_find_enclosing(tmrgpu_forest *f, int order, const double *knots,
+                          const tmrgpu_octant *nodes, int64_t n,
+                          int *out_index);
+
+/* ---- TMROctantArray (reference src/TMROctant.cpp:357-424) ----------------- */
+/* sort + uniq of an arbitrary host array, in place; *nout = new size.
+   use_node_index: 0 element mode (keep finest per anchor), 1 node mode */
+int tmrgpu_array_sort(tmrgpu_ctx *ctx, tmrgpu_octant *recs, int64_t n,
+                      int use_node_index, int64_t *nout);
+/* batched contains() against a SORTED host array: mode 0 exact element,
+   1 position only, 2 node (position+info); out_index = match or -1 */
+int tmrgpu_array_contains(tmrgpu_ctx *ctx, const tmrgpu_octant *sorted,
+                          int64_t n, const tmrgpu_octant *queries, int64_t nq,
+                          int mode, int *out_index);
+
+/* ---- measurement helpers (bench.py / tests) ------------------------------- */
+/* hash-driven refinement flags on the device (SURVEY.md 8(d) recipe):
+   flag = record_hash(seed, octant) % 100 < pct; d_flags has count() ints */
+int tmrgpu_synth_flags(tmrgpu_forest *f, uint64_t seed, int pct, int *d_flags);
+/* order-independent checksum: sum of record_hash(0, octant) mod 2^64 */
+int tmrgpu_checksum(tmrgpu_forest *f, uint64_t *out);
+/* raw device allocations for bench-owned buffers */
+int tmrgpu_dev_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out);
+int tmrgpu_dev_free(tmrgpu_ctx *ctx, void *p);
+/* [0] octants before refine, [1] after refine, [2] after balance */
+int tmrgpu_last_counts(tmrgpu_forest *f, int64_t counts[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,37 @@
+/*
+  tests/emu/prim_emu.h -- TEST INFRASTRUCTURE ONLY.
+
+  Serial host stand-ins for the three device primitives (launch, scan_counts,
+  radix_sort) so that the kernel BODIES of tmr_b200/csrc/gpu/ops_*.h -- plain
+  TMR_HD functors -- and their host orchestration can be run against the
+  oracle on a machine without a GPU.  Built only by tests/emu/Makefile into
+  tests/emu/_build/; the product library (tmr_b200/lib) never contains or
+  loads it.
+*/
+#ifndef TMRGPU_PRIM_EMU_H
+#define TMRGPU_PRIM_EMU_H
+
+#include "prim.h"
+
+namespace tmrgpu {
+
+template <class F>
+void launch(Ctx &ctx, i64 n, F f, const char *) {
+  for (i64 i = 0; i < n; i++) f(i);
+  ctx.launch_count++;
+}
+
+template <class F>
+u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *) {
+  u64 run = 0;
+  for (i64 i = 0; i < n; i++) {
+    const u32 c = f(i);
+    out[i] = (u32)run;
+    run += c;
+  }
+  ctx.launch_count++;
+  return run;
+}
+
+}  // namespace tmrgpu
+#endif

@@ -1,0 +1,118 @@
+/*
+  forest_state.h -- the device-resident forest.
+
+  Elements live in HBM as ONE sorted array of 64-bit keys (common.h: KeyFmt)
+  plus an optional int16 `info` array; the reference's 24-byte TMROctant
+  records (reference src/TMROctant.h:36-54) are only materialised when the
+  host asks for them.  Node data (conn, numbers, dependent CSR) stays on the
+  device until downloaded.
+*/
+#ifndef TMRGPU_FOREST_STATE_H
+#define TMRGPU_FOREST_STATE_H
+
+#include <memory>
+
+#include "prim.h"
+#if defined(TMRGPU_EMU)
+#include "prim_emu.h"
+#else
+#include "prim_cuda.cuh"
+#endif
+
+namespace tmrgpu {
+
+static const int kMaxOrder = 3; /* orders 2 and 3 (label-free node sets) */
+
+struct NodeData {
+  bool valid;
+  int order;
+  int interp_type;
+  double knots[4];
+  i64 num_elements;
+  i64 num_local_nodes; /* unique node entries referenced on this rank */
+  i64 num_dep_nodes;
+  i64 num_owned_nodes;
+  i64 dep_nnz;
+  int node_range_start; /* first global number owned by this rank */
+  NodeFmt nfmt;
+  DBuf<u64> node_keys;  /* sorted unique node keys [num_local_nodes] */
+  DBuf<int> node_num;   /* number of each node entry (node order) */
+  DBuf<int> conn;       /* [num_elements * order^3], global numbers */
+  DBuf<int> dep_ptr;    /* [num_dep_nodes + 1] */
+  DBuf<int> dep_conn;   /* [dep_nnz] */
+  DBuf<double> dep_weights;
+  NodeData()
+      : valid(false), order(2), interp_type(1), num_elements(0),
+        num_local_nodes(0), num_dep_nodes(0), num_owned_nodes(0), dep_nnz(0),
+        node_range_start(0) {}
+  void clear() {
+    valid = false;
+    node_keys.reset();
+    node_num.reset();
+    conn.reset();
+    dep_ptr.reset();
+    dep_conn.reset();
+    dep_weights.reset();
+    num_elements = num_local_nodes = num_dep_nodes = num_owned_nodes = 0;
+    dep_nnz = 0;
+  }
+};
+
+/* prolongation rows built by createInterpolation (fine forest owns them) */
+struct InterpData {
+  bool valid;
+  i64 nrows, nnz;
+  DBuf<int> rows; /* global fine node number of each row, in emission order */
+  DBuf<int> rowp; /* [nrows + 1] */
+  DBuf<int> cols;
+  DBuf<double> vals;
+  InterpData() : valid(false), nrows(0), nnz(0) {}
+  void clear() {
+    valid = false;
+    nrows = nnz = 0;
+    rows.reset();
+    rowp.reset();
+    cols.reset();
+    vals.reset();
+  }
+};
+
+struct Forest {
+  Ctx *ctx;
+  /* connectivity tables (device copies) */
+  ConnTables tables;
+  std::shared_ptr<DBuf<int> > table_store;
+  int nblocks;
+  int bbits;
+  /* elements */
+  DBuf<u64> keys;
+  DBuf<int16_t> info; /* empty => all zero */
+  i64 n;
+  KeyFmt fmt;
+  NodeData nodes;
+  InterpData interp;
+  /* counters describing the last operation (for bench/roofline reporting) */
+  i64 last_in, last_mid, last_out;
+
+  explicit Forest(Ctx *c)
+      : ctx(c), nblocks(0), bbits(1), n(0), last_in(0), last_mid(0),
+        last_out(0) {
+    fmt.D = 0;
+    fmt.bbits = 1;
+    tables = ConnTables();
+  }
+};
+
+inline int bits_for(int nblocks) {
+  int b = 1;
+  while ((1LL << b) < nblocks) b++;
+  return b;
+}
+
+inline bool key_budget_ok(const Forest &f, int D) {
+  return f.bbits + 3 * D + 5 <= 64 && D <= 19;
+}
+
+}  // namespace tmrgpu
+
+#endif

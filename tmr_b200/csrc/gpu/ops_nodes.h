@@ -1,0 +1,641 @@
+/*
+  ops_nodes.h -- createNodes on the device (single-rank numbering; the
+  multi-rank ownership exchange builds on the same arrays).
+
+  Pipeline (replaces reference src/TMROctForest.cpp:4064-4268 and its helpers
+  computeDepFacesAndEdges :3619-3702, createLocalNodes :4290-4640,
+  createLocalConn :4660-4867, labelDependentNodes :3711-3832,
+  createDependentConn :5157-5519):
+
+    hanging_info      per element: 3 face + 3 edge exact-leaf probes (binary
+                      search in the sorted key array, inter-tree transforms)
+    node_candidates   order^3 canonical node keys per element (transformNode)
+                      with payload = element*order^3 + slot
+    radix sort + run heads  -> unique node array, conn[payload] = run index
+                      (one sort instead of 8-27 bsearches per element)
+    dep_label         mark hanging nodes; scan -> dependent / independent
+                      numbering in node order
+    dep_winner        per dependent node: the LAST (element, edge|face) in the
+                      reference's loop order that writes its stencil
+                      (atomicMax), which is the writer whose data survives in
+                      the reference
+    dep_fill          one thread per dependent node: parent edge/face node
+                      numbers (binary search in the node keys) + fp64 weights
+*/
+#ifndef TMRGPU_OPS_NODES_H
+#define TMRGPU_OPS_NODES_H
+
+#include "ops_balance.h"
+
+namespace tmrgpu {
+
+struct ElemView {
+  const u64 *keys;
+  i64 n;
+  KeyFmt fmt;
+  ConnTables t;
+
+  TMR_HD bool leaf_exists(i32 block, i32 x, i32 y, i32 z, int level) const {
+    return find_u64(keys, n, fmt.encode(block, x, y, z, level)) >= 0;
+  }
+  /* is there a level-`level` leaf in another tree that is the image of the
+     out-of-tree octant (x,y,z) across face f?  (reference checkAdjacentFaces
+     src/TMROctForest.cpp:3465-3521) */
+  TMR_HD bool across_face(int f, i32 block, i32 x, i32 y, i32 z,
+                          int level) const {
+    const i32 h = 1 << (kMaxLevel - level);
+    const i32 M = kHmax - h;
+    const int face = t.block_face_conn[6 * block + f];
+    i32 a, b, u, v;
+    face_pick(f, x, y, z, &a, &b);
+    face_to_owner(t.block_face_ids[6 * block + f], M, a, b, &u, &v);
+    for (int ip = t.face_block_ptr[face]; ip < t.face_block_ptr[face + 1];
+         ip++) {
+      const int adj = t.face_block_conn[ip] / 6;
+      if (adj == block) continue;
+      const int af = t.face_block_conn[ip] % 6;
+      i32 a1, b1, X, Y, Z;
+      owner_to_face(t.block_face_ids[6 * adj + af], M, u, v, &a1, &b1);
+      face_place(af, M * (af & 1), a1, b1, &X, &Y, &Z);
+      if (leaf_exists(adj, X, Y, Z, level)) return true;
+    }
+    return false;
+  }
+  /* same across tree edge e (reference checkAdjacentEdges :3532-3605) */
+  TMR_HD bool across_edge(int e, i32 block, i32 x, i32 y, i32 z,
+                          int level) const {
+    const i32 h = 1 << (kMaxLevel - level);
+    const i32 M = kHmax - h;
+    const i32 u = (e < 4) ? x : (e < 8 ? y : z);
+    const int edge = t.block_edge_conn[12 * block + e];
+    for (int ip = t.edge_block_ptr[edge]; ip < t.edge_block_ptr[edge + 1];
+         ip++) {
+      const int adj = t.edge_block_conn[ip] / 12;
+      if (adj == block) continue;
+      const int ae = t.edge_block_conn[ip] % 12;
+      const i32 uu = edge_is_reversed(t, block, e, adj, ae) ? M - u : u;
+      i32 X, Y, Z;
+      edge_place(ae, uu, M, &X, &Y, &Z);
+      if (leaf_exists(adj, X, Y, Z, level)) return true;
+    }
+    return false;
+  }
+};
+
+TMR_HD int child_id_of(i32 x, i32 y, i32 z, int level) {
+  const i32 h = 1 << (kMaxLevel - level);
+  return ((x & h) ? 1 : 0) | ((y & h) ? 2 : 0) | ((z & h) ? 4 : 0);
+}
+
+/* offset of the same-level neighbour across block edge e, in units of h */
+TMR_HD void edge_dir(int e, int *dx, int *dy, int *dz) {
+  const int s = e & 3;
+  const int a = (s & 1) ? 1 : -1, b = (s >> 1) ? 1 : -1;
+  if (e < 4) {
+    *dx = 0; *dy = a; *dz = b;
+  } else if (e < 8) {
+    *dx = a; *dy = 0; *dz = b;
+  } else {
+    *dx = a; *dy = b; *dz = 0;
+  }
+}
+
+/* 6-bit hanging info of every element
+   (reference computeDepFacesAndEdges src/TMROctForest.cpp:3619-3702) */
+struct HangingFn {
+  ElemView ev;
+  int16_t *info;
+  TMR_HD void operator()(i64 i) const {
+    i32 block, x, y, z;
+    int level;
+    ev.fmt.decode(ev.keys[i], &block, &x, &y, &z, &level);
+    if (level == 0) {
+      info[i] = 0;
+      return;
+    }
+    const int id = child_id_of(x, y, z, level);
+    const i32 h = 1 << (kMaxLevel - level);
+    const i32 hp = 2 * h;
+    const i32 px = x & ~h, py = y & ~h, pz = z & ~h;
+    const int pl = level - 1;
+    int bits = 0;
+    for (int k = 0; k < 3; k++) {
+      const int f = child_face(id, k);
+      const i32 d = (f & 1) ? hp : -hp;
+      const i32 nx = px + (k == 0 ? d : 0);
+      const i32 ny = py + (k == 1 ? d : 0);
+      const i32 nz = pz + (k == 2 ? d : 0);
+      const i32 c = (k == 0) ? nx : (k == 1 ? ny : nz);
+      bool hit;
+      if (c >= 0 && c < kHmax) {
+        hit = ev.leaf_exists(block, nx, ny, nz, pl);
+      } else {
+        hit = ev.across_face(f, block, nx, ny, nz, pl);
+      }
+      if (hit) bits |= 1 << k;
+    }
+    for (int k = 0; k < 3; k++) {
+      const int e = child_edge(id, k);
+      int dx, dy, dz;
+      edge_dir(e, &dx, &dy, &dz);
+      const i32 nx = px + dx * hp, ny = py + dy * hp, nz = pz + dz * hp;
+      const int ox = (nx < 0 || nx >= kHmax);
+      const int oy = (ny < 0 || ny >= kHmax);
+      const int oz = (nz < 0 || nz >= kHmax);
+      bool hit;
+      if (ox + oy + oz >= 2) {
+        hit = ev.across_edge(e, block, nx, ny, nz, pl);
+      } else if (ox + oy + oz == 1) {
+        const int f = ox * (nx < 0 ? 0 : 1) + oy * (ny < 0 ? 2 : 3) +
+                      oz * (nz < 0 ? 4 : 5);
+        hit = ev.across_face(f, block, nx, ny, nz, pl);
+      } else {
+        hit = ev.leaf_exists(block, nx, ny, nz, pl);
+      }
+      if (hit) bits |= 1 << (k + 3);
+    }
+    info[i] = (int16_t)bits;
+  }
+};
+
+/* decode the 6-bit info into face / edge masks
+   (reference decode_index_from_info src/TMROctForest.cpp:247-276) */
+TMR_HD void decode_info(int id, int info, int *face_mask, int *edge_mask) {
+  int fm = 0, em = 0;
+  for (int k = 0; k < 3; k++) {
+    if (info & (1 << k)) {
+      fm |= 1 << child_face(id, k);
+      em |= 1 << child_face_edge(id, k, 0);
+      em |= 1 << child_face_edge(id, k, 1);
+    }
+    if (info & (1 << (k + 3))) em |= 1 << child_edge(id, k);
+  }
+  *face_mask = fm;
+  *edge_mask = em;
+}
+
+/* element-local node offset of position p along block edge e */
+TMR_HD int edge_node_offset(int order, int e, int p) {
+  const int s = e & 3, hi = order - 1;
+  const int a = hi * (s & 1), b = hi * (s >> 1);
+  if (e < 4) return p + a * order + b * order * order;
+  if (e < 8) return a + p * order + b * order * order;
+  return a + b * order + p * order * order;
+}
+
+/* element-local node offset of in-face position (p,q) on block face f */
+TMR_HD int face_node_offset(int order, int f, int p, int q) {
+  const int n = (order - 1) * (f & 1);
+  if (f < 2) return n + p * order + q * order * order;
+  if (f < 4) return p + n * order + q * order * order;
+  return p + q * order + n * order * order;
+}
+
+/* canonical node key of element node (ii,jj,kk) -- createLocalNodes +
+   transformNode (reference :4290-4372, :3847-4039) */
+struct NodeCandFn {
+  const u64 *keys;
+  KeyFmt fmt;
+  NodeFmt nfmt;
+  ConnTables t;
+  int order;
+  u64 *out_keys;
+  u32 *out_vals;
+  TMR_HD void operator()(i64 c) const {
+    const int npe = order * order * order;
+    const i64 e = c / npe;
+    const int s = (int)(c % npe);
+    const int ii = s % order, jj = (s / order) % order, kk = s / (order * order);
+    i32 block, x, y, z;
+    int level;
+    fmt.decode(keys[e], &block, &x, &y, &z, &level);
+    const i32 step = (1 << (kMaxLevel - level)) / (order - 1);
+    x += ii * step;
+    y += jj * step;
+    z += kk * step;
+    transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
+    out_keys[c] = nfmt.encode(block, x, y, z);
+    out_vals[c] = (u32)c;
+  }
+};
+
+struct RunHeadFn {
+  const u64 *keys;
+  TMR_HD u32 operator()(i64 i) const {
+    return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  }
+};
+
+/* sorted candidates -> unique node keys + local connectivity */
+struct NodeScatterFn {
+  const u64 *keys;
+  const u32 *vals;
+  const u32 *heads_before; /* exclusive scan of run heads */
+  u64 *node_keys;
+  int *conn_local;
+  TMR_HD void operator()(i64 i) const {
+    const bool head = (i == 0 || keys[i] != keys[i - 1]);
+    const u32 run = heads_before[i] + (head ? 1u : 0u) - 1u;
+    if (head) node_keys[run] = keys[i];
+    conn_local[vals[i]] = (int)run;
+  }
+};
+
+/* labelDependentNodes (reference :3711-3832) */
+struct DepLabelFn {
+  const u64 *keys;
+  const int16_t *info;
+  KeyFmt fmt;
+  int order;
+  int bernstein;
+  const int *conn_local;
+  unsigned char *dep_flag;
+  TMR_HD void operator()(i64 e) const {
+    const int inf = info[e];
+    if (!inf) return;
+    i32 block, x, y, z;
+    int level;
+    fmt.decode(keys[e], &block, &x, &y, &z, &level);
+    const int id = child_id_of(x, y, z, level);
+    int fm, em;
+    decode_info(id, inf, &fm, &em);
+    for (int f = 0; f < 6; f++) {
+      if (fm & (1 << f)) {
+        for (int k = 0; k < 4; k++) em |= 1 << face_edge(f, k);
+      }
+    }
+    const int npe = order * order * order;
+    const int *c = conn_local + e * npe;
+    for (int ed = 0; ed < 12; ed++) {
+      if (!(em & (1 << ed))) continue;
+      const int bit = (id >> (ed >> 2)) & 1;
+      int start, end;
+      if (bit == 0) {
+        start = 1;
+        end = order;
+        if (order == 3 && !bernstein) end = order - 1;
+      } else {
+        start = 0;
+        end = order - 1;
+        if (order == 3 && !bernstein) start = 1;
+      }
+      for (int p = start; p < end; p++) {
+        dep_flag[c[edge_node_offset(order, ed, p)]] = 1;
+      }
+    }
+    for (int f = 0; f < 6; f++) {
+      if (!(fm & (1 << f))) continue;
+      for (int q = 1; q < order - 1; q++) {
+        for (int p = 1; p < order - 1; p++) {
+          dep_flag[c[face_node_offset(order, f, p, q)]] = 1;
+        }
+      }
+    }
+  }
+};
+
+struct DepFlagFn {
+  const unsigned char *dep_flag;
+  TMR_HD u32 operator()(i64 i) const { return dep_flag[i] ? 1u : 0u; }
+};
+
+/* node numbers in node order: dependents -1,-2,..; independents
+   first_owned, first_owned+1, ..  (reference :4113-4181, single rank) */
+struct NumberNodesFn {
+  const unsigned char *dep_flag;
+  const u32 *dep_before;
+  int first_owned;
+  int *node_num;
+  int *dep_node; /* dependent index -> node index */
+  TMR_HD void operator()(i64 i) const {
+    const u32 d = dep_before[i];
+    if (dep_flag[i]) {
+      node_num[i] = -(int)d - 1;
+      dep_node[d] = (int)i;
+    } else {
+      node_num[i] = first_owned + (int)(i - (i64)d);
+    }
+  }
+};
+
+/* createDependentConn passes 1+2 (reference :5183-5270): who writes the
+   stencil of each dependent node, and with which length.  Codes are
+   "1 + position in the reference's loop order" so that 0 means never. */
+struct DepWinnerFn {
+  const u64 *keys;
+  const int16_t *info;
+  KeyFmt fmt;
+  int order;
+  const int *conn_local;
+  const unsigned char *dep_flag;
+  const u32 *dep_before;
+  u64 *win_edge;
+  u64 *win_face;
+  TMR_HD void operator()(i64 e) const {
+    const int inf = info[e];
+    if (!inf) return;
+    i32 block, x, y, z;
+    int level;
+    fmt.decode(keys[e], &block, &x, &y, &z, &level);
+    const int id = child_id_of(x, y, z, level);
+    int fm, em;
+    decode_info(id, inf, &fm, &em);
+    const int npe = order * order * order;
+    const int *c = conn_local + e * npe;
+    for (int ed = 0; ed < 12; ed++) {
+      if (!(em & (1 << ed))) continue;
+      for (int k = 0; k < order; k++) {
+        const int node = c[edge_node_offset(order, ed, k)];
+        if (dep_flag[node]) {
+          const u64 code = (((u64)e * 12 + ed) << 4) + (u64)k + 1;
+          TMR_ATOMIC_MAX_U64(&win_edge[dep_before[node]], code);
+        }
+      }
+    }
+    for (int f = 0; f < 6; f++) {
+      if (!(fm & (1 << f))) continue;
+      for (int q = 0; q < order; q++) {
+        for (int p = 0; p < order; p++) {
+          const int node = c[face_node_offset(order, f, p, q)];
+          if (dep_flag[node]) {
+            const u64 code = (((u64)e * 6 + f) << 8) + (u64)(p + q * order) + 1;
+            TMR_ATOMIC_MAX_U64(&win_face[dep_before[node]], code);
+          }
+        }
+      }
+    }
+  }
+};
+
+struct DepLenFn {
+  const u64 *win_edge;
+  const u64 *win_face;
+  int order;
+  TMR_HD u32 operator()(i64 d) const {
+    if (win_edge[d]) return (u32)order;
+    if (win_face[d]) return (u32)(order * order);
+    return 0;
+  }
+};
+
+struct DepPtrFn {
+  const u32 *off;
+  i64 nd;
+  u32 total;
+  int *dep_ptr;
+  TMR_HD void operator()(i64 d) const {
+    dep_ptr[d] = (d < nd) ? (int)off[d] : (int)total;
+  }
+};
+
+/* createDependentConn pass 3 (reference :5272-5508) */
+struct DepFillFn {
+  const u64 *keys;
+  KeyFmt fmt;
+  NodeFmt nfmt;
+  ConnTables t;
+  int order;
+  double knots[4];
+  const u64 *node_keys;
+  i64 num_nodes;
+  const int *node_num;
+  const u64 *win_edge;
+  const u64 *win_face;
+  const int *dep_ptr;
+  int *dep_conn;
+  double *dep_weights;
+
+  TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z) const {
+    transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
+    const i64 idx = find_u64(node_keys, num_nodes, nfmt.encode(block, x, y, z));
+    return idx >= 0 ? node_num[idx] : 0;
+  }
+
+  TMR_HD void operator()(i64 d) const {
+    const int ptr = dep_ptr[d];
+    if (win_edge[d]) {
+      const u64 code = win_edge[d] - 1;
+      const int k = (int)(code & 15);
+      const u64 ee = code >> 4;
+      const int ed = (int)(ee % 12);
+      const i64 e = (i64)(ee / 12);
+      i32 block, x, y, z;
+      int level;
+      fmt.decode(keys[e], &block, &x, &y, &z, &level);
+      const int id = child_id_of(x, y, z, level);
+      const i32 h = 1 << (kMaxLevel - level);
+      const i32 hp = 2 * h;
+      const i32 px = x & ~h, py = y & ~h, pz = z & ~h;
+      const i32 step = hp / (order - 1);
+      const int s = ed & 3;
+      const i32 ta = hp * (s & 1), tb = hp * (s >> 1);
+      for (int ii = 0; ii < order; ii++) {
+        i32 nx, ny, nz;
+        if (ed < 4) {
+          nx = px + ii * step; ny = py + ta; nz = pz + tb;
+        } else if (ed < 8) {
+          nx = px + ta; ny = py + ii * step; nz = pz + tb;
+        } else {
+          nx = px + ta; ny = py + tb; nz = pz + ii * step;
+        }
+        dep_conn[ptr + ii] = lookup(block, nx, ny, nz);
+      }
+      const int bit = (id >> (ed >> 2)) & 1;
+      const double u = 1.0 * (bit - 1) + 0.5 * (1.0 + knots[k]);
+      lagrange_basis(order, u, knots, dep_weights + ptr);
+    } else if (win_face[d]) {
+      const u64 code = win_face[d] - 1;
+      const int pos = (int)(code & 255);
+      const u64 ff = code >> 8;
+      const int f = (int)(ff % 6);
+      const i64 e = (i64)(ff / 6);
+      const int ii = pos % order, jj = pos / order;
+      i32 block, x, y, z;
+      int level;
+      fmt.decode(keys[e], &block, &x, &y, &z, &level);
+      const int id = child_id_of(x, y, z, level);
+      const i32 h = 1 << (kMaxLevel - level);
+      const i32 hp = 2 * h;
+      const i32 px = x & ~h, py = y & ~h, pz = z & ~h;
+      const i32 step = hp / (order - 1);
+      const i32 nn = hp * (f & 1);
+      for (int q = 0; q < order; q++) {
+        for (int p = 0; p < order; p++) {
+          i32 nx, ny, nz;
+          if (f < 2) {
+            nx = px + nn; ny = py + p * step; nz = pz + q * step;
+          } else if (f < 4) {
+            nx = px + p * step; ny = py + nn; nz = pz + q * step;
+          } else {
+            nx = px + p * step; ny = py + q * step; nz = pz + nn;
+          }
+          dep_conn[ptr + p + q * order] = lookup(block, nx, ny, nz);
+        }
+      }
+      /* child bits along the face's first / second in-face axis */
+      const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
+      const int b1 = (f < 2) ? by : bx;
+      const int b2 = (f < 4) ? bz : by;
+      double u = -1.0 + 0.5 * (1.0 + knots[ii]);
+      double v = -1.0 + 0.5 * (1.0 + knots[jj]);
+      u += 1.0 * b1;
+      v += 1.0 * b2;
+      double Nu[kMaxOrder], Nv[kMaxOrder];
+      lagrange_basis(order, u, knots, Nu);
+      lagrange_basis(order, v, knots, Nv);
+      for (int j = 0; j < order * order; j++) {
+        dep_weights[ptr + j] = Nu[j % order] * Nv[j / order];
+      }
+    }
+  }
+};
+
+struct ConnRemapFn {
+  const int *conn_local;
+  const int *node_num;
+  int *conn;
+  TMR_HD void operator()(i64 j) const { conn[j] = node_num[conn_local[j]]; }
+};
+
+struct ConnRemapInPlaceFn {
+  const int *node_num;
+  int *conn;
+  TMR_HD void operator()(i64 j) const { conn[j] = node_num[conn[j]]; }
+};
+
+inline int create_nodes(Forest &f, int order, int interp_type,
+                        const double *knots) {
+  Ctx &ctx = *f.ctx;
+  NodeData &nd = f.nodes;
+  if (nd.valid) return 0; /* reference :4071-4075 */
+  if (order < 2 || order > kMaxOrder || (interp_type == 2)) {
+    fprintf(stderr,
+            "TMROctForest Error: the CUDA createNodes() supports mesh order 2 "
+            "and 3 with Lagrange interpolation (order %d, type %d requested)\n",
+            order, interp_type);
+    return 1;
+  }
+  const int npe = order * order * order;
+  const i64 E = f.n;
+  if (E * npe >= (1LL << 31)) {
+    fprintf(stderr,
+            "TMROctForest Error: %lld elements of order %d overflow the int32 "
+            "connectivity of the TMROctForest API\n",
+            (long long)E, order);
+    return 1;
+  }
+  nd.clear();
+  nd.order = order;
+  nd.interp_type = interp_type;
+  for (int i = 0; i < 4; i++) nd.knots[i] = (i < order) ? knots[i] : 0.0;
+  nd.num_elements = E;
+  nd.nfmt.Dn = f.fmt.D + (order > 2 ? 1 : 0);
+  nd.nfmt.bbits = f.bbits;
+  if (nd.nfmt.total_bits() > 64 || nd.nfmt.Dn + 1 > 21) {
+    fprintf(stderr,
+            "TMROctForest Error: node keys of %d trees at depth %d exceed the "
+            "64-bit key budget of the CUDA path\n",
+            f.nblocks, nd.nfmt.Dn);
+    return 1;
+  }
+  if (E == 0) {
+    nd.valid = true;
+    nd.dep_ptr.alloc(ctx, 1);
+    dev_zero(ctx, nd.dep_ptr.get(), sizeof(int));
+    return 0;
+  }
+
+  /* 1. hanging faces / edges */
+  if (!f.info.get()) f.info.alloc(ctx, E);
+  ElemView ev = {f.keys.get(), E, f.fmt, f.tables};
+  HangingFn hang = {ev, f.info.get()};
+  launch(ctx, E, hang, "nodes_hanging_info");
+
+  /* 2. node candidates -> sort -> unique nodes + local connectivity */
+  const i64 nc = E * npe;
+  nd.conn.alloc(ctx, nc);
+  i64 Nn;
+  {
+    DBuf<u64> ck(ctx, nc), ck_alt(ctx, nc);
+    DBuf<u32> cv(ctx, nc), cv_alt(ctx, nc);
+    NodeCandFn cand = {f.keys.get(), f.fmt, nd.nfmt, f.tables,
+                       order,        ck.get(), cv.get()};
+    launch(ctx, nc, cand, "nodes_candidates");
+    radix_sort(ctx, ck, ck_alt, cv, cv_alt, nc, 0, nd.nfmt.total_bits());
+    DBuf<u32> heads(ctx, nc);
+    RunHeadFn rh = {ck.get()};
+    Nn = (i64)scan_counts(ctx, nc, rh, heads.get(), "nodes_run_heads");
+    nd.node_keys.alloc(ctx, Nn);
+    NodeScatterFn sc = {ck.get(), cv.get(), heads.get(), nd.node_keys.get(),
+                        nd.conn.get()};
+    launch(ctx, nc, sc, "nodes_scatter_conn");
+  }
+  nd.num_local_nodes = Nn;
+
+  /* 3. dependent labels and numbering */
+  DBuf<unsigned char> dep_flag(ctx, Nn);
+  dev_zero(ctx, dep_flag.get(), (size_t)Nn);
+  DepLabelFn lab = {f.keys.get(), f.info.get(), f.fmt,         order,
+                    0,            nd.conn.get(), dep_flag.get()};
+  launch(ctx, E, lab, "nodes_dep_label");
+  DBuf<u32> dep_before(ctx, Nn);
+  DepFlagFn df = {dep_flag.get()};
+  const i64 Nd = (i64)scan_counts(ctx, Nn, df, dep_before.get(), "nodes_dep_scan");
+  nd.num_dep_nodes = Nd;
+  nd.num_owned_nodes = Nn - Nd;
+  nd.node_range_start = 0;
+  nd.node_num.alloc(ctx, Nn);
+  DBuf<int> dep_node(ctx, Nd);
+  NumberNodesFn num = {dep_flag.get(), dep_before.get(), nd.node_range_start,
+                       nd.node_num.get(), dep_node.get()};
+  launch(ctx, Nn, num, "nodes_number");
+
+  /* 4. dependent-node CSR */
+  nd.dep_ptr.alloc(ctx, Nd + 1);
+  if (Nd > 0) {
+    DBuf<u64> win_edge(ctx, Nd), win_face(ctx, Nd);
+    dev_zero(ctx, win_edge.get(), (size_t)Nd * sizeof(u64));
+    dev_zero(ctx, win_face.get(), (size_t)Nd * sizeof(u64));
+    DepWinnerFn win = {f.keys.get(),   f.info.get(),     f.fmt,
+                       order,          nd.conn.get(),    dep_flag.get(),
+                       dep_before.get(), win_edge.get(), win_face.get()};
+    launch(ctx, E, win, "nodes_dep_winner");
+    DBuf<u32> off(ctx, Nd);
+    DepLenFn len = {win_edge.get(), win_face.get(), order};
+    const u64 nnz = scan_counts(ctx, Nd, len, off.get(), "nodes_dep_len_scan");
+    DepPtrFn dp = {off.get(), Nd, (u32)nnz, nd.dep_ptr.get()};
+    launch(ctx, Nd + 1, dp, "nodes_dep_ptr");
+    nd.dep_nnz = (i64)nnz;
+    nd.dep_conn.alloc(ctx, (i64)nnz);
+    nd.dep_weights.alloc(ctx, (i64)nnz);
+    DepFillFn fill;
+    fill.keys = f.keys.get();
+    fill.fmt = f.fmt;
+    fill.nfmt = nd.nfmt;
+    fill.t = f.tables;
+    fill.order = order;
+    for (int i = 0; i < 4; i++) fill.knots[i] = nd.knots[i];
+    fill.node_keys = nd.node_keys.get();
+    fill.num_nodes = Nn;
+    fill.node_num = nd.node_num.get();
+    fill.win_edge = win_edge.get();
+    fill.win_face = win_face.get();
+    fill.dep_ptr = nd.dep_ptr.get();
+    fill.dep_conn = nd.dep_conn.get();
+    fill.dep_weights = nd.dep_weights.get();
+    launch(ctx, Nd, fill, "nodes_dep_fill");
+  } else {
+    dev_zero(ctx, nd.dep_ptr.get(), sizeof(int));
+    nd.dep_nnz = 0;
+  }
+
+  /* 5. local -> global numbers in the connectivity */
+  ConnRemapInPlaceFn rm = {nd.node_num.get(), nd.conn.get()};
+  launch(ctx, nc, rm, "nodes_conn_remap");
+  nd.valid = true;
+  return check_errors(ctx, "create_nodes");
+}
+
+}  // namespace tmrgpu
+
+#endif

@@ -1,0 +1,132 @@
+/*
+  prim.h -- device-runtime plumbing shared by the forest operations: context,
+  owning device buffers, copies, per-kernel timing.  The parallel primitives
+  themselves (launch / scan_counts / radix sort) are declared in
+  prim_cuda.cuh; the forest operations in forest_ops.h are written against
+  exactly this small surface.
+
+  A test-only host emulation of the same surface lives in tests/emu/ (it lets
+  the kernel BODIES -- plain TMR_HD functors -- be exercised against the
+  oracle on a machine without a GPU).  The product library never contains it.
+*/
+#ifndef TMRGPU_PRIM_H
+#define TMRGPU_PRIM_H
+
+#include <stddef.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace tmrgpu {
+
+struct KernelStat {
+  long launches;
+  double ms;
+  KernelStat() : launches(0), ms(0.0) {}
+};
+
+struct Ctx {
+  int device;
+  void *stream; /* cudaStream_t */
+  int profile;  /* time every named launch with events */
+  int num_sms;
+  long launch_count; /* kernels launched since the last reset */
+  std::map<std::string, KernelStat> stats;
+  /* pending (start, stop) event pairs, resolved lazily at the next sync */
+  std::vector<void *> ev_start, ev_stop;
+  std::vector<std::string> ev_name;
+  std::string last_error;
+  Ctx() : device(0), stream(NULL), profile(0), num_sms(148), launch_count(0) {}
+};
+
+/* --- runtime (prim_cuda.cu / tests/emu/prim_emu.cpp) ---------------------- */
+void *dev_alloc(Ctx &ctx, size_t bytes);
+void dev_free(Ctx &ctx, void *p);
+void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes);
+void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes); /* syncs */
+void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes);
+void dev_zero(Ctx &ctx, void *p, size_t bytes);
+void dev_fill_ff(Ctx &ctx, void *p, size_t bytes);
+void stream_sync(Ctx &ctx);
+/* returns 0 when no CUDA error is pending; otherwise records it in
+   ctx.last_error, prints "TMROctForest Error: ..." and returns nonzero */
+int check_errors(Ctx &ctx, const char *where);
+void prof_begin(Ctx &ctx, const char *name);
+void prof_end(Ctx &ctx);
+void prof_resolve(Ctx &ctx);
+
+/* Owning, move-only device array */
+template <class T>
+class DBuf {
+ public:
+  DBuf() : ctx_(NULL), p_(NULL), n_(0) {}
+  DBuf(Ctx &ctx, i64 n) : ctx_(&ctx), p_(NULL), n_(n) {
+    if (n > 0) p_ = static_cast<T *>(dev_alloc(ctx, (size_t)n * sizeof(T)));
+  }
+  ~DBuf() { reset(); }
+  DBuf(DBuf &&o) : ctx_(o.ctx_), p_(o.p_), n_(o.n_) {
+    o.p_ = NULL;
+    o.n_ = 0;
+  }
+  DBuf &operator=(DBuf &&o) {
+    if (this != &o) {
+      reset();
+      ctx_ = o.ctx_;
+      p_ = o.p_;
+      n_ = o.n_;
+      o.p_ = NULL;
+      o.n_ = 0;
+    }
+    return *this;
+  }
+  void reset() {
+    if (p_) dev_free(*ctx_, p_);
+    p_ = NULL;
+    n_ = 0;
+  }
+  void alloc(Ctx &ctx, i64 n) {
+    reset();
+    ctx_ = &ctx;
+    n_ = n;
+    if (n > 0) p_ = static_cast<T *>(dev_alloc(ctx, (size_t)n * sizeof(T)));
+  }
+  T *get() const { return p_; }
+  i64 size() const { return n_; }
+  /* shrink the logical size without reallocating */
+  void set_size(i64 n) { n_ = n; }
+  void swap(DBuf &o) {
+    Ctx *c = ctx_;
+    T *p = p_;
+    i64 n = n_;
+    ctx_ = o.ctx_;
+    p_ = o.p_;
+    n_ = o.n_;
+    o.ctx_ = c;
+    o.p_ = p;
+    o.n_ = n;
+  }
+
+ private:
+  DBuf(const DBuf &);
+  DBuf &operator=(const DBuf &);
+  Ctx *ctx_;
+  T *p_;
+  i64 n_;
+};
+
+/* --- radix sort (prim_cuda.cu) -------------------------------------------
+   Stable LSD radix sort of 64-bit keys on bits [bit_lo, bit_hi), 8 bits per
+   pass, ping-ponging between the two buffers.  On return `keys` (and `vals`)
+   hold the sorted data; `keys_alt`/`vals_alt` are scratch of the same size.
+   vals may be empty (keys only). */
+void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
+                DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int bit_lo,
+                int bit_hi);
+
+}  // namespace tmrgpu
+
+#endif

@@ -1,0 +1,402 @@
+/*
+  prim_cuda.cu -- CUDA runtime plumbing and the hand-written radix sort.
+
+  Radix sort = "onesweep": one up-front kernel histograms every pass's digit in
+  a single read of the keys; then each 8-bit pass is ONE kernel that reads each
+  key once and writes it once.  Inside a pass a CTA
+    (1) takes a tile ticket (so look-back only ever waits on running CTAs),
+    (2) ranks its 4096 keys with warp match/ballot multi-split (stable),
+    (3) publishes its 256 digit counts and resolves its global digit offsets
+        by decoupled look-back over the preceding tiles' descriptors,
+    (4) stages the tile in shared memory in digit order and writes each digit
+        run to HBM as contiguous, coalesced segments.
+  HBM traffic per pass: 8 B read + 8 B written per key (+4+4 with a payload),
+  plus 2 KB of descriptors per 4096-key tile.  This replaces
+  qsort+comparator in reference src/TMROctant.cpp:357-399.
+*/
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "prim_cuda.cuh"
+
+namespace tmrgpu {
+
+/* ------------------------------------------------------------------------ */
+/* runtime                                                                  */
+/* ------------------------------------------------------------------------ */
+#define TMR_CUDA_OK(call)                                                     \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      fprintf(stderr, "TMROctForest Error: CUDA %s at %s:%d\n",               \
+              cudaGetErrorString(e_), __FILE__, __LINE__);                    \
+    }                                                                         \
+  } while (0)
+
+void *dev_alloc(Ctx &ctx, size_t bytes) {
+  void *p = NULL;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(&p, bytes, (cudaStream_t)ctx.stream);
+  if (e != cudaSuccess) {
+    fprintf(stderr,
+            "TMROctForest Error: device allocation of %zu bytes failed (%s)\n",
+            bytes, cudaGetErrorString(e));
+    ctx.last_error = "device allocation failed";
+    return NULL;
+  }
+  return p;
+}
+
+void dev_free(Ctx &ctx, void *p) {
+  if (p) TMR_CUDA_OK(cudaFreeAsync(p, (cudaStream_t)ctx.stream));
+}
+
+void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return;
+  TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice,
+                              (cudaStream_t)ctx.stream));
+  /* the source may be pageable/stack memory: make the copy complete before
+     the caller can reuse it */
+  TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+}
+
+void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return;
+  TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost,
+                              (cudaStream_t)ctx.stream));
+  TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+}
+
+void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return;
+  TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)ctx.stream));
+}
+
+void dev_zero(Ctx &ctx, void *p, size_t bytes) {
+  if (bytes == 0) return;
+  TMR_CUDA_OK(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)ctx.stream));
+}
+
+void dev_fill_ff(Ctx &ctx, void *p, size_t bytes) {
+  if (bytes == 0) return;
+  TMR_CUDA_OK(cudaMemsetAsync(p, 0xff, bytes, (cudaStream_t)ctx.stream));
+}
+
+void stream_sync(Ctx &ctx) {
+  TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+}
+
+int check_errors(Ctx &ctx, const char *where) {
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)ctx.stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx.last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    fprintf(stderr, "TMROctForest Error: CUDA failure in %s: %s\n", where,
+            cudaGetErrorString(e));
+    return 1;
+  }
+  if (!ctx.last_error.empty()) return 1;
+  return 0;
+}
+
+void prof_begin(Ctx &ctx, const char *name) {
+  if (!ctx.profile) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, (cudaStream_t)ctx.stream);
+  ctx.ev_start.push_back(a);
+  ctx.ev_stop.push_back(b);
+  ctx.ev_name.push_back(name);
+}
+
+void prof_end(Ctx &ctx) {
+  if (!ctx.profile) return;
+  cudaEventRecord((cudaEvent_t)ctx.ev_stop.back(), (cudaStream_t)ctx.stream);
+}
+
+void prof_resolve(Ctx &ctx) {
+  if (ctx.ev_start.empty()) return;
+  cudaStreamSynchronize((cudaStream_t)ctx.stream);
+  for (size_t i = 0; i < ctx.ev_start.size(); i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, (cudaEvent_t)ctx.ev_start[i],
+                         (cudaEvent_t)ctx.ev_stop[i]);
+    KernelStat &s = ctx.stats[ctx.ev_name[i]];
+    s.launches++;
+    s.ms += ms;
+    cudaEventDestroy((cudaEvent_t)ctx.ev_start[i]);
+    cudaEventDestroy((cudaEvent_t)ctx.ev_stop[i]);
+  }
+  ctx.ev_start.clear();
+  ctx.ev_stop.clear();
+  ctx.ev_name.clear();
+}
+
+/* ------------------------------------------------------------------------ */
+/* radix sort                                                               */
+/* ------------------------------------------------------------------------ */
+static const int kRadixBits = 8;
+static const int kRadix = 1 << kRadixBits;
+static const int kSortThreads = 256;
+static const int kSortWarps = kSortThreads / 32;
+static const int kSortItems = 16;
+static const int kSortTile = kSortThreads * kSortItems; /* 4096 keys */
+static const int kMaxPasses = 8;
+
+/* One read of the keys -> digit histograms of every pass. */
+__global__ void __launch_bounds__(kSortThreads)
+    radix_hist_kernel(const u64 *__restrict__ keys, i64 n, int bit_lo,
+                      int bit_hi, int npass, u32 *__restrict__ ghist) {
+  __shared__ u32 s_hist[kMaxPasses * kRadix];
+  for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const i64 nround = ((n + 31) / 32) * 32; /* keep warps converged */
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nround;
+       i += stride) {
+    const bool valid = i < n;
+    const u64 k = valid ? keys[i] : 0;
+    for (int p = 0; p < npass; p++) {
+      const int shift = bit_lo + p * kRadixBits;
+      const int bits = min(kRadixBits, bit_hi - shift);
+      const u32 d = (u32)(k >> shift) & ((1u << bits) - 1u);
+      /* warp-aggregated increment: one shared atomic per distinct digit */
+      const u32 peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+      if (valid && lane == (__ffs(peers) - 1)) {
+        atomicAdd(&s_hist[p * kRadix + d], __popc(peers));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) {
+    const u32 v = s_hist[i];
+    if (v) atomicAdd(&ghist[i], v);
+  }
+}
+
+/* exclusive scan of each pass's 256 bins (one CTA per pass) */
+__global__ void radix_scan_hist_kernel(u32 *ghist) {
+  __shared__ u32 s[kRadix];
+  u32 *h = ghist + blockIdx.x * kRadix;
+  const u32 v = h[threadIdx.x];
+  s[threadIdx.x] = v;
+  __syncthreads();
+  /* Hillis-Steele over 256 entries */
+  for (int d = 1; d < kRadix; d <<= 1) {
+    u32 t = (threadIdx.x >= d) ? s[threadIdx.x - d] : 0;
+    __syncthreads();
+    s[threadIdx.x] += t;
+    __syncthreads();
+  }
+  h[threadIdx.x] = s[threadIdx.x] - v;
+}
+
+template <bool kHasVals>
+__global__ void __launch_bounds__(kSortThreads)
+    radix_pass_kernel(const u64 *__restrict__ kin, u64 *__restrict__ kout,
+                      const u32 *__restrict__ vin, u32 *__restrict__ vout,
+                      i64 n, int shift, int bits,
+                      const u32 *__restrict__ pass_offset, /* [256] */
+                      u32 *ticket, u64 *lookback /* [tiles][256] */) {
+  extern __shared__ unsigned char smem_raw[];
+  u64 *s_keys = reinterpret_cast<u64 *>(smem_raw);            /* tile keys */
+  u32 *s_vals = reinterpret_cast<u32 *>(s_keys + kSortTile);  /* tile vals */
+  u32 *s_whist = s_vals + (kHasVals ? kSortTile : 0);         /* [warps][256] */
+  u32 *s_dbase = s_whist + kSortWarps * kRadix;               /* [256] */
+  u64 *s_goff = reinterpret_cast<u64 *>(s_dbase + kRadix);    /* [256] */
+  __shared__ u32 s_tile;
+  __shared__ u32 s_wsum[kSortWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) s_whist[i] = 0;
+  __syncthreads();
+  const u32 tile = s_tile;
+  const i64 tile_base = (i64)tile * kSortTile;
+  const i64 rem = n - tile_base;
+  const int tile_n = rem < kSortTile ? (int)rem : kSortTile;
+  const u32 dmask = (1u << bits) - 1u;
+
+  /* (2) load warp-striped and rank */
+  u64 key[kSortItems];
+  u32 val[kSortItems];
+  unsigned short rank[kSortItems];
+  const i64 wbase = tile_base + (i64)warp * (32 * kSortItems);
+#pragma unroll
+  for (int j = 0; j < kSortItems; j++) {
+    const i64 i = wbase + j * 32 + lane;
+    key[j] = (i < n) ? kin[i] : ~0ULL;
+    if (kHasVals) val[j] = (i < n) ? vin[i] : 0u;
+  }
+  u32 *my_hist = s_whist + warp * kRadix;
+#pragma unroll
+  for (int j = 0; j < kSortItems; j++) {
+    const u32 d = (u32)(key[j] >> shift) & dmask;
+    const u32 peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    u32 old = 0;
+    if (lane == leader) {
+      old = my_hist[d];
+      my_hist[d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[j] = (unsigned short)(old + __popc(peers & ((1u << lane) - 1u)));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  /* (3) per digit (thread t owns digit t): warp bases, tile count */
+  u32 count = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++) {
+    const u32 c = s_whist[w * kRadix + tid];
+    s_whist[w * kRadix + tid] = count;
+    count += c;
+  }
+  u64 *my_desc = lookback + (size_t)tile * kRadix + tid;
+  if (tile == 0) {
+    st_relaxed_u64(my_desc, kStatusPrefix | (u64)count);
+  } else {
+    st_relaxed_u64(my_desc, kStatusAgg | (u64)count);
+  }
+  /* exclusive scan of the 256 tile counts -> position of each digit run in
+     the staged tile */
+  u32 incl = count;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  u32 woff = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++) {
+    if (w < warp) woff += s_wsum[w];
+  }
+  const u32 dbase = woff + incl - count;
+  s_dbase[tid] = dbase;
+  /* decoupled look-back for digit `tid` */
+  u64 excl = 0;
+  if (tile > 0) {
+    i64 p = (i64)tile - 1;
+    while (true) {
+      const u64 v = ld_relaxed_u64(lookback + (size_t)p * kRadix + tid);
+      const u64 st = v & kStatusMask;
+      if (st == 0) continue;
+      excl += v & ~kStatusMask;
+      if (st == kStatusPrefix) break;
+      p--;
+    }
+    st_relaxed_u64(my_desc, kStatusPrefix | (excl + (u64)count));
+  }
+  /* global index of staged position q holding digit d: goff[d] + q */
+  s_goff[tid] = (u64)pass_offset[tid] + excl - (u64)dbase;
+  __syncthreads();
+
+  /* (4) stage in digit order, then write out coalesced */
+#pragma unroll
+  for (int j = 0; j < kSortItems; j++) {
+    const u32 d = (u32)(key[j] >> shift) & dmask;
+    const u32 q = s_dbase[d] + my_hist[d] + rank[j];
+    s_keys[q] = key[j];
+    if (kHasVals) s_vals[q] = val[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kSortItems; j++) {
+    const int q = j * kSortThreads + tid;
+    if (q < tile_n) {
+      const u64 k = s_keys[q];
+      const u32 d = (u32)(k >> shift) & dmask;
+      const u64 g = s_goff[d] + (u64)q;
+      kout[g] = k;
+      if (kHasVals) vout[g] = s_vals[q];
+    }
+  }
+}
+
+static size_t sort_smem_bytes(bool has_vals) {
+  size_t b = (size_t)kSortTile * sizeof(u64);
+  if (has_vals) b += (size_t)kSortTile * sizeof(u32);
+  b += (size_t)kSortWarps * kRadix * sizeof(u32);
+  b += (size_t)kRadix * sizeof(u32);
+  b += (size_t)kRadix * sizeof(u64);
+  return b;
+}
+
+void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
+                DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int bit_lo,
+                int bit_hi) {
+  if (n <= 1 || bit_hi <= bit_lo) return;
+  const bool has_vals = vals.get() != NULL;
+  int npass = (bit_hi - bit_lo + kRadixBits - 1) / kRadixBits;
+  cudaStream_t st = (cudaStream_t)ctx.stream;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(radix_pass_kernel<true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sort_smem_bytes(true));
+    cudaFuncSetAttribute(radix_pass_kernel<false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sort_smem_bytes(false));
+    attr_set = true;
+  }
+
+  const i64 tiles = (n + kSortTile - 1) / kSortTile;
+  /* scratch: [npass*256 u32 hist][npass u32 tickets (padded)][tiles*256 u64] */
+  const size_t hist_bytes = (size_t)kMaxPasses * kRadix * sizeof(u32);
+  const size_t ticket_bytes = 64;
+  const size_t look_bytes = (size_t)tiles * kRadix * sizeof(u64);
+  unsigned char *scratch = static_cast<unsigned char *>(
+      dev_alloc(ctx, hist_bytes + ticket_bytes + look_bytes));
+  if (!scratch) return;
+  u32 *ghist = reinterpret_cast<u32 *>(scratch);
+  u32 *tickets = reinterpret_cast<u32 *>(scratch + hist_bytes);
+  u64 *lookback = reinterpret_cast<u64 *>(scratch + hist_bytes + ticket_bytes);
+
+  int done = 0;
+  while (done < npass) {
+    /* histogram at most kMaxPasses passes per sweep of the keys */
+    const int chunk = (npass - done < kMaxPasses) ? (npass - done) : kMaxPasses;
+    const int lo = bit_lo + done * kRadixBits;
+    dev_zero(ctx, scratch, hist_bytes + ticket_bytes);
+    prof_begin(ctx, "radix_hist");
+    radix_hist_kernel<<<grid_for(ctx, n, kSortThreads * 4, 8), kSortThreads, 0,
+                        st>>>(keys.get(), n, lo, bit_hi, chunk, ghist);
+    radix_scan_hist_kernel<<<chunk, kRadix, 0, st>>>(ghist);
+    prof_end(ctx);
+    ctx.launch_count += 2;
+    for (int p = 0; p < chunk; p++) {
+      const int shift = lo + p * kRadixBits;
+      const int bits = (bit_hi - shift < kRadixBits) ? (bit_hi - shift)
+                                                     : kRadixBits;
+      dev_zero(ctx, lookback, look_bytes);
+      prof_begin(ctx, has_vals ? "radix_pass_pairs" : "radix_pass_keys");
+      if (has_vals) {
+        radix_pass_kernel<true>
+            <<<(unsigned)tiles, kSortThreads, sort_smem_bytes(true), st>>>(
+                keys.get(), keys_alt.get(), vals.get(), vals_alt.get(), n,
+                shift, bits, ghist + p * kRadix, tickets + p, lookback);
+      } else {
+        radix_pass_kernel<false>
+            <<<(unsigned)tiles, kSortThreads, sort_smem_bytes(false), st>>>(
+                keys.get(), keys_alt.get(), NULL, NULL, n, shift, bits,
+                ghist + p * kRadix, tickets + p, lookback);
+      }
+      prof_end(ctx);
+      ctx.launch_count++;
+      keys.swap(keys_alt);
+      if (has_vals) vals.swap(vals_alt);
+    }
+    done += chunk;
+  }
+  dev_free(ctx, scratch);
+}
+
+}  // namespace tmrgpu

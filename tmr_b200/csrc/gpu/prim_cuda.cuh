@@ -1,0 +1,189 @@
+/*
+  prim_cuda.cuh -- sm_100a implementations of the two templated primitives
+  every forest operation is built from:
+
+    launch(ctx, n, f, name)          f(i) for i in [0,n): grid-stride, grid sized
+                                     as a multiple of the SM count
+    scan_counts(ctx, n, f, out, nm)  out[i] = sum_{j<i} f(j)   (exclusive),
+                                     returns the total; ONE pass over the input
+                                     (chained scan with decoupled look-back),
+                                     so compaction/expansion kernels read their
+                                     input once and write offsets once.
+
+  Both take a plain functor (a TMR_HD struct), so kernel bodies stay
+  host-testable.
+*/
+#ifndef TMRGPU_PRIM_CUDA_CUH
+#define TMRGPU_PRIM_CUDA_CUH
+
+#include <cuda_runtime.h>
+
+#include "prim.h"
+
+namespace tmrgpu {
+
+static const int kLaunchThreads = 256;
+
+template <class F>
+__global__ void __launch_bounds__(kLaunchThreads)
+    launch_kernel(F f, i64 n) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    f(i);
+  }
+}
+
+inline int grid_for(const Ctx &ctx, i64 n, int threads, int max_waves) {
+  i64 blocks = (n + threads - 1) / threads;
+  const i64 cap = (i64)ctx.num_sms * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <class F>
+void launch(Ctx &ctx, i64 n, F f, const char *name) {
+  if (n <= 0) return;
+  /* up to 8 resident CTAs of 256 threads per SM; 4 waves of grid-stride */
+  const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
+  prof_begin(ctx, name);
+  launch_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
+  prof_end(ctx);
+  ctx.launch_count++;
+}
+
+/* ---- chained scan --------------------------------------------------------
+   tile = 256 threads x 8 items (blocked, so each thread owns 8 consecutive
+   outputs and stores them as two 16-byte vectors).  Tile descriptors are one
+   64-bit word: [2-bit status | 62-bit value], written with a single store so
+   status and value can never be observed torn. */
+static const int kScanThreads = 256;
+static const int kScanItems = 8;
+static const int kScanTile = kScanThreads * kScanItems;
+static const u64 kStatusAgg = 1ULL << 62;
+static const u64 kStatusPrefix = 2ULL << 62;
+static const u64 kStatusMask = 3ULL << 62;
+
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v)
+               : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p)
+               : "memory");
+  return v;
+}
+
+template <class F>
+__global__ void __launch_bounds__(kScanThreads)
+    scan_counts_kernel(F f, i64 n, u32 *out, u64 *tile_state, u32 *ticket,
+                       u64 *total) {
+  __shared__ u32 s_tile;
+  __shared__ u64 s_warp_sum[kScanThreads / 32];
+  __shared__ u64 s_tile_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const i64 base = (i64)tile * kScanTile + (i64)threadIdx.x * kScanItems;
+
+  u32 c[kScanItems];
+  u32 mine = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    const i64 i = base + k;
+    c[k] = (i < n) ? f(i) : 0u;
+    mine += c[k];
+  }
+  /* block exclusive scan of per-thread sums */
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u64 incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u64 up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl;
+  __syncthreads();
+  u64 warp_off = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; w++) {
+    const u64 s = s_warp_sum[w];
+    if (w < warp) warp_off += s;
+    tile_sum += s;
+  }
+  /* publish the aggregate, then look back for the exclusive tile prefix */
+  if (threadIdx.x == 0) {
+    if (tile == 0) {
+      st_relaxed_u64(&tile_state[0], kStatusPrefix | tile_sum);
+      s_tile_prefix = 0;
+    } else {
+      st_relaxed_u64(&tile_state[tile], kStatusAgg | tile_sum);
+      u64 excl = 0;
+      i64 p = (i64)tile - 1;
+      while (true) {
+        u64 v = ld_relaxed_u64(&tile_state[p]);
+        const u64 st = v & kStatusMask;
+        if (st == 0) continue; /* predecessor not published yet */
+        excl += v & ~kStatusMask;
+        if (st == kStatusPrefix) break;
+        p--;
+      }
+      st_relaxed_u64(&tile_state[tile], kStatusPrefix | (excl + tile_sum));
+      s_tile_prefix = excl;
+    }
+    if ((i64)(tile + 1) * kScanTile >= n) {
+      *total = s_tile_prefix + tile_sum;
+    }
+  }
+  __syncthreads();
+  u64 run = s_tile_prefix + warp_off + (incl - mine);
+  if (base + kScanItems <= n && ((((size_t)out) & 15) == 0)) {
+    uint4 v0, v1;
+    v0.x = (u32)run; run += c[0];
+    v0.y = (u32)run; run += c[1];
+    v0.z = (u32)run; run += c[2];
+    v0.w = (u32)run; run += c[3];
+    v1.x = (u32)run; run += c[4];
+    v1.y = (u32)run; run += c[5];
+    v1.z = (u32)run; run += c[6];
+    v1.w = (u32)run;
+    uint4 *o = reinterpret_cast<uint4 *>(out + base);
+    o[0] = v0;
+    o[1] = v1;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      const i64 i = base + k;
+      if (i < n) out[i] = (u32)run;
+      run += c[k];
+    }
+  }
+}
+
+template <class F>
+u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *name) {
+  if (n <= 0) return 0;
+  const i64 tiles = (n + kScanTile - 1) / kScanTile;
+  /* scratch: tile descriptors + ticket + total, zeroed per call */
+  const size_t bytes = (size_t)(tiles + 2) * sizeof(u64);
+  u64 *scratch = static_cast<u64 *>(dev_alloc(ctx, bytes));
+  dev_zero(ctx, scratch, bytes);
+  u64 *tile_state = scratch;
+  u32 *ticket = reinterpret_cast<u32 *>(scratch + tiles);
+  u64 *total = scratch + tiles + 1;
+  prof_begin(ctx, name);
+  scan_counts_kernel<F><<<(unsigned)tiles, kScanThreads, 0,
+                          (cudaStream_t)ctx.stream>>>(f, n, out, tile_state,
+                                                      ticket, total);
+  prof_end(ctx);
+  ctx.launch_count++;
+  u64 h_total = 0;
+  copy_d2h(ctx, &h_total, total, sizeof(u64));
+  dev_free(ctx, scratch);
+  return h_total;
+}
+
+}  // namespace tmrgpu
+
+#endif

@@ -1,0 +1,334 @@
+/*
+  tmrgpu_api.inl -- implementation of include/tmrgpu.h on top of ops_*.h.
+  Included by tmrgpu_cuda.cu (the product, compiled by nvcc for sm_100a) and,
+  for pre-GPU logic checks only, by tests/emu/tmrgpu_emu.cpp.
+*/
+#include <string.h>
+
+#include <sstream>
+
+#include "ops_interp.h"
+#include "ops_nodes.h"
+#include "tmrgpu.h"
+
+using namespace tmrgpu;
+
+struct tmrgpu_ctx {
+  Ctx c;
+  bool own_stream;
+};
+
+struct tmrgpu_forest {
+  Forest f;
+  explicit tmrgpu_forest(Ctx *c) : f(c) {}
+};
+
+extern "C" {
+
+int tmrgpu_ctx_sync(tmrgpu_ctx *ctx) { return check_errors(ctx->c, "sync"); }
+void *tmrgpu_ctx_stream(tmrgpu_ctx *ctx) { return ctx->c.stream; }
+
+int tmrgpu_profile_enable(tmrgpu_ctx *ctx, int on) {
+  prof_resolve(ctx->c);
+  ctx->c.profile = on;
+  return 0;
+}
+
+int tmrgpu_profile_reset(tmrgpu_ctx *ctx) {
+  prof_resolve(ctx->c);
+  ctx->c.stats.clear();
+  ctx->c.launch_count = 0;
+  return 0;
+}
+
+int tmrgpu_profile_json(tmrgpu_ctx *ctx, char *buf, int buflen) {
+  prof_resolve(ctx->c);
+  std::ostringstream os;
+  os << "{";
+  bool first = true;
+  for (std::map<std::string, KernelStat>::const_iterator it =
+           ctx->c.stats.begin();
+       it != ctx->c.stats.end(); ++it) {
+    if (!first) os << ", ";
+    first = false;
+    os << "\"" << it->first << "\": {\"launches\": " << it->second.launches
+       << ", \"ms\": " << it->second.ms << "}";
+  }
+  os << "}";
+  const std::string s = os.str();
+  if (buf && buflen > 0) {
+    const size_t nc = s.size() < (size_t)buflen - 1 ? s.size() : (size_t)buflen - 1;
+    memcpy(buf, s.data(), nc);
+    buf[nc] = 0;
+  }
+  return (int)s.size() + 1;
+}
+
+long tmrgpu_launch_count(tmrgpu_ctx *ctx) { return ctx->c.launch_count; }
+
+int tmrgpu_forest_create(tmrgpu_ctx *ctx, tmrgpu_forest **out) {
+  *out = new tmrgpu_forest(&ctx->c);
+  return 0;
+}
+
+int tmrgpu_forest_destroy(tmrgpu_forest *f) {
+  delete f;
+  return 0;
+}
+
+int tmrgpu_set_connectivity(
+    tmrgpu_forest *F, int nblocks, int nnodes, int nedges, int nfaces,
+    const int *block_conn, const int *block_edge_conn,
+    const int *block_face_conn, const int *block_face_ids,
+    const int *node_block_ptr, const int *node_block_conn,
+    const int *edge_block_ptr, const int *edge_block_conn,
+    const int *face_block_ptr, const int *face_block_conn,
+    const int *node_block_owners, const int *edge_block_owners,
+    const int *face_block_owners) {
+  Forest &f = F->f;
+  Ctx &ctx = *f.ctx;
+  const int nbc = node_block_ptr[nnodes], ebc = edge_block_ptr[nedges],
+            fbc = face_block_ptr[nfaces];
+  /* one packed allocation, one H2D copy */
+  std::vector<int> pack;
+  size_t off[13];
+  const int *src[13] = {block_conn,      block_edge_conn,  block_face_conn,
+                        block_face_ids,  node_block_ptr,   node_block_conn,
+                        edge_block_ptr,  edge_block_conn,  face_block_ptr,
+                        face_block_conn, node_block_owners, edge_block_owners,
+                        face_block_owners};
+  const size_t len[13] = {(size_t)8 * nblocks, (size_t)12 * nblocks,
+                          (size_t)6 * nblocks, (size_t)6 * nblocks,
+                          (size_t)nnodes + 1,  (size_t)nbc,
+                          (size_t)nedges + 1,  (size_t)ebc,
+                          (size_t)nfaces + 1,  (size_t)fbc,
+                          (size_t)nnodes,      (size_t)nedges,
+                          (size_t)nfaces};
+  for (int k = 0; k < 13; k++) {
+    off[k] = pack.size();
+    pack.insert(pack.end(), src[k], src[k] + len[k]);
+  }
+  f.table_store.reset(new DBuf<int>(ctx, (i64)pack.size()));
+  int *d = f.table_store->get();
+  copy_h2d(ctx, d, pack.data(), pack.size() * sizeof(int));
+  ConnTables &t = f.tables;
+  t.nblocks = nblocks;
+  t.nnodes = nnodes;
+  t.nedges = nedges;
+  t.nfaces = nfaces;
+  t.block_conn = d + off[0];
+  t.block_edge_conn = d + off[1];
+  t.block_face_conn = d + off[2];
+  t.block_face_ids = d + off[3];
+  t.node_block_ptr = d + off[4];
+  t.node_block_conn = d + off[5];
+  t.edge_block_ptr = d + off[6];
+  t.edge_block_conn = d + off[7];
+  t.face_block_ptr = d + off[8];
+  t.face_block_conn = d + off[9];
+  t.node_block_owners = d + off[10];
+  t.edge_block_owners = d + off[11];
+  t.face_block_owners = d + off[12];
+  f.nblocks = nblocks;
+  f.bbits = bits_for(nblocks);
+  f.fmt.bbits = f.bbits;
+  f.n = 0;
+  f.keys.reset();
+  f.info.reset();
+  f.nodes.clear();
+  return check_errors(ctx, "set_connectivity");
+}
+
+int tmrgpu_share_connectivity(tmrgpu_forest *src, tmrgpu_forest *dst) {
+  dst->f.table_store = src->f.table_store;
+  dst->f.tables = src->f.tables;
+  dst->f.nblocks = src->f.nblocks;
+  dst->f.bbits = src->f.bbits;
+  dst->f.fmt.bbits = src->f.bbits;
+  return 0;
+}
+
+int64_t tmrgpu_count(tmrgpu_forest *f) { return f->f.n; }
+
+int tmrgpu_upload_octants(tmrgpu_forest *f, const tmrgpu_octant *recs,
+                          int64_t n) {
+  return upload_octants(f->f, reinterpret_cast<const Oct24 *>(recs), n);
+}
+
+int tmrgpu_download_octants(tmrgpu_forest *f, tmrgpu_octant *recs) {
+  return download_octants(f->f, reinterpret_cast<Oct24 *>(recs));
+}
+
+int tmrgpu_download_info(tmrgpu_forest *F, int16_t *info) {
+  Forest &f = F->f;
+  if (f.n == 0) return 0;
+  if (!f.info.get()) {
+    memset(info, 0, (size_t)f.n * sizeof(int16_t));
+    return 0;
+  }
+  copy_d2h(*f.ctx, info, f.info.get(), (size_t)f.n * sizeof(int16_t));
+  return check_errors(*f.ctx, "download_info");
+}
+
+int tmrgpu_sort_unique(tmrgpu_forest *f) {
+  sort_unique_elements(f->f);
+  return check_errors(*f->f.ctx, "sort_unique");
+}
+
+int tmrgpu_create_trees(tmrgpu_forest *f, int level, int block_start,
+                        int block_end) {
+  return create_trees(f->f, level, block_start, block_end);
+}
+
+int tmrgpu_refine_device(tmrgpu_forest *f, const int *d_flags, int min_level,
+                         int max_level) {
+  return refine(f->f, d_flags, min_level, max_level);
+}
+
+int tmrgpu_refine(tmrgpu_forest *F, const int *h_flags, int min_level,
+                  int max_level) {
+  Forest &f = F->f;
+  if (!h_flags || f.n == 0) return refine(f, NULL, min_level, max_level);
+  DBuf<int> d_flags(*f.ctx, f.n);
+  copy_h2d(*f.ctx, d_flags.get(), h_flags, (size_t)f.n * sizeof(int));
+  return refine(f, d_flags.get(), min_level, max_level);
+}
+
+int tmrgpu_balance(tmrgpu_forest *f, int balance_corner) {
+  return balance(f->f, balance_corner);
+}
+
+int tmrgpu_coarsen(tmrgpu_forest *src, tmrgpu_forest *dst) {
+  tmrgpu_share_connectivity(src, dst);
+  return coarsen_into(src->f, dst->f);
+}
+
+int tmrgpu_duplicate(tmrgpu_forest *src, tmrgpu_forest *dst) {
+  tmrgpu_share_connectivity(src, dst);
+  return duplicate_into(src->f, dst->f);
+}
+
+int tmrgpu_create_nodes(tmrgpu_forest *f, int order, int interp_type,
+                        const double *knots) {
+  return create_nodes(f->f, order, interp_type, knots);
+}
+
+int tmrgpu_free_nodes(tmrgpu_forest *f) {
+  f->f.nodes.clear();
+  f->f.interp.clear();
+  return 0;
+}
+
+int tmrgpu_node_sizes(tmrgpu_forest *F, int64_t sizes[6]) {
+  const NodeData &nd = F->f.nodes;
+  sizes[0] = nd.num_elements;
+  sizes[1] = nd.num_local_nodes;
+  sizes[2] = nd.num_dep_nodes;
+  sizes[3] = nd.num_owned_nodes;
+  sizes[4] = nd.dep_nnz;
+  sizes[5] = nd.node_range_start;
+  return nd.valid ? 0 : 1;
+}
+
+int tmrgpu_download_nodes(tmrgpu_forest *F, int *conn, int *node_numbers,
+                          int *dep_ptr, int *dep_conn, double *dep_weights) {
+  Forest &f = F->f;
+  NodeData &nd = f.nodes;
+  Ctx &ctx = *f.ctx;
+  if (!nd.valid) return 1;
+  const i64 npe = (i64)nd.order * nd.order * nd.order;
+  if (conn) {
+    copy_d2h(ctx, conn, nd.conn.get(),
+             (size_t)(nd.num_elements * npe) * sizeof(int));
+  }
+  if (node_numbers) {
+    copy_d2h(ctx, node_numbers, nd.node_num.get(),
+             (size_t)nd.num_local_nodes * sizeof(int));
+  }
+  if (dep_ptr) {
+    copy_d2h(ctx, dep_ptr, nd.dep_ptr.get(),
+             (size_t)(nd.num_dep_nodes + 1) * sizeof(int));
+  }
+  if (dep_conn) {
+    copy_d2h(ctx, dep_conn, nd.dep_conn.get(), (size_t)nd.dep_nnz * sizeof(int));
+  }
+  if (dep_weights) {
+    copy_d2h(ctx, dep_weights, nd.dep_weights.get(),
+             (size_t)nd.dep_nnz * sizeof(double));
+  }
+  return check_errors(ctx, "download_nodes");
+}
+
+int tmrgpu_create_interp(tmrgpu_forest *fine, tmrgpu_forest *coarse,
+                         int64_t *nrows, int64_t *nnz) {
+  const int rc = create_interp(fine->f, coarse->f);
+  if (nrows) *nrows = fine->f.interp.nrows;
+  if (nnz) *nnz = fine->f.interp.nnz;
+  return rc;
+}
+
+int tmrgpu_download_interp(tmrgpu_forest *F, int *rows, int *rowp, int *cols,
+                           double *vals) {
+  Forest &f = F->f;
+  InterpData &I = f.interp;
+  Ctx &ctx = *f.ctx;
+  if (!I.valid) return 1;
+  if (rows) copy_d2h(ctx, rows, I.rows.get(), (size_t)I.nrows * sizeof(int));
+  if (rowp) copy_d2h(ctx, rowp, I.rowp.get(), (size_t)(I.nrows + 1) * sizeof(int));
+  if (cols) copy_d2h(ctx, cols, I.cols.get(), (size_t)I.nnz * sizeof(int));
+  if (vals) copy_d2h(ctx, vals, I.vals.get(), (size_t)I.nnz * sizeof(double));
+  return check_errors(ctx, "download_interp");
+}
+
+int tmrgpu_find_enclosing(tmrgpu_forest *F, int order, const double *knots,
+                          const tmrgpu_octant *nodes, int64_t n,
+                          int *out_index) {
+  return find_enclosing_batch(F->f, order, knots,
+                              reinterpret_cast<const Oct24 *>(nodes), n,
+                              out_index);
+}
+
+int tmrgpu_array_sort(tmrgpu_ctx *ctx, tmrgpu_octant *recs, int64_t n,
+                      int use_node_index, int64_t *nout) {
+  return array_sort(ctx->c, reinterpret_cast<Oct24 *>(recs), n, use_node_index,
+                    nout);
+}
+
+int tmrgpu_array_contains(tmrgpu_ctx *ctx, const tmrgpu_octant *sorted,
+                          int64_t n, const tmrgpu_octant *queries, int64_t nq,
+                          int mode, int *out_index) {
+  return array_contains(ctx->c, reinterpret_cast<const Oct24 *>(sorted), n,
+                        reinterpret_cast<const Oct24 *>(queries), nq, mode,
+                        out_index);
+}
+
+int tmrgpu_synth_flags(tmrgpu_forest *F, uint64_t seed, int pct, int *d_flags) {
+  Forest &f = F->f;
+  SynthFlagsFn s = {f.keys.get(), f.fmt, seed, pct, d_flags};
+  launch(*f.ctx, f.n, s, "synth_flags");
+  return 0;
+}
+
+int tmrgpu_checksum(tmrgpu_forest *F, uint64_t *out) {
+  *out = checksum(F->f);
+  return check_errors(*F->f.ctx, "checksum");
+}
+
+int tmrgpu_dev_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out) {
+  *out = dev_alloc(ctx->c, (size_t)bytes);
+  return *out ? 0 : 1;
+}
+
+int tmrgpu_dev_free(tmrgpu_ctx *ctx, void *p) {
+  dev_free(ctx->c, p);
+  return 0;
+}
+
+int tmrgpu_last_counts(tmrgpu_forest *F, int64_t counts[3]) {
+  counts[0] = F->f.last_in;
+  counts[1] = F->f.last_mid;
+  counts[2] = F->f.last_out;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1035 @@
+/*
+  TMROctForest.cpp -- host half of the B200 drop-in forest.
+
+  This file owns what is cheap and serial (the O(nblocks) super-mesh tables,
+  argument checking, lazily materialised host mirrors) and forwards every
+  data-parallel step to the CUDA layer through include/tmrgpu.h.  Each public
+  method cites the reference code whose behaviour it keeps.
+*/
+#include "TMROctForest.h"
+
+#include <math.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.h" /* shared host/device geometry: transform_node, tables */
+#include "tmrgpu.h"
+
+/* ---- small helpers -------------------------------------------------------- */
+namespace {
+
+/* corners of block face f in (u,v) order, k = u + 2v */
+inline int face_corner(int f, int k) {
+  tmrgpu::i32 x, y, z;
+  tmrgpu::face_place(f, f & 1, k & 1, k >> 1, &x, &y, &z);
+  return x + 2 * y + 4 * z;
+}
+
+/* owner face node k coincides with node orient(id,k) of a face whose
+   orientation id relative to the owner is `id` */
+inline int orient(int id, int k) {
+  tmrgpu::i32 a, b;
+  tmrgpu::owner_to_face(id, 1, k & 1, k >> 1, &a, &b);
+  return a + 2 * b;
+}
+
+inline int *copy_ints(const int *src, int n) {
+  int *dst = new int[n > 0 ? n : 1];
+  if (n > 0) memcpy(dst, src, (size_t)n * sizeof(int));
+  return dst;
+}
+
+/* turn counts stored at ptr[i+1] into CSR offsets */
+inline void counts_to_offsets(int *ptr, int n) {
+  ptr[0] = 0;
+  for (int i = 0; i < n; i++) ptr[i + 1] += ptr[i];
+}
+
+inline bool same_pair(int a0, int a1, int b0, int b1) {
+  return (a0 == b0 && a1 == b1) || (a0 == b1 && a1 == b0);
+}
+
+}  // namespace
+
+/* ---- BlockTables (reference src/TMROctForest.cpp:558-1143) ------------------ */
+TMROctForest::BlockTables::BlockTables() {
+  num_nodes = num_edges = num_faces = num_blocks = 0;
+  block_conn = block_face_conn = block_edge_conn = block_face_ids = NULL;
+  node_block_ptr = node_block_conn = NULL;
+  edge_block_ptr = edge_block_conn = NULL;
+  face_block_ptr = face_block_conn = NULL;
+  face_block_owners = edge_block_owners = node_block_owners = NULL;
+}
+
+TMROctForest::BlockTables::~BlockTables() {
+  delete[] block_conn;
+  delete[] block_face_conn;
+  delete[] block_edge_conn;
+  delete[] block_face_ids;
+  delete[] node_block_ptr;
+  delete[] node_block_conn;
+  delete[] edge_block_ptr;
+  delete[] edge_block_conn;
+  delete[] face_block_ptr;
+  delete[] face_block_conn;
+  delete[] face_block_owners;
+  delete[] edge_block_owners;
+  delete[] node_block_owners;
+}
+
+/* node -> (8*block + corner), blocks ascending (reference :643-693) */
+void TMROctForest::BlockTables::nodesToBlocks() {
+  node_block_ptr = new int[num_nodes + 1];
+  std::fill(node_block_ptr, node_block_ptr + num_nodes + 1, 0);
+  for (int i = 0; i < 8 * num_blocks; i++) node_block_ptr[block_conn[i] + 1]++;
+  counts_to_offsets(node_block_ptr, num_nodes);
+  node_block_conn = new int[node_block_ptr[num_nodes] > 0
+                                ? node_block_ptr[num_nodes]
+                                : 1];
+  std::vector<int> fill(node_block_ptr, node_block_ptr + num_nodes);
+  for (int b = 0; b < num_blocks; b++) {
+    for (int c = 0; c < 8; c++) {
+      const int node = block_conn[8 * b + c];
+      /* the reference stores the FIRST corner of b that equals this node */
+      int first = 0;
+      while (block_conn[8 * b + first] != node) first++;
+      node_block_conn[fill[node]++] = 8 * b + first;
+    }
+  }
+}
+
+/* unique edge numbers in first-encounter order (reference :771-842) */
+void TMROctForest::BlockTables::edgesFromNodes() {
+  block_edge_conn = new int[12 * num_blocks > 0 ? 12 * num_blocks : 1];
+  std::fill(block_edge_conn, block_edge_conn + 12 * num_blocks, -1);
+  int next = 0;
+  for (int b = 0; b < num_blocks; b++) {
+    for (int e = 0; e < 12; e++) {
+      if (block_edge_conn[12 * b + e] >= 0) continue;
+      const int n1 = block_conn[8 * b + tmrgpu::edge_corner(e, 0)];
+      const int n2 = block_conn[8 * b + tmrgpu::edge_corner(e, 1)];
+      std::vector<int> unnumbered(1, 12 * b + e);
+      int number = -1;
+      for (int ip = node_block_ptr[n1]; ip < node_block_ptr[n1 + 1]; ip++) {
+        const int ob = node_block_conn[ip] / 8;
+        for (int oe = 0; oe < 12; oe++) {
+          const int m1 = block_conn[8 * ob + tmrgpu::edge_corner(oe, 0)];
+          const int m2 = block_conn[8 * ob + tmrgpu::edge_corner(oe, 1)];
+          if (!same_pair(n1, n2, m1, m2)) continue;
+          if (block_edge_conn[12 * ob + oe] >= 0) {
+            number = block_edge_conn[12 * ob + oe];
+          } else if (unnumbered.size() < 128) {
+            unnumbered.push_back(12 * ob + oe);
+          }
+        }
+      }
+      if (number < 0) number = next++;
+      for (size_t k = 0; k < unnumbered.size(); k++) {
+        block_edge_conn[unnumbered[k]] = number;
+      }
+    }
+  }
+  num_edges = next;
+}
+
+/* unique face numbers in first-encounter order (reference :847-945) */
+void TMROctForest::BlockTables::facesFromNodes() {
+  block_face_conn = new int[6 * num_blocks > 0 ? 6 * num_blocks : 1];
+  std::fill(block_face_conn, block_face_conn + 6 * num_blocks, -1);
+  int next = 0;
+  for (int b = 0; b < num_blocks; b++) {
+    for (int f = 0; f < 6; f++) {
+      if (block_face_conn[6 * b + f] >= 0) continue;
+      int fn[4];
+      for (int k = 0; k < 4; k++) fn[k] = block_conn[8 * b + face_corner(f, k)];
+      std::vector<int> unnumbered(1, 6 * b + f);
+      int number = -1;
+      const int pivot = fn[0];
+      for (int ip = node_block_ptr[pivot]; ip < node_block_ptr[pivot + 1];
+           ip++) {
+        const int ob = node_block_conn[ip] / 8;
+        if (ob == b) continue;
+        for (int of = 0; of < 6; of++) {
+          int on[4];
+          for (int k = 0; k < 4; k++) {
+            on[k] = block_conn[8 * ob + face_corner(of, k)];
+          }
+          bool match = false;
+          for (int id = 0; id < 8 && !match; id++) {
+            match = (fn[0] == on[orient(id, 0)] && fn[1] == on[orient(id, 1)] &&
+                     fn[2] == on[orient(id, 2)] && fn[3] == on[orient(id, 3)]);
+          }
+          if (!match) continue;
+          if (block_face_conn[6 * ob + of] >= 0) {
+            number = block_face_conn[6 * ob + of];
+          } else if (unnumbered.size() < 128) {
+            unnumbered.push_back(6 * ob + of);
+          }
+        }
+      }
+      if (number < 0) number = next++;
+      for (size_t k = 0; k < unnumbered.size(); k++) {
+        block_face_conn[unnumbered[k]] = number;
+      }
+    }
+  }
+  num_faces = next;
+}
+
+/* edge -> (12*block + local edge), owner (lowest block) first
+   (reference :698-766) */
+void TMROctForest::BlockTables::edgesToBlocks() {
+  edge_block_ptr = new int[num_edges + 1];
+  std::fill(edge_block_ptr, edge_block_ptr + num_edges + 1, 0);
+  for (int i = 0; i < 12 * num_blocks; i++) {
+    edge_block_ptr[block_edge_conn[i] + 1]++;
+  }
+  counts_to_offsets(edge_block_ptr, num_edges);
+  edge_block_conn =
+      new int[edge_block_ptr[num_edges] > 0 ? edge_block_ptr[num_edges] : 1];
+  std::vector<int> fill(edge_block_ptr, edge_block_ptr + num_edges);
+  for (int b = 0; b < num_blocks; b++) {
+    for (int e = 0; e < 12; e++) {
+      edge_block_conn[fill[block_edge_conn[12 * b + e]]++] = b;
+    }
+  }
+  for (int edge = 0; edge < num_edges; edge++) {
+    const int begin = edge_block_ptr[edge], end = edge_block_ptr[edge + 1];
+    int owner = num_blocks;
+    for (int ip = begin; ip < end; ip++) {
+      owner = std::min(owner, edge_block_conn[ip]);
+    }
+    if (owner == num_blocks) continue;
+    int oe = 0;
+    while (oe < 12 && block_edge_conn[12 * owner + oe] != edge) oe++;
+    const int n1 = block_conn[8 * owner + tmrgpu::edge_corner(oe, 0)];
+    const int n2 = block_conn[8 * owner + tmrgpu::edge_corner(oe, 1)];
+    for (int ip = begin; ip < end; ip++) {
+      const int b = edge_block_conn[ip];
+      for (int e = 0; e < 12; e++) {
+        const int m1 = block_conn[8 * b + tmrgpu::edge_corner(e, 0)];
+        const int m2 = block_conn[8 * b + tmrgpu::edge_corner(e, 1)];
+        if (same_pair(n1, n2, m1, m2)) {
+          edge_block_conn[ip] = 12 * b + e;
+          break;
+        }
+      }
+    }
+  }
+}
+
+/* face -> (6*block + local face) and the orientation id of every block face
+   relative to its owner face (reference :950-1085) */
+void TMROctForest::BlockTables::facesToBlocks() {
+  face_block_ptr = new int[num_faces + 1];
+  std::fill(face_block_ptr, face_block_ptr + num_faces + 1, 0);
+  for (int i = 0; i < 6 * num_blocks; i++) {
+    face_block_ptr[block_face_conn[i] + 1]++;
+  }
+  counts_to_offsets(face_block_ptr, num_faces);
+  face_block_conn =
+      new int[face_block_ptr[num_faces] > 0 ? face_block_ptr[num_faces] : 1];
+  std::vector<int> fill(face_block_ptr, face_block_ptr + num_faces);
+  for (int b = 0; b < num_blocks; b++) {
+    for (int f = 0; f < 6; f++) {
+      face_block_conn[fill[block_face_conn[6 * b + f]]++] = b;
+    }
+  }
+  block_face_ids = new int[6 * num_blocks > 0 ? 6 * num_blocks : 1];
+  std::fill(block_face_ids, block_face_ids + 6 * num_blocks, 0);
+  for (int face = 0; face < num_faces; face++) {
+    const int begin = face_block_ptr[face], end = face_block_ptr[face + 1];
+    int owner = num_blocks;
+    for (int ip = begin; ip < end; ip++) {
+      owner = std::min(owner, face_block_conn[ip]);
+    }
+    if (owner == num_blocks) continue;
+    int of = 0;
+    while (of < 6 && block_face_conn[6 * owner + of] != face) of++;
+    int on[4];
+    for (int k = 0; k < 4; k++) on[k] = block_conn[8 * owner + face_corner(of, k)];
+    for (int ip = begin; ip < end; ip++) {
+      const int b = face_block_conn[ip];
+      int f = 0;
+      for (; f < 6; f++) {
+        if (block_face_conn[6 * b + f] != face) continue;
+        int an[4];
+        for (int k = 0; k < 4; k++) an[k] = block_conn[8 * b + face_corner(f, k)];
+        bool match = false;
+        for (int id = 0; id < 8; id++) {
+          match = (on[0] == an[orient(id, 0)] && on[1] == an[orient(id, 1)] &&
+                   on[2] == an[orient(id, 2)] && on[3] == an[orient(id, 3)]);
+          if (match) {
+            block_face_ids[6 * b + f] = id;
+            break;
+          }
+        }
+        if (match) break;
+      }
+      face_block_conn[ip] = 6 * b + f;
+    }
+  }
+}
+
+/* owner = lowest block touching the entity (reference :1091-1143) */
+void TMROctForest::BlockTables::entityOwners() {
+  face_block_owners = new int[num_faces > 0 ? num_faces : 1];
+  edge_block_owners = new int[num_edges > 0 ? num_edges : 1];
+  node_block_owners = new int[num_nodes > 0 ? num_nodes : 1];
+  for (int f = 0; f < num_faces; f++) {
+    int o = num_blocks;
+    for (int ip = face_block_ptr[f]; ip < face_block_ptr[f + 1]; ip++) {
+      o = std::min(o, face_block_conn[ip] / 6);
+    }
+    face_block_owners[f] = o;
+  }
+  for (int e = 0; e < num_edges; e++) {
+    int o = num_blocks;
+    for (int ip = edge_block_ptr[e]; ip < edge_block_ptr[e + 1]; ip++) {
+      o = std::min(o, edge_block_conn[ip] / 12);
+    }
+    edge_block_owners[e] = o;
+  }
+  for (int n = 0; n < num_nodes; n++) {
+    int o = num_blocks;
+    for (int ip = node_block_ptr[n]; ip < node_block_ptr[n + 1]; ip++) {
+      o = std::min(o, node_block_conn[ip] / 8);
+    }
+    node_block_owners[n] = o;
+  }
+}
+
+/* ---- construction / teardown ------------------------------------------------- */
+TMROctForest::TMROctForest(MPI_Comm _comm, int _mesh_order,
+                           TMRInterpolationType _interp_type) {
+  if (!TMRIsInitialized()) TMRInitialize();
+  comm = _comm;
+  MPI_Comm_rank(comm, &mpi_rank);
+  MPI_Comm_size(comm, &mpi_size);
+  mesh_order = 2;
+  interp_knots = NULL;
+  topo = NULL;
+  tables = NULL;
+  dev = NULL;
+  octants = NULL;
+  octants_exposed = 0;
+  owners = NULL;
+  conn = node_numbers = node_range = NULL;
+  dep_ptr = dep_conn = NULL;
+  dep_weights = NULL;
+  X = NULL;
+  num_local_nodes = num_dep_nodes = num_owned_nodes = ext_pre_offset = 0;
+  num_elements_nodes = 0;
+  nodes_on_host = nodes_exist = 0;
+  setMeshOrder(_mesh_order, _interp_type);
+}
+
+TMROctForest::~TMROctForest() {
+  if (topo) topo->decref();
+  dropTables();
+  dropMeshData(1, 1);
+  if (dev) tmrgpu_forest_destroy(dev);
+  delete[] interp_knots;
+}
+
+int TMROctForest::ensureDevice() {
+  if (dev) return 0;
+  tmrgpu_ctx *ctx = tmr_b200_context();
+  if (!ctx) return 1;
+  return tmrgpu_forest_create(ctx, &dev);
+}
+
+void TMROctForest::dropTables() {
+  if (tables) tables->decref();
+  tables = NULL;
+}
+
+void TMROctForest::dropHostNodeMirrors() {
+  delete[] conn;
+  delete[] node_numbers;
+  delete[] node_range;
+  delete[] dep_ptr;
+  delete[] dep_conn;
+  delete[] dep_weights;
+  delete[] X;
+  conn = node_numbers = node_range = NULL;
+  dep_ptr = dep_conn = NULL;
+  dep_weights = NULL;
+  X = NULL;
+  num_local_nodes = num_dep_nodes = num_owned_nodes = ext_pre_offset = 0;
+  nodes_on_host = 0;
+}
+
+/* freeMeshData (reference :426-483): node data always goes; octants / owners
+   on request */
+void TMROctForest::dropMeshData(int drop_octants, int drop_owners) {
+  if (drop_owners) {
+    delete[] owners;
+    owners = NULL;
+  }
+  if (drop_octants) {
+    delete octants;
+    octants = NULL;
+    octants_exposed = 0;
+  }
+  dropHostNodeMirrors();
+  nodes_exist = 0;
+  if (dev) tmrgpu_free_nodes(dev);
+}
+
+void TMROctForest::pushTablesToDevice() {
+  if (ensureDevice()) return;
+  BlockTables *t = tables;
+  tmrgpu_set_connectivity(
+      dev, t->num_blocks, t->num_nodes, t->num_edges, t->num_faces,
+      t->block_conn, t->block_edge_conn, t->block_face_conn, t->block_face_ids,
+      t->node_block_ptr, t->node_block_conn, t->edge_block_ptr,
+      t->edge_block_conn, t->face_block_ptr, t->face_block_conn,
+      t->node_block_owners, t->edge_block_owners, t->face_block_owners);
+}
+
+/* ---- topology / connectivity -------------------------------------------------- */
+void TMROctForest::setTopology(TMRTopology *_topo) {
+  dropTables();
+  dropMeshData(1, 1);
+  if (_topo) {
+    _topo->incref();
+    if (topo) topo->decref();
+    topo = _topo;
+    int nn, ne, nf, nb;
+    const int *bc, *bec, *bfc;
+    topo->getConnectivity(&nn, &ne, &nf, &nb, &bc, &bec, &bfc);
+    setFullConnectivity(nn, ne, nf, nb, bc, bec, bfc);
+  }
+}
+
+TMRTopology *TMROctForest::getTopology() { return topo; }
+
+void TMROctForest::setConnectivity(int _num_nodes, const int *_block_conn,
+                                   int _num_blocks) {
+  dropTables();
+  dropMeshData(1, 1);
+  tables = new BlockTables();
+  tables->incref();
+  tables->num_nodes = _num_nodes;
+  tables->num_blocks = _num_blocks;
+  tables->block_conn = copy_ints(_block_conn, 8 * _num_blocks);
+  tables->nodesToBlocks();
+  tables->edgesFromNodes();
+  tables->edgesToBlocks();
+  tables->facesFromNodes();
+  tables->facesToBlocks();
+  tables->entityOwners();
+  pushTablesToDevice();
+}
+
+void TMROctForest::setFullConnectivity(int _num_nodes, int _num_edges,
+                                       int _num_faces, int _num_blocks,
+                                       const int *_block_conn,
+                                       const int *_block_edge_conn,
+                                       const int *_block_face_conn) {
+  dropTables();
+  dropMeshData(1, 1);
+  tables = new BlockTables();
+  tables->incref();
+  tables->num_nodes = _num_nodes;
+  tables->num_edges = _num_edges;
+  tables->num_faces = _num_faces;
+  tables->num_blocks = _num_blocks;
+  tables->block_conn = copy_ints(_block_conn, 8 * _num_blocks);
+  tables->nodesToBlocks();
+  tables->block_edge_conn = copy_ints(_block_edge_conn, 12 * _num_blocks);
+  tables->edgesToBlocks();
+  tables->block_face_conn = copy_ints(_block_face_conn, 6 * _num_blocks);
+  tables->facesToBlocks();
+  tables->entityOwners();
+  pushTablesToDevice();
+}
+
+/* ---- order / knots (reference :1389-1427) -------------------------------------- */
+void TMROctForest::setMeshOrder(int _mesh_order,
+                                TMRInterpolationType _interp_type) {
+  dropMeshData(0, 0);
+  delete[] interp_knots;
+  mesh_order = _mesh_order;
+  if (mesh_order < 2) mesh_order = 2;
+  if (mesh_order > MAX_ORDER) mesh_order = MAX_ORDER;
+  interp_type = _interp_type;
+  interp_knots = new double[2 * mesh_order];
+  std::fill(interp_knots, interp_knots + 2 * mesh_order, 0.0);
+  interp_knots[0] = -1.0;
+  interp_knots[mesh_order - 1] = 1.0;
+  for (int i = 1; i < mesh_order - 1; i++) {
+    if (interp_type == TMR_UNIFORM_POINTS) {
+      interp_knots[i] = -1.0 + 2.0 * i / (mesh_order - 1);
+    } else {
+      interp_knots[i] = -cos(M_PI * i / (mesh_order - 1));
+    }
+  }
+}
+
+int TMROctForest::getMeshOrder() { return mesh_order; }
+TMRInterpolationType TMROctForest::getInterpType() { return interp_type; }
+
+int TMROctForest::getInterpKnots(const double **_knots) {
+  if (_knots) *_knots = interp_knots;
+  return mesh_order;
+}
+
+/* ---- octant mirror management -------------------------------------------------- */
+int TMROctForest::syncOctantsToDevice() {
+  if (ensureDevice()) return 1;
+  if (octants && octants_exposed) {
+    /* the caller holds a mutable pointer into the mirror (Python writes
+       through it, reference tmr/TMR.pyx:3303-3317): re-upload */
+    TMROctant *a;
+    int n;
+    octants->getArray(&a, &n);
+    const int rc = tmrgpu_upload_octants(
+        dev, reinterpret_cast<const tmrgpu_octant *>(a), n);
+    octants_exposed = 0;
+    return rc;
+  }
+  return 0;
+}
+
+void TMROctForest::octantsReplacedOnDevice() {
+  delete octants;
+  octants = NULL;
+  octants_exposed = 0;
+}
+
+void TMROctForest::getOctants(TMROctantArray **_octants) {
+  if (!octants && dev && tables) {
+    const int n = (int)tmrgpu_count(dev);
+    TMROctant *a = new TMROctant[n > 0 ? n : 1];
+    tmrgpu_download_octants(dev, reinterpret_cast<tmrgpu_octant *>(a));
+    octants = new TMROctantArray(a, n);
+  }
+  if (octants) octants_exposed = 1;
+  if (_octants) *_octants = octants;
+}
+
+/* ---- tree creation -------------------------------------------------------------- */
+static void rank_block_range(int num_blocks, int rank, int size, int *start,
+                             int *end) {
+  /* contiguous deal of trees to ranks (reference :1758-1770) */
+  const int base = num_blocks / size, extra = num_blocks % size;
+  *start = rank * base + std::min(rank, extra);
+  *end = *start + base + (rank < extra ? 1 : 0);
+}
+
+void TMROctForest::createTrees(int refine_level) {
+  if (!tables || ensureDevice()) {
+    fprintf(stderr,
+            "TMROctForest Error: Cannot call createTrees(), no connectivity "
+            "has been set\n");
+    return;
+  }
+  dropMeshData(1, 1);
+  int start, end;
+  rank_block_range(tables->num_blocks, mpi_rank, mpi_size, &start, &end);
+  tmrgpu_create_trees(dev, refine_level, start, end);
+}
+
+void TMROctForest::createRandomTrees(int nrand, int min_level, int max_level) {
+  if (!tables || ensureDevice()) {
+    fprintf(stderr,
+            "TMROctForest Error: Cannot call createRandomTrees(), no "
+            "connectivity has been set\n");
+    return;
+  }
+  dropMeshData(1, 1);
+  int start, end;
+  rank_block_range(tables->num_blocks, mpi_rank, mpi_size, &start, &end);
+  /* same rand() draw order as the reference (:1863-1881), so the same libc
+     seed gives the same forest */
+  const int size = nrand * (end - start);
+  std::vector<tmrgpu_octant> recs(size > 0 ? size : 1);
+  for (int count = 0, block = start; block < end; block++) {
+    for (int i = 0; i < nrand; i++, count++) {
+      const int32_t level = min_level + (rand() % (max_level - min_level + 1));
+      const int32_t h = 1 << (TMR_MAX_LEVEL - level);
+      tmrgpu_octant &o = recs[count];
+      o.x = h * (rand() % (1 << level));
+      o.y = h * (rand() % (1 << level));
+      o.z = h * (rand() % (1 << level));
+      o.tag = 0;
+      o.block = block;
+      o.level = (int16_t)level;
+      o.info = 0;
+    }
+  }
+  if (tmrgpu_upload_octants(dev, recs.data(), size) == 0) {
+    tmrgpu_sort_unique(dev);
+  }
+}
+
+/* ---- repartition (reference :1922-2088) ------------------------------------------ */
+void TMROctForest::repartition(int max_rank) {
+  (void)max_rank;
+  dropMeshData(0, 1);
+  if (mpi_size > 1) {
+    fprintf(stderr,
+            "TMROctForest Error: multi-rank repartition() is not available in "
+            "this build\n");
+  }
+  /* single rank: the partition is the whole sorted array; tags stay = index */
+}
+
+/* ---- duplicate / coarsen (reference :2097-2164) ----------------------------------- */
+TMROctForest *TMROctForest::duplicate() {
+  TMROctForest *dup = new TMROctForest(comm, mesh_order, interp_type);
+  if (tables && dev) {
+    syncOctantsToDevice();
+    tables->incref();
+    dup->tables = tables;
+    dup->topo = topo;
+    if (topo) topo->incref();
+    if (dup->ensureDevice() == 0) tmrgpu_duplicate(dev, dup->dev);
+  }
+  return dup;
+}
+
+TMROctForest *TMROctForest::coarsen() {
+  TMROctForest *coarse = new TMROctForest(comm, mesh_order, interp_type);
+  if (tables && dev) {
+    syncOctantsToDevice();
+    tables->incref();
+    coarse->tables = tables;
+    coarse->topo = topo;
+    if (topo) topo->incref();
+    if (coarse->ensureDevice() == 0) tmrgpu_coarsen(dev, coarse->dev);
+  }
+  return coarse;
+}
+
+/* ---- refine / balance -------------------------------------------------------------- */
+void TMROctForest::refine(const int refinement[], int min_level,
+                          int max_level) {
+  if (!tables || !dev) {
+    fprintf(stderr,
+            "TMROctForest Error: Cannot call refine(), no octants have been "
+            "created\n");
+    return;
+  }
+  dropMeshData(0, 0);
+  if (syncOctantsToDevice()) return;
+  if (tmrgpu_refine(dev, refinement, min_level, max_level) == 0) {
+    octantsReplacedOnDevice();
+  }
+}
+
+void TMROctForest::balance(int balance_corner) {
+  if (!tables || !dev) {
+    fprintf(stderr,
+            "TMROctForest Error: Cannot call balance(), no octants have been "
+            "created\n");
+    return;
+  }
+  /* note: like the reference (:2917), balance() does NOT invalidate node data */
+  if (syncOctantsToDevice()) return;
+  if (tmrgpu_balance(dev, balance_corner) == 0) {
+    octantsReplacedOnDevice();
+  }
+}
+
+/* ---- nodes ---------------------------------------------------------------------------- */
+void TMROctForest::createNodes() {
+  if (!tables || !dev) {
+    fprintf(stderr,
+            "TMROctForest Error: Cannot call createNodes(), no octants have "
+            "been created\n");
+    return;
+  }
+  if (nodes_exist) return; /* reference :4071-4075 */
+  if (syncOctantsToDevice()) return;
+  if (tmrgpu_create_nodes(dev, mesh_order, (int)interp_type, interp_knots)) {
+    return;
+  }
+  nodes_exist = 1;
+  nodes_on_host = 0;
+  /* createNodes rewrites the info field of every octant
+     (computeDepFacesAndEdges, reference :3619); keep a live mirror in step */
+  if (octants) {
+    TMROctant *a;
+    int n;
+    octants->getArray(&a, &n);
+    std::vector<int16_t> info(n > 0 ? n : 1);
+    tmrgpu_download_info(dev, info.data());
+    for (int i = 0; i < n; i++) a[i].info = info[i];
+  }
+}
+
+void TMROctForest::fetchNodeData() {
+  if (nodes_on_host || !nodes_exist || !dev) return;
+  int64_t s[6];
+  if (tmrgpu_node_sizes(dev, s)) return;
+  dropHostNodeMirrors();
+  const int npe = mesh_order * mesh_order * mesh_order;
+  num_elements_nodes = (int)s[0];
+  num_local_nodes = (int)s[1];
+  num_dep_nodes = (int)s[2];
+  num_owned_nodes = (int)s[3];
+  const int nnz = (int)s[4];
+  conn = new int[(size_t)num_elements_nodes * npe + 1];
+  node_numbers = new int[num_local_nodes + 1];
+  dep_ptr = new int[num_dep_nodes + 1];
+  dep_conn = new int[nnz + 1];
+  dep_weights = new double[nnz + 1];
+  tmrgpu_download_nodes(dev, conn, node_numbers, dep_ptr, dep_conn,
+                        dep_weights);
+  /* node_range: owned-node prefix over ranks (reference :4165-4172) */
+  node_range = new int[mpi_size + 1];
+  std::fill(node_range, node_range + mpi_size + 1, 0);
+  for (int r = mpi_rank + 1; r <= mpi_size; r++) {
+    node_range[r] = (int)s[5] + num_owned_nodes;
+  }
+  for (int r = 0; r <= mpi_rank; r++) node_range[r] = (int)s[5];
+  /* the reference hands out node_numbers sorted ascending (:4246) */
+  std::sort(node_numbers, node_numbers + num_local_nodes);
+  int *item = std::lower_bound(node_numbers, node_numbers + num_local_nodes,
+                               node_range[mpi_rank]);
+  ext_pre_offset = (int)(item - node_numbers);
+  /* no CAD topology => node locations are zero (reference :5526-5539) */
+  X = new TMRPoint[num_local_nodes + 1];
+  for (int i = 0; i < num_local_nodes; i++) X[i].zero();
+  nodes_on_host = 1;
+}
+
+void TMROctForest::getNodeConn(const int **_conn, int *_num_elements,
+                               int *_num_owned_nodes, int *_num_local_nodes) {
+  fetchNodeData();
+  (void)_num_local_nodes; /* never written by the reference (:5686-5704) */
+  int nelems = 0;
+  if (dev) nelems = (int)tmrgpu_count(dev);
+  if (_conn) *_conn = conn;
+  if (_num_elements) *_num_elements = nelems;
+  if (_num_owned_nodes) *_num_owned_nodes = num_owned_nodes;
+}
+
+int TMROctForest::getDepNodeConn(const int **_ptr, const int **_conn,
+                                 const double **_weights) {
+  fetchNodeData();
+  if (_ptr) *_ptr = dep_ptr;
+  if (_conn) *_conn = dep_conn;
+  if (_weights) *_weights = dep_weights;
+  return num_dep_nodes;
+}
+
+int TMROctForest::getOwnedNodeRange(const int **_node_range) {
+  fetchNodeData();
+  if (_node_range) *_node_range = node_range;
+  return mpi_size;
+}
+
+int TMROctForest::getNodeNumbers(const int **_node_numbers) {
+  fetchNodeData();
+  if (_node_numbers) *_node_numbers = node_numbers;
+  return num_local_nodes;
+}
+
+int TMROctForest::getExtPreOffset() {
+  fetchNodeData();
+  return ext_pre_offset;
+}
+
+int TMROctForest::getPoints(TMRPoint **_X) {
+  fetchNodeData();
+  if (_X) *_X = X;
+  return num_local_nodes;
+}
+
+int TMROctForest::getLocalNodeNumber(int node) {
+  fetchNodeData();
+  if (node_numbers) {
+    int *end = node_numbers + num_local_nodes;
+    int *item = std::lower_bound(node_numbers, end, node);
+    if (item != end && *item == node) return (int)(item - node_numbers);
+  }
+  return -1;
+}
+
+/* ---- interpolation ---------------------------------------------------------------------- */
+void TMROctForest::createInterpolation(TMROctForest *coarse,
+                                       TACSBVecInterp *interp) {
+  createNodes();
+  coarse->createNodes();
+  if (!dev || !coarse->dev || !nodes_exist || !coarse->nodes_exist) return;
+  int64_t nrows = 0, nnz = 0;
+  if (tmrgpu_create_interp(dev, coarse->dev, &nrows, &nnz)) return;
+  std::vector<int> rows(nrows + 1), rowp(nrows + 2), cols(nnz + 1);
+  std::vector<double> vals(nnz + 1);
+  tmrgpu_download_interp(dev, rows.data(), rowp.data(), cols.data(),
+                         vals.data());
+  /* same call stream as the reference's loop (:6683): one addInterp per owned
+     fine node, in first-touch order */
+  for (int64_t r = 0; r < nrows; r++) {
+    interp->addInterp(rows[r], &vals[rowp[r]], &cols[rowp[r]],
+                      rowp[r + 1] - rowp[r]);
+  }
+}
+
+TMROctant *TMROctForest::findEnclosing(const int order, const double *knots,
+                                       TMROctant *node, int *mpi_owner) {
+  if (mpi_owner) *mpi_owner = mpi_rank;
+  if (!dev || syncOctantsToDevice()) return NULL;
+  int index = -1;
+  if (tmrgpu_find_enclosing(dev, order, knots,
+                            reinterpret_cast<const tmrgpu_octant *>(node), 1,
+                            &index)) {
+    return NULL;
+  }
+  if (index < 0) return NULL;
+  TMROctantArray *arr;
+  getOctants(&arr); /* a pointer into the mirror escapes: marks it exposed */
+  TMROctant *a;
+  arr->getArray(&a, NULL);
+  return &a[index];
+}
+
+void TMROctForest::transformNode(TMROctant *oct, int edge_dir,
+                                 int *edge_reversed, int *src_face_id) {
+  if (!tables) return;
+  tmrgpu::ConnTables t;
+  t.nblocks = tables->num_blocks;
+  t.nnodes = tables->num_nodes;
+  t.nedges = tables->num_edges;
+  t.nfaces = tables->num_faces;
+  t.block_conn = tables->block_conn;
+  t.block_edge_conn = tables->block_edge_conn;
+  t.block_face_conn = tables->block_face_conn;
+  t.block_face_ids = tables->block_face_ids;
+  t.node_block_ptr = tables->node_block_ptr;
+  t.node_block_conn = tables->node_block_conn;
+  t.edge_block_ptr = tables->edge_block_ptr;
+  t.edge_block_conn = tables->edge_block_conn;
+  t.face_block_ptr = tables->face_block_ptr;
+  t.face_block_conn = tables->face_block_conn;
+  t.node_block_owners = tables->node_block_owners;
+  t.edge_block_owners = tables->edge_block_owners;
+  t.face_block_owners = tables->face_block_owners;
+  tmrgpu::transform_node(t, &oct->block, &oct->x, &oct->y, &oct->z, edge_dir,
+                         edge_reversed, src_face_id);
+}
+
+/* ---- evalInterp (reference :1508-1620) ---------------------------------------------------- */
+namespace {
+/* value, first and second derivative of the 1-D Lagrange basis */
+void lagrange_all(int order, double u, const double *knots, double *N,
+                  double *Nd, double *Ndd) {
+  for (int i = 0; i < order; i++) {
+    double v = 1.0, d1 = 0.0, d2 = 0.0;
+    for (int j = 0; j < order; j++) {
+      if (j == i) continue;
+      v *= (u - knots[j]) / (knots[i] - knots[j]);
+    }
+    for (int j = 0; j < order; j++) {
+      if (j == i) continue;
+      double t = 1.0 / (knots[i] - knots[j]);
+      for (int k = 0; k < order; k++) {
+        if (k == i || k == j) continue;
+        t *= (u - knots[k]) / (knots[i] - knots[k]);
+      }
+      d1 += t;
+      for (int k = 0; k < order; k++) {
+        if (k == i || k == j) continue;
+        double s = 1.0 / ((knots[i] - knots[j]) * (knots[i] - knots[k]));
+        for (int m = 0; m < order; m++) {
+          if (m == i || m == j || m == k) continue;
+          s *= (u - knots[m]) / (knots[i] - knots[m]);
+        }
+        d2 += s;
+      }
+    }
+    N[i] = v;
+    if (Nd) Nd[i] = d1;
+    if (Ndd) Ndd[i] = d2;
+  }
+}
+}  // namespace
+
+void TMROctForest::evalInterp(const double pt[], double N[]) {
+  double a[3][MAX_ORDER];
+  for (int d = 0; d < 3; d++) {
+    tmrgpu::lagrange_basis(mesh_order, pt[d], interp_knots, a[d]);
+  }
+  for (int k = 0; k < mesh_order; k++) {
+    for (int j = 0; j < mesh_order; j++) {
+      for (int i = 0; i < mesh_order; i++) *N++ = a[0][i] * a[1][j] * a[2][k];
+    }
+  }
+}
+
+void TMROctForest::evalInterp(const double pt[], double N[], double Nxi[],
+                              double Neta[], double Nzeta[]) {
+  double a[3][MAX_ORDER], d[3][MAX_ORDER];
+  for (int c = 0; c < 3; c++) {
+    lagrange_all(mesh_order, pt[c], interp_knots, a[c], d[c], NULL);
+  }
+  for (int k = 0; k < mesh_order; k++) {
+    for (int j = 0; j < mesh_order; j++) {
+      for (int i = 0; i < mesh_order; i++) {
+        *N++ = a[0][i] * a[1][j] * a[2][k];
+        *Nxi++ = d[0][i] * a[1][j] * a[2][k];
+        *Neta++ = a[0][i] * d[1][j] * a[2][k];
+        *Nzeta++ = a[0][i] * a[1][j] * d[2][k];
+      }
+    }
+  }
+}
+
+void TMROctForest::evalInterp(const double pt[], double N[], double N1[],
+                              double N2[], double N3[], double N11[],
+                              double N22[], double N33[], double N23[],
+                              double N13[], double N12[]) {
+  double a[3][MAX_ORDER], d[3][MAX_ORDER], s[3][MAX_ORDER];
+  for (int c = 0; c < 3; c++) {
+    lagrange_all(mesh_order, pt[c], interp_knots, a[c], d[c], s[c]);
+  }
+  for (int k = 0; k < mesh_order; k++) {
+    for (int j = 0; j < mesh_order; j++) {
+      for (int i = 0; i < mesh_order; i++) {
+        *N++ = a[0][i] * a[1][j] * a[2][k];
+        *N1++ = d[0][i] * a[1][j] * a[2][k];
+        *N2++ = a[0][i] * d[1][j] * a[2][k];
+        *N3++ = a[0][i] * a[1][j] * d[2][k];
+        *N11++ = s[0][i] * a[1][j] * a[2][k];
+        *N22++ = a[0][i] * s[1][j] * a[2][k];
+        *N33++ = a[0][i] * a[1][j] * s[2][k];
+        *N23++ = a[0][i] * d[1][j] * d[2][k];
+        *N13++ = d[0][i] * a[1][j] * d[2][k];
+        *N12++ = d[0][i] * d[1][j] * a[2][k];
+      }
+    }
+  }
+}
+
+/* ---- table getters (reference :1625-1739) -------------------------------------------------- */
+void TMROctForest::getConnectivity(int *_nblocks, int *_nfaces, int *_nedges,
+                                   int *_nnodes, const int **_block_conn,
+                                   const int **_block_face_conn,
+                                   const int **_block_edge_conn,
+                                   const int **_block_face_ids) {
+  BlockTables *t = tables;
+  if (_nblocks) *_nblocks = t ? t->num_blocks : 0;
+  if (_nfaces) *_nfaces = t ? t->num_faces : 0;
+  if (_nedges) *_nedges = t ? t->num_edges : 0;
+  if (_nnodes) *_nnodes = t ? t->num_nodes : 0;
+  if (_block_conn) *_block_conn = t ? t->block_conn : NULL;
+  if (_block_face_conn) *_block_face_conn = t ? t->block_face_conn : NULL;
+  if (_block_edge_conn) *_block_edge_conn = t ? t->block_edge_conn : NULL;
+  if (_block_face_ids) *_block_face_ids = t ? t->block_face_ids : NULL;
+}
+
+void TMROctForest::getInverseConnectivity(const int **_node_block_conn,
+                                          const int **_node_block_ptr,
+                                          const int **_edge_block_conn,
+                                          const int **_edge_block_ptr,
+                                          const int **_face_block_conn,
+                                          const int **_face_block_ptr) {
+  BlockTables *t = tables;
+  if (_node_block_conn) *_node_block_conn = t ? t->node_block_conn : NULL;
+  if (_node_block_ptr) *_node_block_ptr = t ? t->node_block_ptr : NULL;
+  if (_edge_block_conn) *_edge_block_conn = t ? t->edge_block_conn : NULL;
+  if (_edge_block_ptr) *_edge_block_ptr = t ? t->edge_block_ptr : NULL;
+  if (_face_block_conn) *_face_block_conn = t ? t->face_block_conn : NULL;
+  if (_face_block_ptr) *_face_block_ptr = t ? t->face_block_ptr : NULL;
+}
+
+/* ---- exchange plumbing (reference :2379-2509), single-rank semantics ------------------------ */
+TMROctantArray *TMROctForest::distributeOctants(TMROctantArray *list,
+                                                int use_tags, int **_oct_ptr,
+                                                int **_oct_recv_ptr,
+                                                int include_local,
+                                                int use_node_index) {
+  (void)use_tags;
+  int size;
+  TMROctant *array;
+  list->getArray(&array, &size);
+  int *oct_ptr = new int[mpi_size + 1];
+  int *oct_recv_ptr = new int[mpi_size + 1];
+  /* one rank owns everything: the local interval is the whole list */
+  oct_ptr[0] = 0;
+  for (int r = 1; r <= mpi_size; r++) oct_ptr[r] = size;
+  oct_recv_ptr[0] = 0;
+  for (int r = 1; r <= mpi_size; r++) {
+    oct_recv_ptr[r] = include_local ? size : 0;
+  }
+  TMROctantArray *dist = sendOctants(list, oct_ptr, oct_recv_ptr, use_node_index);
+  if (_oct_ptr) {
+    *_oct_ptr = oct_ptr;
+  } else {
+    delete[] oct_ptr;
+  }
+  if (_oct_recv_ptr) {
+    *_oct_recv_ptr = oct_recv_ptr;
+  } else {
+    delete[] oct_recv_ptr;
+  }
+  return dist;
+}
+
+TMROctantArray *TMROctForest::sendOctants(TMROctantArray *list,
+                                          const int *oct_ptr,
+                                          const int *oct_recv_ptr,
+                                          int use_node_index) {
+  int size;
+  TMROctant *array;
+  list->getArray(&array, &size);
+  const int recv_size = oct_recv_ptr[mpi_size];
+  TMROctant *recv = new TMROctant[recv_size > 0 ? recv_size : 1];
+  const int r = mpi_rank;
+  const int count = oct_recv_ptr[r + 1] - oct_recv_ptr[r];
+  if (count > 0 && count == oct_ptr[r + 1] - oct_ptr[r]) {
+    memcpy(&recv[oct_recv_ptr[r]], &array[oct_ptr[r]],
+           (size_t)count * sizeof(TMROctant));
+  }
+  return new TMROctantArray(recv, recv_size, use_node_index);
+}
+
+/* ---- CAD-name queries and writers: need the CAD layer (out of scope) -------------------------- */
+TMROctantArray *TMROctForest::getOctsWithName(const char *name) {
+  (void)name;
+  if (!topo) {
+    fprintf(stderr,
+            "TMROctForest Error: getOctsWithName() requires a topology\n");
+    return NULL;
+  }
+  fprintf(stderr,
+          "TMROctForest Error: getOctsWithName() is not part of the B200 "
+          "hot-path build\n");
+  return NULL;
+}
+
+int TMROctForest::getNodesWithName(const char *name, int **_nodes) {
+  (void)name;
+  if (_nodes) *_nodes = NULL;
+  fprintf(stderr,
+          "TMROctForest Error: getNodesWithName() requires the CAD topology "
+          "layer, which is not part of the B200 hot-path build\n");
+  return 0;
+}
+
+void TMROctForest::writeToVTK(const char *filename) {
+  (void)filename;
+  fprintf(stderr,
+          "TMROctForest Error: writeToVTK() requires node locations from the "
+          "CAD layer, which is not part of the B200 hot-path build\n");
+}
+
+void TMROctForest::writeToTecplot(const char *filename) {
+  (void)filename;
+  fprintf(stderr,
+          "TMROctForest Error: writeToTecplot() requires node locations from "
+          "the CAD layer, which is not part of the B200 hot-path build\n");
+}
+
+void TMROctForest::writeForestToVTK(const char *filename) {
+  (void)filename;
+  fprintf(stderr,
+          "TMROctForest Error: writeForestToVTK() requires the CAD topology "
+          "layer, which is not part of the B200 hot-path build\n");
+}
