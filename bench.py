@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py -- octants/s of one adaptation cycle refine -> balance ->
+createNodes (BASELINE.json metric) on synthetic random-refinement forests.
+
+Workload at N=1 (BASELINE.json configs[1], recipe SURVEY.md 8(d) "C2"): 8x8x8
+trees, createTrees(3), four hash-driven passes at pct=35; the timed step is the
+LAST cycle (refine(flags) + balance(0) + createNodes(order 2)) which ends at
+86,278,900 octants.  Every step restarts from a device copy of the pre-step
+forest (the copy is inside the timed region; it is < 0.1% of a step).
+
+  value     whole-job octants/s with the flags already in HBM
+  e2e       the same cycle through the reference-facing TMROctForest API with
+            HOST flags in, and conn / node numbers / dependent CSR read back
+  roofline  dominant kernel, algorithmic bytes / CUDA-event time, vs the
+            measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the unmodified reference C++ (oracle/_ref)
+            on the box's host cores, threads-as-ranks, on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "octants/sec for refine+balance+createNodes"
+UNIT = "octants/s"
+FULL = dict(nb=8, level=3, passes=4, pct=35, order=2, corner=0, seed=2024)
+# bounded CPU sample of the same recipe (two passes instead of four)
+CPU_SAMPLE = dict(nb=8, level=3, passes=2, pct=35, order=2, corner=0, seed=2024)
+
+
+def workload_name(cfg):
+    return ("%dx%dx%d-tree box, createTrees(%d), %d passes pct=%d, last cycle "
+            "refine+balance(%d)+createNodes(order %d)" %
+            (cfg["nb"], cfg["nb"], cfg["nb"], cfg["level"], cfg["passes"],
+             cfg["pct"], cfg["corner"], cfg["order"]))
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [t.strip() for t in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# reference arm (CPU): the unmodified reference through oracle/_ref
+# --------------------------------------------------------------------------
+def run_reference_cycle(cfg, nranks, steps, warmup):
+    """Time the last adaptation cycle of `cfg` on `nranks` thread-ranks of the
+    oracle.  Returns (octants/s, final octants, per-step seconds)."""
+    import util
+    from oracle import ref_loader
+    from tmr_b200.forest import OctForest
+
+    lib = ref_loader.load()
+    conn = util.structured_conn(cfg["nb"])
+    total = steps + warmup
+    times = [[0.0] * total for _ in range(nranks)]
+    finals = [0] * nranks
+    lib.shim_world_begin(nranks)
+    barrier = threading.Barrier(nranks)
+
+    def body(rank):
+        lib.shim_attach(rank)
+        f = OctForest(order=cfg["order"], lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(cfg["level"])
+        f.repartition()
+        for p in range(cfg["passes"] - 1):
+            o = f.getOctants().as_array()
+            f.refine(util.synth_flags(o, cfg["seed"] + p, cfg["pct"]))
+            f.balance(cfg["corner"])
+            f.repartition()
+        o = f.getOctants().as_array()
+        flags = util.synth_flags(o, cfg["seed"] + cfg["passes"] - 1, cfg["pct"])
+        for s in range(total):
+            work = f.duplicate()
+            barrier.wait()
+            t0 = time.perf_counter()
+            work.refine(flags)
+            work.balance(cfg["corner"])
+            work.createNodes()
+            barrier.wait()
+            times[rank][s] = time.perf_counter() - t0
+            finals[rank] = work.getNumOctants()
+            del work
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    lib.shim_world_end()
+    per_step = [max(times[r][s] for r in range(nranks)) for s in range(warmup, total)]
+    n_final = sum(finals)
+    return n_final * len(per_step) / sum(per_step), n_final, per_step
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "oracle/_ref/libtmr_ref.so missing (built by __graft_entry__.build() where /root/reference exists)"}))
+        return
+    cores = min(os.cpu_count() or 1, 8)
+    cfg = CPU_SAMPLE
+    value, n_final, per_step = run_reference_cycle(cfg, cores, args.steps, args.warmup)
+    sample = ("bounded sample: %s -> %d octants, %d thread-ranks (MPI shim), each step = that whole cycle"
+              % (workload_name(cfg), n_final, cores))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": workload_name(FULL), "timed_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
+                         "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--passes", type=int, default=FULL["passes"],
+                    help="refinement passes of the recipe (4 = the named ~86M config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_main(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import util
+    import tmr_b200
+    from tmr_b200.forest import OctForest
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    os.environ["TMR_B200_DEVICE"] = str(local)
+    stream = torch.cuda.current_stream()
+    tmr_b200.use_stream(stream.cuda_stream)
+    lib = tmr_b200.require_gpu()
+
+    P, I64 = ctypes.c_void_p, ctypes.c_int64
+    lib.tmr_b200_context.restype = P
+    lib.tmr_b200_device_forest.restype = P
+    lib.tmr_b200_device_forest.argtypes = [P]
+    for name, argt in [
+        ("tmrgpu_synth_flags", [P, ctypes.c_uint64, ctypes.c_int, P]),
+        ("tmrgpu_refine_device", [P, P, ctypes.c_int, ctypes.c_int]),
+        ("tmrgpu_balance", [P, ctypes.c_int]),
+        ("tmrgpu_create_nodes", [P, ctypes.c_int, ctypes.c_int, P]),
+        ("tmrgpu_duplicate", [P, P]),
+        ("tmrgpu_dev_alloc", [P, I64, ctypes.POINTER(P)]),
+        ("tmrgpu_dev_free", [P, P]),
+        ("tmrgpu_checksum", [P, ctypes.POINTER(ctypes.c_uint64)]),
+        ("tmrgpu_node_sizes", [P, ctypes.POINTER(I64)]),
+        ("tmrgpu_profile_enable", [P, ctypes.c_int]),
+        ("tmrgpu_profile_reset", [P]),
+        ("tmrgpu_profile_json", [P, ctypes.c_char_p, ctypes.c_int]),
+        ("tmrgpu_count", [P]),
+        ("tmrgpu_copy_d2h", [P, P, P, I64]),
+    ]:
+        getattr(lib, name).argtypes = argt
+    lib.tmrgpu_count.restype = I64
+    lib.tmrgpu_launch_count.restype = ctypes.c_long
+    lib.tmrgpu_launch_count.argtypes = [P]
+    ctx = P(lib.tmr_b200_context())
+
+    cfg = dict(FULL)
+    cfg["passes"] = args.passes
+    knots = (ctypes.c_double * 2)(-1.0, 1.0)
+
+    # ---- build-up: everything before the timed cycle, all on the device ----
+    # N>1 (until the NCCL exchange lands): every rank owns an independent
+    # forest of the same recipe (replicas of disjoint tree sets).
+    base = OctForest(order=cfg["order"], lib=lib)
+    base.setConnectivity(util.structured_conn(cfg["nb"]))
+    base.createTrees(cfg["level"])
+    bdev = P(lib.tmr_b200_device_forest(base._ptr))
+
+    def synth(dev, seed):
+        n = lib.tmrgpu_count(dev)
+        buf = P()
+        lib.tmrgpu_dev_alloc(ctx, 4 * max(n, 1), ctypes.byref(buf))
+        lib.tmrgpu_synth_flags(dev, seed, cfg["pct"], buf)
+        return buf, n
+
+    for p in range(cfg["passes"] - 1):
+        buf, _ = synth(bdev, cfg["seed"] + p)
+        assert lib.tmrgpu_refine_device(bdev, buf, 0, 30) == 0
+        assert lib.tmrgpu_balance(bdev, cfg["corner"]) == 0
+        lib.tmrgpu_dev_free(ctx, buf)
+    d_flags, e_in = synth(bdev, cfg["seed"] + cfg["passes"] - 1)
+    # host copy of the flags for the e2e arm (pinned)
+    h_flags_t = torch.empty(max(e_in, 1), dtype=torch.int32).pin_memory()
+    h_flags = h_flags_t.numpy()[:e_in]
+    lib.tmrgpu_copy_d2h(ctx, h_flags.ctypes.data, d_flags, 4 * e_in)
+
+    def step_device():
+        """device-resident cycle: flags already in HBM"""
+        work = base.duplicate()
+        wdev = P(lib.tmr_b200_device_forest(work._ptr))
+        assert lib.tmrgpu_refine_device(wdev, d_flags, 0, 30) == 0
+        assert lib.tmrgpu_balance(wdev, cfg["corner"]) == 0
+        assert lib.tmrgpu_create_nodes(wdev, cfg["order"], 1, knots) == 0
+        return work, wdev
+
+    def step_e2e():
+        """reference-facing API, host flags in, node data out"""
+        work = base.duplicate()
+        lib.tmrc_refine(work._ptr, h_flags.ctypes.data, 0, 30)  # H2D inside
+        lib.tmrc_balance(work._ptr, cfg["corner"])
+        lib.tmrc_create_nodes(work._ptr)
+        cptr = ctypes.POINTER(ctypes.c_int)()
+        ne, no = ctypes.c_int(0), ctypes.c_int(0)
+        lib.tmrc_get_node_conn(work._ptr, ctypes.byref(cptr), ctypes.byref(ne),
+                               ctypes.byref(no))  # D2H of all node arrays
+        return work, ne.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------
+    lib.tmrgpu_profile_enable(ctx, 0)
+    for _ in range(args.warmup):
+        w, wdev = step_device()
+        del w
+    barrier()
+    lib.tmrgpu_profile_reset(ctx)
+    lib.tmrgpu_profile_enable(ctx, 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    last = None
+    for _ in range(args.steps):
+        last = None  # free the previous step's forest
+        last = step_device()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.tmrgpu_launch_count(ctx)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.tmrgpu_profile_json(ctx, buf, len(buf))
+    prof = json.loads(buf.value.decode())
+    lib.tmrgpu_profile_enable(ctx, 0)
+    work, wdev = last
+    e_final = lib.tmrgpu_count(wdev)
+    sizes = (I64 * 6)()
+    lib.tmrgpu_node_sizes(wdev, sizes)
+    csum = ctypes.c_uint64(0)
+    lib.tmrgpu_checksum(wdev, ctypes.byref(csum))
+    del work, last
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(e_final)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    total_octants = float(tot.item())
+    value = total_octants * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm --------------------------------------------------------
+    for _ in range(max(1, args.warmup - 1)):
+        w, _ = step_e2e()
+        del w
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        w, ne = step_e2e()
+        del w
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_octants * args.steps / (float(t.item()) * 1e-3)
+    npe = cfg["order"] ** 3
+    d2h = 4 * (sizes[0] * npe + sizes[1] + sizes[2] + 1 + sizes[4]) + 8 * sizes[4]
+
+    # ---- roofline of the dominant kernel -------------------------------------------
+    peak, peak_src = load_peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    roof = None
+    kernel_share = {k: round(v["ms"] / max(ms, 1e-9), 4) for k, v in
+                    sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+    if dom[0]:
+        name, st = dom
+        # algorithmic bytes per launch of the dominant kernel
+        n_pairs = sizes[0] * npe
+        alg = {"radix_pass_pairs": 2 * 12 * n_pairs, "radix_pass_keys": 2 * 8 * e_final,
+               "nodes_candidates": (8 + 12 * npe) * sizes[0],
+               "nodes_hanging_info": 10 * sizes[0]}.get(name)
+        avg_ms = st["ms"] / st["launches"]
+        if alg:
+            ach = alg / (avg_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                    "launches_per_step": st["launches"] / args.steps,
+                    "algorithmic_bytes_per_launch": alg}
+        else:
+            roof = {"bound": "hbm", "kernel": name, "achieved": None, "peak": peak,
+                    "unit": "GB/s", "frac": None, "traffic": None,
+                    "avg_launch_ms": avg_ms}
+
+    # whole-cycle compulsory traffic (SURVEY.md 8(d) B_alg) as a fraction of HBM peak
+    b_alg = (28 * e_in + 24 * e_in + 24 * e_in + 24 * e_final + 24 * e_final
+             + 4 * npe * e_final + 4 * sizes[1] + 4 * (sizes[2] + 1) + 12 * sizes[4])
+    cycle_frac = b_alg * args.steps / (ms * 1e-3) / 1e9 / peak
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_loader
+
+        if ref_loader.available():
+            cores = min(os.cpu_count() or 1, 8)
+            v, nfin, per = run_reference_cycle(CPU_SAMPLE, cores, 1, 0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": "%s -> %d octants, 1 cycle in %.1f s on %d thread-ranks of the unmodified reference"
+                             % (workload_name(CPU_SAMPLE), nfin, per[0], cores)}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                   "sample": "oracle/_ref not built on this box"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 keys as u64 Morton + f64 weights", "data": "synthetic",
+            "config": {"workload": workload_name(cfg),
+                       "octants_in": int(e_in), "octants_out_per_gpu": int(e_final),
+                       "local_nodes": int(sizes[1]), "dep_nodes": int(sizes[2]),
+                       "dep_nnz": int(sizes[4]), "checksum": "%016x" % csum.value,
+                       "parallelism": "1 GPU" if world == 1 else "%d independent forests (replicas)" % world,
+                       "l2": "inputs larger than L2 (%.0f MB of keys per pass)" % (8e-6 * e_final)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * e_in),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cycle_compulsory_bytes": int(b_alg),
+            "cycle_frac_of_hbm_peak": cycle_frac,
+            "kernel_share_of_step": kernel_share,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

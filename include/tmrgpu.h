@@ -98,6 +98,10 @@ int tmrgpu_node_sizes(tmrgpu_forest *f, int64_t sizes[6]);
 int tmrgpu_download_nodes(tmrgpu_forest *f, int *conn, int *node_numbers,
                           int *dep_ptr, int *dep_conn, double *dep_weights);
 
+/* all local node numbers sorted ascending (what getNodeNumbers() hands out,
+   reference :4246) */
+int tmrgpu_download_sorted_node_numbers(tmrgpu_forest *f, int *out);
+
 /* createInterpolation (reference :6611-6793) between two forests that both
    have nodes.  Builds the CSR on the device; rows are emitted in the
    reference's call order (first touch in element order). */
@@ -131,8 +135,23 @@ int tmrgpu_checksum(tmrgpu_forest *f, uint64_t *out);
 /* raw device allocations for bench-owned buffers */
 int tmrgpu_dev_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out);
 int tmrgpu_dev_free(tmrgpu_ctx *ctx, void *p);
+/* page-locked host buffers (cached per context) for the host mirrors the
+   drop-in hands out, so that D2H runs at PCIe speed */
+int tmrgpu_host_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out);
+int tmrgpu_host_free(tmrgpu_ctx *ctx, void *p);
+int tmrgpu_copy_d2h(tmrgpu_ctx *ctx, void *dst, const void *src, int64_t bytes);
+int tmrgpu_copy_h2d(tmrgpu_ctx *ctx, void *dst, const void *src, int64_t bytes);
 /* [0] octants before refine, [1] after refine, [2] after balance */
 int tmrgpu_last_counts(tmrgpu_forest *f, int64_t counts[3]);
+
+/* ---- primitive self-test hooks (tests/ only) -------------------------------
+   run the radix sort / chained scan on caller data so the primitives can be
+   checked against numpy in isolation */
+int tmrgpu_test_radix_sort(tmrgpu_ctx *ctx, uint64_t *keys, uint32_t *vals,
+                           int64_t n, int bit_lo, int bit_hi);
+int tmrgpu_test_scan(tmrgpu_ctx *ctx, const uint32_t *counts, int64_t n,
+                     uint32_t *out_exclusive, uint64_t *total);
+const char *tmrgpu_build_kind(void);
 
 #ifdef __cplusplus
 }

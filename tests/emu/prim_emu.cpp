@@ -11,6 +11,9 @@ namespace tmrgpu {
 
 void *dev_alloc(Ctx &, size_t bytes) { return malloc(bytes ? bytes : 16); }
 void dev_free(Ctx &, void *p) { free(p); }
+void dev_cache_destroy(Ctx &) {}
+void *host_alloc(Ctx &, size_t bytes) { return malloc(bytes ? bytes : 16); }
+void host_free(Ctx &, void *p) { free(p); }
 void copy_h2d(Ctx &, void *d, const void *s, size_t b) { memcpy(d, s, b); }
 void copy_d2h(Ctx &, void *d, const void *s, size_t b) { memcpy(d, s, b); }
 void copy_d2d(Ctx &, void *d, const void *s, size_t b) { memcpy(d, s, b); }
@@ -21,6 +24,7 @@ int check_errors(Ctx &ctx, const char *) { return ctx.last_error.empty() ? 0 : 1
 void prof_begin(Ctx &, const char *) {}
 void prof_end(Ctx &) {}
 void prof_resolve(Ctx &) {}
+void trace_mark(Ctx &, const char *) {}
 
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &, DBuf<u32> &vals,
                 DBuf<u32> &, i64 n, int bit_lo, int bit_hi) {

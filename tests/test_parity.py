@@ -1,0 +1,260 @@
+"""Parity of the kernel bodies against the oracle (the unmodified reference).
+
+Every test runs twice through the `impl` fixture:
+  * "emu": test-only serial emulation of the kernel bodies (CPU, checks logic)
+  * "gpu": the product library on a B200 (marker: gpu) -- the parity tests
+           proper, through the reference-facing class API / C-ABI.
+Bar: bit-exact octants, info, conn, node numbers, dependent CSR pattern;
+weights within 1e-12 relative (north_star).
+"""
+import numpy as np
+import pytest
+
+import util
+from tmr_b200 import _capi
+from tmr_b200.forest import OctForest, array_contains, array_sort
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def impl(request):
+    return request.getfixturevalue(request.param + "_lib")
+
+
+CASES = [
+    # name, conn, level, passes, pct, corner, order
+    ("single", "single", 2, 3, 30, 0, 2),
+    ("single_corner", "single", 1, 4, 40, 1, 2),
+    ("rectangle", "rectangle", 1, 3, 30, 0, 2),
+    ("box7", "box7", 1, 3, 30, 0, 2),
+    ("box7_corner", "box7", 2, 2, 30, 1, 2),
+    ("connector15", "connector15", 1, 3, 30, 0, 2),
+    ("grid2", "grid2", 1, 3, 35, 0, 2),
+    ("butterfly2", "butterfly2", 1, 2, 30, 1, 2),
+    ("box7_order3", "box7", 1, 2, 30, 1, 3),
+    ("single_order3", "single", 2, 2, 30, 0, 3),
+    ("connector15_order3", "connector15", 0, 3, 40, 0, 3),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_refine_balance_nodes(case, impl, ref_lib):
+    _, conn_name, level, passes, pct, corner, order = case
+    conn = util.CONNS[conn_name]()
+    rec_ref, rec_new = [], []
+    f_ref = util.build_forest(ref_lib, conn, level, passes, pct, corner, order,
+                              record=rec_ref)
+    f_new = util.build_forest(impl, conn, level, passes, pct, corner, order,
+                              record=rec_new)
+    for (name, a), (_, b) in zip(rec_ref, rec_new):
+        util.assert_octants_equal(a, b, name)
+    util.assert_nodes_equal(util.node_results(f_ref), util.node_results(f_new),
+                            case[0])
+
+
+def test_connectivity_tables(impl, ref_lib):
+    """setConnectivity derives identical edge/face numbering, inverse maps,
+    orientation ids (reference src/TMROctForest.cpp:558-1143)."""
+    for name, make in util.CONNS.items():
+        conn = make()
+        a = OctForest(lib=ref_lib)
+        b = OctForest(lib=impl)
+        a.setConnectivity(conn)
+        b.setConnectivity(conn)
+        ca, cb = a.getConnectivity(), b.getConnectivity()
+        for k in ca:
+            assert np.array_equal(ca[k], cb[k]), (name, k)
+        ia, ib = a.getInverseConnectivity(), b.getInverseConnectivity()
+        for k in ia:
+            assert np.array_equal(ia[k], ib[k]), (name, k)
+
+
+def test_refine_negative_and_multilevel(impl, ref_lib):
+    """coarsening flags, multi-level refinement, min/max clamps
+    (reference src/TMROctForest.cpp:2197-2296)."""
+    conn = util.box_conn()
+    rng = np.random.default_rng(7)
+    fa = util.build_forest(ref_lib, conn, 2, 1, 30, 0)
+    fb = util.build_forest(impl, conn, 2, 1, 30, 0)
+    for rnd in range(3):
+        n = fa.getNumOctants()
+        assert n == fb.getNumOctants()
+        flags = rng.integers(-2, 3, n).astype(np.int32)
+        fa.refine(flags, 1, 5)
+        fb.refine(flags, 1, 5)
+        util.assert_octants_equal(fa.getOctants().as_array(),
+                                  fb.getOctants().as_array(), "refine round %d" % rnd)
+        fa.balance(rnd % 2)
+        fb.balance(rnd % 2)
+        util.assert_octants_equal(fa.getOctants().as_array(),
+                                  fb.getOctants().as_array(), "balance round %d" % rnd)
+    util.assert_nodes_equal(util.node_results(fa), util.node_results(fb), "neg")
+
+
+def test_refine_null_everywhere(impl, ref_lib):
+    conn = util.rectangle_conn()
+    fa = util.build_forest(ref_lib, conn, 1, 1, 50, 0)
+    fb = util.build_forest(impl, conn, 1, 1, 50, 0)
+    fa.refine(None, 0, 4)
+    fb.refine(None, 0, 4)
+    util.assert_octants_equal(fa.getOctants().as_array(), fb.getOctants().as_array())
+    fa.balance(1)
+    fb.balance(1)
+    util.assert_octants_equal(fa.getOctants().as_array(), fb.getOctants().as_array())
+
+
+def test_info_survives_refine(impl, ref_lib):
+    """octants kept verbatim by refine() keep the hanging `info` createNodes()
+    wrote (hash stores the record as is, reference :2199,2227)."""
+    conn = util.box_conn()
+    fa = util.build_forest(ref_lib, conn, 1, 2, 30, 0)
+    fb = util.build_forest(impl, conn, 1, 2, 30, 0)
+    fa.createNodes()
+    fb.createNodes()
+    octs = fa.getOctants().as_array()
+    assert octs["info"].any()
+    flags = util.synth_flags(octs, 99, 20)
+    fa.refine(flags)
+    fb.refine(flags)
+    util.assert_octants_equal(fa.getOctants().as_array(), fb.getOctants().as_array())
+
+
+def test_stale_nodes_after_balance(impl, ref_lib):
+    """balance() does not invalidate node data; createNodes() is then a no-op
+    (reference :4071-4075) -- replicated, not fixed."""
+    conn = util.single_conn()
+    fa = util.build_forest(ref_lib, conn, 2, 1, 30, 0)
+    fb = util.build_forest(impl, conn, 2, 1, 30, 0)
+    ra, rb = util.node_results(fa), util.node_results(fb)
+    for f in (fa, fb):
+        f.balance(1)
+        f.createNodes()
+    assert np.array_equal(fa.getMeshConn(), ra["conn"])
+    assert np.array_equal(fb.getMeshConn(), rb["conn"])
+
+
+def test_coarsen_duplicate(impl, ref_lib):
+    conn = util.box_conn()
+    fa = util.build_forest(ref_lib, conn, 2, 2, 30, 1)
+    fb = util.build_forest(impl, conn, 2, 2, 30, 1)
+    da, db = fa.duplicate(), fb.duplicate()
+    util.assert_octants_equal(da.getOctants().as_array(), db.getOctants().as_array())
+    ca, cb = fa.coarsen(), fb.coarsen()
+    util.assert_octants_equal(ca.getOctants().as_array(), cb.getOctants().as_array(),
+                              "coarsen")
+    ca.balance(1)
+    cb.balance(1)
+    util.assert_octants_equal(ca.getOctants().as_array(), cb.getOctants().as_array(),
+                              "coarsen+balance")
+
+
+def _hierarchy(lib, conn, order):
+    """TopOptUtils-style multigrid hierarchy (reference tmr/TopOptUtils.py:79-99)."""
+    f0 = util.build_forest(lib, conn, 1, 2, 30, 1, order=order)
+    forests = [f0]
+    o = order
+    for _ in range(3):
+        prev = forests[-1]
+        if o > 2:
+            nxt = prev.duplicate()
+            o -= 1
+            nxt.setMeshOrder(o)
+        else:
+            nxt = prev.coarsen()
+            nxt.balance(1)
+        forests.append(nxt)
+    interps = []
+    for k in range(len(forests) - 1):
+        interps.append(forests[k].createInterpolation(forests[k + 1]))
+    return forests, interps
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_create_interpolation(order, impl, ref_lib):
+    conn = util.box_conn()
+    fa, ia = _hierarchy(ref_lib, conn, order)
+    fb, ib = _hierarchy(impl, conn, order)
+    for k, (va, vb) in enumerate(zip(ia, ib)):
+        util.assert_interp_equal(va, vb, "level %d" % k)
+        rows, d = util.interp_rows(vb)
+        assert len(rows) == fb[k].getNumOwnedNodes()
+        for r, (c, w) in d.items():
+            assert abs(w.sum() - 1.0) < 1e-13
+
+
+def test_find_enclosing_and_transform(impl, ref_lib):
+    conn = util.box_conn()
+    fa = util.build_forest(ref_lib, conn, 1, 2, 30, 0)
+    fb = util.build_forest(impl, conn, 1, 2, 30, 0)
+    fine_a = util.build_forest(ref_lib, conn, 1, 3, 30, 0)
+    octs = fine_a.getOctants().as_array().copy()
+    rng = np.random.default_rng(3)
+    for order in (2, 3):
+        octs["info"] = rng.integers(0, order ** 3, len(octs))
+        knots = np.array([-1.0, 1.0]) if order == 2 else np.array([-1.0, 0.0, 1.0])
+        ia, _ = fa.findEnclosing(order, knots, octs)
+        ib, _ = fb.findEnclosing(order, knots, octs)
+        assert np.array_equal(ia, ib)
+        assert (ia >= 0).all()
+    # transformNode on every element corner
+    nodes = np.repeat(fine_a.getOctants().as_array(), 8)
+    h = (1 << (30 - nodes["level"].astype(np.int64)))
+    c = np.tile(np.arange(8), len(nodes) // 8)
+    nodes["x"] = nodes["x"] + h * (c & 1)
+    nodes["y"] = nodes["y"] + h * ((c >> 1) & 1)
+    nodes["z"] = nodes["z"] + h * (c >> 2)
+    for edge_dir in (-1, 0, 1, 2):
+        ra, reva, fida = fa.transformNodes(nodes, edge_dir)
+        rb, revb, fidb = fb.transformNodes(nodes, edge_dir)
+        for fld in ("block", "x", "y", "z"):
+            assert np.array_equal(ra[fld], rb[fld])
+        assert np.array_equal(reva, revb)
+        assert np.array_equal(fida, fidb)
+
+
+@pytest.mark.parametrize("node_mode", [0, 1])
+def test_octant_array_sort_contains(node_mode, impl, ref_lib):
+    """TMROctantArray::sort / contains on arbitrary arrays incl. duplicates,
+    nodes at 2^30-1 and negative coordinates (reference src/TMROctant.cpp:357-424)."""
+    rng = np.random.default_rng(11 + node_mode)
+    for n in (0, 1, 2, 33, 1000, 5000):
+        rec = util.random_octants(rng, n, 5, 6)
+        if n >= 33:
+            rec[: n // 4] = rec[n // 4: 2 * (n // 4)]  # duplicates
+            rec["level"][: n // 8] = 6
+            rec["x"][5] = (1 << 30) - 1
+            rec["y"][6] = -(1 << 24)
+        if node_mode:
+            rec["info"] = rng.integers(0, 3, n)
+        a = array_sort(ref_lib, rec, node_mode)
+        b = array_sort(impl, rec, node_mode)
+        assert len(a) == len(b)
+        key = ("block", "x", "y", "z", "info") if node_mode else ("block", "x", "y", "z", "level")
+        for fld in key:
+            assert np.array_equal(a[fld], b[fld]), (n, fld)
+        if n:
+            q = np.concatenate([a[:: max(1, len(a) // 50)], util.random_octants(rng, 20, 5, 6)])
+            for use_pos in (0, 1):
+                ia = array_contains(ref_lib, a, q, node_mode, use_pos)
+                ib = array_contains(impl, b, q, node_mode, use_pos)
+                assert np.array_equal(ia >= 0, ib >= 0)
+                assert np.array_equal(ia, ib)
+
+
+def test_empty_and_level0(impl, ref_lib):
+    """level-0 forests, balance/createNodes on trivial inputs."""
+    for conn in (util.single_conn(), util.box_conn()):
+        fa = OctForest(lib=ref_lib)
+        fb = OctForest(lib=impl)
+        for f in (fa, fb):
+            f.setConnectivity(conn)
+            f.createTrees(0)
+            f.balance(1)
+        util.assert_octants_equal(fa.getOctants().as_array(), fb.getOctants().as_array())
+        util.assert_nodes_equal(util.node_results(fa), util.node_results(fb), "level0")
+        n = fa.getNumOctants()
+        flags = np.zeros(n, dtype=np.int32)
+        flags[0] = 3
+        for f in (fa, fb):
+            f.refine(flags)
+            f.balance(0)
+        util.assert_nodes_equal(util.node_results(fa), util.node_results(fb), "one deep")

@@ -24,8 +24,26 @@ def load_library():
                 "tmr_b200: %s is not built; run `python -c 'import "
                 "__graft_entry__ as g; g.build()'` (there is no CPU fallback)"
                 % LIB_PATH)
-        _LIB = _capi.bind(ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL))
+        _LIB = _capi.bind(ctypes.CDLL(LIB_PATH))
     return _LIB
+
+
+def require_gpu():
+    """Create the process-wide CUDA context now; raise if there is no GPU."""
+    lib = load_library()
+    lib.tmr_b200_context.restype = ctypes.c_void_p
+    if not lib.tmr_b200_context():
+        raise RuntimeError(
+            "tmr_b200: no usable CUDA device (the library has no CPU fallback)")
+    return lib
+
+
+def use_stream(stream_handle):
+    """Run all forest work on this cudaStream_t (e.g. torch's current stream:
+    torch.cuda.current_stream().cuda_stream).  Call before the first forest."""
+    lib = load_library()
+    lib.tmr_b200_use_stream.argtypes = [ctypes.c_void_p]
+    lib.tmr_b200_use_stream(ctypes.c_void_p(stream_handle))
 
 
 from .forest import (  # noqa: E402

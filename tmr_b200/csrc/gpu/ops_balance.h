@@ -307,6 +307,7 @@ inline int balance(Forest &f, int balance_corner) {
   const int bbits = f.bbits;
   const int nb = f.nblocks;
 
+  trace_mark(ctx, NULL);
   /* (a) parents of the input octants, deduplicated against the predecessor */
   DBuf<int> root_flag(ctx, nb);
   dev_zero(ctx, root_flag.get(), (size_t)nb * sizeof(int));
@@ -320,6 +321,7 @@ inline int balance(Forest &f, int balance_corner) {
     ParentFillFn pf = {pk, offset.get(), ckeys.get()};
     launch(ctx, f.n, pf, "balance_parent_fill");
   }
+  trace_mark(ctx, "balance: parents");
   /* (b) sort by (level, block, Morton), dedup, split per level */
   std::vector<DBuf<u64> > R(D);
   std::vector<i64> nR(D, 0);
@@ -341,6 +343,7 @@ inline int balance(Forest &f, int balance_corner) {
     }
   }
   ckeys.reset();
+  trace_mark(ctx, "balance: sort+split");
 
   /* (c) closure, deepest level first */
   for (int l = D - 1; l >= 1; l--) {
@@ -364,6 +367,7 @@ inline int balance(Forest &f, int balance_corner) {
     R[l - 1].swap(merged);
   }
 
+  trace_mark(ctx, "balance: closure");
   /* (e) leaves */
   std::vector<DBuf<u32> > loff(D);
   std::vector<i64> nleaf(D, 0);
@@ -401,12 +405,14 @@ inline int balance(Forest &f, int balance_corner) {
   }
   RootLeafFillFn rf = {rc, root_off.get(), f.fmt, out.get() + base};
   launch(ctx, nb, rf, "balance_root_fill");
+  trace_mark(ctx, "balance: leaf fill");
   /* leaves have distinct anchors: order by (block, Morton) only */
   DBuf<u32> v0, v1;
   radix_sort(ctx, out, out_alt, v0, v1, total, 5, f.fmt.total_bits());
   f.keys.swap(out);
   f.n = total;
   f.last_out = f.n;
+  trace_mark(ctx, "balance: final sort");
   return check_errors(ctx, "balance");
 }
 

@@ -503,6 +503,41 @@ struct ConnRemapInPlaceFn {
   TMR_HD void operator()(i64 j) const { conn[j] = node_num[conn[j]]; }
 };
 
+/* node numbers as sortable unsigned keys and back */
+struct NumToKeyFn {
+  const int *num;
+  u64 *keys;
+  TMR_HD void operator()(i64 i) const {
+    keys[i] = (u64)((u32)num[i] ^ 0x80000000u);
+  }
+};
+struct KeyToNumFn {
+  const u64 *keys;
+  int *num;
+  TMR_HD void operator()(i64 i) const {
+    num[i] = (int)((u32)keys[i] ^ 0x80000000u);
+  }
+};
+
+/* getNodeNumbers(): every local node number, ascending (reference :4246) */
+inline int sorted_node_numbers(Forest &f, int *h_out) {
+  Ctx &ctx = *f.ctx;
+  NodeData &nd = f.nodes;
+  const i64 n = nd.num_local_nodes;
+  if (!nd.valid) return 1;
+  if (n == 0) return 0;
+  DBuf<u64> k(ctx, n), k_alt(ctx, n);
+  DBuf<u32> v0, v1;
+  NumToKeyFn a = {nd.node_num.get(), k.get()};
+  launch(ctx, n, a, "nodes_numbers_to_keys");
+  radix_sort(ctx, k, k_alt, v0, v1, n, 0, 32);
+  DBuf<int> out(ctx, n);
+  KeyToNumFn b = {k.get(), out.get()};
+  launch(ctx, n, b, "nodes_keys_to_numbers");
+  copy_d2h(ctx, h_out, out.get(), (size_t)n * sizeof(int));
+  return check_errors(ctx, "sorted_node_numbers");
+}
+
 inline int create_nodes(Forest &f, int order, int interp_type,
                         const double *knots) {
   Ctx &ctx = *f.ctx;
@@ -545,12 +580,14 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     return 0;
   }
 
+  trace_mark(ctx, NULL);
   /* 1. hanging faces / edges */
   if (!f.info.get()) f.info.alloc(ctx, E);
   ElemView ev = {f.keys.get(), E, f.fmt, f.tables};
   HangingFn hang = {ev, f.info.get()};
   launch(ctx, E, hang, "nodes_hanging_info");
 
+  trace_mark(ctx, "nodes: hanging info");
   /* 2. node candidates -> sort -> unique nodes + local connectivity */
   const i64 nc = E * npe;
   nd.conn.alloc(ctx, nc);
@@ -561,7 +598,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     NodeCandFn cand = {f.keys.get(), f.fmt, nd.nfmt, f.tables,
                        order,        ck.get(), cv.get()};
     launch(ctx, nc, cand, "nodes_candidates");
+    trace_mark(ctx, "nodes: candidates");
     radix_sort(ctx, ck, ck_alt, cv, cv_alt, nc, 0, nd.nfmt.total_bits());
+    trace_mark(ctx, "nodes: sort");
     DBuf<u32> heads(ctx, nc);
     RunHeadFn rh = {ck.get()};
     Nn = (i64)scan_counts(ctx, nc, rh, heads.get(), "nodes_run_heads");
@@ -571,6 +610,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     launch(ctx, nc, sc, "nodes_scatter_conn");
   }
   nd.num_local_nodes = Nn;
+  trace_mark(ctx, "nodes: unique+conn");
 
   /* 3. dependent labels and numbering */
   DBuf<unsigned char> dep_flag(ctx, Nn);
@@ -590,6 +630,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
                        nd.node_num.get(), dep_node.get()};
   launch(ctx, Nn, num, "nodes_number");
 
+  trace_mark(ctx, "nodes: label+number");
   /* 4. dependent-node CSR */
   nd.dep_ptr.alloc(ctx, Nd + 1);
   if (Nd > 0) {
@@ -629,10 +670,12 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     nd.dep_nnz = 0;
   }
 
+  trace_mark(ctx, "nodes: dep CSR");
   /* 5. local -> global numbers in the connectivity */
   ConnRemapInPlaceFn rm = {nd.node_num.get(), nd.conn.get()};
   launch(ctx, nc, rm, "nodes_conn_remap");
   nd.valid = true;
+  trace_mark(ctx, "nodes: conn remap");
   return check_errors(ctx, "create_nodes");
 }
 

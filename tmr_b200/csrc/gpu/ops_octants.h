@@ -168,7 +168,8 @@ inline int upload_octants(Forest &f, const Oct24 *h_recs, i64 n) {
             f.nblocks, D);
     return 1;
   }
-  f.nodes.clear();
+  /* node data is deliberately left alone: writing octants through the
+     borrowed array does not invalidate nodes in the reference either */
   f.fmt.D = D;
   f.fmt.bbits = f.bbits;
   f.n = n;
@@ -312,6 +313,7 @@ inline int refine(Forest &f, const int *d_flags, int min_level, int max_level) {
   f.last_in = f.n;
   if (f.n == 0) return 0;
 
+  trace_mark(ctx, NULL);
   DBuf<int> scalars(ctx, 2);
   dev_zero(ctx, scalars.get(), 2 * sizeof(int));
   DBuf<u32> offset(ctx, f.n);
@@ -355,6 +357,7 @@ inline int refine(Forest &f, const int *d_flags, int min_level, int max_level) {
   copy_d2h(ctx, h_scalars, scalars.get(), 2 * sizeof(int));
   if (h_scalars[1]) sort_unique_elements(f);
   f.last_mid = f.n;
+  trace_mark(ctx, "refine");
   return check_errors(ctx, "refine");
 }
 

@@ -40,12 +40,19 @@ struct Ctx {
   std::vector<void *> ev_start, ev_stop;
   std::vector<std::string> ev_name;
   std::string last_error;
-  Ctx() : device(0), stream(NULL), profile(0), num_sms(148), launch_count(0) {}
+  int trace;        /* TMR_B200_TRACE=1: print synchronised phase times */
+  double trace_t0;  /* wall clock of the previous mark (s) */
+  Ctx()
+      : device(0), stream(NULL), profile(0), num_sms(148), launch_count(0),
+        trace(0), trace_t0(0.0) {}
 };
 
 /* --- runtime (prim_cuda.cu / tests/emu/prim_emu.cpp) ---------------------- */
 void *dev_alloc(Ctx &ctx, size_t bytes);
 void dev_free(Ctx &ctx, void *p);
+void dev_cache_destroy(Ctx &ctx); /* return every cached block to the driver */
+void *host_alloc(Ctx &ctx, size_t bytes); /* page-locked, cached */
+void host_free(Ctx &ctx, void *p);
 void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes);
 void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes); /* syncs */
 void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes);
@@ -58,6 +65,8 @@ int check_errors(Ctx &ctx, const char *where);
 void prof_begin(Ctx &ctx, const char *name);
 void prof_end(Ctx &ctx);
 void prof_resolve(Ctx &ctx);
+/* when tracing: synchronise and print the wall time since the last mark */
+void trace_mark(Ctx &ctx, const char *label);
 
 /* Owning, move-only device array */
 template <class T>

@@ -259,6 +259,10 @@ int tmrgpu_download_nodes(tmrgpu_forest *F, int *conn, int *node_numbers,
   return check_errors(ctx, "download_nodes");
 }
 
+int tmrgpu_download_sorted_node_numbers(tmrgpu_forest *f, int *out) {
+  return sorted_node_numbers(f->f, out);
+}
+
 int tmrgpu_create_interp(tmrgpu_forest *fine, tmrgpu_forest *coarse,
                          int64_t *nrows, int64_t *nnz) {
   const int rc = create_interp(fine->f, coarse->f);
@@ -321,6 +325,61 @@ int tmrgpu_dev_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out) {
 
 int tmrgpu_dev_free(tmrgpu_ctx *ctx, void *p) {
   dev_free(ctx->c, p);
+  return 0;
+}
+
+namespace {
+struct CopyCountFn {
+  const u32 *in;
+  TMR_HD u32 operator()(i64 i) const { return in[i]; }
+};
+}  // namespace
+
+int tmrgpu_test_radix_sort(tmrgpu_ctx *ctx, uint64_t *keys, uint32_t *vals,
+                           int64_t n, int bit_lo, int bit_hi) {
+  Ctx &c = ctx->c;
+  DBuf<u64> k(c, n), ka(c, n);
+  DBuf<u32> v, va;
+  copy_h2d(c, k.get(), keys, (size_t)n * sizeof(u64));
+  if (vals) {
+    v.alloc(c, n);
+    va.alloc(c, n);
+    copy_h2d(c, v.get(), vals, (size_t)n * sizeof(u32));
+  }
+  radix_sort(c, k, ka, v, va, n, bit_lo, bit_hi);
+  copy_d2h(c, keys, k.get(), (size_t)n * sizeof(u64));
+  if (vals) copy_d2h(c, vals, v.get(), (size_t)n * sizeof(u32));
+  return check_errors(c, "test_radix_sort");
+}
+
+int tmrgpu_test_scan(tmrgpu_ctx *ctx, const uint32_t *counts, int64_t n,
+                     uint32_t *out_exclusive, uint64_t *total) {
+  Ctx &c = ctx->c;
+  DBuf<u32> in(c, n), out(c, n);
+  copy_h2d(c, in.get(), counts, (size_t)n * sizeof(u32));
+  CopyCountFn f = {in.get()};
+  *total = scan_counts(c, n, f, out.get(), "test_scan");
+  copy_d2h(c, out_exclusive, out.get(), (size_t)n * sizeof(u32));
+  return check_errors(c, "test_scan");
+}
+
+int tmrgpu_host_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out) {
+  *out = host_alloc(ctx->c, (size_t)bytes);
+  return *out ? 0 : 1;
+}
+
+int tmrgpu_host_free(tmrgpu_ctx *ctx, void *p) {
+  host_free(ctx->c, p);
+  return 0;
+}
+
+int tmrgpu_copy_d2h(tmrgpu_ctx *ctx, void *dst, const void *src, int64_t bytes) {
+  copy_d2h(ctx->c, dst, src, (size_t)bytes);
+  return 0;
+}
+
+int tmrgpu_copy_h2d(tmrgpu_ctx *ctx, void *dst, const void *src, int64_t bytes) {
+  copy_h2d(ctx->c, dst, src, (size_t)bytes);
   return 0;
 }
 

@@ -346,13 +346,30 @@ void TMROctForest::dropTables() {
   tables = NULL;
 }
 
+/* host mirrors of the node arrays live in page-locked memory handed out by
+   the CUDA layer (cached there), so reading them back runs at PCIe speed */
+template <class T>
+static T *mirror_alloc(size_t n) {
+  void *p = NULL;
+  tmrgpu_ctx *ctx = tmr_b200_context();
+  if (!ctx || tmrgpu_host_alloc(ctx, (int64_t)((n + 1) * sizeof(T)), &p)) {
+    return NULL;
+  }
+  return static_cast<T *>(p);
+}
+
+static void mirror_free(void *p) {
+  tmrgpu_ctx *ctx = tmr_b200_context();
+  if (p && ctx) tmrgpu_host_free(ctx, p);
+}
+
 void TMROctForest::dropHostNodeMirrors() {
-  delete[] conn;
-  delete[] node_numbers;
+  mirror_free(conn);
+  mirror_free(node_numbers);
   delete[] node_range;
-  delete[] dep_ptr;
-  delete[] dep_conn;
-  delete[] dep_weights;
+  mirror_free(dep_ptr);
+  mirror_free(dep_conn);
+  mirror_free(dep_weights);
   delete[] X;
   conn = node_numbers = node_range = NULL;
   dep_ptr = dep_conn = NULL;
@@ -674,13 +691,14 @@ void TMROctForest::fetchNodeData() {
   num_dep_nodes = (int)s[2];
   num_owned_nodes = (int)s[3];
   const int nnz = (int)s[4];
-  conn = new int[(size_t)num_elements_nodes * npe + 1];
-  node_numbers = new int[num_local_nodes + 1];
-  dep_ptr = new int[num_dep_nodes + 1];
-  dep_conn = new int[nnz + 1];
-  dep_weights = new double[nnz + 1];
-  tmrgpu_download_nodes(dev, conn, node_numbers, dep_ptr, dep_conn,
-                        dep_weights);
+  conn = mirror_alloc<int>((size_t)num_elements_nodes * npe);
+  node_numbers = mirror_alloc<int>(num_local_nodes);
+  dep_ptr = mirror_alloc<int>(num_dep_nodes + 1);
+  dep_conn = mirror_alloc<int>(nnz);
+  dep_weights = mirror_alloc<double>(nnz);
+  tmrgpu_download_nodes(dev, conn, NULL, dep_ptr, dep_conn, dep_weights);
+  /* the reference hands out node_numbers sorted ascending (:4246) */
+  tmrgpu_download_sorted_node_numbers(dev, node_numbers);
   /* node_range: owned-node prefix over ranks (reference :4165-4172) */
   node_range = new int[mpi_size + 1];
   std::fill(node_range, node_range + mpi_size + 1, 0);
@@ -688,14 +706,9 @@ void TMROctForest::fetchNodeData() {
     node_range[r] = (int)s[5] + num_owned_nodes;
   }
   for (int r = 0; r <= mpi_rank; r++) node_range[r] = (int)s[5];
-  /* the reference hands out node_numbers sorted ascending (:4246) */
-  std::sort(node_numbers, node_numbers + num_local_nodes);
   int *item = std::lower_bound(node_numbers, node_numbers + num_local_nodes,
                                node_range[mpi_rank]);
   ext_pre_offset = (int)(item - node_numbers);
-  /* no CAD topology => node locations are zero (reference :5526-5539) */
-  X = new TMRPoint[num_local_nodes + 1];
-  for (int i = 0; i < num_local_nodes; i++) X[i].zero();
   nodes_on_host = 1;
 }
 
@@ -738,6 +751,12 @@ int TMROctForest::getExtPreOffset() {
 
 int TMROctForest::getPoints(TMRPoint **_X) {
   fetchNodeData();
+  if (!X && nodes_on_host) {
+    /* no CAD topology => node locations are zero (reference :5526-5539);
+       materialised on first request */
+    X = new TMRPoint[num_local_nodes + 1];
+    for (int i = 0; i < num_local_nodes; i++) X[i].zero();
+  }
   if (_X) *_X = X;
   return num_local_nodes;
 }
