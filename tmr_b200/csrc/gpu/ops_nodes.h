@@ -29,14 +29,48 @@
 
 namespace tmrgpu {
 
+/* build table[p] = lower_bound(keys, p << shift) for p in [0, nprefix] */
+struct BuildIndexFn {
+  const u64 *keys;
+  i64 n;
+  int shift;
+  u64 nprefix;
+  u32 *table;
+  TMR_HD void operator()(i64 p) const {
+    table[p] = ((u64)p >= nprefix) ? (u32)n
+                                   : (u32)lower_bound_u64(keys, n, (u64)p << shift);
+  }
+};
+
+/* index over a sorted key array whose keys are < key_limit; at most 2^22
+   buckets (16 MB of u32, L2-resident) */
+inline KeyIndex build_key_index(Ctx &ctx, const u64 *keys, i64 n, u64 key_limit,
+                                DBuf<u32> &store) {
+  int shift = 0;
+  while ((key_limit >> shift) > (1ULL << 22)) shift++;
+  KeyIndex ix;
+  ix.shift = shift;
+  ix.nprefix = (key_limit >> shift) + 1;
+  store.alloc(ctx, (i64)ix.nprefix + 1);
+  BuildIndexFn b = {keys, n, shift, ix.nprefix, store.get()};
+  launch(ctx, (i64)ix.nprefix + 1, b, "build_key_index");
+  ix.table = store.get();
+  return ix;
+}
+
 struct ElemView {
   const u64 *keys;
   i64 n;
   KeyFmt fmt;
   ConnTables t;
+  KeyIndex ix;
 
   TMR_HD bool leaf_exists(i32 block, i32 x, i32 y, i32 z, int level) const {
-    return find_u64(keys, n, fmt.encode(block, x, y, z, level)) >= 0;
+    return ix.find(keys, fmt.encode(block, x, y, z, level)) >= 0;
+  }
+  TMR_HD bool leaf_exists_near(i32 block, i32 x, i32 y, i32 z, int level,
+                               i64) const {
+    return leaf_exists(block, x, y, z, level);
   }
   /* is there a level-`level` leaf in another tree that is the image of the
      out-of-tree octant (x,y,z) across face f?  (reference checkAdjacentFaces
@@ -128,7 +162,7 @@ struct HangingFn {
       const i32 c = (k == 0) ? nx : (k == 1 ? ny : nz);
       bool hit;
       if (c >= 0 && c < kHmax) {
-        hit = ev.leaf_exists(block, nx, ny, nz, pl);
+        hit = ev.leaf_exists_near(block, nx, ny, nz, pl, i);
       } else {
         hit = ev.across_face(f, block, nx, ny, nz, pl);
       }
@@ -150,7 +184,7 @@ struct HangingFn {
                       oz * (nz < 0 ? 4 : 5);
         hit = ev.across_face(f, block, nx, ny, nz, pl);
       } else {
-        hit = ev.leaf_exists(block, nx, ny, nz, pl);
+        hit = ev.leaf_exists_near(block, nx, ny, nz, pl, i);
       }
       if (hit) bits |= 1 << (k + 3);
     }
@@ -191,8 +225,10 @@ TMR_HD int face_node_offset(int order, int f, int p, int q) {
   return p + q * order + n * order * order;
 }
 
-/* canonical node key of element node (ii,jj,kk) -- createLocalNodes +
-   transformNode (reference :4290-4372, :3847-4039) */
+/* canonical node keys of the order^3 nodes of one element -- createLocalNodes
+   + transformNode (reference :4290-4372, :3847-4039).  One thread per
+   element: the key is decoded once and the per-axis bit-interleaves are shared
+   by all nodes; only elements touching a tree boundary take the transform. */
 struct NodeCandFn {
   const u64 *keys;
   KeyFmt fmt;
@@ -201,21 +237,48 @@ struct NodeCandFn {
   int order;
   u64 *out_keys;
   u32 *out_vals;
-  TMR_HD void operator()(i64 c) const {
+  TMR_HD void operator()(i64 e) const {
     const int npe = order * order * order;
-    const i64 e = c / npe;
-    const int s = (int)(c % npe);
-    const int ii = s % order, jj = (s / order) % order, kk = s / (order * order);
     i32 block, x, y, z;
     int level;
     fmt.decode(keys[e], &block, &x, &y, &z, &level);
-    const i32 step = (1 << (kMaxLevel - level)) / (order - 1);
-    x += ii * step;
-    y += jj * step;
-    z += kk * step;
-    transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
-    out_keys[c] = nfmt.encode(block, x, y, z);
-    out_vals[c] = (u32)c;
+    const i32 h = 1 << (kMaxLevel - level);
+    const i32 step = h / (order - 1);
+    u64 *ok = out_keys + e * npe;
+    u32 *ov = out_vals + e * npe;
+    const bool interior = x > 0 && y > 0 && z > 0 && x + h < kHmax &&
+                          y + h < kHmax && z + h < kHmax;
+    if (interior) {
+      u64 sx[kMaxOrder], sy[kMaxOrder], sz[kMaxOrder];
+      for (int a = 0; a < order; a++) {
+        sx[a] = spread3(nfmt.squeeze(x + a * step)) << 2;
+        sy[a] = spread3(nfmt.squeeze(y + a * step)) << 1;
+        sz[a] = spread3(nfmt.squeeze(z + a * step));
+      }
+      const u64 hi = (u64)(u32)block << (3 * (nfmt.Dn + 1));
+      int s = 0;
+      for (int kk = 0; kk < order; kk++) {
+        for (int jj = 0; jj < order; jj++) {
+          for (int ii = 0; ii < order; ii++, s++) {
+            ok[s] = hi | sx[ii] | sy[jj] | sz[kk];
+            ov[s] = (u32)(e * npe + s);
+          }
+        }
+      }
+    } else {
+      int s = 0;
+      for (int kk = 0; kk < order; kk++) {
+        for (int jj = 0; jj < order; jj++) {
+          for (int ii = 0; ii < order; ii++, s++) {
+            i32 b = block, nx = x + ii * step, ny = y + jj * step,
+                nz = z + kk * step;
+            transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
+            ok[s] = nfmt.encode(b, nx, ny, nz);
+            ov[s] = (u32)(e * npe + s);
+          }
+        }
+      }
+    }
   }
 };
 
@@ -405,9 +468,13 @@ struct DepFillFn {
   int *dep_conn;
   double *dep_weights;
 
-  TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z) const {
+  const int *dep_node; /* dependent index -> node index (search hint) */
+
+  KeyIndex node_ix;
+
+  TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, i64) const {
     transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
-    const i64 idx = find_u64(node_keys, num_nodes, nfmt.encode(block, x, y, z));
+    const i64 idx = node_ix.find(node_keys, nfmt.encode(block, x, y, z));
     return idx >= 0 ? node_num[idx] : 0;
   }
 
@@ -438,7 +505,7 @@ struct DepFillFn {
         } else {
           nx = px + ta; ny = py + tb; nz = pz + ii * step;
         }
-        dep_conn[ptr + ii] = lookup(block, nx, ny, nz);
+        dep_conn[ptr + ii] = lookup(block, nx, ny, nz, dep_node[d]);
       }
       const int bit = (id >> (ed >> 2)) & 1;
       const double u = 1.0 * (bit - 1) + 0.5 * (1.0 + knots[k]);
@@ -469,7 +536,7 @@ struct DepFillFn {
           } else {
             nx = px + p * step; ny = py + q * step; nz = pz + nn;
           }
-          dep_conn[ptr + p + q * order] = lookup(block, nx, ny, nz);
+          dep_conn[ptr + p + q * order] = lookup(block, nx, ny, nz, dep_node[d]);
         }
       }
       /* child bits along the face's first / second in-face axis */
@@ -583,7 +650,10 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   trace_mark(ctx, NULL);
   /* 1. hanging faces / edges */
   if (!f.info.get()) f.info.alloc(ctx, E);
-  ElemView ev = {f.keys.get(), E, f.fmt, f.tables};
+  DBuf<u32> elem_index_store;
+  const KeyIndex elem_ix = build_key_index(
+      ctx, f.keys.get(), E, (u64)f.nblocks << (3 * f.fmt.D + 5), elem_index_store);
+  ElemView ev = {f.keys.get(), E, f.fmt, f.tables, elem_ix};
   HangingFn hang = {ev, f.info.get()};
   launch(ctx, E, hang, "nodes_hanging_info");
 
@@ -597,7 +667,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     DBuf<u32> cv(ctx, nc), cv_alt(ctx, nc);
     NodeCandFn cand = {f.keys.get(), f.fmt, nd.nfmt, f.tables,
                        order,        ck.get(), cv.get()};
-    launch(ctx, nc, cand, "nodes_candidates");
+    launch(ctx, E, cand, "nodes_candidates");
     trace_mark(ctx, "nodes: candidates");
     radix_sort(ctx, ck, ck_alt, cv, cv_alt, nc, 0, nd.nfmt.total_bits());
     trace_mark(ctx, "nodes: sort");
@@ -649,7 +719,11 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     nd.dep_nnz = (i64)nnz;
     nd.dep_conn.alloc(ctx, (i64)nnz);
     nd.dep_weights.alloc(ctx, (i64)nnz);
+    DBuf<u32> node_index_store;
     DepFillFn fill;
+    fill.node_ix = build_key_index(ctx, nd.node_keys.get(), Nn,
+                                   (u64)f.nblocks << (3 * (nd.nfmt.Dn + 1)),
+                                   node_index_store);
     fill.keys = f.keys.get();
     fill.fmt = f.fmt;
     fill.nfmt = nd.nfmt;
@@ -661,6 +735,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.node_num = nd.node_num.get();
     fill.win_edge = win_edge.get();
     fill.win_face = win_face.get();
+    fill.dep_node = dep_node.get();
     fill.dep_ptr = nd.dep_ptr.get();
     fill.dep_conn = nd.dep_conn.get();
     fill.dep_weights = nd.dep_weights.get();

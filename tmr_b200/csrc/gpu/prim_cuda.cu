@@ -259,14 +259,15 @@ void trace_mark(Ctx &ctx, const char *label) {
 /* ------------------------------------------------------------------------ */
 static const int kRadixBits = 8;
 static const int kRadix = 1 << kRadixBits;
-static const int kSortThreads = 256;
+static const int kHistThreads = 256;
+static const int kSortThreads = 512;
 static const int kSortWarps = kSortThreads / 32;
-static const int kSortItems = 16;
+static const int kSortItems = 8;
 static const int kSortTile = kSortThreads * kSortItems; /* 4096 keys */
 static const int kMaxPasses = 8;
 
 /* One read of the keys -> digit histograms of every pass. */
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kHistThreads)
     radix_hist_kernel(const u64 *__restrict__ keys, i64 n, int bit_lo,
                       int bit_hi, int npass, u32 *__restrict__ ghist) {
   __shared__ u32 s_hist[kMaxPasses * kRadix];
@@ -314,8 +315,11 @@ __global__ void radix_scan_hist_kernel(u32 *ghist) {
   h[threadIdx.x] = s[threadIdx.x] - v;
 }
 
+/* One 8-bit pass.  512 threads x 8 keys: 16 warps per CTA and <= 64 registers
+   so that two CTAs (32 warps) are resident per SM and the load / rank /
+   look-back / scatter phases of different CTAs overlap. */
 template <bool kHasVals>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 2)
     radix_pass_kernel(const u64 *__restrict__ kin, u64 *__restrict__ kout,
                       const u32 *__restrict__ vin, u32 *__restrict__ vout,
                       i64 n, int shift, int bits,
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(kSortThreads)
   u32 *s_dbase = s_whist + kSortWarps * kRadix;               /* [256] */
   u64 *s_goff = reinterpret_cast<u64 *>(s_dbase + kRadix);    /* [256] */
   __shared__ u32 s_tile;
-  __shared__ u32 s_wsum[kSortWarps];
+  __shared__ u32 s_wsum[kRadix / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -368,53 +372,54 @@ __global__ void __launch_bounds__(kSortThreads)
   }
   __syncthreads();
 
-  /* (3) per digit (thread t owns digit t): warp bases, tile count */
-  u32 count = 0;
-#pragma unroll
-  for (int w = 0; w < kSortWarps; w++) {
-    const u32 c = s_whist[w * kRadix + tid];
-    s_whist[w * kRadix + tid] = count;
-    count += c;
-  }
+  /* (3) per digit (threads 0..255 own one digit each): warp bases, tile count,
+     descriptor, look-back */
+  u32 count = 0, incl = 0;
   u64 *my_desc = lookback + (size_t)tile * kRadix + tid;
-  if (tile == 0) {
-    st_relaxed_u64(my_desc, kStatusPrefix | (u64)count);
-  } else {
-    st_relaxed_u64(my_desc, kStatusAgg | (u64)count);
-  }
-  /* exclusive scan of the 256 tile counts -> position of each digit run in
-     the staged tile */
-  u32 incl = count;
+  if (tid < kRadix) {
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    u32 up = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += up;
-  }
-  if (lane == 31) s_wsum[warp] = incl;
-  __syncthreads();
-  u32 woff = 0;
-#pragma unroll
-  for (int w = 0; w < kSortWarps; w++) {
-    if (w < warp) woff += s_wsum[w];
-  }
-  const u32 dbase = woff + incl - count;
-  s_dbase[tid] = dbase;
-  /* decoupled look-back for digit `tid` */
-  u64 excl = 0;
-  if (tile > 0) {
-    i64 p = (i64)tile - 1;
-    while (true) {
-      const u64 v = ld_relaxed_u64(lookback + (size_t)p * kRadix + tid);
-      const u64 st = v & kStatusMask;
-      if (st == 0) continue;
-      excl += v & ~kStatusMask;
-      if (st == kStatusPrefix) break;
-      p--;
+    for (int w = 0; w < kSortWarps; w++) {
+      const u32 c = s_whist[w * kRadix + tid];
+      s_whist[w * kRadix + tid] = count;
+      count += c;
     }
-    st_relaxed_u64(my_desc, kStatusPrefix | (excl + (u64)count));
+    st_relaxed_u64(my_desc, (tile == 0 ? kStatusPrefix : kStatusAgg) | (u64)count);
+    /* exclusive scan of the 256 tile counts -> position of each digit run in
+       the staged tile */
+    incl = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
   }
-  /* global index of staged position q holding digit d: goff[d] + q */
-  s_goff[tid] = (u64)pass_offset[tid] + excl - (u64)dbase;
+  __syncthreads();
+  if (tid < kRadix) {
+    u32 woff = 0;
+#pragma unroll
+    for (int w = 0; w < kRadix / 32; w++) {
+      if (w < warp) woff += s_wsum[w];
+    }
+    const u32 dbase = woff + incl - count;
+    s_dbase[tid] = dbase;
+    /* decoupled look-back for digit `tid` */
+    u64 excl = 0;
+    if (tile > 0) {
+      i64 p = (i64)tile - 1;
+      while (true) {
+        const u64 v = ld_relaxed_u64(lookback + (size_t)p * kRadix + tid);
+        const u64 st = v & kStatusMask;
+        if (st == 0) continue;
+        excl += v & ~kStatusMask;
+        if (st == kStatusPrefix) break;
+        p--;
+      }
+      st_relaxed_u64(my_desc, kStatusPrefix | (excl + (u64)count));
+    }
+    /* global index of staged position q holding digit d: goff[d] + q */
+    s_goff[tid] = (u64)pass_offset[tid] + excl - (u64)dbase;
+  }
   __syncthreads();
 
   /* (4) stage in digit order, then write out coalesced */
@@ -486,7 +491,7 @@ void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
     const int lo = bit_lo + done * kRadixBits;
     dev_zero(ctx, scratch, hist_bytes + ticket_bytes);
     prof_begin(ctx, "radix_hist");
-    radix_hist_kernel<<<grid_for(ctx, n, kSortThreads * 4, 8), kSortThreads, 0,
+    radix_hist_kernel<<<grid_for(ctx, n, kHistThreads * 4, 8), kHistThreads, 0,
                         st>>>(keys.get(), n, lo, bit_hi, chunk, ghist);
     radix_scan_hist_kernel<<<chunk, kRadix, 0, st>>>(ghist);
     prof_end(ctx);
