@@ -33,5 +33,17 @@ u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *) {
   return run;
 }
 
+template <class F, class G>
+u64 scan_apply(Ctx &ctx, i64 n, F f, G g, const char *) {
+  u64 run = 0;
+  for (i64 i = 0; i < n; i++) {
+    const u32 c = f(i);
+    g(i, (u32)run);
+    run += c;
+  }
+  ctx.launch_count++;
+  return run;
+}
+
 }  // namespace tmrgpu
 #endif

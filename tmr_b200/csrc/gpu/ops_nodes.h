@@ -293,12 +293,12 @@ struct RunHeadFn {
 struct NodeScatterFn {
   const u64 *keys;
   const u32 *vals;
-  const u32 *heads_before; /* exclusive scan of run heads */
   u64 *node_keys;
   int *conn_local;
-  TMR_HD void operator()(i64 i) const {
+  /* heads_before = exclusive scan of run heads */
+  TMR_HD void operator()(i64 i, u32 heads_before) const {
     const bool head = (i == 0 || keys[i] != keys[i - 1]);
-    const u32 run = heads_before[i] + (head ? 1u : 0u) - 1u;
+    const u32 run = heads_before + (head ? 1u : 0u) - 1u;
     if (head) node_keys[run] = keys[i];
     conn_local[vals[i]] = (int)run;
   }
@@ -671,13 +671,13 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     trace_mark(ctx, "nodes: candidates");
     radix_sort(ctx, ck, ck_alt, cv, cv_alt, nc, 0, nd.nfmt.total_bits());
     trace_mark(ctx, "nodes: sort");
-    DBuf<u32> heads(ctx, nc);
+    /* the number of unique nodes is not known before the scan: node keys are
+       written into the (now free) ping-pong buffer and trimmed afterwards */
     RunHeadFn rh = {ck.get()};
-    Nn = (i64)scan_counts(ctx, nc, rh, heads.get(), "nodes_run_heads");
+    NodeScatterFn sc = {ck.get(), cv.get(), ck_alt.get(), nd.conn.get()};
+    Nn = (i64)scan_apply(ctx, nc, rh, sc, "nodes_unique_scatter_conn");
     nd.node_keys.alloc(ctx, Nn);
-    NodeScatterFn sc = {ck.get(), cv.get(), heads.get(), nd.node_keys.get(),
-                        nd.conn.get()};
-    launch(ctx, nc, sc, "nodes_scatter_conn");
+    copy_d2d(ctx, nd.node_keys.get(), ck_alt.get(), (size_t)Nn * sizeof(u64));
   }
   nd.num_local_nodes = Nn;
   trace_mark(ctx, "nodes: unique+conn");

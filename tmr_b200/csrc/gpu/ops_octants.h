@@ -89,14 +89,12 @@ struct RunTailFn {
 struct CompactFn {
   const u64 *keys;
   const u32 *vals; /* optional */
-  const u32 *offset;
   i64 n;
   int shift;
   u64 *out_keys;
   u32 *out_vals;
-  TMR_HD void operator()(i64 i) const {
+  TMR_HD void operator()(i64 i, u32 o) const {
     if (i == n - 1 || (keys[i] >> shift) != (keys[i + 1] >> shift)) {
-      const u32 o = offset[i];
       out_keys[o] = keys[i];
       if (vals) out_vals[o] = vals[i];
     }
@@ -108,12 +106,9 @@ inline i64 unique_keep_last(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
                             DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n,
                             int shift) {
   if (n <= 0) return 0;
-  DBuf<u32> offset(ctx, n);
   RunTailFn tail = {keys.get(), n, shift};
-  const i64 m = (i64)scan_counts(ctx, n, tail, offset.get(), "unique_scan");
-  CompactFn c = {keys.get(),     vals.get(), offset.get(),  n,
-                 shift,          keys_alt.get(), vals_alt.get()};
-  launch(ctx, n, c, "unique_compact");
+  CompactFn c = {keys.get(), vals.get(), n, shift, keys_alt.get(), vals_alt.get()};
+  const i64 m = (i64)scan_apply(ctx, n, tail, c, "unique_compact");
   keys.swap(keys_alt);
   if (vals.get()) vals.swap(vals_alt);
   return m;

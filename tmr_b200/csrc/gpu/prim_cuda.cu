@@ -257,8 +257,8 @@ void trace_mark(Ctx &ctx, const char *label) {
 /* ------------------------------------------------------------------------ */
 /* radix sort                                                               */
 /* ------------------------------------------------------------------------ */
-static const int kRadixBits = 8;
-static const int kRadix = 1 << kRadixBits;
+static const int kMaxRadixBits = 9;           /* up to 512 digits per pass */
+static const int kMaxRadix = 1 << kMaxRadixBits;
 static const int kHistThreads = 256;
 static const int kSortThreads = 512;
 static const int kSortWarps = kSortThreads / 32;
@@ -266,12 +266,20 @@ static const int kSortItems = 8;
 static const int kSortTile = kSortThreads * kSortItems; /* 4096 keys */
 static const int kMaxPasses = 8;
 
+struct PassPlan {
+  int npass;
+  int shift[kMaxPasses];
+  int bits[kMaxPasses];
+};
+
 /* One read of the keys -> digit histograms of every pass. */
 __global__ void __launch_bounds__(kHistThreads)
-    radix_hist_kernel(const u64 *__restrict__ keys, i64 n, int bit_lo,
-                      int bit_hi, int npass, u32 *__restrict__ ghist) {
-  __shared__ u32 s_hist[kMaxPasses * kRadix];
-  for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) s_hist[i] = 0;
+    radix_hist_kernel(const u64 *__restrict__ keys, i64 n, PassPlan plan,
+                      u32 *__restrict__ ghist) {
+  __shared__ u32 s_hist[kMaxPasses * kMaxRadix];
+  for (int i = threadIdx.x; i < plan.npass * kMaxRadix; i += blockDim.x) {
+    s_hist[i] = 0;
+  }
   __syncthreads();
   const i64 stride = (i64)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -280,33 +288,30 @@ __global__ void __launch_bounds__(kHistThreads)
        i += stride) {
     const bool valid = i < n;
     const u64 k = valid ? keys[i] : 0;
-    for (int p = 0; p < npass; p++) {
-      const int shift = bit_lo + p * kRadixBits;
-      const int bits = min(kRadixBits, bit_hi - shift);
-      const u32 d = (u32)(k >> shift) & ((1u << bits) - 1u);
+    for (int p = 0; p < plan.npass; p++) {
+      const u32 d = (u32)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
       /* warp-aggregated increment: one shared atomic per distinct digit */
       const u32 peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
       if (valid && lane == (__ffs(peers) - 1)) {
-        atomicAdd(&s_hist[p * kRadix + d], __popc(peers));
+        atomicAdd(&s_hist[p * kMaxRadix + d], __popc(peers));
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) {
+  for (int i = threadIdx.x; i < plan.npass * kMaxRadix; i += blockDim.x) {
     const u32 v = s_hist[i];
     if (v) atomicAdd(&ghist[i], v);
   }
 }
 
-/* exclusive scan of each pass's 256 bins (one CTA per pass) */
+/* exclusive scan of each pass's bins (one CTA of 512 threads per pass) */
 __global__ void radix_scan_hist_kernel(u32 *ghist) {
-  __shared__ u32 s[kRadix];
-  u32 *h = ghist + blockIdx.x * kRadix;
+  __shared__ u32 s[kMaxRadix];
+  u32 *h = ghist + blockIdx.x * kMaxRadix;
   const u32 v = h[threadIdx.x];
   s[threadIdx.x] = v;
   __syncthreads();
-  /* Hillis-Steele over 256 entries */
-  for (int d = 1; d < kRadix; d <<= 1) {
+  for (int d = 1; d < kMaxRadix; d <<= 1) {
     u32 t = (threadIdx.x >= d) ? s[threadIdx.x - d] : 0;
     __syncthreads();
     s[threadIdx.x] += t;
@@ -315,24 +320,26 @@ __global__ void radix_scan_hist_kernel(u32 *ghist) {
   h[threadIdx.x] = s[threadIdx.x] - v;
 }
 
-/* One 8-bit pass.  512 threads x 8 keys: 16 warps per CTA and <= 64 registers
-   so that two CTAs (32 warps) are resident per SM and the load / rank /
-   look-back / scatter phases of different CTAs overlap. */
-template <bool kHasVals>
+/* One pass of kBits (8 or 9) bits.  512 threads x 8 keys: 16 warps per CTA and
+   <= 64 registers so that two CTAs (32 warps) are resident per SM and the load
+   / rank / look-back / scatter phases of different CTAs overlap.  With 9-bit
+   digits every thread owns one digit in the descriptor phase. */
+template <bool kHasVals, int kBits>
 __global__ void __launch_bounds__(kSortThreads, 2)
     radix_pass_kernel(const u64 *__restrict__ kin, u64 *__restrict__ kout,
                       const u32 *__restrict__ vin, u32 *__restrict__ vout,
                       i64 n, int shift, int bits,
-                      const u32 *__restrict__ pass_offset, /* [256] */
-                      u32 *ticket, u64 *lookback /* [tiles][256] */) {
+                      const u32 *__restrict__ pass_offset, /* [kRadix] */
+                      u32 *ticket, u64 *lookback /* [tiles][kRadix] */) {
+  const int kRadix = 1 << kBits;
   extern __shared__ unsigned char smem_raw[];
   u64 *s_keys = reinterpret_cast<u64 *>(smem_raw);            /* tile keys */
   u32 *s_vals = reinterpret_cast<u32 *>(s_keys + kSortTile);  /* tile vals */
-  u32 *s_whist = s_vals + (kHasVals ? kSortTile : 0);         /* [warps][256] */
-  u32 *s_dbase = s_whist + kSortWarps * kRadix;               /* [256] */
-  u64 *s_goff = reinterpret_cast<u64 *>(s_dbase + kRadix);    /* [256] */
+  u32 *s_whist = s_vals + (kHasVals ? kSortTile : 0);         /* [warps][R] */
+  u32 *s_dbase = s_whist + kSortWarps * kRadix;               /* [R] */
+  u64 *s_goff = reinterpret_cast<u64 *>(s_dbase + kRadix);    /* [R] */
   __shared__ u32 s_tile;
-  __shared__ u32 s_wsum[kRadix / 32];
+  __shared__ u32 s_wsum[kMaxRadix / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1u);
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(kSortThreads, 2)
   }
   __syncthreads();
 
-  /* (3) per digit (threads 0..255 own one digit each): warp bases, tile count,
+  /* (3) per digit (thread t < kRadix owns digit t): warp bases, tile count,
      descriptor, look-back */
   u32 count = 0, incl = 0;
   u64 *my_desc = lookback + (size_t)tile * kRadix + tid;
@@ -384,8 +391,6 @@ __global__ void __launch_bounds__(kSortThreads, 2)
       count += c;
     }
     st_relaxed_u64(my_desc, (tile == 0 ? kStatusPrefix : kStatusAgg) | (u64)count);
-    /* exclusive scan of the 256 tile counts -> position of each digit run in
-       the staged tile */
     incl = count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -403,7 +408,6 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     }
     const u32 dbase = woff + incl - count;
     s_dbase[tid] = dbase;
-    /* decoupled look-back for digit `tid` */
     u64 excl = 0;
     if (tile > 0) {
       i64 p = (i64)tile - 1;
@@ -444,39 +448,69 @@ __global__ void __launch_bounds__(kSortThreads, 2)
   }
 }
 
-static size_t sort_smem_bytes(bool has_vals) {
+static size_t sort_smem_bytes(bool has_vals, int radix) {
   size_t b = (size_t)kSortTile * sizeof(u64);
   if (has_vals) b += (size_t)kSortTile * sizeof(u32);
-  b += (size_t)kSortWarps * kRadix * sizeof(u32);
-  b += (size_t)kRadix * sizeof(u32);
-  b += (size_t)kRadix * sizeof(u64);
+  b += (size_t)kSortWarps * radix * sizeof(u32);
+  b += (size_t)radix * sizeof(u32);
+  b += (size_t)radix * sizeof(u64);
   return b;
+}
+
+/* spread `total` key bits over the fewest passes of <= 9 bits, as evenly as
+   possible, never below 8 bits unless the key is shorter */
+static PassPlan make_plan(int bit_lo, int bit_hi) {
+  PassPlan pl;
+  const int total = bit_hi - bit_lo;
+  int npass = (total + kMaxRadixBits - 1) / kMaxRadixBits;
+  if (npass < 1) npass = 1;
+  pl.npass = npass;
+  int at = bit_lo;
+  for (int p = 0; p < npass; p++) {
+    const int left = bit_hi - at;
+    const int b = (left + (npass - p) - 1) / (npass - p);
+    pl.shift[p] = at;
+    pl.bits[p] = b;
+    at += b;
+  }
+  return pl;
+}
+
+template <bool kHasVals, int kBits>
+static void launch_pass(Ctx &ctx, i64 tiles, DBuf<u64> &keys, DBuf<u64> &keys_alt,
+                        DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int shift,
+                        int bits, const u32 *offs, u32 *ticket, u64 *lookback) {
+  const size_t smem = sort_smem_bytes(kHasVals, 1 << kBits);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(radix_pass_kernel<kHasVals, kBits>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  radix_pass_kernel<kHasVals, kBits>
+      <<<(unsigned)tiles, kSortThreads, smem, (cudaStream_t)ctx.stream>>>(
+          keys.get(), keys_alt.get(), kHasVals ? vals.get() : NULL,
+          kHasVals ? vals_alt.get() : NULL, n, shift, bits, offs, ticket,
+          lookback);
 }
 
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
                 DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int bit_lo,
                 int bit_hi) {
   if (n <= 1 || bit_hi <= bit_lo) return;
-  const bool has_vals = vals.get() != NULL;
-  int npass = (bit_hi - bit_lo + kRadixBits - 1) / kRadixBits;
-  cudaStream_t st = (cudaStream_t)ctx.stream;
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(radix_pass_kernel<true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sort_smem_bytes(true));
-    cudaFuncSetAttribute(radix_pass_kernel<false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sort_smem_bytes(false));
-    attr_set = true;
+  if (n >= (1LL << 32)) {
+    fprintf(stderr, "TMROctForest Error: radix sort of %lld keys exceeds the "
+                    "32-bit offset range\n", (long long)n);
+    ctx.last_error = "radix sort too large";
+    return;
   }
-
+  const bool has_vals = vals.get() != NULL;
+  cudaStream_t st = (cudaStream_t)ctx.stream;
   const i64 tiles = (n + kSortTile - 1) / kSortTile;
-  /* scratch: [npass*256 u32 hist][npass u32 tickets (padded)][tiles*256 u64] */
-  const size_t hist_bytes = (size_t)kMaxPasses * kRadix * sizeof(u32);
+  /* scratch: [kMaxPasses*512 u32 hist][tickets][tiles*512 u64 descriptors] */
+  const size_t hist_bytes = (size_t)kMaxPasses * kMaxRadix * sizeof(u32);
   const size_t ticket_bytes = 64;
-  const size_t look_bytes = (size_t)tiles * kRadix * sizeof(u64);
+  const size_t look_bytes = (size_t)tiles * kMaxRadix * sizeof(u64);
   unsigned char *scratch = static_cast<unsigned char *>(
       dev_alloc(ctx, hist_bytes + ticket_bytes + look_bytes));
   if (!scratch) return;
@@ -484,41 +518,48 @@ void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
   u32 *tickets = reinterpret_cast<u32 *>(scratch + hist_bytes);
   u64 *lookback = reinterpret_cast<u64 *>(scratch + hist_bytes + ticket_bytes);
 
-  int done = 0;
-  while (done < npass) {
-    /* histogram at most kMaxPasses passes per sweep of the keys */
-    const int chunk = (npass - done < kMaxPasses) ? (npass - done) : kMaxPasses;
-    const int lo = bit_lo + done * kRadixBits;
+  int lo = bit_lo;
+  while (lo < bit_hi) {
+    /* at most kMaxPasses passes are histogrammed per sweep of the keys */
+    int hi = bit_hi;
+    if (hi - lo > kMaxPasses * kMaxRadixBits) hi = lo + kMaxPasses * kMaxRadixBits;
+    const PassPlan plan = make_plan(lo, hi);
     dev_zero(ctx, scratch, hist_bytes + ticket_bytes);
     prof_begin(ctx, "radix_hist");
     radix_hist_kernel<<<grid_for(ctx, n, kHistThreads * 4, 8), kHistThreads, 0,
-                        st>>>(keys.get(), n, lo, bit_hi, chunk, ghist);
-    radix_scan_hist_kernel<<<chunk, kRadix, 0, st>>>(ghist);
+                        st>>>(keys.get(), n, plan, ghist);
+    radix_scan_hist_kernel<<<plan.npass, kMaxRadix, 0, st>>>(ghist);
     prof_end(ctx);
     ctx.launch_count += 2;
-    for (int p = 0; p < chunk; p++) {
-      const int shift = lo + p * kRadixBits;
-      const int bits = (bit_hi - shift < kRadixBits) ? (bit_hi - shift)
-                                                     : kRadixBits;
-      dev_zero(ctx, lookback, look_bytes);
+    for (int p = 0; p < plan.npass; p++) {
+      const int bits = plan.bits[p];
+      const int radix = bits > 8 ? 512 : 256;
+      dev_zero(ctx, lookback, (size_t)tiles * radix * sizeof(u64));
       prof_begin(ctx, has_vals ? "radix_pass_pairs" : "radix_pass_keys");
+      const u32 *offs = ghist + p * kMaxRadix;
       if (has_vals) {
-        radix_pass_kernel<true>
-            <<<(unsigned)tiles, kSortThreads, sort_smem_bytes(true), st>>>(
-                keys.get(), keys_alt.get(), vals.get(), vals_alt.get(), n,
-                shift, bits, ghist + p * kRadix, tickets + p, lookback);
+        if (bits > 8) {
+          launch_pass<true, 9>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
+                               plan.shift[p], bits, offs, tickets + p, lookback);
+        } else {
+          launch_pass<true, 8>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
+                               plan.shift[p], bits, offs, tickets + p, lookback);
+        }
       } else {
-        radix_pass_kernel<false>
-            <<<(unsigned)tiles, kSortThreads, sort_smem_bytes(false), st>>>(
-                keys.get(), keys_alt.get(), NULL, NULL, n, shift, bits,
-                ghist + p * kRadix, tickets + p, lookback);
+        if (bits > 8) {
+          launch_pass<false, 9>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
+                                plan.shift[p], bits, offs, tickets + p, lookback);
+        } else {
+          launch_pass<false, 8>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
+                                plan.shift[p], bits, offs, tickets + p, lookback);
+        }
       }
       prof_end(ctx);
       ctx.launch_count++;
       keys.swap(keys_alt);
       if (has_vals) vals.swap(vals_alt);
     }
-    done += chunk;
+    lo = hi;
   }
   dev_free(ctx, scratch);
 }

@@ -75,10 +75,11 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
   return v;
 }
 
-template <class F>
+/* G is called as g(i, exclusive_prefix_of_i) for every i < n */
+template <class F, class G>
 __global__ void __launch_bounds__(kScanThreads)
-    scan_counts_kernel(F f, i64 n, u32 *out, u64 *tile_state, u32 *ticket,
-                       u64 *total) {
+    scan_apply_kernel(F f, G g, i64 n, u64 *tile_state, u32 *ticket,
+                      u64 *total) {
   __shared__ u32 s_tile;
   __shared__ u64 s_warp_sum[kScanThreads / 32];
   __shared__ u64 s_tile_prefix;
@@ -138,34 +139,20 @@ __global__ void __launch_bounds__(kScanThreads)
   }
   __syncthreads();
   u64 run = s_tile_prefix + warp_off + (incl - mine);
-  if (base + kScanItems <= n && ((((size_t)out) & 15) == 0)) {
-    uint4 v0, v1;
-    v0.x = (u32)run; run += c[0];
-    v0.y = (u32)run; run += c[1];
-    v0.z = (u32)run; run += c[2];
-    v0.w = (u32)run; run += c[3];
-    v1.x = (u32)run; run += c[4];
-    v1.y = (u32)run; run += c[5];
-    v1.z = (u32)run; run += c[6];
-    v1.w = (u32)run;
-    uint4 *o = reinterpret_cast<uint4 *>(out + base);
-    o[0] = v0;
-    o[1] = v1;
-  } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-      const i64 i = base + k;
-      if (i < n) out[i] = (u32)run;
-      run += c[k];
-    }
+  for (int k = 0; k < kScanItems; k++) {
+    const i64 i = base + k;
+    if (i < n) g(i, (u32)run);
+    run += c[k];
   }
 }
 
-template <class F>
-u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *name) {
+/* f(i) -> count; g(i, exclusive prefix) consumes it in the same kernel (no
+   offset array round trip through HBM).  Returns the total. */
+template <class F, class G>
+u64 scan_apply(Ctx &ctx, i64 n, F f, G g, const char *name) {
   if (n <= 0) return 0;
   const i64 tiles = (n + kScanTile - 1) / kScanTile;
-  /* scratch: tile descriptors + ticket + total, zeroed per call */
   const size_t bytes = (size_t)(tiles + 2) * sizeof(u64);
   u64 *scratch = static_cast<u64 *>(dev_alloc(ctx, bytes));
   dev_zero(ctx, scratch, bytes);
@@ -173,15 +160,28 @@ u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *name) {
   u32 *ticket = reinterpret_cast<u32 *>(scratch + tiles);
   u64 *total = scratch + tiles + 1;
   prof_begin(ctx, name);
-  scan_counts_kernel<F><<<(unsigned)tiles, kScanThreads, 0,
-                          (cudaStream_t)ctx.stream>>>(f, n, out, tile_state,
-                                                      ticket, total);
+  scan_apply_kernel<F, G><<<(unsigned)tiles, kScanThreads, 0,
+                            (cudaStream_t)ctx.stream>>>(f, g, n, tile_state,
+                                                        ticket, total);
   prof_end(ctx);
   ctx.launch_count++;
   u64 h_total = 0;
   copy_d2h(ctx, &h_total, total, sizeof(u64));
   dev_free(ctx, scratch);
   return h_total;
+}
+
+struct StoreOffsetFn {
+  u32 *out;
+  __device__ __forceinline__ void operator()(i64 i, u32 off) const {
+    out[i] = off;
+  }
+};
+
+template <class F>
+u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *name) {
+  StoreOffsetFn g = {out};
+  return scan_apply(ctx, n, f, g, name);
 }
 
 }  // namespace tmrgpu
