@@ -41,6 +41,16 @@ int tmrgpu_profile_reset(tmrgpu_ctx *ctx);
 int tmrgpu_profile_json(tmrgpu_ctx *ctx, char *buf, int buflen);
 long tmrgpu_launch_count(tmrgpu_ctx *ctx);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------
+   (replaces MPI_Comm + the MPI datatypes of reference src/TMRBase.cpp:42-92)
+   rank 0 obtains an id (128 bytes), ships it to the other processes by any
+   means (torch.distributed, MPI, a file), then every process attaches its
+   context.  Collective. */
+int tmrgpu_comm_unique_id(void *out, int out_bytes);
+int tmrgpu_ctx_init_comm(tmrgpu_ctx *ctx, int rank, int size, const void *id);
+int tmrgpu_ctx_rank(tmrgpu_ctx *ctx);
+int tmrgpu_ctx_size(tmrgpu_ctx *ctx);
+
 /* ---- forest -------------------------------------------------------------- */
 int tmrgpu_forest_create(tmrgpu_ctx *ctx, tmrgpu_forest **out);
 int tmrgpu_forest_destroy(tmrgpu_forest *f);
@@ -81,6 +91,13 @@ int tmrgpu_refine(tmrgpu_forest *f, const int *h_flags, int min_level,
                   int max_level);
 int tmrgpu_refine_device(tmrgpu_forest *f, const int *d_flags, int min_level,
                          int max_level);
+/* repartition (reference :1922-2088): equal-count re-split of the global
+   Morton order over the first max_rank ranks; collective */
+int tmrgpu_repartition(tmrgpu_forest *f, int max_rank);
+/* owners[] table (first octant of every rank), size() records */
+int tmrgpu_get_owners(tmrgpu_forest *f, tmrgpu_octant *out);
+/* owned-node prefix over ranks, size()+1 ints (reference node_range) */
+int tmrgpu_node_range(tmrgpu_forest *f, int *out);
 /* balance (reference :2917-3089) */
 int tmrgpu_balance(tmrgpu_forest *f, int balance_corner);
 /* coarsen / duplicate into an existing forest (reference :2097-2164) */

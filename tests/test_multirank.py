@@ -1,0 +1,41 @@
+"""N>1 on the CPU: the multi-rank exchange logic (SFC partition, owner lookup,
+all-to-all-v routing, ghost layer, node ownership and numbering) run as
+thread-ranks of the test-only emulation and compared, rank by rank and
+bit for bit, with the reference's own MPI path run as thread-ranks of the
+oracle.  The GPU counterpart is tests/multi_gpu_check.py (torchrun)."""
+import numpy as np
+import pytest
+
+import multirank
+import util
+
+
+@pytest.mark.parametrize("case", multirank.CASES, ids=[c[0] for c in multirank.CASES])
+def test_multirank_matches_reference(case, emu_lib, ref_lib):
+    name, conn_name, level, passes, pct, corner, order, ranks, repart = case
+    conn = util.CONNS[conn_name]()
+    body = multirank.adapt_body(conn, level, passes, pct, corner, order, repart)
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_rank_results(a, b, name)
+
+
+def test_rank_count_invariance(emu_lib):
+    """The balanced octant set does not depend on the number of ranks."""
+    conn = util.box_conn()
+    sums = []
+    for ranks in (1, 2, 5):
+        body = multirank.adapt_body(conn, 1, 3, 30, 1, 2, True)
+        out = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+        allocts = np.concatenate([o[0][-1] for o in out])
+        sums.append((len(allocts), util.checksum(allocts)))
+    assert sums[0] == sums[1] == sums[2]
+
+
+def test_partition_counts():
+    from tmr_b200 import dist
+
+    assert dist.partition_counts(10, 4) == [3, 3, 2, 2]
+    assert dist.partition_counts(10, 4, 2) == [5, 5, 0, 0]
+    assert dist.partition_counts(3, 8) == [1, 1, 1, 0, 0, 0, 0, 0]
+    assert sum(dist.partition_counts(86278900, 8)) == 86278900

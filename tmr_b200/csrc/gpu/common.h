@@ -26,6 +26,7 @@
    test-only serial emulation) they degrade to plain read-modify-write. */
 #if defined(__CUDA_ARCH__)
 #define TMR_ATOMIC_MAX_I32(p, v) atomicMax((int *)(p), (int)(v))
+#define TMR_ATOMIC_MIN_I32(p, v) atomicMin((int *)(p), (int)(v))
 #define TMR_ATOMIC_OR_I32(p, v) atomicOr((int *)(p), (int)(v))
 #define TMR_ATOMIC_MAX_U64(p, v) \
   atomicMax((unsigned long long *)(p), (unsigned long long)(v))
@@ -37,6 +38,10 @@
 #define TMR_ATOMIC_MAX_I32(p, v) \
   do {                           \
     if (*(p) < (v)) *(p) = (v);  \
+  } while (0)
+#define TMR_ATOMIC_MIN_I32(p, v) \
+  do {                           \
+    if (*(p) > (v)) *(p) = (v);  \
   } while (0)
 #define TMR_ATOMIC_OR_I32(p, v) \
   do {                          \
@@ -444,6 +449,14 @@ TMR_HD int popc32(u32 v) {
   return __popc(v);
 #else
   return __builtin_popcount(v);
+#endif
+}
+
+TMR_HD int popc64(u64 v) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(v);
+#else
+  return __builtin_popcountll(v);
 #endif
 }
 

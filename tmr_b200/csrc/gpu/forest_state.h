@@ -12,6 +12,7 @@
 
 #include <memory>
 
+#include "comm.h"
 #include "prim.h"
 #if defined(TMRGPU_EMU)
 #include "prim_emu.h"
@@ -91,6 +92,9 @@ struct Forest {
   KeyFmt fmt;
   NodeData nodes;
   InterpData interp;
+  /* SFC partition: owners[r] = first octant of rank r (reference `owners`,
+     src/TMROctForest.h:270); empty for a single rank */
+  std::vector<Oct24> owners;
   /* counters describing the last operation (for bench/roofline reporting) */
   i64 last_in, last_mid, last_out;
 
@@ -102,6 +106,9 @@ struct Forest {
     tables = ConnTables();
   }
 };
+
+inline int part_rank(const Forest &f) { return f.ctx->comm ? f.ctx->comm->rank : 0; }
+inline int part_size(const Forest &f) { return f.ctx->comm ? f.ctx->comm->size : 1; }
 
 inline int bits_for(int nblocks) {
   int b = 1;

@@ -97,6 +97,74 @@ struct SplitLevelFn {
   }
 };
 
+/* Images of the grid cell q (integer coordinates on the N^3 grid of tree
+   `block`, possibly one step outside it) in the forest: the cell itself when
+   inside, otherwise its image in EVERY other tree sharing the tree face /
+   edge / corner it crossed (reference addFaceNeighbors :2525-2590,
+   addEdgeNeighbors :2608-2686, addCornerNeighbors :2704-2745 and their
+   addAdjacent*ToQueue twins :3095-3273). */
+template <class Emit>
+TMR_HD void tree_images(const ConnTables &t, i32 block, const i32 q[3], i32 N,
+                        Emit &emit) {
+  const i32 M = N - 1;
+  int out[3], nout = 0;
+  for (int d = 0; d < 3; d++) {
+    out[d] = (q[d] < 0 || q[d] >= N);
+    nout += out[d];
+  }
+  if (nout == 0) {
+    emit(block, q[0], q[1], q[2]);
+  } else if (nout == 1) {
+    const int axis = out[0] ? 0 : (out[1] ? 1 : 2);
+    const int f = 2 * axis + (q[axis] < 0 ? 0 : 1);
+    const int face = t.block_face_conn[6 * block + f];
+    i32 a0, b0, u, v;
+    face_pick(f, q[0], q[1], q[2], &a0, &b0);
+    face_to_owner(t.block_face_ids[6 * block + f], M, a0, b0, &u, &v);
+    for (int ip = t.face_block_ptr[face]; ip < t.face_block_ptr[face + 1]; ip++) {
+      const int adj = t.face_block_conn[ip] / 6;
+      if (adj == block) continue;
+      const int af = t.face_block_conn[ip] % 6;
+      i32 a1, b1, x, y, z;
+      owner_to_face(t.block_face_ids[6 * adj + af], M, u, v, &a1, &b1);
+      face_place(af, M * (af & 1), a1, b1, &x, &y, &z);
+      emit(adj, x, y, z);
+    }
+  } else if (nout == 2) {
+    int e;
+    i32 u;
+    if (out[1] && out[2]) {
+      e = (q[1] < 0 ? 0 : 1) + (q[2] < 0 ? 0 : 2);
+      u = q[0];
+    } else if (out[0] && out[2]) {
+      e = (q[0] < 0 ? 4 : 5) + (q[2] < 0 ? 0 : 2);
+      u = q[1];
+    } else {
+      e = (q[0] < 0 ? 8 : 9) + (q[1] < 0 ? 0 : 2);
+      u = q[2];
+    }
+    const int edge = t.block_edge_conn[12 * block + e];
+    for (int ip = t.edge_block_ptr[edge]; ip < t.edge_block_ptr[edge + 1]; ip++) {
+      const int adj = t.edge_block_conn[ip] / 12;
+      if (adj == block) continue;
+      const int ae = t.edge_block_conn[ip] % 12;
+      const i32 uu = edge_is_reversed(t, block, e, adj, ae) ? M - u : u;
+      i32 x, y, z;
+      edge_place(ae, uu, M, &x, &y, &z);
+      emit(adj, x, y, z);
+    }
+  } else {
+    const int c = (q[0] < 0 ? 0 : 1) + (q[1] < 0 ? 0 : 2) + (q[2] < 0 ? 0 : 4);
+    const int node = t.block_conn[8 * block + c];
+    for (int ip = t.node_block_ptr[node]; ip < t.node_block_ptr[node + 1]; ip++) {
+      const int adj = t.node_block_conn[ip] / 8;
+      if (adj == block) continue;
+      const int ac = t.node_block_conn[ip] % 8;
+      emit(adj, M * (ac & 1), M * ((ac >> 1) & 1), M * (ac >> 2));
+    }
+  }
+}
+
 /* (c) candidates demanded by p in R_l at level l-1 */
 struct BalanceGen {
   ConnTables t;
@@ -112,7 +180,6 @@ struct BalanceGen {
     u32 px, py, pz;
     unmorton3(pk & low_mask(sh), &px, &py, &pz);
     const i32 N = 1 << (l - 1); /* level-(l-1) grid size */
-    const i32 M = N - 1;
     const i32 q0[3] = {(i32)(px >> 1), (i32)(py >> 1), (i32)(pz >> 1)};
     /* outward direction per axis = the side of its parent p sits on */
     const i32 s[3] = {(px & 1) ? 1 : -1, (py & 1) ? 1 : -1, (pz & 1) ? 1 : -1};
@@ -123,70 +190,8 @@ struct BalanceGen {
     for (int a = 1; a < 8; a++) {
       if (a == 7 && !corner) continue;
       i32 q[3];
-      int out[3], nout = 0;
-      for (int d = 0; d < 3; d++) {
-        q[d] = q0[d] + (((a >> d) & 1) ? s[d] : 0);
-        out[d] = (q[d] < 0 || q[d] >= N);
-        nout += out[d];
-      }
-      if (nout == 0) {
-        emit(block, q[0], q[1], q[2]);
-      } else if (nout == 1) {
-        /* across a tree face (reference addFaceNeighbors :2525-2590) */
-        const int axis = out[0] ? 0 : (out[1] ? 1 : 2);
-        const int f = 2 * axis + (q[axis] < 0 ? 0 : 1);
-        const int face = t.block_face_conn[6 * block + f];
-        i32 a0, b0, u, v;
-        face_pick(f, q[0], q[1], q[2], &a0, &b0);
-        face_to_owner(t.block_face_ids[6 * block + f], M, a0, b0, &u, &v);
-        for (int ip = t.face_block_ptr[face]; ip < t.face_block_ptr[face + 1];
-             ip++) {
-          const int adj = t.face_block_conn[ip] / 6;
-          if (adj == block) continue;
-          const int af = t.face_block_conn[ip] % 6;
-          i32 a1, b1, x, y, z;
-          owner_to_face(t.block_face_ids[6 * adj + af], M, u, v, &a1, &b1);
-          face_place(af, M * (af & 1), a1, b1, &x, &y, &z);
-          emit(adj, x, y, z);
-        }
-      } else if (nout == 2) {
-        /* across a tree edge (reference addEdgeNeighbors :2608-2686) */
-        int e;
-        i32 u;
-        if (out[1] && out[2]) {
-          e = (q[1] < 0 ? 0 : 1) + (q[2] < 0 ? 0 : 2);
-          u = q[0];
-        } else if (out[0] && out[2]) {
-          e = (q[0] < 0 ? 4 : 5) + (q[2] < 0 ? 0 : 2);
-          u = q[1];
-        } else {
-          e = (q[0] < 0 ? 8 : 9) + (q[1] < 0 ? 0 : 2);
-          u = q[2];
-        }
-        const int edge = t.block_edge_conn[12 * block + e];
-        for (int ip = t.edge_block_ptr[edge]; ip < t.edge_block_ptr[edge + 1];
-             ip++) {
-          const int adj = t.edge_block_conn[ip] / 12;
-          if (adj == block) continue;
-          const int ae = t.edge_block_conn[ip] % 12;
-          const i32 uu = edge_is_reversed(t, block, e, adj, ae) ? M - u : u;
-          i32 x, y, z;
-          edge_place(ae, uu, M, &x, &y, &z);
-          emit(adj, x, y, z);
-        }
-      } else {
-        /* across a tree corner (reference addCornerNeighbors :2704-2745) */
-        const int c = (q[0] < 0 ? 0 : 1) + (q[1] < 0 ? 0 : 2) +
-                      (q[2] < 0 ? 0 : 4);
-        const int node = t.block_conn[8 * block + c];
-        for (int ip = t.node_block_ptr[node]; ip < t.node_block_ptr[node + 1];
-             ip++) {
-          const int adj = t.node_block_conn[ip] / 8;
-          if (adj == block) continue;
-          const int ac = t.node_block_conn[ip] % 8;
-          emit(adj, M * (ac & 1), M * ((ac >> 1) & 1), M * (ac >> 2));
-        }
-      }
+      for (int d = 0; d < 3; d++) q[d] = q0[d] + (((a >> d) & 1) ? s[d] : 0);
+      tree_images(t, block, q, N, emit);
     }
   }
 };

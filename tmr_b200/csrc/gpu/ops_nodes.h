@@ -26,6 +26,7 @@
 #define TMRGPU_OPS_NODES_H
 
 #include "ops_balance.h"
+#include "ops_route.h"
 
 namespace tmrgpu {
 
@@ -64,9 +65,13 @@ struct ElemView {
   KeyFmt fmt;
   ConnTables t;
   KeyIndex ix;
+  const u64 *ghost; /* sorted octants received from neighbouring ranks */
+  i64 nghost;
 
   TMR_HD bool leaf_exists(i32 block, i32 x, i32 y, i32 z, int level) const {
-    return ix.find(keys, fmt.encode(block, x, y, z, level)) >= 0;
+    const u64 key = fmt.encode(block, x, y, z, level);
+    if (ix.find(keys, key) >= 0) return true;
+    return nghost > 0 && find_u64(ghost, nghost, key) >= 0;
   }
   TMR_HD bool leaf_exists_near(i32 block, i32 x, i32 y, i32 z, int level,
                                i64) const {
@@ -290,19 +295,187 @@ struct RunHeadFn {
 };
 
 /* sorted candidates -> unique node keys + local connectivity */
+static const u32 kNoSlot = 0xffffffffu; /* candidate that fills no conn slot */
+
 struct NodeScatterFn {
   const u64 *keys;
   const u32 *vals;
   u64 *node_keys;
   int *conn_local;
+  unsigned char *created; /* optional: node is created by a local element */
   /* heads_before = exclusive scan of run heads */
   TMR_HD void operator()(i64 i, u32 heads_before) const {
     const bool head = (i == 0 || keys[i] != keys[i - 1]);
     const u32 run = heads_before + (head ? 1u : 0u) - 1u;
     if (head) node_keys[run] = keys[i];
-    conn_local[vals[i]] = (int)run;
+    if (vals[i] != kNoSlot) {
+      conn_local[vals[i]] = (int)run;
+      if (created) created[run] = 1;
+    }
   }
 };
+
+/* nodes of the PARENT's hanging edges / faces (reference createLocalNodes
+   :4378-4536): needed so that a dependent node's stencil can be numbered even
+   when the coarse neighbour that owns those nodes lives on another rank */
+struct ParentNodeGen {
+  const u64 *keys;
+  const int16_t *info;
+  KeyFmt fmt;
+  NodeFmt nfmt;
+  ConnTables t;
+  int order;
+  template <class Emit>
+  TMR_HD void run(i64 e, Emit &emit) const {
+    const int inf = info[e];
+    if (!inf) return;
+    i32 block, x, y, z;
+    int level;
+    fmt.decode(keys[e], &block, &x, &y, &z, &level);
+    const int id = child_id_of(x, y, z, level);
+    int fm, em;
+    decode_info(id, inf, &fm, &em);
+    const i32 h = 1 << (kMaxLevel - level);
+    const i32 hp = 2 * h;
+    const i32 px = x & ~h, py = y & ~h, pz = z & ~h;
+    const i32 step = hp / (order - 1);
+    for (int ed = 0; ed < 12; ed++) {
+      if (!(em & (1 << ed))) continue;
+      const int s = ed & 3;
+      const i32 ta = hp * (s & 1), tb = hp * (s >> 1);
+      for (int ii = 0; ii < order; ii++) {
+        i32 b = block, nx, ny, nz;
+        if (ed < 4) {
+          nx = px + ii * step; ny = py + ta; nz = pz + tb;
+        } else if (ed < 8) {
+          nx = px + ta; ny = py + ii * step; nz = pz + tb;
+        } else {
+          nx = px + ta; ny = py + tb; nz = pz + ii * step;
+        }
+        transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
+        emit(nfmt.encode(b, nx, ny, nz));
+      }
+    }
+    for (int f = 0; f < 6; f++) {
+      if (!(fm & (1 << f))) continue;
+      const i32 nn = hp * (f & 1);
+      for (int q = 0; q < order; q++) {
+        for (int p = 0; p < order; p++) {
+          i32 b = block, nx, ny, nz;
+          if (f < 2) {
+            nx = px + nn; ny = py + p * step; nz = pz + q * step;
+          } else if (f < 4) {
+            nx = px + p * step; ny = py + nn; nz = pz + q * step;
+          } else {
+            nx = px + p * step; ny = py + q * step; nz = pz + nn;
+          }
+          transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
+          emit(nfmt.encode(b, nx, ny, nz));
+        }
+      }
+    }
+  }
+};
+
+struct CountKeyEmit {
+  u32 n;
+  TMR_HD void operator()(u64) { n++; }
+};
+struct StoreKeyEmit {
+  u64 *k;
+  u32 *v;
+  TMR_HD void operator()(u64 key) {
+    *k++ = key;
+    *v++ = kNoSlot;
+  }
+};
+struct ParentNodeCountFn {
+  ParentNodeGen g;
+  TMR_HD u32 operator()(i64 e) const {
+    CountKeyEmit c = {0};
+    g.run(e, c);
+    return c.n;
+  }
+};
+struct ParentNodeFillFn {
+  ParentNodeGen g;
+  u64 *out_keys;
+  u32 *out_vals;
+  TMR_HD void operator()(i64 e, u32 o) const {
+    StoreKeyEmit s = {out_keys + o, out_vals + o};
+    g.run(e, s);
+  }
+};
+
+/* ---- ghost layer (reference computeAdjacentOctants :3287-3451) -----------------
+   For every local octant: the ranks owning any of the 56 half-size positions
+   around it (across faces, edges, corners, through tree boundaries) need a copy
+   of it to answer their exact-leaf probes. */
+struct GhostGen {
+  const u64 *keys;
+  KeyFmt fmt;
+  ConnTables t;
+  OwnerMap om; /* positions at depth fmt.D */
+  int me;
+
+  struct MaskEmit {
+    const GhostGen *g;
+    int lev1; /* level of the probe cells */
+    u64 mask;
+    TMR_HD void operator()(i32 block, i32 x, i32 y, i32 z) {
+      const int D = g->fmt.D;
+      u64 m;
+      if (lev1 <= D) {
+        m = morton3((u32)x, (u32)y, (u32)z) << (3 * (D - lev1));
+      } else {
+        m = morton3((u32)x >> 1, (u32)y >> 1, (u32)z >> 1);
+      }
+      mask |= 1ULL << g->om.owner(((u64)(u32)block << (3 * D)) | m);
+    }
+  };
+
+  TMR_HD u64 dests(i64 i) const {
+    i32 block, x, y, z;
+    int level;
+    fmt.decode(keys[i], &block, &x, &y, &z, &level);
+    const int lev1 = level + 1;
+    const i32 N = 1 << lev1;
+    const int s = kMaxLevel - lev1;
+    const i32 b[3] = {x >> s, y >> s, z >> s};
+    MaskEmit e = {this, lev1, 0};
+    for (int dz = -1; dz <= 1; dz++) {
+      for (int dy = -1; dy <= 1; dy++) {
+        for (int dx = -1; dx <= 1; dx++) {
+          if (!dx && !dy && !dz) continue;
+          const int d[3] = {dx, dy, dz};
+          /* axes with d=0 range over both halves of the octant */
+          for (int sub = 0; sub < 8; sub++) {
+            i32 q[3];
+            bool skip = false;
+            for (int a = 0; a < 3; a++) {
+              const int bit = (sub >> a) & 1;
+              if (d[a] == 0) {
+                q[a] = b[a] + bit;
+              } else {
+                if (bit) skip = true; /* one position along a moved axis */
+                q[a] = d[a] < 0 ? b[a] - 1 : b[a] + 2;
+              }
+            }
+            if (skip) continue;
+            tree_images(t, block, q, N, e);
+          }
+        }
+      }
+    }
+    return e.mask & ~(1ULL << me);
+  }
+};
+
+struct GhostCountFn {
+  GhostGen g;
+  TMR_HD u32 operator()(i64 i) const { return (u32)popc64(g.dests(i)); }
+};
+
 
 /* labelDependentNodes (reference :3711-3832) */
 struct DepLabelFn {
@@ -605,9 +778,180 @@ inline int sorted_node_numbers(Forest &f, int *h_out) {
   return check_errors(ctx, "sorted_node_numbers");
 }
 
+struct GhostFillFn {
+  GhostGen g;
+  u64 *out_keys;
+  u32 *out_dest;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    u64 m = g.dests(i);
+    for (int r = 0; m; r++, m >>= 1) {
+      if (m & 1) {
+        out_keys[o] = g.keys[i];
+        out_dest[o] = (u32)r;
+        o++;
+      }
+    }
+  }
+};
+
+struct GhostPlaceFn {
+  GhostFillFn fill;
+  const u32 *off;
+  TMR_HD void operator()(i64 i) const { fill(i, off[i]); }
+};
+
+struct ParentPlaceFn {
+  ParentNodeFillFn fill;
+  const u32 *off;
+  TMR_HD void operator()(i64 e) const { fill(e, off[e]); }
+};
+
+struct U32DestFn {
+  const u32 *dest;
+  TMR_HD int operator()(i64 i) const { return (int)dest[i]; }
+};
+
+/* home rank of a node = owner of its position (the reference distributes the
+   node array with matchOctantIntervals, :4545) */
+struct NodeHomeFn {
+  const u64 *node_keys;
+  int Dn;
+  OwnerMap om; /* positions at depth Dn */
+  TMR_HD int operator()(i64 i) const {
+    const u64 k = node_keys[i];
+    const int sh = 3 * (Dn + 1);
+    const u64 block = k >> sh;
+    /* halving every squeezed coordinate = shifting the interleaved code by 3 */
+    const u64 m = (k & low_mask(sh)) >> 3;
+    return om.owner((block << (3 * Dn)) | m);
+  }
+};
+
+/* at the home rank: value of a received item = donating rank or INF */
+struct DonorValueFn {
+  const unsigned char *created; /* received flags */
+  const i64 *recv_off;          /* device, R+1 */
+  int R;
+  u32 *val;
+  u32 *idx;
+  TMR_HD void operator()(i64 i) const {
+    int src = 0;
+    while (src < R - 1 && recv_off[src + 1] <= i) src++;
+    val[i] = created[i] ? (u32)src : 0x7fffffffu;
+    idx[i] = (u32)i;
+  }
+};
+
+struct OwnerMinFn { /* scan_apply body over the key-sorted received items */
+  const u64 *keys;
+  const u32 *idx;
+  const u32 *val; /* by original received index */
+  int *owner_run;
+  u32 *run_of;
+  TMR_HD void operator()(i64 j, u32 heads_before) const {
+    const bool head = (j == 0 || keys[j] != keys[j - 1]);
+    const u32 run = heads_before + (head ? 1u : 0u) - 1u;
+    run_of[j] = run;
+    TMR_ATOMIC_MIN_I32(&owner_run[run], (int)val[idx[j]]);
+  }
+};
+
+struct OwnerReplyFn {
+  const u32 *idx;
+  const u32 *run_of;
+  const int *owner_run;
+  int *reply; /* by original received index */
+  TMR_HD void operator()(i64 j) const {
+    const int o = owner_run[run_of[j]];
+    reply[idx[j]] = (o == 0x7fffffff) ? -1 : o;
+  }
+};
+
+struct FillIntFn {
+  int *p;
+  int v;
+  TMR_HD void operator()(i64 i) const { p[i] = v; }
+};
+
+/* classification of local nodes: 0 dependent, 1 owned here, 2 external */
+struct OwnedFlagFn {
+  const unsigned char *dep_flag;
+  const int *owner; /* NULL on a single rank */
+  int me;
+  TMR_HD u32 operator()(i64 i) const {
+    return (!dep_flag[i] && (!owner || owner[i] == me)) ? 1u : 0u;
+  }
+};
+
+struct ExternalCountFn {
+  const unsigned char *dep_flag;
+  const int *owner;
+  int me;
+  TMR_HD u32 operator()(i64 i) const {
+    return (!dep_flag[i] && owner[i] != me) ? 1u : 0u;
+  }
+};
+
+struct ExternalFillFn {
+  ExternalCountFn c;
+  const u64 *node_keys;
+  u64 *out_keys;
+  u32 *out_dest;
+  u32 *out_node;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    if (c(i)) {
+      out_keys[o] = node_keys[i];
+      out_dest[o] = (u32)(c.owner[i] < 0 ? c.me : c.owner[i]);
+      out_node[o] = (u32)i;
+    }
+  }
+};
+
+struct NumberNodesMultiFn {
+  const unsigned char *dep_flag;
+  const u32 *dep_before;
+  const u32 *owned_before;
+  const int *owner;
+  int me;
+  int first_owned;
+  int *node_num;
+  int *dep_node;
+  TMR_HD void operator()(i64 i) const {
+    if (dep_flag[i]) {
+      node_num[i] = -(int)dep_before[i] - 1;
+      dep_node[dep_before[i]] = (int)i;
+    } else if (!owner || owner[i] == me) {
+      node_num[i] = first_owned + (int)owned_before[i];
+    } else {
+      node_num[i] = 0; /* filled from the owner's reply */
+    }
+  }
+};
+
+struct LookupNumberFn { /* owner side: number of each requested node key */
+  const u64 *req;
+  const u64 *node_keys;
+  i64 n;
+  const int *node_num;
+  int *reply;
+  TMR_HD void operator()(i64 i) const {
+    const i64 j = find_u64(node_keys, n, req[i]);
+    reply[i] = j >= 0 ? node_num[j] : -1;
+  }
+};
+
+struct StoreExternalFn {
+  const u32 *ext_node;
+  const int *number;
+  int *node_num;
+  TMR_HD void operator()(i64 i) const { node_num[ext_node[i]] = number[i]; }
+};
+
 inline int create_nodes(Forest &f, int order, int interp_type,
                         const double *knots) {
   Ctx &ctx = *f.ctx;
+  Comm *comm = ctx.comm;
+  const int me = comm ? comm->rank : 0;
   NodeData &nd = f.nodes;
   if (nd.valid) return 0; /* reference :4071-4075 */
   if (order < 2 || order > kMaxOrder || (interp_type == 2)) {
@@ -626,11 +970,24 @@ inline int create_nodes(Forest &f, int order, int interp_type,
             (long long)E, order);
     return 1;
   }
+  if (comm && comm->size > 64) {
+    fprintf(stderr, "TMROctForest Error: more than 64 ranks are not supported\n");
+    return 1;
+  }
   nd.clear();
   nd.order = order;
   nd.interp_type = interp_type;
   for (int i = 0; i < 4; i++) nd.knots[i] = (i < order) ? knots[i] : 0.0;
   nd.num_elements = E;
+  if (comm) {
+    /* the key depth must agree on every rank */
+    const int Dg = (int)global_max(ctx, *comm, f.fmt.D);
+    if (Dg != f.fmt.D) {
+      RekeyFn rk = {f.keys.get(), f.fmt.D, Dg};
+      launch(ctx, f.n, rk, "rekey");
+      f.fmt.D = Dg;
+    }
+  }
   nd.nfmt.Dn = f.fmt.D + (order > 2 ? 1 : 0);
   nd.nfmt.bbits = f.bbits;
   if (nd.nfmt.total_bits() > 64 || nd.nfmt.Dn + 1 > 21) {
@@ -640,47 +997,140 @@ inline int create_nodes(Forest &f, int order, int interp_type,
             f.nblocks, nd.nfmt.Dn);
     return 1;
   }
-  if (E == 0) {
+  if (E == 0 && !comm) {
     nd.valid = true;
     nd.dep_ptr.alloc(ctx, 1);
     dev_zero(ctx, nd.dep_ptr.get(), sizeof(int));
     return 0;
   }
-
   trace_mark(ctx, NULL);
+
+  /* 0. ghost layer (multi-rank): octants other ranks will probe for */
+  DBuf<u64> ghost;
+  i64 nghost = 0;
+  DBuf<u64> own_store, own_store_n;
+  OwnerMap om = {NULL, 1}, om_n = {NULL, 1};
+  if (comm) {
+    om = make_owner_map(f, f.fmt.D, own_store);
+    om_n = make_owner_map(f, nd.nfmt.Dn, own_store_n);
+    GhostGen gg = {f.keys.get(), f.fmt, f.tables, om, me};
+    GhostCountFn gc = {gg};
+    /* two passes: the count pass sizes the buffers */
+    DBuf<u32> goff(ctx, E);
+    const i64 ng = (i64)scan_counts(ctx, E, gc, goff.get(), "nodes_ghost_count");
+    DBuf<u64> gk(ctx, ng);
+    DBuf<u32> gd(ctx, ng);
+    GhostFillFn gf = {gg, gk.get(), gd.get()};
+    GhostPlaceFn gp = {gf, goff.get()};
+    launch(ctx, E, gp, "nodes_ghost_fill");
+    U32DestFn gdest = {gd.get()};
+    RoutePlan plan;
+    make_route(ctx, *comm, ng, gdest, plan);
+    route_array(ctx, *comm, plan, gk.get(), ghost);
+    nghost = plan.nrecv;
+    if (nghost > 1) {
+      DBuf<u64> alt(ctx, nghost);
+      DBuf<u32> v0, v1;
+      radix_sort(ctx, ghost, alt, v0, v1, nghost, 0, f.fmt.total_bits());
+      nghost = unique_keep_last(ctx, ghost, alt, v0, v1, nghost, 0);
+    }
+    trace_mark(ctx, "nodes: ghost layer");
+  }
+
   /* 1. hanging faces / edges */
   if (!f.info.get()) f.info.alloc(ctx, E);
   DBuf<u32> elem_index_store;
   const KeyIndex elem_ix = build_key_index(
       ctx, f.keys.get(), E, (u64)f.nblocks << (3 * f.fmt.D + 5), elem_index_store);
-  ElemView ev = {f.keys.get(), E, f.fmt, f.tables, elem_ix};
+  ElemView ev = {f.keys.get(), E, f.fmt, f.tables, elem_ix, ghost.get(), nghost};
   HangingFn hang = {ev, f.info.get()};
   launch(ctx, E, hang, "nodes_hanging_info");
-
   trace_mark(ctx, "nodes: hanging info");
+
   /* 2. node candidates -> sort -> unique nodes + local connectivity */
   const i64 nc = E * npe;
   nd.conn.alloc(ctx, nc);
   i64 Nn;
+  DBuf<unsigned char> created;
   {
-    DBuf<u64> ck(ctx, nc), ck_alt(ctx, nc);
-    DBuf<u32> cv(ctx, nc), cv_alt(ctx, nc);
+    /* multi-rank: also the parent edge/face nodes of hanging elements */
+    i64 nextra = 0;
+    DBuf<u32> poff;
+    ParentNodeGen pg = {f.keys.get(), f.info.get(), f.fmt, nd.nfmt, f.tables, order};
+    if (comm) {
+      poff.alloc(ctx, E);
+      ParentNodeCountFn pc = {pg};
+      nextra = (i64)scan_counts(ctx, E, pc, poff.get(), "nodes_parent_count");
+    }
+    const i64 ntot = nc + nextra;
+    if (ntot >= (1LL << 32) - 1) {
+      fprintf(stderr, "TMROctForest Error: too many node candidates\n");
+      return 1;
+    }
+    DBuf<u64> ck(ctx, ntot), ck_alt(ctx, ntot);
+    DBuf<u32> cv(ctx, ntot), cv_alt(ctx, ntot);
     NodeCandFn cand = {f.keys.get(), f.fmt, nd.nfmt, f.tables,
                        order,        ck.get(), cv.get()};
     launch(ctx, E, cand, "nodes_candidates");
+    if (nextra) {
+      ParentNodeFillFn pf = {pg, ck.get() + nc, cv.get() + nc};
+      ParentPlaceFn pp = {pf, poff.get()};
+      launch(ctx, E, pp, "nodes_parent_fill");
+    }
     trace_mark(ctx, "nodes: candidates");
-    radix_sort(ctx, ck, ck_alt, cv, cv_alt, nc, 0, nd.nfmt.total_bits());
+    radix_sort(ctx, ck, ck_alt, cv, cv_alt, ntot, 0, nd.nfmt.total_bits());
     trace_mark(ctx, "nodes: sort");
     /* the number of unique nodes is not known before the scan: node keys are
        written into the (now free) ping-pong buffer and trimmed afterwards */
+    if (comm) {
+      created.alloc(ctx, ntot);
+      dev_zero(ctx, created.get(), (size_t)ntot);
+    }
     RunHeadFn rh = {ck.get()};
-    NodeScatterFn sc = {ck.get(), cv.get(), ck_alt.get(), nd.conn.get()};
-    Nn = (i64)scan_apply(ctx, nc, rh, sc, "nodes_unique_scatter_conn");
+    NodeScatterFn sc = {ck.get(), cv.get(), ck_alt.get(), nd.conn.get(),
+                        created.get()};
+    Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
     nd.node_keys.alloc(ctx, Nn);
     copy_d2d(ctx, nd.node_keys.get(), ck_alt.get(), (size_t)Nn * sizeof(u64));
   }
   nd.num_local_nodes = Nn;
   trace_mark(ctx, "nodes: unique+conn");
+
+  /* 2b. node ownership (multi-rank): lowest rank that creates the node from an
+     element (reference createLocalNodes :4538-4637) */
+  DBuf<int> owner;
+  if (comm) {
+    NodeHomeFn home = {nd.node_keys.get(), nd.nfmt.Dn, om_n};
+    RoutePlan plan;
+    make_route(ctx, *comm, Nn, home, plan);
+    DBuf<u64> rk;
+    DBuf<unsigned char> rc;
+    route_array(ctx, *comm, plan, nd.node_keys.get(), rk);
+    route_array(ctx, *comm, plan, created.get(), rc);
+    const i64 nr = plan.nrecv;
+    DBuf<int> reply(ctx, nr);
+    if (nr > 0) {
+      DBuf<i64> d_roff(ctx, comm->size + 1);
+      copy_h2d(ctx, d_roff.get(), plan.recv_off.data(),
+               (size_t)(comm->size + 1) * sizeof(i64));
+      DBuf<u32> val(ctx, nr), idx(ctx, nr), idx_alt(ctx, nr);
+      DonorValueFn dv = {rc.get(), d_roff.get(), comm->size, val.get(), idx.get()};
+      launch(ctx, nr, dv, "nodes_donor_value");
+      DBuf<u64> rk_alt(ctx, nr);
+      radix_sort(ctx, rk, rk_alt, idx, idx_alt, nr, 0, nd.nfmt.total_bits());
+      DBuf<int> owner_run(ctx, nr);
+      FillIntFn fi = {owner_run.get(), 0x7fffffff};
+      launch(ctx, nr, fi, "nodes_owner_init");
+      DBuf<u32> run_of(ctx, nr);
+      RunHeadFn rh = {rk.get()};
+      OwnerMinFn omin = {rk.get(), idx.get(), val.get(), owner_run.get(), run_of.get()};
+      scan_apply(ctx, nr, rh, omin, "nodes_owner_min");
+      OwnerReplyFn orf = {idx.get(), run_of.get(), owner_run.get(), reply.get()};
+      launch(ctx, nr, orf, "nodes_owner_reply");
+    }
+    route_back(ctx, *comm, plan, reply.get(), owner);
+    trace_mark(ctx, "nodes: ownership");
+  }
 
   /* 3. dependent labels and numbering */
   DBuf<unsigned char> dep_flag(ctx, Nn);
@@ -692,15 +1142,50 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   DepFlagFn df = {dep_flag.get()};
   const i64 Nd = (i64)scan_counts(ctx, Nn, df, dep_before.get(), "nodes_dep_scan");
   nd.num_dep_nodes = Nd;
-  nd.num_owned_nodes = Nn - Nd;
-  nd.node_range_start = 0;
   nd.node_num.alloc(ctx, Nn);
   DBuf<int> dep_node(ctx, Nd);
-  NumberNodesFn num = {dep_flag.get(), dep_before.get(), nd.node_range_start,
-                       nd.node_num.get(), dep_node.get()};
-  launch(ctx, Nn, num, "nodes_number");
-
+  if (!comm) {
+    nd.num_owned_nodes = Nn - Nd;
+    nd.node_range_start = 0;
+    NumberNodesFn num = {dep_flag.get(), dep_before.get(), nd.node_range_start,
+                         nd.node_num.get(), dep_node.get()};
+    launch(ctx, Nn, num, "nodes_number");
+  } else {
+    DBuf<u32> owned_before(ctx, Nn);
+    OwnedFlagFn of = {dep_flag.get(), owner.get(), me};
+    const i64 nown = (i64)scan_counts(ctx, Nn, of, owned_before.get(), "nodes_owned_scan");
+    std::vector<i64> all(comm->size);
+    comm->allgather_host(ctx, &nown, all.data(), sizeof(i64));
+    i64 start = 0;
+    for (int r = 0; r < me; r++) start += all[r];
+    nd.num_owned_nodes = nown;
+    nd.node_range_start = (int)start;
+    NumberNodesMultiFn num = {dep_flag.get(), dep_before.get(), owned_before.get(),
+                              owner.get(),    me,               (int)start,
+                              nd.node_num.get(), dep_node.get()};
+    launch(ctx, Nn, num, "nodes_number");
+    /* numbers of the nodes owned elsewhere (reference :4183-4235) */
+    DBuf<u64> xk(ctx, Nn);
+    DBuf<u32> xd(ctx, Nn), xn(ctx, Nn);
+    ExternalCountFn xc = {dep_flag.get(), owner.get(), me};
+    ExternalFillFn xf = {xc, nd.node_keys.get(), xk.get(), xd.get(), xn.get()};
+    const i64 nx = (i64)scan_apply(ctx, Nn, xc, xf, "nodes_external_list");
+    U32DestFn xdest = {xd.get()};
+    RoutePlan plan;
+    make_route(ctx, *comm, nx, xdest, plan);
+    DBuf<u64> req;
+    route_array(ctx, *comm, plan, xk.get(), req);
+    DBuf<int> rep(ctx, plan.nrecv);
+    LookupNumberFn lk = {req.get(), nd.node_keys.get(), Nn, nd.node_num.get(),
+                         rep.get()};
+    launch(ctx, plan.nrecv, lk, "nodes_external_lookup");
+    DBuf<int> got;
+    route_back(ctx, *comm, plan, rep.get(), got);
+    StoreExternalFn se = {xn.get(), got.get(), nd.node_num.get()};
+    launch(ctx, nx, se, "nodes_external_store");
+  }
   trace_mark(ctx, "nodes: label+number");
+
   /* 4. dependent-node CSR */
   nd.dep_ptr.alloc(ctx, Nd + 1);
   if (Nd > 0) {
@@ -744,8 +1229,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     dev_zero(ctx, nd.dep_ptr.get(), sizeof(int));
     nd.dep_nnz = 0;
   }
-
   trace_mark(ctx, "nodes: dep CSR");
+
   /* 5. local -> global numbers in the connectivity */
   ConnRemapInPlaceFn rm = {nd.node_num.get(), nd.conn.get()};
   launch(ctx, nc, rm, "nodes_conn_remap");

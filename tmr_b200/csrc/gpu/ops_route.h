@@ -1,0 +1,157 @@
+/*
+  ops_route.h -- ownership lookup and all-to-all-v routing of device arrays
+  (the GPU form of distributeOctants / sendOctants, reference
+  src/TMROctForest.cpp:2334-2509).
+*/
+#ifndef TMRGPU_OPS_ROUTE_H
+#define TMRGPU_OPS_ROUTE_H
+
+#include "ops_balance.h"
+
+namespace tmrgpu {
+
+/* ---- ownership ------------------------------------------------------------- */
+/* position key at Morton depth Dp: [block | Morton_Dp] */
+struct OwnerMap {
+  const u64 *pos; /* device, R entries, positions of owners[] at depth Dp */
+  int R;
+  TMR_HD int owner(u64 p) const {
+    int r = 0;
+    while (r < R - 1 && pos[r + 1] <= p) r++;
+    return r;
+  }
+};
+
+/* owners[] as position keys at depth Dp (sentinel = one past the block) */
+inline void owner_positions(const Forest &f, int Dp, std::vector<u64> &out) {
+  const int R = (int)f.owners.size();
+  out.resize(R);
+  for (int r = 0; r < R; r++) {
+    const Oct24 &o = f.owners[r];
+    if (o.x >= kHmax || o.y >= kHmax || o.z >= kHmax) {
+      out[r] = ((u64)(u32)(o.block + 1)) << (3 * Dp);
+    } else {
+      const int s = kMaxLevel - Dp;
+      out[r] = ((u64)(u32)o.block << (3 * Dp)) |
+               morton3((u32)o.x >> s, (u32)o.y >> s, (u32)o.z >> s);
+    }
+  }
+}
+
+inline OwnerMap make_owner_map(Forest &f, int Dp, DBuf<u64> &store) {
+  std::vector<u64> h;
+  owner_positions(f, Dp, h);
+  store.alloc(*f.ctx, (i64)h.size());
+  copy_h2d(*f.ctx, store.get(), h.data(), h.size() * sizeof(u64));
+  OwnerMap m = {store.get(), (int)h.size()};
+  return m;
+}
+
+/* ---- routing ---------------------------------------------------------------- */
+struct RoutePlan {
+  DBuf<u32> idx;                 /* send position -> source index */
+  std::vector<i64> send_off, recv_off;
+  i64 nsend, nrecv;
+  RoutePlan() : nsend(0), nrecv(0) {}
+};
+
+template <class DestFn>
+struct DestKeyFn {
+  DestFn dest;
+  u64 *dk;
+  u32 *idx;
+  TMR_HD void operator()(i64 i) const {
+    dk[i] = (u64)(u32)dest(i);
+    idx[i] = (u32)i;
+  }
+};
+
+struct DestBoundsFn {
+  const u64 *dk;
+  i64 n;
+  i64 *bounds;
+  TMR_HD void operator()(i64 r) const { bounds[r] = lower_bound_u64(dk, n, (u64)r); }
+};
+
+/* group items by destination rank and agree on the all-to-all-v layout */
+template <class DestFn>
+void make_route(Ctx &ctx, Comm &comm, i64 n, DestFn dest, RoutePlan &plan) {
+  const int R = comm.size;
+  plan.idx.alloc(ctx, n);
+  plan.send_off.assign(R + 1, 0);
+  plan.recv_off.assign(R + 1, 0);
+  if (n > 0) {
+    DBuf<u64> dk(ctx, n), dk_alt(ctx, n);
+    DBuf<u32> idx_alt(ctx, n);
+    DestKeyFn<DestFn> k = {dest, dk.get(), plan.idx.get()};
+    launch(ctx, n, k, "route_dest");
+    int bits = 1;
+    while ((1 << bits) < R) bits++;
+    radix_sort(ctx, dk, dk_alt, plan.idx, idx_alt, n, 0, bits);
+    DBuf<i64> d_bounds(ctx, R + 1);
+    DestBoundsFn b = {dk.get(), n, d_bounds.get()};
+    launch(ctx, R + 1, b, "route_bounds");
+    copy_d2h(ctx, plan.send_off.data(), d_bounds.get(), (size_t)(R + 1) * sizeof(i64));
+  }
+  std::vector<i64> sc(R), rc(R);
+  for (int r = 0; r < R; r++) sc[r] = plan.send_off[r + 1] - plan.send_off[r];
+  exchange_counts(ctx, comm, sc.data(), rc.data());
+  for (int r = 0; r < R; r++) plan.recv_off[r + 1] = plan.recv_off[r] + rc[r];
+  plan.nsend = n;
+  plan.nrecv = plan.recv_off[R];
+}
+
+template <class T>
+struct GatherFn {
+  const T *src;
+  const u32 *idx;
+  T *dst;
+  TMR_HD void operator()(i64 i) const { dst[i] = src[idx[i]]; }
+};
+
+template <class T>
+struct ScatterFn {
+  const T *src;
+  const u32 *idx;
+  T *dst;
+  TMR_HD void operator()(i64 i) const { dst[idx[i]] = src[i]; }
+};
+
+/* ship src[] according to the plan; out holds plan.nrecv items grouped by
+   source rank (recv_off) */
+template <class T>
+void route_array(Ctx &ctx, Comm &comm, const RoutePlan &plan, const T *src,
+                 DBuf<T> &out) {
+  DBuf<T> send(ctx, plan.nsend);
+  GatherFn<T> g = {src, plan.idx.get(), send.get()};
+  launch(ctx, plan.nsend, g, "route_gather");
+  out.alloc(ctx, plan.nrecv);
+  comm.alltoallv(ctx, send.get(), plan.send_off.data(), out.get(),
+                 plan.recv_off.data(), sizeof(T));
+}
+
+/* replies travel the plan backwards: reply[] is aligned with what this rank
+   RECEIVED; out[] (size nsend) is aligned with the original item order */
+template <class T>
+void route_back(Ctx &ctx, Comm &comm, const RoutePlan &plan, const T *reply,
+                DBuf<T> &out) {
+  DBuf<T> tmp(ctx, plan.nsend);
+  comm.alltoallv(ctx, reply, plan.recv_off.data(), tmp.get(),
+                 plan.send_off.data(), sizeof(T));
+  out.alloc(ctx, plan.nsend);
+  ScatterFn<T> s = {tmp.get(), plan.idx.get(), out.get()};
+  launch(ctx, plan.nsend, s, "route_scatter_back");
+}
+
+/* global max / sum / or of a small host value */
+inline i64 global_max(Ctx &ctx, Comm &comm, i64 v) {
+  std::vector<i64> all(comm.size);
+  comm.allgather_host(ctx, &v, all.data(), sizeof(i64));
+  i64 m = all[0];
+  for (int r = 1; r < comm.size; r++) m = all[r] > m ? all[r] : m;
+  return m;
+}
+
+}  // namespace tmrgpu
+
+#endif

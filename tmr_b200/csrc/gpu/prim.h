@@ -29,8 +29,11 @@ struct KernelStat {
   KernelStat() : launches(0), ms(0.0) {}
 };
 
+class Comm;
+
 struct Ctx {
   int device;
+  Comm *comm; /* NULL = single rank */
   void *stream; /* cudaStream_t */
   int profile;  /* time every named launch with events */
   int num_sms;
@@ -43,8 +46,8 @@ struct Ctx {
   int trace;        /* TMR_B200_TRACE=1: print synchronised phase times */
   double trace_t0;  /* wall clock of the previous mark (s) */
   Ctx()
-      : device(0), stream(NULL), profile(0), num_sms(148), launch_count(0),
-        trace(0), trace_t0(0.0) {}
+      : device(0), comm(NULL), stream(NULL), profile(0), num_sms(148),
+        launch_count(0), trace(0), trace_t0(0.0) {}
 };
 
 /* --- runtime (prim_cuda.cu / tests/emu/prim_emu.cpp) ---------------------- */

@@ -8,10 +8,18 @@
 #include <sstream>
 
 #include "ops_interp.h"
+#include "ops_multi.h"
 #include "ops_nodes.h"
 #include "tmrgpu.h"
 
 using namespace tmrgpu;
+
+namespace tmrgpu {
+int comm_unique_id(void *out, int out_bytes);
+Comm *comm_create(Ctx &ctx, int rank, int size, const void *id_bytes);
+void comm_destroy(Comm *c);
+}  // namespace tmrgpu
+
 
 struct tmrgpu_ctx {
   Ctx c;
@@ -65,6 +73,23 @@ int tmrgpu_profile_json(tmrgpu_ctx *ctx, char *buf, int buflen) {
 }
 
 long tmrgpu_launch_count(tmrgpu_ctx *ctx) { return ctx->c.launch_count; }
+
+int tmrgpu_comm_unique_id(void *out, int out_bytes) {
+  return comm_unique_id(out, out_bytes);
+}
+
+int tmrgpu_ctx_init_comm(tmrgpu_ctx *ctx, int rank, int size, const void *id) {
+  if (ctx->c.comm) {
+    comm_destroy(ctx->c.comm);
+    ctx->c.comm = NULL;
+  }
+  if (size <= 1) return 0;
+  ctx->c.comm = comm_create(ctx->c, rank, size, id);
+  return ctx->c.comm ? 0 : 1;
+}
+
+int tmrgpu_ctx_rank(tmrgpu_ctx *ctx) { return ctx->c.comm ? ctx->c.comm->rank : 0; }
+int tmrgpu_ctx_size(tmrgpu_ctx *ctx) { return ctx->c.comm ? ctx->c.comm->size : 1; }
 
 int tmrgpu_forest_create(tmrgpu_ctx *ctx, tmrgpu_forest **out) {
   *out = new tmrgpu_forest(&ctx->c);
@@ -172,39 +197,75 @@ int tmrgpu_download_info(tmrgpu_forest *F, int16_t *info) {
 
 int tmrgpu_sort_unique(tmrgpu_forest *f) {
   sort_unique_elements(f->f);
+  if (unify_depth(f->f)) return 1;
+  if (gather_owners(f->f, 1)) return 1; /* createRandomTrees (:1905-1916) */
   return check_errors(*f->f.ctx, "sort_unique");
 }
 
 int tmrgpu_create_trees(tmrgpu_forest *f, int level, int block_start,
                         int block_end) {
-  return create_trees(f->f, level, block_start, block_end);
+  if (create_trees(f->f, level, block_start, block_end)) return 1;
+  if (unify_depth(f->f)) return 1;
+  return gather_owners(f->f, 1); /* back-fill quirk of createTrees (:1826-1832) */
+}
+
+int tmrgpu_repartition(tmrgpu_forest *f, int max_rank) {
+  return repartition(f->f, max_rank);
+}
+
+int tmrgpu_get_owners(tmrgpu_forest *F, tmrgpu_octant *out) {
+  Forest &f = F->f;
+  for (size_t r = 0; r < f.owners.size(); r++) {
+    memcpy(&out[r], &f.owners[r], sizeof(Oct24));
+  }
+  return 0;
+}
+
+int tmrgpu_node_range(tmrgpu_forest *F, int *out) {
+  Forest &f = F->f;
+  Ctx &ctx = *f.ctx;
+  const int R = part_size(f);
+  i64 mine = f.nodes.num_owned_nodes;
+  std::vector<i64> all(R, mine);
+  if (ctx.comm) ctx.comm->allgather_host(ctx, &mine, all.data(), sizeof(i64));
+  out[0] = 0;
+  for (int r = 0; r < R; r++) out[r + 1] = out[r] + (int)all[r];
+  return 0;
 }
 
 int tmrgpu_refine_device(tmrgpu_forest *f, const int *d_flags, int min_level,
                          int max_level) {
-  return refine(f->f, d_flags, min_level, max_level);
+  if (refine(f->f, d_flags, min_level, max_level)) return 1;
+  return refine_exchange(f->f); /* no-op on a single rank */
 }
 
 int tmrgpu_refine(tmrgpu_forest *F, const int *h_flags, int min_level,
                   int max_level) {
   Forest &f = F->f;
-  if (!h_flags || f.n == 0) return refine(f, NULL, min_level, max_level);
+  if (!h_flags || f.n == 0) {
+    if (refine(f, NULL, min_level, max_level)) return 1;
+    return refine_exchange(f);
+  }
   DBuf<int> d_flags(*f.ctx, f.n);
   copy_h2d(*f.ctx, d_flags.get(), h_flags, (size_t)f.n * sizeof(int));
-  return refine(f, d_flags.get(), min_level, max_level);
+  if (refine(f, d_flags.get(), min_level, max_level)) return 1;
+  return refine_exchange(f);
 }
 
 int tmrgpu_balance(tmrgpu_forest *f, int balance_corner) {
+  if (f->f.ctx->comm) return balance_multi(f->f, balance_corner);
   return balance(f->f, balance_corner);
 }
 
 int tmrgpu_coarsen(tmrgpu_forest *src, tmrgpu_forest *dst) {
   tmrgpu_share_connectivity(src, dst);
-  return coarsen_into(src->f, dst->f);
+  if (coarsen_into(src->f, dst->f)) return 1;
+  return gather_owners(dst->f, 0); /* reference :2157-2160 */
 }
 
 int tmrgpu_duplicate(tmrgpu_forest *src, tmrgpu_forest *dst) {
   tmrgpu_share_connectivity(src, dst);
+  dst->f.owners = src->f.owners; /* reference :2104-2106 */
   return duplicate_into(src->f, dst->f);
 }
 

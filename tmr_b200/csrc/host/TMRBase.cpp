@@ -9,8 +9,10 @@
 #include <stdio.h>
 
 static int tmr_initialized = 0;
-static int world_rank = 0;
-static int world_size = 1;
+/* thread_local: one process normally drives one GPU, but the test-only
+   emulation runs several ranks as threads of one process */
+static thread_local int world_rank = 0;
+static thread_local int world_size = 1;
 
 extern "C" {
 void tmr_b200_set_world(int rank, int size) {

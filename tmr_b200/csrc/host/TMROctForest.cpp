@@ -586,14 +586,18 @@ void TMROctForest::createRandomTrees(int nrand, int min_level, int max_level) {
 
 /* ---- repartition (reference :1922-2088) ------------------------------------------ */
 void TMROctForest::repartition(int max_rank) {
-  (void)max_rank;
-  dropMeshData(0, 1);
-  if (mpi_size > 1) {
+  if (!tables || !dev) {
     fprintf(stderr,
-            "TMROctForest Error: multi-rank repartition() is not available in "
-            "this build\n");
+            "TMROctForest Error: Cannot call repartition(), no octants have "
+            "been created\n");
+    return;
   }
-  /* single rank: the partition is the whole sorted array; tags stay = index */
+  dropMeshData(0, 1);
+  if (syncOctantsToDevice()) return;
+  if (mpi_size > 1) {
+    /* equal-count re-split over NCCL; on one rank nothing moves */
+    if (tmrgpu_repartition(dev, max_rank) == 0) octantsReplacedOnDevice();
+  }
 }
 
 /* ---- duplicate / coarsen (reference :2097-2164) ----------------------------------- */
@@ -701,11 +705,7 @@ void TMROctForest::fetchNodeData() {
   tmrgpu_download_sorted_node_numbers(dev, node_numbers);
   /* node_range: owned-node prefix over ranks (reference :4165-4172) */
   node_range = new int[mpi_size + 1];
-  std::fill(node_range, node_range + mpi_size + 1, 0);
-  for (int r = mpi_rank + 1; r <= mpi_size; r++) {
-    node_range[r] = (int)s[5] + num_owned_nodes;
-  }
-  for (int r = 0; r <= mpi_rank; r++) node_range[r] = (int)s[5];
+  tmrgpu_node_range(dev, node_range);
   int *item = std::lower_bound(node_numbers, node_numbers + num_local_nodes,
                                node_range[mpi_rank]);
   ext_pre_offset = (int)(item - node_numbers);

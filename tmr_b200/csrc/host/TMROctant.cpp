@@ -14,9 +14,9 @@
 #include "tmrgpu.h"
 
 /* ---- process-wide context --------------------------------------------------- */
-static tmrgpu_ctx *g_ctx = NULL;
-static void *g_stream = NULL;
-static int g_ctx_failed = 0;
+static thread_local tmrgpu_ctx *g_ctx = NULL;
+static thread_local void *g_stream = NULL;
+static thread_local int g_ctx_failed = 0;
 
 extern "C" void tmr_b200_use_stream(void *stream) { g_stream = stream; }
 

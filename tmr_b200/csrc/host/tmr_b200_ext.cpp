@@ -13,4 +13,15 @@ tmrgpu_forest *tmr_b200_device_forest(void *forest) {
   return static_cast<TMROctForest *>(forest)->getDeviceForest();
 }
 
+/* attach this process (thread) to a world of `size` ranks: sets what
+   MPI_Comm_rank/size report to the drop-in classes and connects the CUDA
+   context to the NCCL communicator identified by `id`
+   (tmrgpu_comm_unique_id).  Collective over the world. */
+int tmr_b200_init_world(int rank, int size, const void *id) {
+  tmr_b200_set_world(rank, size);
+  tmrgpu_ctx *ctx = tmr_b200_context();
+  if (!ctx) return 1;
+  return tmrgpu_ctx_init_comm(ctx, rank, size, id);
+}
+
 }  // extern "C"
