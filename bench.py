@@ -205,6 +205,9 @@ def main():
     ap.add_argument("--passes", type=int, default=FULL["passes"],
                     help="refinement passes of the recipe (4 = the named ~86M config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="N>1: split the SAME 8x8x8-tree forest over the GPUs "
+                         "(default: weak scaling, 8x8x8N trees)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_main(args)
@@ -227,6 +230,10 @@ def main():
     stream = torch.cuda.current_stream()
     tmr_b200.use_stream(stream.cuda_stream)
     lib = tmr_b200.require_gpu()
+    if world > 1:
+        from tmr_b200 import dist as tdist
+
+        tdist.init_from_torch(lib)
 
     P, I64 = ctypes.c_void_p, ctypes.c_int64
     lib.tmr_b200_context.restype = P
@@ -246,6 +253,7 @@ def main():
         ("tmrgpu_profile_reset", [P]),
         ("tmrgpu_profile_json", [P, ctypes.c_char_p, ctypes.c_int]),
         ("tmrgpu_count", [P]),
+        ("tmrgpu_repartition", [P, ctypes.c_int]),
         ("tmrgpu_copy_d2h", [P, P, P, I64]),
     ]:
         getattr(lib, name).argtypes = argt
@@ -259,12 +267,17 @@ def main():
     knots = (ctypes.c_double * 2)(-1.0, 1.0)
 
     # ---- build-up: everything before the timed cycle, all on the device ----
-    # N>1 (until the NCCL exchange lands): every rank owns an independent
-    # forest of the same recipe (replicas of disjoint tree sets).
+    # N>1: ONE forest partitioned along the Morton curve over the N GPUs
+    # (NCCL exchanges inside refine/balance/repartition/createNodes).  Weak
+    # scaling stacks N copies of the 8x8x8-tree box along z (8x8x8N trees);
+    # --strong splits the same 8x8x8 box.
+    nbz = cfg["nb"] * (1 if (args.strong or world == 1) else world)
     base = OctForest(order=cfg["order"], lib=lib)
-    base.setConnectivity(util.structured_conn(cfg["nb"]))
+    base.setConnectivity(util.structured_conn(cfg["nb"], cfg["nb"], nbz))
     base.createTrees(cfg["level"])
     bdev = P(lib.tmr_b200_device_forest(base._ptr))
+    if world > 1:
+        assert lib.tmrgpu_repartition(bdev, -1) == 0
 
     def synth(dev, seed):
         n = lib.tmrgpu_count(dev)
@@ -277,6 +290,8 @@ def main():
         buf, _ = synth(bdev, cfg["seed"] + p)
         assert lib.tmrgpu_refine_device(bdev, buf, 0, 30) == 0
         assert lib.tmrgpu_balance(bdev, cfg["corner"]) == 0
+        if world > 1:
+            assert lib.tmrgpu_repartition(bdev, -1) == 0
         lib.tmrgpu_dev_free(ctx, buf)
     d_flags, e_in = synth(bdev, cfg["seed"] + cfg["passes"] - 1)
     # host copy of the flags for the e2e arm (pinned)
@@ -290,6 +305,8 @@ def main():
         wdev = P(lib.tmr_b200_device_forest(work._ptr))
         assert lib.tmrgpu_refine_device(wdev, d_flags, 0, 30) == 0
         assert lib.tmrgpu_balance(wdev, cfg["corner"]) == 0
+        if world > 1:
+            assert lib.tmrgpu_repartition(wdev, -1) == 0
         assert lib.tmrgpu_create_nodes(wdev, cfg["order"], 1, knots) == 0
         return work, wdev
 
@@ -298,6 +315,8 @@ def main():
         work = base.duplicate()
         lib.tmrc_refine(work._ptr, h_flags.ctypes.data, 0, 30)  # H2D inside
         lib.tmrc_balance(work._ptr, cfg["corner"])
+        if world > 1:
+            lib.tmrc_repartition(work._ptr, -1)
         lib.tmrc_create_nodes(work._ptr)
         cptr = ctypes.POINTER(ctypes.c_int)()
         ne, no = ctypes.c_int(0), ctypes.c_int(0)
@@ -345,12 +364,19 @@ def main():
     del work, last
 
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(e_final)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(e_final), float(e_in)], dtype=torch.float64, device="cuda")
+    # 64-bit wrap-around checksum: reduce as two 32-bit halves
+    cs = torch.tensor([csum.value & 0xFFFFFFFF, csum.value >> 32], dtype=torch.int64,
+                      device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
     ms = float(t.item())
-    total_octants = float(tot.item())
+    total_octants = float(tot[0].item())
+    total_in = float(tot[1].item())
+    lo, hi = int(cs[0].item()), int(cs[1].item())
+    global_checksum = (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
     value = total_octants * args.steps / (ms * 1e-3)
 
     # ---- end-to-end arm --------------------------------------------------------
@@ -424,13 +450,17 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
+            "vs_baseline": None,
             "dtype": "int32 keys as u64 Morton + f64 weights", "data": "synthetic",
             "config": {"workload": workload_name(cfg),
                        "octants_in": int(e_in), "octants_out_per_gpu": int(e_final),
                        "local_nodes": int(sizes[1]), "dep_nodes": int(sizes[2]),
-                       "dep_nnz": int(sizes[4]), "checksum": "%016x" % csum.value,
-                       "parallelism": "1 GPU" if world == 1 else "%d independent forests (replicas)" % world,
+                       "dep_nnz": int(sizes[4]), "checksum": "%016x" % global_checksum,
+                       "octants_out_total": int(total_octants), "octants_in_total": int(total_in),
+                       "parallelism": "1 GPU" if world == 1 else
+                       "%d GPUs, one forest SFC-partitioned, NCCL all-to-all-v (%s: %dx%dx%d trees); cycle includes repartition()"
+                       % (world, "strong" if args.strong else "weak", cfg["nb"], cfg["nb"], nbz),
                        "l2": "inputs larger than L2 (%.0f MB of keys per pass)" % (8e-6 * e_final)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * e_in),
                     "d2h_bytes_per_step": int(d2h)},

@@ -68,19 +68,19 @@ def connector_conn():
         dtype=np.int32).reshape(15, 8)
 
 
-def structured_conn(nb):
-    """nb^3 box of trees, node id i + (nb+1)(j + (nb+1)k), corners in bit order
-    (SURVEY.md 8(d))."""
-    n1 = nb + 1
-    conn = np.zeros((nb * nb * nb, 8), dtype=np.int32)
-    b = 0
-    for k in range(nb):
-        for j in range(nb):
-            for i in range(nb):
-                for c in range(8):
-                    ii, jj, kk = i + (c & 1), j + ((c >> 1) & 1), k + (c >> 2)
-                    conn[b, c] = ii + n1 * (jj + n1 * kk)
-                b += 1
+def structured_conn(nb, nby=None, nbz=None):
+    """nb x nby x nbz box of trees (nb^3 by default), node id
+    i + (nb+1)(j + (nby+1)k), corners in bit order."""
+    nby = nb if nby is None else nby
+    nbz = nb if nbz is None else nbz
+    nx1, ny1 = nb + 1, nby + 1
+    i, j, k = np.meshgrid(np.arange(nb), np.arange(nby), np.arange(nbz), indexing="ij")
+    # block index runs x fastest
+    order = np.lexsort((i.ravel(), j.ravel(), k.ravel()))
+    i, j, k = i.ravel()[order], j.ravel()[order], k.ravel()[order]
+    conn = np.zeros((nb * nby * nbz, 8), dtype=np.int32)
+    for c in range(8):
+        conn[:, c] = (i + (c & 1)) + nx1 * ((j + ((c >> 1) & 1)) + ny1 * (k + (c >> 2)))
     return conn
 
 

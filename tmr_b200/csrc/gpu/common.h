@@ -63,6 +63,22 @@
 
 namespace tmrgpu {
 
+/* fetch-and-add returning the previous value */
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+unsigned long long fetch_add_u64(unsigned long long *p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  const unsigned long long old = *p;
+  *p = old + v;
+  return old;
+#endif
+}
+
 typedef uint64_t u64;
 typedef uint32_t u32;
 typedef int64_t i64;

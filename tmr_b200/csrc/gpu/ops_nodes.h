@@ -65,23 +65,43 @@ struct ElemView {
   KeyFmt fmt;
   ConnTables t;
   KeyIndex ix;
-  const u64 *ghost; /* sorted octants received from neighbouring ranks */
-  i64 nghost;
+  /* multi-rank: probes that land in another rank's range become queries
+     (key, owner, element*8+bit) answered by that rank -- a pull-style ghost
+     exchange: only elements on the partition surface generate traffic */
+  OwnerMap om;
+  int me;
+  int multi;
+  u64 *fq_key;
+  u32 *fq_dest;
+  u64 *fq_code;
+  unsigned long long *fq_count;
+  i64 fq_cap;
 
-  TMR_HD bool leaf_exists(i32 block, i32 x, i32 y, i32 z, int level) const {
+  TMR_HD bool probe(i32 block, i32 x, i32 y, i32 z, int level, u64 code) const {
     const u64 key = fmt.encode(block, x, y, z, level);
-    if (ix.find(keys, key) >= 0) return true;
-    return nghost > 0 && find_u64(ghost, nghost, key) >= 0;
+    if (multi) {
+      const int o = om.owner(key >> 5);
+      if (o != me) {
+        const unsigned long long slot = fetch_add_u64(fq_count, 1ULL);
+        if ((i64)slot < fq_cap) {
+          fq_key[slot] = key;
+          fq_dest[slot] = (u32)o;
+          fq_code[slot] = code;
+        }
+        return false;
+      }
+    }
+    return ix.find(keys, key) >= 0;
   }
-  TMR_HD bool leaf_exists_near(i32 block, i32 x, i32 y, i32 z, int level,
-                               i64) const {
-    return leaf_exists(block, x, y, z, level);
+  TMR_HD bool leaf_exists(i32 block, i32 x, i32 y, i32 z, int level) const {
+    return ix.find(keys, fmt.encode(block, x, y, z, level)) >= 0;
   }
+
   /* is there a level-`level` leaf in another tree that is the image of the
      out-of-tree octant (x,y,z) across face f?  (reference checkAdjacentFaces
      src/TMROctForest.cpp:3465-3521) */
-  TMR_HD bool across_face(int f, i32 block, i32 x, i32 y, i32 z,
-                          int level) const {
+  TMR_HD bool across_face(int f, i32 block, i32 x, i32 y, i32 z, int level,
+                          u64 code) const {
     const i32 h = 1 << (kMaxLevel - level);
     const i32 M = kHmax - h;
     const int face = t.block_face_conn[6 * block + f];
@@ -96,13 +116,13 @@ struct ElemView {
       i32 a1, b1, X, Y, Z;
       owner_to_face(t.block_face_ids[6 * adj + af], M, u, v, &a1, &b1);
       face_place(af, M * (af & 1), a1, b1, &X, &Y, &Z);
-      if (leaf_exists(adj, X, Y, Z, level)) return true;
+      if (probe(adj, X, Y, Z, level, code)) return true;
     }
     return false;
   }
   /* same across tree edge e (reference checkAdjacentEdges :3532-3605) */
-  TMR_HD bool across_edge(int e, i32 block, i32 x, i32 y, i32 z,
-                          int level) const {
+  TMR_HD bool across_edge(int e, i32 block, i32 x, i32 y, i32 z, int level,
+                          u64 code) const {
     const i32 h = 1 << (kMaxLevel - level);
     const i32 M = kHmax - h;
     const i32 u = (e < 4) ? x : (e < 8 ? y : z);
@@ -115,7 +135,7 @@ struct ElemView {
       const i32 uu = edge_is_reversed(t, block, e, adj, ae) ? M - u : u;
       i32 X, Y, Z;
       edge_place(ae, uu, M, &X, &Y, &Z);
-      if (leaf_exists(adj, X, Y, Z, level)) return true;
+      if (probe(adj, X, Y, Z, level, code)) return true;
     }
     return false;
   }
@@ -143,13 +163,13 @@ TMR_HD void edge_dir(int e, int *dx, int *dy, int *dz) {
    (reference computeDepFacesAndEdges src/TMROctForest.cpp:3619-3702) */
 struct HangingFn {
   ElemView ev;
-  int16_t *info;
+  int *info32; /* 32-bit accumulator per element (bits 0-5 info) */
   TMR_HD void operator()(i64 i) const {
     i32 block, x, y, z;
     int level;
     ev.fmt.decode(ev.keys[i], &block, &x, &y, &z, &level);
     if (level == 0) {
-      info[i] = 0;
+      info32[i] = 0;
       return;
     }
     const int id = child_id_of(x, y, z, level);
@@ -166,10 +186,11 @@ struct HangingFn {
       const i32 nz = pz + (k == 2 ? d : 0);
       const i32 c = (k == 0) ? nx : (k == 1 ? ny : nz);
       bool hit;
+      const u64 code = ((u64)i << 3) | (u64)k;
       if (c >= 0 && c < kHmax) {
-        hit = ev.leaf_exists_near(block, nx, ny, nz, pl, i);
+        hit = ev.probe(block, nx, ny, nz, pl, code);
       } else {
-        hit = ev.across_face(f, block, nx, ny, nz, pl);
+        hit = ev.across_face(f, block, nx, ny, nz, pl, code);
       }
       if (hit) bits |= 1 << k;
     }
@@ -182,18 +203,53 @@ struct HangingFn {
       const int oy = (ny < 0 || ny >= kHmax);
       const int oz = (nz < 0 || nz >= kHmax);
       bool hit;
+      const u64 code = ((u64)i << 3) | (u64)(k + 3);
       if (ox + oy + oz >= 2) {
-        hit = ev.across_edge(e, block, nx, ny, nz, pl);
+        hit = ev.across_edge(e, block, nx, ny, nz, pl, code);
       } else if (ox + oy + oz == 1) {
         const int f = ox * (nx < 0 ? 0 : 1) + oy * (ny < 0 ? 2 : 3) +
                       oz * (nz < 0 ? 4 : 5);
-        hit = ev.across_face(f, block, nx, ny, nz, pl);
+        hit = ev.across_face(f, block, nx, ny, nz, pl, code);
       } else {
-        hit = ev.leaf_exists_near(block, nx, ny, nz, pl, i);
+        hit = ev.probe(block, nx, ny, nz, pl, code);
       }
       if (hit) bits |= 1 << (k + 3);
     }
-    info[i] = (int16_t)bits;
+    info32[i] = bits;
+  }
+};
+
+/* owner side of the pull exchange: does each requested leaf exist here? */
+struct AnswerProbeFn {
+  const u64 *req;
+  const u64 *keys;
+  KeyIndex ix;
+  unsigned char *ans;
+  TMR_HD void operator()(i64 i) const { ans[i] = ix.find(keys, req[i]) >= 0 ? 1 : 0; }
+};
+
+/* requester side: set the info bit (and remember it came from another rank)
+   for every probe that was answered "exists" */
+struct PatchProbeFn {
+  const u64 *code;
+  const unsigned char *ans;
+  int *info32; /* bits 0-5 info, bits 8-13 foreign mask */
+  TMR_HD void operator()(i64 i) const {
+    if (ans[i]) {
+      const u64 c = code[i];
+      const int bit = (int)(c & 7);
+      TMR_ATOMIC_OR_I32(&info32[c >> 3], (1 << bit) | (1 << (bit + 8)));
+    }
+  }
+};
+
+struct Info32SplitFn {
+  const int *info32;
+  int16_t *info;
+  unsigned char *fmask; /* optional */
+  TMR_HD void operator()(i64 i) const {
+    info[i] = (int16_t)(info32[i] & 63);
+    if (fmask) fmask[i] = (unsigned char)((info32[i] >> 8) & 63);
   }
 };
 
@@ -320,14 +376,16 @@ struct NodeScatterFn {
    when the coarse neighbour that owns those nodes lives on another rank */
 struct ParentNodeGen {
   const u64 *keys;
-  const int16_t *info;
+  const unsigned char *fmask; /* info bits whose coarse neighbour is remote */
   KeyFmt fmt;
   NodeFmt nfmt;
   ConnTables t;
   int order;
   template <class Emit>
   TMR_HD void run(i64 e, Emit &emit) const {
-    const int inf = info[e];
+    /* a hanging edge/face whose coarse neighbour is a LOCAL leaf needs nothing:
+       that leaf creates the same nodes as its own corners */
+    const int inf = fmask[e];
     if (!inf) return;
     i32 block, x, y, z;
     int level;
@@ -407,74 +465,6 @@ struct ParentNodeFillFn {
   }
 };
 
-/* ---- ghost layer (reference computeAdjacentOctants :3287-3451) -----------------
-   For every local octant: the ranks owning any of the 56 half-size positions
-   around it (across faces, edges, corners, through tree boundaries) need a copy
-   of it to answer their exact-leaf probes. */
-struct GhostGen {
-  const u64 *keys;
-  KeyFmt fmt;
-  ConnTables t;
-  OwnerMap om; /* positions at depth fmt.D */
-  int me;
-
-  struct MaskEmit {
-    const GhostGen *g;
-    int lev1; /* level of the probe cells */
-    u64 mask;
-    TMR_HD void operator()(i32 block, i32 x, i32 y, i32 z) {
-      const int D = g->fmt.D;
-      u64 m;
-      if (lev1 <= D) {
-        m = morton3((u32)x, (u32)y, (u32)z) << (3 * (D - lev1));
-      } else {
-        m = morton3((u32)x >> 1, (u32)y >> 1, (u32)z >> 1);
-      }
-      mask |= 1ULL << g->om.owner(((u64)(u32)block << (3 * D)) | m);
-    }
-  };
-
-  TMR_HD u64 dests(i64 i) const {
-    i32 block, x, y, z;
-    int level;
-    fmt.decode(keys[i], &block, &x, &y, &z, &level);
-    const int lev1 = level + 1;
-    const i32 N = 1 << lev1;
-    const int s = kMaxLevel - lev1;
-    const i32 b[3] = {x >> s, y >> s, z >> s};
-    MaskEmit e = {this, lev1, 0};
-    for (int dz = -1; dz <= 1; dz++) {
-      for (int dy = -1; dy <= 1; dy++) {
-        for (int dx = -1; dx <= 1; dx++) {
-          if (!dx && !dy && !dz) continue;
-          const int d[3] = {dx, dy, dz};
-          /* axes with d=0 range over both halves of the octant */
-          for (int sub = 0; sub < 8; sub++) {
-            i32 q[3];
-            bool skip = false;
-            for (int a = 0; a < 3; a++) {
-              const int bit = (sub >> a) & 1;
-              if (d[a] == 0) {
-                q[a] = b[a] + bit;
-              } else {
-                if (bit) skip = true; /* one position along a moved axis */
-                q[a] = d[a] < 0 ? b[a] - 1 : b[a] + 2;
-              }
-            }
-            if (skip) continue;
-            tree_images(t, block, q, N, e);
-          }
-        }
-      }
-    }
-    return e.mask & ~(1ULL << me);
-  }
-};
-
-struct GhostCountFn {
-  GhostGen g;
-  TMR_HD u32 operator()(i64 i) const { return (u32)popc64(g.dests(i)); }
-};
 
 
 /* labelDependentNodes (reference :3711-3832) */
@@ -778,27 +768,6 @@ inline int sorted_node_numbers(Forest &f, int *h_out) {
   return check_errors(ctx, "sorted_node_numbers");
 }
 
-struct GhostFillFn {
-  GhostGen g;
-  u64 *out_keys;
-  u32 *out_dest;
-  TMR_HD void operator()(i64 i, u32 o) const {
-    u64 m = g.dests(i);
-    for (int r = 0; m; r++, m >>= 1) {
-      if (m & 1) {
-        out_keys[o] = g.keys[i];
-        out_dest[o] = (u32)r;
-        o++;
-      }
-    }
-  }
-};
-
-struct GhostPlaceFn {
-  GhostFillFn fill;
-  const u32 *off;
-  TMR_HD void operator()(i64 i) const { fill(i, off[i]); }
-};
 
 struct ParentPlaceFn {
   ParentNodeFillFn fill;
@@ -1005,46 +974,68 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   }
   trace_mark(ctx, NULL);
 
-  /* 0. ghost layer (multi-rank): octants other ranks will probe for */
-  DBuf<u64> ghost;
-  i64 nghost = 0;
   DBuf<u64> own_store, own_store_n;
   OwnerMap om = {NULL, 1}, om_n = {NULL, 1};
   if (comm) {
     om = make_owner_map(f, f.fmt.D, own_store);
     om_n = make_owner_map(f, nd.nfmt.Dn, own_store_n);
-    GhostGen gg = {f.keys.get(), f.fmt, f.tables, om, me};
-    GhostCountFn gc = {gg};
-    /* two passes: the count pass sizes the buffers */
-    DBuf<u32> goff(ctx, E);
-    const i64 ng = (i64)scan_counts(ctx, E, gc, goff.get(), "nodes_ghost_count");
-    DBuf<u64> gk(ctx, ng);
-    DBuf<u32> gd(ctx, ng);
-    GhostFillFn gf = {gg, gk.get(), gd.get()};
-    GhostPlaceFn gp = {gf, goff.get()};
-    launch(ctx, E, gp, "nodes_ghost_fill");
-    U32DestFn gdest = {gd.get()};
-    RoutePlan plan;
-    make_route(ctx, *comm, ng, gdest, plan);
-    route_array(ctx, *comm, plan, gk.get(), ghost);
-    nghost = plan.nrecv;
-    if (nghost > 1) {
-      DBuf<u64> alt(ctx, nghost);
-      DBuf<u32> v0, v1;
-      radix_sort(ctx, ghost, alt, v0, v1, nghost, 0, f.fmt.total_bits());
-      nghost = unique_keep_last(ctx, ghost, alt, v0, v1, nghost, 0);
-    }
-    trace_mark(ctx, "nodes: ghost layer");
   }
 
-  /* 1. hanging faces / edges */
+  /* 1. hanging faces / edges.  Probes that land in another rank's range are
+     collected as queries, answered by the owning rank and patched in (the
+     reference pushes a ghost layer instead, computeAdjacentOctants
+     :3287-3451; the answers are the same exact-leaf tests) */
   if (!f.info.get()) f.info.alloc(ctx, E);
-  DBuf<u32> elem_index_store;
-  const KeyIndex elem_ix = build_key_index(
-      ctx, f.keys.get(), E, (u64)f.nblocks << (3 * f.fmt.D + 5), elem_index_store);
-  ElemView ev = {f.keys.get(), E, f.fmt, f.tables, elem_ix, ghost.get(), nghost};
-  HangingFn hang = {ev, f.info.get()};
-  launch(ctx, E, hang, "nodes_hanging_info");
+  DBuf<unsigned char> fmask;
+  {
+    DBuf<u32> elem_index_store;
+    const KeyIndex elem_ix =
+        build_key_index(ctx, f.keys.get(), E,
+                        (u64)f.nblocks << (3 * f.fmt.D + 5), elem_index_store);
+    DBuf<int> info32(ctx, E);
+    DBuf<u64> fq_key, fq_code;
+    DBuf<u32> fq_dest;
+    DBuf<unsigned long long> fq_count(ctx, 1);
+    i64 cap = comm ? (E / 8 + 4096) : 0;
+    i64 nq = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if (comm) {
+        fq_key.alloc(ctx, cap);
+        fq_code.alloc(ctx, cap);
+        fq_dest.alloc(ctx, cap);
+        dev_zero(ctx, fq_count.get(), sizeof(unsigned long long));
+      }
+      ElemView ev = {f.keys.get(), E,           f.fmt,         f.tables,
+                     elem_ix,      om,          me,            comm ? 1 : 0,
+                     fq_key.get(), fq_dest.get(), fq_code.get(), fq_count.get(),
+                     cap};
+      HangingFn hang = {ev, info32.get()};
+      launch(ctx, E, hang, "nodes_hanging_info");
+      if (!comm) break;
+      unsigned long long h_count = 0;
+      copy_d2h(ctx, &h_count, fq_count.get(), sizeof(h_count));
+      nq = (i64)h_count;
+      if (nq <= cap) break;
+      cap = nq; /* rare: the partition surface was larger than the guess */
+    }
+    if (comm) {
+      U32DestFn qdest = {fq_dest.get()};
+      RoutePlan plan;
+      make_route(ctx, *comm, nq, qdest, plan);
+      DBuf<u64> req;
+      route_array(ctx, *comm, plan, fq_key.get(), req);
+      DBuf<unsigned char> ans(ctx, plan.nrecv);
+      AnswerProbeFn ap = {req.get(), f.keys.get(), elem_ix, ans.get()};
+      launch(ctx, plan.nrecv, ap, "nodes_probe_answer");
+      DBuf<unsigned char> got;
+      route_back(ctx, *comm, plan, ans.get(), got);
+      PatchProbeFn pp = {fq_code.get(), got.get(), info32.get()};
+      launch(ctx, nq, pp, "nodes_probe_patch");
+      fmask.alloc(ctx, E);
+    }
+    Info32SplitFn sp = {info32.get(), f.info.get(), fmask.get()};
+    launch(ctx, E, sp, "nodes_info_split");
+  }
   trace_mark(ctx, "nodes: hanging info");
 
   /* 2. node candidates -> sort -> unique nodes + local connectivity */
@@ -1056,7 +1047,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     /* multi-rank: also the parent edge/face nodes of hanging elements */
     i64 nextra = 0;
     DBuf<u32> poff;
-    ParentNodeGen pg = {f.keys.get(), f.info.get(), f.fmt, nd.nfmt, f.tables, order};
+    ParentNodeGen pg = {f.keys.get(), fmask.get(), f.fmt, nd.nfmt, f.tables, order};
     if (comm) {
       poff.alloc(ctx, E);
       ParentNodeCountFn pc = {pg};
