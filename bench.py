@@ -163,8 +163,8 @@ def reference_main(args):
     from oracle import ref_loader
 
     if not ref_loader.available():
-        print(json.dumps({"impl": "reference", "unavailable":
-                          "oracle/_ref/libtmr_ref.so missing (built by __graft_entry__.build() where /root/reference exists)"}))
+        emit({"impl": "reference", "unavailable":
+              "oracle/_ref/libtmr_ref.so missing (built by __graft_entry__.build() where /root/reference exists)"})
         return
     cores = min(os.cpu_count() or 1, 8)
     cfg = CPU_SAMPLE
@@ -182,7 +182,7 @@ def reference_main(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -194,6 +194,17 @@ def load_peaks():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def emit(line):
+    """Print the ONE JSON line on the real stdout (everything else -- NCCL's
+    version banner, library chatter -- was redirected to stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# keep stdout clean for the driver: route fd 1 to stderr until the final line
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -472,7 +483,7 @@ def main():
             "kernel_share_of_step": kernel_share,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
