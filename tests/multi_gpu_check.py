@@ -43,7 +43,8 @@ def main():
     for case in cases:
         name, conn_name, level, passes, pct, corner, order, ranks, repart = case
         conn = util.CONNS[conn_name]()
-        body = multirank.adapt_body(conn, level, passes, pct, corner, order, repart)
+        body = multirank.adapt_body(conn, level, passes, pct, corner, order, repart,
+                                    with_interp=True)
         try:
             mine = body(lib, rank)
         except Exception:  # noqa: BLE001

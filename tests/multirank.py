@@ -41,7 +41,8 @@ def run_thread_ranks(lib, nranks, body, is_reference):
     return out
 
 
-def adapt_body(conn, level, passes, pct, corner, order, repartition=True, seed=2024):
+def adapt_body(conn, level, passes, pct, corner, order, repartition=True, seed=2024,
+               with_interp=False):
     """createTrees -> repartition -> passes x {refine, balance, repartition}
     -> createNodes; returns (per-stage octant arrays, node results)."""
 
@@ -60,7 +61,22 @@ def adapt_body(conn, level, passes, pct, corner, order, repartition=True, seed=2
             if repartition:
                 f.repartition()
                 rec.append(f.getOctants().as_array().copy())
-        return rec, util.node_results(f)
+        res = util.node_results(f)
+        if with_interp:
+            # TopOptUtils-style coarse level (reference tmr/TopOptUtils.py:79-99)
+            if order > 2:
+                coarse = f.duplicate()
+                coarse.setMeshOrder(order - 1)
+            else:
+                coarse = f.coarsen()
+                coarse.balance(1)
+            if with_interp == "repartitioned":
+                # a coarse partition that is NOT aligned with the fine one, so
+                # that some rows must be computed by another rank
+                coarse.repartition()
+            rows, d = util.interp_rows(f.createInterpolation(coarse))
+            res["interp"] = {r: (c.copy(), w.copy()) for r, (c, w) in d.items()}
+        return rec, res
 
     return body
 
@@ -84,3 +100,11 @@ def compare_rank_results(a, b, what):
         for k, (x, y) in enumerate(zip(ra, rb)):
             util.assert_octants_equal(x, y, "%s rank %d stage %d" % (what, r, k))
         util.assert_nodes_equal(na, nb, "%s rank %d nodes" % (what, r))
+        if "interp" in na:
+            # rows a rank emits (its own + those it computes for other ranks);
+            # the order of received rows is unspecified in the reference (qsort)
+            ia, ib = na["interp"], nb["interp"]
+            assert sorted(ia) == sorted(ib), "%s rank %d interp rows differ" % (what, r)
+            for row in ia:
+                assert (ia[row][0] == ib[row][0]).all(), (what, r, row)
+                assert abs(ia[row][1] - ib[row][1]).max() <= 1e-12 * abs(ia[row][1]).max()

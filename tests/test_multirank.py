@@ -20,6 +20,20 @@ def test_multirank_matches_reference(case, emu_lib, ref_lib):
     multirank.compare_rank_results(a, b, name)
 
 
+@pytest.mark.parametrize("order,ranks,mode", [(2, 2, True), (2, 4, True), (3, 3, True),
+                                              (2, 3, "repartitioned"),
+                                              (3, 2, "repartitioned")])
+def test_multirank_interpolation(order, ranks, mode, emu_lib, ref_lib):
+    """createInterpolation with rows whose enclosing coarse element lives on
+    another rank (reference src/TMROctForest.cpp:6699-6783)."""
+    conn = util.box_conn()
+    body = multirank.adapt_body(conn, 1, 3, 30, 1, order, True, with_interp=mode)
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_rank_results(a, b, "interp o%d r%d" % (order, ranks))
+    assert sum(len(x[1]["interp"]) for x in b) > 0
+
+
 def test_rank_count_invariance(emu_lib):
     """The balanced octant set does not depend on the number of ranks."""
     conn = util.box_conn()

@@ -16,6 +16,7 @@
 #define TMRGPU_OPS_INTERP_H
 
 #include "ops_nodes.h"
+#include "ops_route.h"
 
 namespace tmrgpu {
 
@@ -111,6 +112,36 @@ struct EnclosingSearch {
     return -1;
   }
 };
+
+/* the point findEnclosing uses to guess the owner of a node it did not find
+   (reference :6354-6374), as a position key at depth D */
+TMR_HD u64 miss_position(i32 block, i32 x, i32 y, i32 z, int level, int info,
+                         int order, const double *knots, int D) {
+  const i32 h = 1 << (kMaxLevel - level);
+  const int ijk[3] = {info % order, (info % (order * order)) / order,
+                      info / (order * order)};
+  const i32 base[3] = {x, y, z};
+  i32 n[3];
+  for (int a = 0; a < 3; a++) {
+    const int i = ijk[a];
+    i32 ci = -1;
+    if (i == 0 || i == order - 1) {
+      ci = base[a] + (i / (order - 1)) * h;
+    } else if (order % 2 == 1 && i == order / 2) {
+      ci = base[a] + h / 2;
+    }
+    const double cd = base[a] + 0.5 * h * (1.0 + knots[i]);
+    n[a] = ci < 0 ? (i32)cd : ci;
+    if (n[a] == 0) {
+      n[a] += 1;
+    } else if (n[a] == kHmax) {
+      n[a] -= 1;
+    }
+  }
+  const int s = kMaxLevel - D;
+  return ((u64)(u32)block << (3 * D)) |
+         morton3((u32)n[0] >> s, (u32)n[1] >> s, (u32)n[2] >> s);
+}
 
 struct FindEnclosingFn {
   EnclosingSearch s;
@@ -223,17 +254,20 @@ struct InterpRow {
     }
   }
 
-  /* builds the sorted, merged row; returns its length or -1 when no coarse
-     element encloses the node */
-  TMR_HD int build(u64 code, int *idx, double *w) const {
-    const int npe = forder * forder * forder;
-    const i64 e = (i64)(code / (u64)npe);
-    const int j = (int)(code % (u64)npe);
+  /* enclosing coarse element of node j of the fine element with key fkey */
+  TMR_HD i64 locate(u64 fkey, int j) const {
     i32 block, x, y, z;
     int level;
-    ffmt.decode(fkeys[e], &block, &x, &y, &z, &level);
-    const i64 t = s.find(block, x, y, z, level, j, forder, fknots);
-    if (t < 0) return -1;
+    ffmt.decode(fkey, &block, &x, &y, &z, &level);
+    return s.find(block, x, y, z, level, j, forder, fknots);
+  }
+
+  /* builds the sorted, merged row of node j of fine element fkey inside coarse
+     element t; returns its length */
+  TMR_HD int build(u64 fkey, int j, i64 t, int *idx, double *w) const {
+    i32 block, x, y, z;
+    int level;
+    ffmt.decode(fkey, &block, &x, &y, &z, &level);
     i32 cb, ox, oy, oz;
     int cl;
     s.cfmt.decode(s.ckeys[t], &cb, &ox, &oy, &oz, &cl);
@@ -287,33 +321,69 @@ struct InterpRow {
   }
 };
 
-struct InterpCountFn {
+/* one request = one row to build: fine element key, local node, fine global
+   node number (the row id), enclosing coarse element */
+struct RowRequests {
+  const u64 *fkey;
+  const int *j;
+  const i64 *t;
+};
+
+struct InterpLocateFn {
   InterpRow r;
   const u64 *row_code;
+  int npe;
+  u64 *fkey;
+  int *j;
+  i64 *t;
+  TMR_HD void operator()(i64 row) const {
+    const u64 code = row_code[row];
+    const i64 e = (i64)(code / (u64)npe);
+    const int jj = (int)(code % (u64)npe);
+    fkey[row] = r.fkeys[e];
+    j[row] = jj;
+    t[row] = r.locate(r.fkeys[e], jj);
+  }
+};
+
+struct InterpLocateRecvFn {
+  InterpRow r;
+  const u64 *fkey;
+  const u64 *payload; /* (j << 32) | fine node number */
+  int *j;
+  int *num;
+  i64 *t;
   int *missing;
+  TMR_HD void operator()(i64 i) const {
+    const int jj = (int)(payload[i] >> 32);
+    j[i] = jj;
+    num[i] = (int)(u32)payload[i];
+    t[i] = r.locate(fkey[i], jj);
+    if (t[i] < 0) TMR_ATOMIC_OR_I32(missing, 1);
+  }
+};
+
+struct InterpCountFn {
+  InterpRow r;
+  RowRequests q;
   TMR_HD u32 operator()(i64 row) const {
+    if (q.t[row] < 0) return 0;
     int idx[kMaxRowEntries];
     double w[kMaxRowEntries];
-    const int n = r.build(row_code[row], idx, w);
-    if (n < 0) {
-      TMR_ATOMIC_OR_I32(missing, 1);
-      return 0;
-    }
-    return (u32)n;
+    return (u32)r.build(q.fkey[row], q.j[row], q.t[row], idx, w);
   }
 };
 
 struct InterpFillFn {
   InterpRow r;
-  const u64 *row_code;
-  const u32 *off;
+  RowRequests q;
   int *cols;
   double *vals;
-  TMR_HD void operator()(i64 row) const {
+  TMR_HD void operator()(i64 row, u32 o) const {
+    if (q.t[row] < 0) return;
     int idx[kMaxRowEntries];
     double w[kMaxRowEntries];
-    const int n = r.build(row_code[row], idx, w);
-    const u32 o = off[row];
+    const int n = r.build(q.fkey[row], q.j[row], q.t[row], idx, w);
     for (int k = 0; k < n; k++) {
       cols[o + k] = idx[k];
       vals[o + k] = w[k];
@@ -331,8 +401,68 @@ struct RowPtrFn {
   }
 };
 
+struct InterpFillPlaceFn {
+  InterpFillFn fill;
+  const u32 *off;
+  TMR_HD void operator()(i64 row) const { fill(row, off[row]); }
+};
+
+/* multi-rank: rows whose coarse element is not on this rank */
+struct MissCountFn {
+  const i64 *t;
+  TMR_HD u32 operator()(i64 i) const { return t[i] < 0 ? 1u : 0u; }
+};
+struct FoundCountFn {
+  const i64 *t;
+  TMR_HD u32 operator()(i64 i) const { return t[i] >= 0 ? 1u : 0u; }
+};
+
+struct MissFillFn {
+  const u64 *fkey;
+  const int *j;
+  const int *num;
+  const i64 *t;
+  KeyFmt ffmt;
+  int forder;
+  double fknots[4];
+  OwnerMap om;
+  int D;
+  u64 *out_key;
+  u64 *out_payload;
+  u32 *out_dest;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    if (t[i] >= 0) return;
+    i32 block, x, y, z;
+    int level;
+    ffmt.decode(fkey[i], &block, &x, &y, &z, &level);
+    out_key[o] = fkey[i];
+    out_payload[o] = ((u64)(u32)j[i] << 32) | (u64)(u32)num[i];
+    out_dest[o] = (u32)om.owner(
+        miss_position(block, x, y, z, level, j[i], forder, fknots, D));
+  }
+};
+
+struct FoundFillFn {
+  const u64 *fkey;
+  const int *j;
+  const int *num;
+  const i64 *t;
+  u64 *o_fkey;
+  int *o_j;
+  int *o_num;
+  i64 *o_t;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    if (t[i] < 0) return;
+    o_fkey[o] = fkey[i];
+    o_j[o] = j[i];
+    o_num[o] = num[i];
+    o_t[o] = t[i];
+  }
+};
+
 inline int create_interp(Forest &fine, Forest &coarse) {
   Ctx &ctx = *fine.ctx;
+  Comm *comm = ctx.comm;
   NodeData &fn = fine.nodes;
   NodeData &cn = coarse.nodes;
   InterpData &I = fine.interp;
@@ -353,25 +483,6 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   const int lo = fn.node_range_start;
   const int hi = lo + (int)fn.num_owned_nodes;
   const i64 nown = fn.num_owned_nodes;
-  if (nown == 0 || nc == 0) {
-    I.valid = true;
-    I.rowp.alloc(ctx, 1);
-    dev_zero(ctx, I.rowp.get(), sizeof(int));
-    return 0;
-  }
-  DBuf<u64> first(ctx, nown);
-  dev_fill_ff(ctx, first.get(), (size_t)nown * sizeof(u64));
-  FirstTouchFn ft = {fn.conn.get(), lo, hi, first.get()};
-  launch(ctx, nc, ft, "interp_first_touch");
-  DBuf<u32> row_of(ctx, nc);
-  IsFirstFn isf = {fn.conn.get(), lo, hi, first.get()};
-  const i64 nrows = (i64)scan_counts(ctx, nc, isf, row_of.get(), "interp_row_scan");
-  DBuf<u64> row_code(ctx, nrows);
-  I.rows.alloc(ctx, nrows);
-  RowCodeFn rcf = {isf, row_of.get(), row_code.get(), I.rows.get()};
-  launch(ctx, nc, rcf, "interp_row_codes");
-  row_of.reset();
-  first.reset();
 
   InterpRow r;
   r.fkeys = fine.keys.get();
@@ -390,25 +501,130 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   r.cdep_conn = cn.dep_conn.get();
   r.cdep_w = cn.dep_weights.get();
 
-  DBuf<int> missing(ctx, 1);
-  dev_zero(ctx, missing.get(), sizeof(int));
-  DBuf<u32> off(ctx, nrows);
-  InterpCountFn cf = {r, row_code.get(), missing.get()};
-  const u64 nnz = scan_counts(ctx, nrows, cf, off.get(), "interp_row_count");
-  int h_missing = 0;
-  copy_d2h(ctx, &h_missing, missing.get(), sizeof(int));
-  if (h_missing) {
-    fprintf(stderr,
-            "TMROctForest Error: createInterpolation found fine nodes with no "
-            "enclosing coarse element on this rank\n");
+  /* rows of this rank's owned fine nodes, in first-touch order */
+  i64 nrows = 0;
+  DBuf<u64> q_fkey;
+  DBuf<int> q_j, q_num;
+  DBuf<i64> q_t;
+  if (nown > 0 && nc > 0) {
+    DBuf<u64> first(ctx, nown);
+    dev_fill_ff(ctx, first.get(), (size_t)nown * sizeof(u64));
+    FirstTouchFn ft = {fn.conn.get(), lo, hi, first.get()};
+    launch(ctx, nc, ft, "interp_first_touch");
+    DBuf<u32> row_of(ctx, nc);
+    IsFirstFn isf = {fn.conn.get(), lo, hi, first.get()};
+    nrows = (i64)scan_counts(ctx, nc, isf, row_of.get(), "interp_row_scan");
+    DBuf<u64> row_code(ctx, nrows);
+    q_num.alloc(ctx, nrows);
+    RowCodeFn rcf = {isf, row_of.get(), row_code.get(), q_num.get()};
+    launch(ctx, nc, rcf, "interp_row_codes");
+    q_fkey.alloc(ctx, nrows);
+    q_j.alloc(ctx, nrows);
+    q_t.alloc(ctx, nrows);
+    InterpLocateFn loc = {r, row_code.get(), npe, q_fkey.get(), q_j.get(), q_t.get()};
+    launch(ctx, nrows, loc, "interp_locate");
   }
+
+  int h_missing = 0;
+  if (comm) {
+    /* ship the nodes this rank could not place to the owner of the point
+       (reference :6699-6783) and take over the ones other ranks could not */
+    DBuf<u64> own_store;
+    OwnerMap om = make_owner_map(coarse, coarse.fmt.D, own_store);
+    DBuf<u64> mk(ctx, nrows), mp(ctx, nrows);
+    DBuf<u32> md(ctx, nrows);
+    MissCountFn mc = {q_t.get()};
+    MissFillFn mf;
+    mf.fkey = q_fkey.get();
+    mf.j = q_j.get();
+    mf.num = q_num.get();
+    mf.t = q_t.get();
+    mf.ffmt = fine.fmt;
+    mf.forder = fn.order;
+    for (int i = 0; i < 4; i++) mf.fknots[i] = fn.knots[i];
+    mf.om = om;
+    mf.D = coarse.fmt.D;
+    mf.out_key = mk.get();
+    mf.out_payload = mp.get();
+    mf.out_dest = md.get();
+    const i64 nmiss = (i64)scan_apply(ctx, nrows, mc, mf, "interp_miss_list");
+    U32DestFn mdest = {md.get()};
+    RoutePlan plan;
+    make_route(ctx, *comm, nmiss, mdest, plan);
+    DBuf<u64> rk, rp;
+    route_array(ctx, *comm, plan, mk.get(), rk);
+    route_array(ctx, *comm, plan, mp.get(), rp);
+    const i64 nrecv = plan.nrecv;
+    /* unified request list: local found rows, then received rows */
+    const i64 nfound = nrows - nmiss;
+    const i64 ntot = nfound + nrecv;
+    DBuf<u64> u_fkey(ctx, ntot);
+    DBuf<int> u_j(ctx, ntot), u_num(ctx, ntot);
+    DBuf<i64> u_t(ctx, ntot);
+    FoundCountFn fc = {q_t.get()};
+    FoundFillFn ff = {q_fkey.get(), q_j.get(), q_num.get(), q_t.get(),
+                      u_fkey.get(), u_j.get(), u_num.get(), u_t.get()};
+    scan_apply(ctx, nrows, fc, ff, "interp_found_compact");
+    if (nrecv > 0) {
+      copy_d2d(ctx, u_fkey.get() + nfound, rk.get(), (size_t)nrecv * sizeof(u64));
+      DBuf<int> missing(ctx, 1);
+      dev_zero(ctx, missing.get(), sizeof(int));
+      InterpLocateRecvFn lr = {r,
+                               u_fkey.get() + nfound,
+                               rp.get(),
+                               u_j.get() + nfound,
+                               u_num.get() + nfound,
+                               u_t.get() + nfound,
+                               missing.get()};
+      launch(ctx, nrecv, lr, "interp_locate_recv");
+      copy_d2h(ctx, &h_missing, missing.get(), sizeof(int));
+      if (h_missing) {
+        fprintf(stderr,
+                "[%d] TMROctForest Error: Destination processor does not own "
+                "node\n", comm->rank);
+      }
+    }
+    q_fkey.swap(u_fkey);
+    q_j.swap(u_j);
+    q_num.swap(u_num);
+    q_t.swap(u_t);
+    nrows = ntot;
+  } else if (nrows > 0) {
+    DBuf<int> missing(ctx, 1);
+    dev_zero(ctx, missing.get(), sizeof(int));
+    MissCountFn mc = {q_t.get()};
+    DBuf<u32> tmp(ctx, nrows);
+    h_missing = scan_counts(ctx, nrows, mc, tmp.get(), "interp_miss_count") > 0;
+    if (h_missing) {
+      fprintf(stderr,
+              "TMROctForest Error: createInterpolation found fine nodes with no "
+              "enclosing coarse element\n");
+    }
+  }
+
+  if (nrows == 0) {
+    I.valid = true;
+    I.rowp.alloc(ctx, 1);
+    dev_zero(ctx, I.rowp.get(), sizeof(int));
+    return check_errors(ctx, "create_interp");
+  }
+  RowRequests q = {q_fkey.get(), q_j.get(), q_t.get()};
+  DBuf<u32> off(ctx, nrows);
+  InterpCountFn cf = {r, q};
+  const u64 nnz = scan_counts(ctx, nrows, cf, off.get(), "interp_row_count");
   I.rowp.alloc(ctx, nrows + 1);
   RowPtrFn rp = {off.get(), nrows, (u32)nnz, I.rowp.get()};
   launch(ctx, nrows + 1, rp, "interp_row_ptr");
   I.cols.alloc(ctx, (i64)nnz);
   I.vals.alloc(ctx, (i64)nnz);
-  InterpFillFn ff = {r, row_code.get(), off.get(), I.cols.get(), I.vals.get()};
-  launch(ctx, nrows, ff, "interp_row_fill");
+  InterpFillFn ffn = {r, q, I.cols.get(), I.vals.get()};
+  {
+    /* offsets are already known: replay the fill through them */
+    InterpFillPlaceFn pl = {ffn, off.get()};
+    launch(ctx, nrows, pl, "interp_row_fill");
+  }
+  I.rows.swap(q_num);
+  I.rows.set_size(nrows);
   I.nrows = nrows;
   I.nnz = (i64)nnz;
   I.valid = true;
