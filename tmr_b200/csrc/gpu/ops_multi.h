@@ -309,11 +309,8 @@ inline int balance_multi(Forest &f, int balance_corner) {
     const i64 nall = npending + npar;
     /* route to the owners of the positions, then sort + dedup */
     LevelOwnerFn lo = {all.get(), l, D, om};
-    RoutePlan plan;
-    make_route(ctx, comm, nall, lo, plan);
     DBuf<u64> got;
-    route_array(ctx, comm, plan, all.get(), got);
-    i64 ngot = plan.nrecv;
+    i64 ngot = route_keys_sparse(ctx, comm, all.get(), nall, lo, got);
     {
       DBuf<u64> alt(ctx, ngot);
       DBuf<u32> v0, v1;
@@ -395,11 +392,8 @@ inline int balance_multi(Forest &f, int balance_corner) {
 
   /* leaves go to the owner of their own position */
   LeafOwnerFn lof = {out.get(), om};
-  RoutePlan plan;
-  make_route(ctx, comm, total, lof, plan);
   DBuf<u64> mine;
-  route_array(ctx, comm, plan, out.get(), mine);
-  const i64 nmine = plan.nrecv;
+  const i64 nmine = route_keys_sparse(ctx, comm, out.get(), total, lof, mine);
   if (nmine >= (1LL << 31)) {
     fprintf(stderr, "TMROctForest Error: balance() leaves %lld octants on one "
                     "rank (int32 index limit)\n", (long long)nmine);

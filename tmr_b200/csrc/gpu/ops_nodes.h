@@ -836,6 +836,88 @@ struct OwnerReplyFn {
   }
 };
 
+/* owner of a node whose home is this rank starts as "me if I create it" */
+struct OwnerInitFn {
+  NodeHomeFn home;
+  int me;
+  const unsigned char *created;
+  int *owner;
+  TMR_HD void operator()(i64 i) const {
+    owner[i] = (home(i) == me && created[i]) ? me : 0x7fffffff;
+  }
+};
+
+struct ForeignNodeCountFn {
+  NodeHomeFn home;
+  int me;
+  TMR_HD u32 operator()(i64 i) const { return home(i) != me ? 1u : 0u; }
+};
+
+struct ForeignNodeFillFn {
+  NodeHomeFn home;
+  int me;
+  const u64 *node_keys;
+  const unsigned char *created;
+  u64 *out_key;
+  u32 *out_dest;
+  u32 *out_index;
+  unsigned char *out_created;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    const int d = home(i);
+    if (d != me) {
+      out_key[o] = node_keys[i];
+      out_dest[o] = (u32)d;
+      out_index[o] = (u32)i;
+      out_created[o] = created[i];
+    }
+  }
+};
+
+/* home side: received donors lower the owner of my own copy of the node */
+struct HomeFoldFn {
+  const u64 *rkeys; /* received keys, sorted */
+  const u32 *run_of;
+  const int *owner_run;
+  const u64 *node_keys;
+  i64 n;
+  int *owner;
+  TMR_HD void operator()(i64 j) const {
+    const i64 i = find_u64(node_keys, n, rkeys[j]);
+    if (i >= 0) TMR_ATOMIC_MIN_I32(&owner[i], owner_run[run_of[j]]);
+  }
+};
+
+struct HomeReplyFn {
+  const u64 *rkeys;
+  const u32 *idx;
+  const u32 *run_of;
+  const int *owner_run;
+  const u64 *node_keys;
+  i64 n;
+  const int *owner;
+  int *reply; /* by original received index */
+  TMR_HD void operator()(i64 j) const {
+    const i64 i = find_u64(node_keys, n, rkeys[j]);
+    int o = owner_run[run_of[j]];
+    if (i >= 0 && owner[i] < o) o = owner[i];
+    reply[idx[j]] = o;
+  }
+};
+
+struct StoreOwnerFn {
+  const u32 *index;
+  const int *value;
+  int *owner;
+  TMR_HD void operator()(i64 k) const { owner[index[k]] = value[k]; }
+};
+
+struct OwnerFinishFn {
+  int *owner;
+  TMR_HD void operator()(i64 i) const {
+    if (owner[i] == 0x7fffffff) owner[i] = -1;
+  }
+};
+
 struct FillIntFn {
   int *p;
   int v;
@@ -1088,16 +1170,31 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   trace_mark(ctx, "nodes: unique+conn");
 
   /* 2b. node ownership (multi-rank): lowest rank that creates the node from an
-     element (reference createLocalNodes :4538-4637) */
+     element (reference createLocalNodes :4538-4637).  The home rank of a node
+     (owner of its position) decides.  Nodes whose home is this rank stay in
+     place; only the few whose home is elsewhere travel, and the home matches
+     what it receives against its own node array. */
   DBuf<int> owner;
   if (comm) {
+    owner.alloc(ctx, Nn);
     NodeHomeFn home = {nd.node_keys.get(), nd.nfmt.Dn, om_n};
+    OwnerInitFn oi = {home, me, created.get(), owner.get()};
+    launch(ctx, Nn, oi, "nodes_owner_init");
+    /* foreign-home nodes: (key, created, local index) */
+    DBuf<u64> fk(ctx, Nn);
+    DBuf<u32> fd(ctx, Nn), fi(ctx, Nn);
+    DBuf<unsigned char> fcr(ctx, Nn);
+    ForeignNodeCountFn fnc = {home, me};
+    ForeignNodeFillFn fnf = {home, me, nd.node_keys.get(), created.get(),
+                             fk.get(), fd.get(), fi.get(), fcr.get()};
+    const i64 nf = (i64)scan_apply(ctx, Nn, fnc, fnf, "nodes_foreign_home_list");
+    U32DestFn fdest = {fd.get()};
     RoutePlan plan;
-    make_route(ctx, *comm, Nn, home, plan);
+    make_route(ctx, *comm, nf, fdest, plan);
     DBuf<u64> rk;
     DBuf<unsigned char> rc;
-    route_array(ctx, *comm, plan, nd.node_keys.get(), rk);
-    route_array(ctx, *comm, plan, created.get(), rc);
+    route_array(ctx, *comm, plan, fk.get(), rk);
+    route_array(ctx, *comm, plan, fcr.get(), rc);
     const i64 nr = plan.nrecv;
     DBuf<int> reply(ctx, nr);
     if (nr > 0) {
@@ -1110,16 +1207,26 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       DBuf<u64> rk_alt(ctx, nr);
       radix_sort(ctx, rk, rk_alt, idx, idx_alt, nr, 0, nd.nfmt.total_bits());
       DBuf<int> owner_run(ctx, nr);
-      FillIntFn fi = {owner_run.get(), 0x7fffffff};
-      launch(ctx, nr, fi, "nodes_owner_init");
+      FillIntFn fi2 = {owner_run.get(), 0x7fffffff};
+      launch(ctx, nr, fi2, "nodes_owner_run_init");
       DBuf<u32> run_of(ctx, nr);
       RunHeadFn rh = {rk.get()};
       OwnerMinFn omin = {rk.get(), idx.get(), val.get(), owner_run.get(), run_of.get()};
       scan_apply(ctx, nr, rh, omin, "nodes_owner_min");
-      OwnerReplyFn orf = {idx.get(), run_of.get(), owner_run.get(), reply.get()};
-      launch(ctx, nr, orf, "nodes_owner_reply");
+      /* fold the received donors into my own nodes, then answer */
+      HomeFoldFn hf = {rk.get(), run_of.get(), owner_run.get(), nd.node_keys.get(),
+                       Nn, owner.get()};
+      launch(ctx, nr, hf, "nodes_owner_fold");
+      HomeReplyFn hr = {rk.get(), idx.get(), run_of.get(), owner_run.get(),
+                        nd.node_keys.get(), Nn, owner.get(), reply.get()};
+      launch(ctx, nr, hr, "nodes_owner_reply");
     }
-    route_back(ctx, *comm, plan, reply.get(), owner);
+    DBuf<int> got;
+    route_back(ctx, *comm, plan, reply.get(), got);
+    StoreOwnerFn so = {fi.get(), got.get(), owner.get()};
+    launch(ctx, nf, so, "nodes_owner_store");
+    OwnerFinishFn of2 = {owner.get()};
+    launch(ctx, Nn, of2, "nodes_owner_finish");
     trace_mark(ctx, "nodes: ownership");
   }
 

@@ -143,6 +143,79 @@ void route_back(Ctx &ctx, Comm &comm, const RoutePlan &plan, const T *reply,
   launch(ctx, plan.nsend, s, "route_scatter_back");
 }
 
+/* ---- sparse routing ----------------------------------------------------------
+   Almost every key already lives on its owner: keep those in place (one
+   compaction) and ship only the few that do not, instead of grouping the whole
+   array by destination. */
+template <class DestFn>
+struct ForeignCountFn {
+  DestFn dest;
+  int me;
+  TMR_HD u32 operator()(i64 i) const { return dest(i) != me ? 1u : 0u; }
+};
+template <class DestFn>
+struct LocalCountFn {
+  DestFn dest;
+  int me;
+  TMR_HD u32 operator()(i64 i) const { return dest(i) == me ? 1u : 0u; }
+};
+template <class DestFn>
+struct ForeignKeyFillFn {
+  DestFn dest;
+  int me;
+  const u64 *keys;
+  u64 *out_keys;
+  u32 *out_dest;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    const int d = dest(i);
+    if (d != me) {
+      out_keys[o] = keys[i];
+      out_dest[o] = (u32)d;
+    }
+  }
+};
+template <class DestFn>
+struct LocalKeyFillFn {
+  DestFn dest;
+  int me;
+  const u64 *keys;
+  u64 *out_keys;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    if (dest(i) == me) out_keys[o] = keys[i];
+  }
+};
+struct DestArrayFn {
+  const u32 *dest;
+  TMR_HD int operator()(i64 i) const { return (int)dest[i]; }
+};
+
+/* out = keys that stay here (original order) followed by the keys received
+   from the other ranks; returns the new count */
+template <class DestFn>
+i64 route_keys_sparse(Ctx &ctx, Comm &comm, const u64 *keys, i64 n, DestFn dest,
+                      DBuf<u64> &out) {
+  const int me = comm.rank;
+  DBuf<u64> fk(ctx, n);
+  DBuf<u32> fd(ctx, n);
+  ForeignCountFn<DestFn> fc = {dest, me};
+  ForeignKeyFillFn<DestFn> ff = {dest, me, keys, fk.get(), fd.get()};
+  const i64 nf = (i64)scan_apply(ctx, n, fc, ff, "route_foreign_compact");
+  DestArrayFn da = {fd.get()};
+  RoutePlan plan;
+  make_route(ctx, comm, nf, da, plan);
+  DBuf<u64> got;
+  route_array(ctx, comm, plan, fk.get(), got);
+  const i64 nloc = n - nf;
+  out.alloc(ctx, nloc + plan.nrecv);
+  LocalCountFn<DestFn> lc = {dest, me};
+  LocalKeyFillFn<DestFn> lf = {dest, me, keys, out.get()};
+  scan_apply(ctx, n, lc, lf, "route_local_compact");
+  if (plan.nrecv) {
+    copy_d2d(ctx, out.get() + nloc, got.get(), (size_t)plan.nrecv * sizeof(u64));
+  }
+  return nloc + plan.nrecv;
+}
+
 /* global max / sum / or of a small host value */
 inline i64 global_max(Ctx &ctx, Comm &comm, i64 v) {
   std::vector<i64> all(comm.size);
