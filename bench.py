@@ -422,8 +422,12 @@ def main():
         name, st = dom
         # algorithmic bytes per launch of the dominant kernel
         n_pairs = sizes[0] * npe
-        alg = {"radix_pass_pairs": 2 * 12 * n_pairs, "radix_pass_keys": 2 * 8 * e_final,
-               "nodes_candidates": (8 + 12 * npe) * sizes[0],
+        alg = {"radix_pass_pairs[nodes]": 2 * 12 * n_pairs,
+               "radix_pass_keys[nodes]": 2 * 8 * n_pairs,
+               "radix_pass_keys[leaves]": 2 * 8 * e_final,
+               "nodes_candidates": (8 + 8 * npe) * sizes[0],
+               "nodes_unique_scatter_conn": (8 + 4) * n_pairs + 8 * sizes[1],
+               "nodes_dep_fill": 12 * sizes[4] + 16 * sizes[2],
                "nodes_hanging_info": 10 * sizes[0]}.get(name)
         avg_ms = st["ms"] / st["launches"]
         if alg:

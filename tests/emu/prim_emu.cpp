@@ -27,7 +27,7 @@ void prof_resolve(Ctx &) {}
 void trace_mark(Ctx &, const char *) {}
 
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &, DBuf<u32> &vals,
-                DBuf<u32> &, i64 n, int bit_lo, int bit_hi) {
+                DBuf<u32> &, i64 n, int bit_lo, int bit_hi, const char *) {
   if (n <= 1 || bit_hi <= bit_lo) return;
   const u64 mask = (bit_hi - bit_lo >= 64) ? ~0ULL
                                            : (((1ULL << (bit_hi - bit_lo)) - 1) << bit_lo);

@@ -413,7 +413,7 @@ inline int balance(Forest &f, int balance_corner) {
   trace_mark(ctx, "balance: leaf fill");
   /* leaves have distinct anchors: order by (block, Morton) only */
   DBuf<u32> v0, v1;
-  radix_sort(ctx, out, out_alt, v0, v1, total, 5, f.fmt.total_bits());
+  radix_sort(ctx, out, out_alt, v0, v1, total, 5, f.fmt.total_bits(), "leaves");
   f.keys.swap(out);
   f.n = total;
   f.last_out = f.n;

@@ -137,7 +137,7 @@ class DBuf {
    vals may be empty (keys only). */
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
                 DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int bit_lo,
-                int bit_hi);
+                int bit_hi, const char *tag = NULL /* profiling label */);
 
 }  // namespace tmrgpu
 

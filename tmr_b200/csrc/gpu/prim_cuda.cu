@@ -496,7 +496,7 @@ static void launch_pass(Ctx &ctx, i64 tiles, DBuf<u64> &keys, DBuf<u64> &keys_al
 
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
                 DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int bit_lo,
-                int bit_hi) {
+                int bit_hi, const char *tag) {
   if (n <= 1 || bit_hi <= bit_lo) return;
   if (n >= (1LL << 32)) {
     fprintf(stderr, "TMROctForest Error: radix sort of %lld keys exceeds the "
@@ -507,6 +507,12 @@ void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
   const bool has_vals = vals.get() != NULL;
   cudaStream_t st = (cudaStream_t)ctx.stream;
   const i64 tiles = (n + kSortTile - 1) / kSortTile;
+  std::string hist_name = "radix_hist", pass_name = has_vals ? "radix_pass_pairs"
+                                                             : "radix_pass_keys";
+  if (tag) {
+    hist_name += std::string("[") + tag + "]";
+    pass_name += std::string("[") + tag + "]";
+  }
   /* scratch: [kMaxPasses*512 u32 hist][tickets][tiles*512 u64 descriptors] */
   const size_t hist_bytes = (size_t)kMaxPasses * kMaxRadix * sizeof(u32);
   const size_t ticket_bytes = 64;
@@ -525,7 +531,7 @@ void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
     if (hi - lo > kMaxPasses * kMaxRadixBits) hi = lo + kMaxPasses * kMaxRadixBits;
     const PassPlan plan = make_plan(lo, hi);
     dev_zero(ctx, scratch, hist_bytes + ticket_bytes);
-    prof_begin(ctx, "radix_hist");
+    prof_begin(ctx, hist_name.c_str());
     radix_hist_kernel<<<grid_for(ctx, n, kHistThreads * 4, 8), kHistThreads, 0,
                         st>>>(keys.get(), n, plan, ghist);
     radix_scan_hist_kernel<<<plan.npass, kMaxRadix, 0, st>>>(ghist);
@@ -535,7 +541,7 @@ void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
       const int bits = plan.bits[p];
       const int radix = bits > 8 ? 512 : 256;
       dev_zero(ctx, lookback, (size_t)tiles * radix * sizeof(u64));
-      prof_begin(ctx, has_vals ? "radix_pass_pairs" : "radix_pass_keys");
+      prof_begin(ctx, pass_name.c_str());
       const u32 *offs = ghist + p * kMaxRadix;
       if (has_vals) {
         if (bits > 8) {
