@@ -370,6 +370,9 @@ def main():
     e_final = lib.tmrgpu_count(wdev)
     sizes = (I64 * 6)()
     lib.tmrgpu_node_sizes(wdev, sizes)
+    lib.tmrgpu_node_candidates.restype = I64
+    lib.tmrgpu_node_candidates.argtypes = [P]
+    n_cand = int(lib.tmrgpu_node_candidates(wdev))
     csum = ctypes.c_uint64(0)
     lib.tmrgpu_checksum(wdev, ctypes.byref(csum))
     del work, last
@@ -422,11 +425,11 @@ def main():
         name, st = dom
         # algorithmic bytes per launch of the dominant kernel
         n_pairs = sizes[0] * npe
-        alg = {"radix_pass_pairs[nodes]": 2 * 12 * n_pairs,
-               "radix_pass_keys[nodes]": 2 * 8 * n_pairs,
+        alg = {"radix_pass_pairs[nodes]": 2 * 12 * n_cand,
+               "radix_pass_keys[nodes]": 2 * 8 * n_cand,
                "radix_pass_keys[leaves]": 2 * 8 * e_final,
-               "nodes_candidates": (8 + 8 * npe) * sizes[0],
-               "nodes_unique_scatter_conn": (8 + 4) * n_pairs + 8 * sizes[1],
+               "nodes_candidates": 8 * sizes[0] + 8 * n_cand,
+               "nodes_unique_scatter_conn": 8 * n_cand + 4 * n_pairs + 8 * sizes[1],
                "nodes_dep_fill": 12 * sizes[4] + 16 * sizes[2],
                "nodes_hanging_info": 10 * sizes[0]}.get(name)
         avg_ms = st["ms"] / st["launches"]
@@ -471,7 +474,7 @@ def main():
             "config": {"workload": workload_name(cfg),
                        "octants_in": int(e_in), "octants_out_per_gpu": int(e_final),
                        "local_nodes": int(sizes[1]), "dep_nodes": int(sizes[2]),
-                       "dep_nnz": int(sizes[4]), "checksum": "%016x" % global_checksum,
+                       "dep_nnz": int(sizes[4]), "node_candidates_sorted": n_cand, "checksum": "%016x" % global_checksum,
                        "octants_out_total": int(total_octants), "octants_in_total": int(total_in),
                        "parallelism": "1 GPU" if world == 1 else
                        "%d GPUs, one forest SFC-partitioned, NCCL all-to-all-v (%s: %dx%dx%d trees); cycle includes repartition()"

@@ -111,6 +111,9 @@ int tmrgpu_free_nodes(tmrgpu_forest *f);
 /* sizes: [0] elements [1] local nodes [2] dependent nodes [3] owned nodes
    [4] dependent nnz [5] first owned node number */
 int tmrgpu_node_sizes(tmrgpu_forest *f, int64_t sizes[6]);
+/* number of node-candidate keys the last createNodes sorted (roofline
+   accounting of the sort passes) */
+int64_t tmrgpu_node_candidates(tmrgpu_forest *f);
 /* copy-out; any pointer may be NULL to skip that array */
 int tmrgpu_download_nodes(tmrgpu_forest *f, int *conn, int *node_numbers,
                           int *dep_ptr, int *dep_conn, double *dep_weights);

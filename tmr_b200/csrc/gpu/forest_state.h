@@ -34,6 +34,7 @@ struct NodeData {
   i64 num_dep_nodes;
   i64 num_owned_nodes;
   i64 dep_nnz;
+  i64 num_candidates; /* node keys that went through the sort */
   int node_range_start; /* first global number owned by this rank */
   NodeFmt nfmt;
   DBuf<u64> node_keys;  /* sorted unique node keys [num_local_nodes] */
@@ -45,7 +46,7 @@ struct NodeData {
   NodeData()
       : valid(false), order(2), interp_type(1), num_elements(0),
         num_local_nodes(0), num_dep_nodes(0), num_owned_nodes(0), dep_nnz(0),
-        node_range_start(0) {}
+        num_candidates(0), node_range_start(0) {}
   void clear() {
     valid = false;
     node_keys.reset();

@@ -286,72 +286,148 @@ TMR_HD int face_node_offset(int order, int f, int p, int q) {
   return p + q * order + n * order * order;
 }
 
-/* canonical node keys of the order^3 nodes of one element -- createLocalNodes
-   + transformNode (reference :4290-4372, :3847-4039).  One thread per
-   element: the key is decoded once and the per-axis bit-interleaves are shared
-   by all nodes; only elements touching a tree boundary take the transform. */
-struct NodeCandFn {
+/* ---- node candidates ---------------------------------------------------------
+   createLocalNodes + transformNode (reference :4290-4372, :3847-4039).
+
+   Every element needs the index of each of its order^3 nodes; the sort of the
+   candidate keys is the most expensive step of createNodes, so as few
+   candidates as possible are emitted:
+     * order 2, a COMPLETE family (8 sibling leaves, consecutive in the array):
+       its leader emits the 27 distinct nodes of the 2x2x2 block once instead
+       of 8x8 = 64; each candidate is tagged "shared" and the scatter fans it
+       out to every sibling that has it as a corner;
+     * everything else: order^3 candidates per element.
+   The payload of a candidate is (element << 4) | code with code = corner
+   (0..7, or slot at order 3 via the wide encoding) and bit 3 = "shared". */
+static const u32 kSharedBit = 8;
+
+struct NodeEmit {
   const u64 *keys;
+  i64 E;
   KeyFmt fmt;
   NodeFmt nfmt;
   ConnTables t;
   int order;
-  u64 *out_keys;
-  u32 *out_vals; /* NULL in packed mode: the payload rides in the key's unused
-                    high bits (LSD passes only touch the low key bits) */
-  int pshift;    /* packed mode: payload << pshift */
-  TMR_HD void operator()(i64 e) const {
-    const int npe = order * order * order;
+  int families; /* use family emission (order 2 only) */
+
+  TMR_HD int digit_of(u64 k) const {
+    const int L = (int)(k & 31);
+    return L == 0 ? 0 : (int)((k >> (5 + 3 * (fmt.D - L))) & 7);
+  }
+  /* is e the first of 8 consecutive sibling leaves? */
+  TMR_HD bool leader(i64 e) const {
+    if (!families || e < 0 || e + 7 >= E) return false;
+    const u64 k = keys[e];
+    const int L = (int)(k & 31);
+    if (L == 0 || digit_of(k) != 0) return false;
+    return keys[e + 7] == k + (7ULL << (5 + 3 * (fmt.D - L)));
+  }
+  /* is element e a member of a complete family? (m = its child digit) */
+  TMR_HD bool in_family(i64 e, int *m) const {
+    *m = digit_of(keys[e]);
+    return families && leader(e - *m);
+  }
+  /* A member (a,b,c) of a complete family emits its corner (di,dj,dk) unless
+     some axis has d=1 with the member on the low side: that point is corner
+     d=0 of the next sibling.  Member (a,b,c) thus emits (1+a)(1+b)(1+c)
+     corners and the family 27 in total, spread over its 8 threads. */
+  TMR_HD u32 count(i64 e) const {
+    if (!families) return (u32)(order * order * order);
+    int m;
+    if (!in_family(e, &m)) return 8;
+    return (u32)((1 + ((m >> 2) & 1)) * (1 + ((m >> 1) & 1)) * (1 + (m & 1)));
+  }
+
+  /* payload encoding */
+  TMR_HD u64 payload(i64 e, int code) const {
+    return families ? (((u64)e << 4) | (u64)code)
+                    : ((u64)e * (u64)(order * order * order) + (u64)code);
+  }
+
+  template <class Emit>
+  TMR_HD void run(i64 e, Emit &emit) const {
+    int m = 0;
+    const bool fam = families && in_family(e, &m);
+    /* sibling bits in x-major order: m = 4*xbit + 2*ybit + zbit */
+    const int bx = (m >> 2) & 1, by = (m >> 1) & 1, bz = m & 1;
     i32 block, x, y, z;
     int level;
     fmt.decode(keys[e], &block, &x, &y, &z, &level);
     const i32 h = 1 << (kMaxLevel - level);
+    const int np = order;
     const i32 step = h / (order - 1);
-    u64 *ok = out_keys + e * npe;
-    u32 *ov = out_vals + e * npe;
     const bool interior = x > 0 && y > 0 && z > 0 && x + h < kHmax &&
                           y + h < kHmax && z + h < kHmax;
+    u64 sx[kMaxOrder], sy[kMaxOrder], sz[kMaxOrder];
     if (interior) {
-      u64 sx[kMaxOrder], sy[kMaxOrder], sz[kMaxOrder];
-      for (int a = 0; a < order; a++) {
+      for (int a = 0; a < np; a++) {
         sx[a] = spread3(nfmt.squeeze(x + a * step)) << 2;
         sy[a] = spread3(nfmt.squeeze(y + a * step)) << 1;
         sz[a] = spread3(nfmt.squeeze(z + a * step));
       }
-      const u64 hi = (u64)(u32)block << (3 * (nfmt.Dn + 1));
-      int s = 0;
-      for (int kk = 0; kk < order; kk++) {
-        for (int jj = 0; jj < order; jj++) {
-          for (int ii = 0; ii < order; ii++, s++) {
-            const u64 k = hi | sx[ii] | sy[jj] | sz[kk];
-            if (out_vals) {
-              ok[s] = k;
-              ov[s] = (u32)(e * npe + s);
-            } else {
-              ok[s] = k | ((u64)(e * npe + s) << pshift);
-            }
-          }
-        }
-      }
-    } else {
-      int s = 0;
-      for (int kk = 0; kk < order; kk++) {
-        for (int jj = 0; jj < order; jj++) {
-          for (int ii = 0; ii < order; ii++, s++) {
+    }
+    const u64 hi = (u64)(u32)block << (3 * (nfmt.Dn + 1));
+    for (int kk = 0; kk < np; kk++) {
+      for (int jj = 0; jj < np; jj++) {
+        for (int ii = 0; ii < np; ii++) {
+          if (fam && ((ii && !bx) || (jj && !by) || (kk && !bz))) continue;
+          u64 key;
+          if (interior) {
+            key = hi | sx[ii] | sy[jj] | sz[kk];
+          } else {
             i32 b = block, nx = x + ii * step, ny = y + jj * step,
                 nz = z + kk * step;
             transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-            const u64 k = nfmt.encode(b, nx, ny, nz);
-            if (out_vals) {
-              ok[s] = k;
-              ov[s] = (u32)(e * npe + s);
-            } else {
-              ok[s] = k | ((u64)(e * npe + s) << pshift);
-            }
+            key = nfmt.encode(b, nx, ny, nz);
           }
+          const int slot = ii + np * jj + np * np * kk;
+          emit(key, payload(e, fam ? (slot | (int)kSharedBit) : slot));
         }
       }
     }
+  }
+};
+
+struct NodeEmitCountFn {
+  NodeEmit g;
+  TMR_HD u32 operator()(i64 e) const { return g.count(e); }
+};
+
+struct CandStore {
+  u64 *k;
+  u32 *v;     /* NULL in packed mode */
+  int pshift; /* packed mode: payload << pshift */
+  TMR_HD void operator()(u64 key, u64 payload) {
+    if (v) {
+      *k++ = key;
+      *v++ = (u32)payload;
+    } else {
+      *k++ = key | (payload << pshift);
+    }
+  }
+};
+
+struct NodeEmitFillFn {
+  NodeEmit g;
+  u64 *out_keys;
+  u32 *out_vals;
+  int pshift;
+  TMR_HD void operator()(i64 e, u32 o) const {
+    CandStore s = {out_keys + o, out_vals ? out_vals + o : (u32 *)0, pshift};
+    g.run(e, s);
+  }
+};
+
+/* fixed order^3 candidates per element: offsets are e*npe, no scan needed */
+struct NodeEmitDenseFn {
+  NodeEmit g;
+  u64 *out_keys;
+  u32 *out_vals;
+  int pshift;
+  TMR_HD void operator()(i64 e) const {
+    const i64 o = e * (i64)(g.order * g.order * g.order);
+    CandStore s = {out_keys + o, out_vals ? out_vals + o : (u32 *)0, pshift};
+    g.run(e, s);
   }
 };
 
@@ -383,16 +459,45 @@ struct NodeScatterFn {
   u64 *node_keys;
   int *conn_local;
   unsigned char *created; /* optional: node is created by a local element */
+  NodeEmit g;             /* payload decoding */
   /* heads_before = exclusive scan of run heads */
   TMR_HD void operator()(i64 i, u32 heads_before) const {
     const u64 k = keys[i] & mask;
     const bool head = (i == 0 || k != (keys[i - 1] & mask));
     const u32 run = heads_before + (head ? 1u : 0u) - 1u;
     if (head) node_keys[run] = k;
-    const u64 slot = vals ? (u64)vals[i] : (keys[i] >> pshift);
-    if (slot != no_slot) {
-      conn_local[slot] = (int)run;
-      if (created) created[run] = 1;
+    const u64 p = vals ? (u64)vals[i] : (keys[i] >> pshift);
+    if (p == no_slot) return;
+    if (created) created[run] = 1;
+    if (!g.families) {
+      conn_local[p] = (int)run;
+      return;
+    }
+    const i64 e = (i64)(p >> 4);
+    const int code = (int)(p & 15);
+    const int cc = code & 7;
+    if (!(code & (int)kSharedBit)) {
+      conn_local[e * 8 + cc] = (int)run;
+      return;
+    }
+    /* shared node of a complete family: fan out to every sibling that has it
+       as a corner.  e is the representative sibling; its child digit gives
+       the family's first element. */
+    const int m = g.digit_of(g.keys[e]);
+    const i64 e0 = e - m;
+    const int pi = ((m >> 2) & 1) + (cc & 1);       /* node position 0..2 */
+    const int pj = ((m >> 1) & 1) + ((cc >> 1) & 1);
+    const int pk = (m & 1) + (cc >> 2);
+    for (int a = 0; a < 2; a++) {
+      if (pi - a < 0 || pi - a > 1) continue;
+      for (int b = 0; b < 2; b++) {
+        if (pj - b < 0 || pj - b > 1) continue;
+        for (int c = 0; c < 2; c++) {
+          if (pk - c < 0 || pk - c > 1) continue;
+          conn_local[(e0 + 4 * a + 2 * b + c) * 8 + (pi - a) + 2 * (pj - b) +
+                     4 * (pk - c)] = (int)run;
+        }
+      }
     }
   }
 };
@@ -802,6 +907,12 @@ inline int sorted_node_numbers(Forest &f, int *h_out) {
 }
 
 
+struct NodeEmitPlaceFn {
+  NodeEmitFillFn fill;
+  const u32 *off;
+  TMR_HD void operator()(i64 e) const { fill(e, off[e]); }
+};
+
 struct ParentPlaceFn {
   ParentNodeFillFn fill;
   const u32 *off;
@@ -1168,7 +1279,18 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       ParentNodeCountFn pc = {pg};
       nextra = (i64)scan_counts(ctx, E, pc, poff.get(), "nodes_parent_count");
     }
-    const i64 ntot = nc + nextra;
+    /* candidate emission plan */
+    NodeEmit emit_gen = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order,
+                         order == 2 ? 1 : 0};
+    i64 nemit = nc;
+    DBuf<u32> eoff;
+    if (emit_gen.families) {
+      eoff.alloc(ctx, E);
+      NodeEmitCountFn ec = {emit_gen};
+      nemit = (i64)scan_counts(ctx, E, ec, eoff.get(), "nodes_emit_count");
+    }
+    const i64 ntot = nemit + nextra;
+    nd.num_candidates = ntot;
     if (ntot >= (1LL << 32) - 1) {
       fprintf(stderr, "TMROctForest Error: too many node candidates\n");
       return 1;
@@ -1177,9 +1299,16 @@ inline int create_nodes(Forest &f, int order, int interp_type,
        (conn slot) rides in the key's high bits and the sort is keys-only:
        16 B instead of 24 B of HBM traffic per candidate per pass */
     const int nbits = nd.nfmt.total_bits();
+    const u64 max_payload =
+        emit_gen.families ? (((u64)E << 4) | 15ULL) : (u64)nc;
     int pbits = 1;
-    while ((1ULL << pbits) <= (u64)ntot) pbits++; /* payload values 0..ntot */
+    while ((1ULL << pbits) <= max_payload + 1) pbits++;
     const bool packed = nbits + pbits <= 64;
+    if (!packed && max_payload >= 0xffffffffULL) {
+      fprintf(stderr, "TMROctForest Error: too many elements for the 32-bit "
+                      "node payload\n");
+      return 1;
+    }
     const u64 kmask = nbits >= 64 ? ~0ULL : ((1ULL << nbits) - 1);
     const u64 no_slot = packed ? ((1ULL << pbits) - 1) : (u64)kNoSlot;
     DBuf<u64> ck(ctx, ntot), ck_alt(ctx, ntot);
@@ -1188,11 +1317,17 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       cv.alloc(ctx, ntot);
       cv_alt.alloc(ctx, ntot);
     }
-    NodeCandFn cand = {f.keys.get(), f.fmt,   nd.nfmt,  f.tables, order,
-                       ck.get(),     cv.get(), nbits};
-    launch(ctx, E, cand, "nodes_candidates");
+    if (emit_gen.families) {
+      NodeEmitFillFn ef = {emit_gen, ck.get(), cv.get(), nbits};
+      NodeEmitPlaceFn ep = {ef, eoff.get()};
+      launch(ctx, E, ep, "nodes_candidates");
+    } else {
+      NodeEmitDenseFn ed = {emit_gen, ck.get(), cv.get(), nbits};
+      launch(ctx, E, ed, "nodes_candidates");
+    }
     if (nextra) {
-      ParentNodeFillFn pf = {pg, ck.get() + nc, packed ? (u32 *)0 : cv.get() + nc,
+      ParentNodeFillFn pf = {pg, ck.get() + nemit,
+                             packed ? (u32 *)0 : cv.get() + nemit,
                              no_slot << nbits};
       ParentPlaceFn pp = {pf, poff.get()};
       launch(ctx, E, pp, "nodes_parent_fill");
@@ -1207,8 +1342,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       dev_zero(ctx, created.get(), (size_t)ntot);
     }
     RunHeadMaskedFn rh = {ck.get(), kmask};
-    NodeScatterFn sc = {ck.get(), cv.get(), kmask,          nbits,
-                        no_slot,  ck_alt.get(), nd.conn.get(), created.get()};
+    NodeScatterFn sc = {ck.get(), cv.get(),     kmask,         nbits,
+                        no_slot,  ck_alt.get(), nd.conn.get(), created.get(),
+                        emit_gen};
     Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
     nd.node_keys.alloc(ctx, Nn);
     copy_d2d(ctx, nd.node_keys.get(), ck_alt.get(), (size_t)Nn * sizeof(u64));

@@ -291,6 +291,8 @@ int tmrgpu_node_sizes(tmrgpu_forest *F, int64_t sizes[6]) {
   return nd.valid ? 0 : 1;
 }
 
+int64_t tmrgpu_node_candidates(tmrgpu_forest *f) { return f->f.nodes.num_candidates; }
+
 int tmrgpu_download_nodes(tmrgpu_forest *F, int *conn, int *node_numbers,
                           int *dep_ptr, int *dep_conn, double *dep_weights) {
   Forest &f = F->f;
