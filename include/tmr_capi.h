@@ -97,6 +97,17 @@ void tmrc_find_enclosing(tmrc_forest f, int order, const double *knots,
                          const tmrc_octant *nodes, int n, int *out_index,
                          int *out_owner);
 
+/* distributeOctants / sendOctants (reference src/TMROctForest.h:166-176) on a
+   caller-provided list; the received records are copied into `out` (capacity
+   `cap`); returns the received count.  oct_ptr / recv_ptr: size()+1 ints. */
+int tmrc_distribute_octants(tmrc_forest f, const tmrc_octant *list, int n,
+                            int use_tags, int include_local, int use_node_index,
+                            tmrc_octant *out, int cap, int *oct_ptr,
+                            int *recv_ptr);
+int tmrc_send_octants(tmrc_forest f, const tmrc_octant *list, int n,
+                      const int *oct_ptr, const int *recv_ptr,
+                      int use_node_index, tmrc_octant *out, int cap);
+
 /* createInterpolation into a recording interp object */
 tmrc_interp tmrc_interp_create(void);
 void tmrc_interp_destroy(tmrc_interp p);

@@ -98,6 +98,16 @@ int tmrgpu_repartition(tmrgpu_forest *f, int max_rank);
 int tmrgpu_get_owners(tmrgpu_forest *f, tmrgpu_octant *out);
 /* owned-node prefix over ranks, size()+1 ints (reference node_range) */
 int tmrgpu_node_range(tmrgpu_forest *f, int *out);
+/* all-to-all-v of 24-byte octant records held in HOST arrays (the public
+   distributeOctants / sendOctants entry points, reference :2379-2509):
+   send_ptr/recv_ptr have size()+1 entries (element offsets); the records are
+   staged through the GPU and exchanged over NCCL.  exchange_counts turns
+   per-destination send counts into per-source receive counts. */
+int tmrgpu_exchange_counts(tmrgpu_ctx *ctx, const int *send_counts,
+                           int *recv_counts);
+int tmrgpu_exchange_records(tmrgpu_ctx *ctx, const tmrgpu_octant *send,
+                            const int *send_ptr, tmrgpu_octant *recv,
+                            const int *recv_ptr);
 /* balance (reference :2917-3089) */
 int tmrgpu_balance(tmrgpu_forest *f, int balance_corner);
 /* coarsen / duplicate into an existing forest (reference :2097-2164) */

@@ -34,6 +34,46 @@ def test_multirank_interpolation(order, ranks, mode, emu_lib, ref_lib):
     assert sum(len(x[1]["interp"]) for x in b) > 0
 
 
+def test_public_distribute_octants(emu_lib, ref_lib):
+    """distributeOctants / sendOctants as external callers use them (reference
+    src/topology/TMR_TACSTopoCreator.cpp:166-217): route a sorted octant list
+    to the owners of the positions and send a reply back."""
+    conn = util.box_conn()
+    ranks = 3
+
+    def body(lib, rank):
+        from tmr_b200.forest import OctForest, array_sort
+
+        f = OctForest(lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(2)
+        f.repartition()
+        rng = np.random.default_rng(100 + rank)
+        mine = util.random_octants(rng, 200, 7, 4)
+        mine["tag"] = rank
+        mine = array_sort(lib, mine, 0)
+        got, optr, rptr = f.distributeOctants(mine, ranks)
+        got2, _, _ = f.distributeOctants(mine, ranks, include_local=1)
+        back = f.sendOctants(got, rptr, optr)
+        return got, optr, rptr, got2, back
+
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    for r in range(ranks):
+        for k in (1, 2):
+            assert np.array_equal(a[r][k], b[r][k]), (r, k)
+        for k in (0, 3):
+            util.assert_octants_equal(a[r][k], b[r][k], "rank %d list %d" % (r, k))
+        # the reply lands in the slots of the original send intervals
+        ra, rb = a[r][4], b[r][4]
+        assert len(ra) == len(rb)
+        optr = a[r][1]
+        for i in range(ranks):
+            if i != r:
+                util.assert_octants_equal(ra[optr[i]:optr[i + 1]], rb[optr[i]:optr[i + 1]],
+                                          "reply rank %d from %d" % (r, i))
+
+
 def test_rank_count_invariance(emu_lib):
     """The balanced octant set does not depend on the number of ranks."""
     conn = util.box_conn()

@@ -258,3 +258,58 @@ def test_empty_and_level0(impl, ref_lib):
             f.refine(flags)
             f.balance(0)
         util.assert_nodes_equal(util.node_results(fa), util.node_results(fb), "one deep")
+
+
+def test_create_random_trees(impl, ref_lib):
+    """createRandomTrees draws from libc rand() in the reference's order
+    (reference src/TMROctForest.cpp:1863-1881): the same seed gives the same
+    forest, and the usual pipeline on top of it matches."""
+    import ctypes
+
+    libc = ctypes.CDLL("libc.so.6")
+    conn = util.connector_conn()
+    results = []
+    for lib in (ref_lib, impl):
+        libc.srand(12345)
+        f = OctForest(lib=lib)
+        f.setConnectivity(conn)
+        f.createRandomTrees(15, 0, 6)
+        first = f.getOctants().as_array().copy()
+        f.balance(1)
+        results.append((first, util.node_results(f)))
+    util.assert_octants_equal(results[0][0], results[1][0], "random trees")
+    util.assert_nodes_equal(results[0][1], results[1][1], "random trees nodes")
+
+
+def test_unbalanced_input_to_create_nodes(impl, ref_lib):
+    """createNodes on a forest that was refined but not balanced: the reference
+    produces *something* deterministic from its probes; so must we."""
+    conn = util.single_conn()
+    fa = OctForest(lib=ref_lib)
+    fb = OctForest(lib=impl)
+    for f in (fa, fb):
+        f.setConnectivity(conn)
+        f.createTrees(2)
+        f.balance(0)
+    util.assert_nodes_equal(util.node_results(fa), util.node_results(fb), "uniform")
+
+
+def test_write_through_octant_array(impl, ref_lib):
+    """Python's OctantArray.__setitem__ writes into the forest's array
+    (reference tmr/TMR.pyx:3303-3317): tags and info written by the caller are
+    what the next getOctants() shows, and octants written by the caller are what
+    the next operation works on."""
+    conn = util.box_conn()
+    outs = []
+    for lib in (ref_lib, impl):
+        f = util.build_forest(lib, conn, 1, 1, 30, 0)
+        rec = f.getOctants().as_array().copy()
+        rec["tag"] = 1000 + np.arange(len(rec))
+        f.writeOctants(rec)
+        again = f.getOctants().as_array().copy()
+        f.createNodes()  # only rewrites info
+        after = f.getOctants().as_array().copy()
+        outs.append((again, after))
+    util.assert_octants_equal(outs[0][0], outs[1][0], "write-through")
+    util.assert_octants_equal(outs[0][1], outs[1][1], "write-through + createNodes")
+    assert (outs[1][1]["tag"] >= 1000).all()

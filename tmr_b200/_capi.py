@@ -60,6 +60,8 @@ SIGNATURES = {
     "tmrc_get_inverse_connectivity": (None, [P, PPI, PPI, PPI, PPI, PPI, PPI]),
     "tmrc_transform_nodes": (None, [P, P, I, I, P, P]),
     "tmrc_find_enclosing": (None, [P, I, P, P, I, P, P]),
+    "tmrc_distribute_octants": (I, [P, P, I, I, I, I, P, I, P, P]),
+    "tmrc_send_octants": (I, [P, P, I, P, P, I, P, I]),
     "tmrc_interp_create": (P, []),
     "tmrc_interp_destroy": (None, [P]),
     "tmrc_create_interpolation": (None, [P, P, P]),

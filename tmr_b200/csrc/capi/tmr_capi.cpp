@@ -183,6 +183,51 @@ void tmrc_find_enclosing(tmrc_forest f, int order, const double *knots,
   }
 }
 
+static TMROctantArray *wrap_list(const tmrc_octant *list, int n, int use_node) {
+  TMROctant *copy = new TMROctant[n > 0 ? n : 1];
+  if (n > 0) memcpy(copy, list, (size_t)n * sizeof(TMROctant));
+  return new TMROctantArray(copy, n, use_node);
+}
+
+static int copy_out(TMROctantArray *arr, tmrc_octant *out, int cap) {
+  TMROctant *a = NULL;
+  int size = 0;
+  arr->getArray(&a, &size);
+  const int ncopy = size < cap ? size : cap;
+  if (ncopy > 0) memcpy(out, a, (size_t)ncopy * sizeof(TMROctant));
+  delete arr;
+  return size;
+}
+
+int tmrc_distribute_octants(tmrc_forest f, const tmrc_octant *list, int n,
+                            int use_tags, int include_local, int use_node_index,
+                            tmrc_octant *out, int cap, int *oct_ptr,
+                            int *recv_ptr) {
+  TMROctantArray *arr = wrap_list(list, n, use_node_index);
+  int *p = NULL, *rp = NULL;
+  TMROctantArray *got = F(f)->distributeOctants(arr, use_tags, &p, &rp,
+                                                include_local, use_node_index);
+  delete arr;
+  int size = 1;
+  MPI_Comm_size(F(f)->getMPIComm(), &size);
+  for (int i = 0; i <= size; i++) {
+    if (oct_ptr) oct_ptr[i] = p[i];
+    if (recv_ptr) recv_ptr[i] = rp[i];
+  }
+  delete[] p;
+  delete[] rp;
+  return copy_out(got, out, cap);
+}
+
+int tmrc_send_octants(tmrc_forest f, const tmrc_octant *list, int n,
+                      const int *oct_ptr, const int *recv_ptr,
+                      int use_node_index, tmrc_octant *out, int cap) {
+  TMROctantArray *arr = wrap_list(list, n, use_node_index);
+  TMROctantArray *got = F(f)->sendOctants(arr, oct_ptr, recv_ptr, use_node_index);
+  delete arr;
+  return copy_out(got, out, cap);
+}
+
 tmrc_interp tmrc_interp_create(void) { return new TACSBVecInterp(); }
 
 void tmrc_interp_destroy(tmrc_interp p) {

@@ -252,6 +252,43 @@ int tmrgpu_refine(tmrgpu_forest *F, const int *h_flags, int min_level,
   return refine_exchange(f);
 }
 
+int tmrgpu_exchange_counts(tmrgpu_ctx *ctx, const int *send_counts,
+                           int *recv_counts) {
+  Comm *comm = ctx->c.comm;
+  if (!comm) {
+    recv_counts[0] = send_counts[0];
+    return 0;
+  }
+  std::vector<i64> sc(comm->size), rc(comm->size);
+  for (int r = 0; r < comm->size; r++) sc[r] = send_counts[r];
+  exchange_counts(ctx->c, *comm, sc.data(), rc.data());
+  for (int r = 0; r < comm->size; r++) recv_counts[r] = (int)rc[r];
+  return check_errors(ctx->c, "exchange_counts");
+}
+
+int tmrgpu_exchange_records(tmrgpu_ctx *ctx, const tmrgpu_octant *send,
+                            const int *send_ptr, tmrgpu_octant *recv,
+                            const int *recv_ptr) {
+  Ctx &c = ctx->c;
+  Comm *comm = c.comm;
+  const int R = comm ? comm->size : 1;
+  const i64 ns = send_ptr[R], nr = recv_ptr[R];
+  if (!comm) {
+    if (nr > 0) memcpy(recv, send + send_ptr[0], (size_t)nr * sizeof(Oct24));
+    return 0;
+  }
+  std::vector<i64> so(R + 1), ro(R + 1);
+  for (int r = 0; r <= R; r++) {
+    so[r] = send_ptr[r];
+    ro[r] = recv_ptr[r];
+  }
+  DBuf<Oct24> ds(c, ns), dr(c, nr);
+  copy_h2d(c, ds.get(), send, (size_t)ns * sizeof(Oct24));
+  comm->alltoallv(c, ds.get(), so.data(), dr.get(), ro.data(), sizeof(Oct24));
+  copy_d2h(c, recv, dr.get(), (size_t)nr * sizeof(Oct24));
+  return check_errors(c, "exchange_records");
+}
+
 int tmrgpu_balance(tmrgpu_forest *f, int balance_corner) {
   if (f->f.ctx->comm) return balance_multi(f->f, balance_corner);
   return balance(f->f, balance_corner);

@@ -958,24 +958,53 @@ void TMROctForest::getInverseConnectivity(const int **_node_block_conn,
   if (_face_block_ptr) *_face_block_ptr = t ? t->face_block_ptr : NULL;
 }
 
-/* ---- exchange plumbing (reference :2379-2509), single-rank semantics ------------------------ */
+/* ---- exchange plumbing (reference :2379-2509) ---------------------------------------------------
+   Public entry points for callers that route their own octant lists (e.g.
+   reference src/topology/TMR_TACSTopoCreator.cpp:166-217).  The interval
+   matching is the reference's (a scan of the sorted list against owners[]);
+   the records travel GPU-to-GPU over NCCL. */
 TMROctantArray *TMROctForest::distributeOctants(TMROctantArray *list,
                                                 int use_tags, int **_oct_ptr,
                                                 int **_oct_recv_ptr,
                                                 int include_local,
                                                 int use_node_index) {
-  (void)use_tags;
   int size;
   TMROctant *array;
   list->getArray(&array, &size);
   int *oct_ptr = new int[mpi_size + 1];
   int *oct_recv_ptr = new int[mpi_size + 1];
-  /* one rank owns everything: the local interval is the whole list */
   oct_ptr[0] = 0;
-  for (int r = 1; r <= mpi_size; r++) oct_ptr[r] = size;
+  if (use_tags) {
+    /* matchTagIntervals (:2365-2374): the list is sorted by destination tag */
+    for (int i = 0, rank = 0; rank < mpi_size; rank++) {
+      while (i < size && array[i].tag <= rank) i++;
+      oct_ptr[rank + 1] = i;
+    }
+  } else {
+    /* matchOctantIntervals (:2348-2360): sorted by position, cut at owners[] */
+    if (mpi_size > 1 && !owners && dev) {
+      owners = new TMROctant[mpi_size];
+      tmrgpu_get_owners(dev, reinterpret_cast<tmrgpu_octant *>(owners));
+    }
+    int index = 0;
+    for (int rank = 0; rank < mpi_size - 1; rank++) {
+      while (index < size && owners &&
+             owners[rank + 1].comparePosition(&array[index]) > 0) {
+        index++;
+      }
+      oct_ptr[rank + 1] = index;
+    }
+  }
+  oct_ptr[mpi_size] = size;
+  std::vector<int> counts(mpi_size), recv_counts(mpi_size);
+  for (int i = 0; i < mpi_size; i++) {
+    counts[i] = (!include_local && i == mpi_rank) ? 0 : oct_ptr[i + 1] - oct_ptr[i];
+  }
+  tmrgpu_ctx *ctx = tmr_b200_context();
+  if (ctx) tmrgpu_exchange_counts(ctx, counts.data(), recv_counts.data());
   oct_recv_ptr[0] = 0;
-  for (int r = 1; r <= mpi_size; r++) {
-    oct_recv_ptr[r] = include_local ? size : 0;
+  for (int i = 0; i < mpi_size; i++) {
+    oct_recv_ptr[i + 1] = oct_recv_ptr[i] + recv_counts[i];
   }
   TMROctantArray *dist = sendOctants(list, oct_ptr, oct_recv_ptr, use_node_index);
   if (_oct_ptr) {
@@ -1000,11 +1029,41 @@ TMROctantArray *TMROctForest::sendOctants(TMROctantArray *list,
   list->getArray(&array, &size);
   const int recv_size = oct_recv_ptr[mpi_size];
   TMROctant *recv = new TMROctant[recv_size > 0 ? recv_size : 1];
+  /* the local segment only moves when both sides agree on its length
+     (reference :2489-2494); the others always do */
+  std::vector<int> sp(oct_ptr, oct_ptr + mpi_size + 1);
+  std::vector<int> send_ptr(mpi_size + 1, 0), send_counts(mpi_size);
   const int r = mpi_rank;
-  const int count = oct_recv_ptr[r + 1] - oct_recv_ptr[r];
-  if (count > 0 && count == oct_ptr[r + 1] - oct_ptr[r]) {
-    memcpy(&recv[oct_recv_ptr[r]], &array[oct_ptr[r]],
-           (size_t)count * sizeof(TMROctant));
+  const int local_recv = oct_recv_ptr[r + 1] - oct_recv_ptr[r];
+  const int local_send = oct_ptr[r + 1] - oct_ptr[r];
+  /* pack the segments that actually travel into one staging array */
+  std::vector<TMROctant> stage;
+  stage.reserve(size);
+  for (int i = 0; i < mpi_size; i++) {
+    int cnt = oct_ptr[i + 1] - oct_ptr[i];
+    if (i == r) cnt = (local_recv > 0 && local_recv == local_send) ? local_send : 0;
+    send_ptr[i + 1] = send_ptr[i] + cnt;
+    for (int k = 0; k < cnt; k++) stage.push_back(array[oct_ptr[i] + k]);
+  }
+  std::vector<int> recv_ptr(oct_recv_ptr, oct_recv_ptr + mpi_size + 1);
+  if (!(local_recv > 0 && local_recv == local_send)) {
+    /* nothing arrives in the local slot: shift the later segments down */
+    for (int i = r + 1; i <= mpi_size; i++) recv_ptr[i] -= local_recv;
+  }
+  tmrgpu_ctx *ctx = tmr_b200_context();
+  if (ctx) {
+    std::vector<TMROctant> tmp(recv_ptr[mpi_size] > 0 ? recv_ptr[mpi_size] : 1);
+    tmrgpu_exchange_records(
+        ctx, reinterpret_cast<const tmrgpu_octant *>(stage.data()),
+        send_ptr.data(), reinterpret_cast<tmrgpu_octant *>(tmp.data()),
+        recv_ptr.data());
+    for (int i = 0; i < mpi_size; i++) {
+      const int cnt = recv_ptr[i + 1] - recv_ptr[i];
+      if (cnt > 0) {
+        memcpy(&recv[oct_recv_ptr[i]], &tmp[recv_ptr[i]],
+               (size_t)cnt * sizeof(TMROctant));
+      }
+    }
   }
   return new TMROctantArray(recv, recv_size, use_node_index);
 }

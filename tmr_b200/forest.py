@@ -252,6 +252,31 @@ class OctForest:
             idx.ctypes.data, own.ctypes.data)
         return idx, own
 
+    def distributeOctants(self, records, nranks, use_tags=0, include_local=0,
+                          use_node_index=0, cap=None):
+        """TMROctForest::distributeOctants on a host list; returns (received
+        records, oct_ptr, recv_ptr)."""
+        rec = np.ascontiguousarray(records, dtype=_capi.OCT_DTYPE)
+        cap = cap if cap is not None else max(16, 64 * len(rec) + 1024)
+        out = np.zeros(cap, dtype=_capi.OCT_DTYPE)
+        optr = np.zeros(nranks + 1, dtype=np.int32)
+        rptr = np.zeros(nranks + 1, dtype=np.int32)
+        n = self._lib.tmrc_distribute_octants(
+            self._ptr, rec.ctypes.data, len(rec), use_tags, include_local,
+            use_node_index, out.ctypes.data, cap, optr.ctypes.data, rptr.ctypes.data)
+        return out[:n].copy(), optr, rptr
+
+    def sendOctants(self, records, oct_ptr, recv_ptr, use_node_index=0, cap=None):
+        rec = np.ascontiguousarray(records, dtype=_capi.OCT_DTYPE)
+        optr = np.ascontiguousarray(oct_ptr, dtype=np.int32)
+        rptr = np.ascontiguousarray(recv_ptr, dtype=np.int32)
+        cap = cap if cap is not None else int(rptr[-1]) + 16
+        out = np.zeros(cap, dtype=_capi.OCT_DTYPE)
+        n = self._lib.tmrc_send_octants(
+            self._ptr, rec.ctypes.data, len(rec), optr.ctypes.data, rptr.ctypes.data,
+            use_node_index, out.ctypes.data, cap)
+        return out[:n].copy()
+
     def createInterpolation(self, coarse, vec=None):
         if vec is None:
             vec = VecInterp(self._lib)
