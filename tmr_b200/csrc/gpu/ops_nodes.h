@@ -772,11 +772,26 @@ struct DepFillFn {
   const int *dep_node; /* dependent index -> node index (search hint) */
 
   KeyIndex node_ix;
+  /* order 2 shortcut: in a complete family the parent's corner c is corner c
+     of sibling c, so the parent's edge/face nodes are read from the siblings'
+     connectivity instead of being searched by key */
+  const int *conn_local;
+  NodeEmit fam;
 
   TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, i64) const {
     transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
     const i64 idx = node_ix.find(node_keys, nfmt.encode(block, x, y, z));
     return idx >= 0 ? node_num[idx] : 0;
+  }
+  /* first element of e's family if that family is complete, else -1 */
+  TMR_HD i64 family_base(i64 e) const {
+    if (order != 2) return -1;
+    int m;
+    return fam.in_family(e, &m) ? e - m : -1;
+  }
+  TMR_HD int parent_corner_node(i64 e0, int c) const {
+    const int m = 4 * (c & 1) + 2 * ((c >> 1) & 1) + (c >> 2);
+    return node_num[conn_local[(e0 + m) * 8 + c]];
   }
 
   TMR_HD void operator()(i64 d) const {
@@ -797,7 +812,16 @@ struct DepFillFn {
       const i32 step = hp / (order - 1);
       const int s = ed & 3;
       const i32 ta = hp * (s & 1), tb = hp * (s >> 1);
+      const i64 e0 = family_base(e);
       for (int ii = 0; ii < order; ii++) {
+        if (e0 >= 0) {
+          const int sa = s & 1, sb = s >> 1;
+          const int c = ed < 4 ? (ii + 2 * sa + 4 * sb)
+                               : (ed < 8 ? (sa + 2 * ii + 4 * sb)
+                                         : (sa + 2 * sb + 4 * ii));
+          dep_conn[ptr + ii] = parent_corner_node(e0, c);
+          continue;
+        }
         i32 nx, ny, nz;
         if (ed < 4) {
           nx = px + ii * step; ny = py + ta; nz = pz + tb;
@@ -827,8 +851,17 @@ struct DepFillFn {
       const i32 px = x & ~h, py = y & ~h, pz = z & ~h;
       const i32 step = hp / (order - 1);
       const i32 nn = hp * (f & 1);
+      const i64 e0 = family_base(e);
       for (int q = 0; q < order; q++) {
         for (int p = 0; p < order; p++) {
+          if (e0 >= 0) {
+            const int n1 = f & 1;
+            const int c = f < 2 ? (n1 + 2 * p + 4 * q)
+                                : (f < 4 ? (p + 2 * n1 + 4 * q)
+                                         : (p + 2 * q + 4 * n1));
+            dep_conn[ptr + p + q * order] = parent_corner_node(e0, c);
+            continue;
+          }
           i32 nx, ny, nz;
           if (f < 2) {
             nx = px + nn; ny = py + p * step; nz = pz + q * step;
@@ -1502,6 +1535,11 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.win_edge = win_edge.get();
     fill.win_face = win_face.get();
     fill.dep_node = dep_node.get();
+    fill.conn_local = nd.conn.get();
+    {
+      NodeEmit fg = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order, order == 2 ? 1 : 0};
+      fill.fam = fg;
+    }
     fill.dep_ptr = nd.dep_ptr.get();
     fill.dep_conn = nd.dep_conn.get();
     fill.dep_weights = nd.dep_weights.get();
