@@ -216,6 +216,13 @@ def main():
     ap.add_argument("--passes", type=int, default=FULL["passes"],
                     help="refinement passes of the recipe (4 = the named ~86M config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2: 8x8x8N-tree box (BASELINE configs[1], the headline); "
+                         "c4: 5x5x6 tiled 7-tree butterfly cells = 1050 trees with all 8 "
+                         "face orientations, balance(1) (BASELINE configs[3])")
+    ap.add_argument("--nbz-per-gpu", type=int, default=8,
+                    help="c2: trees along z per GPU (8 = 86 M octants per GPU; 12 = 130 M, "
+                         "i.e. >1e9 octants on 8 GPUs, BASELINE configs[4])")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: split the SAME 8x8x8-tree forest over the GPUs "
                          "(default: weak scaling, 8x8x8N trees)")
@@ -275,6 +282,9 @@ def main():
 
     cfg = dict(FULL)
     cfg["passes"] = args.passes
+    if args.workload == "c4":
+        cfg["corner"] = 1
+        cfg["pct"] = 30
     knots = (ctypes.c_double * 2)(-1.0, 1.0)
 
     # ---- build-up: everything before the timed cycle, all on the device ----
@@ -282,9 +292,13 @@ def main():
     # (NCCL exchanges inside refine/balance/repartition/createNodes).  Weak
     # scaling stacks N copies of the 8x8x8-tree box along z (8x8x8N trees);
     # --strong splits the same 8x8x8 box.
-    nbz = cfg["nb"] * (1 if (args.strong or world == 1) else world)
+    nbz = args.nbz_per_gpu * (1 if (args.strong or world == 1) else world)
     base = OctForest(order=cfg["order"], lib=lib)
-    base.setConnectivity(util.structured_conn(cfg["nb"], cfg["nb"], nbz))
+    if args.workload == "c4":
+        block_conn = util.butterfly_conn(5, 5, 6 * (1 if (args.strong or world == 1) else world))
+    else:
+        block_conn = util.structured_conn(cfg["nb"], cfg["nb"], nbz)
+    base.setConnectivity(block_conn)
     base.createTrees(cfg["level"])
     bdev = P(lib.tmr_b200_device_forest(base._ptr))
     if world > 1:
@@ -471,7 +485,10 @@ def main():
             "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
             "vs_baseline": None,
             "dtype": "int32 keys as u64 Morton + f64 weights", "data": "synthetic",
-            "config": {"workload": workload_name(cfg),
+            "config": {"workload": workload_name(cfg) if args.workload == "c2" else
+                       "%d-tree tiled butterfly forest (all 8 face orientations, irregular valence), createTrees(%d), %d passes pct=%d, last cycle refine+balance(1)+createNodes(order 2)"
+                       % (len(block_conn), cfg["level"], cfg["passes"], cfg["pct"]),
+                       "trees": int(len(block_conn)),
                        "octants_in": int(e_in), "octants_out_per_gpu": int(e_final),
                        "local_nodes": int(sizes[1]), "dep_nodes": int(sizes[2]),
                        "dep_nnz": int(sizes[4]), "node_candidates_sorted": n_cand, "checksum": "%016x" % global_checksum,
