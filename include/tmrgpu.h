@@ -132,6 +132,20 @@ int tmrgpu_download_nodes(tmrgpu_forest *f, int *conn, int *node_numbers,
    reference :4246) */
 int tmrgpu_download_sorted_node_numbers(tmrgpu_forest *f, int *out);
 
+/* Device-resident views for GPU consumers (the FE assembler and
+   a bulk TACSBVecInterp ingest can read the arrays where they are instead of
+   going through the host int* getters).  Pointers are device pointers owned by
+   the forest, valid until the next mutating call; sizes as tmrgpu_node_sizes /
+   tmrgpu_create_interp report them.  Any out-pointer may be NULL. */
+int tmrgpu_node_device_views(tmrgpu_forest *f, const int **conn,
+                             const int **node_numbers, const int **dep_ptr,
+                             const int **dep_conn, const double **dep_weights,
+                             const uint64_t **element_keys, int *key_depth,
+                             int *block_bits);
+int tmrgpu_interp_device_views(tmrgpu_forest *fine, const int **rows,
+                               const int **rowp, const int **cols,
+                               const double **vals);
+
 /* createInterpolation (reference :6611-6793) between two forests that both
    have nodes.  Builds the CSR on the device; rows are emitted in the
    reference's call order (first touch in element order). */

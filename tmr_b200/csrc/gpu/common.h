@@ -490,54 +490,6 @@ TMR_HD i64 lower_bound_u64(const u64 *a, i64 n, u64 key) {
   return lo;
 }
 
-/* lower_bound that gallops outwards from `hint`: the Morton-sorted arrays are
-   probed for spatial neighbours of entry `hint`, which are usually a few
-   thousand slots away, so the bracket is found in ~2*log2(distance) steps on
-   cache lines that neighbouring threads touch too */
-TMR_HD i64 lower_bound_near(const u64 *a, i64 n, u64 key, i64 hint) {
-  if (n <= 0) return 0;
-  if (hint < 0) hint = 0;
-  if (hint >= n) hint = n - 1;
-  i64 lo, hi;
-  if (a[hint] < key) {
-    /* answer in (hint, n] */
-    i64 step = 1;
-    lo = hint + 1;
-    hi = lo + step;
-    while (hi < n && a[hi - 1] < key) {
-      lo = hi;
-      step <<= 1;
-      hi = lo + step;
-    }
-    if (hi > n) hi = n;
-  } else {
-    /* answer in [0, hint] */
-    i64 step = 1;
-    hi = hint;
-    lo = hi - step;
-    while (lo > 0 && a[lo] >= key) {
-      hi = lo;
-      step <<= 1;
-      lo = hi - step;
-    }
-    if (lo < 0) lo = 0;
-  }
-  while (lo < hi) {
-    const i64 mid = lo + ((hi - lo) >> 1);
-    if (a[mid] < key) {
-      lo = mid + 1;
-    } else {
-      hi = mid;
-    }
-  }
-  return lo;
-}
-
-TMR_HD i64 find_near_u64(const u64 *a, i64 n, u64 key, i64 hint) {
-  const i64 i = lower_bound_near(a, n, key, hint);
-  return (i < n && a[i] == key) ? i : -1;
-}
-
 /* Radix-indexed search: table[p] = first index whose key >> shift >= p, so a
    probe is one table read (the table is sized to stay L2-resident) plus a
    binary search inside one short bucket instead of log2(n) steps over the

@@ -1002,17 +1002,6 @@ struct OwnerMinFn { /* scan_apply body over the key-sorted received items */
   }
 };
 
-struct OwnerReplyFn {
-  const u32 *idx;
-  const u32 *run_of;
-  const int *owner_run;
-  int *reply; /* by original received index */
-  TMR_HD void operator()(i64 j) const {
-    const int o = owner_run[run_of[j]];
-    reply[idx[j]] = (o == 0x7fffffff) ? -1 : o;
-  }
-};
-
 /* owner of a node whose home is this rank starts as "me if I create it" */
 struct OwnerInitFn {
   NodeHomeFn home;

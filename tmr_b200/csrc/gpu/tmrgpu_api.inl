@@ -359,6 +359,35 @@ int tmrgpu_download_nodes(tmrgpu_forest *F, int *conn, int *node_numbers,
   return check_errors(ctx, "download_nodes");
 }
 
+int tmrgpu_node_device_views(tmrgpu_forest *F, const int **conn,
+                             const int **node_numbers, const int **dep_ptr,
+                             const int **dep_conn, const double **dep_weights,
+                             const uint64_t **element_keys, int *key_depth,
+                             int *block_bits) {
+  Forest &f = F->f;
+  const NodeData &nd = f.nodes;
+  if (conn) *conn = nd.conn.get();
+  if (node_numbers) *node_numbers = nd.node_num.get();
+  if (dep_ptr) *dep_ptr = nd.dep_ptr.get();
+  if (dep_conn) *dep_conn = nd.dep_conn.get();
+  if (dep_weights) *dep_weights = nd.dep_weights.get();
+  if (element_keys) *element_keys = f.keys.get();
+  if (key_depth) *key_depth = f.fmt.D;
+  if (block_bits) *block_bits = f.fmt.bbits;
+  return nd.valid ? 0 : 1;
+}
+
+int tmrgpu_interp_device_views(tmrgpu_forest *F, const int **rows,
+                               const int **rowp, const int **cols,
+                               const double **vals) {
+  const InterpData &I = F->f.interp;
+  if (rows) *rows = I.rows.get();
+  if (rowp) *rowp = I.rowp.get();
+  if (cols) *cols = I.cols.get();
+  if (vals) *vals = I.vals.get();
+  return I.valid ? 0 : 1;
+}
+
 int tmrgpu_download_sorted_node_numbers(tmrgpu_forest *f, int *out) {
   return sorted_node_numbers(f->f, out);
 }
