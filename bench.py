@@ -447,10 +447,19 @@ def main():
                "nodes_dep_fill": 12 * sizes[4] + 16 * sizes[2],
                "nodes_hanging_info": 10 * sizes[0]}.get(name)
         avg_ms = st["ms"] / st["launches"]
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as fh:
+                ent = json.load(fh).get(name)
+            # only valid for the launch shape it was captured on
+            if ent and abs(ent["keys"] - n_cand) <= 0.01 * n_cand:
+                traffic = ent["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
         if alg:
             ach = alg / (avg_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "avg_launch_ms": avg_ms,
                     "launches_per_step": st["launches"] / args.steps,
                     "algorithmic_bytes_per_launch": alg}
