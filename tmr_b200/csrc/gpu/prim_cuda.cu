@@ -369,13 +369,11 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     const u32 peers = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(peers) - 1;
     u32 old = 0;
-    if (lane == leader) {
-      old = my_hist[d];
-      my_hist[d] = old + __popc(peers);
-    }
+    /* one shared-memory atomic per distinct digit of the round; rounds of the
+       same warp execute in program order, which keeps the ranking stable */
+    if (lane == leader) old = atomicAdd(&my_hist[d], (u32)__popc(peers));
     old = __shfl_sync(0xffffffffu, old, leader);
     rank[j] = (unsigned short)(old + __popc(peers & ((1u << lane) - 1u)));
-    __syncwarp();
   }
   __syncthreads();
 
@@ -400,14 +398,29 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     if (lane == 31) s_wsum[warp] = incl;
   }
   __syncthreads();
+  u32 dbase = 0;
   if (tid < kRadix) {
     u32 woff = 0;
 #pragma unroll
     for (int w = 0; w < kRadix / 32; w++) {
       if (w < warp) woff += s_wsum[w];
     }
-    const u32 dbase = woff + incl - count;
+    dbase = woff + incl - count;
     s_dbase[tid] = dbase;
+  }
+  __syncthreads();
+
+  /* (4) stage the tile in digit order first: it only needs the local digit
+     bases, and it gives the preceding tiles time to publish before ... */
+#pragma unroll
+  for (int j = 0; j < kSortItems; j++) {
+    const u32 d = (u32)(key[j] >> shift) & dmask;
+    const u32 q = s_dbase[d] + my_hist[d] + rank[j];
+    s_keys[q] = key[j];
+    if (kHasVals) s_vals[q] = val[j];
+  }
+  /* ... (5) the decoupled look-back resolves the global offset of each digit */
+  if (tid < kRadix) {
     u64 excl = 0;
     if (tile > 0) {
       i64 p = (i64)tile - 1;
@@ -423,16 +436,6 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     }
     /* global index of staged position q holding digit d: goff[d] + q */
     s_goff[tid] = (u64)pass_offset[tid] + excl - (u64)dbase;
-  }
-  __syncthreads();
-
-  /* (4) stage in digit order, then write out coalesced */
-#pragma unroll
-  for (int j = 0; j < kSortItems; j++) {
-    const u32 d = (u32)(key[j] >> shift) & dmask;
-    const u32 q = s_dbase[d] + my_hist[d] + rank[j];
-    s_keys[q] = key[j];
-    if (kHasVals) s_vals[q] = val[j];
   }
   __syncthreads();
 #pragma unroll
