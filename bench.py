@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--passes", type=int, default=FULL["passes"],
                     help="refinement passes of the recipe (4 = the named ~86M config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None,
+                    help="write the per-kernel CUDA-event times of the timed region (ms per step) here")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
                     help="c2: 8x8x8N-tree box (BASELINE configs[1], the headline); "
                          "c4: 5x5x6 tiled 7-tree butterfly cells = 1050 trees with all 8 "
@@ -380,6 +382,11 @@ def main():
     lib.tmrgpu_profile_json(ctx, buf, len(buf))
     prof = json.loads(buf.value.decode())
     lib.tmrgpu_profile_enable(ctx, 0)
+    if args.profile_out and rank == 0:
+        with open(args.profile_out, "w") as fh:
+            json.dump({k: {"launches_per_step": v["launches"] / args.steps,
+                           "ms_per_step": v["ms"] / args.steps}
+                       for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}, fh, indent=1)
     work, wdev = last
     e_final = lib.tmrgpu_count(wdev)
     sizes = (I64 * 6)()

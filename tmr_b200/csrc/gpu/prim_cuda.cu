@@ -265,6 +265,8 @@ static const int kSortWarps = kSortThreads / 32;
 static const int kSortItems = 8;
 static const int kSortTile = kSortThreads * kSortItems; /* 4096 keys */
 static const int kMaxPasses = 8;
+static const int kDefaultRadixVariant = 15;
+static const int kScanChunk = 256; /* tiles per chunk of the offset table */
 
 struct PassPlan {
   int npass;
@@ -272,7 +274,15 @@ struct PassPlan {
   int bits[kMaxPasses];
 };
 
-/* One read of the keys -> digit histograms of every pass. */
+/* One read of the keys -> digit histograms of every pass.  Four keys per
+   thread per round are in flight; each key adds 1 to its bin of every pass
+   with a shared-memory RED (3.2 clk per warp instruction on B200 when the
+   lanes hit different bins, measured).  Rows whose 32 digits are equal -- the
+   rule for the high digits of Morton-ordered input -- would serialise 32-fold
+   on one bank, so match.all (2 clk) detects them and one lane adds 32.
+   kMatch = the previous scheme (match.any aggregation: ~2 clk per distinct
+   digit, 61 clk for a random row), kept for A/B measurement. */
+template <bool kMatch>
 __global__ void __launch_bounds__(kHistThreads)
     radix_hist_kernel(const u64 *__restrict__ keys, i64 n, PassPlan plan,
                       u32 *__restrict__ ghist) {
@@ -281,19 +291,54 @@ __global__ void __launch_bounds__(kHistThreads)
     s_hist[i] = 0;
   }
   __syncthreads();
-  const i64 stride = (i64)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  const i64 nround = ((n + 31) / 32) * 32; /* keep warps converged */
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nround;
-       i += stride) {
-    const bool valid = i < n;
-    const u64 k = valid ? keys[i] : 0;
-    for (int p = 0; p < plan.npass; p++) {
-      const u32 d = (u32)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
-      /* warp-aggregated increment: one shared atomic per distinct digit */
-      const u32 peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
-      if (valid && lane == (__ffs(peers) - 1)) {
-        atomicAdd(&s_hist[p * kMaxRadix + d], __popc(peers));
+  if (kMatch) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 nround = ((n + 31) / 32) * 32; /* keep warps converged */
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nround;
+         i += stride) {
+      const bool valid = i < n;
+      const u64 k = valid ? keys[i] : 0;
+      for (int p = 0; p < plan.npass; p++) {
+        const u32 d = (u32)(k >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u);
+        const u32 peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+        if (valid && lane == (__ffs(peers) - 1)) {
+          atomicAdd(&s_hist[p * kMaxRadix + d], __popc(peers));
+        }
+      }
+    }
+  } else {
+    const int kUnroll = 4;
+    const i64 chunk = (i64)blockDim.x * kUnroll;
+    const i64 nchunks = (n + chunk - 1) / chunk;
+    for (i64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+      const i64 base = c * chunk + threadIdx.x;
+      u64 k[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) {
+        const i64 i = base + (i64)u * blockDim.x;
+        k[u] = (i < n) ? keys[i] : 0;
+      }
+      const bool full = (c + 1) * chunk <= n; /* uniform over the CTA */
+      for (int p = 0; p < plan.npass; p++) {
+        const int sh = plan.shift[p];
+        const u32 m = (1u << plan.bits[p]) - 1u;
+        u32 *h = s_hist + p * kMaxRadix;
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) {
+          const u32 d = (u32)(k[u] >> sh) & m;
+          if (full) {
+            int uniform;
+            __match_all_sync(0xffffffffu, d, &uniform);
+            if (uniform) {
+              if (lane == 0) atomicAdd(&h[d], 32u);
+            } else {
+              atomicAdd(&h[d], 1u);
+            }
+          } else if (base + (i64)u * blockDim.x < n) {
+            atomicAdd(&h[d], 1u);
+          }
+        }
       }
     }
   }
@@ -320,17 +365,133 @@ __global__ void radix_scan_hist_kernel(u32 *ghist) {
   h[threadIdx.x] = s[threadIdx.x] - v;
 }
 
+/* ---- table mode: per-tile digit offsets without a look-back chain --------
+   Measured on B200 (ncu, 86 M-octant cycle): with decoupled look-back the
+   pass kernel spent 59 % of its warp time waiting for predecessor tiles -- the
+   prefix can only advance a few tiles per L2 round trip, and a 4096-key tile
+   is processed faster than that.  Reading the keys once more per pass (8 B per
+   key at streaming speed) to histogram every tile, and scanning the [tiles][R]
+   table, removes every inter-CTA dependency from the pass kernel. */
+template <int kBits>
+__global__ void __launch_bounds__(256)
+    radix_tile_hist_kernel(const u64 *__restrict__ keys, i64 n, int shift,
+                           int bits, u32 *__restrict__ thist) {
+  const int kRadix = 1 << kBits;
+  const int kItems = kSortTile / 256;
+  __shared__ u32 s_h[kRadix];
+  for (int i = threadIdx.x; i < kRadix; i += 256) s_h[i] = 0;
+  const i64 tile_base = (i64)blockIdx.x * kSortTile;
+  const bool full = tile_base + kSortTile <= n;
+  const u32 dmask = (1u << bits) - 1u;
+  u64 k[kItems];
+#pragma unroll
+  for (int u = 0; u < kItems; u++) {
+    const i64 i = tile_base + u * 256 + threadIdx.x;
+    k[u] = (full || i < n) ? keys[i] : 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int u = 0; u < kItems; u++) {
+    const u32 d = (u32)(k[u] >> shift) & dmask;
+    if (full) {
+      int uniform;
+      __match_all_sync(0xffffffffu, d, &uniform);
+      if (uniform) {
+        if (lane == 0) atomicAdd(&s_h[d], 32u);
+      } else {
+        atomicAdd(&s_h[d], 1u);
+      }
+    } else if (tile_base + u * 256 + threadIdx.x < n) {
+      atomicAdd(&s_h[d], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRadix; i += 256) {
+    thist[(size_t)blockIdx.x * kRadix + i] = s_h[i];
+  }
+}
+
+/* in place: exclusive prefix of every digit column within a chunk of
+   kScanChunk tiles; the chunk totals go to ctot[chunk][R] */
+template <int kBits>
+__global__ void __launch_bounds__(1 << kBits)
+    radix_tile_scan_kernel(u32 *__restrict__ thist, i64 tiles,
+                           u32 *__restrict__ ctot) {
+  const int kRadix = 1 << kBits;
+  const i64 row0 = (i64)blockIdx.x * kScanChunk;
+  const int rows = (int)((tiles - row0 < kScanChunk) ? (tiles - row0) : kScanChunk);
+  u32 *p = thist + (size_t)row0 * kRadix + threadIdx.x;
+  u32 run = 0;
+  int r = 0;
+  for (; r + 8 <= rows; r += 8) {
+    u32 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = p[(size_t)(r + u) * kRadix];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      p[(size_t)(r + u) * kRadix] = run;
+      run += v[u];
+    }
+  }
+  for (; r < rows; r++) {
+    const u32 v = p[(size_t)r * kRadix];
+    p[(size_t)r * kRadix] = run;
+    run += v;
+  }
+  ctot[(size_t)blockIdx.x * kRadix + threadIdx.x] = run;
+}
+
+/* one CTA: exclusive prefix of the chunk totals per digit (in place) and the
+   exclusive scan of the digit totals -> doff[R] */
+template <int kBits>
+__global__ void __launch_bounds__(1 << kBits)
+    radix_chunk_scan_kernel(u32 *__restrict__ ctot, int chunks,
+                            u32 *__restrict__ doff) {
+  const int kRadix = 1 << kBits;
+  __shared__ u32 s[kRadix];
+  u32 *p = ctot + threadIdx.x;
+  u32 run = 0;
+  int c = 0;
+  for (; c + 8 <= chunks; c += 8) {
+    u32 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = p[(size_t)(c + u) * kRadix];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      p[(size_t)(c + u) * kRadix] = run;
+      run += v[u];
+    }
+  }
+  for (; c < chunks; c++) {
+    const u32 v = p[(size_t)c * kRadix];
+    p[(size_t)c * kRadix] = run;
+    run += v;
+  }
+  s[threadIdx.x] = run;
+  __syncthreads();
+  for (int d = 1; d < kRadix; d <<= 1) {
+    const u32 t = (threadIdx.x >= d) ? s[threadIdx.x - d] : 0;
+    __syncthreads();
+    s[threadIdx.x] += t;
+    __syncthreads();
+  }
+  doff[threadIdx.x] = s[threadIdx.x] - run;
+}
+
 /* One pass of kBits (8 or 9) bits.  512 threads x 8 keys: 16 warps per CTA and
    <= 64 registers so that two CTAs (32 warps) are resident per SM and the load
    / rank / look-back / scatter phases of different CTAs overlap.  With 9-bit
    digits every thread owns one digit in the descriptor phase. */
-template <bool kHasVals, int kBits>
+template <bool kHasVals, int kBits, int kVar>
 __global__ void __launch_bounds__(kSortThreads, 2)
     radix_pass_kernel(const u64 *__restrict__ kin, u64 *__restrict__ kout,
                       const u32 *__restrict__ vin, u32 *__restrict__ vout,
                       i64 n, int shift, int bits,
                       const u32 *__restrict__ pass_offset, /* [kRadix] */
-                      u32 *ticket, u64 *lookback /* [tiles][kRadix] */) {
+                      u32 *ticket, u64 *lookback /* [tiles][kRadix] */,
+                      const u32 *__restrict__ tile_excl,  /* [tiles][kRadix] */
+                      const u32 *__restrict__ chunk_excl /* [chunks][kRadix] */) {
   const int kRadix = 1 << kBits;
   extern __shared__ unsigned char smem_raw[];
   u64 *s_keys = reinterpret_cast<u64 *>(smem_raw);            /* tile keys */
@@ -338,14 +499,27 @@ __global__ void __launch_bounds__(kSortThreads, 2)
   u32 *s_whist = s_vals + (kHasVals ? kSortTile : 0);         /* [warps][R] */
   u32 *s_dbase = s_whist + kSortWarps * kRadix;               /* [R] */
   u64 *s_goff = reinterpret_cast<u64 *>(s_dbase + kRadix);    /* [R] */
+  u32 *s_wmask = reinterpret_cast<u32 *>(s_goff + kRadix);    /* [warps][R] */
   __shared__ u32 s_tile;
   __shared__ u32 s_wsum[kMaxRadix / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) s_whist[i] = 0;
+  const bool kTable = (kVar & 8) != 0;
+  if (!kTable && tid == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) {
+    s_whist[i] = 0;
+    if (kVar & 1) s_wmask[i] = 0;
+  }
   __syncthreads();
-  const u32 tile = s_tile;
+  const u32 tile = kTable ? blockIdx.x : s_tile;
+  /* table mode: the tile's global digit offsets were computed by the
+     histogram + scan kernels; fetch them now, use them after staging */
+  u32 t_off = 0;
+  if (kTable && tid < kRadix) {
+    t_off = pass_offset[tid] +
+            chunk_excl[(size_t)(tile / kScanChunk) * kRadix + tid] +
+            tile_excl[(size_t)tile * kRadix + tid];
+  }
   const i64 tile_base = (i64)tile * kSortTile;
   const i64 rem = n - tile_base;
   const int tile_n = rem < kSortTile ? (int)rem : kSortTile;
@@ -363,17 +537,63 @@ __global__ void __launch_bounds__(kSortThreads, 2)
     if (kHasVals) val[j] = (i < n) ? vin[i] : 0u;
   }
   u32 *my_hist = s_whist + warp * kRadix;
+  bool use_masks = (kVar & 1) != 0;
+  if (kVar & 4) {
+    /* The two peer-discovery schemes have opposite worst cases (measured on
+       B200): match.any costs ~2 clk per DISTINCT digit in the row (61 clk for
+       random digits, 2 for equal ones); the shared-memory masks cost one bank
+       cycle per lane sharing a word (6 clk for distinct digits, 64 for equal
+       ones).  Rows of one warp look alike, so the warp probes rows 0 and 4:
+       if lane 0's digit is shared by >= 4 lanes in either, it uses match.any
+       for the tile. */
+    bool many = false;
 #pragma unroll
-  for (int j = 0; j < kSortItems; j++) {
-    const u32 d = (u32)(key[j] >> shift) & dmask;
-    const u32 peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    u32 old = 0;
-    /* one shared-memory atomic per distinct digit of the round; rounds of the
-       same warp execute in program order, which keeps the ranking stable */
-    if (lane == leader) old = atomicAdd(&my_hist[d], (u32)__popc(peers));
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[j] = (unsigned short)(old + __popc(peers & ((1u << lane) - 1u)));
+    for (int j = 0; j < kSortItems; j += 4) {
+      const u32 d = (u32)(key[j] >> shift) & dmask;
+      u32 b = __ballot_sync(0xffffffffu, d == __shfl_sync(0xffffffffu, d, 0));
+      b &= b - 1u;
+      b &= b - 1u;
+      b &= b - 1u;
+      many = many || (b != 0u);
+    }
+    use_masks = !many;
+  }
+  if (use_masks) {
+    /* Peer discovery through shared memory instead of match.any: every lane
+       ORs its bit into the warp's word for its digit, reads the word back (=
+       the lanes holding the same digit) and clears its own bit again.  All
+       peers read the warp's running count of the digit, the highest peer lane
+       advances it.  Rounds of one warp are ordered by the __syncwarp()s, which
+       keeps the ranking stable. */
+    u32 *my_mask = s_wmask + warp * kRadix;
+    const u32 lane_bit = 1u << lane, lanes_lt = lane_bit - 1u;
+#pragma unroll
+    for (int j = 0; j < kSortItems; j++) {
+      const u32 d = (u32)(key[j] >> shift) & dmask;
+      atomicOr(&my_mask[d], lane_bit);
+      __syncwarp();
+      const u32 peers = my_mask[d];
+      const u32 old = my_hist[d];
+      __syncwarp();
+      atomicAnd(&my_mask[d], ~lane_bit);
+      const u32 below = (u32)__popc(peers & lanes_lt);
+      if ((peers >> lane) == 1u) my_hist[d] = old + below + 1u; /* last peer */
+      rank[j] = (unsigned short)(old + below);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kSortItems; j++) {
+      const u32 d = (u32)(key[j] >> shift) & dmask;
+      const u32 peers = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(peers) - 1;
+      u32 old = 0;
+      /* one shared-memory atomic per distinct digit of the round; rounds of
+         the same warp execute in program order, which keeps the ranking
+         stable */
+      if (lane == leader) old = atomicAdd(&my_hist[d], (u32)__popc(peers));
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rank[j] = (unsigned short)(old + __popc(peers & ((1u << lane) - 1u)));
+    }
   }
   __syncthreads();
 
@@ -388,7 +608,9 @@ __global__ void __launch_bounds__(kSortThreads, 2)
       s_whist[w * kRadix + tid] = count;
       count += c;
     }
-    st_relaxed_u64(my_desc, (tile == 0 ? kStatusPrefix : kStatusAgg) | (u64)count);
+    if (!kTable) {
+      st_relaxed_u64(my_desc, (tile == 0 ? kStatusPrefix : kStatusAgg) | (u64)count);
+    }
     incl = count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -422,20 +644,50 @@ __global__ void __launch_bounds__(kSortThreads, 2)
   /* ... (5) the decoupled look-back resolves the global offset of each digit */
   if (tid < kRadix) {
     u64 excl = 0;
-    if (tile > 0) {
+    if (kTable) {
+      excl = t_off;
+    } else if (tile > 0) {
       i64 p = (i64)tile - 1;
-      while (true) {
-        const u64 v = ld_relaxed_u64(lookback + (size_t)p * kRadix + tid);
-        const u64 st = v & kStatusMask;
-        if (st == 0) continue;
-        excl += v & ~kStatusMask;
-        if (st == kStatusPrefix) break;
-        p--;
+      if (kVar & 2) {
+        /* kLook descriptors of consecutive predecessors are fetched at once:
+           a walk of m tiles costs ~m/kLook L2 round trips instead of m.  Rows
+           before tile 0 read as "inclusive prefix 0". */
+        const int kLook = 8;
+        bool done = false;
+        while (!done) {
+          u64 v[kLook];
+#pragma unroll
+          for (int u = 0; u < kLook; u++) {
+            v[u] = (p - u >= 0)
+                       ? ld_relaxed_u64(lookback + (size_t)(p - u) * kRadix + tid)
+                       : kStatusPrefix;
+          }
+          int used = 0;
+#pragma unroll
+          for (int u = 0; u < kLook; u++) {
+            const u64 st = v[u] & kStatusMask;
+            if (!done && used == u && st != 0) {
+              excl += v[u] & ~kStatusMask;
+              used = u + 1;
+              if (st == kStatusPrefix) done = true;
+            }
+          }
+          p -= used;
+        }
+      } else {
+        while (true) {
+          const u64 v = ld_relaxed_u64(lookback + (size_t)p * kRadix + tid);
+          const u64 st = v & kStatusMask;
+          if (st == 0) continue;
+          excl += v & ~kStatusMask;
+          if (st == kStatusPrefix) break;
+          p--;
+        }
       }
       st_relaxed_u64(my_desc, kStatusPrefix | (excl + (u64)count));
     }
     /* global index of staged position q holding digit d: goff[d] + q */
-    s_goff[tid] = (u64)pass_offset[tid] + excl - (u64)dbase;
+    s_goff[tid] = (kTable ? 0ULL : (u64)pass_offset[tid]) + excl - (u64)dbase;
   }
   __syncthreads();
 #pragma unroll
@@ -451,12 +703,13 @@ __global__ void __launch_bounds__(kSortThreads, 2)
   }
 }
 
-static size_t sort_smem_bytes(bool has_vals, int radix) {
+static size_t sort_smem_bytes(bool has_vals, int radix, int var) {
   size_t b = (size_t)kSortTile * sizeof(u64);
   if (has_vals) b += (size_t)kSortTile * sizeof(u32);
   b += (size_t)kSortWarps * radix * sizeof(u32);
   b += (size_t)radix * sizeof(u32);
   b += (size_t)radix * sizeof(u64);
+  if (var & 1) b += (size_t)kSortWarps * radix * sizeof(u32);
   return b;
 }
 
@@ -479,22 +732,87 @@ static PassPlan make_plan(int bit_lo, int bit_hi) {
   return pl;
 }
 
-template <bool kHasVals, int kBits>
-static void launch_pass(Ctx &ctx, i64 tiles, DBuf<u64> &keys, DBuf<u64> &keys_alt,
+template <bool kHasVals, int kBits, int kVar>
+static void launch_pass_v(Ctx &ctx, i64 tiles, DBuf<u64> &keys, DBuf<u64> &keys_alt,
                         DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int shift,
-                        int bits, const u32 *offs, u32 *ticket, u64 *lookback) {
-  const size_t smem = sort_smem_bytes(kHasVals, 1 << kBits);
+                        int bits, const u32 *offs, u32 *ticket, u64 *lookback,
+                        const u32 *tile_excl, const u32 *chunk_excl) {
+  const size_t smem = sort_smem_bytes(kHasVals, 1 << kBits, kVar);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(radix_pass_kernel<kHasVals, kBits>,
+    cudaFuncSetAttribute(radix_pass_kernel<kHasVals, kBits, kVar>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  radix_pass_kernel<kHasVals, kBits>
+  radix_pass_kernel<kHasVals, kBits, kVar>
       <<<(unsigned)tiles, kSortThreads, smem, (cudaStream_t)ctx.stream>>>(
           keys.get(), keys_alt.get(), kHasVals ? vals.get() : NULL,
           kHasVals ? vals_alt.get() : NULL, n, shift, bits, offs, ticket,
-          lookback);
+          lookback, tile_excl, chunk_excl);
+}
+
+/* TMR_RADIX_VARIANT (measurement switch): bit 0 = peers through shared-memory
+   masks instead of match.any, bit 1 = multi-descriptor look-back, bit 2 =
+   per-warp choice between the masks and match.any, bit 3 = table mode (per-tile
+   offsets from histogram + scan kernels, no look-back) */
+static int radix_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("TMR_RADIX_VARIANT");
+    v = e ? atoi(e) & 15 : kDefaultRadixVariant;
+  }
+  return v;
+}
+
+template <bool kHasVals, int kBits>
+static void launch_pass(Ctx &ctx, i64 tiles, DBuf<u64> &keys, DBuf<u64> &keys_alt,
+                        DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int shift,
+                        int bits, const u32 *offs, u32 *ticket, u64 *lookback,
+                        const u32 *tile_excl, const u32 *chunk_excl) {
+  switch (radix_variant()) {
+#define TMR_PASS_CASE(V)                                                       \
+  case V:                                                                      \
+    launch_pass_v<kHasVals, kBits, V>(ctx, tiles, keys, keys_alt, vals,        \
+                                      vals_alt, n, shift, bits, offs, ticket,  \
+                                      lookback, tile_excl, chunk_excl);        \
+    break;
+    TMR_PASS_CASE(0)
+    TMR_PASS_CASE(2)
+    TMR_PASS_CASE(3)
+    TMR_PASS_CASE(7)
+    TMR_PASS_CASE(15)
+#undef TMR_PASS_CASE
+    default:
+      fprintf(stderr, "TMROctForest Error: unknown TMR_RADIX_VARIANT\n");
+      break;
+  }
+}
+
+template <int kBits>
+static void launch_tile_offsets(Ctx &ctx, const u64 *keys, i64 n, i64 tiles,
+                                int shift, int bits, u32 *thist, u32 *ctot,
+                                u32 *doff) {
+  cudaStream_t st = (cudaStream_t)ctx.stream;
+  const int chunks = (int)((tiles + kScanChunk - 1) / kScanChunk);
+  radix_tile_hist_kernel<kBits><<<(unsigned)tiles, 256, 0, st>>>(keys, n, shift,
+                                                               bits, thist);
+  radix_tile_scan_kernel<kBits><<<chunks, 1 << kBits, 0, st>>>(thist, tiles, ctot);
+  radix_chunk_scan_kernel<kBits><<<1, 1 << kBits, 0, st>>>(ctot, chunks, doff);
+}
+
+template <bool kHasVals>
+static void launch_pass_bits(Ctx &ctx, i64 tiles, DBuf<u64> &keys,
+                             DBuf<u64> &keys_alt, DBuf<u32> &vals,
+                             DBuf<u32> &vals_alt, i64 n, int shift, int bits,
+                             const u32 *offs, u32 *ticket, u64 *lookback,
+                             const u32 *tile_excl, const u32 *chunk_excl) {
+  if (bits > 8) {
+    launch_pass<kHasVals, 9>(ctx, tiles, keys, keys_alt, vals, vals_alt, n, shift,
+                             bits, offs, ticket, lookback, tile_excl, chunk_excl);
+  } else {
+    launch_pass<kHasVals, 8>(ctx, tiles, keys, keys_alt, vals, vals_alt, n, shift,
+                             bits, offs, ticket, lookback, tile_excl, chunk_excl);
+  }
 }
 
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
@@ -508,60 +826,83 @@ void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
     return;
   }
   const bool has_vals = vals.get() != NULL;
+  const bool table = (radix_variant() & 8) != 0;
   cudaStream_t st = (cudaStream_t)ctx.stream;
   const i64 tiles = (n + kSortTile - 1) / kSortTile;
+  const i64 chunks = (tiles + kScanChunk - 1) / kScanChunk;
   std::string hist_name = "radix_hist", pass_name = has_vals ? "radix_pass_pairs"
                                                              : "radix_pass_keys";
   if (tag) {
     hist_name += std::string("[") + tag + "]";
     pass_name += std::string("[") + tag + "]";
   }
-  /* scratch: [kMaxPasses*512 u32 hist][tickets][tiles*512 u64 descriptors] */
+  /* scratch, look-back mode: [kMaxPasses*512 u32 hist][tickets][tiles*512 u64
+     descriptors]; table mode: [512 u32 digit offsets][chunks*512 u32]
+     [tiles*512 u32] */
   const size_t hist_bytes = (size_t)kMaxPasses * kMaxRadix * sizeof(u32);
   const size_t ticket_bytes = 64;
-  const size_t look_bytes = (size_t)tiles * kMaxRadix * sizeof(u64);
+  const size_t look_bytes =
+      table ? (size_t)(tiles + chunks) * kMaxRadix * sizeof(u32)
+            : (size_t)tiles * kMaxRadix * sizeof(u64);
   unsigned char *scratch = static_cast<unsigned char *>(
       dev_alloc(ctx, hist_bytes + ticket_bytes + look_bytes));
   if (!scratch) return;
   u32 *ghist = reinterpret_cast<u32 *>(scratch);
   u32 *tickets = reinterpret_cast<u32 *>(scratch + hist_bytes);
   u64 *lookback = reinterpret_cast<u64 *>(scratch + hist_bytes + ticket_bytes);
+  u32 *ctot = reinterpret_cast<u32 *>(lookback);
+  u32 *thist = ctot + (size_t)chunks * kMaxRadix;
 
   int lo = bit_lo;
   while (lo < bit_hi) {
-    /* at most kMaxPasses passes are histogrammed per sweep of the keys */
+    /* at most kMaxPasses passes are planned per sweep */
     int hi = bit_hi;
     if (hi - lo > kMaxPasses * kMaxRadixBits) hi = lo + kMaxPasses * kMaxRadixBits;
     const PassPlan plan = make_plan(lo, hi);
-    dev_zero(ctx, scratch, hist_bytes + ticket_bytes);
-    prof_begin(ctx, hist_name.c_str());
-    radix_hist_kernel<<<grid_for(ctx, n, kHistThreads * 4, 8), kHistThreads, 0,
-                        st>>>(keys.get(), n, plan, ghist);
-    radix_scan_hist_kernel<<<plan.npass, kMaxRadix, 0, st>>>(ghist);
-    prof_end(ctx);
-    ctx.launch_count += 2;
+    if (!table) {
+      dev_zero(ctx, scratch, hist_bytes + ticket_bytes);
+      prof_begin(ctx, hist_name.c_str());
+      if (radix_variant() & 1) {
+        radix_hist_kernel<false><<<grid_for(ctx, n, kHistThreads * 4, 8),
+                                   kHistThreads, 0, st>>>(keys.get(), n, plan,
+                                                          ghist);
+      } else {
+        radix_hist_kernel<true><<<grid_for(ctx, n, kHistThreads * 4, 8),
+                                  kHistThreads, 0, st>>>(keys.get(), n, plan,
+                                                         ghist);
+      }
+      radix_scan_hist_kernel<<<plan.npass, kMaxRadix, 0, st>>>(ghist);
+      prof_end(ctx);
+      ctx.launch_count += 2;
+    }
     for (int p = 0; p < plan.npass; p++) {
       const int bits = plan.bits[p];
       const int radix = bits > 8 ? 512 : 256;
-      dev_zero(ctx, lookback, (size_t)tiles * radix * sizeof(u64));
-      prof_begin(ctx, pass_name.c_str());
       const u32 *offs = ghist + p * kMaxRadix;
-      if (has_vals) {
+      if (table) {
+        prof_begin(ctx, hist_name.c_str());
         if (bits > 8) {
-          launch_pass<true, 9>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
-                               plan.shift[p], bits, offs, tickets + p, lookback);
+          launch_tile_offsets<9>(ctx, keys.get(), n, tiles, plan.shift[p], bits,
+                                 thist, ctot, ghist);
         } else {
-          launch_pass<true, 8>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
-                               plan.shift[p], bits, offs, tickets + p, lookback);
+          launch_tile_offsets<8>(ctx, keys.get(), n, tiles, plan.shift[p], bits,
+                                 thist, ctot, ghist);
         }
+        prof_end(ctx);
+        ctx.launch_count += 3;
+        offs = ghist;
       } else {
-        if (bits > 8) {
-          launch_pass<false, 9>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
-                                plan.shift[p], bits, offs, tickets + p, lookback);
-        } else {
-          launch_pass<false, 8>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
-                                plan.shift[p], bits, offs, tickets + p, lookback);
-        }
+        dev_zero(ctx, lookback, (size_t)tiles * radix * sizeof(u64));
+      }
+      prof_begin(ctx, pass_name.c_str());
+      if (has_vals) {
+        launch_pass_bits<true>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
+                               plan.shift[p], bits, offs, tickets + p, lookback,
+                               thist, ctot);
+      } else {
+        launch_pass_bits<false>(ctx, tiles, keys, keys_alt, vals, vals_alt, n,
+                                plan.shift[p], bits, offs, tickets + p, lookback,
+                                thist, ctot);
       }
       prof_end(ctx);
       ctx.launch_count++;

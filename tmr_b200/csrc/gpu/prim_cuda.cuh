@@ -113,28 +113,40 @@ __global__ void __launch_bounds__(kScanThreads)
     if (w < warp) warp_off += s;
     tile_sum += s;
   }
-  /* publish the aggregate, then look back for the exclusive tile prefix */
-  if (threadIdx.x == 0) {
+  /* publish the aggregate, then warp 0 looks back for the exclusive tile
+     prefix, 32 predecessors per poll (lane l reads tile-1-l): a walk over m
+     unfinished tiles costs ~m/32 L2 round trips */
+  if (warp == 0) {
+    u64 excl = 0;
     if (tile == 0) {
-      st_relaxed_u64(&tile_state[0], kStatusPrefix | tile_sum);
-      s_tile_prefix = 0;
+      if (lane == 0) st_relaxed_u64(&tile_state[0], kStatusPrefix | tile_sum);
     } else {
-      st_relaxed_u64(&tile_state[tile], kStatusAgg | tile_sum);
-      u64 excl = 0;
+      if (lane == 0) st_relaxed_u64(&tile_state[tile], kStatusAgg | tile_sum);
       i64 p = (i64)tile - 1;
       while (true) {
-        u64 v = ld_relaxed_u64(&tile_state[p]);
+        const i64 q = p - lane;
+        /* positions before tile 0 read as "inclusive prefix 0" */
+        const u64 v = (q >= 0) ? ld_relaxed_u64(&tile_state[q]) : kStatusPrefix;
         const u64 st = v & kStatusMask;
-        if (st == 0) continue; /* predecessor not published yet */
-        excl += v & ~kStatusMask;
-        if (st == kStatusPrefix) break;
-        p--;
+        const unsigned ready = __ballot_sync(0xffffffffu, st != 0);
+        const unsigned pref = __ballot_sync(0xffffffffu, st == kStatusPrefix);
+        const int nready = (~ready == 0u) ? 32 : (__ffs(~ready) - 1);
+        const int fp = pref ? (__ffs(pref) - 1) : 32;
+        const int take = (fp < nready) ? fp + 1 : nready;
+        u64 c = (lane < take) ? (v & ~kStatusMask) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        excl += c;
+        if (fp < nready) break;
+        p -= take;
       }
-      st_relaxed_u64(&tile_state[tile], kStatusPrefix | (excl + tile_sum));
-      s_tile_prefix = excl;
+      if (lane == 0) {
+        st_relaxed_u64(&tile_state[tile], kStatusPrefix | (excl + tile_sum));
+      }
     }
-    if ((i64)(tile + 1) * kScanTile >= n) {
-      *total = s_tile_prefix + tile_sum;
+    if (lane == 0) {
+      s_tile_prefix = excl;
+      if ((i64)(tile + 1) * kScanTile >= n) *total = excl + tile_sum;
     }
   }
   __syncthreads();
