@@ -17,8 +17,10 @@
 
 #if defined(__CUDACC__)
 #define TMR_HD __host__ __device__ __forceinline__
+#define TMR_UNROLL _Pragma("unroll")
 #else
 #define TMR_HD inline
+#define TMR_UNROLL
 #endif
 
 /* Atomics used inside kernel bodies.  In the device pass they are hardware
@@ -511,6 +513,27 @@ struct KeyIndex {
       }
     }
     return (lo < (i64)table[p + 1] && a[lo] == key) ? lo : -1;
+  }
+};
+
+/* One bit per (level, tree, cell): set where a leaf of exactly that level
+   sits.  An exact-leaf probe (the 6 parent-level neighbour tests per element
+   of computeDepFacesAndEdges, reference src/TMROctForest.cpp:3619-3702) then
+   costs one L2-resident word read instead of a table read plus a binary
+   search with 64-bit compares (measured: 377 warp instructions per probe).
+   Levels 0..lmax are covered, lmax chosen so the map stays within a byte
+   budget; probes at deeper levels fall back to the key search. */
+struct LeafMap {
+  const u32 *bits; /* NULL = no map */
+  int lmax;
+  u64 word_off[kMaxLevel + 1];
+  TMR_HD bool covers(int level) const { return bits && level <= lmax; }
+  TMR_HD u64 word(i32 block, u64 cell, int level) const {
+    return word_off[level] + ((((u64)(u32)block << (3 * level)) + cell) >> 5);
+  }
+  TMR_HD bool test(i32 block, u64 cell, int level) const {
+    const u64 idx = ((u64)(u32)block << (3 * level)) + cell;
+    return (bits[word_off[level] + (idx >> 5)] >> (idx & 31)) & 1u;
   }
 };
 

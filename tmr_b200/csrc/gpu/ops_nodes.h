@@ -59,12 +59,32 @@ inline KeyIndex build_key_index(Ctx &ctx, const u64 *keys, i64 n, u64 key_limit,
   return ix;
 }
 
+/* leaf map over the levels that fit a 128 MB budget (see LeafMap) */
+inline LeafMap plan_leaf_map(int D, int nblocks, u64 *total_words) {
+  LeafMap map;
+  map.bits = NULL;
+  map.lmax = -1;
+  const u64 budget = 1ULL << 25; /* 32-bit words */
+  u64 words = 0;
+  for (int l = 0; l <= kMaxLevel; l++) map.word_off[l] = 0;
+  for (int l = 0; l < D; l++) {
+    const u64 w = ((((u64)nblocks << (3 * l)) + 31) >> 5) + 1;
+    if (words + w > budget) break;
+    map.word_off[l] = words;
+    words += w;
+    map.lmax = l;
+  }
+  *total_words = words;
+  return map;
+}
+
 struct ElemView {
   const u64 *keys;
   i64 n;
   KeyFmt fmt;
   ConnTables t;
   KeyIndex ix;
+  LeafMap map;
   /* multi-rank: probes that land in another rank's range become queries
      (key, owner, element*8+bit) answered by that rank -- a pull-style ghost
      exchange: only elements on the partition surface generate traffic */
@@ -77,8 +97,17 @@ struct ElemView {
   unsigned long long *fq_count;
   i64 fq_cap;
 
-  TMR_HD bool probe(i32 block, i32 x, i32 y, i32 z, int level, u64 code) const {
-    const u64 key = fmt.encode(block, x, y, z, level);
+  /* does this rank hold the leaf `key` (exact anchor and level)? */
+  TMR_HD bool local_leaf(u64 key) const {
+    const int level = (int)(key & 31);
+    if (map.covers(level)) {
+      const u64 pos = key >> 5;
+      const u64 m = fmt.D > 0 ? (pos & ((1ULL << (3 * fmt.D)) - 1)) : 0ULL;
+      return map.test((i32)(pos >> (3 * fmt.D)), m >> (3 * (fmt.D - level)), level);
+    }
+    return ix.find(keys, key) >= 0;
+  }
+  TMR_HD bool probe_key(u64 key, u64 code) const {
     if (multi) {
       const int o = om.owner(key >> 5);
       if (o != me) {
@@ -91,10 +120,13 @@ struct ElemView {
         return false;
       }
     }
-    return ix.find(keys, key) >= 0;
+    return local_leaf(key);
+  }
+  TMR_HD bool probe(i32 block, i32 x, i32 y, i32 z, int level, u64 code) const {
+    return probe_key(fmt.encode(block, x, y, z, level), code);
   }
   TMR_HD bool leaf_exists(i32 block, i32 x, i32 y, i32 z, int level) const {
-    return ix.find(keys, fmt.encode(block, x, y, z, level)) >= 0;
+    return local_leaf(fmt.encode(block, x, y, z, level));
   }
 
   /* is there a level-`level` leaf in another tree that is the image of the
@@ -159,59 +191,133 @@ TMR_HD void edge_dir(int e, int *dx, int *dy, int *dz) {
   }
 }
 
+/* set the map bit of every leaf whose level the map covers */
+struct LeafMapBuildFn {
+  const u64 *keys;
+  KeyFmt fmt;
+  LeafMap map;
+  u32 *bits;
+  TMR_HD void operator()(i64 i) const {
+    const u64 key = keys[i];
+    const int level = (int)(key & 31);
+    if (level > map.lmax) return;
+    const u64 pos = key >> 5;
+    const u64 m = fmt.D > 0 ? (pos & ((1ULL << (3 * fmt.D)) - 1)) : 0ULL;
+    const i32 block = (i32)(pos >> (3 * fmt.D));
+    const u64 cell = m >> (3 * (fmt.D - level));
+    const u64 idx = ((u64)(u32)block << (3 * level)) + cell;
+    TMR_ATOMIC_OR_I32(&bits[map.word_off[level] + (idx >> 5)], 1u << (idx & 31));
+  }
+};
+
 /* 6-bit hanging info of every element
-   (reference computeDepFacesAndEdges src/TMROctForest.cpp:3619-3702) */
+   (reference computeDepFacesAndEdges src/TMROctForest.cpp:3619-3702).
+
+   The parent-level neighbours of the element's PARENT across the 3 faces and 3
+   edges meeting at the element's corner are addressed in Morton space: the
+   parent's cell index is the element's Morton code shifted down, a step of one
+   cell along an axis is a dilated increment/decrement on that axis' bits
+   (x-major code: axis k of the child id sits at bit 2-k of every triple).  No
+   coordinates are decoded unless the step leaves the tree; only those probes
+   take the inter-tree path with its orientation transforms. */
 struct HangingFn {
   ElemView ev;
   int *info32; /* 32-bit accumulator per element (bits 0-5 info) */
+
+  TMR_HD bool cell_probe(i32 block, u64 cell, int pl, u64 code) const {
+    if (!ev.multi && ev.map.covers(pl)) return ev.map.test(block, cell, pl);
+    const int D = ev.fmt.D;
+    return ev.probe_key(((u64)(u32)block << (3 * D + 5)) |
+                            (cell << (3 * (D - pl) + 5)) | (u64)pl,
+                        code);
+  }
+
+  /* probes that leave the tree (boundary elements only) */
+  TMR_HD bool outside_face(int id, int k, i32 block, i32 px, i32 py, i32 pz,
+                                i32 hp, int pl, u64 code) const {
+    const int f = child_face(id, k);
+    const i32 d = (f & 1) ? hp : -hp;
+    return ev.across_face(f, block, px + (k == 0 ? d : 0), py + (k == 1 ? d : 0),
+                          pz + (k == 2 ? d : 0), pl, code);
+  }
+  TMR_HD bool outside_edge(int id, int k, i32 block, i32 px, i32 py, i32 pz,
+                                i32 hp, int pl, u64 code) const {
+    const int e = child_edge(id, k);
+    int dx, dy, dz;
+    edge_dir(e, &dx, &dy, &dz);
+    const i32 nx = px + dx * hp, ny = py + dy * hp, nz = pz + dz * hp;
+    const int ox = (nx < 0 || nx >= kHmax);
+    const int oy = (ny < 0 || ny >= kHmax);
+    const int oz = (nz < 0 || nz >= kHmax);
+    if (ox + oy + oz >= 2) return ev.across_edge(e, block, nx, ny, nz, pl, code);
+    const int f = ox * (nx < 0 ? 0 : 1) + oy * (ny < 0 ? 2 : 3) +
+                  oz * (nz < 0 ? 4 : 5);
+    return ev.across_face(f, block, nx, ny, nz, pl, code);
+  }
+
   TMR_HD void operator()(i64 i) const {
-    i32 block, x, y, z;
-    int level;
-    ev.fmt.decode(ev.keys[i], &block, &x, &y, &z, &level);
+    const u64 key = ev.keys[i];
+    const int level = (int)(key & 31);
     if (level == 0) {
       info32[i] = 0;
       return;
     }
-    const int id = child_id_of(x, y, z, level);
-    const i32 h = 1 << (kMaxLevel - level);
-    const i32 hp = 2 * h;
-    const i32 px = x & ~h, py = y & ~h, pz = z & ~h;
+    const int D = ev.fmt.D;
+    const u64 pos = key >> 5;
+    const u64 m = pos & ((1ULL << (3 * D)) - 1);
+    const i32 block = (i32)(pos >> (3 * D));
+    const int sh = 3 * (D - level);
+    const int md = (int)((m >> sh) & 7); /* x-major digit: 4x + 2y + z */
+    const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
     const int pl = level - 1;
-    int bits = 0;
+    const u64 mp = m >> (sh + 3); /* parent's cell index at level pl */
+    const u64 lmask = pl > 0 ? ((1ULL << (3 * pl)) - 1) : 0ULL;
+    u64 am[3], nc[3];
+    bool out[3];
+    TMR_UNROLL
     for (int k = 0; k < 3; k++) {
-      const int f = child_face(id, k);
-      const i32 d = (f & 1) ? hp : -hp;
-      const i32 nx = px + (k == 0 ? d : 0);
-      const i32 ny = py + (k == 1 ? d : 0);
-      const i32 nz = pz + (k == 2 ? d : 0);
-      const i32 c = (k == 0) ? nx : (k == 1 ? ny : nz);
-      bool hit;
-      const u64 code = ((u64)i << 3) | (u64)k;
-      if (c >= 0 && c < kHmax) {
-        hit = ev.probe(block, nx, ny, nz, pl, code);
+      am[k] = (0x1249249249249249ULL << (2 - k)) & lmask;
+      const u64 comp = mp & am[k];
+      if ((id >> k) & 1) {
+        out[k] = comp == am[k];
+        nc[k] = ((comp | ~am[k]) + 1) & am[k];
       } else {
-        hit = ev.across_face(f, block, nx, ny, nz, pl, code);
+        out[k] = comp == 0;
+        nc[k] = (comp - 1) & am[k];
+      }
+    }
+    /* coordinates only for probes that leave the tree */
+    i32 px = 0, py = 0, pz = 0, hp = 0;
+    if (out[0] || out[1] || out[2]) {
+      u32 ux, uy, uz;
+      unmorton3(mp, &ux, &uy, &uz);
+      const int s = kMaxLevel - pl;
+      px = (i32)(ux << s);
+      py = (i32)(uy << s);
+      pz = (i32)(uz << s);
+      hp = 1 << s;
+    }
+    int bits = 0;
+    TMR_UNROLL
+    for (int k = 0; k < 3; k++) {
+      const u64 code = ((u64)i << 3) | (u64)k;
+      bool hit;
+      if (!out[k]) {
+        hit = cell_probe(block, (mp & ~am[k]) | nc[k], pl, code);
+      } else {
+        hit = outside_face(id, k, block, px, py, pz, hp, pl, code);
       }
       if (hit) bits |= 1 << k;
     }
+    TMR_UNROLL
     for (int k = 0; k < 3; k++) {
-      const int e = child_edge(id, k);
-      int dx, dy, dz;
-      edge_dir(e, &dx, &dy, &dz);
-      const i32 nx = px + dx * hp, ny = py + dy * hp, nz = pz + dz * hp;
-      const int ox = (nx < 0 || nx >= kHmax);
-      const int oy = (ny < 0 || ny >= kHmax);
-      const int oz = (nz < 0 || nz >= kHmax);
-      bool hit;
+      const int a = (k == 0) ? 1 : 0, b = (k == 2) ? 1 : 2; /* the other axes */
       const u64 code = ((u64)i << 3) | (u64)(k + 3);
-      if (ox + oy + oz >= 2) {
-        hit = ev.across_edge(e, block, nx, ny, nz, pl, code);
-      } else if (ox + oy + oz == 1) {
-        const int f = ox * (nx < 0 ? 0 : 1) + oy * (ny < 0 ? 2 : 3) +
-                      oz * (nz < 0 ? 4 : 5);
-        hit = ev.across_face(f, block, nx, ny, nz, pl, code);
+      bool hit;
+      if (!out[a] && !out[b]) {
+        hit = cell_probe(block, (mp & ~(am[a] | am[b])) | nc[a] | nc[b], pl, code);
       } else {
-        hit = ev.probe(block, nx, ny, nz, pl, code);
+        hit = outside_edge(id, k, block, px, py, pz, hp, pl, code);
       }
       if (hit) bits |= 1 << (k + 3);
     }
@@ -691,8 +797,8 @@ struct DepWinnerFn {
   KeyFmt fmt;
   int order;
   const int *conn_local;
-  const unsigned char *dep_flag;
-  const u32 *dep_before;
+  const int *node_num; /* dependent node d is numbered -d-1: one gather tells
+                          both whether the node is dependent and which */
   u64 *win_edge;
   u64 *win_face;
   TMR_HD void operator()(i64 e) const {
@@ -709,21 +815,29 @@ struct DepWinnerFn {
     for (int ed = 0; ed < 12; ed++) {
       if (!(em & (1 << ed))) continue;
       for (int k = 0; k < order; k++) {
-        const int node = c[edge_node_offset(order, ed, k)];
-        if (dep_flag[node]) {
+        const int num = node_num[c[edge_node_offset(order, ed, k)]];
+        if (num < 0) {
           const u64 code = (((u64)e * 12 + ed) << 4) + (u64)k + 1;
-          TMR_ATOMIC_MAX_U64(&win_edge[dep_before[node]], code);
+          TMR_ATOMIC_MAX_U64(&win_edge[-num - 1], code);
         }
       }
     }
+    /* Face positions on the two element edges that lie on the parent's own
+       edges are skipped: decode_info put both edges into em, so a dependent
+       node there already has an edge winner from this element, and an edge
+       winner always takes precedence over a face winner (DepLenFn). */
+    const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
     for (int f = 0; f < 6; f++) {
       if (!(fm & (1 << f))) continue;
+      const int p_skip = (order - 1) * ((f < 2) ? by : bx);
+      const int q_skip = (order - 1) * ((f < 4) ? bz : by);
       for (int q = 0; q < order; q++) {
         for (int p = 0; p < order; p++) {
-          const int node = c[face_node_offset(order, f, p, q)];
-          if (dep_flag[node]) {
+          if (p == p_skip || q == q_skip) continue;
+          const int num = node_num[c[face_node_offset(order, f, p, q)]];
+          if (num < 0) {
             const u64 code = (((u64)e * 6 + f) << 8) + (u64)(p + q * order) + 1;
-            TMR_ATOMIC_MAX_U64(&win_face[dep_before[node]], code);
+            TMR_ATOMIC_MAX_U64(&win_face[-num - 1], code);
           }
         }
       }
@@ -1240,6 +1354,16 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     const KeyIndex elem_ix =
         build_key_index(ctx, f.keys.get(), E,
                         (u64)f.nblocks << (3 * f.fmt.D + 5), elem_index_store);
+    DBuf<u32> leaf_bits;
+    u64 map_words = 0;
+    LeafMap lmap = plan_leaf_map(f.fmt.D, f.nblocks, &map_words);
+    if (lmap.lmax >= 0) {
+      leaf_bits.alloc(ctx, (i64)map_words);
+      dev_zero(ctx, leaf_bits.get(), (size_t)map_words * sizeof(u32));
+      LeafMapBuildFn lb = {f.keys.get(), f.fmt, lmap, leaf_bits.get()};
+      launch(ctx, E, lb, "nodes_leaf_map");
+      lmap.bits = leaf_bits.get();
+    }
     DBuf<int> info32(ctx, E);
     DBuf<u64> fq_key, fq_code;
     DBuf<u32> fq_dest;
@@ -1254,7 +1378,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
         dev_zero(ctx, fq_count.get(), sizeof(unsigned long long));
       }
       ElemView ev = {f.keys.get(), E,           f.fmt,         f.tables,
-                     elem_ix,      om,          me,            comm ? 1 : 0,
+                     elem_ix,      lmap,        om,            me,
+                     comm ? 1 : 0,
                      fq_key.get(), fq_dest.get(), fq_code.get(), fq_count.get(),
                      cap};
       HangingFn hang = {ev, info32.get()};
@@ -1495,9 +1620,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     DBuf<u64> win_edge(ctx, Nd), win_face(ctx, Nd);
     dev_zero(ctx, win_edge.get(), (size_t)Nd * sizeof(u64));
     dev_zero(ctx, win_face.get(), (size_t)Nd * sizeof(u64));
-    DepWinnerFn win = {f.keys.get(),   f.info.get(),     f.fmt,
-                       order,          nd.conn.get(),    dep_flag.get(),
-                       dep_before.get(), win_edge.get(), win_face.get()};
+    DepWinnerFn win = {f.keys.get(),  f.info.get(),       f.fmt,
+                       order,         nd.conn.get(),      nd.node_num.get(),
+                       win_edge.get(), win_face.get()};
     launch(ctx, E, win, "nodes_dep_winner");
     DBuf<u32> off(ctx, Nd);
     DepLenFn len = {win_edge.get(), win_face.get(), order};
