@@ -711,7 +711,41 @@ struct ParentNodeFillFn {
 
 
 
-/* labelDependentNodes (reference :3711-3832) */
+/* Edge / face membership of element-local node slot (i,j,k), order n per
+   axis: which of the 12 element edges and 6 faces contain it, and where.
+   Edges 0-3 run along x (index = side_y + 2 side_z), 4-7 along y, 8-11 along
+   z; faces 0..5 = -x,+x,-y,+y,-z,+z with in-face axes as face_node_offset. */
+struct SlotGeom {
+  int ed[3], epos[3]; /* edge along axis a (or -1) and the position on it */
+  int fc[3], fp[3], fq[3]; /* face normal to axis a (or -1) and (p,q) on it */
+};
+TMR_HD SlotGeom slot_geom(int n, int i, int j, int k) {
+  SlotGeom g;
+  const int hi = n - 1;
+  const bool xi = (i == 0 || i == hi), yj = (j == 0 || j == hi),
+             zk = (k == 0 || k == hi);
+  const int sx = i ? 1 : 0, sy = j ? 1 : 0, sz = k ? 1 : 0;
+  g.ed[0] = (yj && zk) ? (sy + 2 * sz) : -1;
+  g.epos[0] = i;
+  g.ed[1] = (xi && zk) ? (4 + sx + 2 * sz) : -1;
+  g.epos[1] = j;
+  g.ed[2] = (xi && yj) ? (8 + sx + 2 * sy) : -1;
+  g.epos[2] = k;
+  g.fc[0] = xi ? sx : -1;
+  g.fp[0] = j;
+  g.fq[0] = k;
+  g.fc[1] = yj ? (2 + sy) : -1;
+  g.fp[1] = i;
+  g.fq[1] = k;
+  g.fc[2] = zk ? (4 + sz) : -1;
+  g.fp[2] = i;
+  g.fq[2] = j;
+  return g;
+}
+
+/* labelDependentNodes (reference :3711-3832), one pass over the element's
+   node slots.  kOrder = 2 or 3 unrolls the slot loop; 0 = run-time order. */
+template <int kOrder>
 struct DepLabelFn {
   const u64 *keys;
   const int16_t *info;
@@ -723,10 +757,11 @@ struct DepLabelFn {
   TMR_HD void operator()(i64 e) const {
     const int inf = info[e];
     if (!inf) return;
-    i32 block, x, y, z;
-    int level;
-    fmt.decode(keys[e], &block, &x, &y, &z, &level);
-    const int id = child_id_of(x, y, z, level);
+    const int n = kOrder ? kOrder : order;
+    const u64 key = keys[e];
+    const int level = (int)(key & 31);
+    const int md = level == 0 ? 0 : (int)((key >> (5 + 3 * (fmt.D - level))) & 7);
+    const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
     int fm, em;
     decode_info(id, inf, &fm, &em);
     for (int f = 0; f < 6; f++) {
@@ -734,30 +769,32 @@ struct DepLabelFn {
         for (int k = 0; k < 4; k++) em |= 1 << face_edge(f, k);
       }
     }
-    const int npe = order * order * order;
-    const int *c = conn_local + e * npe;
-    for (int ed = 0; ed < 12; ed++) {
-      if (!(em & (1 << ed))) continue;
-      const int bit = (id >> (ed >> 2)) & 1;
-      int start, end;
-      if (bit == 0) {
-        start = 1;
-        end = order;
-        if (order == 3 && !bernstein) end = order - 1;
-      } else {
-        start = 0;
-        end = order - 1;
-        if (order == 3 && !bernstein) start = 1;
-      }
-      for (int p = start; p < end; p++) {
-        dep_flag[c[edge_node_offset(order, ed, p)]] = 1;
-      }
-    }
-    for (int f = 0; f < 6; f++) {
-      if (!(fm & (1 << f))) continue;
-      for (int q = 1; q < order - 1; q++) {
-        for (int p = 1; p < order - 1; p++) {
-          dep_flag[c[face_node_offset(order, f, p, q)]] = 1;
+    /* dependent positions along an edge, by the child's side on that axis */
+    const bool trim = (n == 3 && !bernstein);
+    const int lo0 = 1, hi0 = trim ? n - 1 : n;     /* child on the low side */
+    const int lo1 = trim ? 1 : 0, hi1 = n - 1;     /* child on the high side */
+    const int *c = conn_local + e * (n * n * n);
+    TMR_UNROLL
+    for (int kk = 0; kk < n; kk++) {
+      TMR_UNROLL
+      for (int jj = 0; jj < n; jj++) {
+        TMR_UNROLL
+        for (int ii = 0; ii < n; ii++) {
+          const SlotGeom g = slot_geom(n, ii, jj, kk);
+          bool dep = false;
+          TMR_UNROLL
+          for (int a = 0; a < 3; a++) {
+            if (g.ed[a] >= 0 && (em & (1 << g.ed[a]))) {
+              const int bit = (id >> a) & 1;
+              const int p = g.epos[a];
+              dep = dep || (bit ? (p >= lo1 && p < hi1) : (p >= lo0 && p < hi0));
+            }
+            if (g.fc[a] >= 0 && (fm & (1 << g.fc[a]))) {
+              dep = dep || (g.fp[a] >= 1 && g.fp[a] < n - 1 && g.fq[a] >= 1 &&
+                            g.fq[a] < n - 1);
+            }
+          }
+          if (dep) dep_flag[c[ii + n * jj + n * n * kk]] = 1;
         }
       }
     }
@@ -790,7 +827,15 @@ struct NumberNodesFn {
 
 /* createDependentConn passes 1+2 (reference :5183-5270): who writes the
    stencil of each dependent node, and with which length.  Codes are
-   "1 + position in the reference's loop order" so that 0 means never. */
+   "1 + position in the reference's loop order" so that 0 means never; the
+   reference's last writer is the maximum code.  One pass over the element's
+   node slots: among the hanging edges (faces) containing a slot only the
+   highest-numbered one can be this element's maximum, so each slot issues at
+   most one edge and one face atomic.  Face positions on the two element edges
+   that lie on the parent's own edges are skipped: decode_info put both edges
+   into em, so a dependent node there has an edge winner from this element,
+   and an edge winner takes precedence over any face winner (DepLenFn). */
+template <int kOrder>
 struct DepWinnerFn {
   const u64 *keys;
   const int16_t *info;
@@ -804,39 +849,48 @@ struct DepWinnerFn {
   TMR_HD void operator()(i64 e) const {
     const int inf = info[e];
     if (!inf) return;
-    i32 block, x, y, z;
-    int level;
-    fmt.decode(keys[e], &block, &x, &y, &z, &level);
-    const int id = child_id_of(x, y, z, level);
+    const int n = kOrder ? kOrder : order;
+    const u64 key = keys[e];
+    const int level = (int)(key & 31);
+    const int md = level == 0 ? 0 : (int)((key >> (5 + 3 * (fmt.D - level))) & 7);
+    const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
     int fm, em;
     decode_info(id, inf, &fm, &em);
-    const int npe = order * order * order;
-    const int *c = conn_local + e * npe;
-    for (int ed = 0; ed < 12; ed++) {
-      if (!(em & (1 << ed))) continue;
-      for (int k = 0; k < order; k++) {
-        const int num = node_num[c[edge_node_offset(order, ed, k)]];
-        if (num < 0) {
-          const u64 code = (((u64)e * 12 + ed) << 4) + (u64)k + 1;
-          TMR_ATOMIC_MAX_U64(&win_edge[-num - 1], code);
-        }
-      }
-    }
-    /* Face positions on the two element edges that lie on the parent's own
-       edges are skipped: decode_info put both edges into em, so a dependent
-       node there already has an edge winner from this element, and an edge
-       winner always takes precedence over a face winner (DepLenFn). */
     const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
-    for (int f = 0; f < 6; f++) {
-      if (!(fm & (1 << f))) continue;
-      const int p_skip = (order - 1) * ((f < 2) ? by : bx);
-      const int q_skip = (order - 1) * ((f < 4) ? bz : by);
-      for (int q = 0; q < order; q++) {
-        for (int p = 0; p < order; p++) {
-          if (p == p_skip || q == q_skip) continue;
-          const int num = node_num[c[face_node_offset(order, f, p, q)]];
-          if (num < 0) {
-            const u64 code = (((u64)e * 6 + f) << 8) + (u64)(p + q * order) + 1;
+    const int *c = conn_local + e * (n * n * n);
+    TMR_UNROLL
+    for (int kk = 0; kk < n; kk++) {
+      TMR_UNROLL
+      for (int jj = 0; jj < n; jj++) {
+        TMR_UNROLL
+        for (int ii = 0; ii < n; ii++) {
+          const SlotGeom g = slot_geom(n, ii, jj, kk);
+          int best_ed = -1, best_k = 0, best_f = -1, best_pos = 0;
+          TMR_UNROLL
+          for (int a = 0; a < 3; a++) { /* ascending edge / face numbers */
+            if (g.ed[a] >= 0 && (em & (1 << g.ed[a]))) {
+              best_ed = g.ed[a];
+              best_k = g.epos[a];
+            }
+            if (g.fc[a] >= 0 && (fm & (1 << g.fc[a]))) {
+              const int f = g.fc[a];
+              const int p_skip = (n - 1) * ((f < 2) ? by : bx);
+              const int q_skip = (n - 1) * ((f < 4) ? bz : by);
+              if (g.fp[a] != p_skip && g.fq[a] != q_skip) {
+                best_f = f;
+                best_pos = g.fp[a] + g.fq[a] * n;
+              }
+            }
+          }
+          if (best_ed < 0 && best_f < 0) continue;
+          const int num = node_num[c[ii + n * jj + n * n * kk]];
+          if (num >= 0) continue;
+          if (best_ed >= 0) {
+            const u64 code = (((u64)e * 12 + best_ed) << 4) + (u64)best_k + 1;
+            TMR_ATOMIC_MAX_U64(&win_edge[-num - 1], code);
+          }
+          if (best_f >= 0) {
+            const u64 code = (((u64)e * 6 + best_f) << 8) + (u64)best_pos + 1;
             TMR_ATOMIC_MAX_U64(&win_face[-num - 1], code);
           }
         }
@@ -1563,9 +1617,19 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   /* 3. dependent labels and numbering */
   DBuf<unsigned char> dep_flag(ctx, Nn);
   dev_zero(ctx, dep_flag.get(), (size_t)Nn);
-  DepLabelFn lab = {f.keys.get(), f.info.get(), f.fmt,         order,
-                    0,            nd.conn.get(), dep_flag.get()};
-  launch(ctx, E, lab, "nodes_dep_label");
+  if (order == 2) {
+    DepLabelFn<2> lab = {f.keys.get(), f.info.get(), f.fmt,         order,
+                         0,            nd.conn.get(), dep_flag.get()};
+    launch(ctx, E, lab, "nodes_dep_label");
+  } else if (order == 3) {
+    DepLabelFn<3> lab = {f.keys.get(), f.info.get(), f.fmt,         order,
+                         0,            nd.conn.get(), dep_flag.get()};
+    launch(ctx, E, lab, "nodes_dep_label");
+  } else {
+    DepLabelFn<0> lab = {f.keys.get(), f.info.get(), f.fmt,         order,
+                         0,            nd.conn.get(), dep_flag.get()};
+    launch(ctx, E, lab, "nodes_dep_label");
+  }
   DBuf<u32> dep_before(ctx, Nn);
   DepFlagFn df = {dep_flag.get()};
   const i64 Nd = (i64)scan_counts(ctx, Nn, df, dep_before.get(), "nodes_dep_scan");
@@ -1620,10 +1684,22 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     DBuf<u64> win_edge(ctx, Nd), win_face(ctx, Nd);
     dev_zero(ctx, win_edge.get(), (size_t)Nd * sizeof(u64));
     dev_zero(ctx, win_face.get(), (size_t)Nd * sizeof(u64));
-    DepWinnerFn win = {f.keys.get(),  f.info.get(),       f.fmt,
-                       order,         nd.conn.get(),      nd.node_num.get(),
-                       win_edge.get(), win_face.get()};
-    launch(ctx, E, win, "nodes_dep_winner");
+    if (order == 2) {
+      DepWinnerFn<2> win = {f.keys.get(),   f.info.get(),  f.fmt,
+                            order,          nd.conn.get(), nd.node_num.get(),
+                            win_edge.get(), win_face.get()};
+      launch(ctx, E, win, "nodes_dep_winner");
+    } else if (order == 3) {
+      DepWinnerFn<3> win = {f.keys.get(),   f.info.get(),  f.fmt,
+                            order,          nd.conn.get(), nd.node_num.get(),
+                            win_edge.get(), win_face.get()};
+      launch(ctx, E, win, "nodes_dep_winner");
+    } else {
+      DepWinnerFn<0> win = {f.keys.get(),   f.info.get(),  f.fmt,
+                            order,          nd.conn.get(), nd.node_num.get(),
+                            win_edge.get(), win_face.get()};
+      launch(ctx, E, win, "nodes_dep_winner");
+    }
     DBuf<u32> off(ctx, Nd);
     DepLenFn len = {win_edge.get(), win_face.get(), order};
     const u64 nnz = scan_counts(ctx, Nd, len, off.get(), "nodes_dep_len_scan");
