@@ -21,6 +21,20 @@ void launch(Ctx &ctx, i64 n, F f, const char *) {
   ctx.launch_count++;
 }
 
+struct DirectSink {
+  u64 *p;
+  void operator()(u64 v) { *p++ = v; }
+};
+
+template <int kMaxPer, class F>
+void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64, F f, u64 *out, const char *) {
+  for (i64 i = 0; i < n; i++) {
+    DirectSink sink = {out + off[i]};
+    f(i, sink);
+  }
+  ctx.launch_count++;
+}
+
 template <class F>
 u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *) {
   u64 run = 0;

@@ -450,31 +450,77 @@ struct NodeEmit {
                     : ((u64)e * (u64)(order * order * order) + (u64)code);
   }
 
+  /* spread node coordinates of the element along one axis (axis bit a of each
+     Morton triple: 2 = x, 1 = y, 0 = z), already shifted into node-key
+     position; false if the element touches the tree boundary on this axis */
+  template <int kOrder>
+  TMR_HD bool axis_nodes(u64 mc, int a, int level, u64 *out) const {
+    const int order = kOrder ? kOrder : this->order;
+    const int D = fmt.D;
+    const int sh = 3 * (D - level);
+    const int up = 3 * (nfmt.Dn - D);
+    const u64 am = 0x1249249249249249ULL << a;
+    const u64 lvl = (level > 0 ? ((1ULL << (3 * level)) - 1) : 0ULL) & am;
+    const u64 c = mc & am;
+    /* one node step = 2^(Dn-level)/(order-1) units of depth Dn */
+    const int stepbit = sh + up - (order == 3 ? 3 : 0) + a;
+    u64 v = c << up;
+    out[0] = v << 3;
+    TMR_UNROLL
+    for (int i = 1; i < order; i++) {
+      v = ((v | ~am) + (1ULL << stepbit)) & am;
+      out[i] = v << 3;
+    }
+    return c != 0 && ((mc >> sh) & lvl) != lvl;
+  }
+
   template <class Emit>
   TMR_HD void run(i64 e, Emit &emit) const {
+    /* create_nodes admits orders 2 and 3 only (kMaxOrder) */
+    if (order == 2) {
+      run_order<2>(e, emit);
+    } else {
+      run_order<3>(e, emit);
+    }
+  }
+  /* kOrder = 2 or 3 unrolls the node loops */
+  template <int kOrder, class Emit>
+  TMR_HD void run_order(i64 e, Emit &emit) const {
+    const int order = kOrder ? kOrder : this->order;
     int m = 0;
     const bool fam = families && in_family(e, &m);
     /* sibling bits in x-major order: m = 4*xbit + 2*ybit + zbit */
     const int bx = (m >> 2) & 1, by = (m >> 1) & 1, bz = m & 1;
-    i32 block, x, y, z;
-    int level;
-    fmt.decode(keys[e], &block, &x, &y, &z, &level);
-    const i32 h = 1 << (kMaxLevel - level);
+    /* Interior elements (no node on a tree boundary) never leave Morton
+       space: the per-axis components of the element's code ARE the spread
+       node coordinates, a step of h/(order-1) along an axis is a dilated
+       increment at bit 3(D-level) of that axis (the same bit for order 2 at
+       depth D and order 3 at depth D+1), and the node format's trailing flag
+       bit is one more shift by 3.  Only boundary elements decode coordinates
+       and go through transform_node. */
+    const u64 key0 = keys[e];
+    const int level = (int)(key0 & 31);
+    const int D = fmt.D;
+    const u64 mc = D > 0 ? ((key0 >> 5) & ((1ULL << (3 * D)) - 1)) : 0ULL;
+    i32 block = (i32)(key0 >> (3 * D + 5));
     const int np = order;
-    const i32 step = h / (order - 1);
-    const bool interior = x > 0 && y > 0 && z > 0 && x + h < kHmax &&
-                          y + h < kHmax && z + h < kHmax;
+    bool interior = level > 0;
     u64 sx[kMaxOrder], sy[kMaxOrder], sz[kMaxOrder];
-    if (interior) {
-      for (int a = 0; a < np; a++) {
-        sx[a] = spread3(nfmt.squeeze(x + a * step)) << 2;
-        sy[a] = spread3(nfmt.squeeze(y + a * step)) << 1;
-        sz[a] = spread3(nfmt.squeeze(z + a * step));
-      }
+    interior = axis_nodes<kOrder>(mc, 2, level, sx) && interior;
+    interior = axis_nodes<kOrder>(mc, 1, level, sy) && interior;
+    interior = axis_nodes<kOrder>(mc, 0, level, sz) && interior;
+    i32 x = 0, y = 0, z = 0, step = 0;
+    if (!interior) {
+      int lv;
+      fmt.decode(key0, &block, &x, &y, &z, &lv);
+      step = (1 << (kMaxLevel - level)) / (order - 1);
     }
     const u64 hi = (u64)(u32)block << (3 * (nfmt.Dn + 1));
+    TMR_UNROLL
     for (int kk = 0; kk < np; kk++) {
+      TMR_UNROLL
       for (int jj = 0; jj < np; jj++) {
+        TMR_UNROLL
         for (int ii = 0; ii < np; ii++) {
           if (fam && ((ii && !bx) || (jj && !by) || (kk && !bz))) continue;
           u64 key;
@@ -520,20 +566,21 @@ struct NodeEmitFillFn {
   int pshift;
   TMR_HD void operator()(i64 e, u32 o) const {
     CandStore s = {out_keys + o, out_vals ? out_vals + o : (u32 *)0, pshift};
-    g.run(e, s);
+    g.template run_order<2>(e, s); /* family emission is order 2 only */
   }
 };
 
 /* fixed order^3 candidates per element: offsets are e*npe, no scan needed */
+template <int kOrder>
 struct NodeEmitDenseFn {
   NodeEmit g;
   u64 *out_keys;
   u32 *out_vals;
   int pshift;
   TMR_HD void operator()(i64 e) const {
-    const i64 o = e * (i64)(g.order * g.order * g.order);
+    const i64 o = e * (i64)(kOrder * kOrder * kOrder);
     CandStore s = {out_keys + o, out_vals ? out_vals + o : (u32 *)0, pshift};
-    g.run(e, s);
+    g.template run_order<kOrder>(e, s);
   }
 };
 
@@ -588,7 +635,10 @@ struct NodeScatterFn {
     }
     /* shared node of a complete family: fan out to every sibling that has it
        as a corner.  e is the representative sibling; its child digit gives
-       the family's first element. */
+       the family's first element.  (Measured alternative: one store into a
+       per-family 3x3x3 table plus an expansion kernel -- scatter 5.8 -> 4.5 ms
+       but the expansion cost 5.8 ms with one thread per family; an
+       out-of-place expansion moves as many bytes as it saves.) */
     const int m = g.digit_of(g.keys[e]);
     const i64 e0 = e - m;
     const int pi = ((m >> 2) & 1) + (cc & 1);       /* node position 0..2 */
@@ -841,9 +891,8 @@ struct DepWinnerFn {
   const int16_t *info;
   KeyFmt fmt;
   int order;
-  const int *conn_local;
-  const int *node_num; /* dependent node d is numbered -d-1: one gather tells
-                          both whether the node is dependent and which */
+  const int *conn; /* node NUMBERS (already remapped): dependent node d is
+                      -d-1, so no gather is needed to classify a slot */
   u64 *win_edge;
   u64 *win_face;
   TMR_HD void operator()(i64 e) const {
@@ -857,7 +906,7 @@ struct DepWinnerFn {
     int fm, em;
     decode_info(id, inf, &fm, &em);
     const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
-    const int *c = conn_local + e * (n * n * n);
+    const int *c = conn + e * (n * n * n);
     TMR_UNROLL
     for (int kk = 0; kk < n; kk++) {
       TMR_UNROLL
@@ -883,7 +932,7 @@ struct DepWinnerFn {
             }
           }
           if (best_ed < 0 && best_f < 0) continue;
-          const int num = node_num[c[ii + n * jj + n * n * kk]];
+          const int num = c[ii + n * jj + n * n * kk];
           if (num >= 0) continue;
           if (best_ed >= 0) {
             const u64 code = (((u64)e * 12 + best_ed) << 4) + (u64)best_k + 1;
@@ -942,8 +991,9 @@ struct DepFillFn {
   KeyIndex node_ix;
   /* order 2 shortcut: in a complete family the parent's corner c is corner c
      of sibling c, so the parent's edge/face nodes are read from the siblings'
-     connectivity instead of being searched by key */
-  const int *conn_local;
+     connectivity (node numbers, already remapped) instead of being searched
+     by key */
+  const int *conn;
   NodeEmit fam;
 
   TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, i64) const {
@@ -959,7 +1009,7 @@ struct DepFillFn {
   }
   TMR_HD int parent_corner_node(i64 e0, int c) const {
     const int m = 4 * (c & 1) + 2 * ((c >> 1) & 1) + (c >> 2);
-    return node_num[conn_local[(e0 + m) * 8 + c]];
+    return conn[(e0 + m) * 8 + c];
   }
 
   TMR_HD void operator()(i64 d) const {
@@ -1107,6 +1157,23 @@ inline int sorted_node_numbers(Forest &f, int *h_out) {
   return check_errors(ctx, "sorted_node_numbers");
 }
 
+
+/* packed family emission through expand_u64: key | payload << pshift */
+template <class Sink>
+struct PackedEmit {
+  Sink &s;
+  int pshift;
+  TMR_HD void operator()(u64 key, u64 payload) { s(key | (payload << pshift)); }
+};
+struct NodeEmitPackedFn {
+  NodeEmit g;
+  int pshift;
+  template <class Sink>
+  TMR_HD void operator()(i64 e, Sink &sink) const {
+    PackedEmit<Sink> pe = {sink, pshift};
+    g.template run_order<2>(e, pe); /* family emission is order 2 only */
+  }
+};
 
 struct NodeEmitPlaceFn {
   NodeEmitFillFn fill;
@@ -1518,13 +1585,21 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       cv.alloc(ctx, ntot);
       cv_alt.alloc(ctx, ntot);
     }
-    if (emit_gen.families) {
+    if (emit_gen.families && packed) {
+      NodeEmitPackedFn ef = {emit_gen, nbits};
+      expand_u64<8>(ctx, E, eoff.get(), (u64)nemit, ef, ck.get(), "nodes_candidates");
+    } else if (emit_gen.families) {
       NodeEmitFillFn ef = {emit_gen, ck.get(), cv.get(), nbits};
       NodeEmitPlaceFn ep = {ef, eoff.get()};
       launch(ctx, E, ep, "nodes_candidates");
     } else {
-      NodeEmitDenseFn ed = {emit_gen, ck.get(), cv.get(), nbits};
-      launch(ctx, E, ed, "nodes_candidates");
+      if (order == 2) {
+        NodeEmitDenseFn<2> ed = {emit_gen, ck.get(), cv.get(), nbits};
+        launch(ctx, E, ed, "nodes_candidates");
+      } else {
+        NodeEmitDenseFn<3> ed = {emit_gen, ck.get(), cv.get(), nbits};
+        launch(ctx, E, ed, "nodes_candidates");
+      }
     }
     if (nextra) {
       ParentNodeFillFn pf = {pg, ck.get() + nemit,
@@ -1547,6 +1622,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
                         no_slot,  ck_alt.get(), nd.conn.get(), created.get(),
                         emit_gen};
     Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
+
     nd.node_keys.alloc(ctx, Nn);
     copy_d2d(ctx, nd.node_keys.get(), ck_alt.get(), (size_t)Nn * sizeof(u64));
   }
@@ -1678,26 +1754,29 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   }
   trace_mark(ctx, "nodes: label+number");
 
-  /* 4. dependent-node CSR */
+  /* 4. local -> global numbers in the connectivity; the dependent-node CSR
+     below reads numbers straight from it */
+  ConnRemapInPlaceFn rm = {nd.node_num.get(), nd.conn.get()};
+  launch(ctx, nc, rm, "nodes_conn_remap");
+  trace_mark(ctx, "nodes: conn remap");
+
+  /* 5. dependent-node CSR */
   nd.dep_ptr.alloc(ctx, Nd + 1);
   if (Nd > 0) {
     DBuf<u64> win_edge(ctx, Nd), win_face(ctx, Nd);
     dev_zero(ctx, win_edge.get(), (size_t)Nd * sizeof(u64));
     dev_zero(ctx, win_face.get(), (size_t)Nd * sizeof(u64));
     if (order == 2) {
-      DepWinnerFn<2> win = {f.keys.get(),   f.info.get(),  f.fmt,
-                            order,          nd.conn.get(), nd.node_num.get(),
-                            win_edge.get(), win_face.get()};
+      DepWinnerFn<2> win = {f.keys.get(), f.info.get(),   f.fmt,         order,
+                            nd.conn.get(), win_edge.get(), win_face.get()};
       launch(ctx, E, win, "nodes_dep_winner");
     } else if (order == 3) {
-      DepWinnerFn<3> win = {f.keys.get(),   f.info.get(),  f.fmt,
-                            order,          nd.conn.get(), nd.node_num.get(),
-                            win_edge.get(), win_face.get()};
+      DepWinnerFn<3> win = {f.keys.get(), f.info.get(),   f.fmt,         order,
+                            nd.conn.get(), win_edge.get(), win_face.get()};
       launch(ctx, E, win, "nodes_dep_winner");
     } else {
-      DepWinnerFn<0> win = {f.keys.get(),   f.info.get(),  f.fmt,
-                            order,          nd.conn.get(), nd.node_num.get(),
-                            win_edge.get(), win_face.get()};
+      DepWinnerFn<0> win = {f.keys.get(), f.info.get(),   f.fmt,         order,
+                            nd.conn.get(), win_edge.get(), win_face.get()};
       launch(ctx, E, win, "nodes_dep_winner");
     }
     DBuf<u32> off(ctx, Nd);
@@ -1725,7 +1804,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.win_edge = win_edge.get();
     fill.win_face = win_face.get();
     fill.dep_node = dep_node.get();
-    fill.conn_local = nd.conn.get();
+    fill.conn = nd.conn.get();
     {
       NodeEmit fg = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order, order == 2 ? 1 : 0};
       fill.fam = fg;
@@ -1740,11 +1819,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   }
   trace_mark(ctx, "nodes: dep CSR");
 
-  /* 5. local -> global numbers in the connectivity */
-  ConnRemapInPlaceFn rm = {nd.node_num.get(), nd.conn.get()};
-  launch(ctx, nc, rm, "nodes_conn_remap");
   nd.valid = true;
-  trace_mark(ctx, "nodes: conn remap");
   return check_errors(ctx, "create_nodes");
 }
 
