@@ -526,13 +526,19 @@ struct KeyIndex {
 struct LeafMap {
   const u32 *bits; /* NULL = no map */
   int lmax;
+  i32 block0, nblk; /* trees [block0, block0 + nblk): this rank's slice */
   u64 word_off[kMaxLevel + 1];
   TMR_HD bool covers(int level) const { return bits && level <= lmax; }
-  TMR_HD u64 word(i32 block, u64 cell, int level) const {
-    return word_off[level] + ((((u64)(u32)block << (3 * level)) + cell) >> 5);
+  /* leaves of other trees are not on this rank */
+  TMR_HD bool in_range(i32 block) const {
+    return block >= block0 && block < block0 + nblk;
+  }
+  TMR_HD u64 index(i32 block, u64 cell, int level) const {
+    return ((u64)(u32)(block - block0) << (3 * level)) + cell;
   }
   TMR_HD bool test(i32 block, u64 cell, int level) const {
-    const u64 idx = ((u64)(u32)block << (3 * level)) + cell;
+    if (!in_range(block)) return false;
+    const u64 idx = index(block, cell, level);
     return (bits[word_off[level] + (idx >> 5)] >> (idx & 31)) & 1u;
   }
 };

@@ -60,10 +60,12 @@ inline KeyIndex build_key_index(Ctx &ctx, const u64 *keys, i64 n, u64 key_limit,
 }
 
 /* leaf map over the levels that fit a 128 MB budget (see LeafMap) */
-inline LeafMap plan_leaf_map(int D, int nblocks, u64 *total_words) {
+inline LeafMap plan_leaf_map(int D, i32 block0, int nblocks, u64 *total_words) {
   LeafMap map;
   map.bits = NULL;
   map.lmax = -1;
+  map.block0 = block0;
+  map.nblk = nblocks;
   const u64 budget = 1ULL << 25; /* 32-bit words */
   u64 words = 0;
   for (int l = 0; l <= kMaxLevel; l++) map.word_off[l] = 0;
@@ -107,19 +109,20 @@ struct ElemView {
     }
     return ix.find(keys, key) >= 0;
   }
-  TMR_HD bool probe_key(u64 key, u64 code) const {
-    if (multi) {
-      const int o = om.owner(key >> 5);
-      if (o != me) {
-        const unsigned long long slot = fetch_add_u64(fq_count, 1ULL);
-        if ((i64)slot < fq_cap) {
-          fq_key[slot] = key;
-          fq_dest[slot] = (u32)o;
-          fq_code[slot] = code;
-        }
-        return false;
-      }
+  /* multi-rank: a leaf that would live on another rank becomes a query */
+  TMR_HD bool ask_owner(u64 key, u64 code) const {
+    const int o = om.owner(key >> 5);
+    if (o == me) return false;
+    const unsigned long long slot = fetch_add_u64(fq_count, 1ULL);
+    if ((i64)slot < fq_cap) {
+      fq_key[slot] = key;
+      fq_dest[slot] = (u32)o;
+      fq_code[slot] = code;
     }
+    return true;
+  }
+  TMR_HD bool probe_key(u64 key, u64 code) const {
+    if (multi && ask_owner(key, code)) return false;
     return local_leaf(key);
   }
   TMR_HD bool probe(i32 block, i32 x, i32 y, i32 z, int level, u64 code) const {
@@ -204,8 +207,7 @@ struct LeafMapBuildFn {
     const u64 pos = key >> 5;
     const u64 m = fmt.D > 0 ? (pos & ((1ULL << (3 * fmt.D)) - 1)) : 0ULL;
     const i32 block = (i32)(pos >> (3 * fmt.D));
-    const u64 cell = m >> (3 * (fmt.D - level));
-    const u64 idx = ((u64)(u32)block << (3 * level)) + cell;
+    const u64 idx = map.index(block, m >> (3 * (fmt.D - level)), level);
     TMR_ATOMIC_OR_I32(&bits[map.word_off[level] + (idx >> 5)], 1u << (idx & 31));
   }
 };
@@ -225,11 +227,16 @@ struct HangingFn {
   int *info32; /* 32-bit accumulator per element (bits 0-5 info) */
 
   TMR_HD bool cell_probe(i32 block, u64 cell, int pl, u64 code) const {
-    if (!ev.multi && ev.map.covers(pl)) return ev.map.test(block, cell, pl);
     const int D = ev.fmt.D;
-    return ev.probe_key(((u64)(u32)block << (3 * D + 5)) |
-                            (cell << (3 * (D - pl) + 5)) | (u64)pl,
-                        code);
+    const u64 key = ((u64)(u32)block << (3 * D + 5)) |
+                    (cell << (3 * (D - pl) + 5)) | (u64)pl;
+    if (ev.map.covers(pl)) {
+      /* a leaf found here settles it; only a miss can be another rank's */
+      if (ev.map.test(block, cell, pl)) return true;
+      if (ev.multi) ev.ask_owner(key, code);
+      return false;
+    }
+    return ev.probe_key(key, code);
   }
 
   /* probes that leave the tree (boundary elements only) */
@@ -405,7 +412,6 @@ TMR_HD int face_node_offset(int order, int f, int p, int q) {
      * everything else: order^3 candidates per element.
    The payload of a candidate is (element << 4) | code with code = corner
    (0..7, or slot at order 3 via the wide encoding) and bit 3 = "shared". */
-static const u32 kSharedBit = 8;
 
 struct NodeEmit {
   const u64 *keys;
@@ -415,6 +421,13 @@ struct NodeEmit {
   ConnTables t;
   int order;
   int families; /* use family emission (order 2 only) */
+  /* multi-rank: order-preserving dense ids of the trees this rank's node keys
+     can name (NULL = tree index as is); shortens the sort key so that the
+     conn-slot payload still fits beside it */
+  const u32 *dense;
+  TMR_HD u64 tree_id(i32 block) const {
+    return dense ? (u64)dense[block] : (u64)(u32)block;
+  }
 
   TMR_HD int digit_of(u64 k) const {
     const int L = (int)(k & 31);
@@ -446,7 +459,7 @@ struct NodeEmit {
 
   /* payload encoding */
   TMR_HD u64 payload(i64 e, int code) const {
-    return families ? (((u64)e << 4) | (u64)code)
+    return families ? (((u64)e << 3) | (u64)code)
                     : ((u64)e * (u64)(order * order * order) + (u64)code);
   }
 
@@ -515,7 +528,7 @@ struct NodeEmit {
       fmt.decode(key0, &block, &x, &y, &z, &lv);
       step = (1 << (kMaxLevel - level)) / (order - 1);
     }
-    const u64 hi = (u64)(u32)block << (3 * (nfmt.Dn + 1));
+    const u64 hi = tree_id(block) << (3 * (nfmt.Dn + 1));
     TMR_UNROLL
     for (int kk = 0; kk < np; kk++) {
       TMR_UNROLL
@@ -530,10 +543,11 @@ struct NodeEmit {
             i32 b = block, nx = x + ii * step, ny = y + jj * step,
                 nz = z + kk * step;
             transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-            key = nfmt.encode(b, nx, ny, nz);
+            key = nfmt.encode((i32)tree_id(b), nx, ny, nz);
           }
-          const int slot = ii + np * jj + np * np * kk;
-          emit(key, payload(e, fam ? (slot | (int)kSharedBit) : slot));
+          /* whether the slot stands for the whole family is re-derived from
+             the keys at scatter time (in_family), not carried in the payload */
+          emit(key, payload(e, ii + np * jj + np * np * kk));
         }
       }
     }
@@ -613,12 +627,18 @@ struct NodeScatterFn {
   int *conn_local;
   unsigned char *created; /* optional: node is created by a local element */
   NodeEmit g;             /* payload decoding */
+  const u32 *undense;     /* dense tree id -> tree index (NULL = identity) */
+  int mbits;              /* Morton bits of a node key */
   /* heads_before = exclusive scan of run heads */
   TMR_HD void operator()(i64 i, u32 heads_before) const {
     const u64 k = keys[i] & mask;
     const bool head = (i == 0 || k != (keys[i - 1] & mask));
     const u32 run = heads_before + (head ? 1u : 0u) - 1u;
-    if (head) node_keys[run] = k;
+    if (head) {
+      node_keys[run] = undense ? (((u64)undense[k >> mbits] << mbits) |
+                                  (k & ((1ULL << mbits) - 1)))
+                               : k;
+    }
     const u64 p = vals ? (u64)vals[i] : (keys[i] >> pshift);
     if (p == no_slot) return;
     if (created) created[run] = 1;
@@ -626,10 +646,10 @@ struct NodeScatterFn {
       conn_local[p] = (int)run;
       return;
     }
-    const i64 e = (i64)(p >> 4);
-    const int code = (int)(p & 15);
-    const int cc = code & 7;
-    if (!(code & (int)kSharedBit)) {
+    const i64 e = (i64)(p >> 3);
+    const int cc = (int)(p & 7);
+    int m;
+    if (!g.in_family(e, &m)) {
       conn_local[e * 8 + cc] = (int)run;
       return;
     }
@@ -639,7 +659,6 @@ struct NodeScatterFn {
        per-family 3x3x3 table plus an expansion kernel -- scatter 5.8 -> 4.5 ms
        but the expansion cost 5.8 ms with one thread per family; an
        out-of-place expansion moves as many bytes as it saves.) */
-    const int m = g.digit_of(g.keys[e]);
     const i64 e0 = e - m;
     const int pi = ((m >> 2) & 1) + (cc & 1);       /* node position 0..2 */
     const int pj = ((m >> 1) & 1) + ((cc >> 1) & 1);
@@ -668,6 +687,10 @@ struct ParentNodeGen {
   NodeFmt nfmt;
   ConnTables t;
   int order;
+  const u32 *dense; /* as NodeEmit::dense */
+  TMR_HD i32 tree_id(i32 block) const {
+    return dense ? (i32)dense[block] : block;
+  }
   template <class Emit>
   TMR_HD void run(i64 e, Emit &emit) const {
     /* a hanging edge/face whose coarse neighbour is a LOCAL leaf needs nothing:
@@ -698,7 +721,7 @@ struct ParentNodeGen {
           nx = px + ta; ny = py + tb; nz = pz + ii * step;
         }
         transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-        emit(nfmt.encode(b, nx, ny, nz));
+        emit(nfmt.encode(tree_id(b), nx, ny, nz));
       }
     }
     for (int f = 0; f < 6; f++) {
@@ -715,10 +738,46 @@ struct ParentNodeGen {
             nx = px + p * step; ny = py + q * step; nz = pz + nn;
           }
           transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-          emit(nfmt.encode(b, nx, ny, nz));
+          emit(nfmt.encode(tree_id(b), nx, ny, nz));
         }
       }
     }
+  }
+};
+
+/* trees whose index can appear in this rank's node keys: the trees of its own
+   elements and the owner trees of their corners, edges and faces (the targets
+   of transform_node) */
+struct MarkTreesFn {
+  const u64 *keys;
+  i64 E;
+  KeyFmt fmt;
+  ConnTables t;
+  u32 *used;
+  TMR_HD void operator()(i64 b) const {
+    const i64 first = (i64)(keys[0] >> (3 * fmt.D + 5));
+    const i64 last = (i64)(keys[E - 1] >> (3 * fmt.D + 5));
+    if (b < first || b > last) return;
+    used[b] = 1;
+    for (int c = 0; c < 8; c++) used[t.node_block_owners[t.block_conn[8 * b + c]]] = 1;
+    for (int e = 0; e < 12; e++) {
+      used[t.edge_block_owners[t.block_edge_conn[12 * b + e]]] = 1;
+    }
+    for (int f = 0; f < 6; f++) {
+      used[t.face_block_owners[t.block_face_conn[6 * b + f]]] = 1;
+    }
+  }
+};
+struct UsedFlagFn {
+  const u32 *used;
+  TMR_HD u32 operator()(i64 b) const { return used[b]; }
+};
+struct UndenseFn {
+  const u32 *used;
+  const u32 *dense;
+  u32 *undense;
+  TMR_HD void operator()(i64 b) const {
+    if (used[b]) undense[dense[b]] = (u32)b;
   }
 };
 
@@ -1477,7 +1536,17 @@ inline int create_nodes(Forest &f, int order, int interp_type,
                         (u64)f.nblocks << (3 * f.fmt.D + 5), elem_index_store);
     DBuf<u32> leaf_bits;
     u64 map_words = 0;
-    LeafMap lmap = plan_leaf_map(f.fmt.D, f.nblocks, &map_words);
+    /* the map spans the trees of this rank's own slice only, so its size per
+       GPU stays constant under weak scaling */
+    i32 map_b0 = 0, map_nb = f.nblocks;
+    if (comm && E > 0) {
+      u64 k_first = 0, k_last = 0;
+      copy_d2h(ctx, &k_first, f.keys.get(), sizeof(u64));
+      copy_d2h(ctx, &k_last, f.keys.get() + (E - 1), sizeof(u64));
+      map_b0 = (i32)(k_first >> (3 * f.fmt.D + 5));
+      map_nb = (i32)(k_last >> (3 * f.fmt.D + 5)) - map_b0 + 1;
+    }
+    LeafMap lmap = plan_leaf_map(f.fmt.D, map_b0, map_nb, &map_words);
     if (lmap.lmax >= 0) {
       leaf_bits.alloc(ctx, (i64)map_words);
       dev_zero(ctx, leaf_bits.get(), (size_t)map_words * sizeof(u32));
@@ -1541,15 +1610,36 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     /* multi-rank: also the parent edge/face nodes of hanging elements */
     i64 nextra = 0;
     DBuf<u32> poff;
-    ParentNodeGen pg = {f.keys.get(), fmask.get(), f.fmt, nd.nfmt, f.tables, order};
+    /* multi-rank: dense, order-preserving ids for the trees this rank's node
+       keys can name, so that key + payload fit one 64-bit word at any tree
+       count */
+    DBuf<u32> tree_used, tree_dense, tree_undense;
+    int sort_bbits = nd.nfmt.bbits;
+    if (comm && E > 0) {
+      tree_used.alloc(ctx, f.nblocks);
+      tree_dense.alloc(ctx, f.nblocks);
+      dev_zero(ctx, tree_used.get(), (size_t)f.nblocks * sizeof(u32));
+      MarkTreesFn mk = {f.keys.get(), E, f.fmt, f.tables, tree_used.get()};
+      launch(ctx, f.nblocks, mk, "nodes_mark_trees");
+      UsedFlagFn uf = {tree_used.get()};
+      const i64 nused = (i64)scan_counts(ctx, f.nblocks, uf, tree_dense.get(),
+                                         "nodes_dense_trees");
+      tree_undense.alloc(ctx, nused);
+      UndenseFn un = {tree_used.get(), tree_dense.get(), tree_undense.get()};
+      launch(ctx, f.nblocks, un, "nodes_undense_trees");
+      sort_bbits = bits_for((int)nused);
+    }
+    ParentNodeGen pg = {f.keys.get(), fmask.get(), f.fmt,           nd.nfmt,
+                        f.tables,     order,       tree_dense.get()};
     if (comm) {
       poff.alloc(ctx, E);
       ParentNodeCountFn pc = {pg};
       nextra = (i64)scan_counts(ctx, E, pc, poff.get(), "nodes_parent_count");
     }
     /* candidate emission plan */
-    NodeEmit emit_gen = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order,
-                         order == 2 ? 1 : 0};
+    NodeEmit emit_gen = {f.keys.get(), E,     f.fmt,
+                         nd.nfmt,      f.tables, order,
+                         order == 2 ? 1 : 0,     tree_dense.get()};
     i64 nemit = nc;
     DBuf<u32> eoff;
     if (emit_gen.families) {
@@ -1566,9 +1656,10 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     /* packed mode: when node-key bits + payload bits fit in 64, the payload
        (conn slot) rides in the key's high bits and the sort is keys-only:
        16 B instead of 24 B of HBM traffic per candidate per pass */
-    const int nbits = nd.nfmt.total_bits();
+    const int mbits = 3 * (nd.nfmt.Dn + 1);
+    const int nbits = sort_bbits + mbits;
     const u64 max_payload =
-        emit_gen.families ? (((u64)E << 4) | 15ULL) : (u64)nc;
+        emit_gen.families ? (((u64)E << 3) | 7ULL) : (u64)nc;
     int pbits = 1;
     while ((1ULL << pbits) <= max_payload + 1) pbits++;
     const bool packed = nbits + pbits <= 64;
@@ -1620,7 +1711,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     RunHeadMaskedFn rh = {ck.get(), kmask};
     NodeScatterFn sc = {ck.get(), cv.get(),     kmask,         nbits,
                         no_slot,  ck_alt.get(), nd.conn.get(), created.get(),
-                        emit_gen};
+                        emit_gen, tree_undense.get(), mbits};
     Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
 
     nd.node_keys.alloc(ctx, Nn);

@@ -15,7 +15,12 @@ namespace tmrgpu {
 struct OwnerMap {
   const u64 *pos; /* device, R entries, positions of owners[] at depth Dp */
   int R;
+  /* this rank's own slice [my_lo, my_hi), held by value: the common answer
+     "mine" costs two compares and no memory access */
+  int me;
+  u64 my_lo, my_hi;
   TMR_HD int owner(u64 p) const {
+    if (p >= my_lo && p < my_hi) return me;
     int r = 0;
     while (r < R - 1 && pos[r + 1] <= p) r++;
     return r;
@@ -43,7 +48,10 @@ inline OwnerMap make_owner_map(Forest &f, int Dp, DBuf<u64> &store) {
   owner_positions(f, Dp, h);
   store.alloc(*f.ctx, (i64)h.size());
   copy_h2d(*f.ctx, store.get(), h.data(), h.size() * sizeof(u64));
-  OwnerMap m = {store.get(), (int)h.size()};
+  const int R = (int)h.size();
+  const int me = (f.ctx->comm && R > 1) ? f.ctx->comm->rank : 0;
+  OwnerMap m = {store.get(), R, me, me > 0 ? h[me] : 0ULL,
+                me + 1 < R ? h[me + 1] : ~0ULL};
   return m;
 }
 
