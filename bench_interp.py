@@ -92,6 +92,10 @@ def main():
     ap.add_argument("--pct", type=int, default=30)
     ap.add_argument("--cpu-level", type=int, default=3)
     ap.add_argument("--cpu-passes", type=int, default=2)
+    ap.add_argument("--profile-out", default=None,
+                    help="per-kernel CUDA-event times (ms) of the whole hierarchy build go here")
+    ap.add_argument("--no-api", action="store_true",
+                    help="skip the per-row addInterp hand-off timing (device CSR only)")
     args = ap.parse_args()
     import torch
 
@@ -133,7 +137,20 @@ def main():
                                  ctypes.byref(a), ctypes.byref(b))
 
     hierarchy(lib, 2, 2, args.pct, sync, dev_flags)  # warm-up (allocator, kernels)
+    if args.profile_out:
+        lib.tmrgpu_profile_enable.argtypes = [P, ctypes.c_int]
+        lib.tmrgpu_profile_reset.argtypes = [P]
+        lib.tmrgpu_profile_json.argtypes = [P, ctypes.c_char_p, ctypes.c_int]
+        lib.tmrgpu_profile_reset(ctx)
+        lib.tmrgpu_profile_enable(ctx, 1)
     gpu = hierarchy(lib, args.level, args.passes, args.pct, sync, dev_flags, dev_interp)
+    if args.profile_out:
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.tmrgpu_profile_json(ctx, buf, len(buf))
+        lib.tmrgpu_profile_enable(ctx, 0)
+        prof = json.loads(buf.value.decode())
+        with open(args.profile_out, "w") as fh:
+            json.dump(dict(sorted(prof.items(), key=lambda kv: -kv[1]["ms"])), fh, indent=1)
     result = {"workload": "C3 hierarchy: 8 trees, createTrees(%d), %d passes pct %d, balance(1)"
                           % (args.level, args.passes, args.pct), "b200": gpu}
     from oracle import ref_loader

@@ -363,17 +363,36 @@ struct InterpLocateRecvFn {
   }
 };
 
+/* longest possible row: every coarse node of the element a dependent node
+   with a full face stencil, corder^3 * corder^2 (reference :6637) */
+template <int kCOrder>
+struct RowCap {
+  static const int value = (kCOrder == 2) ? 32 : kMaxRowEntries;
+};
+
+/* row lengths, one thread per row (a plain launch: the build is far too heavy
+   to run inside the scan kernel, where each thread would do 8 of them) */
+template <int kCOrder>
 struct InterpCountFn {
   InterpRow r;
   RowRequests q;
-  TMR_HD u32 operator()(i64 row) const {
-    if (q.t[row] < 0) return 0;
-    int idx[kMaxRowEntries];
-    double w[kMaxRowEntries];
-    return (u32)r.build(q.fkey[row], q.j[row], q.t[row], idx, w);
+  u32 *count;
+  TMR_HD void operator()(i64 row) const {
+    if (q.t[row] < 0) {
+      count[row] = 0;
+      return;
+    }
+    int idx[RowCap<kCOrder>::value];
+    double w[RowCap<kCOrder>::value];
+    count[row] = (u32)r.build(q.fkey[row], q.j[row], q.t[row], idx, w);
   }
 };
+struct StoredCountFn {
+  const u32 *count;
+  TMR_HD u32 operator()(i64 i) const { return count[i]; }
+};
 
+template <int kCOrder>
 struct InterpFillFn {
   InterpRow r;
   RowRequests q;
@@ -381,8 +400,8 @@ struct InterpFillFn {
   double *vals;
   TMR_HD void operator()(i64 row, u32 o) const {
     if (q.t[row] < 0) return;
-    int idx[kMaxRowEntries];
-    double w[kMaxRowEntries];
+    int idx[RowCap<kCOrder>::value];
+    double w[RowCap<kCOrder>::value];
     const int n = r.build(q.fkey[row], q.j[row], q.t[row], idx, w);
     for (int k = 0; k < n; k++) {
       cols[o + k] = idx[k];
@@ -401,8 +420,9 @@ struct RowPtrFn {
   }
 };
 
+template <int kCOrder>
 struct InterpFillPlaceFn {
-  InterpFillFn fill;
+  InterpFillFn<kCOrder> fill;
   const u32 *off;
   TMR_HD void operator()(i64 row) const { fill(row, off[row]); }
 };
@@ -609,18 +629,30 @@ inline int create_interp(Forest &fine, Forest &coarse) {
     return check_errors(ctx, "create_interp");
   }
   RowRequests q = {q_fkey.get(), q_j.get(), q_t.get()};
-  DBuf<u32> off(ctx, nrows);
-  InterpCountFn cf = {r, q};
-  const u64 nnz = scan_counts(ctx, nrows, cf, off.get(), "interp_row_count");
+  DBuf<u32> off(ctx, nrows), cnt(ctx, nrows);
+  if (r.corder == 2) {
+    InterpCountFn<2> cf = {r, q, cnt.get()};
+    launch(ctx, nrows, cf, "interp_row_count");
+  } else {
+    InterpCountFn<3> cf = {r, q, cnt.get()};
+    launch(ctx, nrows, cf, "interp_row_count");
+  }
+  StoredCountFn sc = {cnt.get()};
+  const u64 nnz = scan_counts(ctx, nrows, sc, off.get(), "interp_row_offsets");
+  cnt.reset();
   I.rowp.alloc(ctx, nrows + 1);
   RowPtrFn rp = {off.get(), nrows, (u32)nnz, I.rowp.get()};
   launch(ctx, nrows + 1, rp, "interp_row_ptr");
   I.cols.alloc(ctx, (i64)nnz);
   I.vals.alloc(ctx, (i64)nnz);
-  InterpFillFn ffn = {r, q, I.cols.get(), I.vals.get()};
-  {
-    /* offsets are already known: replay the fill through them */
-    InterpFillPlaceFn pl = {ffn, off.get()};
+  /* offsets are known: replay the build and store */
+  if (r.corder == 2) {
+    InterpFillFn<2> ffn = {r, q, I.cols.get(), I.vals.get()};
+    InterpFillPlaceFn<2> pl = {ffn, off.get()};
+    launch(ctx, nrows, pl, "interp_row_fill");
+  } else {
+    InterpFillFn<3> ffn = {r, q, I.cols.get(), I.vals.get()};
+    InterpFillPlaceFn<3> pl = {ffn, off.get()};
     launch(ctx, nrows, pl, "interp_row_fill");
   }
   I.rows.swap(q_num);
