@@ -216,6 +216,8 @@ def main():
     ap.add_argument("--passes", type=int, default=FULL["passes"],
                     help="refinement passes of the recipe (4 = the named ~86M config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     ap.add_argument("--profile-out", default=None,
                     help="write the per-kernel CUDA-event times of the timed region (ms per step) here")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
@@ -368,6 +370,8 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     ev0.record(stream)
     last = None
     for _ in range(args.steps):
@@ -375,6 +379,8 @@ def main():
         last = step_device()
     ev1.record(stream)
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = lib.tmrgpu_launch_count(ctx)
@@ -449,6 +455,7 @@ def main():
         alg = {"radix_pass_pairs[nodes]": 2 * 12 * n_cand,
                "radix_pass_keys[nodes]": 2 * 8 * n_cand,
                "radix_pass_keys[leaves]": 2 * 8 * e_final,
+               "radix_hist[nodes]": 8 * n_cand,
                "nodes_candidates": 8 * sizes[0] + 8 * n_cand,
                "nodes_unique_scatter_conn": 8 * n_cand + 4 * n_pairs + 8 * sizes[1],
                "nodes_dep_fill": 12 * sizes[4] + 16 * sizes[2],

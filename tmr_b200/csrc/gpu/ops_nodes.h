@@ -226,17 +226,13 @@ struct HangingFn {
   ElemView ev;
   int *info32; /* 32-bit accumulator per element (bits 0-5 info) */
 
+  /* exact-leaf probe of a level-pl cell of this tree at levels the map does
+     not cover */
   TMR_HD bool cell_probe(i32 block, u64 cell, int pl, u64 code) const {
     const int D = ev.fmt.D;
-    const u64 key = ((u64)(u32)block << (3 * D + 5)) |
-                    (cell << (3 * (D - pl) + 5)) | (u64)pl;
-    if (ev.map.covers(pl)) {
-      /* a leaf found here settles it; only a miss can be another rank's */
-      if (ev.map.test(block, cell, pl)) return true;
-      if (ev.multi) ev.ask_owner(key, code);
-      return false;
-    }
-    return ev.probe_key(key, code);
+    return ev.probe_key(((u64)(u32)block << (3 * D + 5)) |
+                            (cell << (3 * (D - pl) + 5)) | (u64)pl,
+                        code);
   }
 
   /* probes that leave the tree (boundary elements only) */
@@ -304,29 +300,60 @@ struct HangingFn {
       pz = (i32)(uz << s);
       hp = 1 << s;
     }
-    int bits = 0;
-    TMR_UNROLL
-    for (int k = 0; k < 3; k++) {
-      const u64 code = ((u64)i << 3) | (u64)k;
-      bool hit;
-      if (!out[k]) {
-        hit = cell_probe(block, (mp & ~am[k]) | nc[k], pl, code);
-      } else {
-        hit = outside_face(id, k, block, px, py, pz, hp, pl, code);
-      }
-      if (hit) bits |= 1 << k;
-    }
+    /* the 6 neighbour cells: faces k = 0..2, then edges parallel to axis k */
+    u64 cell[6];
+    bool inside[6];
     TMR_UNROLL
     for (int k = 0; k < 3; k++) {
       const int a = (k == 0) ? 1 : 0, b = (k == 2) ? 1 : 2; /* the other axes */
-      const u64 code = ((u64)i << 3) | (u64)(k + 3);
-      bool hit;
-      if (!out[a] && !out[b]) {
-        hit = cell_probe(block, (mp & ~(am[a] | am[b])) | nc[a] | nc[b], pl, code);
-      } else {
-        hit = outside_edge(id, k, block, px, py, pz, hp, pl, code);
+      cell[k] = (mp & ~am[k]) | nc[k];
+      inside[k] = !out[k];
+      cell[k + 3] = (mp & ~(am[a] | am[b])) | nc[a] | nc[b];
+      inside[k + 3] = !out[a] && !out[b];
+    }
+    int bits = 0;
+    if (ev.map.covers(pl)) {
+      /* all map words are requested before any is tested: six independent
+         L2 reads in flight per thread instead of a chain of probe-and-branch */
+      u32 word[6];
+      TMR_UNROLL
+      for (int q = 0; q < 6; q++) {
+        const u64 idx = ev.map.index(block, cell[q], pl);
+        word[q] = inside[q] ? ev.map.bits[ev.map.word_off[pl] + (idx >> 5)] : 0u;
       }
-      if (hit) bits |= 1 << (k + 3);
+      TMR_UNROLL
+      for (int q = 0; q < 6; q++) {
+        if (!inside[q]) continue;
+        const u64 idx = ev.map.index(block, cell[q], pl);
+        if ((word[q] >> (idx & 31)) & 1u) {
+          bits |= 1 << q;
+        } else if (ev.multi) {
+          /* only a miss can be another rank's leaf */
+          ev.ask_owner(((u64)(u32)block << (3 * D + 5)) |
+                           (cell[q] << (3 * (D - pl) + 5)) | (u64)pl,
+                       ((u64)i << 3) | (u64)q);
+        }
+      }
+    } else {
+      TMR_UNROLL
+      for (int q = 0; q < 6; q++) {
+        if (inside[q] && cell_probe(block, cell[q], pl, ((u64)i << 3) | (u64)q)) {
+          bits |= 1 << q;
+        }
+      }
+    }
+    /* probes that leave the tree (boundary elements only) */
+    TMR_UNROLL
+    for (int k = 0; k < 3; k++) {
+      if (!inside[k] &&
+          outside_face(id, k, block, px, py, pz, hp, pl, ((u64)i << 3) | (u64)k)) {
+        bits |= 1 << k;
+      }
+      if (!inside[k + 3] &&
+          outside_edge(id, k, block, px, py, pz, hp, pl,
+                       ((u64)i << 3) | (u64)(k + 3))) {
+        bits |= 1 << (k + 3);
+      }
     }
     info32[i] = bits;
   }

@@ -588,7 +588,11 @@ static size_t sort_smem_bytes(bool has_vals, int radix) {
 }
 
 /* spread `total` key bits over the fewest passes of <= 9 bits, as evenly as
-   possible, never below 8 bits unless the key is shorter */
+   possible, never below 8 bits unless the key is shorter; the wider digits go
+   LAST (most significant): Morton-ordered input makes the high digits nearly
+   constant within a tile, which is where a 512-bin pass is cheap (measured:
+   a 9-bit pass over the lowest node-key bits took 2.65 ms against 1.55 ms for
+   an 8-bit pass) */
 static PassPlan make_plan(int bit_lo, int bit_hi) {
   PassPlan pl;
   const int total = bit_hi - bit_lo;
@@ -598,7 +602,7 @@ static PassPlan make_plan(int bit_lo, int bit_hi) {
   int at = bit_lo;
   for (int p = 0; p < npass; p++) {
     const int left = bit_hi - at;
-    const int b = (left + (npass - p) - 1) / (npass - p);
+    const int b = left / (npass - p);
     pl.shift[p] = at;
     pl.bits[p] = b;
     at += b;
