@@ -51,6 +51,32 @@ def test_refine_balance_nodes(case, impl, ref_lib):
                             case[0])
 
 
+@pytest.mark.parametrize("conn_name", ["box7", "connector15"])
+def test_bernstein_order2(conn_name, impl, ref_lib):
+    """TMR_BERNSTEIN_POINTS at order 2 (reference eval_bernstein_weights /
+    bernstein_shape_functions, src/TMRInterpolation.h:164-183,309-322):
+    nodes, dependent weights and the prolongation against the oracle."""
+    conn = util.CONNS[conn_name]()
+    res = []
+    for lib in (ref_lib, impl):
+        f = util.build_forest(lib, conn, 1, 3, 30, 1, 2, interp=2)
+        assert f.getInterpType() == 2
+        nodes = util.node_results(f)
+        coarse = f.coarsen()
+        coarse.balance(1)
+        res.append((nodes, f.createInterpolation(coarse)))
+    util.assert_nodes_equal(res[0][0], res[1][0], "bernstein order 2")
+    util.assert_interp_equal(res[0][1], res[1][1], "bernstein order 2 interp")
+
+
+def test_bernstein_order3_refused(impl, capfd):
+    """Order-3 Bernstein points need edge/face/block node labels: the CUDA path
+    says so instead of returning Lagrange data."""
+    f = util.build_forest(impl, util.single_conn(), 1, 1, 30, 0, 3, interp=2)
+    f.createNodes()
+    assert "TMROctForest Error" in capfd.readouterr().err
+
+
 def test_connectivity_tables(impl, ref_lib):
     """setConnectivity derives identical edge/face numbering, inverse maps,
     orientation ids (reference src/TMROctForest.cpp:558-1143)."""

@@ -1492,10 +1492,17 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   const int me = comm ? comm->rank : 0;
   NodeData &nd = f.nodes;
   if (nd.valid) return 0; /* reference :4071-4075 */
-  if (order < 2 || order > kMaxOrder || (interp_type == 2)) {
+  /* Bernstein points (type 2) at order 2: same knots (-1, 1), node labels and
+     label ranges as the Lagrange case, and eval_bernstein_weights(2, u) /
+     bernstein_shape_functions(2, u) = {(1-u)/2, (1+u)/2} are the linear
+     Lagrange functions evaluated at dyadic u -- bit-identical results
+     (reference src/TMRInterpolation.h:164-183,309-322, :5364-5374).  Order-3
+     Bernstein needs edge/face/block node labels (initLabel :6798-6811). */
+  if (order < 2 || order > kMaxOrder || (interp_type == 2 && order > 2)) {
     fprintf(stderr,
             "TMROctForest Error: the CUDA createNodes() supports mesh order 2 "
-            "and 3 with Lagrange interpolation (order %d, type %d requested)\n",
+            "and 3 with Lagrange interpolation and order 2 with Bernstein "
+            "points (order %d, type %d requested)\n",
             order, interp_type);
     return 1;
   }
