@@ -19,33 +19,37 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util  # noqa: E402
 from oracle import ref_loader  # noqa: E402
 
-# name, conn, level, passes, pct, corner, order
+# name, conn, level, passes, pct, corner, order, interpolation type
+# (1 = Gauss-Lobatto, 2 = Bernstein points)
 CASES = [
-    ("single_l2_p3_c0_o2", "single", 2, 3, 30, 0, 2),
-    ("box7_l2_p2_c1_o2", "box7", 2, 2, 30, 1, 2),
-    ("box7_l1_p2_c1_o3", "box7", 1, 2, 30, 1, 3),
-    ("connector15_l1_p3_c0_o2", "connector15", 1, 3, 30, 0, 2),
-    ("butterfly2_l1_p2_c1_o2", "butterfly2", 1, 2, 30, 1, 2),
+    ("single_l2_p3_c0_o2", "single", 2, 3, 30, 0, 2, 1),
+    ("box7_l2_p2_c1_o2", "box7", 2, 2, 30, 1, 2, 1),
+    ("box7_l1_p2_c1_o3", "box7", 1, 2, 30, 1, 3, 1),
+    ("connector15_l1_p3_c0_o2", "connector15", 1, 3, 30, 0, 2, 1),
+    ("butterfly2_l1_p2_c1_o2", "butterfly2", 1, 2, 30, 1, 2, 1),
+    ("box7_l1_p2_c1_o3_bernstein", "box7", 1, 2, 30, 1, 3, 2),
 ]
 
 
 def main():
     lib = ref_loader.load()
-    for name, conn_name, level, passes, pct, corner, order in CASES:
+    for name, conn_name, level, passes, pct, corner, order, interp in CASES:
         conn = util.CONNS[conn_name]()
         rec = []
-        f = util.build_forest(lib, conn, level, passes, pct, corner, order, record=rec)
+        f = util.build_forest(lib, conn, level, passes, pct, corner, order,
+                              interp=interp, record=rec)
         res = util.node_results(f)
         coarse = f.coarsen() if order == 2 else f.duplicate()
         if order == 2:
             coarse.balance(1)
         else:
-            coarse.setMeshOrder(2)
+            coarse.setMeshOrder(2, interp)
         vec = f.createInterpolation(coarse)
         rows, rowp, cols, vals = vec.get()
         out = {
             "block_conn": conn,
             "params": np.array([level, passes, pct, corner, order]),
+            "interp_type": np.array(interp),
             "counts": np.array([len(r[1]) for r in rec]),
             "checksums": np.array([util.checksum(r[1]) for r in rec], dtype=np.uint64),
             "checksum": np.uint64(util.checksum(res["octants"])),

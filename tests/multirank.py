@@ -42,12 +42,12 @@ def run_thread_ranks(lib, nranks, body, is_reference):
 
 
 def adapt_body(conn, level, passes, pct, corner, order, repartition=True, seed=2024,
-               with_interp=False):
+               with_interp=False, interp=1):
     """createTrees -> repartition -> passes x {refine, balance, repartition}
     -> createNodes; returns (per-stage octant arrays, node results)."""
 
     def body(lib, rank):
-        f = OctForest(order=order, lib=lib)
+        f = OctForest(order=order, interp=interp, lib=lib)
         f.setConnectivity(conn)
         f.createTrees(level)
         if repartition:
@@ -66,7 +66,7 @@ def adapt_body(conn, level, passes, pct, corner, order, repartition=True, seed=2
             # TopOptUtils-style coarse level (reference tmr/TopOptUtils.py:79-99)
             if order > 2:
                 coarse = f.duplicate()
-                coarse.setMeshOrder(order - 1)
+                coarse.setMeshOrder(order - 1, interp)
             else:
                 coarse = f.coarsen()
                 coarse.balance(1)

@@ -28,9 +28,10 @@ def lib(request):
 def test_golden_case(path, lib):
     g = np.load(path)
     level, passes, pct, corner, order = [int(v) for v in g["params"]]
+    interp = int(g["interp_type"]) if "interp_type" in g.files else 1
     rec = []
     f = util.build_forest(lib, g["block_conn"], level, passes, pct, corner, order,
-                          record=rec)
+                          interp=interp, record=rec)
     assert [len(r[1]) for r in rec] == list(g["counts"])
     assert [util.checksum(r[1]) for r in rec] == [int(c) for c in g["checksums"]]
     res = util.node_results(f)
@@ -44,7 +45,7 @@ def test_golden_case(path, lib):
     if order == 2:
         coarse.balance(1)
     else:
-        coarse.setMeshOrder(2)
+        coarse.setMeshOrder(2, interp)
     rows, rowp, cols, vals = f.createInterpolation(coarse).get()
     assert np.array_equal(rows, g["interp_rows"])
     assert np.array_equal(rowp, g["interp_rowp"])

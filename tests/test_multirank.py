@@ -34,6 +34,18 @@ def test_multirank_interpolation(order, ranks, mode, emu_lib, ref_lib):
     assert sum(len(x[1]["interp"]) for x in b) > 0
 
 
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_multirank_bernstein_order3(ranks, emu_lib, ref_lib):
+    """Labelled node keys (order-3 Bernstein points) through the multi-rank
+    node ownership, external numbering and remote interpolation rows."""
+    conn = util.box_conn()
+    body = multirank.adapt_body(conn, 1, 2, 30, 1, 3, True, with_interp="repartitioned",
+                                interp=2)
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_rank_results(a, b, "bernstein3_r%d" % ranks)
+
+
 def test_public_distribute_octants(emu_lib, ref_lib):
     """distributeOctants / sendOctants as external callers use them (reference
     src/topology/TMR_TACSTopoCreator.cpp:166-217): route a sorted octant list

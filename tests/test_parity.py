@@ -69,12 +69,27 @@ def test_bernstein_order2(conn_name, impl, ref_lib):
     util.assert_interp_equal(res[0][1], res[1][1], "bernstein order 2 interp")
 
 
-def test_bernstein_order3_refused(impl, capfd):
-    """Order-3 Bernstein points need edge/face/block node labels: the CUDA path
-    says so instead of returning Lagrange data."""
-    f = util.build_forest(impl, util.single_conn(), 1, 1, 30, 0, 3, interp=2)
-    f.createNodes()
-    assert "TMROctForest Error" in capfd.readouterr().err
+@pytest.mark.parametrize("conn_name", ["single", "box7", "connector15"])
+def test_bernstein_order3(conn_name, impl, ref_lib):
+    """Order-3 Bernstein points: corner / edge / face / block node labels
+    (reference initLabel src/TMROctForest.cpp:6798-6811), untrimmed dependent
+    ranges (:3755-3761), subdivision weights (:5364-5374, :5453-5473) and the
+    order 3 -> 2 and 2 -> 2 prolongations (:6434-6500)."""
+    conn = util.CONNS[conn_name]()
+    res = []
+    for lib in (ref_lib, impl):
+        f = util.build_forest(lib, conn, 1, 2, 30, 1, 3, interp=2)
+        nodes = util.node_results(f)
+        low = f.duplicate()
+        low.setMeshOrder(2, 2)
+        v32 = f.createInterpolation(low)
+        coarse = low.coarsen()
+        coarse.balance(1)
+        v22 = low.createInterpolation(coarse)
+        res.append((nodes, v32, v22))
+    util.assert_nodes_equal(res[0][0], res[1][0], "bernstein order 3")
+    util.assert_interp_equal(res[0][1], res[1][1], "bernstein 3 -> 2")
+    util.assert_interp_equal(res[0][2], res[1][2], "bernstein 2 -> 2")
 
 
 def test_connectivity_tables(impl, ref_lib):

@@ -193,16 +193,32 @@ TMR_HD u64 rekey(u64 key, int D_old, int D_new) {
 struct NodeFmt {
   int Dn;
   int bbits;
-  TMR_HD int total_bits() const { return bbits + 3 * (Dn + 1); }
+  /* label bits below the Morton code: 0, or 2 when nodes at one position can
+     differ by label (order-3 Bernstein points: node / edge / face / block
+     labels, reference initLabel src/TMROctForest.cpp:6798-6811).  The
+     reference's compareNode orders by position, then label
+     (src/TMROctant.cpp:245-274). */
+  int lbits;
+  TMR_HD int pos_bits() const { return 3 * (Dn + 1) + lbits; }
+  TMR_HD int total_bits() const { return bbits + pos_bits(); }
   TMR_HD u32 squeeze(i32 c) const {
     if (c >= kHmax - 1) return (1u << (Dn + 1)) - 1u;
     return ((u32)c >> (kMaxLevel - Dn)) << 1;
   }
-  TMR_HD u64 encode(i32 block, i32 x, i32 y, i32 z) const {
+  TMR_HD u64 encode(i32 block, i32 x, i32 y, i32 z, int label = 0) const {
     u64 m = morton3(squeeze(x), squeeze(y), squeeze(z));
-    return ((u64)(u32)block << (3 * (Dn + 1))) | m;
+    return ((((u64)(u32)block << (3 * (Dn + 1))) | m) << lbits) | (u64)label;
   }
 };
+
+/* label of element-local node slot (i,j,k) of an order-3 element when labels
+   are in use: 0 corner, 1 edge midpoint, 2 face centre, 3 body centre */
+TMR_HD int slot_label(int order, int i, int j, int k) {
+  const int hi = order - 1;
+  const int ext = ((i == 0 || i == hi) ? 1 : 0) + ((j == 0 || j == hi) ? 1 : 0) +
+                  ((k == 0 || k == hi) ? 1 : 0);
+  return 3 - ext;
+}
 
 /* ---- super-mesh connectivity tables (device or host pointers) -----------
    Layout and meaning follow reference src/TMROctForest.h:323-410: inverse
@@ -460,6 +476,60 @@ TMR_HD void lagrange_basis(int order, double u, const double *knots,
     }
     N[i] = v;
   }
+}
+
+/* ---- Bernstein points (reference src/TMRInterpolation.h:164-183,309-560) --
+   Bernstein basis of degree order-1 at u in [-1,1] by the usual recurrence
+   B_j^n = (1-t) B_j^(n-1) + t B_(j-1)^(n-1), t = (1+u)/2. */
+TMR_HD void bernstein_basis(int order, double u, double *N) {
+  const double u1 = 0.5 * (1.0 - u);
+  const double u2 = 0.5 * (u + 1.0);
+  N[0] = 1.0;
+  for (int j = 1; j < order; j++) {
+    double s = 0.0;
+    for (int k = 0; k < j; k++) {
+      const double t = N[k];
+      N[k] = s + u1 * t;
+      s = u2 * t;
+    }
+    N[j] = s;
+  }
+}
+
+TMR_HD double binomial_small(int n, int k) {
+  double c = 1.0;
+  for (int i = 0; i < k; i++) c = c * (double)(n - i) / (double)(i + 1);
+  return c;
+}
+
+/* Control point u of the two half-length children of a degree-p Bezier edge
+   (p = order-1; u = -p..0 indexes the left child, 0..p the right one) as a
+   combination of the parent's control points: rows of the midpoint
+   subdivision (de Casteljau) matrices, C(k,j)/2^k.  All values are dyadic, so
+   they equal the reference's tabulated eval_bernstein_weights exactly. */
+TMR_HD void bernstein_subdivision_weights(int order, int u, double *N) {
+  const int p = order - 1;
+  for (int j = 0; j < order; j++) N[j] = 0.0;
+  if (u <= 0) {
+    const int k = u + p;
+    const double scale = 1.0 / (double)(1 << k);
+    for (int j = 0; j <= k; j++) N[j] = binomial_small(k, j) * scale;
+  } else {
+    const int k = u;
+    const double scale = 1.0 / (double)(1 << (p - k));
+    for (int j = k; j <= p; j++) N[j] = binomial_small(p - k, j - k) * scale;
+  }
+}
+
+/* Control point i of a degree-(p+1) curve expressed in the degree-p control
+   points of the same curve (degree elevation), p = coarse_order-1
+   (reference eval_bernstein_interp_weights, one order apart) */
+TMR_HD void bernstein_elevation_weights(int coarse_order, int i, double *N) {
+  const int p = coarse_order - 1;
+  for (int j = 0; j < coarse_order; j++) N[j] = 0.0;
+  const double a = (double)i / (double)(p + 1);
+  if (i > 0) N[i - 1] = a;
+  if (i <= p) N[i] = 1.0 - a;
 }
 
 TMR_HD int popc32(u32 v) {

@@ -232,6 +232,7 @@ struct InterpRow {
   const int *cdep_ptr;
   const int *cdep_conn;
   const double *cdep_w;
+  int bernstein; /* both meshes use Bernstein points (reference :6434-6500) */
 
   /* per-axis weights with the collapse rule (reference :6501-6548) */
   TMR_HD void axis(int i, i32 nx, i32 h, i32 ox, i32 hc, int *start, int *end,
@@ -247,10 +248,16 @@ struct InterpRow {
       *start = corder - 1;
       *end = corder;
       N[corder - 1] = 1.0;
+    } else if (bernstein && forder != corder) {
+      bernstein_elevation_weights(corder, i, N);
     } else {
       const double u =
           -1.0 + 2.0 * (nx + 0.5 * h * (1.0 + fknots[i]) - ox) / hc;
-      lagrange_basis(corder, u, cknots, N);
+      if (bernstein) {
+        bernstein_basis(corder, u, N);
+      } else {
+        lagrange_basis(corder, u, cknots, N);
+      }
     }
   }
 
@@ -520,6 +527,12 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   r.cdep_ptr = cn.dep_ptr.get();
   r.cdep_conn = cn.dep_conn.get();
   r.cdep_w = cn.dep_weights.get();
+  r.bernstein = (fn.interp_type == 2 && cn.interp_type == 2) ? 1 : 0;
+  if (r.bernstein && fn.order - cn.order > 1) {
+    fprintf(stderr,
+            "TMROctForest Error: Mesh order difference across grids should be "
+            "1\n");
+  }
 
   /* rows of this rank's owned fine nodes, in first-touch order */
   i64 nrows = 0;

@@ -556,6 +556,7 @@ struct NodeEmit {
       step = (1 << (kMaxLevel - level)) / (order - 1);
     }
     const u64 hi = tree_id(block) << (3 * (nfmt.Dn + 1));
+    const int lb = nfmt.lbits;
     TMR_UNROLL
     for (int kk = 0; kk < np; kk++) {
       TMR_UNROLL
@@ -563,14 +564,15 @@ struct NodeEmit {
         TMR_UNROLL
         for (int ii = 0; ii < np; ii++) {
           if (fam && ((ii && !bx) || (jj && !by) || (kk && !bz))) continue;
+          const int label = lb ? slot_label(np, ii, jj, kk) : 0;
           u64 key;
           if (interior) {
-            key = hi | sx[ii] | sy[jj] | sz[kk];
+            key = ((hi | sx[ii] | sy[jj] | sz[kk]) << lb) | (u64)label;
           } else {
             i32 b = block, nx = x + ii * step, ny = y + jj * step,
                 nz = z + kk * step;
             transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-            key = nfmt.encode((i32)tree_id(b), nx, ny, nz);
+            key = nfmt.encode((i32)tree_id(b), nx, ny, nz, label);
           }
           /* whether the slot stands for the whole family is re-derived from
              the keys at scatter time (in_family), not carried in the payload */
@@ -748,7 +750,10 @@ struct ParentNodeGen {
           nx = px + ta; ny = py + tb; nz = pz + ii * step;
         }
         transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-        emit(nfmt.encode(tree_id(b), nx, ny, nz));
+        /* parent edge: end points are corners, the rest edge nodes */
+        const int label =
+            nfmt.lbits ? ((ii == 0 || ii == order - 1) ? 0 : 1) : 0;
+        emit(nfmt.encode(tree_id(b), nx, ny, nz, label));
       }
     }
     for (int f = 0; f < 6; f++) {
@@ -765,7 +770,10 @@ struct ParentNodeGen {
             nx = px + p * step; ny = py + q * step; nz = pz + nn;
           }
           transform_node(t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-          emit(nfmt.encode(tree_id(b), nx, ny, nz));
+          const int pe = (p == 0 || p == order - 1) ? 1 : 0;
+          const int qe = (q == 0 || q == order - 1) ? 1 : 0;
+          const int label = nfmt.lbits ? (2 - pe - qe) : 0;
+          emit(nfmt.encode(tree_id(b), nx, ny, nz, label));
         }
       }
     }
@@ -1082,10 +1090,17 @@ struct DepFillFn {
   const int *conn;
   NodeEmit fam;
 
-  TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, i64) const {
+  int bernstein;
+
+  TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, int label) const {
     transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
-    const i64 idx = node_ix.find(node_keys, nfmt.encode(block, x, y, z));
+    const i64 idx = node_ix.find(node_keys, nfmt.encode(block, x, y, z, label));
     return idx >= 0 ? node_num[idx] : 0;
+  }
+  /* labels in use: end points of a parent edge are corner nodes, the rest
+     edge nodes; on a face additionally the centre is a face node */
+  TMR_HD int line_label(int i) const {
+    return nfmt.lbits ? ((i == 0 || i == order - 1) ? 0 : 1) : 0;
   }
   /* first element of e's family if that family is complete, else -1 */
   TMR_HD i64 family_base(i64 e) const {
@@ -1134,11 +1149,17 @@ struct DepFillFn {
         } else {
           nx = px + ta; ny = py + tb; nz = pz + ii * step;
         }
-        dep_conn[ptr + ii] = lookup(block, nx, ny, nz, dep_node[d]);
+        dep_conn[ptr + ii] = lookup(block, nx, ny, nz, line_label(ii));
       }
       const int bit = (id >> (ed >> 2)) & 1;
-      const double u = 1.0 * (bit - 1) + 0.5 * (1.0 + knots[k]);
-      lagrange_basis(order, u, knots, dep_weights + ptr);
+      if (bernstein) {
+        /* reference :5364-5374 */
+        bernstein_subdivision_weights(order, (order - 1) * (bit - 1) + k,
+                                      dep_weights + ptr);
+      } else {
+        const double u = 1.0 * (bit - 1) + 0.5 * (1.0 + knots[k]);
+        lagrange_basis(order, u, knots, dep_weights + ptr);
+      }
     } else if (win_face[d]) {
       const u64 code = win_face[d] - 1;
       const int pos = (int)(code & 255);
@@ -1174,20 +1195,28 @@ struct DepFillFn {
           } else {
             nx = px + p * step; ny = py + q * step; nz = pz + nn;
           }
-          dep_conn[ptr + p + q * order] = lookup(block, nx, ny, nz, dep_node[d]);
+          dep_conn[ptr + p + q * order] =
+              lookup(block, nx, ny, nz,
+                     nfmt.lbits ? (line_label(p) + line_label(q)) : 0);
         }
       }
       /* child bits along the face's first / second in-face axis */
       const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
       const int b1 = (f < 2) ? by : bx;
       const int b2 = (f < 4) ? bz : by;
-      double u = -1.0 + 0.5 * (1.0 + knots[ii]);
-      double v = -1.0 + 0.5 * (1.0 + knots[jj]);
-      u += 1.0 * b1;
-      v += 1.0 * b2;
       double Nu[kMaxOrder], Nv[kMaxOrder];
-      lagrange_basis(order, u, knots, Nu);
-      lagrange_basis(order, v, knots, Nv);
+      if (bernstein) {
+        /* reference :5453-5473 */
+        bernstein_subdivision_weights(order, -(order - 1) + ii + (order - 1) * b1, Nu);
+        bernstein_subdivision_weights(order, -(order - 1) + jj + (order - 1) * b2, Nv);
+      } else {
+        double u = -1.0 + 0.5 * (1.0 + knots[ii]);
+        double v = -1.0 + 0.5 * (1.0 + knots[jj]);
+        u += 1.0 * b1;
+        v += 1.0 * b2;
+        lagrange_basis(order, u, knots, Nu);
+        lagrange_basis(order, v, knots, Nv);
+      }
       for (int j = 0; j < order * order; j++) {
         dep_weights[ptr + j] = Nu[j % order] * Nv[j / order];
       }
@@ -1283,9 +1312,10 @@ struct U32DestFn {
 struct NodeHomeFn {
   const u64 *node_keys;
   int Dn;
+  int lbits;
   OwnerMap om; /* positions at depth Dn */
   TMR_HD int operator()(i64 i) const {
-    const u64 k = node_keys[i];
+    const u64 k = node_keys[i] >> lbits;
     const int sh = 3 * (Dn + 1);
     const u64 block = k >> sh;
     /* halving every squeezed coordinate = shifting the interleaved code by 3 */
@@ -1498,11 +1528,10 @@ inline int create_nodes(Forest &f, int order, int interp_type,
      Lagrange functions evaluated at dyadic u -- bit-identical results
      (reference src/TMRInterpolation.h:164-183,309-322, :5364-5374).  Order-3
      Bernstein needs edge/face/block node labels (initLabel :6798-6811). */
-  if (order < 2 || order > kMaxOrder || (interp_type == 2 && order > 2)) {
+  if (order < 2 || order > kMaxOrder) {
     fprintf(stderr,
-            "TMROctForest Error: the CUDA createNodes() supports mesh order 2 "
-            "and 3 with Lagrange interpolation and order 2 with Bernstein "
-            "points (order %d, type %d requested)\n",
+            "TMROctForest Error: the CUDA createNodes() supports mesh orders 2 "
+            "and 3 (order %d, type %d requested)\n",
             order, interp_type);
     return 1;
   }
@@ -1535,6 +1564,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   }
   nd.nfmt.Dn = f.fmt.D + (order > 2 ? 1 : 0);
   nd.nfmt.bbits = f.bbits;
+  const int bernstein = (interp_type == 2) ? 1 : 0;
+  nd.nfmt.lbits = (bernstein && order >= 3) ? 2 : 0;
   if (nd.nfmt.total_bits() > 64 || nd.nfmt.Dn + 1 > 21) {
     fprintf(stderr,
             "TMROctForest Error: node keys of %d trees at depth %d exceed the "
@@ -1690,7 +1721,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     /* packed mode: when node-key bits + payload bits fit in 64, the payload
        (conn slot) rides in the key's high bits and the sort is keys-only:
        16 B instead of 24 B of HBM traffic per candidate per pass */
-    const int mbits = 3 * (nd.nfmt.Dn + 1);
+    const int mbits = nd.nfmt.pos_bits(); /* Morton + label bits */
     const int nbits = sort_bbits + mbits;
     const u64 max_payload =
         emit_gen.families ? (((u64)E << 3) | 7ULL) : (u64)nc;
@@ -1762,7 +1793,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   DBuf<int> owner;
   if (comm) {
     owner.alloc(ctx, Nn);
-    NodeHomeFn home = {nd.node_keys.get(), nd.nfmt.Dn, om_n};
+    NodeHomeFn home = {nd.node_keys.get(), nd.nfmt.Dn, nd.nfmt.lbits, om_n};
     OwnerInitFn oi = {home, me, created.get(), owner.get()};
     launch(ctx, Nn, oi, "nodes_owner_init");
     /* foreign-home nodes: (key, created, local index) */
@@ -1820,15 +1851,15 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   dev_zero(ctx, dep_flag.get(), (size_t)Nn);
   if (order == 2) {
     DepLabelFn<2> lab = {f.keys.get(), f.info.get(), f.fmt,         order,
-                         0,            nd.conn.get(), dep_flag.get()};
+                         bernstein,    nd.conn.get(), dep_flag.get()};
     launch(ctx, E, lab, "nodes_dep_label");
   } else if (order == 3) {
     DepLabelFn<3> lab = {f.keys.get(), f.info.get(), f.fmt,         order,
-                         0,            nd.conn.get(), dep_flag.get()};
+                         bernstein,    nd.conn.get(), dep_flag.get()};
     launch(ctx, E, lab, "nodes_dep_label");
   } else {
     DepLabelFn<0> lab = {f.keys.get(), f.info.get(), f.fmt,         order,
-                         0,            nd.conn.get(), dep_flag.get()};
+                         bernstein,    nd.conn.get(), dep_flag.get()};
     launch(ctx, E, lab, "nodes_dep_label");
   }
   DBuf<u32> dep_before(ctx, Nn);
@@ -1915,7 +1946,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     DBuf<u32> node_index_store;
     DepFillFn fill;
     fill.node_ix = build_key_index(ctx, nd.node_keys.get(), Nn,
-                                   (u64)f.nblocks << (3 * (nd.nfmt.Dn + 1)),
+                                   (u64)f.nblocks << nd.nfmt.pos_bits(),
                                    node_index_store);
     fill.keys = f.keys.get();
     fill.fmt = f.fmt;
@@ -1929,6 +1960,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.win_edge = win_edge.get();
     fill.win_face = win_face.get();
     fill.dep_node = dep_node.get();
+    fill.bernstein = bernstein;
     fill.conn = nd.conn.get();
     {
       NodeEmit fg = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order, order == 2 ? 1 : 0};
