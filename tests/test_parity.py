@@ -92,6 +92,30 @@ def test_bernstein_order3(conn_name, impl, ref_lib):
     util.assert_interp_equal(res[0][2], res[1][2], "bernstein 2 -> 2")
 
 
+@pytest.mark.parametrize("interp", [1, 2], ids=["gauss_lobatto", "bernstein"])
+@pytest.mark.parametrize("conn_name", ["single", "box7", "connector15"])
+def test_order4(conn_name, interp, impl, ref_lib):
+    """Order 4: (order-2)^dim nodes per edge / face / block entity, ordered
+    through edge reversal and face orientation (reference createLocalConn
+    src/TMROctForest.cpp:4660-4867, getEdgeNodes/getFaceNodes :4886-5146), and
+    the 4 -> 3 -> 2 prolongations (examples/interp/interp.py uses order 4)."""
+    conn = util.CONNS[conn_name]()
+    res = []
+    for lib in (ref_lib, impl):
+        f = util.build_forest(lib, conn, 1, 2, 30, 1, 4, interp=interp)
+        nodes = util.node_results(f)
+        o3 = f.duplicate()
+        o3.setMeshOrder(3, interp)
+        v43 = f.createInterpolation(o3)
+        o2 = o3.duplicate()
+        o2.setMeshOrder(2, interp)
+        v32 = o3.createInterpolation(o2)
+        res.append((nodes, v43, v32))
+    util.assert_nodes_equal(res[0][0], res[1][0], "order 4")
+    util.assert_interp_equal(res[0][1], res[1][1], "order 4 -> 3")
+    util.assert_interp_equal(res[0][2], res[1][2], "order 3 -> 2")
+
+
 def test_connectivity_tables(impl, ref_lib):
     """setConnectivity derives identical edge/face numbering, inverse maps,
     orientation ids (reference src/TMROctForest.cpp:558-1143)."""

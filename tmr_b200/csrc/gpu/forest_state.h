@@ -22,7 +22,13 @@
 
 namespace tmrgpu {
 
-static const int kMaxOrder = 3; /* orders 2 and 3 (label-free node sets) */
+/* mesh orders 2..4.  Orders 2 and 3 have one node per corner / edge / face /
+   block entity; from order 4 on an entity carries (order-2)^dim nodes that are
+   numbered consecutively and reached through the edge-reversal and
+   face-orientation permutations of reference createLocalConn
+   (src/TMROctForest.cpp:4660-4867).  The bound is the size of the per-thread
+   knot and basis arrays, nothing structural. */
+static const int kMaxOrder = 4;
 
 struct NodeData {
   bool valid;

@@ -374,7 +374,7 @@ struct InterpLocateRecvFn {
    with a full face stencil, corder^3 * corder^2 (reference :6637) */
 template <int kCOrder>
 struct RowCap {
-  static const int value = (kCOrder == 2) ? 32 : kMaxRowEntries;
+  static const int value = (kCOrder == 2) ? 32 : (kCOrder == 3 ? 243 : 1024);
 };
 
 /* row lengths, one thread per row (a plain launch: the build is far too heavy
@@ -646,8 +646,11 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   if (r.corder == 2) {
     InterpCountFn<2> cf = {r, q, cnt.get()};
     launch(ctx, nrows, cf, "interp_row_count");
-  } else {
+  } else if (r.corder == 3) {
     InterpCountFn<3> cf = {r, q, cnt.get()};
+    launch(ctx, nrows, cf, "interp_row_count");
+  } else {
+    InterpCountFn<4> cf = {r, q, cnt.get()};
     launch(ctx, nrows, cf, "interp_row_count");
   }
   StoredCountFn sc = {cnt.get()};
@@ -663,9 +666,13 @@ inline int create_interp(Forest &fine, Forest &coarse) {
     InterpFillFn<2> ffn = {r, q, I.cols.get(), I.vals.get()};
     InterpFillPlaceFn<2> pl = {ffn, off.get()};
     launch(ctx, nrows, pl, "interp_row_fill");
-  } else {
+  } else if (r.corder == 3) {
     InterpFillFn<3> ffn = {r, q, I.cols.get(), I.vals.get()};
     InterpFillPlaceFn<3> pl = {ffn, off.get()};
+    launch(ctx, nrows, pl, "interp_row_fill");
+  } else {
+    InterpFillFn<4> ffn = {r, q, I.cols.get(), I.vals.get()};
+    InterpFillPlaceFn<4> pl = {ffn, off.get()};
     launch(ctx, nrows, pl, "interp_row_fill");
   }
   I.rows.swap(q_num);

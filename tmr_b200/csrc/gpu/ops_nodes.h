@@ -1063,6 +1063,121 @@ struct DepPtrFn {
   }
 };
 
+/* ---- orders >= 4: entities -> nodes ------------------------------------------
+   The sorted unique keys are the 27-per-element ENTITIES (corner, edge, face,
+   block, told apart by the label bits); an entity with label L owns
+   (order-2)^L consecutive local nodes (reference createNodes :4090-4100). */
+struct EntityMultFn {
+  const u64 *ent_keys;
+  int order;
+  TMR_HD u32 operator()(i64 i) const {
+    const int label = (int)(ent_keys[i] & 3);
+    u32 m = 1;
+    for (int k = 0; k < label; k++) m *= (u32)(order - 2);
+    return m;
+  }
+};
+
+/* local node id of the sub-node of an entity reached from a tree whose own
+   frame may differ from the owner tree's: `b,x,y,z` = the entity's position in
+   the tree it is seen from.  Edge nodes run backwards when the edge is
+   reversed on the owner, face nodes go through the face orientation
+   (reference createLocalConn :4716-4836, getEdgeNodes :4947-4964,
+   getFaceNodes :5083-5141). */
+struct EntityNodes {
+  ConnTables t;
+  int order;
+  /* position p = 1..order-2 along the edge that runs in direction edge_dir */
+  TMR_HD int edge_sub(i32 b, i32 x, i32 y, i32 z, int edge_dir, int p) const {
+    int rev = 0;
+    transform_node(t, &b, &x, &y, &z, edge_dir, &rev, NULL);
+    return rev ? (order - 2 - p) : (p - 1);
+  }
+  TMR_HD int edge_reversed(i32 b, i32 x, i32 y, i32 z, int edge_dir) const {
+    int rev = 0;
+    transform_node(t, &b, &x, &y, &z, edge_dir, &rev, NULL);
+    return rev;
+  }
+  TMR_HD int face_id(i32 b, i32 x, i32 y, i32 z) const {
+    int id = 0;
+    transform_node(t, &b, &x, &y, &z, -1, NULL, &id);
+    return id;
+  }
+  /* in-face position (a, c), both 1..order-2, on a face with orientation id */
+  TMR_HD int face_sub(int id, int a, int c) const {
+    i32 u, v;
+    face_to_owner(id, order - 1, a, c, &u, &v);
+    return (u - 1) + (v - 1) * (order - 2);
+  }
+};
+
+/* createLocalConn (reference :4660-4867) from the element's 27 entity indices */
+struct ConnBuildFn {
+  const u64 *keys;
+  KeyFmt fmt;
+  EntityNodes en;
+  const int *ent_conn; /* [E][27] entity index per 3x3x3 position */
+  const u32 *ent_off;  /* first local node of every entity */
+  int *conn;           /* [E][order^3] local node ids */
+  TMR_HD void operator()(i64 e) const {
+    const int n = en.order;
+    i32 block, x, y, z;
+    int level;
+    fmt.decode(keys[e], &block, &x, &y, &z, &level);
+    const i32 h = 1 << (kMaxLevel - level - 1);
+    const int *ec = ent_conn + e * 27;
+    int *c = conn + e * (i64)(n * n * n);
+    for (int k3 = 0; k3 < 3; k3++) {
+      for (int j3 = 0; j3 < 3; j3++) {
+        for (int i3 = 0; i3 < 3; i3++) {
+          const int base = (int)ent_off[ec[i3 + 3 * j3 + 9 * k3]];
+          const i32 ex = x + h * i3, ey = y + h * j3, ez = z + h * k3;
+          const int mx = (i3 == 1), my = (j3 == 1), mz = (k3 == 1);
+          /* slot index of an extreme (0 / order-1) coordinate */
+          const int ci = (n - 1) * (i3 / 2), cj = (n - 1) * (j3 / 2),
+                    ck = (n - 1) * (k3 / 2);
+          if (mx + my + mz == 0) {
+            c[ci + n * cj + n * n * ck] = base;
+          } else if (mx + my + mz == 1) {
+            const int dir = mx ? 0 : (my ? 1 : 2);
+            const int rev = en.edge_reversed(block, ex, ey, ez, dir);
+            for (int p = 1; p < n - 1; p++) {
+              const int ii = mx ? p : ci, jj = my ? p : cj, kk = mz ? p : ck;
+              c[ii + n * jj + n * n * kk] = base + (rev ? (n - 2 - p) : (p - 1));
+            }
+          } else if (mx + my + mz == 2) {
+            const int id = en.face_id(block, ex, ey, ez);
+            for (int q = 1; q < n - 1; q++) {
+              for (int p = 1; p < n - 1; p++) {
+                /* in-face axes in the reference's order: (y,z), (x,z), (x,y) */
+                int ii, jj, kk;
+                if (!mx) {
+                  ii = ci; jj = p; kk = q;
+                } else if (!my) {
+                  ii = p; jj = cj; kk = q;
+                } else {
+                  ii = p; jj = q; kk = ck;
+                }
+                c[ii + n * jj + n * n * kk] = base + en.face_sub(id, p, q);
+              }
+            }
+          } else {
+            for (int kk = 1; kk < n - 1; kk++) {
+              for (int jj = 1; jj < n - 1; jj++) {
+                for (int ii = 1; ii < n - 1; ii++) {
+                  c[ii + n * jj + n * n * kk] =
+                      base + (ii - 1) + (jj - 1) * (n - 2) +
+                      (kk - 1) * (n - 2) * (n - 2);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+};
+
 /* createDependentConn pass 3 (reference :5272-5508) */
 struct DepFillFn {
   const u64 *keys;
@@ -1091,6 +1206,92 @@ struct DepFillFn {
   NodeEmit fam;
 
   int bernstein;
+  /* orders >= 4: first local node of every entity (NULL below order 4, where
+     entity index == node index) and the sub-node permutations */
+  const u32 *ent_off;
+  EntityNodes en;
+
+  /* entity at (block,x,y,z) with `label` -> first local node (or -1) */
+  TMR_HD i64 entity_base(i32 block, i32 x, i32 y, i32 z, int label) const {
+    transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
+    const i64 idx = node_ix.find(node_keys, nfmt.encode(block, x, y, z, label));
+    if (idx < 0) return -1;
+    return ent_off ? (i64)ent_off[idx] : idx;
+  }
+  TMR_HD int num_at(i64 node) const { return node >= 0 ? node_num[node] : 0; }
+
+  /* the `order` nodes of edge ed of the octant (block, px,py,pz) of size hp
+     (reference getEdgeNodes :4886-4966) */
+  TMR_HD void edge_nodes_general(i32 block, i32 px, i32 py, i32 pz, i32 hp,
+                                 int ed, int *out) const {
+    const int n = order;
+    const i32 hh = hp / 2;
+    const int s = ed & 3;
+    const i32 ta = hp * (s & 1), tb = hp * (s >> 1);
+    for (int g = 0; g < 3; g++) {
+      i32 nx, ny, nz;
+      if (ed < 4) {
+        nx = px + g * hh; ny = py + ta; nz = pz + tb;
+      } else if (ed < 8) {
+        nx = px + ta; ny = py + g * hh; nz = pz + tb;
+      } else {
+        nx = px + ta; ny = py + tb; nz = pz + g * hh;
+      }
+      if (g != 1) {
+        out[(g / 2) * (n - 1)] = num_at(entity_base(block, nx, ny, nz, 0));
+      } else {
+        const i64 base = entity_base(block, nx, ny, nz, 1);
+        const int rev = en.edge_reversed(block, nx, ny, nz, ed >> 2);
+        for (int k = 1; k < n - 1; k++) {
+          out[k] = num_at(base < 0 ? -1 : base + (rev ? (n - 2 - k) : (k - 1)));
+        }
+      }
+    }
+  }
+  /* the order^2 nodes of face f (reference getFaceNodes :4990-5146) */
+  TMR_HD void face_nodes_general(i32 block, i32 px, i32 py, i32 pz, i32 hp,
+                                 int f, int *out) const {
+    const int n = order;
+    const i32 hh = hp / 2;
+    const i32 nn = hp * (f & 1);
+    /* directions of the first / second in-face axis */
+    const int ax1 = (f < 2) ? 1 : 0, ax2 = (f < 4) ? 2 : 1;
+    for (int jj = 0; jj < 3; jj++) {
+      for (int ii = 0; ii < 3; ii++) {
+        i32 nx, ny, nz;
+        if (f < 2) {
+          nx = px + nn; ny = py + hh * ii; nz = pz + hh * jj;
+        } else if (f < 4) {
+          nx = px + hh * ii; ny = py + nn; nz = pz + hh * jj;
+        } else {
+          nx = px + hh * ii; ny = py + hh * jj; nz = pz + nn;
+        }
+        const int ie = (ii != 1), je = (jj != 1);
+        if (ie && je) {
+          out[(ii / 2) * (n - 1) + (jj / 2) * (n - 1) * n] =
+              num_at(entity_base(block, nx, ny, nz, 0));
+        } else if (ie || je) {
+          /* an edge of the face: it runs along the axis whose index is 1 */
+          const i64 base = entity_base(block, nx, ny, nz, 1);
+          const int rev = en.edge_reversed(block, nx, ny, nz, ie ? ax2 : ax1);
+          const int incr = ie ? n : 1;
+          const int start = ie ? (ii / 2) * (n - 1) : (jj / 2) * (n - 1) * n;
+          for (int k = 1; k < n - 1; k++) {
+            out[start + k * incr] =
+                num_at(base < 0 ? -1 : base + (rev ? (n - 2 - k) : (k - 1)));
+          }
+        } else {
+          const i64 base = entity_base(block, nx, ny, nz, 2);
+          const int id = en.face_id(block, nx, ny, nz);
+          for (int k = 1; k < n - 1; k++) {
+            for (int j = 1; j < n - 1; j++) {
+              out[j + k * n] = num_at(base < 0 ? -1 : base + en.face_sub(id, j, k));
+            }
+          }
+        }
+      }
+    }
+  }
 
   TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, int label) const {
     transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
@@ -1132,7 +1333,8 @@ struct DepFillFn {
       const int s = ed & 3;
       const i32 ta = hp * (s & 1), tb = hp * (s >> 1);
       const i64 e0 = family_base(e);
-      for (int ii = 0; ii < order; ii++) {
+      if (ent_off) edge_nodes_general(block, px, py, pz, hp, ed, dep_conn + ptr);
+      for (int ii = 0; ii < order && !ent_off; ii++) {
         if (e0 >= 0) {
           const int sa = s & 1, sb = s >> 1;
           const int c = ed < 4 ? (ii + 2 * sa + 4 * sb)
@@ -1177,7 +1379,8 @@ struct DepFillFn {
       const i32 step = hp / (order - 1);
       const i32 nn = hp * (f & 1);
       const i64 e0 = family_base(e);
-      for (int q = 0; q < order; q++) {
+      if (ent_off) face_nodes_general(block, px, py, pz, hp, f, dep_conn + ptr);
+      for (int q = 0; q < order && !ent_off; q++) {
         for (int p = 0; p < order; p++) {
           if (e0 >= 0) {
             const int n1 = f & 1;
@@ -1535,6 +1738,16 @@ inline int create_nodes(Forest &f, int order, int interp_type,
             order, interp_type);
     return 1;
   }
+  /* from order 4 on the sorted keys are entities, not nodes (see
+     EntityMultFn); single rank only for now */
+  const bool general = order > 3;
+  if (general && comm) {
+    fprintf(stderr,
+            "TMROctForest Error: mesh orders above 3 are not available on more "
+            "than one rank yet\n");
+    return 1;
+  }
+  const int gorder = general ? 3 : order; /* geometry: 2x2x2 or 3x3x3 positions */
   const int npe = order * order * order;
   const i64 E = f.n;
   if (E * npe >= (1LL << 31)) {
@@ -1565,7 +1778,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   nd.nfmt.Dn = f.fmt.D + (order > 2 ? 1 : 0);
   nd.nfmt.bbits = f.bbits;
   const int bernstein = (interp_type == 2) ? 1 : 0;
-  nd.nfmt.lbits = (bernstein && order >= 3) ? 2 : 0;
+  /* labels: reference initLabel :6798-6811 */
+  nd.nfmt.lbits = (general || (bernstein && order >= 3)) ? 2 : 0;
   if (nd.nfmt.total_bits() > 64 || nd.nfmt.Dn + 1 > 21) {
     fprintf(stderr,
             "TMROctForest Error: node keys of %d trees at depth %d exceed the "
@@ -1667,8 +1881,13 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   trace_mark(ctx, "nodes: hanging info");
 
   /* 2. node candidates -> sort -> unique nodes + local connectivity */
-  const i64 nc = E * npe;
+  const i64 nc = E * npe;               /* connectivity entries */
+  const i64 ngc = E * (i64)(gorder * gorder * gorder); /* entity slots */
   nd.conn.alloc(ctx, nc);
+  /* orders >= 4: the scatter fills the entity table, ConnBuildFn the conn */
+  DBuf<int> ent_conn;
+  if (general) ent_conn.alloc(ctx, ngc);
+  DBuf<u32> ent_off;
   i64 Nn;
   DBuf<unsigned char> created;
   {
@@ -1703,9 +1922,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     }
     /* candidate emission plan */
     NodeEmit emit_gen = {f.keys.get(), E,     f.fmt,
-                         nd.nfmt,      f.tables, order,
+                         nd.nfmt,      f.tables, gorder,
                          order == 2 ? 1 : 0,     tree_dense.get()};
-    i64 nemit = nc;
+    i64 nemit = ngc;
     DBuf<u32> eoff;
     if (emit_gen.families) {
       eoff.alloc(ctx, E);
@@ -1724,7 +1943,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     const int mbits = nd.nfmt.pos_bits(); /* Morton + label bits */
     const int nbits = sort_bbits + mbits;
     const u64 max_payload =
-        emit_gen.families ? (((u64)E << 3) | 7ULL) : (u64)nc;
+        emit_gen.families ? (((u64)E << 3) | 7ULL) : (u64)ngc;
     int pbits = 1;
     while ((1ULL << pbits) <= max_payload + 1) pbits++;
     const bool packed = nbits + pbits <= 64;
@@ -1749,7 +1968,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       NodeEmitPlaceFn ep = {ef, eoff.get()};
       launch(ctx, E, ep, "nodes_candidates");
     } else {
-      if (order == 2) {
+      if (gorder == 2) {
         NodeEmitDenseFn<2> ed = {emit_gen, ck.get(), cv.get(), nbits};
         launch(ctx, E, ed, "nodes_candidates");
       } else {
@@ -1775,12 +1994,30 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     }
     RunHeadMaskedFn rh = {ck.get(), kmask};
     NodeScatterFn sc = {ck.get(), cv.get(),     kmask,         nbits,
-                        no_slot,  ck_alt.get(), nd.conn.get(), created.get(),
+                        no_slot,  ck_alt.get(),
+                        general ? ent_conn.get() : nd.conn.get(), created.get(),
                         emit_gen, tree_undense.get(), mbits};
     Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
 
     nd.node_keys.alloc(ctx, Nn);
     copy_d2d(ctx, nd.node_keys.get(), ck_alt.get(), (size_t)Nn * sizeof(u64));
+  }
+  if (general) {
+    /* entities -> nodes: Nn becomes the number of local NODES; node_keys
+       keeps one key per entity (stencil look-ups go through ent_off) */
+    const i64 nent = Nn;
+    ent_off.alloc(ctx, nent);
+    EntityMultFn em = {nd.node_keys.get(), order};
+    Nn = (i64)scan_counts(ctx, nent, em, ent_off.get(), "nodes_entity_offsets");
+    EntityNodes en = {f.tables, order};
+    ConnBuildFn cb = {f.keys.get(), f.fmt, en, ent_conn.get(), ent_off.get(),
+                      nd.conn.get()};
+    launch(ctx, E, cb, "nodes_conn_build");
+    ent_conn.reset();
+    if (Nn >= (1LL << 31)) {
+      fprintf(stderr, "TMROctForest Error: too many local nodes\n");
+      return 1;
+    }
   }
   nd.num_local_nodes = Nn;
   trace_mark(ctx, "nodes: unique+conn");
@@ -1945,7 +2182,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     nd.dep_weights.alloc(ctx, (i64)nnz);
     DBuf<u32> node_index_store;
     DepFillFn fill;
-    fill.node_ix = build_key_index(ctx, nd.node_keys.get(), Nn,
+    fill.node_ix = build_key_index(ctx, nd.node_keys.get(), nd.node_keys.size(),
                                    (u64)f.nblocks << nd.nfmt.pos_bits(),
                                    node_index_store);
     fill.keys = f.keys.get();
@@ -1955,12 +2192,17 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.order = order;
     for (int i = 0; i < 4; i++) fill.knots[i] = nd.knots[i];
     fill.node_keys = nd.node_keys.get();
-    fill.num_nodes = Nn;
+    fill.num_nodes = nd.node_keys.size();
     fill.node_num = nd.node_num.get();
     fill.win_edge = win_edge.get();
     fill.win_face = win_face.get();
     fill.dep_node = dep_node.get();
     fill.bernstein = bernstein;
+    fill.ent_off = general ? ent_off.get() : NULL;
+    {
+      EntityNodes en = {f.tables, order};
+      fill.en = en;
+    }
     fill.conn = nd.conn.get();
     {
       NodeEmit fg = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order, order == 2 ? 1 : 0};
