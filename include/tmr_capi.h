@@ -72,6 +72,13 @@ int tmrc_get_owned_node_range(tmrc_forest f, const int **node_range);
 int tmrc_get_ext_pre_offset(tmrc_forest f);
 int tmrc_get_local_node_number(tmrc_forest f, int node);
 int tmrc_get_interp_knots(tmrc_forest f, const double **knots);
+/* TMROctForest::evalInterp (reference src/TMROctForest.cpp:1508-1620): shape
+   functions and, where the pointers are non-NULL, their first (3) and second
+   (6: 11,22,33,23,13,12) derivatives at pt[3]; each array holds order^3
+   values */
+void tmrc_eval_interp(tmrc_forest f, const double *pt, double *N, double *N1,
+                      double *N2, double *N3, double *N11, double *N22,
+                      double *N33, double *N23, double *N13, double *N12);
 
 void tmrc_get_connectivity(tmrc_forest f, int *nblocks, int *nfaces,
                            int *nedges, int *nnodes, const int **block_conn,

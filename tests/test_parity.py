@@ -116,6 +116,22 @@ def test_order4(conn_name, interp, impl, ref_lib):
     util.assert_interp_equal(res[0][2], res[1][2], "order 3 -> 2")
 
 
+@pytest.mark.parametrize("interp", [0, 1, 2], ids=["uniform", "gauss_lobatto", "bernstein"])
+@pytest.mark.parametrize("order", [2, 3, 4])
+def test_eval_interp(order, interp, impl, ref_lib):
+    """evalInterp: shape functions and their first / second derivatives
+    (reference src/TMROctForest.cpp:1508-1620)."""
+    pts = [(0.0, 0.0, 0.0), (-1.0, 1.0, 0.25), (0.3, -0.7, 0.9)]
+    a = OctForest(order=order, interp=interp, lib=ref_lib)
+    b = OctForest(order=order, interp=interp, lib=impl)
+    for pt in pts:
+        for der in (0, 1, 2):
+            ra, rb = a.evalInterp(pt, der), b.evalInterp(pt, der)
+            ra, rb = (ra, rb) if der else ([ra], [rb])
+            for x, y in zip(ra, rb):
+                np.testing.assert_allclose(y, x, rtol=1e-12, atol=1e-13)
+
+
 def test_connectivity_tables(impl, ref_lib):
     """setConnectivity derives identical edge/face numbering, inverse maps,
     orientation ids (reference src/TMROctForest.cpp:558-1143)."""

@@ -56,6 +56,7 @@ SIGNATURES = {
     "tmrc_get_ext_pre_offset": (I, [P]),
     "tmrc_get_local_node_number": (I, [P, I]),
     "tmrc_get_interp_knots": (I, [P, PPD]),
+    "tmrc_eval_interp": (None, [P] + [P] * 11),
     "tmrc_get_connectivity": (None, [P, PI, PI, PI, PI, PPI, PPI, PPI, PPI]),
     "tmrc_get_inverse_connectivity": (None, [P, PPI, PPI, PPI, PPI, PPI, PPI]),
     "tmrc_transform_nodes": (None, [P, P, I, I, P, P]),

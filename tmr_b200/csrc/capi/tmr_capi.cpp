@@ -135,6 +135,18 @@ int tmrc_get_interp_knots(tmrc_forest f, const double **knots) {
   return F(f)->getInterpKnots(knots);
 }
 
+void tmrc_eval_interp(tmrc_forest f, const double *pt, double *N, double *N1,
+                      double *N2, double *N3, double *N11, double *N22,
+                      double *N33, double *N23, double *N13, double *N12) {
+  if (N11) {
+    F(f)->evalInterp(pt, N, N1, N2, N3, N11, N22, N33, N23, N13, N12);
+  } else if (N1) {
+    F(f)->evalInterp(pt, N, N1, N2, N3);
+  } else {
+    F(f)->evalInterp(pt, N);
+  }
+}
+
 void tmrc_get_connectivity(tmrc_forest f, int *nblocks, int *nfaces,
                            int *nedges, int *nnodes, const int **block_conn,
                            const int **block_face_conn,

@@ -868,12 +868,51 @@ void lagrange_all(int order, double u, const double *knots, double *N,
     if (Ndd) Ndd[i] = d2;
   }
 }
+/* value, first and second derivative of the Bernstein basis of degree
+   order-1 on [-1,1]: B' = p/2 (B_{j-1}^{p-1} - B_j^{p-1}) and once more for B''
+   (reference src/TMRInterpolation.h:164-300) */
+void bernstein_all(int order, double u, double *N, double *Nd, double *Ndd) {
+  const int p = order - 1;
+  tmrgpu::bernstein_basis(order, u, N);
+  if (Nd) {
+    double lo[TMROctForest::MAX_ORDER];
+    if (p >= 1) tmrgpu::bernstein_basis(order - 1, u, lo);
+    for (int j = 0; j < order; j++) {
+      const double a = (p >= 1 && j >= 1) ? lo[j - 1] : 0.0;
+      const double b = (p >= 1 && j <= p - 1) ? lo[j] : 0.0;
+      Nd[j] = 0.5 * p * (a - b);
+    }
+  }
+  if (Ndd) {
+    double lo[TMROctForest::MAX_ORDER];
+    if (p >= 2) tmrgpu::bernstein_basis(order - 2, u, lo);
+    for (int j = 0; j < order; j++) {
+      const double a = (p >= 2 && j >= 2) ? lo[j - 2] : 0.0;
+      const double b = (p >= 2 && j >= 1 && j <= p - 1) ? lo[j - 1] : 0.0;
+      const double c = (p >= 2 && j <= p - 2) ? lo[j] : 0.0;
+      Ndd[j] = 0.25 * p * (p - 1) * (a - 2.0 * b + c);
+    }
+  }
+}
+
+void basis_all(int interp_type, int order, double u, const double *knots,
+               double *N, double *Nd, double *Ndd) {
+  if (interp_type == TMR_BERNSTEIN_POINTS) {
+    bernstein_all(order, u, N, Nd, Ndd);
+  } else {
+    lagrange_all(order, u, knots, N, Nd, Ndd);
+  }
+}
 }  // namespace
 
 void TMROctForest::evalInterp(const double pt[], double N[]) {
   double a[3][MAX_ORDER];
   for (int d = 0; d < 3; d++) {
-    tmrgpu::lagrange_basis(mesh_order, pt[d], interp_knots, a[d]);
+    if (interp_type == TMR_BERNSTEIN_POINTS) {
+      tmrgpu::bernstein_basis(mesh_order, pt[d], a[d]);
+    } else {
+      tmrgpu::lagrange_basis(mesh_order, pt[d], interp_knots, a[d]);
+    }
   }
   for (int k = 0; k < mesh_order; k++) {
     for (int j = 0; j < mesh_order; j++) {
@@ -886,7 +925,7 @@ void TMROctForest::evalInterp(const double pt[], double N[], double Nxi[],
                               double Neta[], double Nzeta[]) {
   double a[3][MAX_ORDER], d[3][MAX_ORDER];
   for (int c = 0; c < 3; c++) {
-    lagrange_all(mesh_order, pt[c], interp_knots, a[c], d[c], NULL);
+    basis_all(interp_type, mesh_order, pt[c], interp_knots, a[c], d[c], NULL);
   }
   for (int k = 0; k < mesh_order; k++) {
     for (int j = 0; j < mesh_order; j++) {
@@ -906,7 +945,7 @@ void TMROctForest::evalInterp(const double pt[], double N[], double N1[],
                               double N13[], double N12[]) {
   double a[3][MAX_ORDER], d[3][MAX_ORDER], s[3][MAX_ORDER];
   for (int c = 0; c < 3; c++) {
-    lagrange_all(mesh_order, pt[c], interp_knots, a[c], d[c], s[c]);
+    basis_all(interp_type, mesh_order, pt[c], interp_knots, a[c], d[c], s[c]);
   }
   for (int k = 0; k < mesh_order; k++) {
     for (int j = 0; j < mesh_order; j++) {
@@ -917,10 +956,12 @@ void TMROctForest::evalInterp(const double pt[], double N[], double N1[],
         *N3++ = a[0][i] * a[1][j] * d[2][k];
         *N11++ = s[0][i] * a[1][j] * a[2][k];
         *N22++ = a[0][i] * s[1][j] * a[2][k];
-        *N33++ = a[0][i] * a[1][j] * s[2][k];
         *N23++ = a[0][i] * d[1][j] * d[2][k];
         *N13++ = d[0][i] * a[1][j] * d[2][k];
-        *N12++ = d[0][i] * d[1][j] * a[2][k];
+        /* as the reference does (src/TMROctForest.cpp:1611-1613): the mixed
+           xy derivative lands in N33 and N12 is never written -- kept for
+           drop-in behaviour, not corrected */
+        *N33++ = d[0][i] * d[1][j] * a[2][k];
       }
     }
   }

@@ -202,6 +202,18 @@ class OctForest:
         n = self._lib.tmrc_get_interp_knots(self._ptr, C.byref(ptr))
         return _capi.as_double_array(ptr, n)
 
+    def evalInterp(self, pt, derivatives=0):
+        """Shape functions at pt (3 values in [-1,1]); derivatives=1 adds the
+        three first derivatives, 2 the six second derivatives as well
+        (reference TMROctForest::evalInterp, tmr/TMR.pyx)."""
+        npe = self.getMeshOrder() ** 3
+        nout = {0: 1, 1: 4, 2: 10}[derivatives]
+        out = [np.zeros(npe) for _ in range(nout)]
+        pt = np.ascontiguousarray(pt, dtype=np.float64)
+        ptrs = [a.ctypes.data for a in out] + [None] * (10 - nout)
+        self._lib.tmrc_eval_interp(self._ptr, pt.ctypes.data, *ptrs)
+        return out[0] if derivatives == 0 else out
+
     def getConnectivity(self):
         nb, nf, ne, nn = (C.c_int(0) for _ in range(4))
         bc, bfc, bec, bfi = (C.POINTER(C.c_int)() for _ in range(4))
