@@ -216,7 +216,6 @@ struct RowCodeFn {
   }
 };
 
-static const int kMaxRowEntries = 243; /* order^5 at order 3 (reference :6637) */
 
 struct InterpRow {
   /* fine */
@@ -371,7 +370,7 @@ struct InterpLocateRecvFn {
 };
 
 /* longest possible row: every coarse node of the element a dependent node
-   with a full face stencil, corder^3 * corder^2 (reference :6637) */
+   with a full face stencil, corder^3 * corder^2 = corder^5 (reference :6637) */
 template <int kCOrder>
 struct RowCap {
   static const int value = (kCOrder == 2) ? 32 : (kCOrder == 3 ? 243 : 1024);

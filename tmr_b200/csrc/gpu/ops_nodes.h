@@ -446,7 +446,7 @@ struct NodeEmit {
   KeyFmt fmt;
   NodeFmt nfmt;
   ConnTables t;
-  int order;
+  int order;    /* geometry order: 2, or 3 for every mesh order >= 3 */
   int families; /* use family emission (order 2 only) */
   /* multi-rank: order-preserving dense ids of the trees this rank's node keys
      can name (NULL = tree index as is); shortens the sort key so that the
@@ -514,16 +514,8 @@ struct NodeEmit {
     return c != 0 && ((mc >> sh) & lvl) != lvl;
   }
 
-  template <class Emit>
-  TMR_HD void run(i64 e, Emit &emit) const {
-    /* create_nodes admits orders 2 and 3 only (kMaxOrder) */
-    if (order == 2) {
-      run_order<2>(e, emit);
-    } else {
-      run_order<3>(e, emit);
-    }
-  }
-  /* kOrder = 2 or 3 unrolls the node loops */
+  /* kOrder = 2 or 3 (the geometry: 2x2x2 corners or 3x3x3 entity positions)
+     unrolls the node loops */
   template <int kOrder, class Emit>
   TMR_HD void run_order(i64 e, Emit &emit) const {
     const int order = kOrder ? kOrder : this->order;

@@ -131,8 +131,8 @@ class DBuf {
 };
 
 /* --- radix sort (prim_cuda.cu) -------------------------------------------
-   Stable LSD radix sort of 64-bit keys on bits [bit_lo, bit_hi), 8 bits per
-   pass, ping-ponging between the two buffers.  On return `keys` (and `vals`)
+   Stable LSD radix sort of 64-bit keys on bits [bit_lo, bit_hi), 8 or 9 bits
+   per pass, ping-ponging between the two buffers.  On return `keys` (and `vals`)
    hold the sorted data; `keys_alt`/`vals_alt` are scratch of the same size.
    vals may be empty (keys only). */
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,

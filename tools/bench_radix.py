@@ -1,6 +1,8 @@
 """Radix-sort pass timing on device (per-kernel CUDA events from the library's
 profile hooks) on uniform random keys.  Usage: python tools/bench_radix.py [n] [bit_hi] [pairs]
-TMR_RADIX_VARIANT selects the pass-kernel variant (read once per process)."""
+(The look-back / match.any variants this tool compared during round 1 are
+recorded in profiles/bench_radix_variants_r01.jsonl; the library now holds only
+the per-tile offset-table version.)"""
 import ctypes
 import json
 import os
@@ -41,7 +43,7 @@ def main():
     if pairs:
         ok = ok and bool(np.array_equal(keys[v], k))
     bytes_per = 16 + (8 if pairs else 0)
-    out = {"variant": os.environ.get("TMR_RADIX_VARIANT", "default"), "n": n, "bits": hi,
+    out = {"n": n, "bits": hi,
            "pairs": pairs, "sorted": ok, "kernels": prof}
     for name, st in (prof.items() if isinstance(prof, dict) else []):
         if "radix_pass" in name:
