@@ -46,6 +46,19 @@ def test_multirank_bernstein_order3(ranks, emu_lib, ref_lib):
     multirank.compare_rank_results(a, b, "bernstein3_r%d" % ranks)
 
 
+@pytest.mark.parametrize("ranks,interp", [(2, 1), (3, 2)])
+def test_multirank_order4(ranks, interp, emu_lib, ref_lib):
+    """Order 4 on several ranks: entity owners expanded to nodes, external
+    numbers requested per (entity, sub-node) (reference :4139-4232), remote
+    prolongation rows."""
+    conn = util.box_conn()
+    body = multirank.adapt_body(conn, 1, 2, 30, 1, 4, True, with_interp="repartitioned",
+                                interp=interp)
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_rank_results(a, b, "order4_r%d" % ranks)
+
+
 def test_public_distribute_octants(emu_lib, ref_lib):
     """distributeOctants / sendOctants as external callers use them (reference
     src/topology/TMR_TACSTopoCreator.cpp:166-217): route a sorted octant list

@@ -1655,15 +1655,42 @@ struct ExternalCountFn {
   }
 };
 
+/* orders >= 4: node-level copies of the entity owners */
+struct ExpandOwnerFn {
+  EntityMultFn mult;
+  const u32 *ent_off;
+  const int *ent_owner;
+  u32 *ent_of;
+  int *node_owner;
+  TMR_HD void operator()(i64 j) const {
+    const u32 m = mult(j), o = ent_off[j];
+    for (u32 k = 0; k < m; k++) {
+      ent_of[o + k] = (u32)j;
+      node_owner[o + k] = ent_owner[j];
+    }
+  }
+};
+
+/* orders >= 4: a request names the entity key and, in bits 56..63, which of
+   its nodes is meant */
+static const int kSubNodeShift = 56;
+
 struct ExternalFillFn {
   ExternalCountFn c;
   const u64 *node_keys;
   u64 *out_keys;
   u32 *out_dest;
   u32 *out_node;
+  const u32 *ent_of;  /* NULL below order 4 */
+  const u32 *ent_off;
   TMR_HD void operator()(i64 i, u32 o) const {
     if (c(i)) {
-      out_keys[o] = node_keys[i];
+      if (ent_of) {
+        const u32 e = ent_of[i];
+        out_keys[o] = node_keys[e] | ((u64)((u32)i - ent_off[e]) << kSubNodeShift);
+      } else {
+        out_keys[o] = node_keys[i];
+      }
       out_dest[o] = (u32)(c.owner[i] < 0 ? c.me : c.owner[i]);
       out_node[o] = (u32)i;
     }
@@ -1697,9 +1724,16 @@ struct LookupNumberFn { /* owner side: number of each requested node key */
   i64 n;
   const int *node_num;
   int *reply;
+  const u32 *ent_off; /* NULL below order 4 */
   TMR_HD void operator()(i64 i) const {
-    const i64 j = find_u64(node_keys, n, req[i]);
-    reply[i] = j >= 0 ? node_num[j] : -1;
+    if (ent_off) {
+      const u64 sub = req[i] >> kSubNodeShift;
+      const i64 j = find_u64(node_keys, n, req[i] & low_mask(kSubNodeShift));
+      reply[i] = j >= 0 ? node_num[ent_off[j] + sub] : -1;
+    } else {
+      const i64 j = find_u64(node_keys, n, req[i]);
+      reply[i] = j >= 0 ? node_num[j] : -1;
+    }
   }
 };
 
@@ -1731,14 +1765,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     return 1;
   }
   /* from order 4 on the sorted keys are entities, not nodes (see
-     EntityMultFn); single rank only for now */
+     EntityMultFn) */
   const bool general = order > 3;
-  if (general && comm) {
-    fprintf(stderr,
-            "TMROctForest Error: mesh orders above 3 are not available on more "
-            "than one rank yet\n");
-    return 1;
-  }
   const int gorder = general ? 3 : order; /* geometry: 2x2x2 or 3x3x3 positions */
   const int npe = order * order * order;
   const i64 E = f.n;
@@ -1772,7 +1800,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   const int bernstein = (interp_type == 2) ? 1 : 0;
   /* labels: reference initLabel :6798-6811 */
   nd.nfmt.lbits = (general || (bernstein && order >= 3)) ? 2 : 0;
-  if (nd.nfmt.total_bits() > 64 || nd.nfmt.Dn + 1 > 21) {
+  if (nd.nfmt.total_bits() > (general && comm ? kSubNodeShift : 64) ||
+      nd.nfmt.Dn + 1 > 21) {
     fprintf(stderr,
             "TMROctForest Error: node keys of %d trees at depth %d exceed the "
             "64-bit key budget of the CUDA path\n",
@@ -1879,7 +1908,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   /* orders >= 4: the scatter fills the entity table, ConnBuildFn the conn */
   DBuf<int> ent_conn;
   if (general) ent_conn.alloc(ctx, ngc);
-  DBuf<u32> ent_off;
+  DBuf<u32> ent_off, ent_of; /* entity -> first node, node -> entity */
   i64 Nn;
   DBuf<unsigned char> created;
   {
@@ -1906,7 +1935,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       sort_bbits = bits_for((int)nused);
     }
     ParentNodeGen pg = {f.keys.get(), fmask.get(), f.fmt,           nd.nfmt,
-                        f.tables,     order,       tree_dense.get()};
+                        f.tables,     gorder,      tree_dense.get()};
     if (comm) {
       poff.alloc(ctx, E);
       ParentNodeCountFn pc = {pg};
@@ -1994,23 +2023,6 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     nd.node_keys.alloc(ctx, Nn);
     copy_d2d(ctx, nd.node_keys.get(), ck_alt.get(), (size_t)Nn * sizeof(u64));
   }
-  if (general) {
-    /* entities -> nodes: Nn becomes the number of local NODES; node_keys
-       keeps one key per entity (stencil look-ups go through ent_off) */
-    const i64 nent = Nn;
-    ent_off.alloc(ctx, nent);
-    EntityMultFn em = {nd.node_keys.get(), order};
-    Nn = (i64)scan_counts(ctx, nent, em, ent_off.get(), "nodes_entity_offsets");
-    EntityNodes en = {f.tables, order};
-    ConnBuildFn cb = {f.keys.get(), f.fmt, en, ent_conn.get(), ent_off.get(),
-                      nd.conn.get()};
-    launch(ctx, E, cb, "nodes_conn_build");
-    ent_conn.reset();
-    if (Nn >= (1LL << 31)) {
-      fprintf(stderr, "TMROctForest Error: too many local nodes\n");
-      return 1;
-    }
-  }
   nd.num_local_nodes = Nn;
   trace_mark(ctx, "nodes: unique+conn");
 
@@ -2075,6 +2087,34 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     trace_mark(ctx, "nodes: ownership");
   }
 
+  if (general) {
+    /* entities -> nodes: Nn becomes the number of local NODES; node_keys
+       keeps one key per entity (stencil look-ups go through ent_off) */
+    const i64 nent = Nn;
+    ent_off.alloc(ctx, nent);
+    EntityMultFn em = {nd.node_keys.get(), order};
+    Nn = (i64)scan_counts(ctx, nent, em, ent_off.get(), "nodes_entity_offsets");
+    EntityNodes en = {f.tables, order};
+    ConnBuildFn cb = {f.keys.get(), f.fmt, en, ent_conn.get(), ent_off.get(),
+                      nd.conn.get()};
+    launch(ctx, E, cb, "nodes_conn_build");
+    ent_conn.reset();
+    if (Nn >= (1LL << 31)) {
+      fprintf(stderr, "TMROctForest Error: too many local nodes\n");
+      return 1;
+    }
+    if (comm) {
+      /* the owner of an entity owns all its nodes (reference :4139-4150) */
+      ent_of.alloc(ctx, Nn);
+      DBuf<int> owner_node(ctx, Nn);
+      ExpandOwnerFn eo = {em, ent_off.get(), owner.get(), ent_of.get(),
+                          owner_node.get()};
+      launch(ctx, nent, eo, "nodes_entity_owner");
+      owner.swap(owner_node);
+    }
+    nd.num_local_nodes = Nn;
+  }
+
   /* 3. dependent labels and numbering */
   DBuf<unsigned char> dep_flag(ctx, Nn);
   dev_zero(ctx, dep_flag.get(), (size_t)Nn);
@@ -2121,7 +2161,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     DBuf<u64> xk(ctx, Nn);
     DBuf<u32> xd(ctx, Nn), xn(ctx, Nn);
     ExternalCountFn xc = {dep_flag.get(), owner.get(), me};
-    ExternalFillFn xf = {xc, nd.node_keys.get(), xk.get(), xd.get(), xn.get()};
+    ExternalFillFn xf = {xc,       nd.node_keys.get(), xk.get(),     xd.get(),
+                         xn.get(), ent_of.get(),       ent_off.get()};
     const i64 nx = (i64)scan_apply(ctx, Nn, xc, xf, "nodes_external_list");
     U32DestFn xdest = {xd.get()};
     RoutePlan plan;
@@ -2129,8 +2170,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     DBuf<u64> req;
     route_array(ctx, *comm, plan, xk.get(), req);
     DBuf<int> rep(ctx, plan.nrecv);
-    LookupNumberFn lk = {req.get(), nd.node_keys.get(), Nn, nd.node_num.get(),
-                         rep.get()};
+    LookupNumberFn lk = {req.get(),         nd.node_keys.get(),
+                         nd.node_keys.size(), nd.node_num.get(),
+                         rep.get(),         general ? ent_off.get() : NULL};
     launch(ctx, plan.nrecv, lk, "nodes_external_lookup");
     DBuf<int> got;
     route_back(ctx, *comm, plan, rep.get(), got);
