@@ -132,6 +132,27 @@ def test_eval_interp(order, interp, impl, ref_lib):
                 np.testing.assert_allclose(y, x, rtol=1e-12, atol=1e-13)
 
 
+@pytest.mark.parametrize("order,interp,conn_name", [(5, 1, "box7"), (5, 2, "connector15"),
+                                                    (6, 1, "connector15"),
+                                                    (8, 1, "single"), (7, 0, "box7")])
+def test_high_order(order, interp, conn_name, impl, ref_lib):
+    """Orders 5..8 (kMaxOrder): same entity machinery as order 4, prolongation
+    to the next lower order.  Bernstein points stop at order 5: the reference's
+    eval_bernstein_weights has no table beyond it (src/TMRInterpolation.h:309-455)
+    and leaves the weights unset."""
+    conn = util.CONNS[conn_name]()
+    res = []
+    for lib in (ref_lib, impl):
+        f = util.build_forest(lib, conn, 0 if conn_name != "single" else 1, 2, 30, 1,
+                              order, interp=interp)
+        nodes = util.node_results(f)
+        low = f.duplicate()
+        low.setMeshOrder(order - 1, interp)
+        res.append((nodes, f.createInterpolation(low)))
+    util.assert_nodes_equal(res[0][0], res[1][0], "order %d" % order)
+    util.assert_interp_equal(res[0][1], res[1][1], "order %d -> %d" % (order, order - 1))
+
+
 def test_connectivity_tables(impl, ref_lib):
     """setConnectivity derives identical edge/face numbering, inverse maps,
     orientation ids (reference src/TMROctForest.cpp:558-1143)."""

@@ -522,14 +522,18 @@ TMR_HD void bernstein_subdivision_weights(int order, int u, double *N) {
 }
 
 /* Control point i of a degree-(p+1) curve expressed in the degree-p control
-   points of the same curve (degree elevation), p = coarse_order-1
-   (reference eval_bernstein_interp_weights, one order apart) */
+   points of the same curve (degree elevation), p = coarse_order-1: weights
+   i/(p+1) on point i-1 and (p+1-i)/(p+1) on point i (reference
+   eval_bernstein_interp_weights, src/TMRInterpolation.h:456-560, tabulated for
+   coarse orders 2..5).  The reference's table for coarse order 4 has the rows
+   of fine points 2 and 3 exchanged; a drop-in has to return what the
+   reference returns, so the exchange is reproduced here. */
 TMR_HD void bernstein_elevation_weights(int coarse_order, int i, double *N) {
   const int p = coarse_order - 1;
   for (int j = 0; j < coarse_order; j++) N[j] = 0.0;
-  const double a = (double)i / (double)(p + 1);
-  if (i > 0) N[i - 1] = a;
-  if (i <= p) N[i] = 1.0 - a;
+  if (coarse_order == 4 && (i == 2 || i == 3)) i = 5 - i;
+  if (i > 0) N[i - 1] = (double)i / (double)(p + 1);
+  if (i <= p) N[i] = (double)(p + 1 - i) / (double)(p + 1);
 }
 
 TMR_HD int popc32(u32 v) {

@@ -22,19 +22,19 @@
 
 namespace tmrgpu {
 
-/* mesh orders 2..4.  Orders 2 and 3 have one node per corner / edge / face /
-   block entity; from order 4 on an entity carries (order-2)^dim nodes that are
-   numbered consecutively and reached through the edge-reversal and
-   face-orientation permutations of reference createLocalConn
-   (src/TMROctForest.cpp:4660-4867).  The bound is the size of the per-thread
-   knot and basis arrays, nothing structural. */
-static const int kMaxOrder = 4;
+/* mesh orders 2..8 (the reference allows 16).  Orders 2 and 3 have one node per
+   corner / edge / face / block entity; from order 4 on an entity carries
+   (order-2)^dim nodes that are numbered consecutively and reached through the
+   edge-reversal and face-orientation permutations of reference
+   createLocalConn (src/TMROctForest.cpp:4660-4867).  The bound is the size of
+   the per-thread knot, basis and prolongation-row arrays, nothing structural. */
+static const int kMaxOrder = 8;
 
 struct NodeData {
   bool valid;
   int order;
   int interp_type;
-  double knots[4];
+  double knots[kMaxOrder];
   i64 num_elements;
   i64 num_local_nodes; /* unique node entries referenced on this rank */
   i64 num_dep_nodes;

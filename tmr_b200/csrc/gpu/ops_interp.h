@@ -147,7 +147,7 @@ struct FindEnclosingFn {
   EnclosingSearch s;
   const Oct24 *nodes;
   int order;
-  double knots[4];
+  double knots[kMaxOrder];
   int *out;
   TMR_HD void operator()(i64 i) const {
     const Oct24 q = nodes[i];
@@ -173,7 +173,7 @@ inline int find_enclosing_batch(Forest &f, int order, const double *knots,
   fe.s.cfmt = f.fmt;
   fe.nodes = d_nodes.get();
   fe.order = order;
-  for (int i = 0; i < 4; i++) fe.knots[i] = (i < order) ? knots[i] : 0.0;
+  for (int i = 0; i < kMaxOrder; i++) fe.knots[i] = (i < order) ? knots[i] : 0.0;
   fe.out = d_out.get();
   launch(ctx, n, fe, "find_enclosing");
   copy_d2h(ctx, h_out, d_out.get(), (size_t)n * sizeof(int));
@@ -222,16 +222,17 @@ struct InterpRow {
   const u64 *fkeys;
   KeyFmt ffmt;
   int forder;
-  double fknots[4];
+  double fknots[kMaxOrder];
   /* coarse */
   EnclosingSearch s;
   int corder;
-  double cknots[4];
+  double cknots[kMaxOrder];
   const int *cconn;
   const int *cdep_ptr;
   const int *cdep_conn;
   const double *cdep_w;
   int bernstein; /* both meshes use Bernstein points (reference :6434-6500) */
+  int *overflow; /* set if a row ever exceeded its buffer (see RowCap) */
 
   /* per-axis weights with the collapse rule (reference :6501-6548) */
   TMR_HD void axis(int i, i32 nx, i32 h, i32 ox, i32 hc, int *start, int *end,
@@ -270,7 +271,7 @@ struct InterpRow {
 
   /* builds the sorted, merged row of node j of fine element fkey inside coarse
      element t; returns its length */
-  TMR_HD int build(u64 fkey, int j, i64 t, int *idx, double *w) const {
+  TMR_HD int build(u64 fkey, int j, i64 t, int *idx, double *w, int cap) const {
     i32 block, x, y, z;
     int level;
     ffmt.decode(fkey, &block, &x, &y, &z, &level);
@@ -295,11 +296,11 @@ struct InterpRow {
           const int off = ii + jj * corder + kk * corder * corder;
           const double weight = Nu[ii] * Nv[jj] * Nw[kk];
           if (c[off] >= 0) {
-            n = insert(idx, w, n, c[off], weight);
+            n = insert(idx, w, n, cap, c[off], weight);
           } else {
             const int dn = -c[off] - 1;
             for (int jp = cdep_ptr[dn]; jp < cdep_ptr[dn + 1]; jp++) {
-              n = insert(idx, w, n, cdep_conn[jp], weight * cdep_w[jp]);
+              n = insert(idx, w, n, cap, cdep_conn[jp], weight * cdep_w[jp]);
             }
           }
         }
@@ -310,11 +311,16 @@ struct InterpRow {
 
   /* sorted insert with duplicate columns summed
      (TMRIndexWeight::uniqueSort, reference src/TMRBase.h:112-135) */
-  TMR_HD int insert(int *idx, double *w, int n, int col, double val) const {
+  TMR_HD int insert(int *idx, double *w, int n, int cap, int col,
+                    double val) const {
     int p = n;
     while (p > 0 && idx[p - 1] > col) p--;
     if (p > 0 && idx[p - 1] == col) {
       w[p - 1] += val;
+      return n;
+    }
+    if (n >= cap) {
+      TMR_ATOMIC_OR_I32(overflow, 1);
       return n;
     }
     for (int q = n; q > p; q--) {
@@ -369,11 +375,19 @@ struct InterpLocateRecvFn {
   }
 };
 
-/* longest possible row: every coarse node of the element a dependent node
-   with a full face stencil, corder^3 * corder^2 = corder^5 (reference :6637) */
+/* Capacity of the merged row buffer.  The reference allocates corder^5 (every
+   coarse node dependent with a full face stencil, :6637), but the buffer here
+   is kept sorted and duplicate-free at every insertion, so it never holds more
+   than the DISTINCT columns a row can name: the coarse element's own nodes
+   (corder^3) plus the nodes of the parent's faces and edges its dependent
+   nodes hang on -- at most the 3 faces and 3 edges meeting at the child's
+   corner (3 corder^2 + 3 corder).  An overflow would be a logic error; it is
+   caught (the entry is dropped and the error flag raised), never written past
+   the buffer. */
 template <int kCOrder>
 struct RowCap {
-  static const int value = (kCOrder == 2) ? 32 : (kCOrder == 3 ? 243 : 1024);
+  static const int value =
+      kCOrder * kCOrder * kCOrder + 3 * kCOrder * kCOrder + 3 * kCOrder + 2;
 };
 
 /* row lengths, one thread per row (a plain launch: the build is far too heavy
@@ -390,7 +404,8 @@ struct InterpCountFn {
     }
     int idx[RowCap<kCOrder>::value];
     double w[RowCap<kCOrder>::value];
-    count[row] = (u32)r.build(q.fkey[row], q.j[row], q.t[row], idx, w);
+    count[row] = (u32)r.build(q.fkey[row], q.j[row], q.t[row], idx, w,
+                              RowCap<kCOrder>::value);
   }
 };
 struct StoredCountFn {
@@ -408,7 +423,8 @@ struct InterpFillFn {
     if (q.t[row] < 0) return;
     int idx[RowCap<kCOrder>::value];
     double w[RowCap<kCOrder>::value];
-    const int n = r.build(q.fkey[row], q.j[row], q.t[row], idx, w);
+    const int n = r.build(q.fkey[row], q.j[row], q.t[row], idx, w,
+                          RowCap<kCOrder>::value);
     for (int k = 0; k < n; k++) {
       cols[o + k] = idx[k];
       vals[o + k] = w[k];
@@ -450,7 +466,7 @@ struct MissFillFn {
   const i64 *t;
   KeyFmt ffmt;
   int forder;
-  double fknots[4];
+  double fknots[kMaxOrder];
   OwnerMap om;
   int D;
   u64 *out_key;
@@ -515,7 +531,7 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   r.ffmt = fine.fmt;
   r.forder = fn.order;
   r.corder = cn.order;
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < kMaxOrder; i++) {
     r.fknots[i] = fn.knots[i];
     r.cknots[i] = cn.knots[i];
   }
@@ -527,6 +543,9 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   r.cdep_conn = cn.dep_conn.get();
   r.cdep_w = cn.dep_weights.get();
   r.bernstein = (fn.interp_type == 2 && cn.interp_type == 2) ? 1 : 0;
+  DBuf<int> row_overflow(ctx, 1);
+  dev_zero(ctx, row_overflow.get(), sizeof(int));
+  r.overflow = row_overflow.get();
   if (r.bernstein && fn.order - cn.order > 1) {
     fprintf(stderr,
             "TMROctForest Error: Mesh order difference across grids should be "
@@ -573,7 +592,7 @@ inline int create_interp(Forest &fine, Forest &coarse) {
     mf.t = q_t.get();
     mf.ffmt = fine.fmt;
     mf.forder = fn.order;
-    for (int i = 0; i < 4; i++) mf.fknots[i] = fn.knots[i];
+    for (int i = 0; i < kMaxOrder; i++) mf.fknots[i] = fn.knots[i];
     mf.om = om;
     mf.D = coarse.fmt.D;
     mf.out_key = mk.get();
@@ -642,16 +661,22 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   }
   RowRequests q = {q_fkey.get(), q_j.get(), q_t.get()};
   DBuf<u32> off(ctx, nrows), cnt(ctx, nrows);
-  if (r.corder == 2) {
-    InterpCountFn<2> cf = {r, q, cnt.get()};
-    launch(ctx, nrows, cf, "interp_row_count");
-  } else if (r.corder == 3) {
-    InterpCountFn<3> cf = {r, q, cnt.get()};
-    launch(ctx, nrows, cf, "interp_row_count");
-  } else {
-    InterpCountFn<4> cf = {r, q, cnt.get()};
-    launch(ctx, nrows, cf, "interp_row_count");
+  /* corder is a template parameter only to size the per-thread row buffer */
+#define TMR_INTERP_COUNT(C)                          \
+  {                                                  \
+    InterpCountFn<C> cf = {r, q, cnt.get()};         \
+    launch(ctx, nrows, cf, "interp_row_count");      \
   }
+  switch (r.corder) {
+    case 2: TMR_INTERP_COUNT(2) break;
+    case 3: TMR_INTERP_COUNT(3) break;
+    case 4: TMR_INTERP_COUNT(4) break;
+    case 5: TMR_INTERP_COUNT(5) break;
+    case 6: TMR_INTERP_COUNT(6) break;
+    case 7: TMR_INTERP_COUNT(7) break;
+    default: TMR_INTERP_COUNT(8) break;
+  }
+#undef TMR_INTERP_COUNT
   StoredCountFn sc = {cnt.get()};
   const u64 nnz = scan_counts(ctx, nrows, sc, off.get(), "interp_row_offsets");
   cnt.reset();
@@ -661,18 +686,31 @@ inline int create_interp(Forest &fine, Forest &coarse) {
   I.cols.alloc(ctx, (i64)nnz);
   I.vals.alloc(ctx, (i64)nnz);
   /* offsets are known: replay the build and store */
-  if (r.corder == 2) {
-    InterpFillFn<2> ffn = {r, q, I.cols.get(), I.vals.get()};
-    InterpFillPlaceFn<2> pl = {ffn, off.get()};
-    launch(ctx, nrows, pl, "interp_row_fill");
-  } else if (r.corder == 3) {
-    InterpFillFn<3> ffn = {r, q, I.cols.get(), I.vals.get()};
-    InterpFillPlaceFn<3> pl = {ffn, off.get()};
-    launch(ctx, nrows, pl, "interp_row_fill");
-  } else {
-    InterpFillFn<4> ffn = {r, q, I.cols.get(), I.vals.get()};
-    InterpFillPlaceFn<4> pl = {ffn, off.get()};
-    launch(ctx, nrows, pl, "interp_row_fill");
+#define TMR_INTERP_FILL(C)                                      \
+  {                                                             \
+    InterpFillFn<C> ffn = {r, q, I.cols.get(), I.vals.get()};   \
+    InterpFillPlaceFn<C> pl = {ffn, off.get()};                 \
+    launch(ctx, nrows, pl, "interp_row_fill");                  \
+  }
+  switch (r.corder) {
+    case 2: TMR_INTERP_FILL(2) break;
+    case 3: TMR_INTERP_FILL(3) break;
+    case 4: TMR_INTERP_FILL(4) break;
+    case 5: TMR_INTERP_FILL(5) break;
+    case 6: TMR_INTERP_FILL(6) break;
+    case 7: TMR_INTERP_FILL(7) break;
+    default: TMR_INTERP_FILL(8) break;
+  }
+#undef TMR_INTERP_FILL
+  {
+    int h_overflow = 0;
+    copy_d2h(ctx, &h_overflow, row_overflow.get(), sizeof(int));
+    if (h_overflow) {
+      fprintf(stderr,
+              "TMROctForest Error: a prolongation row exceeded its buffer "
+              "(RowCap)\n");
+      ctx.last_error = "interpolation row overflow";
+    }
   }
   I.rows.swap(q_num);
   I.rows.set_size(nrows);

@@ -1177,7 +1177,7 @@ struct DepFillFn {
   NodeFmt nfmt;
   ConnTables t;
   int order;
-  double knots[4];
+  double knots[kMaxOrder];
   const u64 *node_keys;
   i64 num_nodes;
   const int *node_num;
@@ -1784,7 +1784,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   nd.clear();
   nd.order = order;
   nd.interp_type = interp_type;
-  for (int i = 0; i < 4; i++) nd.knots[i] = (i < order) ? knots[i] : 0.0;
+  for (int i = 0; i < kMaxOrder; i++) nd.knots[i] = (i < order) ? knots[i] : 0.0;
   nd.num_elements = E;
   if (comm) {
     /* the key depth must agree on every rank */
@@ -2224,7 +2224,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.nfmt = nd.nfmt;
     fill.t = f.tables;
     fill.order = order;
-    for (int i = 0; i < 4; i++) fill.knots[i] = nd.knots[i];
+    for (int i = 0; i < kMaxOrder; i++) fill.knots[i] = nd.knots[i];
     fill.node_keys = nd.node_keys.get();
     fill.num_nodes = nd.node_keys.size();
     fill.node_num = nd.node_num.get();
