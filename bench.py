@@ -507,10 +507,11 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
             "vs_baseline": None,
-            "dtype": "int32 keys as u64 Morton + f64 weights", "data": "synthetic",
+            "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(cfg) if args.workload == "c2" else
                        "%d-tree tiled butterfly forest (all 8 face orientations, irregular valence), createTrees(%d), %d passes pct=%d, last cycle refine+balance(1)+createNodes(order 2)"
                        % (len(block_conn), cfg["level"], cfg["passes"], cfg["pct"]),
+                       "arithmetic": "u64 Morton keys, int32 connectivity, f64 stencil weights",
                        "trees": int(len(block_conn)),
                        "octants_in": int(e_in), "octants_out_per_gpu": int(e_final),
                        "local_nodes": int(sizes[1]), "dep_nodes": int(sizes[2]),

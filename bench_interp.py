@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None):
+def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None, api=True):
     import util
     from tmr_b200.forest import OctForest
 
@@ -67,11 +67,20 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None):
             sync()
             t_dev = time.perf_counter() - t_a
             t2 = time.perf_counter()
-        vec = fine.createInterpolation(coarse)
-        sync()
-        t3 = time.perf_counter()
-        rows, rowp, cols, vals = vec.get()
-        sums = np.add.reduceat(vals, rowp[:-1]) if len(rows) else np.zeros(0)
+        if api:
+            vec = fine.createInterpolation(coarse)
+            sync()
+            t3 = time.perf_counter()
+            rows, rowp, cols, vals = vec.get()
+        else:
+            t3 = t2
+            a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+            lib.tmrgpu_create_interp(ctypes.c_void_p(lib.tmr_b200_device_forest(fine._ptr)),
+                                     ctypes.c_void_p(lib.tmr_b200_device_forest(coarse._ptr)),
+                                     ctypes.byref(a), ctypes.byref(b))
+            rows, cols = np.zeros(a.value, np.int8), np.zeros(b.value, np.int8)
+            rowp, vals = np.zeros(1, np.int64), np.zeros(0)
+        sums = np.add.reduceat(vals, rowp[:-1]) if (api and len(rows)) else np.zeros(0)
         out.append({
             "level": k, "fine_order": fine.getMeshOrder(), "coarse_order": coarse.getMeshOrder(),
             "fine_octants": fine.getNumOctants(), "coarse_octants": coarse.getNumOctants(),
@@ -80,7 +89,7 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None):
             "create_interp_s": t3 - t2, "rows_per_s": len(rows) / max(t3 - t2, 1e-9),
             "device_csr_s": t_dev,
             "device_rows_per_s": (len(rows) / t_dev) if t_dev else None,
-            "max_rowsum_err": float(np.abs(sums - 1).max()) if len(rows) else 0.0,
+            "max_rowsum_err": float(np.abs(sums - 1).max()) if len(sums) else None,
         })
     return out
 
@@ -143,7 +152,8 @@ def main():
         lib.tmrgpu_profile_json.argtypes = [P, ctypes.c_char_p, ctypes.c_int]
         lib.tmrgpu_profile_reset(ctx)
         lib.tmrgpu_profile_enable(ctx, 1)
-    gpu = hierarchy(lib, args.level, args.passes, args.pct, sync, dev_flags, dev_interp)
+    gpu = hierarchy(lib, args.level, args.passes, args.pct, sync, dev_flags, dev_interp,
+                    api=not args.no_api)
     if args.profile_out:
         buf = ctypes.create_string_buffer(1 << 16)
         lib.tmrgpu_profile_json(ctx, buf, len(buf))
