@@ -1171,7 +1171,7 @@ struct ConnBuildFn {
 };
 
 /* createDependentConn pass 3 (reference :5272-5508) */
-struct DepFillFn {
+struct DepFillData {
   const u64 *keys;
   KeyFmt fmt;
   NodeFmt nfmt;
@@ -1202,6 +1202,13 @@ struct DepFillFn {
      entity index == node index) and the sub-node permutations */
   const u32 *ent_off;
   EntityNodes en;
+};
+
+/* kOrder = 2 or 3 compiles the label-free fast paths only (the order-2 kernel
+   is one of the five largest of the cycle); 0 = run-time order incl. the
+   entity look-ups of orders >= 4 */
+template <int kOrder>
+struct DepFillFn : DepFillData {
 
   /* entity at (block,x,y,z) with `label` -> first local node (or -1) */
   TMR_HD i64 entity_base(i32 block, i32 x, i32 y, i32 z, int label) const {
@@ -1297,7 +1304,7 @@ struct DepFillFn {
   }
   /* first element of e's family if that family is complete, else -1 */
   TMR_HD i64 family_base(i64 e) const {
-    if (order != 2) return -1;
+    if (kOrder != 2) return -1;
     int m;
     return fam.in_family(e, &m) ? e - m : -1;
   }
@@ -1307,6 +1314,8 @@ struct DepFillFn {
   }
 
   TMR_HD void operator()(i64 d) const {
+    const int order = kOrder ? kOrder : DepFillData::order;
+    const bool general = (kOrder == 0) && ent_off != NULL;
     const int ptr = dep_ptr[d];
     if (win_edge[d]) {
       const u64 code = win_edge[d] - 1;
@@ -1325,8 +1334,8 @@ struct DepFillFn {
       const int s = ed & 3;
       const i32 ta = hp * (s & 1), tb = hp * (s >> 1);
       const i64 e0 = family_base(e);
-      if (ent_off) edge_nodes_general(block, px, py, pz, hp, ed, dep_conn + ptr);
-      for (int ii = 0; ii < order && !ent_off; ii++) {
+      if (general) edge_nodes_general(block, px, py, pz, hp, ed, dep_conn + ptr);
+      for (int ii = 0; ii < order && !general; ii++) {
         if (e0 >= 0) {
           const int sa = s & 1, sb = s >> 1;
           const int c = ed < 4 ? (ii + 2 * sa + 4 * sb)
@@ -1371,8 +1380,8 @@ struct DepFillFn {
       const i32 step = hp / (order - 1);
       const i32 nn = hp * (f & 1);
       const i64 e0 = family_base(e);
-      if (ent_off) face_nodes_general(block, px, py, pz, hp, f, dep_conn + ptr);
-      for (int q = 0; q < order && !ent_off; q++) {
+      if (general) face_nodes_general(block, px, py, pz, hp, f, dep_conn + ptr);
+      for (int q = 0; q < order && !general; q++) {
         for (int p = 0; p < order; p++) {
           if (e0 >= 0) {
             const int n1 = f & 1;
@@ -1399,7 +1408,7 @@ struct DepFillFn {
       const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
       const int b1 = (f < 2) ? by : bx;
       const int b2 = (f < 4) ? bz : by;
-      double Nu[kMaxOrder], Nv[kMaxOrder];
+      double Nu[kOrder ? kOrder : kMaxOrder], Nv[kOrder ? kOrder : kMaxOrder];
       if (bernstein) {
         /* reference :5453-5473 */
         bernstein_subdivision_weights(order, -(order - 1) + ii + (order - 1) * b1, Nu);
@@ -2215,7 +2224,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     nd.dep_conn.alloc(ctx, (i64)nnz);
     nd.dep_weights.alloc(ctx, (i64)nnz);
     DBuf<u32> node_index_store;
-    DepFillFn fill;
+    DepFillData fill;
     fill.node_ix = build_key_index(ctx, nd.node_keys.get(), nd.node_keys.size(),
                                    (u64)f.nblocks << nd.nfmt.pos_bits(),
                                    node_index_store);
@@ -2245,7 +2254,19 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.dep_ptr = nd.dep_ptr.get();
     fill.dep_conn = nd.dep_conn.get();
     fill.dep_weights = nd.dep_weights.get();
-    launch(ctx, Nd, fill, "nodes_dep_fill");
+    if (order == 2) {
+      DepFillFn<2> k;
+      static_cast<DepFillData &>(k) = fill;
+      launch(ctx, Nd, k, "nodes_dep_fill");
+    } else if (order == 3) {
+      DepFillFn<3> k;
+      static_cast<DepFillData &>(k) = fill;
+      launch(ctx, Nd, k, "nodes_dep_fill");
+    } else {
+      DepFillFn<0> k;
+      static_cast<DepFillData &>(k) = fill;
+      launch(ctx, Nd, k, "nodes_dep_fill");
+    }
   } else {
     dev_zero(ctx, nd.dep_ptr.get(), sizeof(int));
     nd.dep_nnz = 0;
