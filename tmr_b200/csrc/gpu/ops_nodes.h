@@ -1458,12 +1458,27 @@ struct KeyToNumFn {
 };
 
 /* getNodeNumbers(): every local node number, ascending (reference :4246) */
+struct NumberRangeFn {
+  int first;
+  int *out;
+  TMR_HD void operator()(i64 i) const { out[i] = first + (int)i; }
+};
+
 inline int sorted_node_numbers(Forest &f, int *h_out) {
   Ctx &ctx = *f.ctx;
   NodeData &nd = f.nodes;
   const i64 n = nd.num_local_nodes;
   if (!nd.valid) return 1;
   if (n == 0) return 0;
+  if (!ctx.comm) {
+    /* one rank: the numbers are -Nd..-1 (dependent) and 0..owned-1, every
+       value once -- the sorted array is a range, no sort needed */
+    DBuf<int> out(ctx, n);
+    NumberRangeFn r = {-(int)nd.num_dep_nodes, out.get()};
+    launch(ctx, n, r, "nodes_number_range");
+    copy_d2h(ctx, h_out, out.get(), (size_t)n * sizeof(int));
+    return check_errors(ctx, "sorted_node_numbers");
+  }
   DBuf<u64> k(ctx, n), k_alt(ctx, n);
   DBuf<u32> v0, v1;
   NumToKeyFn a = {nd.node_num.get(), k.get()};
@@ -1558,16 +1573,6 @@ struct OwnerMinFn { /* scan_apply body over the key-sorted received items */
 };
 
 /* owner of a node whose home is this rank starts as "me if I create it" */
-struct OwnerInitFn {
-  NodeHomeFn home;
-  int me;
-  const unsigned char *created;
-  int *owner;
-  TMR_HD void operator()(i64 i) const {
-    owner[i] = (home(i) == me && created[i]) ? me : 0x7fffffff;
-  }
-};
-
 struct ForeignNodeCountFn {
   NodeHomeFn home;
   int me;
@@ -1583,8 +1588,10 @@ struct ForeignNodeFillFn {
   u32 *out_dest;
   u32 *out_index;
   unsigned char *out_created;
+  int *owner; /* also initialised here: one pass over the nodes instead of two */
   TMR_HD void operator()(i64 i, u32 o) const {
     const int d = home(i);
+    owner[i] = (d == me && created[i]) ? me : 0x7fffffff;
     if (d != me) {
       out_key[o] = node_keys[i];
       out_dest[o] = (u32)d;
@@ -1684,28 +1691,6 @@ struct ExpandOwnerFn {
    its nodes is meant */
 static const int kSubNodeShift = 56;
 
-struct ExternalFillFn {
-  ExternalCountFn c;
-  const u64 *node_keys;
-  u64 *out_keys;
-  u32 *out_dest;
-  u32 *out_node;
-  const u32 *ent_of;  /* NULL below order 4 */
-  const u32 *ent_off;
-  TMR_HD void operator()(i64 i, u32 o) const {
-    if (c(i)) {
-      if (ent_of) {
-        const u32 e = ent_of[i];
-        out_keys[o] = node_keys[e] | ((u64)((u32)i - ent_off[e]) << kSubNodeShift);
-      } else {
-        out_keys[o] = node_keys[i];
-      }
-      out_dest[o] = (u32)(c.owner[i] < 0 ? c.me : c.owner[i]);
-      out_node[o] = (u32)i;
-    }
-  }
-};
-
 struct NumberNodesMultiFn {
   const unsigned char *dep_flag;
   const u32 *dep_before;
@@ -1726,6 +1711,33 @@ struct NumberNodesMultiFn {
     }
   }
 };
+
+/* lists the nodes owned elsewhere and, in the same pass, numbers every node
+   (NumberNodesMultiFn) */
+struct ExternalFillFn {
+  ExternalCountFn c;
+  NumberNodesMultiFn number;
+  const u64 *node_keys;
+  u64 *out_keys;
+  u32 *out_dest;
+  u32 *out_node;
+  const u32 *ent_of;  /* NULL below order 4 */
+  const u32 *ent_off;
+  TMR_HD void operator()(i64 i, u32 o) const {
+    number(i);
+    if (c(i)) {
+      if (ent_of) {
+        const u32 e = ent_of[i];
+        out_keys[o] = node_keys[e] | ((u64)((u32)i - ent_off[e]) << kSubNodeShift);
+      } else {
+        out_keys[o] = node_keys[i];
+      }
+      out_dest[o] = (u32)(c.owner[i] < 0 ? c.me : c.owner[i]);
+      out_node[o] = (u32)i;
+    }
+  }
+};
+
 
 struct LookupNumberFn { /* owner side: number of each requested node key */
   const u64 *req;
@@ -2044,15 +2056,14 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   if (comm) {
     owner.alloc(ctx, Nn);
     NodeHomeFn home = {nd.node_keys.get(), nd.nfmt.Dn, nd.nfmt.lbits, om_n};
-    OwnerInitFn oi = {home, me, created.get(), owner.get()};
-    launch(ctx, Nn, oi, "nodes_owner_init");
     /* foreign-home nodes: (key, created, local index) */
     DBuf<u64> fk(ctx, Nn);
     DBuf<u32> fd(ctx, Nn), fi(ctx, Nn);
     DBuf<unsigned char> fcr(ctx, Nn);
     ForeignNodeCountFn fnc = {home, me};
-    ForeignNodeFillFn fnf = {home, me, nd.node_keys.get(), created.get(),
-                             fk.get(), fd.get(), fi.get(), fcr.get()};
+    ForeignNodeFillFn fnf = {home,     me,       nd.node_keys.get(), created.get(),
+                             fk.get(), fd.get(), fi.get(),           fcr.get(),
+                             owner.get()};
     const i64 nf = (i64)scan_apply(ctx, Nn, fnc, fnf, "nodes_foreign_home_list");
     U32DestFn fdest = {fd.get()};
     RoutePlan plan;
@@ -2165,13 +2176,12 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     NumberNodesMultiFn num = {dep_flag.get(), dep_before.get(), owned_before.get(),
                               owner.get(),    me,               (int)start,
                               nd.node_num.get(), dep_node.get()};
-    launch(ctx, Nn, num, "nodes_number");
     /* numbers of the nodes owned elsewhere (reference :4183-4235) */
     DBuf<u64> xk(ctx, Nn);
     DBuf<u32> xd(ctx, Nn), xn(ctx, Nn);
     ExternalCountFn xc = {dep_flag.get(), owner.get(), me};
-    ExternalFillFn xf = {xc,       nd.node_keys.get(), xk.get(),     xd.get(),
-                         xn.get(), ent_of.get(),       ent_off.get()};
+    ExternalFillFn xf = {xc,       num,      nd.node_keys.get(), xk.get(),
+                         xd.get(), xn.get(), ent_of.get(),       ent_off.get()};
     const i64 nx = (i64)scan_apply(ctx, Nn, xc, xf, "nodes_external_list");
     U32DestFn xdest = {xd.get()};
     RoutePlan plan;
