@@ -161,35 +161,24 @@ struct ForeignCountFn {
   int me;
   TMR_HD u32 operator()(i64 i) const { return dest(i) != me ? 1u : 0u; }
 };
+/* one pass splits the array: foreign keys (with their destination) are packed
+   at their foreign rank `o`, the keys that stay at i - o */
 template <class DestFn>
-struct LocalCountFn {
-  DestFn dest;
-  int me;
-  TMR_HD u32 operator()(i64 i) const { return dest(i) == me ? 1u : 0u; }
-};
-template <class DestFn>
-struct ForeignKeyFillFn {
+struct SplitKeysFn {
   DestFn dest;
   int me;
   const u64 *keys;
-  u64 *out_keys;
-  u32 *out_dest;
+  u64 *foreign_keys;
+  u32 *foreign_dest;
+  u64 *local_keys;
   TMR_HD void operator()(i64 i, u32 o) const {
     const int d = dest(i);
     if (d != me) {
-      out_keys[o] = keys[i];
-      out_dest[o] = (u32)d;
+      foreign_keys[o] = keys[i];
+      foreign_dest[o] = (u32)d;
+    } else {
+      local_keys[i - (i64)o] = keys[i];
     }
-  }
-};
-template <class DestFn>
-struct LocalKeyFillFn {
-  DestFn dest;
-  int me;
-  const u64 *keys;
-  u64 *out_keys;
-  TMR_HD void operator()(i64 i, u32 o) const {
-    if (dest(i) == me) out_keys[o] = keys[i];
   }
 };
 struct DestArrayFn {
@@ -203,24 +192,25 @@ template <class DestFn>
 i64 route_keys_sparse(Ctx &ctx, Comm &comm, const u64 *keys, i64 n, DestFn dest,
                       DBuf<u64> &out) {
   const int me = comm.rank;
-  DBuf<u64> fk(ctx, n);
+  DBuf<u64> fk(ctx, n), loc(ctx, n);
   DBuf<u32> fd(ctx, n);
   ForeignCountFn<DestFn> fc = {dest, me};
-  ForeignKeyFillFn<DestFn> ff = {dest, me, keys, fk.get(), fd.get()};
-  const i64 nf = (i64)scan_apply(ctx, n, fc, ff, "route_foreign_compact");
+  SplitKeysFn<DestFn> sp = {dest, me, keys, fk.get(), fd.get(), loc.get()};
+  const i64 nf = (i64)scan_apply(ctx, n, fc, sp, "route_split");
   DestArrayFn da = {fd.get()};
   RoutePlan plan;
   make_route(ctx, comm, nf, da, plan);
   DBuf<u64> got;
   route_array(ctx, comm, plan, fk.get(), got);
   const i64 nloc = n - nf;
-  out.alloc(ctx, nloc + plan.nrecv);
-  LocalCountFn<DestFn> lc = {dest, me};
-  LocalKeyFillFn<DestFn> lf = {dest, me, keys, out.get()};
-  scan_apply(ctx, n, lc, lf, "route_local_compact");
-  if (plan.nrecv) {
-    copy_d2d(ctx, out.get() + nloc, got.get(), (size_t)plan.nrecv * sizeof(u64));
+  if (plan.nrecv == 0) {
+    out.swap(loc);
+    out.set_size(nloc);
+    return nloc;
   }
+  out.alloc(ctx, nloc + plan.nrecv);
+  copy_d2d(ctx, out.get(), loc.get(), (size_t)nloc * sizeof(u64));
+  copy_d2d(ctx, out.get() + nloc, got.get(), (size_t)plan.nrecv * sizeof(u64));
   return nloc + plan.nrecv;
 }
 
