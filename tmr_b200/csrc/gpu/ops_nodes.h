@@ -473,20 +473,26 @@ struct NodeEmit {
     *m = digit_of(keys[e]);
     return families && leader(e - *m);
   }
-  /* A member (a,b,c) of a complete family emits its corner (di,dj,dk) unless
-     some axis has d=1 with the member on the low side: that point is corner
-     d=0 of the next sibling.  Member (a,b,c) thus emits (1+a)(1+b)(1+c)
-     corners and the family 27 in total, spread over its 8 threads. */
+  /* A member (a,b,c) of a complete family emits its node (i,j,k) unless some
+     axis has the LAST index (order-1) with the member on the low side: that
+     point is index 0 of the next sibling.  Per axis the two siblings emit
+     order-1 and order positions, so the family emits (2 order - 1)^3 distinct
+     nodes (27 at order 2, 125 at order 3) instead of 8 order^3, spread over
+     its 8 threads. */
   TMR_HD u32 count(i64 e) const {
-    if (!families) return (u32)(order * order * order);
+    const int n = order;
+    if (!families) return (u32)(n * n * n);
     int m;
-    if (!in_family(e, &m)) return 8;
-    return (u32)((1 + ((m >> 2) & 1)) * (1 + ((m >> 1) & 1)) * (1 + (m & 1)));
+    if (!in_family(e, &m)) return (u32)(n * n * n);
+    return (u32)((n - 1 + ((m >> 2) & 1)) * (n - 1 + ((m >> 1) & 1)) *
+                 (n - 1 + (m & 1)));
   }
 
-  /* payload encoding */
+  /* payload encoding: (element, slot); family mode keeps the slot in the low
+     3 (order 2) or 5 (order 3) bits */
+  TMR_HD int slot_bits() const { return order == 2 ? 3 : 5; }
   TMR_HD u64 payload(i64 e, int code) const {
-    return families ? (((u64)e << 3) | (u64)code)
+    return families ? (((u64)e << slot_bits()) | (u64)code)
                     : ((u64)e * (u64)(order * order * order) + (u64)code);
   }
 
@@ -555,7 +561,10 @@ struct NodeEmit {
       for (int jj = 0; jj < np; jj++) {
         TMR_UNROLL
         for (int ii = 0; ii < np; ii++) {
-          if (fam && ((ii && !bx) || (jj && !by) || (kk && !bz))) continue;
+          if (fam && ((ii == np - 1 && !bx) || (jj == np - 1 && !by) ||
+                      (kk == np - 1 && !bz))) {
+            continue;
+          }
           const int label = lb ? slot_label(np, ii, jj, kk) : 0;
           u64 key;
           if (interior) {
@@ -594,6 +603,7 @@ struct CandStore {
   }
 };
 
+template <int kOrder>
 struct NodeEmitFillFn {
   NodeEmit g;
   u64 *out_keys;
@@ -601,7 +611,7 @@ struct NodeEmitFillFn {
   int pshift;
   TMR_HD void operator()(i64 e, u32 o) const {
     CandStore s = {out_keys + o, out_vals ? out_vals + o : (u32 *)0, pshift};
-    g.template run_order<2>(e, s); /* family emission is order 2 only */
+    g.template run_order<kOrder>(e, s);
   }
 };
 
@@ -667,31 +677,37 @@ struct NodeScatterFn {
       conn_local[p] = (int)run;
       return;
     }
-    const i64 e = (i64)(p >> 3);
-    const int cc = (int)(p & 7);
+    const int np = g.order, npe = np * np * np, sb = g.slot_bits();
+    const i64 e = (i64)(p >> sb);
+    const int slot = (int)(p & ((1u << sb) - 1u));
     int m;
     if (!g.in_family(e, &m)) {
-      conn_local[e * 8 + cc] = (int)run;
+      conn_local[e * npe + slot] = (int)run;
       return;
     }
-    /* shared node of a complete family: fan out to every sibling that has it
-       as a corner.  e is the representative sibling; its child digit gives
-       the family's first element.  (Measured alternative: one store into a
-       per-family 3x3x3 table plus an expansion kernel -- scatter 5.8 -> 4.5 ms
-       but the expansion cost 5.8 ms with one thread per family; an
-       out-of-place expansion moves as many bytes as it saves.) */
+    /* node of a complete family: fan out to every sibling that holds it.  e is
+       the emitting sibling, its child digit gives the family's first element
+       and the node's position 0..2(np-1) on the family's grid; a sibling on
+       side a of an axis holds grid position q at index q - a (np-1).
+       (Measured alternative: one store into a per-family node table plus an
+       expansion kernel -- scatter 5.8 -> 4.5 ms but the expansion cost 5.8 ms
+       with one thread per family; an out-of-place expansion moves as many
+       bytes as it saves.) */
     const i64 e0 = e - m;
-    const int pi = ((m >> 2) & 1) + (cc & 1);       /* node position 0..2 */
-    const int pj = ((m >> 1) & 1) + ((cc >> 1) & 1);
-    const int pk = (m & 1) + (cc >> 2);
+    const int qi = (np - 1) * ((m >> 2) & 1) + slot % np;
+    const int qj = (np - 1) * ((m >> 1) & 1) + (slot / np) % np;
+    const int qk = (np - 1) * (m & 1) + slot / (np * np);
     for (int a = 0; a < 2; a++) {
-      if (pi - a < 0 || pi - a > 1) continue;
+      const int ia = qi - a * (np - 1);
+      if (ia < 0 || ia > np - 1) continue;
       for (int b = 0; b < 2; b++) {
-        if (pj - b < 0 || pj - b > 1) continue;
+        const int jb = qj - b * (np - 1);
+        if (jb < 0 || jb > np - 1) continue;
         for (int c = 0; c < 2; c++) {
-          if (pk - c < 0 || pk - c > 1) continue;
-          conn_local[(e0 + 4 * a + 2 * b + c) * 8 + (pi - a) + 2 * (pj - b) +
-                     4 * (pk - c)] = (int)run;
+          const int kc = qk - c * (np - 1);
+          if (kc < 0 || kc > np - 1) continue;
+          conn_local[(e0 + 4 * a + 2 * b + c) * npe + ia + np * jb + np * np * kc] =
+              (int)run;
         }
       }
     }
@@ -1505,12 +1521,13 @@ struct NodeEmitPackedFn {
   template <class Sink>
   TMR_HD void operator()(i64 e, Sink &sink) const {
     PackedEmit<Sink> pe = {sink, pshift};
-    g.template run_order<2>(e, pe); /* family emission is order 2 only */
+    g.template run_order<2>(e, pe); /* staged path: 8 outputs per item at most */
   }
 };
 
+template <int kOrder>
 struct NodeEmitPlaceFn {
-  NodeEmitFillFn fill;
+  NodeEmitFillFn<kOrder> fill;
   const u32 *off;
   TMR_HD void operator()(i64 e) const { fill(e, off[e]); }
 };
@@ -1963,9 +1980,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       nextra = (i64)scan_counts(ctx, E, pc, poff.get(), "nodes_parent_count");
     }
     /* candidate emission plan */
-    NodeEmit emit_gen = {f.keys.get(), E,     f.fmt,
-                         nd.nfmt,      f.tables, gorder,
-                         order == 2 ? 1 : 0,     tree_dense.get()};
+    NodeEmit emit_gen = {f.keys.get(), E,        f.fmt, nd.nfmt,
+                         f.tables,     gorder,   1,     tree_dense.get()};
     i64 nemit = ngc;
     DBuf<u32> eoff;
     if (emit_gen.families) {
@@ -1985,7 +2001,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     const int mbits = nd.nfmt.pos_bits(); /* Morton + label bits */
     const int nbits = sort_bbits + mbits;
     const u64 max_payload =
-        emit_gen.families ? (((u64)E << 3) | 7ULL) : (u64)ngc;
+        emit_gen.families
+            ? (((u64)E << emit_gen.slot_bits()) | ((1ULL << emit_gen.slot_bits()) - 1))
+            : (u64)ngc;
     int pbits = 1;
     while ((1ULL << pbits) <= max_payload + 1) pbits++;
     const bool packed = nbits + pbits <= 64;
@@ -2002,12 +2020,16 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       cv.alloc(ctx, ntot);
       cv_alt.alloc(ctx, ntot);
     }
-    if (emit_gen.families && packed) {
+    if (emit_gen.families && packed && gorder == 2) {
       NodeEmitPackedFn ef = {emit_gen, nbits};
       expand_u64<8>(ctx, E, eoff.get(), (u64)nemit, ef, ck.get(), "nodes_candidates");
+    } else if (emit_gen.families && gorder == 2) {
+      NodeEmitFillFn<2> ef = {emit_gen, ck.get(), cv.get(), nbits};
+      NodeEmitPlaceFn<2> ep = {ef, eoff.get()};
+      launch(ctx, E, ep, "nodes_candidates");
     } else if (emit_gen.families) {
-      NodeEmitFillFn ef = {emit_gen, ck.get(), cv.get(), nbits};
-      NodeEmitPlaceFn ep = {ef, eoff.get()};
+      NodeEmitFillFn<3> ef = {emit_gen, ck.get(), cv.get(), nbits};
+      NodeEmitPlaceFn<3> ep = {ef, eoff.get()};
       launch(ctx, E, ep, "nodes_candidates");
     } else {
       if (gorder == 2) {
