@@ -694,9 +694,13 @@ struct NodeScatterFn {
        with one thread per family; an out-of-place expansion moves as many
        bytes as it saves.) */
     const i64 e0 = e - m;
-    const int qi = (np - 1) * ((m >> 2) & 1) + slot % np;
-    const int qj = (np - 1) * ((m >> 1) & 1) + (slot / np) % np;
-    const int qk = (np - 1) * (m & 1) + slot / (np * np);
+    /* np is 2 or 3: constant divisors instead of run-time divisions */
+    const int si = (np == 2) ? (slot & 1) : (slot % 3);
+    const int sj = (np == 2) ? ((slot >> 1) & 1) : ((slot / 3) % 3);
+    const int sk = (np == 2) ? (slot >> 2) : (slot / 9);
+    const int qi = (np - 1) * ((m >> 2) & 1) + si;
+    const int qj = (np - 1) * ((m >> 1) & 1) + sj;
+    const int qk = (np - 1) * (m & 1) + sk;
     for (int a = 0; a < 2; a++) {
       const int ia = qi - a * (np - 1);
       if (ia < 0 || ia > np - 1) continue;
