@@ -577,7 +577,9 @@ struct NodeEmit {
           }
           /* whether the slot stands for the whole family is re-derived from
              the keys at scatter time (in_family), not carried in the payload */
-          emit(key, payload(e, ii + np * jj + np * np * kk));
+          emit(key, families ? (((u64)e << (kOrder == 2 ? 3 : 5)) |
+                                (u64)(ii + np * jj + np * np * kk))
+                             : payload(e, ii + np * jj + np * np * kk));
         }
       }
     }
@@ -648,6 +650,7 @@ struct RunHeadMaskedFn {
 /* sorted candidates -> unique node keys + local connectivity */
 static const u32 kNoSlot = 0xffffffffu; /* candidate that fills no conn slot */
 
+template <int kNp> /* geometry order 2 or 3: folds the slot arithmetic */
 struct NodeScatterFn {
   const u64 *keys;
   const u32 *vals; /* NULL: payload = keys[i] >> pshift */
@@ -677,7 +680,7 @@ struct NodeScatterFn {
       conn_local[p] = (int)run;
       return;
     }
-    const int np = g.order, npe = np * np * np, sb = g.slot_bits();
+    const int np = kNp, npe = np * np * np, sb = (kNp == 2) ? 3 : 5;
     const i64 e = (i64)(p >> sb);
     const int slot = (int)(p & ((1u << sb) - 1u));
     int m;
@@ -2061,11 +2064,23 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       dev_zero(ctx, created.get(), (size_t)ntot);
     }
     RunHeadMaskedFn rh = {ck.get(), kmask};
-    NodeScatterFn sc = {ck.get(), cv.get(),     kmask,         nbits,
-                        no_slot,  ck_alt.get(),
-                        general ? ent_conn.get() : nd.conn.get(), created.get(),
-                        emit_gen, tree_undense.get(), mbits};
-    Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
+    if (gorder == 2) {
+      NodeScatterFn<2> sc = {ck.get(),     cv.get(),
+                             kmask,        nbits,
+                             no_slot,      ck_alt.get(),
+                             general ? ent_conn.get() : nd.conn.get(),
+                             created.get(), emit_gen,
+                             tree_undense.get(), mbits};
+      Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
+    } else {
+      NodeScatterFn<3> sc = {ck.get(),     cv.get(),
+                             kmask,        nbits,
+                             no_slot,      ck_alt.get(),
+                             general ? ent_conn.get() : nd.conn.get(),
+                             created.get(), emit_gen,
+                             tree_undense.get(), mbits};
+      Nn = (i64)scan_apply(ctx, ntot, rh, sc, "nodes_unique_scatter_conn");
+    }
 
     nd.node_keys.alloc(ctx, Nn);
     copy_d2d(ctx, nd.node_keys.get(), ck_alt.get(), (size_t)Nn * sizeof(u64));
