@@ -28,6 +28,7 @@ CASES = [
     ("connector15_l1_p3_c0_o2", "connector15", 1, 3, 30, 0, 2, 1),
     ("butterfly2_l1_p2_c1_o2", "butterfly2", 1, 2, 30, 1, 2, 1),
     ("box7_l1_p2_c1_o3_bernstein", "box7", 1, 2, 30, 1, 3, 2),
+    ("connector15_l0_p2_c1_o4", "connector15", 0, 2, 30, 1, 4, 1),
 ]
 
 
