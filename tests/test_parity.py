@@ -134,16 +134,18 @@ def test_eval_interp(order, interp, impl, ref_lib):
 
 @pytest.mark.parametrize("order,interp,conn_name", [(5, 1, "box7"), (5, 2, "connector15"),
                                                     (6, 1, "connector15"),
-                                                    (8, 1, "single"), (7, 0, "box7")])
+                                                    (8, 1, "single"), (7, 0, "box7"),
+                                                    (10, 1, "single")])
 def test_high_order(order, interp, conn_name, impl, ref_lib):
-    """Orders 5..8 (kMaxOrder): same entity machinery as order 4, prolongation
+    """Orders 5..16 (kMaxOrder = the reference's MAX_ORDER): same entity machinery as order 4, prolongation
     to the next lower order.  Bernstein points stop at order 5: the reference's
     eval_bernstein_weights has no table beyond it (src/TMRInterpolation.h:309-455)
     and leaves the weights unset."""
     conn = util.CONNS[conn_name]()
     res = []
     for lib in (ref_lib, impl):
-        f = util.build_forest(lib, conn, 0 if conn_name != "single" else 1, 2, 30, 1,
+        level = 1 if (conn_name == "single" and order < 9) else 0
+        f = util.build_forest(lib, conn, level, 2, 40 if order >= 9 else 30, 1,
                               order, interp=interp)
         nodes = util.node_results(f)
         low = f.duplicate()
@@ -151,6 +153,18 @@ def test_high_order(order, interp, conn_name, impl, ref_lib):
         res.append((nodes, f.createInterpolation(low)))
     util.assert_nodes_equal(res[0][0], res[1][0], "order %d" % order)
     util.assert_interp_equal(res[0][1], res[1][1], "order %d -> %d" % (order, order - 1))
+
+
+def test_order16_nodes(impl, ref_lib):
+    """The reference's MAX_ORDER: 14 nodes per edge, 196 per face, 2744 per
+    block entity, on a tree with hanging faces and edges (nodes and dependent
+    CSR; the prolongation at this order takes the reference itself minutes)."""
+    res = []
+    for lib in (ref_lib, impl):
+        f = util.build_forest(lib, util.single_conn(), 1, 1, 30, 1, 16, interp=1)
+        res.append(util.node_results(f))
+    assert len(res[0]["dep"][0]) > 1
+    util.assert_nodes_equal(res[0], res[1], "order 16")
 
 
 def test_connectivity_tables(impl, ref_lib):

@@ -22,13 +22,13 @@
 
 namespace tmrgpu {
 
-/* mesh orders 2..8 (the reference allows 16).  Orders 2 and 3 have one node per
+/* mesh orders 2..16, as the reference (MAX_ORDER, src/TMROctForest.h:49).  Orders 2 and 3 have one node per
    corner / edge / face / block entity; from order 4 on an entity carries
    (order-2)^dim nodes that are numbered consecutively and reached through the
    edge-reversal and face-orientation permutations of reference
    createLocalConn (src/TMROctForest.cpp:4660-4867).  The bound is the size of
    the per-thread knot, basis and prolongation-row arrays, nothing structural. */
-static const int kMaxOrder = 8;
+static const int kMaxOrder = 16;
 
 struct NodeData {
   bool valid;

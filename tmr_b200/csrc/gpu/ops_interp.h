@@ -674,7 +674,15 @@ inline int create_interp(Forest &fine, Forest &coarse) {
     case 5: TMR_INTERP_COUNT(5) break;
     case 6: TMR_INTERP_COUNT(6) break;
     case 7: TMR_INTERP_COUNT(7) break;
-    default: TMR_INTERP_COUNT(8) break;
+    case 8: TMR_INTERP_COUNT(8) break;
+    case 9: TMR_INTERP_COUNT(9) break;
+    case 10: TMR_INTERP_COUNT(10) break;
+    case 11: TMR_INTERP_COUNT(11) break;
+    case 12: TMR_INTERP_COUNT(12) break;
+    case 13: TMR_INTERP_COUNT(13) break;
+    case 14: TMR_INTERP_COUNT(14) break;
+    case 15: TMR_INTERP_COUNT(15) break;
+    default: TMR_INTERP_COUNT(16) break;
   }
 #undef TMR_INTERP_COUNT
   StoredCountFn sc = {cnt.get()};
@@ -699,7 +707,15 @@ inline int create_interp(Forest &fine, Forest &coarse) {
     case 5: TMR_INTERP_FILL(5) break;
     case 6: TMR_INTERP_FILL(6) break;
     case 7: TMR_INTERP_FILL(7) break;
-    default: TMR_INTERP_FILL(8) break;
+    case 8: TMR_INTERP_FILL(8) break;
+    case 9: TMR_INTERP_FILL(9) break;
+    case 10: TMR_INTERP_FILL(10) break;
+    case 11: TMR_INTERP_FILL(11) break;
+    case 12: TMR_INTERP_FILL(12) break;
+    case 13: TMR_INTERP_FILL(13) break;
+    case 14: TMR_INTERP_FILL(14) break;
+    case 15: TMR_INTERP_FILL(15) break;
+    default: TMR_INTERP_FILL(16) break;
   }
 #undef TMR_INTERP_FILL
   {
