@@ -271,6 +271,7 @@ struct InterpRow {
 
   /* builds the sorted, merged row of node j of fine element fkey inside coarse
      element t; returns its length */
+  template <int kCOrder> /* sizes the coarse basis arrays */
   TMR_HD int build(u64 fkey, int j, i64 t, int *idx, double *w, int cap) const {
     i32 block, x, y, z;
     int level;
@@ -282,7 +283,7 @@ struct InterpRow {
     const i32 hc = 1 << (kMaxLevel - cl);
     const int i0 = j % forder, j0 = (j % (forder * forder)) / forder,
               k0 = j / (forder * forder);
-    double Nu[kMaxOrder], Nv[kMaxOrder], Nw[kMaxOrder];
+    double Nu[kCOrder], Nv[kCOrder], Nw[kCOrder];
     int is, ie, js, je, ks, ke;
     axis(i0, x, h, ox, hc, &is, &ie, Nu);
     axis(j0, y, h, oy, hc, &js, &je, Nv);
@@ -404,8 +405,8 @@ struct InterpCountFn {
     }
     int idx[RowCap<kCOrder>::value];
     double w[RowCap<kCOrder>::value];
-    count[row] = (u32)r.build(q.fkey[row], q.j[row], q.t[row], idx, w,
-                              RowCap<kCOrder>::value);
+    count[row] = (u32)r.template build<kCOrder>(q.fkey[row], q.j[row], q.t[row],
+                                                idx, w, RowCap<kCOrder>::value);
   }
 };
 struct StoredCountFn {
@@ -423,8 +424,8 @@ struct InterpFillFn {
     if (q.t[row] < 0) return;
     int idx[RowCap<kCOrder>::value];
     double w[RowCap<kCOrder>::value];
-    const int n = r.build(q.fkey[row], q.j[row], q.t[row], idx, w,
-                          RowCap<kCOrder>::value);
+    const int n = r.template build<kCOrder>(q.fkey[row], q.j[row], q.t[row], idx,
+                                            w, RowCap<kCOrder>::value);
     for (int k = 0; k < n; k++) {
       cols[o + k] = idx[k];
       vals[o + k] = w[k];
