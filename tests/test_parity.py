@@ -167,6 +167,27 @@ def test_order16_nodes(impl, ref_lib):
     util.assert_nodes_equal(res[0], res[1], "order 16")
 
 
+def test_deep_corner_refinement(impl, ref_lib):
+    """A tree refined 13 levels deep into one corner: the leaf bitmap of the
+    hanging-node kernel covers levels 0..9 within its budget, so the probes at
+    parent levels 10-12 take the key-search path; the node keys use 14+1 bits
+    per axis."""
+    res = []
+    for lib in (ref_lib, impl):
+        f = OctForest(order=2, lib=lib)
+        f.setConnectivity(util.single_conn())
+        f.createTrees(1)
+        for _ in range(12):
+            flags = np.zeros(f.getNumOctants(), dtype=np.int32)
+            flags[0] = 1
+            f.refine(flags)
+            f.balance(1)
+        res.append(util.node_results(f))
+    assert int(res[0]["octants"]["level"].max()) == 13
+    util.assert_octants_equal(res[0]["octants"], res[1]["octants"], "deep corner")
+    util.assert_nodes_equal(res[0], res[1], "deep corner")
+
+
 def test_connectivity_tables(impl, ref_lib):
     """setConnectivity derives identical edge/face numbering, inverse maps,
     orientation ids (reference src/TMROctForest.cpp:558-1143)."""
