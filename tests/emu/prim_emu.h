@@ -35,6 +35,21 @@ void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64, F f, u64 *out, const char 
   ctx.launch_count++;
 }
 
+
+static const int kLaunchThreads = 256;
+
+template <class F>
+void launch_block2(Ctx &ctx, i64 n, F f, const char *) {
+  typename F::Shared *sh = new typename F::Shared();
+  for (i64 i0 = 0; i0 < n; i0 += kLaunchThreads) {
+    const i64 i1 = (i0 + kLaunchThreads < n) ? i0 + kLaunchThreads : n;
+    for (i64 i = i0; i < i1; i++) f.stage(i, (int)(i - i0), *sh);
+    for (i64 i = i0; i < i1; i++) f.finish(i, (int)(i - i0), *sh);
+  }
+  delete sh;
+  ctx.launch_count++;
+}
+
 template <class F>
 u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *) {
   u64 run = 0;

@@ -588,6 +588,22 @@ struct KeyIndex {
     }
     return (lo < (i64)table[p + 1] && a[lo] == key) ? lo : -1;
   }
+  /* index of the last key <= `key` (-1 if none): the element whose Morton
+     range starts at or before a position */
+  TMR_HD i64 pred(const u64 *a, u64 key) const {
+    u64 p = key >> shift;
+    if (p >= nprefix) p = nprefix - 1;
+    i64 lo = table[p], hi = table[p + 1];
+    while (lo < hi) {
+      const i64 mid = lo + ((hi - lo) >> 1);
+      if (a[mid] <= key) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    return lo - 1;
+  }
 };
 
 /* One bit per (level, tree, cell): set where a leaf of exactly that level

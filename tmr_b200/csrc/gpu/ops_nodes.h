@@ -25,8 +25,12 @@
 #ifndef TMRGPU_OPS_NODES_H
 #define TMRGPU_OPS_NODES_H
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "ops_balance.h"
 #include "ops_route.h"
+#include "ops_nodes_slots.h"
 
 namespace tmrgpu {
 
@@ -768,7 +772,7 @@ struct ParentNodeGen {
         /* parent edge: end points are corners, the rest edge nodes */
         const int label =
             nfmt.lbits ? ((ii == 0 || ii == order - 1) ? 0 : 1) : 0;
-        emit(nfmt.encode(tree_id(b), nx, ny, nz, label));
+        emit(b, nx, ny, nz, label);
       }
     }
     for (int f = 0; f < 6; f++) {
@@ -788,7 +792,7 @@ struct ParentNodeGen {
           const int pe = (p == 0 || p == order - 1) ? 1 : 0;
           const int qe = (q == 0 || q == order - 1) ? 1 : 0;
           const int label = nfmt.lbits ? (2 - pe - qe) : 0;
-          emit(nfmt.encode(tree_id(b), nx, ny, nz, label));
+          emit(b, nx, ny, nz, label);
         }
       }
     }
@@ -833,13 +837,15 @@ struct UndenseFn {
 
 struct CountKeyEmit {
   u32 n;
-  TMR_HD void operator()(u64) { n++; }
+  TMR_HD void operator()(i32, i32, i32, i32, int) { n++; }
 };
 struct StoreKeyEmit {
+  const ParentNodeGen *g;
   u64 *k;
   u32 *v; /* NULL in packed mode */
   u64 packed_no_slot; /* no_slot << pshift */
-  TMR_HD void operator()(u64 key) {
+  TMR_HD void operator()(i32 b, i32 x, i32 y, i32 z, int label) {
+    const u64 key = g->nfmt.encode(g->tree_id(b), x, y, z, label);
     if (v) {
       *k++ = key;
       *v++ = kNoSlot;
@@ -862,7 +868,7 @@ struct ParentNodeFillFn {
   u32 *out_vals;
   u64 packed_no_slot;
   TMR_HD void operator()(i64 e, u32 o) const {
-    StoreKeyEmit s = {out_keys + o, out_vals ? out_vals + o : (u32 *)0,
+    StoreKeyEmit s = {&g, out_keys + o, out_vals ? out_vals + o : (u32 *)0,
                       packed_no_slot};
     g.run(e, s);
   }
@@ -1789,6 +1795,166 @@ struct StoreExternalFn {
   TMR_HD void operator()(i64 i) const { node_num[ext_node[i]] = number[i]; }
 };
 
+/* ---- slot construction of nodes + connectivity (ops_nodes_slots.h) ---------- */
+struct ParentSlotFn {
+  ParentNodeGen g;
+  SlotView v;
+  NodeSlotFn ns;
+  TMR_HD void operator()(i64 e) const {
+    SlotKeyEmit em = {&v, &ns.nfmt, &ns};
+    g.run(e, em);
+  }
+};
+
+/* B nodes (several ranks): sorted (key, payload) -> unique keys, run index */
+struct BUniqueFn {
+  const u64 *k;
+  const u32 *pay;
+  u64 *ukeys;
+  unsigned char *ucreated;
+  u32 *run_of;
+  TMR_HD void operator()(i64 i, u32 heads_before) const {
+    const bool head = (i == 0 || k[i] != k[i - 1]);
+    const u32 run = heads_before + (head ? 1u : 0u) - 1u;
+    if (head) ukeys[run] = k[i];
+    run_of[i] = run;
+    if (pay[i] != kConnB) ucreated[run] = 1;
+  }
+};
+struct BLowCountFn {
+  const u64 *ukeys;
+  i64 n;
+  u64 first_key; /* node-key image of this rank's first position */
+  i64 *out;
+  TMR_HD void operator()(i64) const { out[0] = lower_bound_u64(ukeys, n, first_key); }
+};
+/* B nodes below the rank's range keep their run index, the others follow the
+   NA slot nodes */
+struct BPlaceFn {
+  const u64 *k;
+  const u32 *pay;
+  const u32 *run_of;
+  const unsigned char *ucreated;
+  i64 nlow, NA;
+  u64 *node_keys;
+  unsigned char *created;
+  int *conn;
+  TMR_HD void operator()(i64 i) const {
+    const i64 run = (i64)run_of[i];
+    const i64 idx = run < nlow ? run : run + NA;
+    if (i == 0 || k[i] != k[i - 1]) {
+      node_keys[idx] = k[i];
+      created[idx] = ucreated[run];
+    }
+    if (pay[i] != kConnB) conn[pay[i]] = (int)idx;
+  }
+};
+
+/* 1 = nodes, connectivity (local indices) and `created` are built; 0 = the
+   forest needs the general candidate sort; < 0 error */
+inline int build_nodes_slots(Forest &f, NodeData &nd, const KeyIndex &elem_ix,
+                             const unsigned char *fmask, u64 k_first, u64 k_last,
+                             DBuf<unsigned char> &created, i64 *Nn_out) {
+  Ctx &ctx = *f.ctx;
+  Comm *comm = ctx.comm;
+  const i64 E = f.n;
+  const int D = f.fmt.D;
+  DBuf<u32> mask(ctx, E), cmask;
+  dev_zero(ctx, mask.get(), (size_t)E * sizeof(u32));
+  if (comm) {
+    cmask.alloc(ctx, E);
+    dev_zero(ctx, cmask.get(), (size_t)E * sizeof(u32));
+  }
+  DBuf<unsigned long long> ctl(ctx, 2); /* [0] B count, [1] fail flag */
+  DBuf<unsigned char> slot8(ctx, E * 8);
+  u64 pos_lo = 0, pos_hi = ~0ULL;
+  if (comm && E > 0) {
+    pos_lo = k_first >> 5;
+    pos_hi = (k_last >> 5) + (1ULL << (3 * (D - (int)(k_last & 31))));
+  }
+  DBuf<u64> b_key;
+  DBuf<u32> b_pay;
+  i64 cap = comm ? (E / 2 + 65536) : 0, nb = 0;
+  unsigned long long h_ctl[2] = {0, 0};
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (comm) {
+      b_key.alloc(ctx, cap);
+      b_pay.alloc(ctx, cap);
+    }
+    dev_zero(ctx, ctl.get(), 2 * sizeof(unsigned long long));
+    SlotView v = {f.keys.get(), E, f.fmt, f.tables, elem_ix, comm ? 1 : 0, pos_lo,
+                  pos_hi, mask.get(), cmask.get(),
+                  reinterpret_cast<int *>(ctl.get() + 1)};
+    NodeSlotFn ns = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8.get(),
+                     nd.nfmt, b_key.get(), b_pay.get(), ctl.get(), cap};
+    launch_block2(ctx, E, ns, "nodes_slot_locate");
+    if (comm && fmask) {
+      ParentNodeGen pg = {f.keys.get(), fmask, f.fmt, nd.nfmt, f.tables, 2, NULL};
+      ParentSlotFn ps = {pg, v, ns};
+      launch(ctx, E, ps, "nodes_slot_parents");
+    }
+    if (!comm) break;
+    copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
+    nb = (i64)h_ctl[0];
+    if (h_ctl[1] || nb <= cap) break;
+    cap = nb; /* rare: more off-range corners than the guess; marks are idempotent */
+  }
+  /* B nodes: sort, unique */
+  i64 nbu = 0, nlow = 0;
+  DBuf<u64> b_ukeys;
+  DBuf<unsigned char> b_ucreated;
+  DBuf<u32> b_run;
+  if (comm && !h_ctl[1] && nb > 0) {
+    DBuf<u64> k_alt(ctx, nb);
+    DBuf<u32> p_alt(ctx, nb);
+    b_key.set_size(nb);
+    b_pay.set_size(nb);
+    radix_sort(ctx, b_key, k_alt, b_pay, p_alt, nb, 0, nd.nfmt.total_bits(), "nodes_b");
+    b_ukeys.alloc(ctx, nb);
+    b_ucreated.alloc(ctx, nb);
+    b_run.alloc(ctx, nb);
+    dev_zero(ctx, b_ucreated.get(), (size_t)nb);
+    RunHeadFn rh = {b_key.get()};
+    BUniqueFn bu = {b_key.get(), b_pay.get(), b_ukeys.get(), b_ucreated.get(),
+                    b_run.get()};
+    nbu = (i64)scan_apply(ctx, nb, rh, bu, "nodes_b_unique");
+    if (E > 0) {
+      DBuf<i64> d_low(ctx, 1);
+      BLowCountFn lc = {b_ukeys.get(), nbu, pos_lo << 3, d_low.get()};
+      launch(ctx, 1, lc, "nodes_b_low");
+      copy_d2h(ctx, &nlow, d_low.get(), sizeof(i64));
+    }
+  }
+  /* slot nodes: scan of the occupied slots */
+  DBuf<u64> slotinfo(ctx, E);
+  SlotCountFn sc = {mask.get()};
+  SlotInfoFn si = {mask.get(), slotinfo.get()};
+  const i64 NA = (i64)scan_apply(ctx, E, sc, si, "nodes_slot_scan");
+  if (!comm) copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
+  if (h_ctl[1]) return 0;
+  const i64 Nn = NA + nbu;
+  if (Nn >= (1LL << 31)) {
+    fprintf(stderr, "TMROctForest Error: too many local nodes\n");
+    return -1;
+  }
+  nd.node_keys.alloc(ctx, Nn);
+  if (comm) created.alloc(ctx, Nn);
+  SlotKeysFn kf = {f.keys.get(), f.fmt,         slotinfo.get(), cmask.get(),
+                   nd.node_keys.get(), created.get(), nlow};
+  launch(ctx, E, kf, "nodes_slot_keys");
+  SlotResolveFn rs = {slotinfo.get(), slot8.get(),
+                      reinterpret_cast<u32 *>(nd.conn.get()), (u32)nlow};
+  launch(ctx, E, rs, "nodes_slot_resolve");
+  if (nb > 0) {
+    BPlaceFn bp = {b_key.get(), b_pay.get(), b_run.get(), b_ucreated.get(), nlow, NA,
+                   nd.node_keys.get(), created.get(), nd.conn.get()};
+    launch(ctx, nb, bp, "nodes_b_place");
+  }
+  nd.num_candidates = nb;
+  *Nn_out = Nn;
+  return 1;
+}
+
 inline int create_nodes(Forest &f, int order, int interp_type,
                         const double *knots) {
   Ctx &ctx = *f.ctx;
@@ -1874,18 +2040,18 @@ inline int create_nodes(Forest &f, int order, int interp_type,
      :3287-3451; the answers are the same exact-leaf tests) */
   if (!f.info.get()) f.info.alloc(ctx, E);
   DBuf<unsigned char> fmask;
+  DBuf<u32> elem_index_store;
+  const KeyIndex elem_ix =
+      build_key_index(ctx, f.keys.get(), E, (u64)f.nblocks << (3 * f.fmt.D + 5),
+                      elem_index_store);
+  u64 k_first = 0, k_last = 0;
   {
-    DBuf<u32> elem_index_store;
-    const KeyIndex elem_ix =
-        build_key_index(ctx, f.keys.get(), E,
-                        (u64)f.nblocks << (3 * f.fmt.D + 5), elem_index_store);
     DBuf<u32> leaf_bits;
     u64 map_words = 0;
     /* the map spans the trees of this rank's own slice only, so its size per
        GPU stays constant under weak scaling */
     i32 map_b0 = 0, map_nb = f.nblocks;
     if (comm && E > 0) {
-      u64 k_first = 0, k_last = 0;
       copy_d2h(ctx, &k_first, f.keys.get(), sizeof(u64));
       copy_d2h(ctx, &k_last, f.keys.get() + (E - 1), sizeof(u64));
       map_b0 = (i32)(k_first >> (3 * f.fmt.D + 5));
@@ -1954,9 +2120,25 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   DBuf<int> ent_conn;
   if (general) ent_conn.alloc(ctx, ngc);
   DBuf<u32> ent_off, ent_of; /* entity -> first node, node -> entity */
-  i64 Nn;
+  i64 Nn = 0;
   DBuf<unsigned char> created;
+  /* order 2 without labels: nodes named by (leaf, slot), no candidate sort
+     (ops_nodes_slots.h); TMR_B200_NODES=sort forces the general path */
+  int slots_done = 0;
   {
+    const char *mode = getenv("TMR_B200_NODES");
+    if (gorder == 2 && !general && nd.nfmt.lbits == 0 && E > 0 &&
+        !(mode && strcmp(mode, "sort") == 0)) {
+      slots_done = build_nodes_slots(f, nd, elem_ix, fmask.get(), k_first, k_last,
+                                     created, &Nn);
+      if (slots_done < 0) return 1;
+      if (getenv("TMR_B200_NODES_VERBOSE")) {
+        fprintf(stderr, "[tmr_b200] createNodes: %s path, %lld elements\n",
+                slots_done ? "slot" : "slot->sort fallback", (long long)E);
+      }
+    }
+  }
+  if (!slots_done) {
     /* multi-rank: also the parent edge/face nodes of hanging elements */
     i64 nextra = 0;
     DBuf<u32> poff;

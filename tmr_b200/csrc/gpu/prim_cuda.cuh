@@ -100,6 +100,36 @@ void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64 total, F f, u64 *out,
   ctx.launch_count++;
 }
 
+
+/* ---- two-phase block kernel ------------------------------------------------
+   256 consecutive items per CTA: f.stage(i, t, shared) for every item, a
+   barrier, then f.finish(i, t, shared).  The items of one CTA exchange
+   results through F::Shared (sibling elements of an octant family share the
+   point locations of the family's 27 nodes, ops_nodes_slots.h). */
+template <class F>
+__global__ void __launch_bounds__(kLaunchThreads)
+    block2_kernel(F f, i64 n) {
+  __shared__ typename F::Shared sh;
+  const i64 nblk = (n + kLaunchThreads - 1) / kLaunchThreads;
+  for (i64 b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const i64 i = b * kLaunchThreads + threadIdx.x;
+    if (i < n) f.stage(i, (int)threadIdx.x, sh);
+    __syncthreads();
+    if (i < n) f.finish(i, (int)threadIdx.x, sh);
+    __syncthreads();
+  }
+}
+
+template <class F>
+void launch_block2(Ctx &ctx, i64 n, F f, const char *name) {
+  if (n <= 0) return;
+  const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
+  prof_begin(ctx, name);
+  block2_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
+  prof_end(ctx);
+  ctx.launch_count++;
+}
+
 /* ---- chained scan --------------------------------------------------------
    tile = 256 threads x 8 items (blocked, so each thread owns 8 consecutive
    outputs and stores them as two 16-byte vectors).  Tile descriptors are one
