@@ -98,6 +98,18 @@ int tmrgpu_repartition(tmrgpu_forest *f, int max_rank);
 int tmrgpu_get_owners(tmrgpu_forest *f, tmrgpu_octant *out);
 /* owned-node prefix over ranks, size()+1 ints (reference node_range) */
 int tmrgpu_node_range(tmrgpu_forest *f, int *out);
+/* Borrowed pointer to a page-locked host copy of one node array, owned by the
+   forest and valid until its node data is freed -- the storage behind the
+   borrowed-pointer getters getNodeConn / getNodeNumbers / getDepNodeConn
+   (reference src/TMROctForest.cpp:5686-5740).  which: 0 conn, 1 node numbers
+   sorted ascending (:4246), 2 dep_ptr, 3 dep_conn, 4 dep_weights.  Only the
+   array asked for is copied. */
+int tmrgpu_node_mirror(tmrgpu_forest *f, int which, const void **out);
+/* bit mask of arrays whose host copy createNodes starts on a second stream as
+   soon as the array is final (1 conn, 2 node numbers, 4 dependent CSR), so
+   the read-back overlaps the rest of createNodes; duplicates inherit it.
+   Default: TMR_B200_NODE_PREFETCH or 0. */
+int tmrgpu_set_node_prefetch(tmrgpu_forest *f, int mask);
 /* all-to-all-v of 24-byte octant records held in HOST arrays (the public
    distributeOctants / sendOctants entry points, reference :2379-2509):
    send_ptr/recv_ptr have size()+1 entries (element offsets); the records are

@@ -39,11 +39,13 @@ void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64, F f, u64 *out, const char 
 static const int kLaunchThreads = 256;
 
 template <class F>
-void launch_block2(Ctx &ctx, i64 n, F f, const char *) {
+void launch_block3(Ctx &ctx, i64 n, F f, const char *) {
   typename F::Shared *sh = new typename F::Shared();
   for (i64 i0 = 0; i0 < n; i0 += kLaunchThreads) {
     const i64 i1 = (i0 + kLaunchThreads < n) ? i0 + kLaunchThreads : n;
-    for (i64 i = i0; i < i1; i++) f.stage(i, (int)(i - i0), *sh);
+    sh->reset();
+    for (i64 i = i0; i < i1; i++) f.collect(i, (int)(i - i0), *sh);
+    for (int t = 0; t < kLaunchThreads; t++) f.process(i0, t, *sh);
     for (i64 i = i0; i < i1; i++) f.finish(i, (int)(i - i0), *sh);
   }
   delete sh;

@@ -81,6 +81,22 @@ unsigned long long fetch_add_u64(unsigned long long *p, unsigned long long v) {
 #endif
 }
 
+/* fetch-and-add on an int (shared-memory task counters) */
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+int fetch_add_i32(int *p, int v) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  const int old = *p;
+  *p = old + v;
+  return old;
+#endif
+}
+
 typedef uint64_t u64;
 typedef uint32_t u32;
 typedef int64_t i64;

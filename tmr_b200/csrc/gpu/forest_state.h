@@ -10,6 +10,8 @@
 #ifndef TMRGPU_FOREST_STATE_H
 #define TMRGPU_FOREST_STATE_H
 
+#include <stdlib.h>
+
 #include <memory>
 
 #include "comm.h"
@@ -30,6 +32,17 @@ namespace tmrgpu {
    the per-thread knot, basis and prolongation-row arrays, nothing structural. */
 static const int kMaxOrder = 16;
 
+/* page-locked host copy of one node array, owned by the forest: the
+   reference's getters hand out borrowed pointers into forest-owned arrays
+   (src/TMROctForest.cpp:5686-5740), here they point into these */
+struct HostMirror {
+  void *p;
+  void *ev; /* pending copy (copy_d2h_async handle) */
+  HostMirror() : p(NULL), ev(NULL) {}
+};
+enum { kMirrorConn = 0, kMirrorNumbers, kMirrorDepPtr, kMirrorDepConn,
+       kMirrorDepWeights, kNumMirrors };
+
 struct NodeData {
   bool valid;
   int order;
@@ -42,6 +55,7 @@ struct NodeData {
   i64 dep_nnz;
   i64 num_candidates; /* node keys that went through the sort */
   int node_range_start; /* first global number owned by this rank */
+  std::vector<int> node_range; /* owned-node prefix over ranks (size + 1) */
   NodeFmt nfmt;
   DBuf<u64> node_keys;  /* sorted unique node keys [num_local_nodes] */
   DBuf<int> node_num;   /* number of each node entry (node order) */
@@ -49,11 +63,28 @@ struct NodeData {
   DBuf<int> dep_ptr;    /* [num_dep_nodes + 1] */
   DBuf<int> dep_conn;   /* [dep_nnz] */
   DBuf<double> dep_weights;
+  /* host mirrors; prefetch = bit mask of the arrays whose copy createNodes
+     starts on the copy stream as soon as the array is final (bit 0 conn, 1
+     sorted node numbers, 2 the dependent CSR) */
+  Ctx *mctx;
+  HostMirror mirror[kNumMirrors];
+  DBuf<int> sorted_numbers; /* device staging of the sorted node numbers */
+  int prefetch;
   NodeData()
       : valid(false), order(2), interp_type(1), num_elements(0),
         num_local_nodes(0), num_dep_nodes(0), num_owned_nodes(0), dep_nnz(0),
-        num_candidates(0), node_range_start(0) {}
+        num_candidates(0), node_range_start(0), mctx(NULL), prefetch(0) {}
+  ~NodeData() { drop_mirrors(); }
+  void drop_mirrors() {
+    for (int k = 0; k < kNumMirrors; k++) {
+      if (mirror[k].ev) copy_wait(*mctx, mirror[k].ev);
+      if (mirror[k].p) host_free(*mctx, mirror[k].p);
+      mirror[k] = HostMirror();
+    }
+    sorted_numbers.reset();
+  }
   void clear() {
+    drop_mirrors();
     valid = false;
     node_keys.reset();
     node_num.reset();
@@ -61,6 +92,7 @@ struct NodeData {
     dep_ptr.reset();
     dep_conn.reset();
     dep_weights.reset();
+    node_range.clear();
     num_elements = num_local_nodes = num_dep_nodes = num_owned_nodes = 0;
     dep_nnz = 0;
   }
@@ -111,6 +143,8 @@ struct Forest {
     fmt.D = 0;
     fmt.bbits = 1;
     tables = ConnTables();
+    const char *ev = getenv("TMR_B200_NODE_PREFETCH");
+    nodes.prefetch = ev ? atoi(ev) : 0;
   }
 };
 

@@ -50,9 +50,9 @@ struct BuildIndexFn {
 /* index over a sorted key array whose keys are < key_limit; at most 2^22
    buckets (16 MB of u32, L2-resident) */
 inline KeyIndex build_key_index(Ctx &ctx, const u64 *keys, i64 n, u64 key_limit,
-                                DBuf<u32> &store) {
+                                DBuf<u32> &store, int max_bits = 22) {
   int shift = 0;
-  while ((key_limit >> shift) > (1ULL << 22)) shift++;
+  while ((key_limit >> shift) > (1ULL << max_bits)) shift++;
   KeyIndex ix;
   ix.shift = shift;
   ix.nprefix = (key_limit >> shift) + 1;
@@ -1493,33 +1493,94 @@ struct NumberRangeFn {
   TMR_HD void operator()(i64 i) const { out[i] = first + (int)i; }
 };
 
-inline int sorted_node_numbers(Forest &f, int *h_out) {
+/* every local node number, ascending, in a device array */
+inline int build_sorted_numbers(Forest &f, DBuf<int> &out) {
   Ctx &ctx = *f.ctx;
   NodeData &nd = f.nodes;
   const i64 n = nd.num_local_nodes;
   if (!nd.valid) return 1;
+  out.alloc(ctx, n);
   if (n == 0) return 0;
   if (!ctx.comm) {
     /* one rank: the numbers are -Nd..-1 (dependent) and 0..owned-1, every
        value once -- the sorted array is a range, no sort needed */
-    DBuf<int> out(ctx, n);
     NumberRangeFn r = {-(int)nd.num_dep_nodes, out.get()};
     launch(ctx, n, r, "nodes_number_range");
-    copy_d2h(ctx, h_out, out.get(), (size_t)n * sizeof(int));
-    return check_errors(ctx, "sorted_node_numbers");
+    return 0;
   }
   DBuf<u64> k(ctx, n), k_alt(ctx, n);
   DBuf<u32> v0, v1;
   NumToKeyFn a = {nd.node_num.get(), k.get()};
   launch(ctx, n, a, "nodes_numbers_to_keys");
   radix_sort(ctx, k, k_alt, v0, v1, n, 0, 32);
-  DBuf<int> out(ctx, n);
   KeyToNumFn b = {k.get(), out.get()};
   launch(ctx, n, b, "nodes_keys_to_numbers");
-  copy_d2h(ctx, h_out, out.get(), (size_t)n * sizeof(int));
+  return 0;
+}
+
+inline int sorted_node_numbers(Forest &f, int *h_out) {
+  Ctx &ctx = *f.ctx;
+  DBuf<int> out;
+  if (build_sorted_numbers(f, out)) return 1;
+  copy_d2h(ctx, h_out, out.get(), (size_t)f.nodes.num_local_nodes * sizeof(int));
   return check_errors(ctx, "sorted_node_numbers");
 }
 
+/* ---- host mirrors of the node arrays -------------------------------------------
+   Page-locked copies owned by the forest.  node_mirror_start enqueues the copy
+   on the context's copy stream (ordered after the main stream's work so far),
+   node_mirror_get waits for it.  createNodes starts the arrays named by
+   NodeData::prefetch as soon as each is final, so the 5.9 GB read-back of the
+   86 M-octant mesh overlaps the rest of createNodes instead of following it. */
+inline int node_mirror_start(Forest &f, int which) {
+  NodeData &nd = f.nodes;
+  Ctx &ctx = *f.ctx;
+  if (which < 0 || which >= kNumMirrors) return 1;
+  if (nd.mirror[which].p) return 0;
+  const void *src = NULL;
+  size_t bytes = 0;
+  const i64 npe = (i64)nd.order * nd.order * nd.order;
+  switch (which) {
+    case kMirrorConn:
+      src = nd.conn.get();
+      bytes = (size_t)(nd.num_elements * npe) * sizeof(int);
+      break;
+    case kMirrorNumbers:
+      if (build_sorted_numbers(f, nd.sorted_numbers)) return 1;
+      src = nd.sorted_numbers.get();
+      bytes = (size_t)nd.num_local_nodes * sizeof(int);
+      break;
+    case kMirrorDepPtr:
+      src = nd.dep_ptr.get();
+      bytes = (size_t)(nd.num_dep_nodes + 1) * sizeof(int);
+      break;
+    case kMirrorDepConn:
+      src = nd.dep_conn.get();
+      bytes = (size_t)nd.dep_nnz * sizeof(int);
+      break;
+    default:
+      src = nd.dep_weights.get();
+      bytes = (size_t)nd.dep_nnz * sizeof(double);
+      break;
+  }
+  nd.mctx = &ctx;
+  void *p = host_alloc(ctx, bytes + 16);
+  if (!p) return 1;
+  nd.mirror[which].p = p;
+  nd.mirror[which].ev = copy_d2h_async(ctx, p, src, bytes);
+  return 0;
+}
+
+inline const void *node_mirror_get(Forest &f, int which) {
+  NodeData &nd = f.nodes;
+  if (!nd.valid || node_mirror_start(f, which)) return NULL;
+  if (nd.mirror[which].ev) {
+    copy_wait(*f.ctx, nd.mirror[which].ev);
+    nd.mirror[which].ev = NULL;
+    if (which == kMirrorNumbers) nd.sorted_numbers.reset();
+  }
+  return nd.mirror[which].p;
+}
 
 /* packed family emission through expand_u64: key | payload << pshift */
 template <class Sink>
@@ -1852,7 +1913,7 @@ struct BPlaceFn {
 
 /* 1 = nodes, connectivity (local indices) and `created` are built; 0 = the
    forest needs the general candidate sort; < 0 error */
-inline int build_nodes_slots(Forest &f, NodeData &nd, const KeyIndex &elem_ix,
+inline int build_nodes_slots(Forest &f, NodeData &nd,
                              const unsigned char *fmask, u64 k_first, u64 k_last,
                              DBuf<unsigned char> &created, i64 *Nn_out) {
   Ctx &ctx = *f.ctx;
@@ -1867,11 +1928,17 @@ inline int build_nodes_slots(Forest &f, NodeData &nd, const KeyIndex &elem_ix,
   }
   DBuf<unsigned long long> ctl(ctx, 2); /* [0] B count, [1] fail flag */
   DBuf<unsigned char> slot8(ctx, E * 8);
-  u64 pos_lo = 0, pos_hi = ~0ULL;
-  if (comm && E > 0) {
-    pos_lo = k_first >> 5;
-    pos_hi = (k_last >> 5) + (1ULL << (3 * (D - (int)(k_last & 31))));
-  }
+  /* this rank's range of positions and the rank index over it */
+  const u64 pos_lo = k_first >> 5;
+  const u64 pos_hi = (k_last >> 5) + (1ULL << (3 * (D - (int)(k_last & 31))));
+  DBuf<RankEntry> rank_tab;
+  DBuf<u32> rank_cells;
+  size_t ix_budget = (size_t)8 * (size_t)E > ((size_t)64 << 20)
+                         ? (size_t)8 * (size_t)E
+                         : ((size_t)64 << 20);
+  if (const char *ev = getenv("TMR_B200_RANK_BUDGET")) ix_budget = (size_t)atol(ev);
+  const RankIndex elem_ix = build_rank_index(ctx, f.keys.get(), E, D, pos_lo, pos_hi,
+                                             ix_budget, rank_tab, rank_cells);
   DBuf<u64> b_key;
   DBuf<u32> b_pay;
   i64 cap = comm ? (E / 2 + 65536) : 0, nb = 0;
@@ -1887,7 +1954,7 @@ inline int build_nodes_slots(Forest &f, NodeData &nd, const KeyIndex &elem_ix,
                   reinterpret_cast<int *>(ctl.get() + 1)};
     NodeSlotFn ns = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8.get(),
                      nd.nfmt, b_key.get(), b_pay.get(), ctl.get(), cap};
-    launch_block2(ctx, E, ns, "nodes_slot_locate");
+    launch_block3(ctx, E, ns, "nodes_slot_locate");
     if (comm && fmask) {
       ParentNodeGen pg = {f.keys.get(), fmask, f.fmt, nd.nfmt, f.tables, 2, NULL};
       ParentSlotFn ps = {pg, v, ns};
@@ -2021,6 +2088,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   }
   if (E == 0 && !comm) {
     nd.valid = true;
+    nd.node_range.assign(2, 0);
     nd.dep_ptr.alloc(ctx, 1);
     dev_zero(ctx, nd.dep_ptr.get(), sizeof(int));
     return 0;
@@ -2041,9 +2109,11 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   if (!f.info.get()) f.info.alloc(ctx, E);
   DBuf<unsigned char> fmask;
   DBuf<u32> elem_index_store;
+  int ix_bits = 22;
+  if (const char *ev = getenv("TMR_B200_IXBITS")) ix_bits = atoi(ev);
   const KeyIndex elem_ix =
       build_key_index(ctx, f.keys.get(), E, (u64)f.nblocks << (3 * f.fmt.D + 5),
-                      elem_index_store);
+                      elem_index_store, ix_bits);
   u64 k_first = 0, k_last = 0;
   {
     DBuf<u32> leaf_bits;
@@ -2051,9 +2121,11 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     /* the map spans the trees of this rank's own slice only, so its size per
        GPU stays constant under weak scaling */
     i32 map_b0 = 0, map_nb = f.nblocks;
-    if (comm && E > 0) {
+    if (E > 0) {
       copy_d2h(ctx, &k_first, f.keys.get(), sizeof(u64));
       copy_d2h(ctx, &k_last, f.keys.get() + (E - 1), sizeof(u64));
+    }
+    if (comm && E > 0) {
       map_b0 = (i32)(k_first >> (3 * f.fmt.D + 5));
       map_nb = (i32)(k_last >> (3 * f.fmt.D + 5)) - map_b0 + 1;
     }
@@ -2129,8 +2201,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     const char *mode = getenv("TMR_B200_NODES");
     if (gorder == 2 && !general && nd.nfmt.lbits == 0 && E > 0 &&
         !(mode && strcmp(mode, "sort") == 0)) {
-      slots_done = build_nodes_slots(f, nd, elem_ix, fmask.get(), k_first, k_last,
-                                     created, &Nn);
+      slots_done = build_nodes_slots(f, nd, fmask.get(), k_first, k_last, created,
+                                     &Nn);
       if (slots_done < 0) return 1;
       if (getenv("TMR_B200_NODES_VERBOSE")) {
         fprintf(stderr, "[tmr_b200] createNodes: %s path, %lld elements\n",
@@ -2383,6 +2455,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   if (!comm) {
     nd.num_owned_nodes = Nn - Nd;
     nd.node_range_start = 0;
+    nd.node_range.assign(2, 0);
+    nd.node_range[1] = (int)(Nn - Nd);
     NumberNodesFn num = {dep_flag.get(), dep_before.get(), nd.node_range_start,
                          nd.node_num.get(), dep_node.get()};
     launch(ctx, Nn, num, "nodes_number");
@@ -2394,6 +2468,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     comm->allgather_host(ctx, &nown, all.data(), sizeof(i64));
     i64 start = 0;
     for (int r = 0; r < me; r++) start += all[r];
+    /* reference node_range (:4165-4172): kept so that the getters stay local */
+    nd.node_range.assign(comm->size + 1, 0);
+    for (int r = 0; r < comm->size; r++) nd.node_range[r + 1] = nd.node_range[r] + (int)all[r];
     nd.num_owned_nodes = nown;
     nd.node_range_start = (int)start;
     NumberNodesMultiFn num = {dep_flag.get(), dep_before.get(), owned_before.get(),
@@ -2428,6 +2505,14 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   ConnRemapInPlaceFn rm = {nd.node_num.get(), nd.conn.get()};
   launch(ctx, nc, rm, "nodes_conn_remap");
   trace_mark(ctx, "nodes: conn remap");
+  /* node_mirror_start needs the sizes; `valid` stays false until the end */
+  const int prefetch = nd.prefetch;
+  if (prefetch) {
+    nd.valid = true;
+    if (prefetch & 1) node_mirror_start(f, kMirrorConn);
+    if ((prefetch & 2) && !comm) node_mirror_start(f, kMirrorNumbers);
+    nd.valid = false;
+  }
 
   /* 5. dependent-node CSR */
   nd.dep_ptr.alloc(ctx, Nd + 1);
@@ -2507,6 +2592,12 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   trace_mark(ctx, "nodes: dep CSR");
 
   nd.valid = true;
+  if (prefetch & 4) {
+    node_mirror_start(f, kMirrorDepPtr);
+    node_mirror_start(f, kMirrorDepConn);
+    node_mirror_start(f, kMirrorDepWeights);
+  }
+  if ((prefetch & 2) && comm) node_mirror_start(f, kMirrorNumbers);
   return check_errors(ctx, "create_nodes");
 }
 

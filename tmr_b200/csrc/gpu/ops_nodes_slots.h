@@ -29,7 +29,7 @@
   of the element keys.  A complete family of 8 siblings shares the 27 points
   of its 3x3x3 grid; 8 of them are the siblings' own anchors, the other 19
   are located once and handed to the siblings through shared memory
-  (launch_block2), 2.4 searches per element instead of 7.
+  (launch_block3), 2.4 searches per element instead of 7.
 
   Anything the slots cannot name -- a corner at a quarter position of its
   leaf (unbalanced input), a position not covered by any leaf (incomplete
@@ -66,10 +66,12 @@ TMR_HD int ctz32(u32 v) {
 }
 
 TMR_HD int slot_ord(int c6) { return popc64(kSlotValid & ((1ULL << c6) - 1)); }
+/* ordinal -> code: the 27 valid codes, 6 bits each, 10 per word */
 TMR_HD int slot_code(int ord) {
-  u64 v = kSlotValid;
-  for (int r = 0; r < ord; r++) v &= v - 1;
-  return ctz64(v);
+  const int w = ord / 10, r = ord - 10 * w;
+  const u64 k = w == 0 ? 0x81b699612409200ULL
+                       : (w == 1 ? 0xe36d32c2db29a24ULL : 0x3ffbdf3beb9ULL);
+  return (int)((k >> (6 * r)) & 63);
 }
 
 /* add one at bit `bit` of the dilated axis-a component of a Morton code */
@@ -99,13 +101,154 @@ TMR_HD void load8_u32(const u32 *p, u32 *v) {
 #endif
 }
 
+/* ---- rank index: predecessor search in O(1) ----------------------------------
+   One entry per bucket of 64 cells of level Dg: a 64-bit map of the cells in
+   which a leaf is anchored and the number of marked cells before the bucket.
+   With Dg = D every leaf has its own cell, so the last leaf at or before a
+   position is `start + popc(bits up to the cell) - 1`: one 16-byte load
+   instead of a table read plus a binary search (measured on the 86 M-octant
+   forest: 6 dependent loads and 120 warp instructions per search; the search
+   loop was where the kernel waited).  When that table would outgrow its
+   budget, Dg < D, a marked cell holds several leaves, `cell_first` lists the
+   first leaf of every marked cell and the leaves of one cell are bisected. */
+struct RankEntry {
+  u32 bits[2];
+  u32 start;
+  u32 pad;
+};
+
+struct RankIndex {
+  const RankEntry *tab;
+  const u32 *cell_first; /* NULL when Dg = D; else [marked cells + 1] */
+  u64 cell0;             /* first cell (level Dg, incl. the tree index) */
+  int shift;             /* 3 (D - Dg) */
+  TMR_HD RankEntry load(u64 b) const {
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4 *>(tab + b);
+    RankEntry e;
+    e.bits[0] = v.x;
+    e.bits[1] = v.y;
+    e.start = v.z;
+    e.pad = v.w;
+    return e;
+#else
+    return tab[b];
+#endif
+  }
+  /* index of the last leaf anchored at or before position `pos` (depth D),
+     -1 if none; pos must lie in the table's range */
+  TMR_HD i64 pred(const u64 *keys, u64 pos) const {
+    const u64 cell = (pos >> shift) - cell0;
+    const RankEntry e = load(cell >> 6);
+    const int bit = (int)(cell & 63);
+    const u64 bits = ((u64)e.bits[1] << 32) | (u64)e.bits[0];
+    const i64 ci = (i64)e.start + popc64(bits << (63 - bit)) - 1;
+    if (!cell_first) return ci;
+    if (ci < 0) return -1;
+    if (!((bits >> bit) & 1)) return (i64)cell_first[ci + 1] - 1;
+    i64 lo = cell_first[ci], hi = cell_first[ci + 1];
+    const u64 q = (pos << 5) | 31ULL;
+    while (lo < hi) {
+      const i64 mid = lo + ((hi - lo) >> 1);
+      if (keys[mid] <= q) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    return lo - 1;
+  }
+};
+
+/* is element i the first leaf of its level-Dg cell? */
+TMR_HD bool rank_first_of_cell(const u64 *keys, i64 i, int shift) {
+  return i == 0 || ((keys[i - 1] >> 5) >> shift) != ((keys[i] >> 5) >> shift);
+}
+struct RankMarkFn {
+  const u64 *keys;
+  RankEntry *tab;
+  u64 cell0;
+  int shift;
+  TMR_HD void operator()(i64 i) const {
+    if (shift && !rank_first_of_cell(keys, i, shift)) return;
+    const u64 cell = ((keys[i] >> 5) >> shift) - cell0;
+    const int bit = (int)(cell & 63);
+    TMR_ATOMIC_OR_I32(&tab[cell >> 6].bits[bit >> 5], 1u << (bit & 31));
+  }
+};
+struct RankBitsFn {
+  const RankEntry *tab;
+  TMR_HD u32 operator()(i64 b) const {
+    return (u32)(popc32(tab[b].bits[0]) + popc32(tab[b].bits[1]));
+  }
+};
+struct RankStartFn {
+  RankEntry *tab;
+  TMR_HD void operator()(i64 b, u32 before) const { tab[b].start = before; }
+};
+struct RankCellFirstFn {
+  const u64 *keys;
+  i64 n;
+  RankIndex ix;
+  u32 *cell_first;
+  u32 nmarked;
+  TMR_HD void operator()(i64 i) const {
+    if (i == n) {
+      cell_first[nmarked] = (u32)n;
+      return;
+    }
+    if (!rank_first_of_cell(keys, i, ix.shift)) return;
+    const u64 cell = ((keys[i] >> 5) >> ix.shift) - ix.cell0;
+    const RankEntry e = ix.load(cell >> 6);
+    const int bit = (int)(cell & 63);
+    const u64 bits = ((u64)e.bits[1] << 32) | (u64)e.bits[0];
+    cell_first[(i64)e.start + popc64(bits << (63 - bit)) - 1] = (u32)i;
+  }
+};
+
+/* rank index over the sorted element keys [first, last] of this rank */
+inline RankIndex build_rank_index(Ctx &ctx, const u64 *keys, i64 n, int D,
+                                  u64 pos_first, u64 pos_end, size_t budget,
+                                  DBuf<RankEntry> &tab_store, DBuf<u32> &cf_store) {
+  RankIndex ix;
+  int Dg = D;
+  u64 c0, c1;
+  while (true) {
+    const int sh = 3 * (D - Dg);
+    c0 = (pos_first >> sh) & ~63ULL;
+    c1 = ((pos_end - 1) >> sh) + 1;
+    if (((c1 - c0 + 63) >> 6) * sizeof(RankEntry) <= budget || Dg == 0) break;
+    Dg--;
+  }
+  ix.shift = 3 * (D - Dg);
+  ix.cell0 = c0;
+  ix.cell_first = NULL;
+  const i64 nbuckets = (i64)((c1 - c0 + 63) >> 6);
+  tab_store.alloc(ctx, nbuckets);
+  dev_zero(ctx, tab_store.get(), (size_t)nbuckets * sizeof(RankEntry));
+  RankMarkFn mk = {keys, tab_store.get(), c0, ix.shift};
+  launch(ctx, n, mk, "rank_index_mark");
+  RankBitsFn bf = {tab_store.get()};
+  RankStartFn sf = {tab_store.get()};
+  const i64 nmarked = (i64)scan_apply(ctx, nbuckets, bf, sf, "rank_index_scan");
+  ix.tab = tab_store.get();
+  if (ix.shift) {
+    cf_store.alloc(ctx, nmarked + 1);
+    RankCellFirstFn cf = {keys, n, ix, cf_store.get(), (u32)nmarked};
+    launch(ctx, n + 1, cf, "rank_index_cells");
+    ix.cell_first = cf_store.get();
+  }
+  return ix;
+}
+
 struct SlotView {
   const u64 *keys;
   i64 E;
   KeyFmt fmt;
   ConnTables t;
-  KeyIndex ix;
-  /* several ranks: positions (depth D) of this rank's own range */
+  RankIndex ix;
+  /* positions (depth D) of this rank's own range; with several ranks a
+     position outside it belongs to another rank (B list) */
   int multi;
   u64 pos_lo, pos_hi;
   u32 *mask;  /* per leaf: occupied slots */
@@ -118,8 +261,8 @@ struct SlotView {
   TMR_HD u64 locate(i32 block, u64 m, int clamp) const {
     const int D = fmt.D;
     const u64 pos = ((u64)(u32)block << (3 * D)) | m;
-    if (multi && (pos < pos_lo || pos >= pos_hi)) return kLocB;
-    const i64 j = ix.pred(keys, (pos << 5) | 31ULL);
+    if (pos < pos_lo || pos >= pos_hi) return multi ? kLocB : kLocFail;
+    const i64 j = ix.pred(keys, pos);
     if (j < 0) return kLocFail;
     const u64 kl = keys[j];
     const int k = D - (int)(kl & 31);
@@ -157,7 +300,10 @@ struct SlotView {
   }
 };
 
-/* per element: (leaf, slot) of its 8 corners */
+/* per element: (leaf, slot) of its 8 corners.  Runs through launch_block3:
+   collect() classifies the element and queues the points that need a search,
+   process() drains the queues with all lanes busy, finish() assembles the
+   element's row. */
 struct NodeSlotFn {
   SlotView v;
   u32 *conn_leaf;       /* [E][8] leaf index of every corner (kConnB: B list) */
@@ -170,8 +316,17 @@ struct NodeSlotFn {
   i64 b_cap;
 
   struct Shared {
-    u64 val[kLaunchThreads * 4];
-    short fam0[kLaunchThreads];
+    u64 val[kLaunchThreads * 8];   /* [item][r or corner] */
+    /* task = (item << 3) | code; one list per kind of work so that the lanes
+       of a warp run the same code: family grid points (code = r), corners of
+       interior elements outside complete families (code = corner), corners of
+       elements on a tree face (transform_node) */
+    unsigned short fam[kLaunchThreads * 4];
+    unsigned short own[kLaunchThreads * 8];
+    unsigned short slow[kLaunchThreads * 8];
+    short fam0[kLaunchThreads]; /* first item of the item's family, or -1 */
+    int nfam, nown, nslow;
+    TMR_HD void reset() { nfam = nown = nslow = 0; }
   };
 
   TMR_HD void append_b(u64 key, u32 payload) const {
@@ -182,142 +337,163 @@ struct NodeSlotFn {
     }
   }
 
-  TMR_HD void stage(i64 i, int t, Shared &sh) const {
+  /* point tp = gx + 3 gy + 9 gz of the 3x3x3 grid of a family: is it the
+     anchor of one of the 8 siblings? */
+  TMR_HD static bool family_inner(int tp) {
+    return (tp % 3) < 2 && ((tp / 3) % 3) < 2 && tp < 18;
+  }
+
+  TMR_HD void collect(i64 i, int t, Shared &sh) const {
     const u64 key = v.keys[i];
     const int L = (int)(key & 31), D = v.fmt.D;
     const int s = 3 * (D - L);
     const u64 m = D > 0 ? ((key >> 5) & ((1ULL << (3 * D)) - 1)) : 0ULL;
-    const i32 block = (i32)(key >> (3 * D + 5));
     sh.fam0[t] = -1;
-    if (L == 0) return;
+    /* does the element's cell / its parent's cell touch a tree face? */
+    bool lower = false, elem_in = L > 0, par_in = L > 1;
+    {
+      const u64 lv = L > 0 ? ((1ULL << (3 * L)) - 1) : 0ULL;
+      const u64 lvp = L > 1 ? ((1ULL << (3 * (L - 1))) - 1) : 0ULL;
+      const u64 mc = m >> s, mp = mc >> 3;
+      TMR_UNROLL
+      for (int a = 0; a < 3; a++) {
+        const u64 am = (0x1249249249249249ULL << a) & lv;
+        const u64 c = mc & am;
+        lower = lower || c == 0;
+        elem_in = elem_in && c != 0 && c != am;
+        const u64 amp = (0x1249249249249249ULL << a) & lvp;
+        const u64 cp = mp & amp;
+        par_in = par_in && cp != 0 && cp != amp;
+      }
+    }
     /* the element's own anchor is a node in place unless it lies on a lower
        tree face (then it goes through transform_node like any other corner) */
-    {
-      const u64 lv = (1ULL << (3 * L)) - 1;
-      const u64 mc = m >> s;
-      if ((mc & 0x1249249249249249ULL & lv) && (mc & 0x2492492492492492ULL & lv) &&
-          (mc & 0x4924924924924924ULL & lv)) {
-        v.mark((u64)i << 5, true);
-      }
-    }
-    const int md = (int)((m >> s) & 7);
-    const i64 e0 = i - md, i0 = i - t;
-    if (e0 < i0 || e0 + 7 >= i0 + kLaunchThreads || e0 + 7 >= v.E) return;
-    const u64 k0 = v.keys[e0];
-    if ((k0 & 31) != (u64)L || ((k0 >> (5 + s)) & 7) != 0 ||
-        v.keys[e0 + 7] != k0 + (7ULL << (5 + s))) {
-      return;
-    }
-    /* 8 consecutive keys from sibling 0 to sibling 7: in a valid leaf set
-       they are the 8 siblings, and this element is number md of them */
-    if (key != k0 + ((u64)md << (5 + s))) {
-      *v.fail = 1;
-      return;
-    }
-    /* interior family: the parent's cell touches no tree face */
-    const int Lp = L - 1;
-    const u64 lvp = Lp > 0 ? ((1ULL << (3 * Lp)) - 1) : 0ULL;
-    const u64 mp = m >> (s + 3);
-    TMR_UNROLL
-    for (int a = 0; a < 3; a++) {
-      const u64 am = (0x1249249249249249ULL << a) & lvp;
-      const u64 c = mp & am;
-      if (c == 0 || c == am) return;
-    }
-    sh.fam0[t] = (short)(e0 - i0);
-    const u64 mP = (m >> (s + 3)) << (s + 3);
-    TMR_UNROLL
-    for (int r = 0; r < 4; r++) {
-      const int tp = md + 8 * r;
-      if (tp >= 27) break;
-      const int g[3] = {tp / 9, (tp / 3) % 3, tp % 3}; /* axis a: 0 z, 1 y, 2 x */
-      u64 val;
-      if (g[0] < 2 && g[1] < 2 && g[2] < 2) {
-        val = (u64)(e0 + 4 * g[2] + 2 * g[1] + g[0]) << 5;
-      } else {
-        u64 mq = mP;
-        TMR_UNROLL
-        for (int a = 0; a < 3; a++) {
-          if (g[a] == 1) mq |= 1ULL << (s + a);
-          if (g[a] == 2) mq = morton_axis_add(mq, a, s + 3 + a);
+    if (L > 0 && !lower) v.mark((u64)i << 5, true);
+    if (par_in) {
+      const int md = (int)((m >> s) & 7);
+      const i64 e0 = i - md, i0 = i - t;
+      if (e0 >= i0 && e0 + 7 < i0 + kLaunchThreads && e0 + 7 < v.E) {
+        const u64 k0 = v.keys[e0];
+        if ((k0 & 31) == (u64)L && ((k0 >> (5 + s)) & 7) == 0 &&
+            v.keys[e0 + 7] == k0 + (7ULL << (5 + s))) {
+          /* 8 consecutive keys from sibling 0 to sibling 7: in a valid leaf
+             set they are the 8 siblings and this element is number md */
+          if (key != k0 + ((u64)md << (5 + s))) {
+            *v.fail = 1;
+            return;
+          }
+          sh.fam0[t] = (short)(e0 - i0);
+          int need = 0;
+          TMR_UNROLL
+          for (int r = 0; r < 4; r++) {
+            const int tp = md + 8 * r;
+            if (tp >= 27) break;
+            if (family_inner(tp)) {
+              sh.val[t * 8 + r] =
+                  (u64)(e0 + 4 * (tp % 3) + 2 * ((tp / 3) % 3) + tp / 9) << 5;
+            } else {
+              need |= 1 << r;
+            }
+          }
+          int q = fetch_add_i32(&sh.nfam, popc32((u32)need));
+          TMR_UNROLL
+          for (int r = 0; r < 4; r++) {
+            if (need & (1 << r)) sh.fam[q++] = (unsigned short)((t << 3) | r);
+          }
+          return;
         }
-        val = v.locate(block, mq, 0);
-        v.mark(val, true);
       }
-      sh.val[t * 4 + r] = val;
+    }
+    if (elem_in) {
+      sh.val[t * 8] = (u64)i << 5;
+      int q = fetch_add_i32(&sh.nown, 7);
+      TMR_UNROLL
+      for (int c = 1; c < 8; c++) sh.own[q++] = (unsigned short)((t << 3) | c);
+    } else {
+      int q = fetch_add_i32(&sh.nslow, 8);
+      TMR_UNROLL
+      for (int c = 0; c < 8; c++) sh.slow[q++] = (unsigned short)((t << 3) | c);
+    }
+  }
+
+  TMR_HD void process(i64 i0, int t, Shared &sh) const {
+    const int D = v.fmt.D;
+    /* family grid points: steps of the element size from the parent's anchor */
+    for (int q = t; q < sh.nfam; q += kLaunchThreads) {
+      const int task = sh.fam[q], ts = task >> 3, code = task & 7;
+      const u64 key = v.keys[i0 + ts];
+      const int s = 3 * (D - (int)(key & 31));
+      const u64 m = (key >> 5) & ((1ULL << (3 * D)) - 1);
+      const int tp = (int)((m >> s) & 7) + 8 * code;
+      const int g[3] = {tp / 9, (tp / 3) % 3, tp % 3}; /* axis 0 z, 1 y, 2 x */
+      u64 mq = (m >> (s + 3)) << (s + 3);
+      TMR_UNROLL
+      for (int a = 0; a < 3; a++) {
+        if (g[a] == 1) mq |= 1ULL << (s + a);
+        if (g[a] == 2) mq = morton_axis_add(mq, a, s + 3 + a);
+      }
+      const u64 val = v.locate((i32)(key >> (3 * D + 5)), mq, 0);
+      v.mark(val, true);
+      sh.val[ts * 8 + code] = val;
+    }
+    /* corners of interior elements */
+    for (int q = t; q < sh.nown; q += kLaunchThreads) {
+      const int task = sh.own[q], ts = task >> 3, code = task & 7;
+      const u64 key = v.keys[i0 + ts];
+      const int s = 3 * (D - (int)(key & 31));
+      u64 mq = (key >> 5) & ((1ULL << (3 * D)) - 1);
+      if (code & 1) mq = morton_axis_add(mq, 2, s + 2);
+      if (code & 2) mq = morton_axis_add(mq, 1, s + 1);
+      if (code & 4) mq = morton_axis_add(mq, 0, s);
+      const u64 val = v.locate((i32)(key >> (3 * D + 5)), mq, 0);
+      v.mark(val, true);
+      sh.val[ts * 8 + code] = val;
+    }
+    /* corners of elements on a tree face: coordinates and transform_node */
+    for (int q = t; q < sh.nslow; q += kLaunchThreads) {
+      const int task = sh.slow[q], ts = task >> 3, c = task & 7;
+      i32 b, x, y, z;
+      int L;
+      v.fmt.decode(v.keys[i0 + ts], &b, &x, &y, &z, &L);
+      const i32 h = 1 << (kMaxLevel - L);
+      x += (c & 1) * h;
+      y += ((c >> 1) & 1) * h;
+      z += (c >> 2) * h;
+      transform_node(v.t, &b, &x, &y, &z, -1, NULL, NULL);
+      const u64 val = v.locate_xyz(b, x, y, z);
+      v.mark(val, true);
+      sh.val[ts * 8 + c] = val;
     }
   }
 
   TMR_HD void finish(i64 i, int t, Shared &sh) const {
-    const u64 key = v.keys[i];
-    const int L = (int)(key & 31), D = v.fmt.D;
-    const int s = 3 * (D - L);
-    const u64 m = D > 0 ? ((key >> 5) & ((1ULL << (3 * D)) - 1)) : 0ULL;
-    const i32 block = (i32)(key >> (3 * D + 5));
-    u64 val[8];
     const int f0 = sh.fam0[t];
+    int gx0 = 0, gy0 = 0, gz0 = 0;
     if (f0 >= 0) {
-      const int md = (int)((m >> s) & 7);
-      const int gz0 = md & 1, gy0 = (md >> 1) & 1, gx0 = (md >> 2) & 1;
-      TMR_UNROLL
-      for (int c = 0; c < 8; c++) {
-        const int gx = gx0 + (c & 1), gy = gy0 + ((c >> 1) & 1), gz = gz0 + (c >> 2);
-        const int tp = 9 * gz + 3 * gy + gx;
-        val[c] = sh.val[(f0 + (tp & 7)) * 4 + (tp >> 3)];
-      }
-    } else {
-      /* own corners.  Interior element: Morton space; else coordinates and
-         transform_node */
-      bool interior = L > 0;
-      if (interior) {
-        const u64 lv = (1ULL << (3 * L)) - 1;
-        const u64 mc = m >> s;
-        TMR_UNROLL
-        for (int a = 0; a < 3; a++) {
-          const u64 am = (0x1249249249249249ULL << a) & lv;
-          const u64 c = mc & am;
-          if (c == 0 || c == am) interior = false;
-        }
-      }
-      if (interior) {
-        TMR_UNROLL
-        for (int c = 0; c < 8; c++) {
-          if (c == 0) {
-            val[c] = (u64)i << 5;
-            continue;
-          }
-          u64 mq = m;
-          if (c & 1) mq = morton_axis_add(mq, 2, s + 2);
-          if (c & 2) mq = morton_axis_add(mq, 1, s + 1);
-          if (c & 4) mq = morton_axis_add(mq, 0, s);
-          val[c] = v.locate(block, mq, 0);
-          v.mark(val[c], true);
-        }
-      } else {
-        i32 b0, x, y, z;
-        int lv;
-        v.fmt.decode(key, &b0, &x, &y, &z, &lv);
-        const i32 h = 1 << (kMaxLevel - L);
-        for (int c = 0; c < 8; c++) {
-          i32 b = b0, nx = x + (c & 1) * h, ny = y + ((c >> 1) & 1) * h,
-              nz = z + (c >> 2) * h;
-          transform_node(v.t, &b, &nx, &ny, &nz, -1, NULL, NULL);
-          val[c] = v.locate_xyz(b, nx, ny, nz);
-          v.mark(val[c], true);
-        }
-      }
+      const u64 key = v.keys[i];
+      const int md = (int)((key >> (5 + 3 * (v.fmt.D - (int)(key & 31)))) & 7);
+      gz0 = md & 1;
+      gy0 = (md >> 1) & 1;
+      gx0 = (md >> 2) & 1;
     }
     u32 leaf[8];
     u64 ords = 0;
     TMR_UNROLL
     for (int c = 0; c < 8; c++) {
-      if (val[c] == kLocFail) {
+      u64 val;
+      if (f0 >= 0) {
+        const int tp = 9 * (gz0 + (c >> 2)) + 3 * (gy0 + ((c >> 1) & 1)) + gx0 + (c & 1);
+        val = sh.val[(f0 + (tp & 7)) * 8 + (tp >> 3)];
+      } else {
+        val = sh.val[t * 8 + c];
+      }
+      if (val == kLocFail) {
         *v.fail = 1;
         leaf[c] = 0;
-      } else if (val[c] == kLocB) {
+      } else if (val == kLocB) {
         i32 b, x, y, z;
-        int lv;
-        v.fmt.decode(key, &b, &x, &y, &z, &lv);
+        int L;
+        v.fmt.decode(v.keys[i], &b, &x, &y, &z, &L);
         const i32 h = 1 << (kMaxLevel - L);
         x += (c & 1) * h;
         y += ((c >> 1) & 1) * h;
@@ -326,8 +502,8 @@ struct NodeSlotFn {
         append_b(nfmt.encode(b, x, y, z, 0), (u32)(i * 8 + c));
         leaf[c] = kConnB;
       } else {
-        leaf[c] = (u32)(val[c] >> 5);
-        ords |= (val[c] & 31) << (8 * c);
+        leaf[c] = (u32)(val >> 5);
+        ords |= (val & 31) << (8 * c);
       }
     }
     store8_u32(conn_leaf + i * 8, leaf);

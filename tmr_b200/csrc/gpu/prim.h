@@ -35,6 +35,7 @@ struct Ctx {
   int device;
   Comm *comm; /* NULL = single rank */
   void *stream; /* cudaStream_t */
+  void *copy_stream; /* second stream for device->host mirrors, lazily created */
   int profile;  /* time every named launch with events */
   int num_sms;
   long launch_count; /* kernels launched since the last reset */
@@ -46,7 +47,8 @@ struct Ctx {
   int trace;        /* TMR_B200_TRACE=1: print synchronised phase times */
   double trace_t0;  /* wall clock of the previous mark (s) */
   Ctx()
-      : device(0), comm(NULL), stream(NULL), profile(0), num_sms(148),
+      : device(0), comm(NULL), stream(NULL), copy_stream(NULL), profile(0),
+        num_sms(148),
         launch_count(0), trace(0), trace_t0(0.0) {}
 };
 
@@ -59,6 +61,11 @@ void host_free(Ctx &ctx, void *p);
 void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes);
 void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes); /* syncs */
 void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes);
+/* device->host copy on the context's COPY stream, ordered after everything
+   enqueued so far on the main stream and overlapping what follows there; dst
+   must be page-locked (host_alloc).  Returns a handle for copy_wait. */
+void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes);
+void copy_wait(Ctx &ctx, void *handle); /* blocks until done, releases it */
 void dev_zero(Ctx &ctx, void *p, size_t bytes);
 void dev_fill_ff(Ctx &ctx, void *p, size_t bytes);
 void stream_sync(Ctx &ctx);

@@ -163,6 +163,32 @@ void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes) {
   TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
 }
 
+void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return NULL;
+  if (!ctx.copy_stream) {
+    cudaStream_t s;
+    TMR_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    ctx.copy_stream = s;
+  }
+  cudaEvent_t ready, done;
+  TMR_CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  TMR_CUDA_OK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  TMR_CUDA_OK(cudaEventRecord(ready, (cudaStream_t)ctx.stream));
+  TMR_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)ctx.copy_stream, ready, 0));
+  TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost,
+                              (cudaStream_t)ctx.copy_stream));
+  TMR_CUDA_OK(cudaEventRecord(done, (cudaStream_t)ctx.copy_stream));
+  cudaEventDestroy(ready);
+  return done;
+}
+
+void copy_wait(Ctx &ctx, void *handle) {
+  (void)ctx;
+  if (!handle) return;
+  TMR_CUDA_OK(cudaEventSynchronize((cudaEvent_t)handle));
+  cudaEventDestroy((cudaEvent_t)handle);
+}
+
 void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
   if (bytes == 0) return;
   TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice,

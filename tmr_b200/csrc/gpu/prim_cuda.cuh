@@ -101,19 +101,30 @@ void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64 total, F f, u64 *out,
 }
 
 
-/* ---- two-phase block kernel ------------------------------------------------
-   256 consecutive items per CTA: f.stage(i, t, shared) for every item, a
-   barrier, then f.finish(i, t, shared).  The items of one CTA exchange
-   results through F::Shared (sibling elements of an octant family share the
-   point locations of the family's 27 nodes, ops_nodes_slots.h). */
+/* ---- block kernel with a shared task list ------------------------------------
+   256 consecutive items per CTA, three phases separated by barriers:
+     f.collect(i, t, shared)   every item classifies itself and appends the
+                               work it needs to task lists in shared memory
+     f.process(i0, t, shared)  all 256 threads drain the lists densely (a task
+                               is not tied to the thread that queued it, so a
+                               warp never idles behind one expensive item)
+     f.finish(i, t, shared)    every item assembles its outputs
+   F::Shared::reset() clears the list counters.  Used by the node-slot
+   construction (ops_nodes_slots.h), where sibling elements share the point
+   locations of their family's 27 nodes. */
 template <class F>
 __global__ void __launch_bounds__(kLaunchThreads)
-    block2_kernel(F f, i64 n) {
+    block3_kernel(F f, i64 n) {
   __shared__ typename F::Shared sh;
   const i64 nblk = (n + kLaunchThreads - 1) / kLaunchThreads;
   for (i64 b = blockIdx.x; b < nblk; b += gridDim.x) {
-    const i64 i = b * kLaunchThreads + threadIdx.x;
-    if (i < n) f.stage(i, (int)threadIdx.x, sh);
+    const i64 i0 = b * kLaunchThreads;
+    const i64 i = i0 + threadIdx.x;
+    if (threadIdx.x == 0) sh.reset();
+    __syncthreads();
+    if (i < n) f.collect(i, (int)threadIdx.x, sh);
+    __syncthreads();
+    f.process(i0, (int)threadIdx.x, sh);
     __syncthreads();
     if (i < n) f.finish(i, (int)threadIdx.x, sh);
     __syncthreads();
@@ -121,11 +132,11 @@ __global__ void __launch_bounds__(kLaunchThreads)
 }
 
 template <class F>
-void launch_block2(Ctx &ctx, i64 n, F f, const char *name) {
+void launch_block3(Ctx &ctx, i64 n, F f, const char *name) {
   if (n <= 0) return;
   const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
   prof_begin(ctx, name);
-  block2_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
+  block3_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
   prof_end(ctx);
   ctx.launch_count++;
 }

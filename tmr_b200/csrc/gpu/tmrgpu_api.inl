@@ -222,14 +222,23 @@ int tmrgpu_get_owners(tmrgpu_forest *F, tmrgpu_octant *out) {
 }
 
 int tmrgpu_node_range(tmrgpu_forest *F, int *out) {
-  Forest &f = F->f;
-  Ctx &ctx = *f.ctx;
-  const int R = part_size(f);
-  i64 mine = f.nodes.num_owned_nodes;
-  std::vector<i64> all(R, mine);
-  if (ctx.comm) ctx.comm->allgather_host(ctx, &mine, all.data(), sizeof(i64));
-  out[0] = 0;
-  for (int r = 0; r < R; r++) out[r + 1] = out[r] + (int)all[r];
+  /* computed inside createNodes (reference :4165-4172): no communication here,
+     so the getters built on it stay local calls like the reference's */
+  const NodeData &nd = F->f.nodes;
+  const int R = part_size(F->f);
+  for (int r = 0; r <= R; r++) {
+    out[r] = r < (int)nd.node_range.size() ? nd.node_range[r] : 0;
+  }
+  return nd.valid ? 0 : 1;
+}
+
+int tmrgpu_node_mirror(tmrgpu_forest *F, int which, const void **out) {
+  *out = node_mirror_get(F->f, which);
+  return *out ? 0 : 1;
+}
+
+int tmrgpu_set_node_prefetch(tmrgpu_forest *F, int mask) {
+  F->f.nodes.prefetch = mask;
   return 0;
 }
 
@@ -302,6 +311,7 @@ int tmrgpu_coarsen(tmrgpu_forest *src, tmrgpu_forest *dst) {
 
 int tmrgpu_duplicate(tmrgpu_forest *src, tmrgpu_forest *dst) {
   tmrgpu_share_connectivity(src, dst);
+  dst->f.nodes.prefetch = src->f.nodes.prefetch;
   dst->f.owners = src->f.owners; /* reference :2104-2106 */
   return duplicate_into(src->f, dst->f);
 }

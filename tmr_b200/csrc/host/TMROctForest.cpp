@@ -346,30 +346,11 @@ void TMROctForest::dropTables() {
   tables = NULL;
 }
 
-/* host mirrors of the node arrays live in page-locked memory handed out by
-   the CUDA layer (cached there), so reading them back runs at PCIe speed */
-template <class T>
-static T *mirror_alloc(size_t n) {
-  void *p = NULL;
-  tmrgpu_ctx *ctx = tmr_b200_context();
-  if (!ctx || tmrgpu_host_alloc(ctx, (int64_t)((n + 1) * sizeof(T)), &p)) {
-    return NULL;
-  }
-  return static_cast<T *>(p);
-}
-
-static void mirror_free(void *p) {
-  tmrgpu_ctx *ctx = tmr_b200_context();
-  if (p && ctx) tmrgpu_host_free(ctx, p);
-}
-
+/* The host copies of the node arrays are page-locked buffers owned by the
+   device-side forest (tmrgpu_node_mirror): each getter copies only the array
+   it hands out, and the pointers stay valid until the node data is freed. */
 void TMROctForest::dropHostNodeMirrors() {
-  mirror_free(conn);
-  mirror_free(node_numbers);
   delete[] node_range;
-  mirror_free(dep_ptr);
-  mirror_free(dep_conn);
-  mirror_free(dep_weights);
   delete[] X;
   conn = node_numbers = node_range = NULL;
   dep_ptr = dep_conn = NULL;
@@ -684,37 +665,46 @@ void TMROctForest::createNodes() {
   }
 }
 
+/* sizes and the owned-node ranges: a few integers, no array is copied */
 void TMROctForest::fetchNodeData() {
   if (nodes_on_host || !nodes_exist || !dev) return;
   int64_t s[6];
   if (tmrgpu_node_sizes(dev, s)) return;
   dropHostNodeMirrors();
-  const int npe = mesh_order * mesh_order * mesh_order;
   num_elements_nodes = (int)s[0];
   num_local_nodes = (int)s[1];
   num_dep_nodes = (int)s[2];
   num_owned_nodes = (int)s[3];
-  const int nnz = (int)s[4];
-  conn = mirror_alloc<int>((size_t)num_elements_nodes * npe);
-  node_numbers = mirror_alloc<int>(num_local_nodes);
-  dep_ptr = mirror_alloc<int>(num_dep_nodes + 1);
-  dep_conn = mirror_alloc<int>(nnz);
-  dep_weights = mirror_alloc<double>(nnz);
-  tmrgpu_download_nodes(dev, conn, NULL, dep_ptr, dep_conn, dep_weights);
-  /* the reference hands out node_numbers sorted ascending (:4246) */
-  tmrgpu_download_sorted_node_numbers(dev, node_numbers);
   /* node_range: owned-node prefix over ranks (reference :4165-4172) */
   node_range = new int[mpi_size + 1];
   tmrgpu_node_range(dev, node_range);
-  int *item = std::lower_bound(node_numbers, node_numbers + num_local_nodes,
-                               node_range[mpi_rank]);
-  ext_pre_offset = (int)(item - node_numbers);
+  ext_pre_offset = -1; /* needs the sorted node numbers: see fetchNodeNumbers */
   nodes_on_host = 1;
+}
+
+template <class T>
+static T *fetch_mirror(tmrgpu_forest *dev, int which) {
+  const void *p = NULL;
+  if (!dev || tmrgpu_node_mirror(dev, which, &p)) return NULL;
+  return const_cast<T *>(static_cast<const T *>(p));
+}
+
+void TMROctForest::fetchNodeNumbers() {
+  fetchNodeData();
+  if (node_numbers || !nodes_on_host) return;
+  /* the reference hands out node_numbers sorted ascending (:4246) */
+  node_numbers = fetch_mirror<int>(dev, 1);
+  if (node_numbers) {
+    int *item = std::lower_bound(node_numbers, node_numbers + num_local_nodes,
+                                 node_range[mpi_rank]);
+    ext_pre_offset = (int)(item - node_numbers);
+  }
 }
 
 void TMROctForest::getNodeConn(const int **_conn, int *_num_elements,
                                int *_num_owned_nodes, int *_num_local_nodes) {
   fetchNodeData();
+  if (nodes_on_host && !conn) conn = fetch_mirror<int>(dev, 0);
   (void)_num_local_nodes; /* never written by the reference (:5686-5704) */
   int nelems = 0;
   if (dev) nelems = (int)tmrgpu_count(dev);
@@ -726,6 +716,11 @@ void TMROctForest::getNodeConn(const int **_conn, int *_num_elements,
 int TMROctForest::getDepNodeConn(const int **_ptr, const int **_conn,
                                  const double **_weights) {
   fetchNodeData();
+  if (nodes_on_host && !dep_ptr) {
+    dep_ptr = fetch_mirror<int>(dev, 2);
+    dep_conn = fetch_mirror<int>(dev, 3);
+    dep_weights = fetch_mirror<double>(dev, 4);
+  }
   if (_ptr) *_ptr = dep_ptr;
   if (_conn) *_conn = dep_conn;
   if (_weights) *_weights = dep_weights;
@@ -739,13 +734,13 @@ int TMROctForest::getOwnedNodeRange(const int **_node_range) {
 }
 
 int TMROctForest::getNodeNumbers(const int **_node_numbers) {
-  fetchNodeData();
+  fetchNodeNumbers();
   if (_node_numbers) *_node_numbers = node_numbers;
   return num_local_nodes;
 }
 
 int TMROctForest::getExtPreOffset() {
-  fetchNodeData();
+  fetchNodeNumbers();
   return ext_pre_offset;
 }
 
@@ -762,7 +757,7 @@ int TMROctForest::getPoints(TMRPoint **_X) {
 }
 
 int TMROctForest::getLocalNodeNumber(int node) {
-  fetchNodeData();
+  fetchNodeNumbers();
   if (node_numbers) {
     int *end = node_numbers + num_local_nodes;
     int *item = std::lower_bound(node_numbers, end, node);

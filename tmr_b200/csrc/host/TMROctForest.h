@@ -142,6 +142,7 @@ class TMROctForest : public TMREntity {
   int syncOctantsToDevice();
   void octantsReplacedOnDevice();
   void fetchNodeData();
+  void fetchNodeNumbers();
   int ensureDevice();
 
   MPI_Comm comm;
