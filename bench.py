@@ -36,6 +36,14 @@ UNIT = "octants/s"
 FULL = dict(nb=8, level=3, passes=4, pct=35, order=2, corner=0, seed=2024)
 # bounded CPU sample of the same recipe (two passes instead of four)
 CPU_SAMPLE = dict(nb=8, level=3, passes=2, pct=35, order=2, corner=0, seed=2024)
+# BASELINE.json configs[0] (SURVEY.md 8(d) "C1"): one tree, createTrees(4), four
+# passes pct=30 -> 1,027,916 octants.  Small enough for the reference to run in
+# FULL, so both arms time it: the one same-input GPU/CPU comparison.
+C1 = dict(nb=1, level=4, passes=4, pct=30, order=2, corner=0, seed=2024)
+# fingerprints of the reference on C2 / C1 (pinned by the oracle)
+C2_PIN = dict(octants=86278900, checksum="da1d7223d950ef5c", owned_nodes=53774081)
+C1_PIN = dict(octants=1027916, checksum="55e9487c98c7a2ff", owned_nodes=652025,
+              dep_nodes=908576, dep_nnz=2441728)
 
 
 def workload_name(cfg):
@@ -171,6 +179,9 @@ def reference_main(args):
     value, n_final, per_step = run_reference_cycle(cfg, cores, args.steps, args.warmup)
     sample = ("bounded sample: %s -> %d octants, %d thread-ranks (MPI shim), each step = that whole cycle"
               % (workload_name(cfg), n_final, cores))
+    # the same-input comparison: configs[0] (C1) in full, at `cores` ranks and at 1 rank
+    c1_v, c1_n, c1_t = run_reference_cycle(C1, cores, 2, 1)
+    c1_v1, _, c1_t1 = run_reference_cycle(C1, 1, 1, 0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -181,6 +192,10 @@ def reference_main(args):
                          "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
+        "same_config": {"workload": workload_name(C1) + " (BASELINE configs[0], in full)",
+                        "octants": int(c1_n), "value": c1_v, "unit": UNIT, "cores": cores,
+                        "ms_per_step": 1e3 * float(np.mean(c1_t)),
+                        "value_1_rank": c1_v1, "ms_per_step_1_rank": 1e3 * c1_t1[0]},
     }
     emit(line)
 
@@ -216,6 +231,8 @@ def main():
     ap.add_argument("--passes", type=int, default=FULL["passes"],
                     help="refinement passes of the recipe (4 = the named ~86M config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="skip the parity gate that runs before the timed region")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     ap.add_argument("--profile-out", default=None,
@@ -246,6 +263,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    from tmr_b200 import dist as tdist
+
+    numa_cpus = tdist.bind_to_gpu_numa(local)  # page-locked mirrors on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.environ["TMR_B200_DEVICE"] = str(local)
@@ -253,8 +273,6 @@ def main():
     tmr_b200.use_stream(stream.cuda_stream)
     lib = tmr_b200.require_gpu()
     if world > 1:
-        from tmr_b200 import dist as tdist
-
         tdist.init_from_torch(lib)
 
     P, I64 = ctypes.c_void_p, ctypes.c_int64
@@ -277,12 +295,35 @@ def main():
         ("tmrgpu_count", [P]),
         ("tmrgpu_repartition", [P, ctypes.c_int]),
         ("tmrgpu_copy_d2h", [P, P, P, I64]),
+        ("tmrgpu_copy_h2d", [P, P, P, I64]),
+        ("tmrgpu_set_node_prefetch", [P, ctypes.c_int]),
     ]:
         getattr(lib, name).argtypes = argt
     lib.tmrgpu_count.restype = I64
     lib.tmrgpu_launch_count.restype = ctypes.c_long
     lib.tmrgpu_launch_count.argtypes = [P]
     ctx = P(lib.tmr_b200_context())
+
+    # ---- parity gate (before anything is timed) -----------------------------------
+    # N>1: every multi-rank case of tests/multi_gpu_check.py, rank by rank against
+    # the oracle at the same rank count; then the C2 forest split over the N GPUs
+    # must reproduce the reference's fingerprint.  A mismatch ends the run.
+    parity = {"cases": 0, "ok": True}
+    if world > 1 and not args.no_parity:
+        import multi_gpu_check
+
+        ncases, nfail, nunchecked = multi_gpu_check.check_cases(lib, rank, world, verbose=True)
+        parity = {"cases": ncases, "ok": nfail == 0, "failures": nfail,
+                  "without_oracle": nunchecked,
+                  "what": "octants per stage, conn, node numbers, node_range, dependent CSR, "
+                          "prolongation rows of every rank vs the same rank of the reference "
+                          "at %d ranks" % world}
+        if nfail:
+            if rank == 0:
+                emit({"metric": METRIC, "value": None, "parity": parity,
+                      "error": "multi-GPU parity mismatch"})
+            dist.destroy_process_group()
+            sys.exit(1)
 
     cfg = dict(FULL)
     cfg["passes"] = args.passes
@@ -297,50 +338,113 @@ def main():
     # scaling stacks N copies of the 8x8x8-tree box along z (8x8x8N trees);
     # --strong splits the same 8x8x8 box.
     nbz = args.nbz_per_gpu * (1 if (args.strong or world == 1) else world)
-    base = OctForest(order=cfg["order"], lib=lib)
     if args.workload == "c4":
         block_conn = util.butterfly_conn(5, 5, 6 * (1 if (args.strong or world == 1) else world))
     else:
         block_conn = util.structured_conn(cfg["nb"], cfg["nb"], nbz)
-    base.setConnectivity(block_conn)
-    base.createTrees(cfg["level"])
-    bdev = P(lib.tmr_b200_device_forest(base._ptr))
-    if world > 1:
-        assert lib.tmrgpu_repartition(bdev, -1) == 0
 
-    def synth(dev, seed):
+    def synth(dev, seed, pct):
         n = lib.tmrgpu_count(dev)
         buf = P()
         lib.tmrgpu_dev_alloc(ctx, 4 * max(n, 1), ctypes.byref(buf))
-        lib.tmrgpu_synth_flags(dev, seed, cfg["pct"], buf)
+        lib.tmrgpu_synth_flags(dev, seed, pct, buf)
         return buf, n
 
-    for p in range(cfg["passes"] - 1):
-        buf, _ = synth(bdev, cfg["seed"] + p)
-        assert lib.tmrgpu_refine_device(bdev, buf, 0, 30) == 0
-        assert lib.tmrgpu_balance(bdev, cfg["corner"]) == 0
+    def build_base(conn, c):
+        """everything before the timed cycle, all on the device"""
+        b = OctForest(order=c["order"], lib=lib)
+        b.setConnectivity(conn)
+        b.createTrees(c["level"])
+        dev = P(lib.tmr_b200_device_forest(b._ptr))
         if world > 1:
-            assert lib.tmrgpu_repartition(bdev, -1) == 0
-        lib.tmrgpu_dev_free(ctx, buf)
-    d_flags, e_in = synth(bdev, cfg["seed"] + cfg["passes"] - 1)
-    # host copy of the flags for the e2e arm (pinned)
+            assert lib.tmrgpu_repartition(dev, -1) == 0
+        for p in range(c["passes"] - 1):
+            buf, _ = synth(dev, c["seed"] + p, c["pct"])
+            assert lib.tmrgpu_refine_device(dev, buf, 0, 30) == 0
+            assert lib.tmrgpu_balance(dev, c["corner"]) == 0
+            if world > 1:
+                assert lib.tmrgpu_repartition(dev, -1) == 0
+            lib.tmrgpu_dev_free(ctx, buf)
+        flags, n_in = synth(dev, c["seed"] + c["passes"] - 1, c["pct"])
+        return b, dev, flags, n_in
+
+    def cycle(b, flags, c):
+        work = b.duplicate()
+        wdev = P(lib.tmr_b200_device_forest(work._ptr))
+        assert lib.tmrgpu_refine_device(wdev, flags, 0, 30) == 0
+        assert lib.tmrgpu_balance(wdev, c["corner"]) == 0
+        if world > 1:
+            assert lib.tmrgpu_repartition(wdev, -1) == 0
+        assert lib.tmrgpu_create_nodes(wdev, c["order"], 1, knots) == 0
+        return work, wdev
+
+    def fingerprint(wdev):
+        """global (octants, checksum, owned nodes, dependent nodes, stencil entries)"""
+        sz = (I64 * 6)()
+        lib.tmrgpu_node_sizes(wdev, sz)
+        cs_ = ctypes.c_uint64(0)
+        lib.tmrgpu_checksum(wdev, ctypes.byref(cs_))
+        v = torch.tensor([lib.tmrgpu_count(wdev), cs_.value & 0xFFFFFFFF, cs_.value >> 32,
+                          sz[3], sz[2], sz[4]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        v = [int(x) for x in v.tolist()]
+        return {"octants": v[0],
+                "checksum": "%016x" % ((v[1] + (v[2] << 32)) & 0xFFFFFFFFFFFFFFFF),
+                "owned_nodes": v[3], "dep_nodes": v[4], "dep_nnz": v[5]}
+
+    def timed_cycles(b, flags, c, steps, warmup):
+        for _ in range(warmup):
+            w, _ = cycle(b, flags, c)
+            del w
+        barrier()
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        w = None
+        for _ in range(steps):
+            w = None
+            w = cycle(b, flags, c)
+        z.record(stream)
+        barrier()
+        fp = fingerprint(w[1])
+        return a.elapsed_time(z) / steps, fp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # N>1: the SAME C2 forest split over the N GPUs must give the reference's result
+    if world > 1 and not args.no_parity and not args.strong:
+        sb, sdev, sflags, _ = build_base(util.structured_conn(8), FULL)
+        sw, swdev = cycle(sb, sflags, FULL)
+        fp = fingerprint(swdev)
+        ok = all(fp[k] == C2_PIN[k] for k in C2_PIN)
+        parity["c2_split_over_%d_gpus" % world] = dict(fp, matches_reference=ok)
+        parity["ok"] = parity["ok"] and ok
+        del sw, sb
+        lib.tmrgpu_dev_free(ctx, sflags)
+        if not ok:
+            if rank == 0:
+                emit({"metric": METRIC, "value": None, "parity": parity,
+                      "error": "C2 fingerprint mismatch on %d GPUs" % world})
+            dist.destroy_process_group()
+            sys.exit(1)
+
+    base, bdev, d_flags, e_in = build_base(block_conn, cfg)
+    # host copy of the flags (pinned): the e2e arm uploads it every step
     h_flags_t = torch.empty(max(e_in, 1), dtype=torch.int32).pin_memory()
     h_flags = h_flags_t.numpy()[:e_in]
     lib.tmrgpu_copy_d2h(ctx, h_flags.ctypes.data, d_flags, 4 * e_in)
 
     def step_device():
         """device-resident cycle: flags already in HBM"""
-        work = base.duplicate()
-        wdev = P(lib.tmr_b200_device_forest(work._ptr))
-        assert lib.tmrgpu_refine_device(wdev, d_flags, 0, 30) == 0
-        assert lib.tmrgpu_balance(wdev, cfg["corner"]) == 0
-        if world > 1:
-            assert lib.tmrgpu_repartition(wdev, -1) == 0
-        assert lib.tmrgpu_create_nodes(wdev, cfg["order"], 1, knots) == 0
-        return work, wdev
+        return cycle(base, d_flags, cfg)
 
     def step_e2e():
-        """reference-facing API, host flags in, node data out"""
+        """reference-facing API: host flags in; conn, node numbers and the
+        dependent-node CSR out (everything createTACS reads, reference
+        src/TMR_TACSCreator.cpp:332-461)"""
         work = base.duplicate()
         lib.tmrc_refine(work._ptr, h_flags.ctypes.data, 0, 30)  # H2D inside
         lib.tmrc_balance(work._ptr, cfg["corner"])
@@ -350,13 +454,18 @@ def main():
         cptr = ctypes.POINTER(ctypes.c_int)()
         ne, no = ctypes.c_int(0), ctypes.c_int(0)
         lib.tmrc_get_node_conn(work._ptr, ctypes.byref(cptr), ctypes.byref(ne),
-                               ctypes.byref(no))  # D2H of all node arrays
-        return work, ne.value
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+                               ctypes.byref(no))
+        p1, p2 = ctypes.POINTER(ctypes.c_int)(), ctypes.POINTER(ctypes.c_int)()
+        p3 = ctypes.POINTER(ctypes.c_double)()
+        nd_ = lib.tmrc_get_dep_node_conn(work._ptr, ctypes.byref(p1), ctypes.byref(p2),
+                                         ctypes.byref(p3))
+        p4 = ctypes.POINTER(ctypes.c_int)()
+        nn_ = lib.tmrc_get_node_numbers(work._ptr, ctypes.byref(p4))
+        # touch the last word of every array: the copies have landed
+        probe = 0
+        if ne.value:
+            probe += cptr[ne.value * 8 - 1] + p4[nn_ - 1] + p1[nd_]
+        return work, ne.value, probe
 
     # ---- device-resident arm -------------------------------------------------
     lib.tmrgpu_profile_enable(ctx, 0)
@@ -394,6 +503,13 @@ def main():
                            "ms_per_step": v["ms"] / args.steps}
                        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}, fh, indent=1)
     work, wdev = last
+    fp_final = fingerprint(wdev)
+    pinned = (args.workload == "c2" and cfg["passes"] == FULL["passes"] and
+              (world == 1 or args.strong) and args.nbz_per_gpu == 8)
+    if pinned:
+        ok = all(fp_final[k] == C2_PIN[k] for k in C2_PIN)
+        parity["timed_result_matches_reference_c2"] = ok
+        parity["ok"] = parity["ok"] and ok
     e_final = lib.tmrgpu_count(wdev)
     sizes = (I64 * 6)()
     lib.tmrgpu_node_sizes(wdev, sizes)
@@ -420,16 +536,57 @@ def main():
     global_checksum = (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
     value = total_octants * args.steps / (ms * 1e-3)
 
+    # the same cycle with the H2D of the flags inside the timed region
+    def step_device_h2d():
+        lib.tmrgpu_copy_h2d(ctx, d_flags, h_flags.ctypes.data, 4 * e_in)
+        return cycle(base, d_flags, cfg)
+
+    w = step_device_h2d()
+    del w
+    barrier()
+    a_, z_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_.record(stream)
+    for _ in range(args.steps):
+        w = None
+        w = step_device_h2d()
+    z_.record(stream)
+    barrier()
+    del w
+    th = torch.tensor([a_.elapsed_time(z_)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    value_h2d = total_octants * args.steps / (float(th.item()) * 1e-3)
+
+    # BASELINE configs[0] (C1) in full on the GPU: the reference arm times the same
+    # input in full, so this pair is a same-config comparison
+    same_config = None
+    if world == 1 and not args.no_parity:
+        b1, d1, f1, _ = build_base(util.structured_conn(1), C1)
+        c1_ms, c1_fp = timed_cycles(b1, f1, C1, max(args.steps, 5), 2)
+        c1_ok = all(c1_fp[k] == C1_PIN[k] for k in C1_PIN)
+        parity["c1_matches_reference"] = c1_ok
+        parity["ok"] = parity["ok"] and c1_ok
+        same_config = {"workload": workload_name(C1) + " (BASELINE configs[0], in full)",
+                       "octants": c1_fp["octants"], "ms_per_step": c1_ms,
+                       "value": c1_fp["octants"] / (c1_ms * 1e-3), "unit": UNIT,
+                       "fingerprint": c1_fp}
+        del b1
+        lib.tmrgpu_dev_free(ctx, f1)
+
     # ---- end-to-end arm --------------------------------------------------------
+    # node arrays are copied to page-locked host memory on a second stream as
+    # soon as each is final (conn after the renumbering, the dependent CSR at
+    # the end): the 5.9 GB read-back overlaps the rest of createNodes
+    lib.tmrgpu_set_node_prefetch(bdev, 7)
     for _ in range(max(1, args.warmup - 1)):
-        w, _ = step_e2e()
+        w = step_e2e()
         del w
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
-        w, ne = step_e2e()
+        w = step_e2e()
         del w
     e1.record(stream)
     barrier()
@@ -439,6 +596,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_octants * args.steps / (float(t.item()) * 1e-3)
+    lib.tmrgpu_set_node_prefetch(bdev, 0)
     npe = cfg["order"] ** 3
     d2h = 4 * (sizes[0] * npe + sizes[1] + sizes[2] + 1 + sizes[4]) + 8 * sizes[4]
 
@@ -452,22 +610,31 @@ def main():
         name, st = dom
         # algorithmic bytes per launch of the dominant kernel
         n_pairs = sizes[0] * npe
+        n_slot_nodes = sizes[1]
         alg = {"radix_pass_pairs[nodes]": 2 * 12 * n_cand,
                "radix_pass_keys[nodes]": 2 * 8 * n_cand,
                "radix_pass_keys[leaves]": 2 * 8 * e_final,
                "radix_hist[nodes]": 8 * n_cand,
                "nodes_candidates": 8 * sizes[0] + 8 * n_cand,
                "nodes_unique_scatter_conn": 8 * n_cand + 4 * n_pairs + 8 * sizes[1],
+               # keys in; (leaf, slot) of every corner out; slot masks read+written;
+               # one 16-byte rank entry per 64 finest cells of the forest
+               "nodes_slot_locate": (8 + 4 * npe + npe + 8) * sizes[0]
+                                    + 16 * (len(block_conn) << (3 * 7)) // 64,
+               "nodes_slot_resolve": (2 * 4 * npe + npe + 8) * sizes[0],
+               "nodes_slot_keys": 16 * sizes[0] + 8 * n_slot_nodes,
+               "nodes_conn_remap": 2 * 4 * n_pairs + 4 * sizes[1],
+               "nodes_dep_winner": (8 + 2 + 4 * npe) * sizes[0] + 16 * sizes[2],
                "nodes_dep_fill": 12 * sizes[4] + 16 * sizes[2],
                "nodes_hanging_info": 10 * sizes[0]}.get(name)
         avg_ms = st["ms"] / st["launches"]
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as fh:
-                ent = json.load(fh).get(name)
-            # only valid for the launch shape it was captured on
-            if ent and abs(ent["keys"] - n_cand) <= 0.01 * n_cand:
-                traffic = ent["traffic_bytes_per_launch"]
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as fh:
+                ent = json.load(fh)["kernels"].get(name)
+            # only valid for the launch shape it was captured on (the C2 cycle)
+            if ent and pinned:
+                traffic = ent["dram_bytes_per_launch"]
         except Exception:
             traffic = None
         if alg:
@@ -486,6 +653,27 @@ def main():
     b_alg = (28 * e_in + 24 * e_in + 24 * e_in + 24 * e_final + 24 * e_final
              + 4 * npe * e_final + 4 * sizes[1] + 4 * (sizes[2] + 1) + 12 * sizes[4])
     cycle_frac = b_alg * args.steps / (ms * 1e-3) / 1e9 / peak
+
+    # whole cycle, measured: DRAM bytes of every kernel of one C2 cycle from the
+    # committed ncu capture (profiles/ncu_traffic_r02.json, tools/ncu_cycle.py),
+    # weighted with the kernel times measured live above
+    cycle_dram = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as fh:
+            cap = json.load(fh)
+        if pinned:
+            tot_b = sum(k["dram_bytes_per_step"] for k in cap["kernels"].values())
+            kern_ms = sum(v["ms"] for v in prof.values()) / args.steps
+            cycle_dram = {
+                "measured_dram_bytes_per_cycle": int(tot_b),
+                "amplification_vs_compulsory": tot_b / b_alg,
+                "dram_gbs_over_kernel_time": tot_b / (kern_ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak_over_kernel_time": tot_b / (kern_ms * 1e-3) / 1e9 / peak,
+                "frac_of_hbm_peak_over_step_time": tot_b / (ms / args.steps * 1e-3) / 1e9 / peak,
+                "source": "ncu dram__bytes_read+write of every kernel of one cycle (%s), "
+                          "times measured live" % cap.get("captured", "profiles/")}
+    except Exception:
+        cycle_dram = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -522,18 +710,29 @@ def main():
                        % (world, "strong" if args.strong else "weak", cfg["nb"], cfg["nb"], nbz),
                        "l2": "inputs larger than L2 (%.0f MB of keys per pass)" % (8e-6 * e_final)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * e_in),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t.item()) / args.steps,
+                    "what": "TMROctForest API: refine(host flags) + balance + createNodes + "
+                            "getNodeConn + getDepNodeConn + getNodeNumbers; read-back overlapped "
+                            "with createNodes on a copy stream"},
+            "value_with_flags_h2d": value_h2d,
+            "parity": parity,
+            "same_config": same_config,
+            "fingerprint": fp_final,
+            "numa_bound_cpus": numa_cpus,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
             "cycle_compulsory_bytes": int(b_alg),
             "cycle_frac_of_hbm_peak": cycle_frac,
+            "cycle_dram_measured": cycle_dram,
             "kernel_share_of_step": kernel_share,
             "cpu_baseline": cpu,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not parity["ok"]:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

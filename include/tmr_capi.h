@@ -133,6 +133,29 @@ void tmrc_array_contains(tmrc_octant *array, int n, int use_node_index,
                          const tmrc_octant *queries, int nq, int use_position,
                          int *out_index);
 
+/* merge(): set union of two arrays, `a` keeps its entry on ties (reference
+   src/TMROctant.cpp:429-509); both are sorted first if needed.  Returns the
+   merged size (out may be NULL to query it). */
+int tmrc_array_merge(const tmrc_octant *a, int na, const tmrc_octant *b, int nb,
+                     int use_node_index, tmrc_octant *out, int cap);
+
+/* ---- TMROctantQueue (reference src/TMROctant.h:89-113, .cpp:514-590) ---- */
+/* push `n` octants, pop `npop` (into popped[]), toArray() the rest into rest[];
+   returns length() after the pops */
+int tmrc_queue_exercise(const tmrc_octant *in, int n, int npop,
+                        tmrc_octant *popped, tmrc_octant *rest);
+
+/* ---- TMROctantHash (reference src/TMROctant.h:121-151, .cpp:599-798) ---- */
+/* addOctant() for every input (added[i] = its return value), then toArray();
+   returns the number of unique octants.  The ORDER of toArray() is a hash
+   detail callers never rely on (they sort): compare as sets. */
+int tmrc_hash_exercise(const tmrc_octant *in, int n, int use_node_index,
+                       int *added, tmrc_octant *out, int cap);
+
+/* a forest on MPI_COMM_SELF: not partitioned even inside a multi-rank job
+   (reference src/TMROctForest.cpp:331-337) */
+tmrc_forest tmrc_forest_create_self(int mesh_order, int interp_type);
+
 #ifdef __cplusplus
 }
 #endif

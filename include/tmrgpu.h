@@ -53,6 +53,11 @@ int tmrgpu_ctx_size(tmrgpu_ctx *ctx);
 
 /* ---- forest -------------------------------------------------------------- */
 int tmrgpu_forest_create(tmrgpu_ctx *ctx, tmrgpu_forest **out);
+/* The forest lives on this GPU alone although the context has a communicator:
+   a TMROctForest constructed on a one-rank communicator (MPI_COMM_SELF) inside
+   a multi-rank job (reference src/TMROctForest.cpp:331-337 takes rank and size
+   from the communicator it is given).  Inherited by duplicate / coarsen. */
+int tmrgpu_forest_set_serial(tmrgpu_forest *f, int serial);
 int tmrgpu_forest_destroy(tmrgpu_forest *f);
 
 /* Super-mesh tables computed by the host class (replaces the reads of

@@ -22,20 +22,15 @@ import multirank  # noqa: E402
 import util  # noqa: E402
 
 
-def main():
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    os.environ["TMR_B200_DEVICE"] = str(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import tmr_b200
-    from tmr_b200 import dist as tdist
-
-    lib = tmr_b200.require_gpu()
-    rank, size = tdist.init_from_torch(lib)
+def check_cases(lib, rank, size, verbose=True):
+    """Run every multi-rank case defined for `size` ranks on the GPUs (one
+    process per GPU, NCCL already initialised) and compare each rank's results
+    with the same rank of the oracle run at the same rank count.  Returns
+    (cases, failures, cases without an oracle) on every rank."""
     from oracle import ref_loader
 
     ref = ref_loader.load() if (rank == 0 and ref_loader.available()) else None
-    failures = 0
+    failures = unchecked = 0
     cases = [c for c in multirank.CASES if c[7] == size]
     # a heavier case at this rank count: 2x2x2 trees, 4 passes
     cases.append(("grid2_big_r%d" % size, "grid2", 2, 4, 35, 0, 2, size, True))
@@ -61,17 +56,35 @@ def main():
                     multirank.compare_rank_results(expect, gathered, name)
                     how = "bit-exact vs reference at %d ranks" % size
                 else:
+                    unchecked += 1
                     how = "oracle not available: only ran"
                 allocts = np.concatenate([g[0][-1] for g in gathered])
-                print("[multi-gpu] %-28s OK  %8d octants  checksum %016x  (%s)" %
-                      (name, total, util.checksum(allocts), how), flush=True)
+                if verbose:
+                    print("[multi-gpu] %-28s OK  %8d octants  checksum %016x  (%s)" %
+                          (name, total, util.checksum(allocts), how), file=sys.stderr,
+                          flush=True)
             except AssertionError as e:
                 failures += 1
-                print("[multi-gpu] %-28s FAIL %s" % (name, str(e)[:400]), flush=True)
-    flag = torch.tensor([failures], device="cuda")
+                print("[multi-gpu] %-28s FAIL %s" % (name, str(e)[:400]), file=sys.stderr,
+                      flush=True)
+    flag = torch.tensor([failures, unchecked], device="cuda")
     dist.broadcast(flag, src=0)
+    return len(cases), int(flag[0].item()), int(flag[1].item())
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["TMR_B200_DEVICE"] = str(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import tmr_b200
+    from tmr_b200 import dist as tdist
+
+    lib = tmr_b200.require_gpu()
+    rank, size = tdist.init_from_torch(lib)
+    _, failures, _ = check_cases(lib, rank, size)
     dist.destroy_process_group()
-    sys.exit(1 if int(flag.item()) else 0)
+    sys.exit(1 if failures else 0)
 
 
 if __name__ == "__main__":

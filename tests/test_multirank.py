@@ -118,3 +118,41 @@ def test_partition_counts():
     assert dist.partition_counts(10, 4, 2) == [5, 5, 0, 0]
     assert dist.partition_counts(3, 8) == [1, 1, 1, 0, 0, 0, 0, 0]
     assert sum(dist.partition_counts(86278900, 8)) == 86278900
+
+
+def test_serial_forest_inside_multirank_job(emu_lib, ref_lib):
+    """A TMROctForest built on MPI_COMM_SELF while the process belongs to a
+    multi-rank world is not partitioned: every rank gets the full single-rank
+    result (reference src/TMROctForest.cpp:331-337 takes rank and size from
+    the communicator it is given)."""
+    from tmr_b200.forest import OctForest
+
+    conn = util.box_conn()
+
+    def body(lib, rank):
+        # a partitioned forest first, so the world communicator is in use
+        w = OctForest(order=2, lib=lib)
+        w.setConnectivity(conn)
+        w.createTrees(1)
+        w.repartition()
+        f = OctForest(order=2, lib=lib, comm_self=True)
+        f.setConnectivity(conn)
+        f.createTrees(1)
+        f.repartition()
+        rec = []
+        for p in range(2):
+            o = f.getOctants().as_array()
+            f.refine(util.synth_flags(o, 2024 + p, 30))
+            f.balance(1)
+            rec.append(f.getOctants().as_array().copy())
+        res = util.node_results(f)
+        c = f.coarsen()
+        c.balance(1)
+        rows, d = util.interp_rows(f.createInterpolation(c))
+        res["interp"] = {r: (cc.copy(), ww.copy()) for r, (cc, ww) in d.items()}
+        return rec, res
+
+    one = multirank.run_thread_ranks(ref_lib, 1, body, True)
+    for ranks in (2, 3):
+        got = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+        multirank.compare_rank_results(one * ranks, got, "serial in %d-rank job" % ranks)

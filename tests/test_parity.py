@@ -450,3 +450,85 @@ def test_write_through_octant_array(impl, ref_lib):
     util.assert_octants_equal(outs[0][0], outs[1][0], "write-through")
     util.assert_octants_equal(outs[0][1], outs[1][1], "write-through + createNodes")
     assert (outs[1][1]["tag"] >= 1000).all()
+
+
+def _oct_ptr(a):
+    return a.ctypes.data if len(a) else None
+
+
+@pytest.mark.parametrize("node_mode", [0])
+def test_octant_array_merge(node_mode, impl, ref_lib):
+    """TMROctantArray::merge (reference src/TMROctant.cpp:429-509): set union,
+    `this` keeps its entry on ties, unsorted inputs are sorted first.  Element
+    arrays only: the reference sorts node arrays with compareNode but merges
+    with compare(), which overruns its own buffer on node arrays (and nothing
+    in the reference calls merge at all)."""
+    rng = np.random.default_rng(5 + node_mode)
+    for na, nb in ((0, 0), (0, 7), (9, 0), (40, 40), (500, 333)):
+        a = util.random_octants(rng, na, 3, 4)
+        b = util.random_octants(rng, nb, 3, 4)
+        if na >= 40 and nb >= 40:
+            b[: nb // 3] = a[: nb // 3]  # common entries
+            b["tag"][: nb // 3] = 77     # ... told apart by the tag: a's survive
+        if node_mode:
+            a["info"] = rng.integers(0, 3, na)
+            b["info"] = rng.integers(0, 3, nb)
+        res = []
+        for lib in (ref_lib, impl):
+            out = np.zeros(na + nb + 1, dtype=_capi.OCT_DTYPE)
+            n = lib.tmrc_array_merge(_oct_ptr(a), na, _oct_ptr(b), nb, node_mode,
+                                     out.ctypes.data, len(out))
+            res.append(out[:n].copy())
+        assert len(res[0]) == len(res[1]), (na, nb)
+        for fld in ("block", "x", "y", "z", "level", "tag"):
+            assert np.array_equal(res[0][fld], res[1][fld]), (na, nb, fld)
+
+
+def test_octant_queue(impl, ref_lib):
+    """TMROctantQueue push / pop / length / toArray: FIFO (reference
+    src/TMROctant.cpp:514-590)."""
+    rng = np.random.default_rng(3)
+    for n, npop in ((0, 0), (1, 1), (50, 17), (50, 50), (20, 30)):
+        rec = util.random_octants(rng, n, 2, 5)
+        res = []
+        for lib in (ref_lib, impl):
+            popped = np.zeros(max(npop, 1), dtype=_capi.OCT_DTYPE)
+            rest = np.zeros(max(n, 1), dtype=_capi.OCT_DTYPE)
+            left = lib.tmrc_queue_exercise(_oct_ptr(rec), n, npop, popped.ctypes.data,
+                                           rest.ctypes.data)
+            res.append((left, popped[: min(n, npop)].copy(), rest[:left].copy()))
+        assert res[0][0] == res[1][0] == max(0, n - npop)
+        assert res[0][1].tobytes() == res[1][1].tobytes()
+        assert res[0][2].tobytes() == res[1][2].tobytes()
+        assert res[1][1].tobytes() == rec[: min(n, npop)].tobytes()
+
+
+@pytest.mark.parametrize("node_mode", [0, 1])
+def test_octant_hash(node_mode, impl, ref_lib):
+    """TMROctantHash::addOctant / toArray (reference src/TMROctant.cpp:599-798):
+    which insertions are new, and the unique set (toArray order is a hash detail
+    every caller sorts away, so sets are compared).  50 000 entries cross the
+    reference's rehash threshold (10 x 4095)."""
+    rng = np.random.default_rng(17 + node_mode)
+    for n in (0, 1, 300, 50000):
+        rec = util.random_octants(rng, n, 3, 5 if n < 1000 else 8)
+        if n >= 300:
+            rec[n // 2:] = rec[: n - n // 2]  # every entry twice
+            if node_mode:
+                rec["info"] = rng.integers(0, 2, n)
+            else:
+                rec["level"][: n // 10] += 1  # same anchor, other level: distinct
+        res = []
+        for lib in (ref_lib, impl):
+            added = np.zeros(max(n, 1), dtype=np.int32)
+            out = np.zeros(max(n, 1), dtype=_capi.OCT_DTYPE)
+            m = lib.tmrc_hash_exercise(_oct_ptr(rec), n, node_mode, added.ctypes.data,
+                                       out.ctypes.data, len(out))
+            o = out[:m]
+            key = np.lexsort((o["info"] if node_mode else o["level"], o["z"], o["y"],
+                              o["x"], o["block"]))
+            res.append((added[:n].copy(), o[key].copy()))
+        assert np.array_equal(res[0][0], res[1][0])
+        assert len(res[0][1]) == len(res[1][1])
+        for fld in ("block", "x", "y", "z", "level", "info", "tag"):
+            assert np.array_equal(res[0][1][fld], res[1][1][fld]), fld

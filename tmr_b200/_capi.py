@@ -69,6 +69,10 @@ SIGNATURES = {
     "tmrc_interp_get": (None, [P, PI, PI, PPI, PPI, PPI, PPD]),
     "tmrc_array_sort": (I, [P, I, I]),
     "tmrc_array_contains": (None, [P, I, I, P, I, I, P]),
+    "tmrc_array_merge": (I, [P, I, P, I, I, P, I]),
+    "tmrc_queue_exercise": (I, [P, I, I, P, P]),
+    "tmrc_hash_exercise": (I, [P, I, I, P, P, I]),
+    "tmrc_forest_create_self": (P, [I, I]),
 }
 
 

@@ -29,6 +29,13 @@ tmrc_forest tmrc_forest_create(int mesh_order, int interp_type) {
   return forest;
 }
 
+tmrc_forest tmrc_forest_create_self(int mesh_order, int interp_type) {
+  TMROctForest *forest = new TMROctForest(
+      MPI_COMM_SELF, mesh_order, (TMRInterpolationType)interp_type);
+  forest->incref();
+  return forest;
+}
+
 void tmrc_forest_destroy(tmrc_forest f) {
   if (f) F(f)->decref();
 }
@@ -290,6 +297,66 @@ void tmrc_array_contains(tmrc_octant *array, int n, int use_node_index,
     TMROctant *t = arr.contains(&q, use_position);
     out_index[i] = t ? (int)(t - sorted) : -1;
   }
+}
+
+
+static TMROctantArray *copy_to_array(const tmrc_octant *a, int n, int use_node_index) {
+  TMROctant *copy = new TMROctant[n > 0 ? n : 1];
+  if (n > 0) memcpy(copy, a, (size_t)n * sizeof(TMROctant));
+  return new TMROctantArray(copy, n, use_node_index);
+}
+
+int tmrc_array_merge(const tmrc_octant *a, int na, const tmrc_octant *b, int nb,
+                     int use_node_index, tmrc_octant *out, int cap) {
+  TMROctantArray *A = copy_to_array(a, na, use_node_index);
+  TMROctantArray *B = copy_to_array(b, nb, use_node_index);
+  A->merge(B);
+  TMROctant *arr = NULL;
+  int size = 0;
+  A->getArray(&arr, &size);
+  if (out && size <= cap && size > 0) memcpy(out, arr, (size_t)size * sizeof(TMROctant));
+  delete A;
+  delete B;
+  return size;
+}
+
+int tmrc_queue_exercise(const tmrc_octant *in, int n, int npop,
+                        tmrc_octant *popped, tmrc_octant *rest) {
+  TMROctantQueue q;
+  for (int i = 0; i < n; i++) {
+    TMROctant o;
+    memcpy(&o, &in[i], sizeof(TMROctant));
+    q.push(&o);
+  }
+  for (int i = 0; i < npop && q.length() > 0; i++) {
+    TMROctant o = q.pop();
+    memcpy(&popped[i], &o, sizeof(TMROctant));
+  }
+  const int left = q.length();
+  TMROctantArray *arr = q.toArray();
+  TMROctant *a = NULL;
+  int size = 0;
+  arr->getArray(&a, &size);
+  if (size > 0) memcpy(rest, a, (size_t)size * sizeof(TMROctant));
+  delete arr;
+  return left;
+}
+
+int tmrc_hash_exercise(const tmrc_octant *in, int n, int use_node_index,
+                       int *added, tmrc_octant *out, int cap) {
+  TMROctantHash h(use_node_index);
+  for (int i = 0; i < n; i++) {
+    TMROctant o;
+    memcpy(&o, &in[i], sizeof(TMROctant));
+    added[i] = h.addOctant(&o);
+  }
+  TMROctantArray *arr = h.toArray();
+  TMROctant *a = NULL;
+  int size = 0;
+  arr->getArray(&a, &size);
+  if (out && size <= cap && size > 0) memcpy(out, a, (size_t)size * sizeof(TMROctant));
+  delete arr;
+  return size;
 }
 
 }  // extern "C"

@@ -134,12 +134,16 @@ struct Forest {
   /* SFC partition: owners[r] = first octant of rank r (reference `owners`,
      src/TMROctForest.h:270); empty for a single rank */
   std::vector<Oct24> owners;
+  /* a forest built on a one-rank communicator (MPI_COMM_SELF in a multi-rank
+     job) lives on this GPU alone: no exchange, whatever the context's
+     communicator is */
+  bool serial;
   /* counters describing the last operation (for bench/roofline reporting) */
   i64 last_in, last_mid, last_out;
 
   explicit Forest(Ctx *c)
-      : ctx(c), nblocks(0), bbits(1), n(0), last_in(0), last_mid(0),
-        last_out(0) {
+      : ctx(c), nblocks(0), bbits(1), n(0), serial(false), last_in(0),
+        last_mid(0), last_out(0) {
     fmt.D = 0;
     fmt.bbits = 1;
     tables = ConnTables();
@@ -148,8 +152,10 @@ struct Forest {
   }
 };
 
-inline int part_rank(const Forest &f) { return f.ctx->comm ? f.ctx->comm->rank : 0; }
-inline int part_size(const Forest &f) { return f.ctx->comm ? f.ctx->comm->size : 1; }
+/* the communicator the forest is partitioned over (NULL = this GPU alone) */
+inline Comm *forest_comm(const Forest &f) { return f.serial ? NULL : f.ctx->comm; }
+inline int part_rank(const Forest &f) { return forest_comm(f) ? forest_comm(f)->rank : 0; }
+inline int part_size(const Forest &f) { return forest_comm(f) ? forest_comm(f)->size : 1; }
 
 inline int bits_for(int nblocks) {
   int b = 1;

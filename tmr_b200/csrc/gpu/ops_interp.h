@@ -505,7 +505,7 @@ struct FoundFillFn {
 
 inline int create_interp(Forest &fine, Forest &coarse) {
   Ctx &ctx = *fine.ctx;
-  Comm *comm = ctx.comm;
+  Comm *comm = forest_comm(fine);
   NodeData &fn = fine.nodes;
   NodeData &cn = coarse.nodes;
   InterpData &I = fine.interp;

@@ -22,7 +22,7 @@ namespace tmrgpu {
    tag -1) for an empty rank (reference :1805-1832, :2062-2081) */
 inline int gather_owners(Forest &f, int backfill) {
   Ctx &ctx = *f.ctx;
-  Comm *comm = ctx.comm;
+  Comm *comm = forest_comm(f);
   if (!comm) {
     f.owners.clear();
     return 0;
@@ -59,7 +59,7 @@ inline int gather_owners(Forest &f, int backfill) {
 /* make the key depth identical on all ranks (the deepest level anywhere) */
 inline int unify_depth(Forest &f) {
   Ctx &ctx = *f.ctx;
-  Comm *comm = ctx.comm;
+  Comm *comm = forest_comm(f);
   if (!comm) return 0;
   const int Dg = (int)global_max(ctx, *comm, f.fmt.D);
   if (Dg != f.fmt.D) {
@@ -79,7 +79,7 @@ inline int unify_depth(Forest &f) {
 /* ---- repartition (reference :1922-2088) ------------------------------------------ */
 inline int repartition(Forest &f, int max_rank) {
   Ctx &ctx = *f.ctx;
-  Comm *comm = ctx.comm;
+  Comm *comm = forest_comm(f);
   f.nodes.clear();
   f.interp.clear();
   if (!comm) return 0;
@@ -138,7 +138,7 @@ struct CountForeignFn {
 
 inline int refine_exchange(Forest &f) {
   Ctx &ctx = *f.ctx;
-  Comm *comm = ctx.comm;
+  Comm *comm = forest_comm(f);
   if (!comm) return 0;
   if (unify_depth(f)) return 1;
   DBuf<u64> own_store;
@@ -278,7 +278,7 @@ struct LeafOwnerFn {
 
 inline int balance_multi(Forest &f, int balance_corner) {
   Ctx &ctx = *f.ctx;
-  Comm &comm = *ctx.comm;
+  Comm &comm = *forest_comm(f);
   const int me = comm.rank;
   f.last_mid = f.n;
   f.info.reset();

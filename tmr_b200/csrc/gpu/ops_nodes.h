@@ -1501,7 +1501,7 @@ inline int build_sorted_numbers(Forest &f, DBuf<int> &out) {
   if (!nd.valid) return 1;
   out.alloc(ctx, n);
   if (n == 0) return 0;
-  if (!ctx.comm) {
+  if (!forest_comm(f)) {
     /* one rank: the numbers are -Nd..-1 (dependent) and 0..owned-1, every
        value once -- the sorted array is a range, no sort needed */
     NumberRangeFn r = {-(int)nd.num_dep_nodes, out.get()};
@@ -1917,7 +1917,7 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
                              const unsigned char *fmask, u64 k_first, u64 k_last,
                              DBuf<unsigned char> &created, i64 *Nn_out) {
   Ctx &ctx = *f.ctx;
-  Comm *comm = ctx.comm;
+  Comm *comm = forest_comm(f);
   const i64 E = f.n;
   const int D = f.fmt.D;
   DBuf<u32> mask(ctx, E), cmask;
@@ -2025,7 +2025,7 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
 inline int create_nodes(Forest &f, int order, int interp_type,
                         const double *knots) {
   Ctx &ctx = *f.ctx;
-  Comm *comm = ctx.comm;
+  Comm *comm = forest_comm(f);
   const int me = comm ? comm->rank : 0;
   NodeData &nd = f.nodes;
   if (nd.valid) return 0; /* reference :4071-4075 */

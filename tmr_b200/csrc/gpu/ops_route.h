@@ -49,7 +49,7 @@ inline OwnerMap make_owner_map(Forest &f, int Dp, DBuf<u64> &store) {
   store.alloc(*f.ctx, (i64)h.size());
   copy_h2d(*f.ctx, store.get(), h.data(), h.size() * sizeof(u64));
   const int R = (int)h.size();
-  const int me = (f.ctx->comm && R > 1) ? f.ctx->comm->rank : 0;
+  const int me = (forest_comm(f) && R > 1) ? forest_comm(f)->rank : 0;
   OwnerMap m = {store.get(), R, me, me > 0 ? h[me] : 0ULL,
                 me + 1 < R ? h[me + 1] : ~0ULL};
   return m;

@@ -96,6 +96,11 @@ int tmrgpu_forest_create(tmrgpu_ctx *ctx, tmrgpu_forest **out) {
   return 0;
 }
 
+int tmrgpu_forest_set_serial(tmrgpu_forest *f, int serial) {
+  f->f.serial = serial != 0;
+  return 0;
+}
+
 int tmrgpu_forest_destroy(tmrgpu_forest *f) {
   delete f;
   return 0;
@@ -299,12 +304,13 @@ int tmrgpu_exchange_records(tmrgpu_ctx *ctx, const tmrgpu_octant *send,
 }
 
 int tmrgpu_balance(tmrgpu_forest *f, int balance_corner) {
-  if (f->f.ctx->comm) return balance_multi(f->f, balance_corner);
+  if (forest_comm(f->f)) return balance_multi(f->f, balance_corner);
   return balance(f->f, balance_corner);
 }
 
 int tmrgpu_coarsen(tmrgpu_forest *src, tmrgpu_forest *dst) {
   tmrgpu_share_connectivity(src, dst);
+  dst->f.serial = src->f.serial;
   if (coarsen_into(src->f, dst->f)) return 1;
   return gather_owners(dst->f, 0); /* reference :2157-2160 */
 }
@@ -312,6 +318,7 @@ int tmrgpu_coarsen(tmrgpu_forest *src, tmrgpu_forest *dst) {
 int tmrgpu_duplicate(tmrgpu_forest *src, tmrgpu_forest *dst) {
   tmrgpu_share_connectivity(src, dst);
   dst->f.nodes.prefetch = src->f.nodes.prefetch;
+  dst->f.serial = src->f.serial;
   dst->f.owners = src->f.owners; /* reference :2104-2106 */
   return duplicate_into(src->f, dst->f);
 }

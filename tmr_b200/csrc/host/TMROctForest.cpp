@@ -338,7 +338,11 @@ int TMROctForest::ensureDevice() {
   if (dev) return 0;
   tmrgpu_ctx *ctx = tmr_b200_context();
   if (!ctx) return 1;
-  return tmrgpu_forest_create(ctx, &dev);
+  if (tmrgpu_forest_create(ctx, &dev)) return 1;
+  /* a one-rank communicator (MPI_COMM_SELF) inside a multi-rank job: this
+     forest is not partitioned, whatever communicator the context holds */
+  if (mpi_size == 1) tmrgpu_forest_set_serial(dev, 1);
+  return 0;
 }
 
 void TMROctForest::dropTables() {
@@ -1037,7 +1041,11 @@ TMROctantArray *TMROctForest::distributeOctants(TMROctantArray *list,
     counts[i] = (!include_local && i == mpi_rank) ? 0 : oct_ptr[i + 1] - oct_ptr[i];
   }
   tmrgpu_ctx *ctx = tmr_b200_context();
-  if (ctx) tmrgpu_exchange_counts(ctx, counts.data(), recv_counts.data());
+  if (mpi_size == 1) {
+    recv_counts[0] = counts[0];
+  } else if (ctx) {
+    tmrgpu_exchange_counts(ctx, counts.data(), recv_counts.data());
+  }
   oct_recv_ptr[0] = 0;
   for (int i = 0; i < mpi_size; i++) {
     oct_recv_ptr[i + 1] = oct_recv_ptr[i] + recv_counts[i];
@@ -1087,7 +1095,11 @@ TMROctantArray *TMROctForest::sendOctants(TMROctantArray *list,
     for (int i = r + 1; i <= mpi_size; i++) recv_ptr[i] -= local_recv;
   }
   tmrgpu_ctx *ctx = tmr_b200_context();
-  if (ctx) {
+  if (mpi_size == 1) {
+    if (recv_ptr[1] > 0) {
+      memcpy(&recv[oct_recv_ptr[0]], stage.data(), (size_t)recv_ptr[1] * sizeof(TMROctant));
+    }
+  } else if (ctx) {
     std::vector<TMROctant> tmp(recv_ptr[mpi_size] > 0 ? recv_ptr[mpi_size] : 1);
     tmrgpu_exchange_records(
         ctx, reinterpret_cast<const tmrgpu_octant *>(stage.data()),

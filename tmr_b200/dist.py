@@ -54,3 +54,28 @@ def init_from_torch(lib=None):
     dist.broadcast(t, src=0)
     init_world(lib, rank, size, bytes(t.cpu().tolist()))
     return rank, size
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores local to its GPU (NVML's ideal CPU
+    affinity), so that page-locked host mirrors are allocated on the GPU's own
+    NUMA node: with one process per GPU, node-array read-backs then do not
+    cross the inter-socket link.  Returns the number of CPUs bound to, or 0
+    when NVML is unavailable (nothing changed)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001
+        return 0

@@ -76,13 +76,17 @@ class OctForest:
     """Forest of octrees behind the TMROctForest C++ class
     (reference src/TMROctForest.h:46-181)."""
 
-    def __init__(self, order=2, interp=GAUSS_LOBATTO_POINTS, lib=None, _ptr=None):
+    def __init__(self, order=2, interp=GAUSS_LOBATTO_POINTS, lib=None, _ptr=None,
+                 comm_self=False):
+        """comm_self: construct on MPI_COMM_SELF (an unpartitioned forest, also
+        inside a multi-rank job) instead of the world communicator."""
         if lib is None:
             from . import load_library
 
             lib = load_library()
         self._lib = lib
-        self._ptr = _ptr if _ptr is not None else lib.tmrc_forest_create(order, interp)
+        create = lib.tmrc_forest_create_self if comm_self else lib.tmrc_forest_create
+        self._ptr = _ptr if _ptr is not None else create(order, interp)
         if not self._ptr:
             raise RuntimeError("TMROctForest construction failed")
 
