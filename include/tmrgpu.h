@@ -196,6 +196,10 @@ int tmrgpu_checksum(tmrgpu_forest *f, uint64_t *out);
 /* raw device allocations for bench-owned buffers */
 int tmrgpu_dev_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out);
 int tmrgpu_dev_free(tmrgpu_ctx *ctx, void *p);
+/* test hook: the nth next device allocation of this context fails (0 = off).
+   The operation it hits must print "TMROctForest Error", launch nothing on
+   the missing buffer, return nonzero, and leave the context usable. */
+int tmrgpu_test_fail_alloc(tmrgpu_ctx *ctx, long nth);
 /* page-locked host buffers (cached per context) for the host mirrors the
    drop-in hands out, so that D2H runs at PCIe speed */
 int tmrgpu_host_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out);

@@ -66,10 +66,11 @@ u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *) {
 
 template <class F, class G>
 u64 scan_apply(Ctx &ctx, i64 n, F f, G g, const char *) {
+  typedef decltype(f((i64)0)) T;
   u64 run = 0;
   for (i64 i = 0; i < n; i++) {
-    const u32 c = f(i);
-    g(i, (u32)run);
+    const T c = f(i);
+    g(i, (T)run);
     run += c;
   }
   ctx.launch_count++;

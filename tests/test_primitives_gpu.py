@@ -72,3 +72,31 @@ def test_scan_counts(prim, n):
     ex = np.cumsum(c, dtype=np.uint64) - c
     assert total.value == int(c.sum(dtype=np.uint64))
     assert np.array_equal(out, ex.astype(np.uint32))
+
+
+def test_allocation_failure_is_contained(prim, ref_lib):
+    """A device allocation that fails in the middle of an operation (injected)
+    must not launch a kernel on the missing buffer -- an illegal address would
+    destroy the process's CUDA context -- the operation reports an error, and
+    the NEXT operation on the same context runs normally and gives the
+    reference's result."""
+    import util
+    from tmr_b200.forest import OctForest
+
+    lib, ctx = prim
+    lib.tmrgpu_test_fail_alloc.argtypes = [ctypes.c_void_p, ctypes.c_long]
+    conn = util.box_conn()
+    want = util.node_results(util.build_forest(ref_lib, conn, 1, 2, 30, 1, 2))
+    for nth in (1, 2, 5, 9, 17, 33):
+        f = OctForest(order=2, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(1)
+        o = f.getOctants().as_array()
+        f.refine(util.synth_flags(o, 2024, 30))
+        lib.tmrgpu_test_fail_alloc(ctx, nth)
+        f.balance(1)          # hits the injected failure (prints an error)
+        f.createNodes()       # may hit it too if balance allocated less
+        lib.tmrgpu_test_fail_alloc(ctx, 0)
+        # the context is still alive and clean: a fresh forest gives the right answer
+        got = util.node_results(util.build_forest(lib, conn, 1, 2, 30, 1, 2))
+        util.assert_nodes_equal(want, got, "after injected failure %d" % nth)

@@ -413,6 +413,26 @@ TMR_HD void decode_info(int id, int info, int *face_mask, int *edge_mask) {
   *edge_mask = em;
 }
 
+TMR_HD int dep_corner_mask2(int id, int inf) {
+  int fm, em;
+  decode_info(id, inf, &fm, &em);
+  for (int f = 0; f < 6; f++) {
+    if (fm & (1 << f)) {
+      for (int k = 0; k < 4; k++) em |= 1 << face_edge(f, k);
+    }
+  }
+  int out = 0;
+  TMR_UNROLL
+  for (int c = 0; c < 8; c++) {
+    const int ii = c & 1, jj = (c >> 1) & 1, kk = c >> 2;
+    const bool dep = (((em >> (jj + 2 * kk)) & 1) && ii != (id & 1)) ||
+                     (((em >> (4 + ii + 2 * kk)) & 1) && jj != ((id >> 1) & 1)) ||
+                     (((em >> (8 + ii + 2 * jj)) & 1) && kk != (id >> 2));
+    if (dep) out |= 1 << c;
+  }
+  return out;
+}
+
 /* element-local node offset of position p along block edge e */
 TMR_HD int edge_node_offset(int order, int e, int p) {
   const int s = e & 3, hi = order - 1;
@@ -1857,15 +1877,33 @@ struct StoreExternalFn {
 };
 
 /* ---- slot construction of nodes + connectivity (ops_nodes_slots.h) ---------- */
+template <class M>
 struct ParentSlotFn {
   ParentNodeGen g;
   SlotView v;
-  NodeSlotFn ns;
+  NodeSlotFn<M> ns;
   TMR_HD void operator()(i64 e) const {
-    SlotKeyEmit em = {&v, &ns.nfmt, &ns};
+    SlotKeyEmit<NodeSlotFn<M> > em = {&v, &ns.nfmt, &ns};
     g.run(e, em);
   }
 };
+
+/* the locate pass (and, on several ranks, the parent nodes of remote hanging
+   faces), instantiated for the Morton word the depth needs */
+template <class M>
+inline void launch_slot_locate(Ctx &ctx, Forest &f, NodeData &nd, const SlotView &v,
+                               unsigned char *slot8, u64 *b_key, u32 *b_pay,
+                               unsigned long long *b_count, i64 cap,
+                               const unsigned char *fmask) {
+  NodeSlotFn<M> ns = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8, f.info.get(),
+                      nd.nfmt, b_key, b_pay, b_count, cap};
+  launch_block3(ctx, f.n, ns, "nodes_slot_locate");
+  if (v.multi && fmask) {
+    ParentNodeGen pg = {f.keys.get(), fmask, f.fmt, nd.nfmt, f.tables, 2, NULL};
+    ParentSlotFn<M> ps = {pg, v, ns};
+    launch(ctx, f.n, ps, "nodes_slot_parents");
+  }
+}
 
 /* B nodes (several ranks): sorted (key, payload) -> unique keys, run index */
 struct BUniqueFn {
@@ -1911,20 +1949,28 @@ struct BPlaceFn {
   }
 };
 
-/* 1 = nodes, connectivity (local indices) and `created` are built; 0 = the
-   forest needs the general candidate sort; < 0 error */
+/* 1 = done; 0 = the forest needs the general candidate sort; < 0 error.
+   Several ranks: nodes, connectivity as LOCAL indices and `created` are built,
+   numbering follows in create_nodes.  One rank: dependent nodes are labelled
+   in slot space and the connectivity comes out as final node NUMBERS
+   (node_num, num_dep_nodes filled too): *numbered = 1. */
 inline int build_nodes_slots(Forest &f, NodeData &nd,
                              const unsigned char *fmask, u64 k_first, u64 k_last,
-                             DBuf<unsigned char> &created, i64 *Nn_out) {
+                             DBuf<unsigned char> &created, i64 *Nn_out,
+                             int *numbered) {
   Ctx &ctx = *f.ctx;
   Comm *comm = forest_comm(f);
   const i64 E = f.n;
   const int D = f.fmt.D;
-  DBuf<u32> mask(ctx, E), cmask;
+  *numbered = 0;
+  DBuf<u32> mask(ctx, E), cmask, dmask;
   dev_zero(ctx, mask.get(), (size_t)E * sizeof(u32));
   if (comm) {
     cmask.alloc(ctx, E);
     dev_zero(ctx, cmask.get(), (size_t)E * sizeof(u32));
+  } else {
+    dmask.alloc(ctx, E);
+    dev_zero(ctx, dmask.get(), (size_t)E * sizeof(u32));
   }
   DBuf<unsigned long long> ctl(ctx, 2); /* [0] B count, [1] fail flag */
   DBuf<unsigned char> slot8(ctx, E * 8);
@@ -1950,15 +1996,14 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     }
     dev_zero(ctx, ctl.get(), 2 * sizeof(unsigned long long));
     SlotView v = {f.keys.get(), E, f.fmt, f.tables, elem_ix, comm ? 1 : 0, pos_lo,
-                  pos_hi, mask.get(), cmask.get(),
+                  pos_hi, mask.get(), cmask.get(), dmask.get(),
                   reinterpret_cast<int *>(ctl.get() + 1)};
-    NodeSlotFn ns = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8.get(),
-                     nd.nfmt, b_key.get(), b_pay.get(), ctl.get(), cap};
-    launch_block3(ctx, E, ns, "nodes_slot_locate");
-    if (comm && fmask) {
-      ParentNodeGen pg = {f.keys.get(), fmask, f.fmt, nd.nfmt, f.tables, 2, NULL};
-      ParentSlotFn ps = {pg, v, ns};
-      launch(ctx, E, ps, "nodes_slot_parents");
+    if (3 * D <= 30) {
+      launch_slot_locate<u32>(ctx, f, nd, v, slot8.get(), b_key.get(), b_pay.get(),
+                              ctl.get(), cap, fmask);
+    } else {
+      launch_slot_locate<u64>(ctx, f, nd, v, slot8.get(), b_key.get(), b_pay.get(),
+                              ctl.get(), cap, fmask);
     }
     if (!comm) break;
     copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
@@ -1966,12 +2011,35 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     if (h_ctl[1] || nb <= cap) break;
     cap = nb; /* rare: more off-range corners than the guess; marks are idempotent */
   }
+  if (!comm) {
+    /* ---- one rank: scan nodes and dependents together, number directly ---- */
+    DBuf<SlotInfo2> slotinfo(ctx, E);
+    SlotCount2Fn sc = {mask.get(), dmask.get()};
+    SlotInfo2Fn si = {mask.get(), dmask.get(), slotinfo.get()};
+    const u64 tot = scan_apply(ctx, E, sc, si, "nodes_slot_scan");
+    copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
+    if (h_ctl[1]) return 0;
+    const i64 Nn = (i64)(tot & 0x7fffffffULL), Nd = (i64)(tot >> 31);
+    nd.node_keys.alloc(ctx, Nn);
+    nd.node_num.alloc(ctx, Nn);
+    SlotKeys2Fn kf = {f.keys.get(), f.fmt, slotinfo.get(), nd.node_keys.get(),
+                      nd.node_num.get()};
+    launch(ctx, E, kf, "nodes_slot_keys");
+    SlotResolve2Fn rs = {slotinfo.get(), slot8.get(),
+                         reinterpret_cast<u32 *>(nd.conn.get())};
+    launch(ctx, E, rs, "nodes_slot_resolve");
+    nd.num_candidates = 0;
+    nd.num_dep_nodes = Nd;
+    *Nn_out = Nn;
+    *numbered = 1;
+    return 1;
+  }
   /* B nodes: sort, unique */
   i64 nbu = 0, nlow = 0;
   DBuf<u64> b_ukeys;
   DBuf<unsigned char> b_ucreated;
   DBuf<u32> b_run;
-  if (comm && !h_ctl[1] && nb > 0) {
+  if (!h_ctl[1] && nb > 0) {
     DBuf<u64> k_alt(ctx, nb);
     DBuf<u32> p_alt(ctx, nb);
     b_key.set_size(nb);
@@ -1997,7 +2065,6 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
   SlotCountFn sc = {mask.get()};
   SlotInfoFn si = {mask.get(), slotinfo.get()};
   const i64 NA = (i64)scan_apply(ctx, E, sc, si, "nodes_slot_scan");
-  if (!comm) copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
   if (h_ctl[1]) return 0;
   const i64 Nn = NA + nbu;
   if (Nn >= (1LL << 31)) {
@@ -2005,7 +2072,7 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     return -1;
   }
   nd.node_keys.alloc(ctx, Nn);
-  if (comm) created.alloc(ctx, Nn);
+  created.alloc(ctx, Nn);
   SlotKeysFn kf = {f.keys.get(), f.fmt,         slotinfo.get(), cmask.get(),
                    nd.node_keys.get(), created.get(), nlow};
   launch(ctx, E, kf, "nodes_slot_keys");
@@ -2196,13 +2263,13 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   DBuf<unsigned char> created;
   /* order 2 without labels: nodes named by (leaf, slot), no candidate sort
      (ops_nodes_slots.h); TMR_B200_NODES=sort forces the general path */
-  int slots_done = 0;
+  int slots_done = 0, numbered = 0;
   {
     const char *mode = getenv("TMR_B200_NODES");
     if (gorder == 2 && !general && nd.nfmt.lbits == 0 && E > 0 &&
         !(mode && strcmp(mode, "sort") == 0)) {
       slots_done = build_nodes_slots(f, nd, fmask.get(), k_first, k_last, created,
-                                     &Nn);
+                                     &Nn, &numbered);
       if (slots_done < 0) return 1;
       if (getenv("TMR_B200_NODES_VERBOSE")) {
         fprintf(stderr, "[tmr_b200] createNodes: %s path, %lld elements\n",
@@ -2430,7 +2497,16 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     nd.num_local_nodes = Nn;
   }
 
-  /* 3. dependent labels and numbering */
+  /* 3. dependent labels and numbering (already done by the one-rank slot
+     construction, which numbers in slot space) */
+  i64 Nd = nd.num_dep_nodes;
+  DBuf<int> dep_node;
+  if (numbered) {
+    nd.num_owned_nodes = Nn - Nd;
+    nd.node_range_start = 0;
+    nd.node_range.assign(2, 0);
+    nd.node_range[1] = (int)(Nn - Nd);
+  } else {
   DBuf<unsigned char> dep_flag(ctx, Nn);
   dev_zero(ctx, dep_flag.get(), (size_t)Nn);
   if (order == 2) {
@@ -2448,10 +2524,10 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   }
   DBuf<u32> dep_before(ctx, Nn);
   DepFlagFn df = {dep_flag.get()};
-  const i64 Nd = (i64)scan_counts(ctx, Nn, df, dep_before.get(), "nodes_dep_scan");
+  Nd = (i64)scan_counts(ctx, Nn, df, dep_before.get(), "nodes_dep_scan");
   nd.num_dep_nodes = Nd;
   nd.node_num.alloc(ctx, Nn);
-  DBuf<int> dep_node(ctx, Nd);
+  dep_node.alloc(ctx, Nd);
   if (!comm) {
     nd.num_owned_nodes = Nn - Nd;
     nd.node_range_start = 0;
@@ -2505,6 +2581,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   ConnRemapInPlaceFn rm = {nd.node_num.get(), nd.conn.get()};
   launch(ctx, nc, rm, "nodes_conn_remap");
   trace_mark(ctx, "nodes: conn remap");
+  } /* !numbered */
   /* node_mirror_start needs the sizes; `valid` stays false until the end */
   const int prefetch = nd.prefetch;
   if (prefetch) {

@@ -74,10 +74,18 @@ TMR_HD int slot_code(int ord) {
   return (int)((k >> (6 * r)) & 63);
 }
 
+/* The in-tree Morton code of a position is 3 D bits: a 32-bit word up to depth
+   10, which halves the instruction count of the dilated arithmetic below on
+   a 32-bit machine; deeper forests use 64-bit words.  M = u32 or u64. */
+template <class M>
+TMR_HD M axis_mask(int a) {
+  return (M)(0x1249249249249249ULL << a);
+}
 /* add one at bit `bit` of the dilated axis-a component of a Morton code */
-TMR_HD u64 morton_axis_add(u64 m, int a, int bit) {
-  const u64 am = 0x1249249249249249ULL << a;
-  const u64 nc = (((m & am) | ~am) + (1ULL << bit)) & am;
+template <class M>
+TMR_HD M morton_axis_add(M m, int a, int bit) {
+  const M am = axis_mask<M>(a);
+  const M nc = (((m & am) | ~am) + ((M)1 << bit)) & am;
   return (m & ~am) | nc;
 }
 
@@ -253,32 +261,37 @@ struct SlotView {
   u64 pos_lo, pos_hi;
   u32 *mask;  /* per leaf: occupied slots */
   u32 *cmask; /* several ranks: slots that are a corner of a local element */
+  u32 *dmask; /* one rank: slots that are dependent (hanging) nodes */
   int *fail;
 
   /* leaf and slot of the canonical position (block, Morton m of the depth-D
      cell holding it, clamp bit a set where the coordinate is 2^30-1; a = 2 x,
      1 y, 0 z): (leaf << 5) | ordinal, kLocB or kLocFail */
-  TMR_HD u64 locate(i32 block, u64 m, int clamp) const {
+  template <class M>
+  TMR_HD u64 locate(i32 block, M m, int clamp) const {
     const int D = fmt.D;
-    const u64 pos = ((u64)(u32)block << (3 * D)) | m;
+    const u64 pos = ((u64)(u32)block << (3 * D)) | (u64)m;
     if (pos < pos_lo || pos >= pos_hi) return multi ? kLocB : kLocFail;
     const i64 j = ix.pred(keys, pos);
     if (j < 0) return kLocFail;
     const u64 kl = keys[j];
     const int k = D - (int)(kl & 31);
-    if (k < 0 || ((kl >> 5) >> (3 * k)) != (pos >> (3 * k))) return kLocFail;
-    const u64 lm = k > 0 ? ((1ULL << (3 * k)) - 1) : 0ULL;
-    const u64 d = pos & lm;
+    const M mall = D > 0 ? (M)(((u64)1 << (3 * D)) - 1) : (M)0;
+    const M ml = (M)(kl >> 5) & mall;
+    if (k < 0 || (i32)(kl >> (3 * D + 5)) != block) return kLocFail;
+    const M lm = k > 0 ? (M)(((u64)1 << (3 * k)) - 1) : (M)0;
+    if (((ml ^ m) & ~lm) != 0) return kLocFail; /* not inside the leaf */
+    const M d = m & lm;
     int c6 = 0;
     TMR_UNROLL
     for (int a = 0; a < 3; a++) {
-      const u64 am = (0x1249249249249249ULL << a) & lm;
-      const u64 da = d & am;
+      const M am = axis_mask<M>(a) & lm;
+      const M da = d & am;
       if ((clamp >> a) & 1) {
         if (da != am) return kLocFail;
         c6 |= (8 | 1) << a;
       } else if (da != 0) {
-        if (da != (1ULL << (3 * (k - 1) + a))) return kLocFail;
+        if (da != ((M)1 << (3 * (k - 1) + a))) return kLocFail;
         c6 |= 8 << a;
       }
     }
@@ -289,25 +302,35 @@ struct SlotView {
     const int s = kMaxLevel - fmt.D;
     const int clamp = ((x == kHmax - 1) ? 4 : 0) | ((y == kHmax - 1) ? 2 : 0) |
                       ((z == kHmax - 1) ? 1 : 0);
-    return locate(block, morton3((u32)x >> s, (u32)y >> s, (u32)z >> s), clamp);
+    return locate<u64>(block, morton3((u32)x >> s, (u32)y >> s, (u32)z >> s), clamp);
   }
   TMR_HD void mark(u64 v, bool corner) const {
     if (v >= kLocFail) return;
     const i64 leaf = (i64)(v >> 5);
     const u32 bit = 1u << (int)(v & 31);
-    if (!(mask[leaf] & bit)) TMR_ATOMIC_OR_I32(&mask[leaf], bit);
-    if (cmask && corner && !(cmask[leaf] & bit)) TMR_ATOMIC_OR_I32(&cmask[leaf], bit);
+    /* fire-and-forget reductions: no load to wait for, no branch */
+    TMR_ATOMIC_OR_I32(&mask[leaf], bit);
+    if (cmask && corner) TMR_ATOMIC_OR_I32(&cmask[leaf], bit);
   }
 };
+
+/* corners of an order-2 element that are dependent nodes, given its child id
+   and 6-bit hanging info (labelDependentNodes, reference
+   src/TMROctForest.cpp:3711-3832): the corner on the far end, from the
+   parent's corner, of a hanging edge (or of an edge of a hanging face) is the
+   parent's edge midpoint */
+TMR_HD int dep_corner_mask2(int id, int inf);
 
 /* per element: (leaf, slot) of its 8 corners.  Runs through launch_block3:
    collect() classifies the element and queues the points that need a search,
    process() drains the queues with all lanes busy, finish() assembles the
-   element's row. */
+   element's row.  M: Morton word (u32 up to depth 10, else u64). */
+template <class M>
 struct NodeSlotFn {
   SlotView v;
   u32 *conn_leaf;       /* [E][8] leaf index of every corner (kConnB: B list) */
   unsigned char *slot8; /* [E][8] slot ordinal */
+  const int16_t *info;  /* hanging info of the elements (with v.dmask) */
   /* several ranks: corners whose position is not in this rank's range */
   NodeFmt nfmt;
   u64 *b_key;
@@ -418,21 +441,23 @@ struct NodeSlotFn {
 
   TMR_HD void process(i64 i0, int t, Shared &sh) const {
     const int D = v.fmt.D;
+    const M mall = D > 0 ? (M)(((u64)1 << (3 * D)) - 1) : (M)0;
     /* family grid points: steps of the element size from the parent's anchor */
     for (int q = t; q < sh.nfam; q += kLaunchThreads) {
       const int task = sh.fam[q], ts = task >> 3, code = task & 7;
       const u64 key = v.keys[i0 + ts];
       const int s = 3 * (D - (int)(key & 31));
-      const u64 m = (key >> 5) & ((1ULL << (3 * D)) - 1);
+      const M m = (M)(key >> 5) & mall;
       const int tp = (int)((m >> s) & 7) + 8 * code;
-      const int g[3] = {tp / 9, (tp / 3) % 3, tp % 3}; /* axis 0 z, 1 y, 2 x */
-      u64 mq = (m >> (s + 3)) << (s + 3);
-      TMR_UNROLL
-      for (int a = 0; a < 3; a++) {
-        if (g[a] == 1) mq |= 1ULL << (s + a);
-        if (g[a] == 2) mq = morton_axis_add(mq, a, s + 3 + a);
-      }
-      const u64 val = v.locate((i32)(key >> (3 * D + 5)), mq, 0);
+      const int gz = tp / 9, gy = (tp - 9 * gz) / 3, gx = tp - 9 * gz - 3 * gy;
+      M mq = (m >> (s + 3)) << (s + 3);
+      if (gz == 1) mq |= (M)1 << s;
+      if (gy == 1) mq |= (M)1 << (s + 1);
+      if (gx == 1) mq |= (M)1 << (s + 2);
+      if (gz == 2) mq = morton_axis_add<M>(mq, 0, s + 3);
+      if (gy == 2) mq = morton_axis_add<M>(mq, 1, s + 4);
+      if (gx == 2) mq = morton_axis_add<M>(mq, 2, s + 5);
+      const u64 val = v.template locate<M>((i32)(key >> (3 * D + 5)), mq, 0);
       v.mark(val, true);
       sh.val[ts * 8 + code] = val;
     }
@@ -441,11 +466,11 @@ struct NodeSlotFn {
       const int task = sh.own[q], ts = task >> 3, code = task & 7;
       const u64 key = v.keys[i0 + ts];
       const int s = 3 * (D - (int)(key & 31));
-      u64 mq = (key >> 5) & ((1ULL << (3 * D)) - 1);
-      if (code & 1) mq = morton_axis_add(mq, 2, s + 2);
-      if (code & 2) mq = morton_axis_add(mq, 1, s + 1);
-      if (code & 4) mq = morton_axis_add(mq, 0, s);
-      const u64 val = v.locate((i32)(key >> (3 * D + 5)), mq, 0);
+      M mq = (M)(key >> 5) & mall;
+      if (code & 1) mq = morton_axis_add<M>(mq, 2, s + 2);
+      if (code & 2) mq = morton_axis_add<M>(mq, 1, s + 1);
+      if (code & 4) mq = morton_axis_add<M>(mq, 0, s);
+      const u64 val = v.template locate<M>((i32)(key >> (3 * D + 5)), mq, 0);
       v.mark(val, true);
       sh.val[ts * 8 + code] = val;
     }
@@ -508,15 +533,30 @@ struct NodeSlotFn {
     }
     store8_u32(conn_leaf + i * 8, leaf);
     *reinterpret_cast<u64 *>(slot8 + i * 8) = ords;
+    /* one rank: dependent nodes are labelled right here, in slot space */
+    if (v.dmask && info[i]) {
+      const u64 key = v.keys[i];
+      const int L = (int)(key & 31);
+      const int md = L == 0 ? 0 : (int)((key >> (5 + 3 * (v.fmt.D - L))) & 7);
+      const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
+      const int dm = dep_corner_mask2(id, info[i]);
+      TMR_UNROLL
+      for (int c = 0; c < 8; c++) {
+        if ((dm >> c) & 1) {
+          TMR_ATOMIC_OR_I32(&v.dmask[leaf[c]], 1u << (int)((ords >> (8 * c)) & 31));
+        }
+      }
+    }
   }
 };
 
 /* several ranks: the parent edge / face nodes of hanging elements whose coarse
    neighbour is remote (ParentNodeGen) must exist as nodes too */
+template <class NS>
 struct SlotKeyEmit {
   const SlotView *v;
   const NodeFmt *nfmt;
-  const NodeSlotFn *ns;
+  const NS *ns;
   TMR_HD void operator()(i32 b, i32 x, i32 y, i32 z, int) const {
     const u64 val = v->locate_xyz(b, x, y, z);
     if (val == kLocFail) {
@@ -541,7 +581,64 @@ struct SlotInfoFn {
   }
 };
 
-/* node keys (NodeFmt at Dn = D) of every occupied slot, in order */
+/* one rank: nodes and dependent nodes counted together, lo | hi << 31 */
+struct SlotInfo2 {
+  u32 node_off, mask, dep_off, dmask;
+};
+struct SlotCount2Fn {
+  const u32 *mask;
+  const u32 *dmask;
+  TMR_HD u64 operator()(i64 i) const {
+    return (u64)popc32(mask[i]) | ((u64)popc32(dmask[i]) << 31);
+  }
+};
+struct SlotInfo2Fn {
+  const u32 *mask;
+  const u32 *dmask;
+  SlotInfo2 *slotinfo;
+  TMR_HD void operator()(i64 i, u64 off) const {
+    SlotInfo2 si = {(u32)(off & 0x7fffffffULL), mask[i], (u32)(off >> 31), dmask[i]};
+    slotinfo[i] = si;
+  }
+};
+/* number of the node in slot `ord` of a leaf on ONE rank (reference
+   :4113-4181): dependents -1, -2, .. and independents 0, 1, .. both in node
+   order */
+TMR_HD int slot_node_number(const SlotInfo2 &si, int ord) {
+  const u32 below = (1u << ord) - 1u;
+  const int dep_before = (int)si.dep_off + popc32(si.dmask & below);
+  if ((si.dmask >> ord) & 1u) return -dep_before - 1;
+  return (int)si.node_off + popc32(si.mask & below) - dep_before;
+}
+TMR_HD SlotInfo2 load_slotinfo2(const SlotInfo2 *p) {
+#if defined(__CUDA_ARCH__)
+  const uint4 v = *reinterpret_cast<const uint4 *>(p);
+  SlotInfo2 si = {v.x, v.y, v.z, v.w};
+  return si;
+#else
+  return *p;
+#endif
+}
+
+/* key (NodeFmt at Dn = D) of slot c6 of the leaf `key` */
+TMR_HD u64 slot_node_key(u64 key, int D, int c6) {
+  const int k = D - (int)(key & 31);
+  const u64 m = D > 0 ? ((key >> 5) & ((1ULL << (3 * D)) - 1)) : 0ULL;
+  const u64 block = key >> (3 * D + 5);
+  const u64 lm = (1ULL << (3 * (k + 1))) - 1;
+  u64 extra = 0;
+  TMR_UNROLL
+  for (int a = 0; a < 3; a++) {
+    if ((c6 >> a) & 1) {
+      extra |= (0x1249249249249249ULL << a) & lm;
+    } else if ((c6 >> (3 + a)) & 1) {
+      extra |= 1ULL << (3 * k + a);
+    }
+  }
+  return (block << (3 * (D + 1))) | (m << 3) | extra;
+}
+
+/* node keys of every occupied slot, in order (several ranks: + created flags) */
 struct SlotKeysFn {
   const u64 *keys;
   KeyFmt fmt;
@@ -555,29 +652,35 @@ struct SlotKeysFn {
     u32 mk = (u32)si;
     if (!mk) return;
     const u64 key = keys[i];
-    const int D = fmt.D;
-    const int k = D - (int)(key & 31);
-    const u64 m = D > 0 ? ((key >> 5) & ((1ULL << (3 * D)) - 1)) : 0ULL;
-    const u64 block = key >> (3 * D + 5);
-    const u64 nb = (block << (3 * (D + 1))) | (m << 3);
-    const u64 lm = (1ULL << (3 * (k + 1))) - 1;
     i64 o = base + (i64)(si >> 32);
     const u32 cm = cmask ? cmask[i] : 0u;
     while (mk) {
       const int ord = ctz32(mk);
       mk &= mk - 1;
-      const int c6 = slot_code(ord);
-      u64 extra = 0;
-      TMR_UNROLL
-      for (int a = 0; a < 3; a++) {
-        if ((c6 >> a) & 1) {
-          extra |= (0x1249249249249249ULL << a) & lm;
-        } else if ((c6 >> (3 + a)) & 1) {
-          extra |= 1ULL << (3 * k + a);
-        }
-      }
-      node_keys[o] = nb | extra;
+      node_keys[o] = slot_node_key(key, fmt.D, slot_code(ord));
       if (created) created[o] = (unsigned char)((cm >> ord) & 1u);
+      o++;
+    }
+  }
+};
+/* one rank: node keys and node numbers */
+struct SlotKeys2Fn {
+  const u64 *keys;
+  KeyFmt fmt;
+  const SlotInfo2 *slotinfo;
+  u64 *node_keys;
+  int *node_num;
+  TMR_HD void operator()(i64 i) const {
+    const SlotInfo2 si = load_slotinfo2(slotinfo + i);
+    u32 mk = si.mask;
+    if (!mk) return;
+    const u64 key = keys[i];
+    i64 o = si.node_off;
+    while (mk) {
+      const int ord = ctz32(mk);
+      mk &= mk - 1;
+      node_keys[o] = slot_node_key(key, fmt.D, slot_code(ord));
+      node_num[o] = slot_node_number(si, ord);
       o++;
     }
   }
@@ -599,6 +702,24 @@ struct SlotResolveFn {
       const u64 si = slotinfo[leaf[c]];
       const int ord = (int)((ords >> (8 * c)) & 31);
       leaf[c] = base + (u32)(si >> 32) + (u32)popc32((u32)si & ((1u << ord) - 1u));
+    }
+    store8_u32(conn + e * 8, leaf);
+  }
+};
+/* one rank: (leaf, slot) -> node NUMBER, in place: the connectivity is final
+   after this pass (no local-index stage, no renumbering pass) */
+struct SlotResolve2Fn {
+  const SlotInfo2 *slotinfo;
+  const unsigned char *slot8;
+  u32 *conn;
+  TMR_HD void operator()(i64 e) const {
+    u32 leaf[8];
+    load8_u32(conn + e * 8, leaf);
+    const u64 ords = *reinterpret_cast<const u64 *>(slot8 + e * 8);
+    TMR_UNROLL
+    for (int c = 0; c < 8; c++) {
+      const SlotInfo2 si = load_slotinfo2(slotinfo + leaf[c]);
+      leaf[c] = (u32)slot_node_number(si, (int)((ords >> (8 * c)) & 31));
     }
     store8_u32(conn + e * 8, leaf);
   }

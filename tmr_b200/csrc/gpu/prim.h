@@ -44,12 +44,13 @@ struct Ctx {
   std::vector<void *> ev_start, ev_stop;
   std::vector<std::string> ev_name;
   std::string last_error;
+  long fail_alloc_in; /* fault injection for tests: the n-th next dev_alloc fails (0 = off) */
   int trace;        /* TMR_B200_TRACE=1: print synchronised phase times */
   double trace_t0;  /* wall clock of the previous mark (s) */
   Ctx()
       : device(0), comm(NULL), stream(NULL), copy_stream(NULL), profile(0),
         num_sms(148),
-        launch_count(0), trace(0), trace_t0(0.0) {}
+        launch_count(0), fail_alloc_in(0), trace(0), trace_t0(0.0) {}
 };
 
 /* --- runtime (prim_cuda.cu / tests/emu/prim_emu.cpp) ---------------------- */

@@ -15,12 +15,18 @@ namespace tmrgpu {
 /* ------------------------------------------------------------------------ */
 /* runtime                                                                  */
 /* ------------------------------------------------------------------------ */
+/* a failed runtime call is printed AND recorded in the context: the current
+   operation stops launching (prim_cuda.cuh: ctx_ok) and its check_errors
+   reports the failure to the caller */
 #define TMR_CUDA_OK(call)                                                     \
   do {                                                                        \
     cudaError_t e_ = (call);                                                  \
     if (e_ != cudaSuccess) {                                                  \
       fprintf(stderr, "TMROctForest Error: CUDA %s at %s:%d\n",               \
               cudaGetErrorString(e_), __FILE__, __LINE__);                    \
+      if (ctx.last_error.empty()) {                                           \
+        ctx.last_error = std::string("CUDA ") + cudaGetErrorString(e_);       \
+      }                                                                       \
     }                                                                         \
   } while (0)
 
@@ -70,6 +76,12 @@ void dev_cache_destroy(Ctx &ctx) {
 size_t dev_cache_peak_bytes(Ctx &ctx) { return g_caches[&ctx].peak_bytes; }
 
 void *dev_alloc(Ctx &ctx, size_t bytes) {
+  if (ctx.fail_alloc_in > 0 && --ctx.fail_alloc_in == 0) {
+    fprintf(stderr, "TMROctForest Error: device allocation of %zu bytes failed "
+                    "(injected by tmrgpu_test_fail_alloc)\n", bytes);
+    ctx.last_error = "device allocation failed";
+    return NULL;
+  }
   DevCache &c = g_caches[&ctx];
   const size_t cls = size_class(bytes);
   void *p = NULL;
@@ -148,7 +160,7 @@ void host_free(Ctx &ctx, void *p) {
 }
 
 void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
-  if (bytes == 0) return;
+  if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return;
   TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice,
                               (cudaStream_t)ctx.stream));
   /* the source may be pageable/stack memory: make the copy complete before
@@ -157,14 +169,14 @@ void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
 }
 
 void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes) {
-  if (bytes == 0) return;
+  if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return;
   TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost,
                               (cudaStream_t)ctx.stream));
   TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
 }
 
 void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes) {
-  if (bytes == 0) return NULL;
+  if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return NULL;
   if (!ctx.copy_stream) {
     cudaStream_t s;
     TMR_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -183,25 +195,24 @@ void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes) {
 }
 
 void copy_wait(Ctx &ctx, void *handle) {
-  (void)ctx;
   if (!handle) return;
   TMR_CUDA_OK(cudaEventSynchronize((cudaEvent_t)handle));
   cudaEventDestroy((cudaEvent_t)handle);
 }
 
 void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
-  if (bytes == 0) return;
+  if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return;
   TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice,
                               (cudaStream_t)ctx.stream));
 }
 
 void dev_zero(Ctx &ctx, void *p, size_t bytes) {
-  if (bytes == 0) return;
+  if (bytes == 0 || !p || !ctx.last_error.empty()) return;
   TMR_CUDA_OK(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)ctx.stream));
 }
 
 void dev_fill_ff(Ctx &ctx, void *p, size_t bytes) {
-  if (bytes == 0) return;
+  if (bytes == 0 || !p || !ctx.last_error.empty()) return;
   TMR_CUDA_OK(cudaMemsetAsync(p, 0xff, bytes, (cudaStream_t)ctx.stream));
 }
 
@@ -213,12 +224,20 @@ int check_errors(Ctx &ctx, const char *where) {
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)ctx.stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
-    ctx.last_error = std::string(where) + ": " + cudaGetErrorString(e);
     fprintf(stderr, "TMROctForest Error: CUDA failure in %s: %s\n", where,
             cudaGetErrorString(e));
+    ctx.last_error.clear();
     return 1;
   }
-  if (!ctx.last_error.empty()) return 1;
+  if (!ctx.last_error.empty()) {
+    /* recorded by the operation that just ended (allocation failure, size
+       limit, NCCL): reported to its caller here, once -- the next operation
+       starts clean */
+    fprintf(stderr, "TMROctForest Error: %s failed: %s\n", where,
+            ctx.last_error.c_str());
+    ctx.last_error.clear();
+    return 1;
+  }
   return 0;
 }
 
@@ -654,11 +673,14 @@ static void launch_pass(Ctx &ctx, i64 tiles, DBuf<u64> &keys, DBuf<u64> &keys_al
                         int bits, const u32 *doff, const u32 *thist,
                         const u32 *ctot) {
   const size_t smem = sort_smem_bytes(kHasVals, 1 << kBits);
-  static bool attr_set = false;
-  if (!attr_set) {
+  /* the attribute is per device: set it once for every device this process
+     drives (bit mask of devices done, per kernel instantiation) */
+  static unsigned long long attr_devices = 0;
+  const unsigned long long dev_bit = 1ULL << (ctx.device & 63);
+  if (!(attr_devices & dev_bit)) {
     cudaFuncSetAttribute(radix_pass_kernel<kHasVals, kBits>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_devices |= dev_bit;
   }
   radix_pass_kernel<kHasVals, kBits>
       <<<(unsigned)tiles, kSortThreads, smem, (cudaStream_t)ctx.stream>>>(
@@ -669,7 +691,8 @@ static void launch_pass(Ctx &ctx, i64 tiles, DBuf<u64> &keys, DBuf<u64> &keys_al
 void radix_sort(Ctx &ctx, DBuf<u64> &keys, DBuf<u64> &keys_alt,
                 DBuf<u32> &vals, DBuf<u32> &vals_alt, i64 n, int bit_lo,
                 int bit_hi, const char *tag) {
-  if (n <= 1 || bit_hi <= bit_lo) return;
+  if (n <= 1 || bit_hi <= bit_lo || !ctx.last_error.empty()) return;
+  if (!keys.get() || !keys_alt.get()) return;
   if (n >= (1LL << 32)) {
     fprintf(stderr, "TMROctForest Error: radix sort of %lld keys exceeds the "
                     "32-bit offset range\n", (long long)n);

@@ -41,9 +41,16 @@ inline int grid_for(const Ctx &ctx, i64 n, int threads, int max_waves) {
   return (int)blocks;
 }
 
+/* false once an operation has recorded a failure (allocation, size limit,
+   NCCL): nothing more is launched -- a kernel must never run on the NULL
+   buffer of a failed allocation (an illegal address is a sticky error that
+   takes the whole process's CUDA context with it) -- and the operation's
+   closing check_errors reports it */
+inline bool ctx_ok(const Ctx &ctx) { return ctx.last_error.empty(); }
+
 template <class F>
 void launch(Ctx &ctx, i64 n, F f, const char *name) {
-  if (n <= 0) return;
+  if (n <= 0 || !ctx_ok(ctx)) return;
   /* up to 8 resident CTAs of 256 threads per SM; 4 waves of grid-stride */
   const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
   prof_begin(ctx, name);
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(kLaunchThreads)
 template <int kMaxPer, class F>
 void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64 total, F f, u64 *out,
                 const char *name) {
-  if (n <= 0) return;
+  if (n <= 0 || !ctx_ok(ctx)) return;
   const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
   prof_begin(ctx, name);
   expand_kernel<F, kMaxPer><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(kLaunchThreads)
 
 template <class F>
 void launch_block3(Ctx &ctx, i64 n, F f, const char *name) {
-  if (n <= 0) return;
+  if (n <= 0 || !ctx_ok(ctx)) return;
   const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
   prof_begin(ctx, name);
   block3_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
@@ -164,11 +171,15 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
   return v;
 }
 
-/* G is called as g(i, exclusive_prefix_of_i) for every i < n */
+/* G is called as g(i, exclusive_prefix_of_i) for every i < n.  The count type
+   is whatever F returns: u32, or u64 when two counters ride in one word
+   (ops_nodes_slots.h packs node and dependent-node counts as lo | hi << 31;
+   a tile descriptor holds 62 value bits). */
 template <class F, class G>
 __global__ void __launch_bounds__(kScanThreads)
     scan_apply_kernel(F f, G g, i64 n, u64 *tile_state, u32 *ticket,
                       u64 *total) {
+  typedef decltype(f((i64)0)) T;
   __shared__ u32 s_tile;
   __shared__ u64 s_warp_sum[kScanThreads / 32];
   __shared__ u64 s_tile_prefix;
@@ -177,12 +188,12 @@ __global__ void __launch_bounds__(kScanThreads)
   const u32 tile = s_tile;
   const i64 base = (i64)tile * kScanTile + (i64)threadIdx.x * kScanItems;
 
-  u32 c[kScanItems];
-  u32 mine = 0;
+  T c[kScanItems];
+  u64 mine = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
     const i64 i = base + k;
-    c[k] = (i < n) ? f(i) : 0u;
+    c[k] = (i < n) ? f(i) : (T)0;
     mine += c[k];
   }
   /* block exclusive scan of per-thread sums */
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(kScanThreads)
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
     const i64 i = base + k;
-    if (i < n) g(i, (u32)run);
+    if (i < n) g(i, (T)run);
     run += c[k];
   }
 }
@@ -252,10 +263,11 @@ __global__ void __launch_bounds__(kScanThreads)
    offset array round trip through HBM).  Returns the total. */
 template <class F, class G>
 u64 scan_apply(Ctx &ctx, i64 n, F f, G g, const char *name) {
-  if (n <= 0) return 0;
+  if (n <= 0 || !ctx_ok(ctx)) return 0;
   const i64 tiles = (n + kScanTile - 1) / kScanTile;
   const size_t bytes = (size_t)(tiles + 2) * sizeof(u64);
   u64 *scratch = static_cast<u64 *>(dev_alloc(ctx, bytes));
+  if (!scratch) return 0;
   dev_zero(ctx, scratch, bytes);
   u64 *tile_state = scratch;
   u32 *ticket = reinterpret_cast<u32 *>(scratch + tiles);

@@ -509,6 +509,11 @@ int tmrgpu_test_scan(tmrgpu_ctx *ctx, const uint32_t *counts, int64_t n,
   return check_errors(c, "test_scan");
 }
 
+int tmrgpu_test_fail_alloc(tmrgpu_ctx *ctx, long nth) {
+  ctx->c.fail_alloc_in = nth;
+  return 0;
+}
+
 int tmrgpu_host_alloc(tmrgpu_ctx *ctx, int64_t bytes, void **out) {
   *out = host_alloc(ctx->c, (size_t)bytes);
   return *out ? 0 : 1;
