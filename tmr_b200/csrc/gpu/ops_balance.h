@@ -25,6 +25,9 @@
 #ifndef TMRGPU_OPS_BALANCE_H
 #define TMRGPU_OPS_BALANCE_H
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "ops_octants.h"
 
 namespace tmrgpu {
@@ -296,10 +299,25 @@ struct RootLeafFillFn {
   }
 };
 
+int balance_map(Forest &f, int balance_corner); /* ops_balance_map.h */
+
 inline int balance(Forest &f, int balance_corner) {
   Ctx &ctx = *f.ctx;
   f.last_mid = f.n;
   if (f.n == 0) return 0;
+  {
+    /* cell bitmaps when they fit (ops_balance_map.h); TMR_B200_BALANCE=sort
+       forces the sorted-array closure below */
+    const char *mode = getenv("TMR_B200_BALANCE");
+    if (f.fmt.D > 0 && !(mode && strcmp(mode, "sort") == 0)) {
+      const int rc = balance_map(f, balance_corner);
+      if (getenv("TMR_B200_NODES_VERBOSE")) {
+        fprintf(stderr, "[tmr_b200] balance: %s\n",
+                rc >= 0 ? "cell bitmaps" : "sorted-array closure (maps over budget)");
+      }
+      if (rc >= 0) return rc;
+    }
+  }
   const int D = f.fmt.D;
   /* info of every surviving octant is 0 after balance (getSibling zeroes it,
      reference src/TMROctant.cpp:52) */

@@ -1892,11 +1892,11 @@ struct ParentSlotFn {
    faces), instantiated for the Morton word the depth needs */
 template <class M>
 inline void launch_slot_locate(Ctx &ctx, Forest &f, NodeData &nd, const SlotView &v,
-                               unsigned char *slot8, u64 *b_key, u32 *b_pay,
-                               unsigned long long *b_count, i64 cap,
-                               const unsigned char *fmask) {
+                               unsigned char *slot8, const unsigned char *dep_table,
+                               u64 *b_key, u32 *b_pay, unsigned long long *b_count,
+                               i64 cap, const unsigned char *fmask) {
   NodeSlotFn<M> ns = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8, f.info.get(),
-                      nd.nfmt, b_key, b_pay, b_count, cap};
+                      dep_table, nd.nfmt, b_key, b_pay, b_count, cap};
   launch_block3(ctx, f.n, ns, "nodes_slot_locate");
   if (v.multi && fmask) {
     ParentNodeGen pg = {f.keys.get(), fmask, f.fmt, nd.nfmt, f.tables, 2, NULL};
@@ -1974,6 +1974,12 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
   }
   DBuf<unsigned long long> ctl(ctx, 2); /* [0] B count, [1] fail flag */
   DBuf<unsigned char> slot8(ctx, E * 8);
+  DBuf<unsigned char> dep_table;
+  if (!comm) {
+    dep_table.alloc(ctx, 512);
+    DepTableFn dt = {dep_table.get()};
+    launch(ctx, 512, dt, "nodes_dep_table");
+  }
   /* this rank's range of positions and the rank index over it */
   const u64 pos_lo = k_first >> 5;
   const u64 pos_hi = (k_last >> 5) + (1ULL << (3 * (D - (int)(k_last & 31))));
@@ -1999,11 +2005,11 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
                   pos_hi, mask.get(), cmask.get(), dmask.get(),
                   reinterpret_cast<int *>(ctl.get() + 1)};
     if (3 * D <= 30) {
-      launch_slot_locate<u32>(ctx, f, nd, v, slot8.get(), b_key.get(), b_pay.get(),
-                              ctl.get(), cap, fmask);
+      launch_slot_locate<u32>(ctx, f, nd, v, slot8.get(), dep_table.get(), b_key.get(),
+                              b_pay.get(), ctl.get(), cap, fmask);
     } else {
-      launch_slot_locate<u64>(ctx, f, nd, v, slot8.get(), b_key.get(), b_pay.get(),
-                              ctl.get(), cap, fmask);
+      launch_slot_locate<u64>(ctx, f, nd, v, slot8.get(), dep_table.get(), b_key.get(),
+                              b_pay.get(), ctl.get(), cap, fmask);
     }
     if (!comm) break;
     copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));

@@ -66,12 +66,13 @@ TMR_HD int ctz32(u32 v) {
 }
 
 TMR_HD int slot_ord(int c6) { return popc64(kSlotValid & ((1ULL << c6) - 1)); }
-/* ordinal -> code: the 27 valid codes, 6 bits each, 10 per word */
+/* ordinal -> code: the 27 valid codes, one byte each, 8 per word */
 TMR_HD int slot_code(int ord) {
-  const int w = ord / 10, r = ord - 10 * w;
-  const u64 k = w == 0 ? 0x81b699612409200ULL
-                       : (w == 1 ? 0xe36d32c2db29a24ULL : 0x3ffbdf3beb9ULL);
-  return (int)((k >> (6 * r)) & 63);
+  const int w = ord >> 3;
+  const u64 k = w == 0 ? 0x1a19181210090800ULL
+                       : (w == 1 ? 0x302d2c292824201bULL
+                                 : (w == 2 ? 0x3c3b3a3938363432ULL : 0x3f3e3dULL));
+  return (int)((k >> (8 * (ord & 7))) & 63);
 }
 
 /* The in-tree Morton code of a position is 3 D bits: a 32-bit word up to depth
@@ -320,6 +321,13 @@ struct SlotView {
    parent's corner, of a hanging edge (or of an edge of a hanging face) is the
    parent's edge midpoint */
 TMR_HD int dep_corner_mask2(int id, int inf);
+/* tabulated: 8 child ids x 64 info values (512 bytes, built on the device) */
+struct DepTableFn {
+  unsigned char *table;
+  TMR_HD void operator()(i64 i) const {
+    table[i] = (unsigned char)dep_corner_mask2((int)(i >> 6), (int)(i & 63));
+  }
+};
 
 /* per element: (leaf, slot) of its 8 corners.  Runs through launch_block3:
    collect() classifies the element and queues the points that need a search,
@@ -331,6 +339,7 @@ struct NodeSlotFn {
   u32 *conn_leaf;       /* [E][8] leaf index of every corner (kConnB: B list) */
   unsigned char *slot8; /* [E][8] slot ordinal */
   const int16_t *info;  /* hanging info of the elements (with v.dmask) */
+  const unsigned char *dep_table; /* [child id][info] -> dependent corners */
   /* several ranks: corners whose position is not in this rank's range */
   NodeFmt nfmt;
   u64 *b_key;
@@ -539,7 +548,7 @@ struct NodeSlotFn {
       const int L = (int)(key & 31);
       const int md = L == 0 ? 0 : (int)((key >> (5 + 3 * (v.fmt.D - L))) & 7);
       const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
-      const int dm = dep_corner_mask2(id, info[i]);
+      const int dm = dep_table[(id << 6) | (info[i] & 63)];
       TMR_UNROLL
       for (int c = 0; c < 8; c++) {
         if ((dm >> c) & 1) {
@@ -597,8 +606,13 @@ struct SlotInfo2Fn {
   const u32 *dmask;
   SlotInfo2 *slotinfo;
   TMR_HD void operator()(i64 i, u64 off) const {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4 *>(slotinfo + i) =
+        make_uint4((u32)(off & 0x7fffffffULL), mask[i], (u32)(off >> 31), dmask[i]);
+#else
     SlotInfo2 si = {(u32)(off & 0x7fffffffULL), mask[i], (u32)(off >> 31), dmask[i]};
     slotinfo[i] = si;
+#endif
   }
 };
 /* number of the node in slot `ord` of a leaf on ONE rank (reference

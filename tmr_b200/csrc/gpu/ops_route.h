@@ -7,6 +7,7 @@
 #define TMRGPU_OPS_ROUTE_H
 
 #include "ops_balance.h"
+#include "ops_balance_map.h"
 
 namespace tmrgpu {
 

@@ -149,10 +149,15 @@ void launch_block3(Ctx &ctx, i64 n, F f, const char *name) {
 }
 
 /* ---- chained scan --------------------------------------------------------
-   tile = 256 threads x 8 items (blocked, so each thread owns 8 consecutive
-   outputs and stores them as two 16-byte vectors).  Tile descriptors are one
-   64-bit word: [2-bit status | 62-bit value], written with a single store so
-   status and value can never be observed torn. */
+   tile = 256 threads x 8 items, warp-striped: warp w owns items [256 w,
+   256 w + 256) of the tile and lane l takes items l, l + 32, .. of them, so
+   every load and store of f and g is a coalesced 128-byte row (a blocked
+   layout -- 8 consecutive items per thread -- made each warp instruction
+   touch 32 sectors: measured 1.9 ms for a 24-byte-per-item scan of 86 M items
+   that moves 2 GB).  Prefixes in item order: one warp scan per row plus the
+   row totals carried along.  Tile descriptors are one 64-bit word:
+   [2-bit status | 62-bit value], written with a single store so status and
+   value can never be observed torn. */
 static const int kScanThreads = 256;
 static const int kScanItems = 8;
 static const int kScanTile = kScanThreads * kScanItems;
@@ -186,25 +191,31 @@ __global__ void __launch_bounds__(kScanThreads)
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const u32 tile = s_tile;
-  const i64 base = (i64)tile * kScanTile + (i64)threadIdx.x * kScanItems;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const i64 base = (i64)tile * kScanTile + (i64)warp * (32 * kScanItems) + lane;
 
+  /* c[k]: count of item base + 32 k; x[k]: its exclusive prefix within the
+     warp's 256 items */
   T c[kScanItems];
-  u64 mine = 0;
+  u64 x[kScanItems];
+  u64 carry = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
-    const i64 i = base + k;
+    const i64 i = base + 32 * k;
     c[k] = (i < n) ? f(i) : (T)0;
-    mine += c[k];
   }
-  /* block exclusive scan of per-thread sums */
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  u64 incl = mine;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    u64 up = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += up;
+  for (int k = 0; k < kScanItems; k++) {
+    T incl = c[k];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const T up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    x[k] = carry + (u64)(incl - c[k]);
+    carry += (u64)__shfl_sync(0xffffffffu, incl, 31);
   }
-  if (lane == 31) s_warp_sum[warp] = incl;
+  if (lane == 31) s_warp_sum[warp] = carry;
   __syncthreads();
   u64 warp_off = 0, tile_sum = 0;
 #pragma unroll
@@ -250,12 +261,11 @@ __global__ void __launch_bounds__(kScanThreads)
     }
   }
   __syncthreads();
-  u64 run = s_tile_prefix + warp_off + (incl - mine);
+  const u64 run = s_tile_prefix + warp_off;
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
-    const i64 i = base + k;
-    if (i < n) g(i, (T)run);
-    run += c[k];
+    const i64 i = base + 32 * k;
+    if (i < n) g(i, (T)(run + x[k]));
   }
 }
 
