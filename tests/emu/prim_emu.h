@@ -38,6 +38,8 @@ void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64, F f, u64 *out, const char 
 
 static const int kLaunchThreads = 256;
 
+inline bool ctx_ok(const Ctx &ctx) { return ctx.last_error.empty(); }
+
 template <class F>
 void launch_block3(Ctx &ctx, i64 n, F f, const char *) {
   typename F::Shared *sh = new typename F::Shared();

@@ -286,6 +286,8 @@ inline int balance_map(Forest &f, int balance_corner) {
     launch(ctx, l == 0 ? ((i64)f.nblocks + 7) / 8 : mp.cells(l - 1), ff,
            "balance_map_fill");
   }
+  /* a failed allocation above launched nothing: leave the forest as it was */
+  if (!ctx_ok(ctx)) return check_errors(ctx, "balance");
   f.keys.swap(out);
   f.n = total;
   f.last_out = f.n;

@@ -31,6 +31,16 @@ struct tmrgpu_forest {
   explicit tmrgpu_forest(Ctx *c) : f(c) {}
 };
 
+/* Every mutating entry point leaves through here: a failure recorded by the
+   operation (allocation, size limit, NCCL) that an early return skipped past
+   is reported and CLEARED now, so it can neither be lost nor leak into the
+   next operation on the context. */
+static int swept(Ctx &ctx, int rc, const char *where) {
+  if (rc == 0 && ctx.last_error.empty()) return 0;
+  const int e = check_errors(ctx, where);
+  return rc ? rc : e;
+}
+
 extern "C" {
 
 int tmrgpu_ctx_sync(tmrgpu_ctx *ctx) { return check_errors(ctx->c, "sync"); }
@@ -182,11 +192,13 @@ int64_t tmrgpu_count(tmrgpu_forest *f) { return f->f.n; }
 
 int tmrgpu_upload_octants(tmrgpu_forest *f, const tmrgpu_octant *recs,
                           int64_t n) {
-  return upload_octants(f->f, reinterpret_cast<const Oct24 *>(recs), n);
+  return swept(*f->f.ctx, upload_octants(f->f, reinterpret_cast<const Oct24 *>(recs), n),
+               "upload_octants");
 }
 
 int tmrgpu_download_octants(tmrgpu_forest *f, tmrgpu_octant *recs) {
-  return download_octants(f->f, reinterpret_cast<Oct24 *>(recs));
+  return swept(*f->f.ctx, download_octants(f->f, reinterpret_cast<Oct24 *>(recs)),
+               "download_octants");
 }
 
 int tmrgpu_download_info(tmrgpu_forest *F, int16_t *info) {
@@ -202,20 +214,22 @@ int tmrgpu_download_info(tmrgpu_forest *F, int16_t *info) {
 
 int tmrgpu_sort_unique(tmrgpu_forest *f) {
   sort_unique_elements(f->f);
-  if (unify_depth(f->f)) return 1;
-  if (gather_owners(f->f, 1)) return 1; /* createRandomTrees (:1905-1916) */
+  if (unify_depth(f->f)) return swept(*f->f.ctx, 1, "sort_unique");
+  /* createRandomTrees (:1905-1916) */
+  if (gather_owners(f->f, 1)) return swept(*f->f.ctx, 1, "sort_unique");
   return check_errors(*f->f.ctx, "sort_unique");
 }
 
 int tmrgpu_create_trees(tmrgpu_forest *f, int level, int block_start,
                         int block_end) {
-  if (create_trees(f->f, level, block_start, block_end)) return 1;
-  if (unify_depth(f->f)) return 1;
-  return gather_owners(f->f, 1); /* back-fill quirk of createTrees (:1826-1832) */
+  int rc = create_trees(f->f, level, block_start, block_end);
+  if (!rc) rc = unify_depth(f->f);
+  if (!rc) rc = gather_owners(f->f, 1); /* back-fill quirk of createTrees (:1826-1832) */
+  return swept(*f->f.ctx, rc, "create_trees");
 }
 
 int tmrgpu_repartition(tmrgpu_forest *f, int max_rank) {
-  return repartition(f->f, max_rank);
+  return swept(*f->f.ctx, repartition(f->f, max_rank), "repartition");
 }
 
 int tmrgpu_get_owners(tmrgpu_forest *F, tmrgpu_octant *out) {
@@ -239,7 +253,7 @@ int tmrgpu_node_range(tmrgpu_forest *F, int *out) {
 
 int tmrgpu_node_mirror(tmrgpu_forest *F, int which, const void **out) {
   *out = node_mirror_get(F->f, which);
-  return *out ? 0 : 1;
+  return swept(*F->f.ctx, *out ? 0 : 1, "node_mirror");
 }
 
 int tmrgpu_set_node_prefetch(tmrgpu_forest *F, int mask) {
@@ -249,21 +263,24 @@ int tmrgpu_set_node_prefetch(tmrgpu_forest *F, int mask) {
 
 int tmrgpu_refine_device(tmrgpu_forest *f, const int *d_flags, int min_level,
                          int max_level) {
-  if (refine(f->f, d_flags, min_level, max_level)) return 1;
-  return refine_exchange(f->f); /* no-op on a single rank */
+  int rc = refine(f->f, d_flags, min_level, max_level);
+  if (!rc) rc = refine_exchange(f->f); /* no-op on a single rank */
+  return swept(*f->f.ctx, rc, "refine");
 }
 
 int tmrgpu_refine(tmrgpu_forest *F, const int *h_flags, int min_level,
                   int max_level) {
   Forest &f = F->f;
   if (!h_flags || f.n == 0) {
-    if (refine(f, NULL, min_level, max_level)) return 1;
-    return refine_exchange(f);
+    int rc = refine(f, NULL, min_level, max_level);
+    if (!rc) rc = refine_exchange(f);
+    return swept(*f.ctx, rc, "refine");
   }
   DBuf<int> d_flags(*f.ctx, f.n);
   copy_h2d(*f.ctx, d_flags.get(), h_flags, (size_t)f.n * sizeof(int));
-  if (refine(f, d_flags.get(), min_level, max_level)) return 1;
-  return refine_exchange(f);
+  int rc = refine(f, d_flags.get(), min_level, max_level);
+  if (!rc) rc = refine_exchange(f);
+  return swept(*f.ctx, rc, "refine");
 }
 
 int tmrgpu_exchange_counts(tmrgpu_ctx *ctx, const int *send_counts,
@@ -304,15 +321,17 @@ int tmrgpu_exchange_records(tmrgpu_ctx *ctx, const tmrgpu_octant *send,
 }
 
 int tmrgpu_balance(tmrgpu_forest *f, int balance_corner) {
-  if (forest_comm(f->f)) return balance_multi(f->f, balance_corner);
-  return balance(f->f, balance_corner);
+  const int rc = forest_comm(f->f) ? balance_multi(f->f, balance_corner)
+                                  : balance(f->f, balance_corner);
+  return swept(*f->f.ctx, rc, "balance");
 }
 
 int tmrgpu_coarsen(tmrgpu_forest *src, tmrgpu_forest *dst) {
   tmrgpu_share_connectivity(src, dst);
   dst->f.serial = src->f.serial;
-  if (coarsen_into(src->f, dst->f)) return 1;
-  return gather_owners(dst->f, 0); /* reference :2157-2160 */
+  int rc = coarsen_into(src->f, dst->f);
+  if (!rc) rc = gather_owners(dst->f, 0); /* reference :2157-2160 */
+  return swept(*dst->f.ctx, rc, "coarsen");
 }
 
 int tmrgpu_duplicate(tmrgpu_forest *src, tmrgpu_forest *dst) {
@@ -320,12 +339,12 @@ int tmrgpu_duplicate(tmrgpu_forest *src, tmrgpu_forest *dst) {
   dst->f.nodes.prefetch = src->f.nodes.prefetch;
   dst->f.serial = src->f.serial;
   dst->f.owners = src->f.owners; /* reference :2104-2106 */
-  return duplicate_into(src->f, dst->f);
+  return swept(*dst->f.ctx, duplicate_into(src->f, dst->f), "duplicate");
 }
 
 int tmrgpu_create_nodes(tmrgpu_forest *f, int order, int interp_type,
                         const double *knots) {
-  return create_nodes(f->f, order, interp_type, knots);
+  return swept(*f->f.ctx, create_nodes(f->f, order, interp_type, knots), "create_nodes");
 }
 
 int tmrgpu_free_nodes(tmrgpu_forest *f) {
@@ -406,7 +425,7 @@ int tmrgpu_interp_device_views(tmrgpu_forest *F, const int **rows,
 }
 
 int tmrgpu_download_sorted_node_numbers(tmrgpu_forest *f, int *out) {
-  return sorted_node_numbers(f->f, out);
+  return swept(*f->f.ctx, sorted_node_numbers(f->f, out), "sorted_node_numbers");
 }
 
 int tmrgpu_create_interp(tmrgpu_forest *fine, tmrgpu_forest *coarse,
@@ -414,7 +433,7 @@ int tmrgpu_create_interp(tmrgpu_forest *fine, tmrgpu_forest *coarse,
   const int rc = create_interp(fine->f, coarse->f);
   if (nrows) *nrows = fine->f.interp.nrows;
   if (nnz) *nnz = fine->f.interp.nnz;
-  return rc;
+  return swept(*fine->f.ctx, rc, "create_interp");
 }
 
 int tmrgpu_download_interp(tmrgpu_forest *F, int *rows, int *rowp, int *cols,
@@ -433,23 +452,26 @@ int tmrgpu_download_interp(tmrgpu_forest *F, int *rows, int *rowp, int *cols,
 int tmrgpu_find_enclosing(tmrgpu_forest *F, int order, const double *knots,
                           const tmrgpu_octant *nodes, int64_t n,
                           int *out_index) {
-  return find_enclosing_batch(F->f, order, knots,
-                              reinterpret_cast<const Oct24 *>(nodes), n,
-                              out_index);
+  return swept(*F->f.ctx,
+               find_enclosing_batch(F->f, order, knots,
+                                    reinterpret_cast<const Oct24 *>(nodes), n, out_index),
+               "find_enclosing");
 }
 
 int tmrgpu_array_sort(tmrgpu_ctx *ctx, tmrgpu_octant *recs, int64_t n,
                       int use_node_index, int64_t *nout) {
-  return array_sort(ctx->c, reinterpret_cast<Oct24 *>(recs), n, use_node_index,
-                    nout);
+  return swept(ctx->c,
+               array_sort(ctx->c, reinterpret_cast<Oct24 *>(recs), n, use_node_index, nout),
+               "array_sort");
 }
 
 int tmrgpu_array_contains(tmrgpu_ctx *ctx, const tmrgpu_octant *sorted,
                           int64_t n, const tmrgpu_octant *queries, int64_t nq,
                           int mode, int *out_index) {
-  return array_contains(ctx->c, reinterpret_cast<const Oct24 *>(sorted), n,
-                        reinterpret_cast<const Oct24 *>(queries), nq, mode,
-                        out_index);
+  return swept(ctx->c,
+               array_contains(ctx->c, reinterpret_cast<const Oct24 *>(sorted), n,
+                              reinterpret_cast<const Oct24 *>(queries), nq, mode, out_index),
+               "array_contains");
 }
 
 int tmrgpu_synth_flags(tmrgpu_forest *F, uint64_t seed, int pct, int *d_flags) {

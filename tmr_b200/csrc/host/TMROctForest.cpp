@@ -800,7 +800,47 @@ TMROctant *TMROctForest::findEnclosing(const int order, const double *knots,
                             &index)) {
     return NULL;
   }
-  if (index < 0) return NULL;
+  if (index < 0) {
+    /* not on this rank: name the rank that owns the node's position
+       (reference :6348-6372; src/topology/TMR_TACSTopoCreator.cpp:166-217
+       routes on this value) */
+    if (mpi_owner && mpi_size > 1) {
+      const int32_t hmax = 1 << TMR_MAX_LEVEL;
+      const int32_t h = 1 << (TMR_MAX_LEVEL - node->level);
+      const int idx[3] = {node->info % order, (node->info % (order * order)) / order,
+                          node->info / (order * order)};
+      const int32_t base[3] = {node->x, node->y, node->z};
+      int32_t c[3];
+      for (int a = 0; a < 3; a++) {
+        int32_t ci = -1;
+        if (idx[a] == 0 || idx[a] == order - 1) {
+          ci = base[a] + (idx[a] / (order - 1)) * h;
+        } else if (order % 2 == 1 && idx[a] == order / 2) {
+          ci = base[a] + h / 2;
+        }
+        const double cd = base[a] + 0.5 * h * (1.0 + knots[idx[a]]);
+        c[a] = ci < 0 ? (int)cd : ci;
+        if (c[a] == 0) {
+          c[a] += 1;
+        } else if (c[a] == hmax) {
+          c[a] -= 1;
+        }
+      }
+      TMROctant n;
+      n.block = node->block;
+      n.x = c[0];
+      n.y = c[1];
+      n.z = c[2];
+      if (!owners) {
+        owners = new TMROctant[mpi_size];
+        tmrgpu_get_owners(dev, reinterpret_cast<tmrgpu_octant *>(owners));
+      }
+      int rank = 0; /* getOctantMPIOwner (:2334-2343) */
+      while (rank < mpi_size - 1 && owners[rank + 1].comparePosition(&n) <= 0) rank++;
+      *mpi_owner = rank;
+    }
+    return NULL;
+  }
   TMROctantArray *arr;
   getOctants(&arr); /* a pointer into the mirror escapes: marks it exposed */
   TMROctant *a;
