@@ -493,6 +493,9 @@ def main():
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = lib.tmrgpu_launch_count(ctx)
+    lib.tmrgpu_sync_count.restype = ctypes.c_long
+    lib.tmrgpu_sync_count.argtypes = [P]
+    host_syncs = lib.tmrgpu_sync_count(ctx)
     buf = ctypes.create_string_buffer(1 << 16)
     lib.tmrgpu_profile_json(ctx, buf, len(buf))
     prof = json.loads(buf.value.decode())
@@ -720,6 +723,9 @@ def main():
             "fingerprint": fp_final,
             "numa_bound_cpus": numa_cpus,
             "gpu_launches": int(launches),
+            "kernel_launches_per_step": launches / args.steps,
+            "blocking_host_round_trips_per_step": host_syncs / args.steps,
+            "kernel_ms_per_step": sum(v["ms"] for v in prof.values()) / args.steps,
             "clocks": clocks,
             "roofline": roof,
             "cycle_compulsory_bytes": int(b_alg),

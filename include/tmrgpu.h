@@ -40,6 +40,9 @@ int tmrgpu_profile_enable(tmrgpu_ctx *ctx, int on);
 int tmrgpu_profile_reset(tmrgpu_ctx *ctx);
 int tmrgpu_profile_json(tmrgpu_ctx *ctx, char *buf, int buflen);
 long tmrgpu_launch_count(tmrgpu_ctx *ctx);
+/* blocking host<->device round trips (synchronising copies, error sweeps)
+   since the last tmrgpu_profile_reset: the control-plane cost of an operation */
+long tmrgpu_sync_count(tmrgpu_ctx *ctx);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------
    (replaces MPI_Comm + the MPI datatypes of reference src/TMRBase.cpp:42-92)

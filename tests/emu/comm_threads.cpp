@@ -37,6 +37,9 @@ class ThreadComm : public Comm {
     }
     pthread_barrier_wait(&w->bar);
   }
+  void allgather_dev(Ctx &ctx, const void *send, void *recv, size_t bytes) override {
+    allgather_host(ctx, send, recv, bytes);
+  }
   void alltoallv(Ctx &, const void *send, const i64 *send_off, void *recv,
                  const i64 *recv_off, size_t eb) override {
     w->ptr[rank] = send;

@@ -26,6 +26,11 @@ class Comm {
      size*bytes (small control data: counts, partition keys) */
   virtual void allgather_host(Ctx &ctx, const void *send, void *recv,
                               size_t bytes) = 0;
+  /* same with DEVICE buffers, enqueued on the context's stream, no host
+     round trip: counts produced by one kernel and consumed by the next (or
+     read back together with other results in one copy) */
+  virtual void allgather_dev(Ctx &ctx, const void *send, void *recv,
+                             size_t bytes) = 0;
   /* variable all-to-all of DEVICE buffers; offsets are in elements of
      elem_bytes bytes, arrays of size+1 entries */
   virtual void alltoallv(Ctx &ctx, const void *send, const i64 *send_off,

@@ -33,13 +33,30 @@ class NcclComm : public Comm {
       memcpy(recv, send, bytes);
       return;
     }
+    /* page-locked staging (cached by the context), so the upload does not
+       need its own synchronisation: ONE blocking round trip per call */
     unsigned char *d = static_cast<unsigned char *>(
         dev_alloc(ctx, bytes * (size_t)(size + 1)));
-    copy_h2d(ctx, d, send, bytes);
-    TMR_NCCL_OK(ncclAllGather(d, d + bytes, bytes, ncclChar, comm,
-                              (cudaStream_t)ctx.stream));
-    copy_d2h(ctx, recv, d + bytes, bytes * (size_t)size);
+    unsigned char *h = static_cast<unsigned char *>(
+        host_alloc(ctx, bytes * (size_t)(size + 1)));
+    if (!d || !h) return;
+    memcpy(h, send, bytes);
+    cudaStream_t st = (cudaStream_t)ctx.stream;
+    cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+    TMR_NCCL_OK(ncclAllGather(d, d + bytes, bytes, ncclChar, comm, st));
+    copy_d2h(ctx, h + bytes, d + bytes, bytes * (size_t)size);
+    memcpy(recv, h + bytes, bytes * (size_t)size);
+    host_free(ctx, h);
     dev_free(ctx, d);
+  }
+  void allgather_dev(Ctx &ctx, const void *send, void *recv,
+                     size_t bytes) override {
+    if (size == 1) {
+      copy_d2d(ctx, recv, send, bytes);
+      return;
+    }
+    TMR_NCCL_OK(ncclAllGather(send, recv, bytes, ncclChar, comm,
+                              (cudaStream_t)ctx.stream));
   }
   void alltoallv(Ctx &ctx, const void *send, const i64 *send_off, void *recv,
                  const i64 *recv_off, size_t elem_bytes) override {

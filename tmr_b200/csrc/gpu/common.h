@@ -568,6 +568,21 @@ TMR_HD int popc64(u64 v) {
 #endif
 }
 
+TMR_HD int ctz64(u64 v) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+TMR_HD int ctz32(u32 v) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+
 /* first index i in [0,n) with a[i] >= key */
 TMR_HD i64 lower_bound_u64(const u64 *a, i64 n, u64 key) {
   i64 lo = 0, hi = n;

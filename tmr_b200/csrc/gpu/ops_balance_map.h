@@ -40,7 +40,13 @@ struct CellMaps {
   const u32 *wrank;       /* refined cells before each word (all levels) */
   i64 woff[kMaxMapLevels + 1];
   int D;                  /* levels 0 .. D-1 */
-  int nblocks;
+  int nblocks;            /* trees covered: block0 .. block0 + nblocks - 1 */
+  int block0;             /* (several ranks: the trees of this rank's range) */
+  TMR_HD bool has_block(i64 b) const { return b >= block0 && b < block0 + nblocks; }
+  /* local cell index of global cell (block, Morton m) at level l */
+  TMR_HD i64 cell_of(i64 block, u64 m, int l) const {
+    return ((block - block0) << (3 * l)) | (i64)m;
+  }
   TMR_HD u32 byte_of(int l, i64 group) const {
     /* refined mask of the 8 level-l cells 8 group .. 8 group + 7 */
     const i64 bit = group << 3;
@@ -57,70 +63,179 @@ struct CellMaps {
   TMR_HD i64 cells(int l) const { return (i64)nblocks << (3 * l); }
 };
 
+/* several ranks: a cell of a tree that other ranks hold too (a tree cut by a
+   partition boundary, or a tree outside this rank's span) is forwarded to
+   them as (level << 58 | global cell), one entry per destination */
+struct MapRemote {
+  const i32 *span_b0; /* per rank: first / last tree of its span (b0 > b1: none) */
+  const i32 *span_b1;
+  int R, me;
+  int lo_shared, hi_shared; /* my first / last tree is in another rank's span */
+  u64 *key;
+  u32 *dest;
+  unsigned long long *count;
+  i64 cap;
+  TMR_HD bool on() const { return R > 1; }
+  TMR_HD bool needs_forward(const CellMaps &mp, i64 block) const {
+    if (!mp.has_block(block)) return true;
+    return (block == mp.block0 && lo_shared) ||
+           (block == mp.block0 + mp.nblocks - 1 && hi_shared);
+  }
+  TMR_HD void forward(i64 block, u64 m, int l) const {
+    const u64 k = ((u64)l << 58) | ((u64)block << (3 * l)) | m;
+    for (int r = 0; r < R; r++) {
+      if (r == me || block < span_b0[r] || block > span_b1[r]) continue;
+      const unsigned long long s = fetch_add_u64(count, 1ULL);
+      if ((i64)s < cap) {
+        key[s] = k;
+        dest[s] = (u32)r;
+      }
+    }
+  }
+};
+
 /* every input octant marks its parent; level-0 octants flag their tree */
 struct MapMarkParentsFn {
   const u64 *keys;
   KeyFmt fmt;
   CellMaps mp;
-  int *root_flag;
-  TMR_HD i64 parent_cell(u64 k, int *L) const {
+  int *root_flag; /* by global tree */
+  MapRemote rm;
+  /* parent as (tree, Morton at level L-1); false for level-0 octants */
+  TMR_HD bool parent_cell(u64 k, int *L, i64 *block, u64 *m) const {
     *L = (int)(k & 31);
-    if (*L == 0) return -1;
+    if (*L == 0) return false;
     const u64 rest = k >> 5;
-    const u64 block = rest >> (3 * fmt.D);
-    const u64 m = rest & low_mask(3 * fmt.D);
-    return (i64)((block << (3 * (*L - 1))) | (m >> (3 * (fmt.D - *L + 1))));
+    *block = (i64)(rest >> (3 * fmt.D));
+    *m = (rest & low_mask(3 * fmt.D)) >> (3 * (fmt.D - *L + 1));
+    return true;
   }
   TMR_HD void operator()(i64 i) const {
     int L, Lp;
-    const i64 pc = parent_cell(keys[i], &L);
-    if (pc < 0) {
+    i64 b, bp;
+    u64 m, mq;
+    if (!parent_cell(keys[i], &L, &b, &m)) {
       root_flag[(int)((keys[i] >> 5) >> (3 * fmt.D))] = 1;
       return;
     }
-    if (i > 0 && parent_cell(keys[i - 1], &Lp) == pc && Lp == L) return;
+    if (i > 0 && parent_cell(keys[i - 1], &Lp, &bp, &mq) && Lp == L && bp == b &&
+        mq == m) {
+      return;
+    }
+    const i64 pc = mp.cell_of(b, m, L - 1);
     TMR_ATOMIC_OR_I32(&mp.bits[mp.woff[L - 1] + (pc >> 5)], 1u << (int)(pc & 31));
+    if (rm.on() && rm.needs_forward(mp, b)) rm.forward(b, m, L - 1);
+  }
+};
+
+/* cells received from other ranks */
+struct MapOrReceivedFn {
+  const u64 *key;
+  CellMaps mp;
+  TMR_HD void operator()(i64 i) const {
+    const u64 k = key[i];
+    const int l = (int)(k >> 58);
+    const u64 c = k & low_mask(58);
+    const i64 block = (i64)(c >> (3 * l));
+    if (!mp.has_block(block)) return;
+    const i64 pc = mp.cell_of(block, c & low_mask(3 * l), l);
+    TMR_ATOMIC_OR_I32(&mp.bits[mp.woff[l] + (pc >> 5)], 1u << (int)(pc & 31));
   }
 };
 
 struct MapOrEmit {
-  u32 *words; /* level l-1 */
-  int sh;     /* 3 (l-1) */
+  const CellMaps *mp;
+  const MapRemote *rm;
+  int lp; /* level of the demanded cells */
   TMR_HD void operator()(i32 block, i32 x, i32 y, i32 z) {
-    const u64 c = ((u64)(u32)block << sh) | morton3((u32)x, (u32)y, (u32)z);
-    TMR_ATOMIC_OR_I32(&words[c >> 5], 1u << (int)(c & 31));
+    const u64 m = morton3((u32)x, (u32)y, (u32)z);
+    if (mp->has_block(block)) {
+      const i64 c = mp->cell_of(block, m, lp);
+      TMR_ATOMIC_OR_I32(&mp->bits[mp->woff[lp] + (c >> 5)], 1u << (int)(c & 31));
+    }
+    if (rm->on() && rm->needs_forward(*mp, block)) rm->forward(block, m, lp);
   }
 };
 
-/* closure step l -> l-1, one thread per sibling group of level l */
+/* which of the 27 cells around the parent (offset (ox,oy,oz) in {-1,0,1}^3,
+   bit (ox+1) + 3 (oy+1) + 9 (oz+1)) a refined child with x-major digit d
+   demands: the parent itself and its neighbours on the child's side across
+   faces and edges (and the corner when corners are balanced) */
+TMR_HD u32 child_demand_mask(int d, int corner) {
+  const int s[3] = {(d & 4) ? 1 : -1, (d & 2) ? 1 : -1, (d & 1) ? 1 : -1};
+  u32 need = 0;
+  TMR_UNROLL
+  for (int a = 0; a < 8; a++) {
+    if (a == 7 && !corner) continue;
+    const int ox = (a & 1) ? s[0] : 0, oy = (a & 2) ? s[1] : 0, oz = (a & 4) ? s[2] : 0;
+    need |= 1u << ((ox + 1) + 3 * (oy + 1) + 9 * (oz + 1));
+  }
+  return need;
+}
+
+/* closure step l -> l-1, one thread per sibling group of level l.  The
+   demands of the group's refined members are united first (8 refined siblings
+   ask for 19 or 27 distinct cells, not 8 x 7), and a parent that does not
+   touch its tree's boundary finds its neighbours by dilated +-1 on the three
+   axis components of its Morton code. */
 struct MapClosureFn {
   CellMaps mp;
   ConnTables t;
   int l;
   int corner;
+  MapRemote rm;
   TMR_HD void operator()(i64 g) const {
     const u32 byte = mp.byte_of(l, g);
     if (!byte) return;
+    u32 need = 0;
+    TMR_UNROLL
+    for (int d = 0; d < 8; d++) {
+      if ((byte >> d) & 1u) need |= child_demand_mask(d, corner);
+    }
     /* g is the cell index of the group's parent at level l-1 */
     const int shp = 3 * (l - 1);
-    const i32 block = (i32)(g >> shp);
-    u32 qx, qy, qz;
-    unmorton3((u64)g & low_mask(shp), &qx, &qy, &qz);
-    const i32 N = 1 << (l - 1);
-    MapOrEmit emit = {mp.bits + mp.woff[l - 1], shp};
-    /* the members' own parent */
-    emit(block, (i32)qx, (i32)qy, (i32)qz);
-    for (int d = 0; d < 8; d++) {
-      if (!((byte >> d) & 1u)) continue;
-      /* x-major digit d = 4 xbit + 2 ybit + zbit: the side of the parent the
-         member sits on */
-      const i32 s[3] = {(d & 4) ? 1 : -1, (d & 2) ? 1 : -1, (d & 1) ? 1 : -1};
-      for (int a = 1; a < 8; a++) {
-        if (a == 7 && !corner) continue;
-        i32 q[3] = {(i32)qx + ((a & 1) ? s[0] : 0), (i32)qy + ((a & 2) ? s[1] : 0),
-                    (i32)qz + ((a & 4) ? s[2] : 0)};
-        tree_images(t, block, q, N, emit);
+    const u64 mq = (u64)g & low_mask(shp);
+    u32 *words = mp.bits + mp.woff[l - 1];
+    /* per axis: the component one step down / in place / one step up, and
+       whether the parent touches the low / high tree face */
+    u64 comp[3][3];
+    bool lo = false, hi = false;
+    TMR_UNROLL
+    for (int a = 0; a < 3; a++) { /* a = 0 x, 1 y, 2 z; x is Morton bit 2 */
+      const u64 am = (0x1249249249249249ULL << (2 - a)) & low_mask(shp);
+      const u64 c = mq & am;
+      lo = lo || c == 0;
+      hi = hi || c == am;
+      comp[a][0] = (c - 1) & am;
+      comp[a][1] = c;
+      comp[a][2] = ((c | ~am) + 1) & am;
+    }
+    const i32 block = (i32)(g >> shp) + mp.block0;
+    if (!lo && !hi) {
+      /* all demands stay inside this tree */
+      const u64 base = ((u64)g >> shp) << shp; /* local tree bits */
+      const bool fwd = rm.on() && rm.needs_forward(mp, block);
+      while (need) {
+        const int o = ctz32(need);
+        need &= need - 1;
+        const int oz = o / 9, oy = (o - 9 * oz) / 3, ox = o - 9 * oz - 3 * oy;
+        const u64 mc = comp[0][ox] | comp[1][oy] | comp[2][oz];
+        const u64 c = base | mc;
+        TMR_ATOMIC_OR_I32(&words[c >> 5], 1u << (int)(c & 31));
+        if (fwd) rm.forward(block, mc, l - 1);
       }
+      return;
+    }
+    u32 qx, qy, qz;
+    unmorton3(mq, &qx, &qy, &qz);
+    const i32 N = 1 << (l - 1);
+    MapOrEmit emit = {&mp, &rm, l - 1};
+    while (need) {
+      const int o = ctz32(need);
+      need &= need - 1;
+      const int oz = o / 9, oy = (o - 9 * oz) / 3, ox = o - 9 * oz - 3 * oy;
+      const i32 q[3] = {(i32)qx + ox - 1, (i32)qy + oy - 1, (i32)qz + oz - 1};
+      tree_images(t, block, q, N, emit);
     }
   }
 };
@@ -161,23 +276,29 @@ struct MapTreeCountFn {
   CellMaps mp;
   const u32 *cnt;
   const int *root_flag;
-  TMR_HD u32 operator()(i64 b) const {
+  TMR_HD u32 operator()(i64 b) const { /* b: tree of the map (local index) */
     if (mp.test(0, b)) return cnt[mp.rank_of(0, b)];
-    return root_flag[b] ? 1u : 0u;
+    return root_flag[b + mp.block0] ? 1u : 0u;
   }
 };
 
 /* top-down: start of the leaves of every refined cell; children that are not
-   refined are leaves and are written in place */
+   refined are leaves and are written in place.  Several ranks: the maps span
+   whole trees, the rank keeps the leaves [first, last) of that sequence (its
+   own range of positions). */
 struct MapFillFn {
   CellMaps mp;
   int l;
   const u32 *cnt;
   u32 *off;          /* by dense index (levels >= 1) */
-  const u32 *toff;   /* per tree (level 0) */
+  const u32 *toff;   /* per tree of the map (level 0) */
   const int *root_flag;
   KeyFmt fmt;
   u64 *out;
+  u32 first, last;
+  TMR_HD void put(u32 at, u64 key) const {
+    if (at >= first && at < last) out[at - first] = key;
+  }
   TMR_HD void operator()(i64 g) const {
     u32 byte;
     if (l == 0) {
@@ -188,8 +309,8 @@ struct MapFillFn {
         if (b >= mp.nblocks) break;
         if (mp.test(0, b)) {
           byte |= 1u << d;
-        } else if (root_flag[b]) {
-          out[toff[b]] = (u64)b << (3 * fmt.D + 5);
+        } else if (root_flag[b + mp.block0]) {
+          put(toff[b], (u64)(b + mp.block0) << (3 * fmt.D + 5));
         }
       }
     } else {
@@ -202,7 +323,7 @@ struct MapFillFn {
       const i64 cell = (g << 3) | d;
       u32 at = (l == 0) ? toff[cell] : off[mp.rank_of(l, cell)];
       const u32 kids = (L < mp.D) ? mp.byte_of(L, cell) : 0u;
-      const u64 block = (u64)cell >> (3 * l);
+      const u64 block = ((u64)cell >> (3 * l)) + (u64)mp.block0;
       const u64 m = (u64)cell & low_mask(3 * l);
       for (int e = 0; e < 8; e++) {
         const i64 child = (cell << 3) | e;
@@ -212,10 +333,48 @@ struct MapFillFn {
           at += cnt[r];
         } else {
           const u64 mD = ((m << 3) | (u64)e) << (3 * (fmt.D - L));
-          out[at++] = (block << (3 * fmt.D + 5)) | (mD << 5) | (u64)L;
+          put(at++, (block << (3 * fmt.D + 5)) | (mD << 5) | (u64)L);
         }
       }
     }
+  }
+};
+
+/* number of leaves of the map's trees that lie before position `pos` (depth
+   D, global), for pos on a leaf boundary: walks one root-to-leaf path */
+struct MapLeavesBeforeFn {
+  CellMaps mp;
+  const u32 *cnt;
+  const u32 *toff;
+  u32 total;
+  int D;
+  const u64 *pos; /* [nq] */
+  u32 *out;
+  TMR_HD void operator()(i64 q) const {
+    const u64 p = pos[q];
+    const i64 block = (i64)(p >> (3 * D));
+    if (block < mp.block0) {
+      out[q] = 0;
+      return;
+    }
+    if (block >= mp.block0 + mp.nblocks) {
+      out[q] = total;
+      return;
+    }
+    const u64 m = p & low_mask(3 * D);
+    u32 n = toff[block - mp.block0];
+    i64 cell = block - mp.block0;
+    for (int l = 0; l < D; l++) {
+      if (!mp.test(l, cell)) break; /* a leaf anchored at or before pos */
+      const int e = (int)((m >> (3 * (D - l - 1))) & 7);
+      const u32 kids = (l + 1 < mp.D) ? mp.byte_of(l + 1, cell) : 0u;
+      for (int k = 0; k < e; k++) {
+        n += ((kids >> k) & 1u) ? cnt[mp.rank_of(l + 1, (cell << 3) | k)] : 1u;
+      }
+      cell = (cell << 3) | e;
+      if (!((kids >> e) & 1u)) break;
+    }
+    out[q] = n;
   }
 };
 
@@ -231,6 +390,65 @@ inline i64 balance_map_words(int nblocks, int D, i64 budget_words, i64 *woff) {
   }
   woff[D] = w;
   return w;
+}
+
+/* The shared back half of both drivers: rank the refined cells, count leaves
+   bottom-up, place them top-down.  pos_lo/pos_hi: keep the leaves of that
+   range of positions (several ranks), or NULL for all. */
+inline int balance_map_leaves(Forest &f, CellMaps &mp, i64 words, DBuf<u32> &wrank,
+                              const int *root_flag, const u64 *range /* [2] or NULL */) {
+  Ctx &ctx = *f.ctx;
+  const int D = mp.D;
+  MapWordPopFn wp = {mp.bits};
+  const i64 nref = (i64)scan_counts(ctx, words, wp, wrank.get(), "balance_map_rank");
+  DBuf<u32> cnt(ctx, nref), off(ctx, nref), toff(ctx, mp.nblocks);
+  for (int l = D - 1; l >= 0; l--) {
+    MapCountFn cf = {mp, l, cnt.get()};
+    launch(ctx, l == 0 ? ((i64)mp.nblocks + 7) / 8 : mp.cells(l - 1), cf,
+           "balance_map_count");
+  }
+  MapTreeCountFn tc = {mp, cnt.get(), root_flag};
+  const i64 total =
+      (i64)scan_counts(ctx, mp.nblocks, tc, toff.get(), "balance_map_trees");
+  if (total >= (1LL << 32) - 1) {
+    fprintf(stderr, "TMROctForest Error: balance() would create %lld octants in the "
+                    "trees of one rank\n", (long long)total);
+    return 1;
+  }
+  u32 first = 0, last = (u32)total;
+  if (range) {
+    DBuf<u64> d_pos(ctx, 2);
+    DBuf<u32> d_n(ctx, 2);
+    copy_h2d(ctx, d_pos.get(), range, 2 * sizeof(u64));
+    MapLeavesBeforeFn lb = {mp, cnt.get(), toff.get(), (u32)total, f.fmt.D,
+                            d_pos.get(), d_n.get()};
+    launch(ctx, 2, lb, "balance_map_range");
+    u32 h_n[2] = {0, 0};
+    copy_d2h(ctx, h_n, d_n.get(), sizeof(h_n));
+    first = h_n[0];
+    last = h_n[1];
+  }
+  const i64 mine = (i64)last - (i64)first;
+  if (mine >= (1LL << 31)) {
+    fprintf(stderr,
+            "TMROctForest Error: balance() would create %lld octants on one "
+            "rank (int32 index limit of the TMROctForest API)\n",
+            (long long)mine);
+    return 1;
+  }
+  DBuf<u64> out(ctx, mine);
+  for (int l = 0; l < D; l++) {
+    MapFillFn ff = {mp,       l,     cnt.get(), off.get(), toff.get(), root_flag,
+                    f.fmt,    out.get(), first, last};
+    launch(ctx, l == 0 ? ((i64)mp.nblocks + 7) / 8 : mp.cells(l - 1), ff,
+           "balance_map_fill");
+  }
+  /* a failed allocation above launched nothing: leave the forest as it was */
+  if (!ctx_ok(ctx)) return check_errors(ctx, "balance");
+  f.keys.swap(out);
+  f.n = mine;
+  f.last_out = f.n;
+  return 0;
 }
 
 /* returns 0 ok, 1 error, -1 = not applicable (use the sorted-array closure) */
@@ -253,44 +471,19 @@ inline int balance_map(Forest &f, int balance_corner) {
   mp.wrank = wrank.get();
   mp.D = D;
   mp.nblocks = f.nblocks;
+  mp.block0 = 0;
   DBuf<int> root_flag(ctx, f.nblocks);
   dev_zero(ctx, root_flag.get(), (size_t)f.nblocks * sizeof(int));
-  MapMarkParentsFn mk = {f.keys.get(), f.fmt, mp, root_flag.get()};
+  MapRemote rm = {NULL, NULL, 1, 0, 0, 0, NULL, NULL, NULL, 0};
+  MapMarkParentsFn mk = {f.keys.get(), f.fmt, mp, root_flag.get(), rm};
   launch(ctx, f.n, mk, "balance_map_mark");
   for (int l = D - 1; l >= 1; l--) {
-    MapClosureFn cl = {mp, f.tables, l, balance_corner};
+    MapClosureFn cl = {mp, f.tables, l, balance_corner, rm};
     launch(ctx, mp.cells(l - 1), cl, "balance_map_closure");
   }
   trace_mark(ctx, "balance: closure");
-  MapWordPopFn wp = {bits.get()};
-  const i64 nref = (i64)scan_counts(ctx, words, wp, wrank.get(), "balance_map_rank");
-  DBuf<u32> cnt(ctx, nref), off(ctx, nref), toff(ctx, f.nblocks);
-  for (int l = D - 1; l >= 0; l--) {
-    MapCountFn cf = {mp, l, cnt.get()};
-    launch(ctx, l == 0 ? ((i64)f.nblocks + 7) / 8 : mp.cells(l - 1), cf,
-           "balance_map_count");
-  }
-  MapTreeCountFn tc = {mp, cnt.get(), root_flag.get()};
-  const i64 total = (i64)scan_counts(ctx, f.nblocks, tc, toff.get(), "balance_map_trees");
-  if (total >= (1LL << 31)) {
-    fprintf(stderr,
-            "TMROctForest Error: balance() would create %lld octants on one "
-            "rank (int32 index limit of the TMROctForest API)\n",
-            (long long)total);
-    return 1;
-  }
-  DBuf<u64> out(ctx, total);
-  for (int l = 0; l < D; l++) {
-    MapFillFn ff = {mp, l, cnt.get(), off.get(), toff.get(), root_flag.get(), f.fmt,
-                    out.get()};
-    launch(ctx, l == 0 ? ((i64)f.nblocks + 7) / 8 : mp.cells(l - 1), ff,
-           "balance_map_fill");
-  }
-  /* a failed allocation above launched nothing: leave the forest as it was */
-  if (!ctx_ok(ctx)) return check_errors(ctx, "balance");
-  f.keys.swap(out);
-  f.n = total;
-  f.last_out = f.n;
+  const int rc = balance_map_leaves(f, mp, words, wrank, root_flag.get(), NULL);
+  if (rc) return rc;
   trace_mark(ctx, "balance: leaves");
   return check_errors(ctx, "balance");
 }

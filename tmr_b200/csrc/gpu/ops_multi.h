@@ -276,6 +276,137 @@ struct LeafOwnerFn {
   TMR_HD int operator()(i64 i) const { return om.owner(keys[i] >> 5); }
 };
 
+/* ---- balance across ranks on cell bitmaps (ops_balance_map.h) ---------------------
+   Every rank keeps the maps of the trees its own range of positions touches.
+   A demand that lands in a tree other ranks hold too -- a tree cut by a
+   partition boundary, or a tree outside this rank's span -- is also sent to
+   them, level by level (the closure only ever goes from level l to l-1, so
+   one exchange per level closes it exactly).  Each rank then has the final
+   refinement of every cell that overlaps its range and writes its own leaves
+   in Morton order: no distributed sort, no leaf routing.
+   Returns -1 when not applicable (maps over budget, or octants held outside
+   their owner's range, the createTrees back-fill state of reference
+   :1826-1832): the sorted-array closure below takes over. */
+struct MapU32DestFn {
+  const u32 *dest;
+  TMR_HD int operator()(i64 i) const { return (int)dest[i]; }
+};
+
+inline int balance_multi_map(Forest &f, int balance_corner) {
+  Ctx &ctx = *f.ctx;
+  Comm &comm = *forest_comm(f);
+  const int me = comm.rank, R = comm.size;
+  const int D = f.fmt.D;
+  if (D < 1 || D > kMaxMapLevels) return -1;
+  std::vector<u64> pos;
+  owner_positions(f, D, pos);
+  const u64 end = (u64)f.nblocks << (3 * D);
+  std::vector<u64> lo(R), hi(R);
+  std::vector<i32> span(2 * R);
+  int ok = 1;
+  for (int r = 0; r < R; r++) {
+    lo[r] = r == 0 ? 0 : pos[r];
+    hi[r] = r + 1 < R ? pos[r + 1] : end;
+    if (lo[r] > end) lo[r] = end;
+    if (hi[r] > end) hi[r] = end;
+    if (hi[r] < lo[r]) ok = 0;
+    span[r] = hi[r] > lo[r] ? (i32)(lo[r] >> (3 * D)) : 1;
+    span[R + r] = hi[r] > lo[r] ? (i32)((hi[r] - 1) >> (3 * D)) : 0;
+  }
+  const int b0 = span[me], b1 = span[R + me];
+  const int nblk = b1 >= b0 ? b1 - b0 + 1 : 0;
+  CellMaps mp;
+  i64 budget = (i64)1 << 27;
+  if (const char *ev = getenv("TMR_B200_BALANCE_MAP_WORDS")) budget = atol(ev);
+  i64 words = ok ? balance_map_words(nblk > 0 ? nblk : 1, D, budget, mp.woff) : -1;
+  if (words < 0) ok = 0;
+  /* my octants must lie in my owner range */
+  if (ok && f.n > 0) {
+    u64 kf = 0, kl = 0;
+    copy_d2h(ctx, &kf, f.keys.get(), sizeof(u64));
+    copy_d2h(ctx, &kl, f.keys.get() + (f.n - 1), sizeof(u64));
+    if ((kf >> 5) < lo[me] || (kl >> 5) >= hi[me]) ok = 0;
+  }
+  {
+    std::vector<i64> all(R);
+    const i64 mine = ok;
+    comm.allgather_host(ctx, &mine, all.data(), sizeof(i64));
+    for (int r = 0; r < R; r++) {
+      if (!all[r]) return -1;
+    }
+  }
+  f.last_mid = f.n;
+  f.info.reset();
+  DBuf<u32> bits(ctx, words), wrank(ctx, words);
+  dev_zero(ctx, bits.get(), (size_t)words * sizeof(u32));
+  mp.bits = bits.get();
+  mp.wrank = wrank.get();
+  mp.D = D;
+  mp.nblocks = nblk;
+  mp.block0 = nblk > 0 ? b0 : 0;
+  DBuf<int> root_flag(ctx, f.nblocks);
+  dev_zero(ctx, root_flag.get(), (size_t)f.nblocks * sizeof(int));
+  DBuf<i32> d_span(ctx, 2 * R);
+  copy_h2d(ctx, d_span.get(), span.data(), (size_t)(2 * R) * sizeof(i32));
+  int lo_shared = 0, hi_shared = 0;
+  for (int r = 0; r < R; r++) {
+    if (r == me || nblk == 0) continue;
+    if (span[r] <= b0 && b0 <= span[R + r]) lo_shared = 1;
+    if (span[r] <= b1 && b1 <= span[R + r]) hi_shared = 1;
+  }
+  i64 cap = 1 << 20;
+  DBuf<u64> rkey(ctx, cap);
+  DBuf<u32> rdest(ctx, cap);
+  DBuf<unsigned long long> rcount(ctx, 1);
+  dev_zero(ctx, rcount.get(), sizeof(unsigned long long));
+
+  /* one closure stage: run `stage` (a kernel that ORs locally and appends the
+     cells other ranks need), ship the appended cells, OR what arrives */
+  for (int l = D; l >= 1; l--) {
+    i64 nsend = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      MapRemote rm = {d_span.get(), d_span.get() + R, R,         me,
+                      lo_shared,    hi_shared,        rkey.get(), rdest.get(),
+                      rcount.get(), cap};
+      if (l == D) {
+        /* stage D: the parents of my own octants */
+        MapMarkParentsFn mk = {f.keys.get(), f.fmt, mp, root_flag.get(), rm};
+        launch(ctx, f.n, mk, "balance_map_mark");
+      } else {
+        MapClosureFn cl = {mp, f.tables, l, balance_corner, rm};
+        launch(ctx, mp.cells(l - 1), cl, "balance_map_closure");
+      }
+      unsigned long long h = 0;
+      copy_d2h(ctx, &h, rcount.get(), sizeof(h));
+      dev_zero(ctx, rcount.get(), sizeof(unsigned long long));
+      nsend = (i64)h;
+      if (nsend <= cap) break;
+      /* the appended cells did not fit: the local ORs are idempotent, rerun */
+      cap = nsend + (nsend >> 2);
+      rkey.alloc(ctx, cap);
+      rdest.alloc(ctx, cap);
+    }
+    MapU32DestFn dest = {rdest.get()};
+    RoutePlan plan;
+    make_route(ctx, comm, nsend, dest, plan);
+    DBuf<u64> got;
+    route_array(ctx, comm, plan, rkey.get(), got);
+    MapOrReceivedFn orf = {got.get(), mp};
+    launch(ctx, plan.nrecv, orf, "balance_map_received");
+  }
+  const u64 range[2] = {lo[me], hi[me]};
+  if (nblk == 0) {
+    DBuf<u64> none;
+    f.keys.swap(none);
+    f.n = 0;
+    f.last_out = 0;
+    return check_errors(ctx, "balance_multi");
+  }
+  const int rc = balance_map_leaves(f, mp, words, wrank, root_flag.get(), range);
+  if (rc) return rc;
+  return check_errors(ctx, "balance_multi");
+}
+
 inline int balance_multi(Forest &f, int balance_corner) {
   Ctx &ctx = *f.ctx;
   Comm &comm = *forest_comm(f);
@@ -287,6 +418,17 @@ inline int balance_multi(Forest &f, int balance_corner) {
   if (D == 0) {
     f.last_out = f.n;
     return 0;
+  }
+  {
+    const char *mode = getenv("TMR_B200_BALANCE");
+    if (!(mode && strcmp(mode, "sort") == 0)) {
+      const int rc = balance_multi_map(f, balance_corner);
+      if (getenv("TMR_B200_NODES_VERBOSE")) {
+        fprintf(stderr, "[tmr_b200] balance (rank %d): %s\n", me,
+                rc >= 0 ? "cell bitmaps" : "sorted-array closure");
+      }
+      if (rc >= 0) return rc;
+    }
   }
   const int bbits = f.bbits, nb = f.nblocks;
   DBuf<u64> own_store;

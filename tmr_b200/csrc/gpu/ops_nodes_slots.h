@@ -50,21 +50,6 @@ static const u64 kLocB = ~0ULL;        /* outside this rank's Morton range */
 static const u64 kLocFail = ~0ULL - 1; /* not nameable: general path */
 static const u32 kConnB = 0xffffffffu; /* conn entry filled by the B pass */
 
-TMR_HD int ctz64(u64 v) {
-#if defined(__CUDA_ARCH__)
-  return __ffsll((long long)v) - 1;
-#else
-  return __builtin_ctzll(v);
-#endif
-}
-TMR_HD int ctz32(u32 v) {
-#if defined(__CUDA_ARCH__)
-  return __ffs((int)v) - 1;
-#else
-  return __builtin_ctz(v);
-#endif
-}
-
 TMR_HD int slot_ord(int c6) { return popc64(kSlotValid & ((1ULL << c6) - 1)); }
 /* ordinal -> code: the 27 valid codes, one byte each, 8 per word */
 TMR_HD int slot_code(int ord) {

@@ -75,37 +75,57 @@ struct DestKeyFn {
   }
 };
 
+/* bounds[r] = first item for rank r (r = 0..R), counts[r] = items for rank r;
+   the buffer is laid out [bounds R+1 | counts R | all ranks' counts R*R] */
 struct DestBoundsFn {
   const u64 *dk;
   i64 n;
-  i64 *bounds;
-  TMR_HD void operator()(i64 r) const { bounds[r] = lower_bound_u64(dk, n, (u64)r); }
+  int R;
+  i64 *buf;
+  TMR_HD void operator()(i64 r) const {
+    const i64 lo = n > 0 ? lower_bound_u64(dk, n, (u64)r) : 0;
+    buf[r] = lo;
+    if (r < R) {
+      const i64 hi = n > 0 ? lower_bound_u64(dk, n, (u64)(r + 1)) : 0;
+      buf[R + 1 + r] = hi - lo;
+    }
+  }
 };
 
-/* group items by destination rank and agree on the all-to-all-v layout */
+/* group items by destination rank and agree on the all-to-all-v layout.  The
+   per-destination counts never visit the host on their way to the other
+   ranks: bounds kernel -> ncclAllGather (device to device) -> one read-back
+   of bounds and everybody's counts together (was: three blocking round
+   trips per route) */
 template <class DestFn>
 void make_route(Ctx &ctx, Comm &comm, i64 n, DestFn dest, RoutePlan &plan) {
   const int R = comm.size;
   plan.idx.alloc(ctx, n);
   plan.send_off.assign(R + 1, 0);
   plan.recv_off.assign(R + 1, 0);
+  DBuf<u64> dk, dk_alt;
   if (n > 0) {
-    DBuf<u64> dk(ctx, n), dk_alt(ctx, n);
+    dk.alloc(ctx, n);
+    dk_alt.alloc(ctx, n);
     DBuf<u32> idx_alt(ctx, n);
     DestKeyFn<DestFn> k = {dest, dk.get(), plan.idx.get()};
     launch(ctx, n, k, "route_dest");
     int bits = 1;
     while ((1 << bits) < R) bits++;
     radix_sort(ctx, dk, dk_alt, plan.idx, idx_alt, n, 0, bits);
-    DBuf<i64> d_bounds(ctx, R + 1);
-    DestBoundsFn b = {dk.get(), n, d_bounds.get()};
-    launch(ctx, R + 1, b, "route_bounds");
-    copy_d2h(ctx, plan.send_off.data(), d_bounds.get(), (size_t)(R + 1) * sizeof(i64));
   }
-  std::vector<i64> sc(R), rc(R);
-  for (int r = 0; r < R; r++) sc[r] = plan.send_off[r + 1] - plan.send_off[r];
-  exchange_counts(ctx, comm, sc.data(), rc.data());
-  for (int r = 0; r < R; r++) plan.recv_off[r + 1] = plan.recv_off[r] + rc[r];
+  const i64 words = (R + 1) + R + (i64)R * R;
+  DBuf<i64> d_buf(ctx, words);
+  DestBoundsFn b = {dk.get(), n, R, d_buf.get()};
+  launch(ctx, R + 1, b, "route_bounds");
+  comm.allgather_dev(ctx, d_buf.get() + (R + 1), d_buf.get() + (2 * R + 1),
+                     (size_t)R * sizeof(i64));
+  std::vector<i64> h(words);
+  copy_d2h(ctx, h.data(), d_buf.get(), (size_t)words * sizeof(i64));
+  for (int r = 0; r <= R; r++) plan.send_off[r] = h[r];
+  for (int r = 0; r < R; r++) {
+    plan.recv_off[r + 1] = plan.recv_off[r] + h[(2 * R + 1) + (size_t)r * R + comm.rank];
+  }
   plan.nsend = n;
   plan.nrecv = plan.recv_off[R];
 }

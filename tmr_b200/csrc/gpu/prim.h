@@ -39,6 +39,7 @@ struct Ctx {
   int profile;  /* time every named launch with events */
   int num_sms;
   long launch_count; /* kernels launched since the last reset */
+  long sync_count;   /* blocking host<->device round trips since the last reset */
   std::map<std::string, KernelStat> stats;
   /* pending (start, stop) event pairs, resolved lazily at the next sync */
   std::vector<void *> ev_start, ev_stop;
@@ -50,7 +51,7 @@ struct Ctx {
   Ctx()
       : device(0), comm(NULL), stream(NULL), copy_stream(NULL), profile(0),
         num_sms(148),
-        launch_count(0), fail_alloc_in(0), trace(0), trace_t0(0.0) {}
+        launch_count(0), sync_count(0), fail_alloc_in(0), trace(0), trace_t0(0.0) {}
 };
 
 /* --- runtime (prim_cuda.cu / tests/emu/prim_emu.cpp) ---------------------- */

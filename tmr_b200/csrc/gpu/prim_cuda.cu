@@ -166,6 +166,7 @@ void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
   /* the source may be pageable/stack memory: make the copy complete before
      the caller can reuse it */
   TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+  ctx.sync_count++;
 }
 
 void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes) {
@@ -173,6 +174,7 @@ void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes) {
   TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost,
                               (cudaStream_t)ctx.stream));
   TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+  ctx.sync_count++;
 }
 
 void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes) {
@@ -218,10 +220,12 @@ void dev_fill_ff(Ctx &ctx, void *p, size_t bytes) {
 
 void stream_sync(Ctx &ctx) {
   TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+  ctx.sync_count++;
 }
 
 int check_errors(Ctx &ctx, const char *where) {
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)ctx.stream);
+  ctx.sync_count++;
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     fprintf(stderr, "TMROctForest Error: CUDA failure in %s: %s\n", where,

@@ -56,6 +56,7 @@ int tmrgpu_profile_reset(tmrgpu_ctx *ctx) {
   prof_resolve(ctx->c);
   ctx->c.stats.clear();
   ctx->c.launch_count = 0;
+  ctx->c.sync_count = 0;
   return 0;
 }
 
@@ -83,6 +84,7 @@ int tmrgpu_profile_json(tmrgpu_ctx *ctx, char *buf, int buflen) {
 }
 
 long tmrgpu_launch_count(tmrgpu_ctx *ctx) { return ctx->c.launch_count; }
+long tmrgpu_sync_count(tmrgpu_ctx *ctx) { return ctx->c.sync_count; }
 
 int tmrgpu_comm_unique_id(void *out, int out_bytes) {
   return comm_unique_id(out, out_bytes);
