@@ -46,12 +46,14 @@ struct Ctx {
   std::vector<std::string> ev_name;
   std::string last_error;
   long fail_alloc_in; /* fault injection for tests: the n-th next dev_alloc fails (0 = off) */
+  FILE *launch_log; /* TMR_B200_LAUNCH_LOG=<file>: "<launch index> <name>" per profiled bracket */
   int trace;        /* TMR_B200_TRACE=1: print synchronised phase times */
   double trace_t0;  /* wall clock of the previous mark (s) */
   Ctx()
       : device(0), comm(NULL), stream(NULL), copy_stream(NULL), profile(0),
         num_sms(148),
-        launch_count(0), sync_count(0), fail_alloc_in(0), trace(0), trace_t0(0.0) {}
+        launch_count(0), sync_count(0), fail_alloc_in(0), launch_log(NULL), trace(0),
+        trace_t0(0.0) {}
 };
 
 /* --- runtime (prim_cuda.cu / tests/emu/prim_emu.cpp) ---------------------- */

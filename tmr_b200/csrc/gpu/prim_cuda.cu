@@ -247,6 +247,7 @@ int check_errors(Ctx &ctx, const char *where) {
 
 void prof_begin(Ctx &ctx, const char *name) {
   if (!ctx.profile) return;
+  if (ctx.launch_log) fprintf(ctx.launch_log, "%ld %s\n", ctx.launch_count, name);
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);

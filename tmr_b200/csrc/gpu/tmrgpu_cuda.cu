@@ -48,6 +48,7 @@ int tmrgpu_ctx_create(int device, void *stream, tmrgpu_ctx **out) {
     c->c.num_sms = prop.multiProcessorCount;
   }
   c->c.trace = getenv("TMR_B200_TRACE") ? atoi(getenv("TMR_B200_TRACE")) : 0;
+  if (getenv("TMR_B200_LAUNCH_LOG")) c->c.launch_log = fopen(getenv("TMR_B200_LAUNCH_LOG"), "w");
   *out = c;
   return 0;
 }
@@ -57,6 +58,7 @@ int tmrgpu_ctx_destroy(tmrgpu_ctx *ctx) {
   prof_resolve(ctx->c);
   cudaStreamSynchronize((cudaStream_t)ctx->c.stream);
   dev_cache_destroy(ctx->c);
+  if (ctx->c.launch_log) fclose(ctx->c.launch_log);
   if (ctx->own_stream) cudaStreamDestroy((cudaStream_t)ctx->c.stream);
   delete ctx;
   return 0;
