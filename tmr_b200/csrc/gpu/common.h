@@ -30,6 +30,8 @@
 #define TMR_ATOMIC_MAX_I32(p, v) atomicMax((int *)(p), (int)(v))
 #define TMR_ATOMIC_MIN_I32(p, v) atomicMin((int *)(p), (int)(v))
 #define TMR_ATOMIC_OR_I32(p, v) atomicOr((int *)(p), (int)(v))
+#define TMR_ATOMIC_OR_U64(p, v) \
+  atomicOr((unsigned long long *)(p), (unsigned long long)(v))
 #define TMR_ATOMIC_MAX_U64(p, v) \
   atomicMax((unsigned long long *)(p), (unsigned long long)(v))
 #define TMR_ATOMIC_MIN_U64(p, v) \
@@ -46,6 +48,10 @@
     if (*(p) > (v)) *(p) = (v);  \
   } while (0)
 #define TMR_ATOMIC_OR_I32(p, v) \
+  do {                          \
+    *(p) |= (v);                \
+  } while (0)
+#define TMR_ATOMIC_OR_U64(p, v) \
   do {                          \
     *(p) |= (v);                \
   } while (0)

@@ -97,6 +97,9 @@ struct ElemView {
   OwnerMap om;
   int me;
   int multi;
+  /* trees strictly between these two lie entirely in this rank's range: a
+     probe inside such a tree can never be another rank's leaf */
+  i32 own_tree_lo, own_tree_hi;
   u64 *fq_key;
   u32 *fq_dest;
   u64 *fq_code;
@@ -331,7 +334,7 @@ struct HangingFn {
         const u64 idx = ev.map.index(block, cell[q], pl);
         if ((word[q] >> (idx & 31)) & 1u) {
           bits |= 1 << q;
-        } else if (ev.multi) {
+        } else if (ev.multi && !(block > ev.own_tree_lo && block < ev.own_tree_hi)) {
           /* only a miss can be another rank's leaf */
           ev.ask_owner(((u64)(u32)block << (3 * D + 5)) |
                            (cell[q] << (3 * (D - pl) + 5)) | (u64)pl,
@@ -1911,13 +1914,17 @@ struct BUniqueFn {
   const u32 *pay;
   u64 *ukeys;
   unsigned char *ucreated;
+  unsigned char *udep; /* some element labels the node dependent */
   u32 *run_of;
   TMR_HD void operator()(i64 i, u32 heads_before) const {
     const bool head = (i == 0 || k[i] != k[i - 1]);
     const u32 run = heads_before + (head ? 1u : 0u) - 1u;
     if (head) ukeys[run] = k[i];
     run_of[i] = run;
-    if (pay[i] != kConnB) ucreated[run] = 1;
+    if (pay[i] != kConnB) {
+      ucreated[run] = 1;
+      if (pay[i] & kPayDep) udep[run] = 1;
+    }
   }
 };
 struct BLowCountFn {
@@ -1928,88 +1935,100 @@ struct BLowCountFn {
   TMR_HD void operator()(i64) const { out[0] = lower_bound_u64(ukeys, n, first_key); }
 };
 /* B nodes below the rank's range keep their run index, the others follow the
-   NA slot nodes */
+   NA slot nodes; their connectivity entries get the final numbers */
 struct BPlaceFn {
   const u64 *k;
   const u32 *pay;
   const u32 *run_of;
-  const unsigned char *ucreated;
+  const int *unum; /* number of every unique B node */
   i64 nlow, NA;
   u64 *node_keys;
-  unsigned char *created;
+  int *node_num;
   int *conn;
   TMR_HD void operator()(i64 i) const {
     const i64 run = (i64)run_of[i];
     const i64 idx = run < nlow ? run : run + NA;
     if (i == 0 || k[i] != k[i - 1]) {
       node_keys[idx] = k[i];
-      created[idx] = ucreated[run];
+      node_num[idx] = unum[run];
     }
-    if (pay[i] != kConnB) conn[pay[i]] = (int)idx;
+    if (pay[i] != kConnB) conn[pay[i] & ~kPayDep] = unum[run];
   }
 };
+struct OwnerFromReplyFn {
+  const int *got;
+  int *owner;
+  TMR_HD void operator()(i64 r) const { owner[r] = got[r] == 0x7fffffff ? -1 : got[r]; }
+};
+struct BHomeDestFn {
+  NodeHomeFn home;
+  TMR_HD int operator()(i64 r) const { return home(r); }
+};
 
-/* 1 = done; 0 = the forest needs the general candidate sort; < 0 error.
-   Several ranks: nodes, connectivity as LOCAL indices and `created` are built,
-   numbering follows in create_nodes.  One rank: dependent nodes are labelled
-   in slot space and the connectivity comes out as final node NUMBERS
-   (node_num, num_dep_nodes filled too): *numbered = 1. */
+/* 1 = done; 0 = the forest needs the general candidate sort (agreed on by
+   all ranks); < 0 error.  Dependent nodes are labelled in slot space and the
+   connectivity comes out as final node NUMBERS (node_keys, node_num, the
+   counts and node_range of `nd` are filled too).  Several ranks: `om_n` maps
+   node positions to their home rank. */
 inline int build_nodes_slots(Forest &f, NodeData &nd,
                              const unsigned char *fmask, u64 k_first, u64 k_last,
-                             DBuf<unsigned char> &created, i64 *Nn_out,
-                             int *numbered) {
+                             const OwnerMap &om_n, i64 *Nn_out) {
   Ctx &ctx = *f.ctx;
   Comm *comm = forest_comm(f);
+  const int me = comm ? comm->rank : 0;
   const i64 E = f.n;
   const int D = f.fmt.D;
-  *numbered = 0;
-  DBuf<u32> mask(ctx, E), cmask, dmask;
-  dev_zero(ctx, mask.get(), (size_t)E * sizeof(u32));
+  DBuf<u32> mask, dmask(ctx, E);
+  DBuf<u64> mc;
+  dev_zero(ctx, dmask.get(), (size_t)E * sizeof(u32));
   if (comm) {
-    cmask.alloc(ctx, E);
-    dev_zero(ctx, cmask.get(), (size_t)E * sizeof(u32));
+    mc.alloc(ctx, E);
+    dev_zero(ctx, mc.get(), (size_t)E * sizeof(u64));
   } else {
-    dmask.alloc(ctx, E);
-    dev_zero(ctx, dmask.get(), (size_t)E * sizeof(u32));
+    mask.alloc(ctx, E);
+    dev_zero(ctx, mask.get(), (size_t)E * sizeof(u32));
   }
   DBuf<unsigned long long> ctl(ctx, 2); /* [0] B count, [1] fail flag */
   DBuf<unsigned char> slot8(ctx, E * 8);
-  DBuf<unsigned char> dep_table;
-  if (!comm) {
-    dep_table.alloc(ctx, 512);
-    DepTableFn dt = {dep_table.get()};
-    launch(ctx, 512, dt, "nodes_dep_table");
-  }
+  DBuf<unsigned char> dep_table(ctx, 512);
+  DepTableFn dt = {dep_table.get()};
+  launch(ctx, 512, dt, "nodes_dep_table");
   /* this rank's range of positions and the rank index over it */
-  const u64 pos_lo = k_first >> 5;
-  const u64 pos_hi = (k_last >> 5) + (1ULL << (3 * (D - (int)(k_last & 31))));
+  const u64 pos_lo = E > 0 ? (k_first >> 5) : 0ULL;
+  const u64 pos_hi =
+      E > 0 ? (k_last >> 5) + (1ULL << (3 * (D - (int)(k_last & 31)))) : 0ULL;
   DBuf<RankEntry> rank_tab;
   DBuf<u32> rank_cells;
   size_t ix_budget = (size_t)8 * (size_t)E > ((size_t)64 << 20)
                          ? (size_t)8 * (size_t)E
                          : ((size_t)64 << 20);
   if (const char *ev = getenv("TMR_B200_RANK_BUDGET")) ix_budget = (size_t)atol(ev);
-  const RankIndex elem_ix = build_rank_index(ctx, f.keys.get(), E, D, pos_lo, pos_hi,
-                                             ix_budget, rank_tab, rank_cells);
+  RankIndex elem_ix = {NULL, NULL, 0, 0};
+  if (E > 0) {
+    elem_ix = build_rank_index(ctx, f.keys.get(), E, D, pos_lo, pos_hi, ix_budget,
+                               rank_tab, rank_cells);
+  }
   DBuf<u64> b_key;
   DBuf<u32> b_pay;
   i64 cap = comm ? (E / 2 + 65536) : 0, nb = 0;
   unsigned long long h_ctl[2] = {0, 0};
+  SlotView v = {f.keys.get(), E, f.fmt, f.tables, elem_ix, comm ? 1 : 0, pos_lo,
+                pos_hi, mask.get(), mc.get(), dmask.get(), NULL};
   for (int attempt = 0; attempt < 2; attempt++) {
     if (comm) {
       b_key.alloc(ctx, cap);
       b_pay.alloc(ctx, cap);
     }
     dev_zero(ctx, ctl.get(), 2 * sizeof(unsigned long long));
-    SlotView v = {f.keys.get(), E, f.fmt, f.tables, elem_ix, comm ? 1 : 0, pos_lo,
-                  pos_hi, mask.get(), cmask.get(), dmask.get(),
-                  reinterpret_cast<int *>(ctl.get() + 1)};
-    if (3 * D <= 30) {
-      launch_slot_locate<u32>(ctx, f, nd, v, slot8.get(), dep_table.get(), b_key.get(),
-                              b_pay.get(), ctl.get(), cap, fmask);
-    } else {
-      launch_slot_locate<u64>(ctx, f, nd, v, slot8.get(), dep_table.get(), b_key.get(),
-                              b_pay.get(), ctl.get(), cap, fmask);
+    v.fail = reinterpret_cast<int *>(ctl.get() + 1);
+    if (E > 0) {
+      if (3 * D <= 30) {
+        launch_slot_locate<u32>(ctx, f, nd, v, slot8.get(), dep_table.get(),
+                                b_key.get(), b_pay.get(), ctl.get(), cap, fmask);
+      } else {
+        launch_slot_locate<u64>(ctx, f, nd, v, slot8.get(), dep_table.get(),
+                                b_key.get(), b_pay.get(), ctl.get(), cap, fmask);
+      }
     }
     if (!comm) break;
     copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
@@ -2036,16 +2055,23 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     launch(ctx, E, rs, "nodes_slot_resolve");
     nd.num_candidates = 0;
     nd.num_dep_nodes = Nd;
+    nd.num_owned_nodes = Nn - Nd;
+    nd.node_range_start = 0;
+    nd.node_range.assign(2, 0);
+    nd.node_range[1] = (int)(Nn - Nd);
     *Nn_out = Nn;
-    *numbered = 1;
     return 1;
   }
+  /* ---- several ranks.  Every rank takes the same path from here on: the
+     exchanges below are collective ---- */
+  if (global_max(ctx, *comm, h_ctl[1] ? 1 : 0)) return 0;
+  const int R = comm->size;
   /* B nodes: sort, unique */
   i64 nbu = 0, nlow = 0;
   DBuf<u64> b_ukeys;
-  DBuf<unsigned char> b_ucreated;
+  DBuf<unsigned char> b_ucreated, b_udep;
   DBuf<u32> b_run;
-  if (!h_ctl[1] && nb > 0) {
+  if (nb > 0) {
     DBuf<u64> k_alt(ctx, nb);
     DBuf<u32> p_alt(ctx, nb);
     b_key.set_size(nb);
@@ -2053,11 +2079,13 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     radix_sort(ctx, b_key, k_alt, b_pay, p_alt, nb, 0, nd.nfmt.total_bits(), "nodes_b");
     b_ukeys.alloc(ctx, nb);
     b_ucreated.alloc(ctx, nb);
+    b_udep.alloc(ctx, nb);
     b_run.alloc(ctx, nb);
     dev_zero(ctx, b_ucreated.get(), (size_t)nb);
+    dev_zero(ctx, b_udep.get(), (size_t)nb);
     RunHeadFn rh = {b_key.get()};
     BUniqueFn bu = {b_key.get(), b_pay.get(), b_ukeys.get(), b_ucreated.get(),
-                    b_run.get()};
+                    b_udep.get(), b_run.get()};
     nbu = (i64)scan_apply(ctx, nb, rh, bu, "nodes_b_unique");
     if (E > 0) {
       DBuf<i64> d_low(ctx, 1);
@@ -2066,28 +2094,147 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
       copy_d2h(ctx, &nlow, d_low.get(), sizeof(i64));
     }
   }
-  /* slot nodes: scan of the occupied slots */
-  DBuf<u64> slotinfo(ctx, E);
-  SlotCountFn sc = {mask.get()};
-  SlotInfoFn si = {mask.get(), slotinfo.get()};
-  const i64 NA = (i64)scan_apply(ctx, E, sc, si, "nodes_slot_scan");
-  if (h_ctl[1]) return 0;
+  /* first scan: position of every leaf's nodes in node order */
+  DBuf<u64> slotinfo1(ctx, E);
+  SlotCountMFn sc1 = {mc.get()};
+  SlotInfoMFn si1 = {mc.get(), slotinfo1.get()};
+  const i64 NA = (i64)scan_apply(ctx, E, sc1, si1, "nodes_slot_scan");
   const i64 Nn = NA + nbu;
   if (Nn >= (1LL << 31)) {
     fprintf(stderr, "TMROctForest Error: too many local nodes\n");
     return -1;
   }
+  /* ---- ownership: the B nodes go to their home ranks (reference :4538-4637) ---- */
+  DBuf<u32> lowmask(ctx, E);
+  dev_zero(ctx, lowmask.get(), (size_t)E * sizeof(u32));
+  DBuf<int> b_owner(ctx, nbu);
+  DBuf<u64> xref, xref_alt;
+  DBuf<u32> xdest, xdest_alt;
+  i64 nx = 0;
+  {
+    NodeHomeFn home = {b_ukeys.get(), nd.nfmt.Dn, nd.nfmt.lbits, om_n};
+    BHomeDestFn hdest = {home};
+    RoutePlan plan;
+    make_route(ctx, *comm, nbu, hdest, plan);
+    DBuf<u64> rk;
+    DBuf<unsigned char> rc;
+    route_array(ctx, *comm, plan, b_ukeys.get(), rk);
+    route_array(ctx, *comm, plan, b_ucreated.get(), rc);
+    const i64 nr = plan.nrecv;
+    DBuf<int> reply(ctx, nr);
+    DBuf<unsigned long long> xcount(ctx, 1);
+    dev_zero(ctx, xcount.get(), sizeof(unsigned long long));
+    xref.alloc(ctx, nr);
+    xdest.alloc(ctx, nr);
+    if (nr > 0) {
+      DBuf<i64> d_roff(ctx, R + 1);
+      copy_h2d(ctx, d_roff.get(), plan.recv_off.data(), (size_t)(R + 1) * sizeof(i64));
+      DBuf<u32> val(ctx, nr), idx(ctx, nr), idx_alt(ctx, nr);
+      DonorValueFn dv = {rc.get(), d_roff.get(), R, val.get(), idx.get()};
+      launch(ctx, nr, dv, "nodes_donor_value");
+      DBuf<u64> rk_alt(ctx, nr);
+      radix_sort(ctx, rk, rk_alt, idx, idx_alt, nr, 0, nd.nfmt.total_bits());
+      DBuf<int> owner_run(ctx, nr);
+      FillIntFn fi2 = {owner_run.get(), 0x7fffffff};
+      launch(ctx, nr, fi2, "nodes_owner_run_init");
+      DBuf<u32> run_of(ctx, nr);
+      RunHeadFn rh = {rk.get()};
+      OwnerMinFn omin = {rk.get(), idx.get(), val.get(), owner_run.get(), run_of.get()};
+      scan_apply(ctx, nr, rh, omin, "nodes_owner_min");
+      HomeSlotFn hs = {v,          rk.get(),    idx.get(),   run_of.get(), owner_run.get(),
+                       me,         lowmask.get(), xref.get(), xdest.get(), xcount.get(),
+                       reply.get()};
+      launch(ctx, nr, hs, "nodes_owner_home");
+      unsigned long long h_nx = 0;
+      copy_d2h(ctx, &h_nx, xcount.get(), sizeof(h_nx));
+      nx = (i64)h_nx;
+    }
+    DBuf<int> got;
+    route_back(ctx, *comm, plan, reply.get(), got);
+    OwnerFromReplyFn fr = {got.get(), b_owner.get()};
+    launch(ctx, nbu, fr, "nodes_owner_store");
+  }
+  /* second scan: dependents and owned independents per leaf */
+  DBuf<SlotInfoM> slotinfo(ctx, E);
+  SlotCount3Fn sc3 = {mc.get(), dmask.get(), lowmask.get()};
+  SlotInfo3Fn si3 = {sc3, slotinfo.get()};
+  const u64 tot3 = scan_apply(ctx, E, sc3, si3, "nodes_slot_scan2");
+  const i64 dep_slots = (i64)(tot3 & 0x7fffffffULL), own_slots = (i64)(tot3 >> 31);
+  /* the same two counts over the B nodes */
+  DBuf<u64> b_before(ctx, nbu + 1);
+  BCountFn bc = {b_udep.get(), b_owner.get(), me};
+  BStoreFn bs = {b_before.get()};
+  const u64 totb = scan_apply(ctx, nbu, bc, bs, "nodes_b_scan");
+  u64 lowb = 0;
+  if (nlow >= nbu) {
+    lowb = totb;
+  } else {
+    copy_d2h(ctx, &lowb, b_before.get() + nlow, sizeof(u64));
+  }
+  const i64 Nd = dep_slots + (i64)(totb & 0x7fffffffULL);
+  const i64 nown = own_slots + (i64)(totb >> 31);
+  std::vector<i64> all(R);
+  comm->allgather_host(ctx, &nown, all.data(), sizeof(i64));
+  i64 start = 0;
+  for (int r = 0; r < me; r++) start += all[r];
+  /* reference node_range (:4165-4172): kept so that the getters stay local */
+  nd.node_range.assign(R + 1, 0);
+  for (int r = 0; r < R; r++) nd.node_range[r + 1] = nd.node_range[r] + (int)all[r];
+  nd.num_owned_nodes = nown;
+  nd.node_range_start = (int)start;
+  nd.num_dep_nodes = Nd;
+  BNumbers bn = {b_before.get(), b_udep.get(), b_owner.get(), nlow, me, (int)start,
+                 (int)dep_slots, (int)own_slots};
+  DBuf<int> b_num(ctx, nbu);
+  BNumberFn bnf = {bn, b_num.get()};
+  launch(ctx, nbu, bnf, "nodes_b_number");
+  /* ---- numbers of the nodes owned elsewhere (reference :4183-4235) ---- */
+  if (nx > 1) {
+    xref.set_size(nx);
+    xdest.set_size(nx);
+    xref_alt.alloc(ctx, nx);
+    xdest_alt.alloc(ctx, nx);
+    radix_sort(ctx, xref, xref_alt, xdest, xdest_alt, nx, 0, 37);
+  }
+  DBuf<int> xnum(ctx, nx);
+  SlotNumbers sn = {slotinfo.get(), xref.get(), xnum.get(), nx,
+                    (int)(lowb & 0x7fffffffULL), (int)start + (int)(lowb >> 31)};
+  {
+    DBuf<u64> qk(ctx, nx + nbu);
+    DBuf<u32> qd(ctx, nx + nbu), qn(ctx, nbu);
+    XrefKeyFn xk = {f.keys.get(), D, xref.get(), qk.get()};
+    launch(ctx, nx, xk, "nodes_external_keys");
+    if (nx > 0) copy_d2d(ctx, qd.get(), xdest.get(), (size_t)nx * sizeof(u32));
+    BExternalCountFn xc = {b_udep.get(), b_owner.get(), me};
+    BExternalFillFn xf = {xc, b_ukeys.get(), qk.get() + nx, qd.get() + nx, qn.get()};
+    const i64 nxb = (i64)scan_apply(ctx, nbu, xc, xf, "nodes_external_list");
+    U32DestFn xdest_fn = {qd.get()};
+    RoutePlan plan;
+    make_route(ctx, *comm, nx + nxb, xdest_fn, plan);
+    DBuf<u64> req;
+    route_array(ctx, *comm, plan, qk.get(), req);
+    DBuf<int> rep(ctx, plan.nrecv);
+    SlotNumbers sn_own = sn;
+    sn_own.nx = 0; /* a node asked for here is owned here: never external */
+    LookupSlotNumberFn lk = {req.get(), v, sn_own, b_ukeys.get(), nbu, bn, rep.get()};
+    launch(ctx, plan.nrecv, lk, "nodes_external_lookup");
+    DBuf<int> got;
+    route_back(ctx, *comm, plan, rep.get(), got);
+    if (nx > 0) copy_d2d(ctx, xnum.get(), got.get(), (size_t)nx * sizeof(int));
+    StoreBExternalFn se = {qn.get(), got.get() + nx, b_num.get()};
+    launch(ctx, nxb, se, "nodes_external_store");
+  }
+  /* ---- node keys, numbers, connectivity ---- */
   nd.node_keys.alloc(ctx, Nn);
-  created.alloc(ctx, Nn);
-  SlotKeysFn kf = {f.keys.get(), f.fmt,         slotinfo.get(), cmask.get(),
-                   nd.node_keys.get(), created.get(), nlow};
+  nd.node_num.alloc(ctx, Nn);
+  SlotKeys3Fn kf = {f.keys.get(), f.fmt, slotinfo1.get(), sn, nd.node_keys.get(),
+                    nd.node_num.get(), nlow};
   launch(ctx, E, kf, "nodes_slot_keys");
-  SlotResolveFn rs = {slotinfo.get(), slot8.get(),
-                      reinterpret_cast<u32 *>(nd.conn.get()), (u32)nlow};
+  SlotResolve3Fn rs = {sn, slot8.get(), reinterpret_cast<u32 *>(nd.conn.get())};
   launch(ctx, E, rs, "nodes_slot_resolve");
   if (nb > 0) {
-    BPlaceFn bp = {b_key.get(), b_pay.get(), b_run.get(), b_ucreated.get(), nlow, NA,
-                   nd.node_keys.get(), created.get(), nd.conn.get()};
+    BPlaceFn bp = {b_key.get(), b_pay.get(), b_run.get(), b_num.get(), nlow, NA,
+                   nd.node_keys.get(), nd.node_num.get(), nd.conn.get()};
     launch(ctx, nb, bp, "nodes_b_place");
   }
   nd.num_candidates = nb;
@@ -2226,6 +2373,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       ElemView ev = {f.keys.get(), E,           f.fmt,         f.tables,
                      elem_ix,      lmap,        om,            me,
                      comm ? 1 : 0,
+                     E > 0 ? (i32)(k_first >> (3 * f.fmt.D + 5)) : 0,
+                     E > 0 ? (i32)(k_last >> (3 * f.fmt.D + 5)) : 0,
                      fq_key.get(), fq_dest.get(), fq_code.get(), fq_count.get(),
                      cap};
       HangingFn hang = {ev, info32.get()};
@@ -2271,12 +2420,14 @@ inline int create_nodes(Forest &f, int order, int interp_type,
      (ops_nodes_slots.h); TMR_B200_NODES=sort forces the general path */
   int slots_done = 0, numbered = 0;
   {
+    /* the choice must be the same on every rank (the slot construction has
+       its own exchanges): nothing rank-local enters the condition */
     const char *mode = getenv("TMR_B200_NODES");
-    if (gorder == 2 && !general && nd.nfmt.lbits == 0 && E > 0 &&
+    if (gorder == 2 && !general && nd.nfmt.lbits == 0 && (comm || E > 0) &&
         !(mode && strcmp(mode, "sort") == 0)) {
-      slots_done = build_nodes_slots(f, nd, fmask.get(), k_first, k_last, created,
-                                     &Nn, &numbered);
+      slots_done = build_nodes_slots(f, nd, fmask.get(), k_first, k_last, om_n, &Nn);
       if (slots_done < 0) return 1;
+      numbered = slots_done;
       if (getenv("TMR_B200_NODES_VERBOSE")) {
         fprintf(stderr, "[tmr_b200] createNodes: %s path, %lld elements\n",
                 slots_done ? "slot" : "slot->sort fallback", (long long)E);
@@ -2421,7 +2572,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
      place; only the few whose home is elsewhere travel, and the home matches
      what it receives against its own node array. */
   DBuf<int> owner;
-  if (comm) {
+  if (comm && !numbered) {
     owner.alloc(ctx, Nn);
     NodeHomeFn home = {nd.node_keys.get(), nd.nfmt.Dn, nd.nfmt.lbits, om_n};
     /* foreign-home nodes: (key, created, local index) */
@@ -2507,12 +2658,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
      construction, which numbers in slot space) */
   i64 Nd = nd.num_dep_nodes;
   DBuf<int> dep_node;
-  if (numbered) {
-    nd.num_owned_nodes = Nn - Nd;
-    nd.node_range_start = 0;
-    nd.node_range.assign(2, 0);
-    nd.node_range[1] = (int)(Nn - Nd);
-  } else {
+  if (!numbered) {
   DBuf<unsigned char> dep_flag(ctx, Nn);
   dev_zero(ctx, dep_flag.get(), (size_t)Nn);
   if (order == 2) {

@@ -49,6 +49,7 @@ static const u64 kSlotValid = 0xff5533110f050301ULL; /* codes with l <= h */
 static const u64 kLocB = ~0ULL;        /* outside this rank's Morton range */
 static const u64 kLocFail = ~0ULL - 1; /* not nameable: general path */
 static const u32 kConnB = 0xffffffffu; /* conn entry filled by the B pass */
+static const u32 kPayDep = 0x80000000u; /* B payload: the corner is a dependent node */
 
 TMR_HD int slot_ord(int c6) { return popc64(kSlotValid & ((1ULL << c6) - 1)); }
 /* ordinal -> code: the 27 valid codes, one byte each, 8 per word */
@@ -245,9 +246,11 @@ struct SlotView {
      position outside it belongs to another rank (B list) */
   int multi;
   u64 pos_lo, pos_hi;
-  u32 *mask;  /* per leaf: occupied slots */
-  u32 *cmask; /* several ranks: slots that are a corner of a local element */
-  u32 *dmask; /* one rank: slots that are dependent (hanging) nodes */
+  u32 *mask;  /* one rank, per leaf: occupied slots */
+  /* several ranks: occupied slots (low word) and, in the high word, the slots
+     that are a corner of a LOCAL element -- one 64-bit reduction per mark */
+  u64 *mc;
+  u32 *dmask; /* slots that are dependent (hanging) nodes */
   int *fail;
 
   /* leaf and slot of the canonical position (block, Morton m of the depth-D
@@ -290,13 +293,24 @@ struct SlotView {
                       ((z == kHmax - 1) ? 1 : 0);
     return locate<u64>(block, morton3((u32)x >> s, (u32)y >> s, (u32)z >> s), clamp);
   }
+  /* leaf and slot of a node KEY (NodeFmt at Dn = D, no label bits): the low
+     bit of a squeezed coordinate is set exactly when it is the clamped
+     2^30-1, and halving every coordinate drops the lowest bit triple */
+  TMR_HD u64 locate_key(u64 nkey) const {
+    const int sh = 3 * (fmt.D + 1);
+    const u64 kk = nkey & ((1ULL << sh) - 1);
+    return locate<u64>((i32)(nkey >> sh), kk >> 3, (int)(kk & 7));
+  }
   TMR_HD void mark(u64 v, bool corner) const {
     if (v >= kLocFail) return;
     const i64 leaf = (i64)(v >> 5);
     const u32 bit = 1u << (int)(v & 31);
-    /* fire-and-forget reductions: no load to wait for, no branch */
-    TMR_ATOMIC_OR_I32(&mask[leaf], bit);
-    if (cmask && corner) TMR_ATOMIC_OR_I32(&cmask[leaf], bit);
+    /* fire-and-forget reductions: no load to wait for */
+    if (mc) {
+      TMR_ATOMIC_OR_U64(&mc[leaf], (u64)bit | (corner ? ((u64)bit << 32) : 0ULL));
+    } else {
+      TMR_ATOMIC_OR_I32(&mask[leaf], bit);
+    }
   }
 };
 
@@ -495,6 +509,15 @@ struct NodeSlotFn {
       gy0 = (md >> 1) & 1;
       gx0 = (md >> 2) & 1;
     }
+    /* dependent corners (labelDependentNodes), labelled right here in slot space */
+    int dm = 0;
+    if (v.dmask && info[i]) {
+      const u64 key = v.keys[i];
+      const int L = (int)(key & 31);
+      const int md = L == 0 ? 0 : (int)((key >> (5 + 3 * (v.fmt.D - L))) & 7);
+      const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
+      dm = dep_table[(id << 6) | (info[i] & 63)];
+    }
     u32 leaf[8];
     u64 ords = 0;
     TMR_UNROLL
@@ -509,6 +532,7 @@ struct NodeSlotFn {
       if (val == kLocFail) {
         *v.fail = 1;
         leaf[c] = 0;
+        dm &= ~(1 << c);
       } else if (val == kLocB) {
         i32 b, x, y, z;
         int L;
@@ -518,8 +542,11 @@ struct NodeSlotFn {
         y += ((c >> 1) & 1) * h;
         z += (c >> 2) * h;
         transform_node(v.t, &b, &x, &y, &z, -1, NULL, NULL);
-        append_b(nfmt.encode(b, x, y, z, 0), (u32)(i * 8 + c));
+        /* payload: conn slot, bit 31 = this corner is a dependent node */
+        append_b(nfmt.encode(b, x, y, z, 0),
+                 (u32)(i * 8 + c) | (((dm >> c) & 1) ? kPayDep : 0u));
         leaf[c] = kConnB;
+        dm &= ~(1 << c);
       } else {
         leaf[c] = (u32)(val >> 5);
         ords |= (val & 31) << (8 * c);
@@ -527,13 +554,7 @@ struct NodeSlotFn {
     }
     store8_u32(conn_leaf + i * 8, leaf);
     *reinterpret_cast<u64 *>(slot8 + i * 8) = ords;
-    /* one rank: dependent nodes are labelled right here, in slot space */
-    if (v.dmask && info[i]) {
-      const u64 key = v.keys[i];
-      const int L = (int)(key & 31);
-      const int md = L == 0 ? 0 : (int)((key >> (5 + 3 * (v.fmt.D - L))) & 7);
-      const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
-      const int dm = dep_table[(id << 6) | (info[i] & 63)];
+    if (dm) {
       TMR_UNROLL
       for (int c = 0; c < 8; c++) {
         if ((dm >> c) & 1) {
@@ -563,17 +584,6 @@ struct SlotKeyEmit {
   }
 };
 
-struct SlotCountFn {
-  const u32 *mask;
-  TMR_HD u32 operator()(i64 i) const { return (u32)popc32(mask[i]); }
-};
-struct SlotInfoFn {
-  const u32 *mask;
-  u64 *slotinfo;
-  TMR_HD void operator()(i64 i, u32 off) const {
-    slotinfo[i] = ((u64)off << 32) | (u64)mask[i];
-  }
-};
 
 /* one rank: nodes and dependent nodes counted together, lo | hi << 31 */
 struct SlotInfo2 {
@@ -637,31 +647,6 @@ TMR_HD u64 slot_node_key(u64 key, int D, int c6) {
   return (block << (3 * (D + 1))) | (m << 3) | extra;
 }
 
-/* node keys of every occupied slot, in order (several ranks: + created flags) */
-struct SlotKeysFn {
-  const u64 *keys;
-  KeyFmt fmt;
-  const u64 *slotinfo;
-  const u32 *cmask;
-  u64 *node_keys;
-  unsigned char *created;
-  i64 base; /* index of the first slot node */
-  TMR_HD void operator()(i64 i) const {
-    const u64 si = slotinfo[i];
-    u32 mk = (u32)si;
-    if (!mk) return;
-    const u64 key = keys[i];
-    i64 o = base + (i64)(si >> 32);
-    const u32 cm = cmask ? cmask[i] : 0u;
-    while (mk) {
-      const int ord = ctz32(mk);
-      mk &= mk - 1;
-      node_keys[o] = slot_node_key(key, fmt.D, slot_code(ord));
-      if (created) created[o] = (unsigned char)((cm >> ord) & 1u);
-      o++;
-    }
-  }
-};
 /* one rank: node keys and node numbers */
 struct SlotKeys2Fn {
   const u64 *keys;
@@ -685,26 +670,6 @@ struct SlotKeys2Fn {
   }
 };
 
-/* (leaf, slot) -> local node index, in place */
-struct SlotResolveFn {
-  const u64 *slotinfo;
-  const unsigned char *slot8;
-  u32 *conn;
-  u32 base;
-  TMR_HD void operator()(i64 e) const {
-    u32 leaf[8];
-    load8_u32(conn + e * 8, leaf);
-    const u64 ords = *reinterpret_cast<const u64 *>(slot8 + e * 8);
-    TMR_UNROLL
-    for (int c = 0; c < 8; c++) {
-      if (leaf[c] == kConnB) continue;
-      const u64 si = slotinfo[leaf[c]];
-      const int ord = (int)((ords >> (8 * c)) & 31);
-      leaf[c] = base + (u32)(si >> 32) + (u32)popc32((u32)si & ((1u << ord) - 1u));
-    }
-    store8_u32(conn + e * 8, leaf);
-  }
-};
 /* one rank: (leaf, slot) -> node NUMBER, in place: the connectivity is final
    after this pass (no local-index stage, no renumbering pass) */
 struct SlotResolve2Fn {
@@ -719,6 +684,255 @@ struct SlotResolve2Fn {
     for (int c = 0; c < 8; c++) {
       const SlotInfo2 si = load_slotinfo2(slotinfo + leaf[c]);
       leaf[c] = (u32)slot_node_number(si, (int)((ords >> (8 * c)) & 31));
+    }
+    store8_u32(conn + e * 8, leaf);
+  }
+};
+
+
+/* ---- several ranks: ownership and numbering in slot space ---------------------
+   Every slot node lies in this rank's own Morton range, so this rank is its
+   HOME (the reference distributes the node array by position,
+   src/TMROctForest.cpp:4545): only the B nodes travel for the ownership
+   decision (lowest rank creating the node from an element, :4538-4637), and
+   a slot node is owned here unless a lower rank donated it (lowmask) or no
+   local element creates it (mask & ~cmask).  Those few "external" slot nodes
+   are listed (xref, sorted by leaf and slot) and their numbers fetched from
+   the owners; every other number follows from two prefix counts per leaf. */
+struct SlotInfoM { /* 16 bytes: what a node NUMBER needs */
+  u32 dep_off, dmask, own_off, omask; /* omask: owned independent slots */
+};
+TMR_HD SlotInfoM load_slotinfom(const SlotInfoM *p) {
+#if defined(__CUDA_ARCH__)
+  const uint4 a = *reinterpret_cast<const uint4 *>(p);
+  SlotInfoM si = {a.x, a.y, a.z, a.w};
+  return si;
+#else
+  return *p;
+#endif
+}
+struct SlotNumbers {
+  const SlotInfoM *si;
+  const u64 *xref; /* external slot nodes, (leaf << 5 | slot) ascending */
+  const int *xnum; /* their numbers, from the owners */
+  i64 nx;
+  int dep_base; /* dependent B nodes below the rank's range */
+  int own_base; /* first owned number + owned B nodes below the range */
+  /* number of the node in occupied slot `ord` of `leaf` */
+  TMR_HD int number(const SlotInfoM &s, i64 leaf, int ord) const {
+    const u32 bit = 1u << ord, below = bit - 1u;
+    if (s.dmask & bit) return -(dep_base + (int)s.dep_off + popc32(s.dmask & below)) - 1;
+    if (s.omask & bit) return own_base + (int)s.own_off + popc32(s.omask & below);
+    const i64 j = find_u64(xref, nx, ((u64)leaf << 5) | (u64)ord);
+    return j >= 0 ? xnum[j] : 0;
+  }
+};
+/* first scan: node positions */
+struct SlotCountMFn {
+  const u64 *mc;
+  TMR_HD u32 operator()(i64 i) const { return (u32)popc32((u32)mc[i]); }
+};
+struct SlotInfoMFn {
+  const u64 *mc;
+  u64 *slotinfo;
+  TMR_HD void operator()(i64 i, u32 off) const {
+    slotinfo[i] = ((u64)off << 32) | (u64)(u32)mc[i];
+  }
+};
+/* second scan: dependents and owned independents, lo | hi << 31 */
+struct SlotCount3Fn {
+  const u64 *mc;
+  const u32 *dmask, *lowmask;
+  TMR_HD u32 om(i64 i) const { /* owned independent slots */
+    const u64 m = mc[i];
+    return (u32)m & (u32)(m >> 32) & ~lowmask[i] & ~dmask[i];
+  }
+  TMR_HD u64 operator()(i64 i) const {
+    return (u64)popc32(dmask[i]) | ((u64)popc32(om(i)) << 31);
+  }
+};
+struct SlotInfo3Fn {
+  SlotCount3Fn c;
+  SlotInfoM *out;
+  TMR_HD void operator()(i64 i, u64 off) const {
+    const u32 dep_off = (u32)(off & 0x7fffffffULL), own_off = (u32)(off >> 31);
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4 *>(out + i) = make_uint4(dep_off, c.dmask[i], own_off, c.om(i));
+#else
+    SlotInfoM si = {dep_off, c.dmask[i], own_off, c.om(i)};
+    out[i] = si;
+#endif
+  }
+};
+/* home side of the ownership exchange: the received B nodes of the other
+   ranks (sorted by key, run-wise minimum donor in owner_run) against my
+   slots.  Replies the owner; marks my copy as external when it is not me. */
+struct HomeSlotFn {
+  SlotView v;
+  const u64 *rkeys;
+  const u32 *idx;
+  const u32 *run_of;
+  const int *owner_run;
+  int me;
+  u32 *lowmask;
+  u64 *xref;
+  u32 *xdest;
+  unsigned long long *xcount;
+  int *reply; /* by original received index */
+  TMR_HD void operator()(i64 j) const {
+    int o = owner_run[run_of[j]];
+    const u64 loc = v.locate_key(rkeys[j]);
+    if (loc < kLocFail) {
+      const i64 leaf = (i64)(loc >> 5);
+      const u32 bit = 1u << (int)(loc & 31);
+      const u64 m = v.mc[leaf];
+      if ((u32)m & bit) {
+        if (((u32)(m >> 32) & bit) && me < o) o = me;
+        if (o != me && (j == 0 || rkeys[j - 1] != rkeys[j])) {
+          TMR_ATOMIC_OR_I32(&lowmask[leaf], bit);
+          const unsigned long long q = fetch_add_u64(xcount, 1ULL);
+          xref[q] = loc;
+          xdest[q] = (u32)(o == 0x7fffffff ? me : o);
+        }
+      }
+    }
+    reply[idx[j]] = o;
+  }
+};
+/* request keys of the external slot nodes (xref sorted) */
+struct XrefKeyFn {
+  const u64 *keys;
+  int D;
+  const u64 *xref;
+  u64 *out;
+  TMR_HD void operator()(i64 q) const {
+    out[q] = slot_node_key(keys[xref[q] >> 5], D, slot_code((int)(xref[q] & 31)));
+  }
+};
+/* B nodes: per unique node dependent / owned flags, numbers */
+struct BCountFn {
+  const unsigned char *udep;
+  const int *owner;
+  int me;
+  TMR_HD u64 operator()(i64 r) const {
+    return udep[r] ? 1ULL : ((owner[r] == me) ? (1ULL << 31) : 0ULL);
+  }
+};
+struct BStoreFn {
+  u64 *before;
+  TMR_HD void operator()(i64 r, u64 off) const { before[r] = off; }
+};
+struct BExternalCountFn {
+  const unsigned char *udep;
+  const int *owner;
+  int me;
+  TMR_HD u32 operator()(i64 r) const { return (!udep[r] && owner[r] != me) ? 1u : 0u; }
+};
+struct BExternalFillFn {
+  BExternalCountFn c;
+  const u64 *ukeys;
+  u64 *out_key;
+  u32 *out_dest;
+  u32 *out_node;
+  TMR_HD void operator()(i64 r, u32 o) const {
+    if (c(r)) {
+      out_key[o] = ukeys[r];
+      out_dest[o] = (u32)(c.owner[r] < 0 ? c.me : c.owner[r]);
+      out_node[o] = (u32)r;
+    }
+  }
+};
+/* numbers of the B nodes: [dependents | owned] counted before them in node
+   order = their own prefix, plus everything in the slots for the B nodes that
+   follow the rank's range */
+struct BNumbers {
+  const u64 *before; /* dep | own << 31, exclusive */
+  const unsigned char *udep;
+  const int *owner;
+  i64 nlow;
+  int me;
+  int first_owned;
+  int dep_slots, own_slots; /* totals of the slot nodes */
+  TMR_HD int number(i64 r) const { /* 0 for an external node */
+    const int d = (int)(before[r] & 0x7fffffffULL), o = (int)(before[r] >> 31);
+    if (udep[r]) return -(d + (r < nlow ? 0 : dep_slots)) - 1;
+    if (owner[r] == me) return first_owned + o + (r < nlow ? 0 : own_slots);
+    return 0;
+  }
+};
+struct BNumberFn {
+  BNumbers b;
+  int *num;
+  TMR_HD void operator()(i64 r) const { num[r] = b.number(r); }
+};
+/* owner side of the number exchange */
+struct LookupSlotNumberFn {
+  const u64 *req;
+  SlotView v;
+  SlotNumbers sn;
+  const u64 *b_ukeys;
+  i64 nbu;
+  BNumbers bn;
+  int *reply;
+  TMR_HD void operator()(i64 i) const {
+    const u64 loc = v.locate_key(req[i]);
+    if (loc < kLocFail) {
+      const i64 leaf = (i64)(loc >> 5);
+      const int ord = (int)(loc & 31);
+      const SlotInfoM s = load_slotinfom(sn.si + leaf);
+      /* sn.nx = 0 here: a slot that is neither dependent nor owned answers 0 */
+      reply[i] = !(((u32)v.mc[leaf] >> ord) & 1u) ? -1 : sn.number(s, leaf, ord);
+    } else {
+      const i64 r = find_u64(b_ukeys, nbu, req[i]);
+      reply[i] = r >= 0 ? bn.number(r) : -1;
+    }
+  }
+};
+struct StoreBExternalFn {
+  const u32 *node;
+  const int *number;
+  int *num;
+  TMR_HD void operator()(i64 k) const { num[node[k]] = number[k]; }
+};
+/* node keys and numbers of every occupied slot, in node order */
+struct SlotKeys3Fn {
+  const u64 *keys;
+  KeyFmt fmt;
+  const u64 *slotinfo1; /* first scan: node_off << 32 | mask */
+  SlotNumbers sn;
+  u64 *node_keys;
+  int *node_num;
+  i64 base; /* index of the first slot node */
+  TMR_HD void operator()(i64 i) const {
+    const u64 s1 = slotinfo1[i];
+    u32 mk = (u32)s1;
+    if (!mk) return;
+    const SlotInfoM s = load_slotinfom(sn.si + i);
+    const u64 key = keys[i];
+    i64 o = base + (i64)(s1 >> 32);
+    while (mk) {
+      const int ord = ctz32(mk);
+      mk &= mk - 1;
+      node_keys[o] = slot_node_key(key, fmt.D, slot_code(ord));
+      node_num[o] = sn.number(s, i, ord);
+      o++;
+    }
+  }
+};
+/* (leaf, slot) -> node NUMBER, in place (B corners are placed by BPlace3Fn) */
+struct SlotResolve3Fn {
+  SlotNumbers sn;
+  const unsigned char *slot8;
+  u32 *conn;
+  TMR_HD void operator()(i64 e) const {
+    u32 leaf[8];
+    load8_u32(conn + e * 8, leaf);
+    const u64 ords = *reinterpret_cast<const u64 *>(slot8 + e * 8);
+    TMR_UNROLL
+    for (int c = 0; c < 8; c++) {
+      if (leaf[c] == kConnB) continue;
+      const SlotInfoM s = load_slotinfom(sn.si + leaf[c]);
+      leaf[c] = (u32)sn.number(s, (i64)leaf[c], (int)((ords >> (8 * c)) & 31));
     }
     store8_u32(conn + e * 8, leaf);
   }
