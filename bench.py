@@ -265,7 +265,7 @@ def main():
     torch.cuda.set_device(local)
     from tmr_b200 import dist as tdist
 
-    numa_cpus = tdist.bind_to_gpu_numa(local)  # page-locked mirrors on the GPU's NUMA node
+    numa_cpus = tdist.bind_to_gpu_numa(local, world)  # page-locked mirrors on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     os.environ["TMR_B200_DEVICE"] = str(local)
@@ -441,26 +441,35 @@ def main():
         """device-resident cycle: flags already in HBM"""
         return cycle(base, d_flags, cfg)
 
-    def step_e2e():
+    def step_e2e(marks=None):
         """reference-facing API: host flags in; conn, node numbers and the
         dependent-node CSR out (everything createTACS reads, reference
         src/TMR_TACSCreator.cpp:332-461)"""
+        def mark(name):
+            if marks is not None:
+                marks.append((name, time.perf_counter()))
+        mark("start")
         work = base.duplicate()
         lib.tmrc_refine(work._ptr, h_flags.ctypes.data, 0, 30)  # H2D inside
         lib.tmrc_balance(work._ptr, cfg["corner"])
         if world > 1:
             lib.tmrc_repartition(work._ptr, -1)
+        mark("refine+balance (host returns)")
         lib.tmrc_create_nodes(work._ptr)
+        mark("createNodes (host returns)")
         cptr = ctypes.POINTER(ctypes.c_int)()
         ne, no = ctypes.c_int(0), ctypes.c_int(0)
         lib.tmrc_get_node_conn(work._ptr, ctypes.byref(cptr), ctypes.byref(ne),
                                ctypes.byref(no))
+        mark("getNodeConn")
         p1, p2 = ctypes.POINTER(ctypes.c_int)(), ctypes.POINTER(ctypes.c_int)()
         p3 = ctypes.POINTER(ctypes.c_double)()
         nd_ = lib.tmrc_get_dep_node_conn(work._ptr, ctypes.byref(p1), ctypes.byref(p2),
                                          ctypes.byref(p3))
+        mark("getDepNodeConn")
         p4 = ctypes.POINTER(ctypes.c_int)()
         nn_ = lib.tmrc_get_node_numbers(work._ptr, ctypes.byref(p4))
+        mark("getNodeNumbers")
         # touch the last word of every array: the copies have landed
         probe = 0
         if ne.value:
@@ -585,6 +594,9 @@ def main():
         w = step_e2e()
         del w
     barrier()
+    lib.tmrgpu_bus_bytes.restype = I64
+    lib.tmrgpu_bus_bytes.argtypes = [P, ctypes.c_int]
+    lib.tmrgpu_profile_reset(ctx)  # zero the bus byte counters
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
@@ -594,14 +606,26 @@ def main():
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    bus_d2h = int(lib.tmrgpu_bus_bytes(ctx, 0)) // args.steps
+    bus_h2d = int(lib.tmrgpu_bus_bytes(ctx, 1)) // args.steps
     e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_octants * args.steps / (float(t.item()) * 1e-3)
+    # where one end-to-end step spends its wall time (host clock, rank 0)
+    marks = []
+    w = step_e2e(marks)
+    del w
+    barrier()
+    e2e_breakdown = {marks[k][0]: round(1e3 * (marks[k][1] - marks[k - 1][1]), 2)
+                     for k in range(1, len(marks))}
     lib.tmrgpu_set_node_prefetch(bdev, 0)
     npe = cfg["order"] ** 3
-    d2h = 4 * (sizes[0] * npe + sizes[1] + sizes[2] + 1 + sizes[4]) + 8 * sizes[4]
+    # bytes the host arrays handed out hold (conn, sorted numbers, dependent CSR);
+    # what crossed the bus is counted by the library (dep_ptr / dep_weights travel
+    # as 2-byte stencil codes, one rank's sorted numbers are a range)
+    d2h_arrays = 4 * (sizes[0] * npe + sizes[1] + sizes[2] + 1 + sizes[4]) + 8 * sizes[4]
 
     # ---- roofline of the dominant kernel -------------------------------------------
     peak, peak_src = load_peaks()
@@ -712,8 +736,10 @@ def main():
                        "%d GPUs, one forest SFC-partitioned, NCCL all-to-all-v (%s: %dx%dx%d trees); cycle includes repartition()"
                        % (world, "strong" if args.strong else "weak", cfg["nb"], cfg["nb"], nbz),
                        "l2": "inputs larger than L2 (%.0f MB of keys per pass)" % (8e-6 * e_final)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * e_in),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t.item()) / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bus_h2d,
+                    "d2h_bytes_per_step": bus_d2h, "host_array_bytes_per_step": int(d2h_arrays),
+                    "ms_per_step": float(t.item()) / args.steps,
+                    "host_ms_per_call": e2e_breakdown,
                     "what": "TMROctForest API: refine(host flags) + balance + createNodes + "
                             "getNodeConn + getDepNodeConn + getNodeNumbers; read-back overlapped "
                             "with createNodes on a copy stream"},

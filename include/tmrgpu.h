@@ -43,6 +43,9 @@ long tmrgpu_launch_count(tmrgpu_ctx *ctx);
 /* blocking host<->device round trips (synchronising copies, error sweeps)
    since the last tmrgpu_profile_reset: the control-plane cost of an operation */
 long tmrgpu_sync_count(tmrgpu_ctx *ctx);
+/* bytes copied device->host (h2d = 0) or host->device (1) since the last
+   tmrgpu_profile_reset: what the end-to-end figures of bench.py count */
+int64_t tmrgpu_bus_bytes(tmrgpu_ctx *ctx, int h2d);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------
    (replaces MPI_Comm + the MPI datatypes of reference src/TMRBase.cpp:42-92)

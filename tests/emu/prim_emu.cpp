@@ -16,11 +16,12 @@ void *host_alloc(Ctx &, size_t bytes) { return malloc(bytes ? bytes : 16); }
 void host_free(Ctx &, void *p) { free(p); }
 void copy_h2d(Ctx &, void *d, const void *s, size_t b) { memcpy(d, s, b); }
 void copy_d2h(Ctx &, void *d, const void *s, size_t b) { memcpy(d, s, b); }
-void *copy_d2h_async(Ctx &, void *d, const void *s, size_t b) {
+void *copy_d2h_async(Ctx &, void *d, const void *s, size_t b, int) {
   memcpy(d, s, b);
   return NULL;
 }
 void copy_wait(Ctx &, void *) {}
+void copy_sync(Ctx &, void *) {}
 void copy_d2d(Ctx &, void *d, const void *s, size_t b) { memcpy(d, s, b); }
 void dev_zero(Ctx &, void *p, size_t b) { memset(p, 0, b); }
 void dev_fill_ff(Ctx &, void *p, size_t b) { memset(p, 0xff, b); }

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include <memory>
+#include <thread>
 
 #include "comm.h"
 #include "prim.h"
@@ -38,10 +39,38 @@ static const int kMaxOrder = 16;
 struct HostMirror {
   void *p;
   void *ev; /* pending copy (copy_d2h_async handle) */
-  HostMirror() : p(NULL), ev(NULL) {}
+  void *thread; /* std::thread* filling the array on the host, or NULL */
+  void *aux;    /* page-locked staging the fill reads from, or NULL */
+  HostMirror() : p(NULL), ev(NULL), thread(NULL), aux(NULL) {}
+  void join() {
+    if (thread) {
+      std::thread *t = static_cast<std::thread *>(thread);
+      t->join();
+      delete t;
+      thread = NULL;
+    }
+  }
 };
 enum { kMirrorConn = 0, kMirrorNumbers, kMirrorDepPtr, kMirrorDepConn,
        kMirrorDepWeights, kNumMirrors };
+
+/* dep_ptr and dep_weights reach the host in compact form: one 16-bit stencil
+   code per dependent node (which parent edge / face position it sits on) and
+   the small table of 1-D weight rows the codes index; host threads rebuild
+   the two arrays while the large copies (conn, dep_conn) are still on the
+   bus.  A dependent stencil of an order-p mesh is one of 2 p rows (edge) or
+   the tensor product of two of them (face) -- 12 bytes per entry shrink to 2
+   bytes per NODE.  Code: 0xffff none; edge 0x8000 | bit << 4 | k; face
+   b1 << 9 | i << 5 | b2 << 4 | j. */
+static const unsigned short kDepCodeNone = 0xffff;
+static const unsigned short kDepCodeEdge = 0x8000;
+struct DepExpandJob {
+  void *thread;  /* std::thread* running the expansion, joined by the getters */
+  void *codes;   /* page-locked staging of the codes */
+  double *table; /* page-locked staging of the weight rows */
+  void *ev_codes, *ev_table;
+  DepExpandJob() : thread(NULL), codes(NULL), table(NULL), ev_codes(NULL), ev_table(NULL) {}
+};
 
 struct NodeData {
   bool valid;
@@ -63,22 +92,50 @@ struct NodeData {
   DBuf<int> dep_ptr;    /* [num_dep_nodes + 1] */
   DBuf<int> dep_conn;   /* [dep_nnz] */
   DBuf<double> dep_weights;
+  DBuf<unsigned short> dep_code; /* [num_dep_nodes] stencil codes (DepExpandJob) */
+  DBuf<double> dep_wtab; /* [2 kinds][2 sides][order positions][order] weight rows */
+  DepExpandJob dep_job;
   /* host mirrors; prefetch = bit mask of the arrays whose copy createNodes
      starts on the copy stream as soon as the array is final (bit 0 conn, 1
      sorted node numbers, 2 the dependent CSR) */
   Ctx *mctx;
   HostMirror mirror[kNumMirrors];
   DBuf<int> sorted_numbers; /* device staging of the sorted node numbers */
+  /* several ranks, slot construction: numbers of the nodes owned elsewhere
+     (unsorted).  All other local numbers are two ranges (dependents, owned) */
+  DBuf<int> ext_numbers;
+  bool ext_numbers_valid;
   int prefetch;
   NodeData()
       : valid(false), order(2), interp_type(1), num_elements(0),
         num_local_nodes(0), num_dep_nodes(0), num_owned_nodes(0), dep_nnz(0),
-        num_candidates(0), node_range_start(0), mctx(NULL), prefetch(0) {}
+        num_candidates(0), node_range_start(0), ext_numbers_valid(false), mctx(NULL),
+        prefetch(0) {}
   ~NodeData() { drop_mirrors(); }
+  /* the expansion job writes into the DepPtr / DepWeights mirrors: join it
+     before anything is released */
+  void finish_dep_job() {
+    if (dep_job.thread) {
+      std::thread *t = static_cast<std::thread *>(dep_job.thread);
+      t->join();
+      delete t;
+      dep_job.thread = NULL;
+    }
+    if (dep_job.ev_codes) copy_wait(*mctx, dep_job.ev_codes);
+    if (dep_job.ev_table) copy_wait(*mctx, dep_job.ev_table);
+    dep_job.ev_codes = dep_job.ev_table = NULL;
+    if (dep_job.codes) host_free(*mctx, dep_job.codes);
+    if (dep_job.table) host_free(*mctx, dep_job.table);
+    dep_job.codes = NULL;
+    dep_job.table = NULL;
+  }
   void drop_mirrors() {
+    finish_dep_job();
     for (int k = 0; k < kNumMirrors; k++) {
+      mirror[k].join();
       if (mirror[k].ev) copy_wait(*mctx, mirror[k].ev);
       if (mirror[k].p) host_free(*mctx, mirror[k].p);
+      if (mirror[k].aux) host_free(*mctx, mirror[k].aux);
       mirror[k] = HostMirror();
     }
     sorted_numbers.reset();
@@ -92,6 +149,10 @@ struct NodeData {
     dep_ptr.reset();
     dep_conn.reset();
     dep_weights.reset();
+    dep_code.reset();
+    dep_wtab.reset();
+    ext_numbers.reset();
+    ext_numbers_valid = false;
     node_range.clear();
     num_elements = num_local_nodes = num_dep_nodes = num_owned_nodes = 0;
     dep_nnz = 0;

@@ -25,8 +25,12 @@
 #ifndef TMRGPU_OPS_NODES_H
 #define TMRGPU_OPS_NODES_H
 
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <thread>
+#include <vector>
 
 #include "ops_balance.h"
 #include "ops_route.h"
@@ -1223,6 +1227,30 @@ struct ConnBuildFn {
 };
 
 /* createDependentConn pass 3 (reference :5272-5508) */
+/* rows of the weight table: [kind 0 edge / 1 face][side bit][position k] ->
+   `order` weights, by exactly the expressions DepFillFn evaluates */
+struct DepWeightTableFn {
+  int order;
+  int bernstein;
+  double knots[kMaxOrder];
+  double *table;
+  TMR_HD void operator()(i64 item) const {
+    const int k = (int)(item % order), b = (int)((item / order) & 1),
+              kind = (int)(item / (2 * order));
+    double *row = table + item * order;
+    if (bernstein) {
+      bernstein_subdivision_weights(order, (order - 1) * (b - 1) + k, row);
+    } else if (kind == 0) {
+      const double u = 1.0 * (b - 1) + 0.5 * (1.0 + knots[k]);
+      lagrange_basis(order, u, knots, row);
+    } else {
+      double u = -1.0 + 0.5 * (1.0 + knots[k]);
+      u += 1.0 * b;
+      lagrange_basis(order, u, knots, row);
+    }
+  }
+};
+
 struct DepFillData {
   const u64 *keys;
   KeyFmt fmt;
@@ -1238,8 +1266,7 @@ struct DepFillData {
   const int *dep_ptr;
   int *dep_conn;
   double *dep_weights;
-
-  const int *dep_node; /* dependent index -> node index (search hint) */
+  unsigned short *dep_code; /* compact form of ptr + weights (DepExpandJob) */
 
   KeyIndex node_ix;
   /* order 2 shortcut: in a complete family the parent's corner c is corner c
@@ -1369,6 +1396,7 @@ struct DepFillFn : DepFillData {
     const int order = kOrder ? kOrder : DepFillData::order;
     const bool general = (kOrder == 0) && ent_off != NULL;
     const int ptr = dep_ptr[d];
+    if (!win_edge[d] && !win_face[d]) dep_code[d] = kDepCodeNone;
     if (win_edge[d]) {
       const u64 code = win_edge[d] - 1;
       const int k = (int)(code & 15);
@@ -1407,6 +1435,7 @@ struct DepFillFn : DepFillData {
         dep_conn[ptr + ii] = lookup(block, nx, ny, nz, line_label(ii));
       }
       const int bit = (id >> (ed >> 2)) & 1;
+      dep_code[d] = (unsigned short)(kDepCodeEdge | (bit << 4) | k);
       if (bernstein) {
         /* reference :5364-5374 */
         bernstein_subdivision_weights(order, (order - 1) * (bit - 1) + k,
@@ -1460,6 +1489,7 @@ struct DepFillFn : DepFillData {
       const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
       const int b1 = (f < 2) ? by : bx;
       const int b2 = (f < 4) ? bz : by;
+      dep_code[d] = (unsigned short)((b1 << 9) | (ii << 5) | (b2 << 4) | jj);
       double Nu[kOrder ? kOrder : kMaxOrder], Nv[kOrder ? kOrder : kMaxOrder];
       if (bernstein) {
         /* reference :5453-5473 */
@@ -1555,11 +1585,153 @@ inline int sorted_node_numbers(Forest &f, int *h_out) {
    node_mirror_get waits for it.  createNodes starts the arrays named by
    NodeData::prefetch as soon as each is final, so the 5.9 GB read-back of the
    86 M-octant mesh overlaps the rest of createNodes instead of following it. */
+/* number of host threads for the mirror expansion: the CPUs this process may
+   run on (bench.py binds each rank to its GPU's NUMA node), at most 8 (measured on
+   the C2 mesh: 2 / 4 / 8 / 16 threads -> 197 / 124 / 101 / 105 ms per end-to-end
+   step; beyond 8 they take memory bandwidth from the DMA of conn) */
+inline int mirror_threads() {
+  int n = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+#endif
+  if (const char *ev = getenv("TMR_B200_HOST_THREADS")) n = atoi(ev);
+  return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+
+/* run body(t, T) on T threads (the caller is thread 0) */
+template <class Body>
+inline void host_parallel(int T, const Body &body) {
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.push_back(std::thread([&body, t, T]() { body(t, T); }));
+  body(0, T);
+  for (size_t k = 0; k < th.size(); k++) th[k].join();
+}
+
+/* dep_ptr and dep_weights from the stencil codes (DepExpandJob): lengths ->
+   prefix sums -> weight rows, each of T threads on a contiguous slice.  The
+   distinct codes of a mesh are few (4 edge rows and 16 face products at order
+   2), so every code is first mapped to a dense class whose full weight row is
+   tabulated once; the per-node work is then a table copy without
+   data-dependent branches. */
+inline void dep_expand_host(const unsigned short *codes, const double *table, i64 nd,
+                            int order, int *ptr, double *w, int T) {
+  const int n2 = order * order;
+  /* classes: [0, 2 p) edge rows, [2 p, 2 p + 4 p^2) face products, last = none */
+  const int nclass = 2 * order + 4 * n2 + 1;
+  std::vector<unsigned short> cls(65536, (unsigned short)(nclass - 1));
+  std::vector<int> len(nclass, 0);
+  std::vector<double> rows((size_t)nclass * n2, 0.0);
+  const double *face = table + (size_t)2 * order * order;
+  for (int b = 0; b < 2; b++) {
+    for (int k = 0; k < order; k++) {
+      const int c = b * order + k;
+      cls[kDepCodeEdge | (b << 4) | k] = (unsigned short)c;
+      len[c] = order;
+      for (int j = 0; j < order; j++) rows[(size_t)c * n2 + j] = table[(size_t)c * order + j];
+    }
+  }
+  for (int b1 = 0; b1 < 2; b1++) {
+    for (int i = 0; i < order; i++) {
+      for (int b2 = 0; b2 < 2; b2++) {
+        for (int j = 0; j < order; j++) {
+          const int c = 2 * order + ((b1 * order + i) * 2 + b2) * order + j;
+          cls[(b1 << 9) | (i << 5) | (b2 << 4) | j] = (unsigned short)c;
+          len[c] = n2;
+          const double *nu = face + (size_t)(b1 * order + i) * order;
+          const double *nv = face + (size_t)(b2 * order + j) * order;
+          for (int q = 0; q < n2; q++) rows[(size_t)c * n2 + q] = nu[q % order] * nv[q / order];
+        }
+      }
+    }
+  }
+  std::vector<i64> sum(T + 1, 0);
+  host_parallel(T, [&](int t, int TT) {
+    const i64 a = nd * t / TT, b = nd * (t + 1) / TT;
+    i64 s = 0;
+    for (i64 d = a; d < b; d++) s += len[cls[codes[d]]];
+    sum[t + 1] = s;
+  });
+  for (int t = 0; t < T; t++) sum[t + 1] += sum[t];
+  host_parallel(T, [&](int t, int TT) {
+    const i64 a = nd * t / TT, b = nd * (t + 1) / TT;
+    i64 o = sum[t];
+    i64 d = a;
+    if (order == 2) {
+      /* 4 doubles are stored for every node and the cursor advances by the
+         true length (an edge row's two surplus values are overwritten by the
+         next node); near the end of the slice's output range the exact path
+         takes over so that nothing is written past it */
+      const double *r4 = rows.data();
+      const i64 end = sum[t + 1];
+      for (; d < b && o + 4 <= end; d++) {
+        const int c = cls[codes[d]];
+        ptr[d] = (int)o;
+        const double *r = r4 + 4 * c;
+        w[o] = r[0];
+        w[o + 1] = r[1];
+        w[o + 2] = r[2];
+        w[o + 3] = r[3];
+        o += len[c];
+      }
+    }
+    for (; d < b; d++) {
+      const int c = cls[codes[d]];
+      ptr[d] = (int)o;
+      const double *r = rows.data() + (size_t)c * n2;
+      for (int j = 0; j < len[c]; j++) w[o + j] = r[j];
+      o += len[c];
+    }
+    if (t == TT - 1) ptr[nd] = (int)o;
+  });
+}
+
+/* dep_ptr + dep_weights mirrors: 2 bytes per dependent node over the bus
+   (on their own copy lane, ahead of the large arrays), expanded by host
+   threads in the background */
+inline int dep_expand_start(Forest &f) {
+  NodeData &nd = f.nodes;
+  Ctx &ctx = *f.ctx;
+  if (nd.mirror[kMirrorDepPtr].p) return 0;
+  nd.mctx = &ctx;
+  const i64 Nd = nd.num_dep_nodes;
+  const int order = nd.order;
+  int *ptr = static_cast<int *>(host_alloc(ctx, (size_t)(Nd + 1) * sizeof(int) + 16));
+  double *w = static_cast<double *>(host_alloc(ctx, (size_t)nd.dep_nnz * sizeof(double) + 16));
+  if (!ptr || !w) return 1;
+  nd.mirror[kMirrorDepPtr].p = ptr;
+  nd.mirror[kMirrorDepWeights].p = w;
+  if (Nd == 0) {
+    ptr[0] = 0;
+    return 0;
+  }
+  DepExpandJob &job = nd.dep_job;
+  const size_t tab_n = (size_t)4 * order * order;
+  job.codes = host_alloc(ctx, (size_t)Nd * sizeof(unsigned short) + 16);
+  job.table = static_cast<double *>(host_alloc(ctx, tab_n * sizeof(double)));
+  if (!job.codes || !job.table) return 1;
+  job.ev_table = copy_d2h_async(ctx, job.table, nd.dep_wtab.get(), tab_n * sizeof(double), 1);
+  job.ev_codes = copy_d2h_async(ctx, job.codes, nd.dep_code.get(),
+                                (size_t)Nd * sizeof(unsigned short), 1);
+  Ctx *c = &ctx;
+  void *ev_codes = job.ev_codes, *ev_table = job.ev_table;
+  const unsigned short *codes = static_cast<const unsigned short *>(job.codes);
+  const double *table = job.table;
+  const int T = mirror_threads();
+  job.thread = new std::thread([c, ev_codes, ev_table, codes, table, Nd, order, ptr, w, T]() {
+    copy_sync(*c, ev_table);
+    copy_sync(*c, ev_codes);
+    dep_expand_host(codes, table, Nd, order, ptr, w, T);
+  });
+  return 0;
+}
+
 inline int node_mirror_start(Forest &f, int which) {
   NodeData &nd = f.nodes;
   Ctx &ctx = *f.ctx;
   if (which < 0 || which >= kNumMirrors) return 1;
   if (nd.mirror[which].p) return 0;
+  if (which == kMirrorDepPtr || which == kMirrorDepWeights) return dep_expand_start(f);
   const void *src = NULL;
   size_t bytes = 0;
   const i64 npe = (i64)nd.order * nd.order * nd.order;
@@ -1569,21 +1741,74 @@ inline int node_mirror_start(Forest &f, int which) {
       bytes = (size_t)(nd.num_elements * npe) * sizeof(int);
       break;
     case kMirrorNumbers:
+      bytes = (size_t)nd.num_local_nodes * sizeof(int);
+      if (!forest_comm(f)) {
+        /* one rank: the numbers are -Nd..-1 (dependent) and 0..owned-1, every
+           value once: the sorted array is a range, written by host threads
+           (no sort, nothing over the bus) */
+        int *p = static_cast<int *>(host_alloc(ctx, bytes + 16));
+        if (!p) return 1;
+        nd.mctx = &ctx;
+        nd.mirror[which].p = p;
+        const i64 n = nd.num_local_nodes;
+        const int first = -(int)nd.num_dep_nodes;
+        const int T = mirror_threads() > 4 ? 4 : mirror_threads();
+        nd.mirror[which].thread = new std::thread([p, n, first, T]() {
+          host_parallel(T, [p, n, first](int t, int TT) {
+            const i64 a = n * t / TT, b = n * (t + 1) / TT;
+            for (i64 i = a; i < b; i++) p[i] = first + (int)i;
+          });
+        });
+        return 0;
+      }
+      if (nd.ext_numbers_valid) {
+        /* several ranks, slot construction: dependents -Nd..-1, then this
+           rank's owned range with the (few) numbers owned elsewhere merged in
+           around it: only those cross the bus */
+        const i64 nx = nd.ext_numbers.size();
+        int *p = static_cast<int *>(host_alloc(ctx, bytes + 16));
+        int *xs = static_cast<int *>(host_alloc(ctx, (size_t)nx * sizeof(int) + 16));
+        if (!p || !xs) return 1;
+        nd.mctx = &ctx;
+        nd.mirror[which].p = p;
+        void *ev = NULL;
+        if (nx > 0) {
+          DBuf<u64> k(ctx, nx), k_alt(ctx, nx);
+          DBuf<u32> v0, v1;
+          NumToKeyFn a = {nd.ext_numbers.get(), k.get()};
+          launch(ctx, nx, a, "nodes_numbers_to_keys");
+          radix_sort(ctx, k, k_alt, v0, v1, nx, 0, 32);
+          nd.sorted_numbers.alloc(ctx, nx);
+          KeyToNumFn b = {k.get(), nd.sorted_numbers.get()};
+          launch(ctx, nx, b, "nodes_keys_to_numbers");
+          ev = copy_d2h_async(ctx, xs, nd.sorted_numbers.get(), (size_t)nx * sizeof(int), 1);
+        }
+        Ctx *c = &ctx;
+        const i64 Ndep = nd.num_dep_nodes, nown = nd.num_owned_nodes;
+        const int start = nd.node_range_start;
+        nd.mirror[which].ev = ev; /* released by node_mirror_get */
+        nd.mirror[which].aux = xs;
+        const int T = mirror_threads() > 4 ? 4 : mirror_threads();
+        nd.mirror[which].thread = new std::thread([c, ev, p, xs, nx, Ndep, nown, start, T]() {
+          copy_sync(*c, ev);
+          i64 nlo = 0; /* externals owned by lower ranks */
+          while (nlo < nx && xs[nlo] < start) nlo++;
+          for (i64 q = 0; q < nlo; q++) p[Ndep + q] = xs[q];
+          for (i64 q = nlo; q < nx; q++) p[Ndep + nown + q] = xs[q];
+          int *pd = p, *po = p + Ndep + nlo;
+          host_parallel(T, [pd, po, Ndep, nown, start](int t, int TT) {
+            for (i64 i = Ndep * t / TT; i < Ndep * (t + 1) / TT; i++) pd[i] = (int)(i - Ndep);
+            for (i64 i = nown * t / TT; i < nown * (t + 1) / TT; i++) po[i] = start + (int)i;
+          });
+        });
+        return 0;
+      }
       if (build_sorted_numbers(f, nd.sorted_numbers)) return 1;
       src = nd.sorted_numbers.get();
-      bytes = (size_t)nd.num_local_nodes * sizeof(int);
-      break;
-    case kMirrorDepPtr:
-      src = nd.dep_ptr.get();
-      bytes = (size_t)(nd.num_dep_nodes + 1) * sizeof(int);
-      break;
-    case kMirrorDepConn:
-      src = nd.dep_conn.get();
-      bytes = (size_t)nd.dep_nnz * sizeof(int);
       break;
     default:
-      src = nd.dep_weights.get();
-      bytes = (size_t)nd.dep_nnz * sizeof(double);
+      src = nd.dep_conn.get();
+      bytes = (size_t)nd.dep_nnz * sizeof(int);
       break;
   }
   nd.mctx = &ctx;
@@ -1597,6 +1822,8 @@ inline int node_mirror_start(Forest &f, int which) {
 inline const void *node_mirror_get(Forest &f, int which) {
   NodeData &nd = f.nodes;
   if (!nd.valid || node_mirror_start(f, which)) return NULL;
+  if (which == kMirrorDepPtr || which == kMirrorDepWeights) nd.finish_dep_job();
+  nd.mirror[which].join();
   if (nd.mirror[which].ev) {
     copy_wait(*f.ctx, nd.mirror[which].ev);
     nd.mirror[which].ev = NULL;
@@ -2223,6 +2450,11 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     if (nx > 0) copy_d2d(ctx, xnum.get(), got.get(), (size_t)nx * sizeof(int));
     StoreBExternalFn se = {qn.get(), got.get() + nx, b_num.get()};
     launch(ctx, nxb, se, "nodes_external_store");
+    /* kept for getNodeNumbers(): with them the sorted list of local numbers
+       is two ranges and a short merge (node_mirror_start) */
+    nd.ext_numbers.swap(got);
+    nd.ext_numbers.set_size(nx + nxb);
+    nd.ext_numbers_valid = (Nd + nown + nx + nxb == Nn);
   }
   /* ---- node keys, numbers, connectivity ---- */
   nd.node_keys.alloc(ctx, Nn);
@@ -2786,7 +3018,6 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.node_num = nd.node_num.get();
     fill.win_edge = win_edge.get();
     fill.win_face = win_face.get();
-    fill.dep_node = dep_node.get();
     fill.bernstein = bernstein;
     fill.ent_off = general ? ent_off.get() : NULL;
     {
@@ -2801,6 +3032,16 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.dep_ptr = nd.dep_ptr.get();
     fill.dep_conn = nd.dep_conn.get();
     fill.dep_weights = nd.dep_weights.get();
+    nd.dep_code.alloc(ctx, Nd);
+    fill.dep_code = nd.dep_code.get();
+    /* the 1-D weight rows the codes index, computed by the same device
+       arithmetic as the stencils themselves */
+    nd.dep_wtab.alloc(ctx, (i64)4 * order * order);
+    {
+      DepWeightTableFn wt = {order, bernstein, {0}, nd.dep_wtab.get()};
+      for (int i = 0; i < kMaxOrder; i++) wt.knots[i] = nd.knots[i];
+      launch(ctx, (i64)4 * order, wt, "nodes_dep_weight_table");
+    }
     if (order == 2) {
       DepFillFn<2> k;
       static_cast<DepFillData &>(k) = fill;

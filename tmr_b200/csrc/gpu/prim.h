@@ -36,10 +36,18 @@ struct Ctx {
   Comm *comm; /* NULL = single rank */
   void *stream; /* cudaStream_t */
   void *copy_stream; /* second stream for device->host mirrors, lazily created */
+  void *copy_stream2; /* lane 1: copies done by an SM kernel into page-locked memory (not queued
+                         behind the copy engine's large transfers) */
+  /* page-locked, device-visible words the kernels write results the host
+     waits for into (scan totals, small read-backs): a PCIe store instead of a
+     copy-engine job that would queue behind a 2.8 GB mirror transfer */
+  unsigned long long *mailbox;
+  int mailbox_next;
   int profile;  /* time every named launch with events */
   int num_sms;
   long launch_count; /* kernels launched since the last reset */
   long sync_count;   /* blocking host<->device round trips since the last reset */
+  long long bytes_d2h, bytes_h2d; /* bytes copied over the bus since the last reset */
   std::map<std::string, KernelStat> stats;
   /* pending (start, stop) event pairs, resolved lazily at the next sync */
   std::vector<void *> ev_start, ev_stop;
@@ -50,9 +58,10 @@ struct Ctx {
   int trace;        /* TMR_B200_TRACE=1: print synchronised phase times */
   double trace_t0;  /* wall clock of the previous mark (s) */
   Ctx()
-      : device(0), comm(NULL), stream(NULL), copy_stream(NULL), profile(0),
+      : device(0), comm(NULL), stream(NULL), copy_stream(NULL), copy_stream2(NULL),
+        mailbox(NULL), mailbox_next(0), profile(0),
         num_sms(148),
-        launch_count(0), sync_count(0), fail_alloc_in(0), launch_log(NULL), trace(0),
+        launch_count(0), sync_count(0), bytes_d2h(0), bytes_h2d(0), fail_alloc_in(0), launch_log(NULL), trace(0),
         trace_t0(0.0) {}
 };
 
@@ -68,8 +77,12 @@ void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes);
 /* device->host copy on the context's COPY stream, ordered after everything
    enqueued so far on the main stream and overlapping what follows there; dst
    must be page-locked (host_alloc).  Returns a handle for copy_wait. */
-void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes);
+void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes, int lane = 0);
 void copy_wait(Ctx &ctx, void *handle); /* blocks until done, releases it */
+/* next 8-byte mailbox slot (device-visible host memory), zeroed */
+unsigned long long *mailbox_slot(Ctx &ctx);
+/* blocks until done, keeps the handle; callable from a worker thread */
+void copy_sync(Ctx &ctx, void *handle);
 void dev_zero(Ctx &ctx, void *p, size_t bytes);
 void dev_fill_ff(Ctx &ctx, void *p, size_t bytes);
 void stream_sync(Ctx &ctx);

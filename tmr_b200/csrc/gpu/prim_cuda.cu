@@ -163,35 +163,99 @@ void copy_h2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
   if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return;
   TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice,
                               (cudaStream_t)ctx.stream));
+  ctx.bytes_h2d += (long long)bytes;
   /* the source may be pageable/stack memory: make the copy complete before
      the caller can reuse it */
   TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
   ctx.sync_count++;
 }
 
-void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes) {
-  if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return;
-  TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost,
-                              (cudaStream_t)ctx.stream));
-  TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
-  ctx.sync_count++;
+static const int kMailboxWords = 1024; /* 8 KB */
+
+static bool mailbox_init(Ctx &ctx) {
+  if (ctx.mailbox) return true;
+  void *p = NULL;
+  if (cudaHostAlloc(&p, kMailboxWords * sizeof(unsigned long long),
+                    cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  ctx.mailbox = static_cast<unsigned long long *>(p);
+  return true;
 }
 
-void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes) {
+unsigned long long *mailbox_slot(Ctx &ctx) {
+  if (!mailbox_init(ctx)) return NULL;
+  /* the upper half is the staging area of small copy_d2h calls */
+  ctx.mailbox_next = (ctx.mailbox_next + 1) % (kMailboxWords / 2);
+  ctx.mailbox[ctx.mailbox_next] = 0;
+  return ctx.mailbox + ctx.mailbox_next;
+}
+
+__global__ void small_copy_kernel(unsigned char *dst, const unsigned char *src, int bytes) {
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+
+/* grid-stride 16-byte copy into device-visible host memory (lane 1) */
+__global__ void sm_copy_kernel(uint4 *dst, const uint4 *src, size_t n16,
+                               unsigned char *dst_tail, const unsigned char *src_tail,
+                               int tail) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    dst[i] = src[i];
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+void copy_d2h(Ctx &ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return;
+  const size_t half = (kMailboxWords / 2) * sizeof(unsigned long long);
+  if (bytes <= half && mailbox_init(ctx)) {
+    /* small read-back: an SM store into page-locked memory, independent of
+       what the copy engines are busy with */
+    unsigned char *stage = reinterpret_cast<unsigned char *>(ctx.mailbox + kMailboxWords / 2);
+    small_copy_kernel<<<1, 128, 0, (cudaStream_t)ctx.stream>>>(
+        stage, static_cast<const unsigned char *>(src), (int)bytes);
+    TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+    memcpy(dst, stage, bytes);
+  } else {
+    TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost,
+                                (cudaStream_t)ctx.stream));
+    TMR_CUDA_OK(cudaStreamSynchronize((cudaStream_t)ctx.stream));
+  }
+  ctx.sync_count++;
+  ctx.bytes_d2h += (long long)bytes;
+}
+
+void *copy_d2h_async(Ctx &ctx, void *dst, const void *src, size_t bytes, int lane) {
   if (bytes == 0 || !dst || !src || !ctx.last_error.empty()) return NULL;
-  if (!ctx.copy_stream) {
+  void *&slot = lane ? ctx.copy_stream2 : ctx.copy_stream;
+  if (!slot) {
     cudaStream_t s;
     TMR_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    ctx.copy_stream = s;
+    slot = s;
   }
+  const cudaStream_t cs = (cudaStream_t)slot;
   cudaEvent_t ready, done;
   TMR_CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   TMR_CUDA_OK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
   TMR_CUDA_OK(cudaEventRecord(ready, (cudaStream_t)ctx.stream));
-  TMR_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)ctx.copy_stream, ready, 0));
-  TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost,
-                              (cudaStream_t)ctx.copy_stream));
-  TMR_CUDA_OK(cudaEventRecord(done, (cudaStream_t)ctx.copy_stream));
+  TMR_CUDA_OK(cudaStreamWaitEvent(cs, ready, 0));
+  if (lane && (reinterpret_cast<size_t>(dst) % 16 == 0) &&
+      (reinterpret_cast<size_t>(src) % 16 == 0)) {
+    /* dst is page-locked (host_alloc) and, under unified addressing,
+       device-visible at the same address */
+    const size_t n16 = bytes / 16;
+    const int tail = (int)(bytes % 16);
+    sm_copy_kernel<<<64, 256, 0, cs>>>(
+        static_cast<uint4 *>(dst), static_cast<const uint4 *>(src), n16,
+        static_cast<unsigned char *>(dst) + n16 * 16,
+        static_cast<const unsigned char *>(src) + n16 * 16, tail);
+  } else {
+    TMR_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cs));
+  }
+  ctx.bytes_d2h += (long long)bytes;
+  TMR_CUDA_OK(cudaEventRecord(done, cs));
   cudaEventDestroy(ready);
   return done;
 }
@@ -200,6 +264,12 @@ void copy_wait(Ctx &ctx, void *handle) {
   if (!handle) return;
   TMR_CUDA_OK(cudaEventSynchronize((cudaEvent_t)handle));
   cudaEventDestroy((cudaEvent_t)handle);
+}
+
+void copy_sync(Ctx &ctx, void *handle) {
+  if (!handle) return;
+  cudaSetDevice(ctx.device); /* worker threads start on device 0 */
+  cudaEventSynchronize((cudaEvent_t)handle);
 }
 
 void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {

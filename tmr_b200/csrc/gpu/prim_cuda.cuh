@@ -281,7 +281,9 @@ u64 scan_apply(Ctx &ctx, i64 n, F f, G g, const char *name) {
   dev_zero(ctx, scratch, bytes);
   u64 *tile_state = scratch;
   u32 *ticket = reinterpret_cast<u32 *>(scratch + tiles);
-  u64 *total = scratch + tiles + 1;
+  /* the last tile stores the total straight into page-locked host memory */
+  unsigned long long *slot = mailbox_slot(ctx);
+  u64 *total = slot ? reinterpret_cast<u64 *>(slot) : scratch + tiles + 1;
   prof_begin(ctx, name);
   scan_apply_kernel<F, G><<<(unsigned)tiles, kScanThreads, 0,
                             (cudaStream_t)ctx.stream>>>(f, g, n, tile_state,
@@ -289,7 +291,12 @@ u64 scan_apply(Ctx &ctx, i64 n, F f, G g, const char *name) {
   prof_end(ctx);
   ctx.launch_count++;
   u64 h_total = 0;
-  copy_d2h(ctx, &h_total, total, sizeof(u64));
+  if (slot) {
+    stream_sync(ctx);
+    h_total = (u64)*static_cast<volatile unsigned long long *>(slot);
+  } else {
+    copy_d2h(ctx, &h_total, total, sizeof(u64));
+  }
   dev_free(ctx, scratch);
   return h_total;
 }

@@ -57,6 +57,7 @@ int tmrgpu_profile_reset(tmrgpu_ctx *ctx) {
   ctx->c.stats.clear();
   ctx->c.launch_count = 0;
   ctx->c.sync_count = 0;
+  ctx->c.bytes_d2h = ctx->c.bytes_h2d = 0;
   return 0;
 }
 
@@ -85,6 +86,9 @@ int tmrgpu_profile_json(tmrgpu_ctx *ctx, char *buf, int buflen) {
 
 long tmrgpu_launch_count(tmrgpu_ctx *ctx) { return ctx->c.launch_count; }
 long tmrgpu_sync_count(tmrgpu_ctx *ctx) { return ctx->c.sync_count; }
+int64_t tmrgpu_bus_bytes(tmrgpu_ctx *ctx, int h2d) {
+  return h2d ? ctx->c.bytes_h2d : ctx->c.bytes_d2h;
+}
 
 int tmrgpu_comm_unique_id(void *out, int out_bytes) {
   return comm_unique_id(out, out_bytes);

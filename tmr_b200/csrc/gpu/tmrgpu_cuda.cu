@@ -59,6 +59,9 @@ int tmrgpu_ctx_destroy(tmrgpu_ctx *ctx) {
   cudaStreamSynchronize((cudaStream_t)ctx->c.stream);
   dev_cache_destroy(ctx->c);
   if (ctx->c.launch_log) fclose(ctx->c.launch_log);
+  if (ctx->c.mailbox) cudaFreeHost(ctx->c.mailbox);
+  if (ctx->c.copy_stream) cudaStreamDestroy((cudaStream_t)ctx->c.copy_stream);
+  if (ctx->c.copy_stream2) cudaStreamDestroy((cudaStream_t)ctx->c.copy_stream2);
   if (ctx->own_stream) cudaStreamDestroy((cudaStream_t)ctx->c.stream);
   delete ctx;
   return 0;

@@ -56,24 +56,37 @@ def init_from_torch(lib=None):
     return rank, size
 
 
-def bind_to_gpu_numa(device_index):
-    """Pin this process to the CPU cores local to its GPU (NVML's ideal CPU
+def bind_to_gpu_numa(device_index, local_world=1):
+    """Pin this process to CPU cores local to its GPU (NVML's ideal CPU
     affinity), so that page-locked host mirrors are allocated on the GPU's own
     NUMA node: with one process per GPU, node-array read-backs then do not
-    cross the inter-socket link.  Returns the number of CPUs bound to, or 0
-    when NVML is unavailable (nothing changed)."""
+    cross the inter-socket link.  When several of the `local_world` GPUs of
+    this job share one affinity set, each process takes its own contiguous
+    slice of it, so that the host threads that rebuild the node arrays
+    (ops_nodes.h: dep_expand_host) of one rank do not run on another rank's
+    cores.  Returns the number of CPUs bound to, or 0 when NVML is unavailable
+    (nothing changed)."""
     import os
 
     try:
         import pynvml
 
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
         words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
         allowed = set(os.sched_getaffinity(0))
-        cpus = [c for c in cpus if c in allowed]
+
+        def cpus_of(index):
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            return [64 * w + b for w, m in enumerate(mask) for b in range(64)
+                    if (m >> b) & 1 and (64 * w + b) in allowed]
+
+        cpus = cpus_of(device_index)
+        if local_world > 1 and cpus:
+            sharing = [d for d in range(local_world) if cpus_of(d) == cpus]
+            k, n = sharing.index(device_index), len(sharing)
+            if len(cpus) >= 2 * n:
+                cpus = cpus[len(cpus) * k // n:len(cpus) * (k + 1) // n]
         if cpus:
             os.sched_setaffinity(0, cpus)
         return len(cpus)
