@@ -75,6 +75,26 @@ def main():
                      "checksums": ["d80cc85220bc9c0e", "9bd697a577179487", "bae29ce1fadfa5d9"],
                      "owned_nodes": 39894697},
     }
+    # C4 (BASELINE configs[3]): the full 1050-tree butterfly lattice with all 8
+    # face orientations and edge valence 2/3/4/8, computed here on the oracle
+    conn = util.butterfly_conn(5, 5, 6)
+    rec = []
+    f = util.build_forest(lib, conn, 1, 2, 30, 1, 2, record=rec)
+    res = util.node_results(f)
+    fp["C4_1050_trees"] = {
+        "recipe": "butterfly_conn(5,5,6) = 1050 trees, createTrees(1), 2 passes pct=30, "
+                  "balance(1), order 2",
+        "trees": int(len(conn)),
+        "counts": [len(r[1]) for r in rec if r[0].startswith("balance")],
+        "checksum": "%016x" % util.checksum(res["octants"]),
+        "owned_nodes": int(f.getNumOwnedNodes()),
+        "dep_nodes": int(len(res["dep"][0]) - 1),
+        "dep_nnz": int(len(res["dep"][1])),
+        "local_nodes": int(len(res["node_numbers"])),
+        "conn_checksum": "%016x" % (int(np.sum(res["conn"].astype(np.int64).ravel() *
+                                               (np.arange(res["conn"].size) % 1000003 + 1)))
+                                    & 0xFFFFFFFFFFFFFFFF),
+    }
     with open(os.path.join(HERE, "fingerprints.json"), "w") as fh:
         json.dump(fp, fh, indent=1)
 

@@ -67,9 +67,36 @@ def check_cases(lib, rank, size, verbose=True):
                 failures += 1
                 print("[multi-gpu] %-28s FAIL %s" % (name, str(e)[:400]), file=sys.stderr,
                       flush=True)
+    # findEnclosing for nodes held by OTHER ranks: no element, mpi_owner = owner rank
+    conn = util.box_conn()
+    q = [multirank.find_enclosing_queries(ref, conn) if ref is not None else None]
+    dist.broadcast_object_list(q, src=0)
+    ncases = len(cases)
+    if q[0] is not None:
+        ncases += 1
+        body = multirank.find_enclosing_body(conn, q[0])
+        try:
+            mine = body(lib, rank)
+        except Exception:  # noqa: BLE001
+            traceback.print_exc()
+            mine = None
+        gathered = [None] * size
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            try:
+                assert all(g is not None for g in gathered), "a rank failed"
+                expect = multirank.run_thread_ranks(ref, size, body, True)
+                nm = multirank.compare_find_enclosing(expect, gathered, size)
+                if verbose:
+                    print("[multi-gpu] %-28s OK  %8d misses name the reference's owner rank" %
+                          ("find_enclosing_r%d" % size, nm), file=sys.stderr, flush=True)
+            except AssertionError as e:
+                failures += 1
+                print("[multi-gpu] find_enclosing FAIL %s" % str(e)[:400], file=sys.stderr,
+                      flush=True)
     flag = torch.tensor([failures, unchecked], device="cuda")
     dist.broadcast(flag, src=0)
-    return len(cases), int(flag[0].item()), int(flag[1].item())
+    return ncases, int(flag[0].item()), int(flag[1].item())
 
 
 def main():

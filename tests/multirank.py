@@ -3,6 +3,8 @@ test-only emulation (threads + in-process communicator), or real GPUs (one
 process per GPU under torchrun -- see tests/multi_gpu_check.py)."""
 import threading
 
+import numpy as np
+
 import util
 from tmr_b200 import dist
 from tmr_b200.forest import OctForest
@@ -108,3 +110,46 @@ def compare_rank_results(a, b, what):
             for row in ia:
                 assert (ia[row][0] == ib[row][0]).all(), (what, r, row)
                 assert abs(ia[row][1] - ib[row][1]).max() <= 1e-12 * abs(ia[row][1]).max()
+
+
+def find_enclosing_body(conn, queries):
+    """every rank asks findEnclosing about every record of `queries` (element
+    records of the whole forest with info = a local node index): hits name the
+    local element, misses the owner rank of the node's position (reference
+    src/TMROctForest.cpp:6348-6372)"""
+    knots = np.array([-1.0, 1.0])
+
+    def body(lib, rank):
+        f = OctForest(order=2, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(1)
+        f.repartition()
+        for p in range(2):
+            o = f.getOctants().as_array()
+            f.refine(util.synth_flags(o, 2024 + p, 30))
+            f.balance(0)
+            f.repartition()
+        f.createNodes()
+        idx, own = f.findEnclosing(2, knots, queries)
+        return idx.copy(), own.copy()
+
+    return body
+
+
+def find_enclosing_queries(ref_lib, conn):
+    octs = util.build_forest(ref_lib, conn, 1, 2, 30, 0).getOctants().as_array().copy()
+    octs["info"] = np.random.default_rng(5).integers(0, 8, len(octs))
+    return octs
+
+
+def compare_find_enclosing(a, b, ranks):
+    misses = 0
+    for r in range(ranks):
+        hit = a[r][0] >= 0
+        assert np.array_equal(hit, b[r][0] >= 0), "rank %d: hit/miss differs" % r
+        assert np.array_equal(a[r][0][hit], b[r][0][hit]), "rank %d: element index" % r
+        assert np.array_equal(a[r][1], b[r][1]), "rank %d: mpi_owner" % r
+        misses += int((~hit).sum())
+        assert set(np.unique(b[r][1][~hit]).tolist()) <= set(range(ranks)) - {r}
+    assert misses > 0
+    return misses

@@ -73,3 +73,26 @@ def test_pinned_fingerprint_c1(lib):
     # size-independent structure: every dependent stencil sums to 1
     sums = np.add.reduceat(w, ptr[:-1])
     assert np.abs(sums - 1.0).max() < 1e-14
+
+
+def test_pinned_fingerprint_c4_1050_trees(lib):
+    """BASELINE.json configs[3] connectivity in full: the 5x5x6 lattice of
+    7-tree butterfly cells (1050 trees, every face orientation id, irregular
+    edge valence), createTrees(1), 2 passes pct 30, balance(1), order 2 --
+    fingerprint computed on the oracle by tests/golden/make_golden.py."""
+    with open(os.path.join(GOLD, "fingerprints.json")) as fh:
+        fp = json.load(fh)["C4_1050_trees"]
+    conn = util.butterfly_conn(5, 5, 6)
+    assert len(conn) == fp["trees"]
+    rec = []
+    f = util.build_forest(lib, conn, 1, 2, 30, 1, 2, record=rec)
+    assert [len(r[1]) for r in rec if r[0].startswith("balance")] == fp["counts"]
+    res = util.node_results(f)
+    assert "%016x" % util.checksum(res["octants"]) == fp["checksum"]
+    assert f.getNumOwnedNodes() == fp["owned_nodes"]
+    assert len(res["dep"][0]) - 1 == fp["dep_nodes"]
+    assert len(res["dep"][1]) == fp["dep_nnz"]
+    assert len(res["node_numbers"]) == fp["local_nodes"]
+    cs = int(np.sum(res["conn"].astype(np.int64).ravel() *
+                    (np.arange(res["conn"].size) % 1000003 + 1))) & 0xFFFFFFFFFFFFFFFF
+    assert "%016x" % cs == fp["conn_checksum"]

@@ -156,3 +156,17 @@ def test_serial_forest_inside_multirank_job(emu_lib, ref_lib):
     for ranks in (2, 3):
         got = multirank.run_thread_ranks(emu_lib, ranks, body, False)
         multirank.compare_rank_results(one * ranks, got, "serial in %d-rank job" % ranks)
+
+
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_find_enclosing_names_the_owner_of_a_miss(ranks, emu_lib, ref_lib):
+    """findEnclosing for nodes this rank does NOT hold: no element, and
+    mpi_owner = the rank owning the node's position (reference
+    src/TMROctForest.cpp:6348-6372; src/topology/TMR_TACSTopoCreator.cpp:166-217
+    routes on that value).  Every rank asks about every element corner of the
+    whole forest."""
+    conn = util.box_conn()
+    body = multirank.find_enclosing_body(conn, multirank.find_enclosing_queries(ref_lib, conn))
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_find_enclosing(a, b, ranks)

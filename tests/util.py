@@ -116,6 +116,8 @@ CONNS = {
     "connector15": connector_conn,
     "grid2": lambda: structured_conn(2),
     "butterfly2": lambda: butterfly_conn(2, 2, 2),
+    # BASELINE configs[3]: 1050 trees, all 8 face orientations, edge valence 2/3/4/8
+    "butterfly556": lambda: butterfly_conn(5, 5, 6),
 }
 
 
