@@ -67,11 +67,22 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None, a
             sync()
             t_dev = time.perf_counter() - t_a
             t2 = time.perf_counter()
-        if api:
+        t_bulk = None
+        if api == "bulk" or api is True:
+            # the whole CSR in one hand-off (tmr_b200_create_interpolation_csr)
+            tb = time.perf_counter()
+            rows, rowp, cols, vals = fine.createInterpolationCSR(coarse)
+            sync()
+            t_bulk = time.perf_counter() - tb
+            t2 = time.perf_counter()
+        if api is True:
+            # the reference's own hand-off: one addInterp call per row
             vec = fine.createInterpolation(coarse)
             sync()
             t3 = time.perf_counter()
             rows, rowp, cols, vals = vec.get()
+        elif api == "bulk":
+            t3 = t2
         else:
             t3 = t2
             a, b = ctypes.c_int64(0), ctypes.c_int64(0)
@@ -81,13 +92,17 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None, a
             rows, cols = np.zeros(a.value, np.int8), np.zeros(b.value, np.int8)
             rowp, vals = np.zeros(1, np.int64), np.zeros(0)
         sums = np.add.reduceat(vals, rowp[:-1]) if (api and len(rows)) else np.zeros(0)
+        if api and len(rows):
+            rowp = np.asarray(rowp)
         out.append({
             "level": k, "fine_order": fine.getMeshOrder(), "coarse_order": coarse.getMeshOrder(),
             "fine_octants": fine.getNumOctants(), "coarse_octants": coarse.getNumOctants(),
             "rows": int(len(rows)), "nnz": int(len(cols)),
             "create_nodes_fine_s": t1 - t0, "create_nodes_coarse_s": t2 - t1,
-            "create_interp_s": t3 - t2, "rows_per_s": len(rows) / max(t3 - t2, 1e-9),
-            "device_csr_s": t_dev,
+            "create_interp_s": (t3 - t2) if api is True else None,
+            "rows_per_s": (len(rows) / max(t3 - t2, 1e-9)) if api is True else None,
+            "device_csr_s": t_dev, "api_bulk_csr_s": t_bulk,
+            "api_bulk_rows_per_s": (len(rows) / t_bulk) if t_bulk else None,
             "device_rows_per_s": (len(rows) / t_dev) if t_dev else None,
             "max_rowsum_err": float(np.abs(sums - 1).max()) if len(sums) else None,
         })
@@ -105,6 +120,9 @@ def main():
                     help="per-kernel CUDA-event times (ms) of the whole hierarchy build go here")
     ap.add_argument("--no-api", action="store_true",
                     help="skip the per-row addInterp hand-off timing (device CSR only)")
+    ap.add_argument("--bulk-only", action="store_true",
+                    help="time the one-call CSR hand-off (createInterpolationCSR) but not the "
+                         "per-row addInterp loop")
     args = ap.parse_args()
     import torch
 
@@ -153,7 +171,7 @@ def main():
         lib.tmrgpu_profile_reset(ctx)
         lib.tmrgpu_profile_enable(ctx, 1)
     gpu = hierarchy(lib, args.level, args.passes, args.pct, sync, dev_flags, dev_interp,
-                    api=not args.no_api)
+                    api=("bulk" if args.bulk_only else (not args.no_api)))
     if args.profile_out:
         buf = ctypes.create_string_buffer(1 << 16)
         lib.tmrgpu_profile_json(ctx, buf, len(buf))

@@ -165,6 +165,23 @@ int tmrgpu_node_device_views(tmrgpu_forest *f, const int **conn,
                              const int **dep_conn, const double **dep_weights,
                              const uint64_t **element_keys, int *key_depth,
                              int *block_bits);
+/* The arrays TMROctTACSCreator::createTACS hands to TACSAssembler (reference
+   src/TMR_TACSCreator.cpp:332-461: setElementConnectivity(ptr, conn),
+   setDependentNodes(dep_ptr, dep_conn, dep_weights) and the three counts of
+   the TACSAssembler constructor), as DEVICE pointers in exactly that shape,
+   for an assembler that lives on the GPU.  elem_ptr[i] = order^3 * i is built
+   on first request.  Valid until the next mutating call on the forest. */
+typedef struct {
+  int64_t num_elements, num_owned_nodes, num_dep_nodes, num_local_nodes, dep_nnz;
+  int order;
+  const int *elem_ptr;      /* [num_elements + 1] */
+  const int *conn;          /* [num_elements * order^3] global node numbers */
+  const int *dep_ptr;       /* [num_dep_nodes + 1] */
+  const int *dep_conn;      /* [dep_nnz] */
+  const double *dep_weights; /* [dep_nnz] */
+  const int *node_numbers;  /* [num_local_nodes] number of each local node, node order */
+} tmrgpu_assembler_view;
+int tmrgpu_assembler_views(tmrgpu_forest *f, tmrgpu_assembler_view *out);
 int tmrgpu_interp_device_views(tmrgpu_forest *fine, const int **rows,
                                const int **rowp, const int **cols,
                                const double **vals);

@@ -532,3 +532,42 @@ def test_octant_hash(node_mode, impl, ref_lib):
         assert len(res[0][1]) == len(res[1][1])
         for fld in ("block", "x", "y", "z", "level", "info", "tag"):
             assert np.array_equal(res[0][1][fld], res[1][1][fld]), fld
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_device_views_hold_what_the_getters_return(order, impl, ref_lib):
+    """the device-resident arrays a GPU assembler would read
+    (tmrgpu_assembler_views: elem_ptr/conn/dependent CSR in the shape createTACS
+    hands to TACSAssembler, reference src/TMR_TACSCreator.cpp:332-461) equal the
+    arrays the host getters return -- which are compared with the oracle -- and
+    the bulk prolongation hand-off (createInterpolationCSR) equals the per-row
+    addInterp stream of the reference."""
+    conn = util.box_conn()
+    fa = util.build_forest(ref_lib, conn, 1, 2, 30, 1, order)
+    fb = util.build_forest(impl, conn, 1, 2, 30, 1, order)
+    ra, rb = util.node_results(fa), util.node_results(fb)
+    util.assert_nodes_equal(ra, rb, "device views")
+    v = fb.assemblerViews()
+    npe = order ** 3
+    assert v["num_elements"] == len(rb["octants"]) and v["order"] == order
+    assert v["num_owned_nodes"] == fa.getNumOwnedNodes()
+    assert np.array_equal(v["elem_ptr"], npe * np.arange(len(rb["octants"]) + 1))
+    assert np.array_equal(v["conn"].reshape(-1, npe), ra["conn"].reshape(-1, npe))
+    assert np.array_equal(v["dep_ptr"], ra["dep"][0])
+    assert np.array_equal(v["dep_conn"], ra["dep"][1])
+    np.testing.assert_allclose(v["dep_weights"], ra["dep"][2], rtol=1e-12, atol=0)
+    assert np.array_equal(np.sort(v["node_numbers"]), ra["node_numbers"])
+    # bulk prolongation vs the reference's addInterp stream
+    ca = fa.coarsen() if order == 2 else fa.duplicate()
+    cb = fb.coarsen() if order == 2 else fb.duplicate()
+    if order == 2:
+        ca.balance(1)
+        cb.balance(1)
+    else:
+        ca.setMeshOrder(2)
+        cb.setMeshOrder(2)
+    rows_a, rowp_a, cols_a, vals_a = fa.createInterpolation(ca).get()
+    rows_b, rowp_b, cols_b, vals_b = fb.createInterpolationCSR(cb)
+    assert np.array_equal(rows_a, rows_b) and np.array_equal(rowp_a, rowp_b)
+    assert np.array_equal(cols_a, cols_b)
+    np.testing.assert_allclose(vals_b, vals_a, rtol=1e-12, atol=1e-300)

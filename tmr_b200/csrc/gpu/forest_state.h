@@ -91,6 +91,7 @@ struct NodeData {
   DBuf<int> conn;       /* [num_elements * order^3], global numbers */
   DBuf<int> dep_ptr;    /* [num_dep_nodes + 1] */
   DBuf<int> dep_conn;   /* [dep_nnz] */
+  DBuf<int> elem_ptr;   /* [num_elements + 1] order^3 * i, built on request (tmrgpu_assembler_views) */
   DBuf<double> dep_weights;
   DBuf<unsigned short> dep_code; /* [num_dep_nodes] stencil codes (DepExpandJob) */
   DBuf<double> dep_wtab; /* [2 kinds][2 sides][order positions][order] weight rows */
@@ -151,6 +152,7 @@ struct NodeData {
     dep_weights.reset();
     dep_code.reset();
     dep_wtab.reset();
+    elem_ptr.reset();
     ext_numbers.reset();
     ext_numbers_valid = false;
     node_range.clear();

@@ -419,6 +419,37 @@ int tmrgpu_node_device_views(tmrgpu_forest *F, const int **conn,
   return nd.valid ? 0 : 1;
 }
 
+struct ElemPtrFn {
+  int npe;
+  int *out;
+  TMR_HD void operator()(i64 i) const { out[i] = (int)(npe * i); }
+};
+
+int tmrgpu_assembler_views(tmrgpu_forest *F, tmrgpu_assembler_view *out) {
+  Forest &f = F->f;
+  NodeData &nd = f.nodes;
+  if (!out || !nd.valid) return 1;
+  const int npe = nd.order * nd.order * nd.order;
+  if (nd.elem_ptr.size() != nd.num_elements + 1) {
+    nd.elem_ptr.alloc(*f.ctx, nd.num_elements + 1);
+    ElemPtrFn ep = {npe, nd.elem_ptr.get()};
+    launch(*f.ctx, nd.num_elements + 1, ep, "nodes_elem_ptr");
+  }
+  out->num_elements = nd.num_elements;
+  out->num_owned_nodes = nd.num_owned_nodes;
+  out->num_dep_nodes = nd.num_dep_nodes;
+  out->num_local_nodes = nd.num_local_nodes;
+  out->dep_nnz = nd.dep_nnz;
+  out->order = nd.order;
+  out->elem_ptr = nd.elem_ptr.get();
+  out->conn = nd.conn.get();
+  out->dep_ptr = nd.dep_ptr.get();
+  out->dep_conn = nd.dep_conn.get();
+  out->dep_weights = nd.dep_weights.get();
+  out->node_numbers = nd.node_num.get();
+  return swept(*f.ctx, 0, "assembler_views");
+}
+
 int tmrgpu_interp_device_views(tmrgpu_forest *F, const int **rows,
                                const int **rowp, const int **cols,
                                const double **vals) {

@@ -318,6 +318,8 @@ TMROctForest::TMROctForest(MPI_Comm _comm, int _mesh_order,
   owners = NULL;
   conn = node_numbers = node_range = NULL;
   dep_ptr = dep_conn = NULL;
+  interp_rows = interp_rowp = interp_cols = NULL;
+  interp_vals = NULL;
   dep_weights = NULL;
   X = NULL;
   num_local_nodes = num_dep_nodes = num_owned_nodes = ext_pre_offset = 0;
@@ -332,6 +334,10 @@ TMROctForest::~TMROctForest() {
   dropMeshData(1, 1);
   if (dev) tmrgpu_forest_destroy(dev);
   delete[] interp_knots;
+  delete[] interp_rows;
+  delete[] interp_rowp;
+  delete[] interp_cols;
+  delete[] interp_vals;
 }
 
 int TMROctForest::ensureDevice() {
@@ -771,20 +777,45 @@ int TMROctForest::getLocalNodeNumber(int node) {
 }
 
 /* ---- interpolation ---------------------------------------------------------------------- */
-void TMROctForest::createInterpolation(TMROctForest *coarse,
-                                       TACSBVecInterp *interp) {
+int TMROctForest::createInterpolationCSR(TMROctForest *coarse, const int **rows,
+                                         const int **rowp, const int **cols,
+                                         const double **vals) {
+  if (rows) *rows = NULL;
+  if (rowp) *rowp = NULL;
+  if (cols) *cols = NULL;
+  if (vals) *vals = NULL;
   createNodes();
   coarse->createNodes();
-  if (!dev || !coarse->dev || !nodes_exist || !coarse->nodes_exist) return;
+  if (!dev || !coarse->dev || !nodes_exist || !coarse->nodes_exist) return 0;
   int64_t nrows = 0, nnz = 0;
-  if (tmrgpu_create_interp(dev, coarse->dev, &nrows, &nnz)) return;
-  std::vector<int> rows(nrows + 1), rowp(nrows + 2), cols(nnz + 1);
-  std::vector<double> vals(nnz + 1);
-  tmrgpu_download_interp(dev, rows.data(), rowp.data(), cols.data(),
-                         vals.data());
+  if (tmrgpu_create_interp(dev, coarse->dev, &nrows, &nnz)) return 0;
+  delete[] interp_rows;
+  delete[] interp_rowp;
+  delete[] interp_cols;
+  delete[] interp_vals;
+  interp_rows = new int[nrows + 1];
+  interp_rowp = new int[nrows + 2];
+  interp_cols = new int[nnz + 1];
+  interp_vals = new double[nnz + 1];
+  if (tmrgpu_download_interp(dev, interp_rows, interp_rowp, interp_cols,
+                             interp_vals)) {
+    return 0;
+  }
+  if (rows) *rows = interp_rows;
+  if (rowp) *rowp = interp_rowp;
+  if (cols) *cols = interp_cols;
+  if (vals) *vals = interp_vals;
+  return (int)nrows;
+}
+
+void TMROctForest::createInterpolation(TMROctForest *coarse,
+                                       TACSBVecInterp *interp) {
+  const int *rows, *rowp, *cols;
+  const double *vals;
+  const int nrows = createInterpolationCSR(coarse, &rows, &rowp, &cols, &vals);
   /* same call stream as the reference's loop (:6683): one addInterp per owned
      fine node, in first-touch order */
-  for (int64_t r = 0; r < nrows; r++) {
+  for (int r = 0; r < nrows; r++) {
     interp->addInterp(rows[r], &vals[rowp[r]], &cols[rowp[r]],
                       rowp[r + 1] - rowp[r]);
   }

@@ -113,6 +113,14 @@ class TMROctForest : public TMREntity {
   /* B200 extension (not in the reference): the device forest behind this
      object, for callers that keep node data on the GPU */
   tmrgpu_forest *getDeviceForest() { return dev; }
+  /* B200 extension: the whole prolongation in ONE hand-off instead of one
+     TACSBVecInterp::addInterp call per row (reference :6683, :6775): CSR
+     arrays owned by this forest, rows in exactly the order
+     createInterpolation() would emit them; returns the number of rows.
+     createInterpolation(coarse, interp) is this followed by the addInterp loop. */
+  int createInterpolationCSR(TMROctForest *coarse, const int **rows,
+                             const int **rowp, const int **cols,
+                             const double **vals);
 
  private:
   /* super-mesh connectivity shared between a forest and its duplicates */
@@ -144,6 +152,10 @@ class TMROctForest : public TMREntity {
   void fetchNodeData();
   void fetchNodeNumbers();
   int ensureDevice();
+
+  /* createInterpolationCSR results */
+  int *interp_rows, *interp_rowp, *interp_cols;
+  double *interp_vals;
 
   MPI_Comm comm;
   int mpi_rank, mpi_size;

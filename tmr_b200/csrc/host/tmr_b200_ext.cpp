@@ -4,6 +4,7 @@
   the CUDA layer (include/tmrgpu.h) on device-resident inputs.
 */
 #include "TMROctForest.h"
+#include "tmr_b200_ext.h"
 #include "tmrgpu.h"
 
 extern "C" {
@@ -22,6 +23,19 @@ int tmr_b200_init_world(int rank, int size, const void *id) {
   tmrgpu_ctx *ctx = tmr_b200_context();
   if (!ctx) return 1;
   return tmrgpu_ctx_init_comm(ctx, rank, size, id);
+}
+
+/* the whole prolongation at once (TMROctForest::createInterpolationCSR):
+   borrowed pointers into arrays owned by the fine forest; returns the rows */
+int tmr_b200_create_interpolation_csr(void *fine, void *coarse, const int **rows,
+                                      const int **rowp, const int **cols,
+                                      const double **vals, int *nnz) {
+  const int *rp = NULL;
+  const int n = static_cast<TMROctForest *>(fine)->createInterpolationCSR(
+      static_cast<TMROctForest *>(coarse), rows, &rp, cols, vals);
+  if (rowp) *rowp = rp;
+  if (nnz) *nnz = (rp && n > 0) ? rp[n] : 0;
+  return n;
 }
 
 }  // extern "C"

@@ -299,6 +299,67 @@ class OctForest:
         self._lib.tmrc_create_interpolation(self._ptr, coarse._ptr, vec._ptr)
         return vec
 
+    # ---- B200 extensions (include/tmr_b200_ext.h, include/tmrgpu.h) ----------
+    def createInterpolationCSR(self, coarse):
+        """The whole prolongation in one hand-off: (rows, rowp, cols, vals),
+        rows in the order createInterpolation() emits its addInterp calls
+        (tmr_b200_create_interpolation_csr; not available on the oracle)."""
+        lib = self._lib
+        rows, rowp, cols = (C.POINTER(C.c_int)() for _ in range(3))
+        vals = C.POINTER(C.c_double)()
+        nnz = C.c_int(0)
+        lib.tmr_b200_create_interpolation_csr.restype = C.c_int
+        lib.tmr_b200_create_interpolation_csr.argtypes = [C.c_void_p, C.c_void_p] + [C.c_void_p] * 5
+        n = lib.tmr_b200_create_interpolation_csr(
+            self._ptr, coarse._ptr, C.byref(rows), C.byref(rowp), C.byref(cols),
+            C.byref(vals), C.byref(nnz))
+        return (_capi.as_int_array(rows, n).copy(), _capi.as_int_array(rowp, n + 1).copy(),
+                _capi.as_int_array(cols, nnz.value).copy(),
+                _capi.as_double_array(vals, nnz.value).copy())
+
+    def assemblerViews(self):
+        """Copies of the DEVICE arrays tmrgpu_assembler_views exposes (the
+        arrays createTACS hands to TACSAssembler, reference
+        src/TMR_TACSCreator.cpp:332-461), for checking them against the host
+        getters; a GPU consumer would use the pointers where they are."""
+        lib = self._lib
+
+        class View(C.Structure):
+            _fields_ = [(n, C.c_int64) for n in ("num_elements", "num_owned_nodes",
+                                                 "num_dep_nodes", "num_local_nodes", "dep_nnz")]
+            _fields_ += [("order", C.c_int)]
+            _fields_ += [(n, C.c_void_p) for n in ("elem_ptr", "conn", "dep_ptr", "dep_conn",
+                                                   "dep_weights", "node_numbers")]
+
+        lib.tmr_b200_device_forest.restype = C.c_void_p
+        lib.tmr_b200_device_forest.argtypes = [C.c_void_p]
+        lib.tmr_b200_context.restype = C.c_void_p
+        dev = C.c_void_p(lib.tmr_b200_device_forest(self._ptr))
+        ctx = C.c_void_p(lib.tmr_b200_context())
+        v = View()
+        lib.tmrgpu_assembler_views.argtypes = [C.c_void_p, C.c_void_p]
+        if lib.tmrgpu_assembler_views(dev, C.byref(v)) != 0:
+            raise RuntimeError("tmr_b200: no node data on the device (call createNodes)")
+        lib.tmrgpu_copy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+
+        def pull(ptr, n, dtype):
+            out = np.zeros(n, dtype=dtype)
+            if n:
+                lib.tmrgpu_copy_d2h(ctx, out.ctypes.data, ptr, out.nbytes)
+            return out
+
+        npe = v.order ** 3
+        return {
+            "num_elements": v.num_elements, "num_owned_nodes": v.num_owned_nodes,
+            "num_dep_nodes": v.num_dep_nodes, "order": v.order,
+            "elem_ptr": pull(v.elem_ptr, v.num_elements + 1, np.int32),
+            "conn": pull(v.conn, v.num_elements * npe, np.int32),
+            "dep_ptr": pull(v.dep_ptr, v.num_dep_nodes + 1, np.int32),
+            "dep_conn": pull(v.dep_conn, v.dep_nnz, np.int32),
+            "dep_weights": pull(v.dep_weights, v.dep_nnz, np.float64),
+            "node_numbers": pull(v.node_numbers, v.num_local_nodes, np.int32),
+        }
+
 
 def array_sort(lib, records, use_node_index=0):
     """TMROctantArray::sort (reference src/TMROctant.cpp:357-399)."""
