@@ -72,6 +72,12 @@ struct DepExpandJob {
   DepExpandJob() : thread(NULL), codes(NULL), table(NULL), ev_codes(NULL), ev_table(NULL) {}
 };
 
+/* per-leaf prefix counts of the slot construction (ops_nodes_slots.h): nodes and
+   dependent nodes before the leaf, and which of its 27 slots hold either */
+struct SlotInfo2 {
+  u32 node_off, mask, dep_off, dmask;
+};
+
 struct NodeData {
   bool valid;
   int order;
@@ -91,6 +97,10 @@ struct NodeData {
   DBuf<int> conn;       /* [num_elements * order^3], global numbers */
   DBuf<int> dep_ptr;    /* [num_dep_nodes + 1] */
   DBuf<int> dep_conn;   /* [dep_nnz] */
+  /* one rank, slot construction: per-leaf prefix counts (16 B, SlotInfo2).  node_keys /
+     node_num are then built on first request (ensure_node_arrays): createNodes itself
+     and the host getters never need them */
+  DBuf<SlotInfo2> slot_info;
   DBuf<int> elem_ptr;   /* [num_elements + 1] order^3 * i, built on request (tmrgpu_assembler_views) */
   DBuf<double> dep_weights;
   DBuf<unsigned short> dep_code; /* [num_dep_nodes] stencil codes (DepExpandJob) */
@@ -153,6 +163,7 @@ struct NodeData {
     dep_code.reset();
     dep_wtab.reset();
     elem_ptr.reset();
+    slot_info.reset();
     ext_numbers.reset();
     ext_numbers_valid = false;
     node_range.clear();

@@ -1267,6 +1267,7 @@ struct DepFillData {
   int *dep_conn;
   double *dep_weights;
   unsigned short *dep_code; /* compact form of ptr + weights (DepExpandJob) */
+  SlotLookup sl; /* one rank, slot construction: node numbers by position */
 
   KeyIndex node_ix;
   /* order 2 shortcut: in a complete family the parent's corner c is corner c
@@ -1373,6 +1374,7 @@ struct DepFillFn : DepFillData {
 
   TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, int label) const {
     transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
+    if (sl.on) return sl.number(block, x, y, z);
     const i64 idx = node_ix.find(node_keys, nfmt.encode(block, x, y, z, label));
     return idx >= 0 ? node_num[idx] : 0;
   }
@@ -2197,9 +2199,31 @@ struct BHomeDestFn {
    connectivity comes out as final node NUMBERS (node_keys, node_num, the
    counts and node_range of `nd` are filled too).  Several ranks: `om_n` maps
    node positions to their home rank. */
+/* node_keys and node_num on request (one rank, slot construction) */
+inline int ensure_node_arrays(Forest &f) {
+  NodeData &nd = f.nodes;
+  Ctx &ctx = *f.ctx;
+  if (!nd.valid) return 1;
+  if (nd.num_local_nodes == 0 || nd.node_num.size() == nd.num_local_nodes) return 0;
+  if (nd.slot_info.size() != f.n) return 1;
+  nd.node_keys.alloc(ctx, nd.num_local_nodes);
+  nd.node_num.alloc(ctx, nd.num_local_nodes);
+  SlotKeys2Fn kf = {f.keys.get(), f.fmt, nd.slot_info.get(), nd.node_keys.get(),
+                    nd.node_num.get()};
+  launch(ctx, f.n, kf, "nodes_slot_keys");
+  return 0;
+}
+
+struct SlotState { /* outlives build_nodes_slots: the dependent CSR looks nodes up in it */
+  DBuf<RankEntry> rank_tab;
+  DBuf<u32> rank_cells;
+  SlotLookup lookup;
+  SlotState() { lookup.on = 0; }
+};
+
 inline int build_nodes_slots(Forest &f, NodeData &nd,
                              const unsigned char *fmask, u64 k_first, u64 k_last,
-                             const OwnerMap &om_n, i64 *Nn_out) {
+                             const OwnerMap &om_n, i64 *Nn_out, SlotState &st) {
   Ctx &ctx = *f.ctx;
   Comm *comm = forest_comm(f);
   const int me = comm ? comm->rank : 0;
@@ -2224,8 +2248,8 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
   const u64 pos_lo = E > 0 ? (k_first >> 5) : 0ULL;
   const u64 pos_hi =
       E > 0 ? (k_last >> 5) + (1ULL << (3 * (D - (int)(k_last & 31)))) : 0ULL;
-  DBuf<RankEntry> rank_tab;
-  DBuf<u32> rank_cells;
+  DBuf<RankEntry> &rank_tab = st.rank_tab;
+  DBuf<u32> &rank_cells = st.rank_cells;
   size_t ix_budget = (size_t)8 * (size_t)E > ((size_t)64 << 20)
                          ? (size_t)8 * (size_t)E
                          : ((size_t)64 << 20);
@@ -2272,14 +2296,17 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
     if (h_ctl[1]) return 0;
     const i64 Nn = (i64)(tot & 0x7fffffffULL), Nd = (i64)(tot >> 31);
-    nd.node_keys.alloc(ctx, Nn);
-    nd.node_num.alloc(ctx, Nn);
-    SlotKeys2Fn kf = {f.keys.get(), f.fmt, slotinfo.get(), nd.node_keys.get(),
-                      nd.node_num.get()};
-    launch(ctx, E, kf, "nodes_slot_keys");
     SlotResolve2Fn rs = {slotinfo.get(), slot8.get(),
                          reinterpret_cast<u32 *>(nd.conn.get())};
     launch(ctx, E, rs, "nodes_slot_resolve");
+    /* node_keys / node_num (1.5 GB at 86 M octants) are not needed by anything
+       createNodes produces: they are written on first request from the
+       per-leaf counts kept here (ensure_node_arrays) */
+    nd.slot_info.swap(slotinfo);
+    st.lookup.on = 1;
+    st.lookup.v = v;
+    st.lookup.v.fail = NULL;
+    st.lookup.si = nd.slot_info.get();
     nd.num_candidates = 0;
     nd.num_dep_nodes = Nd;
     nd.num_owned_nodes = Nn - Nd;
@@ -2651,13 +2678,15 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   /* order 2 without labels: nodes named by (leaf, slot), no candidate sort
      (ops_nodes_slots.h); TMR_B200_NODES=sort forces the general path */
   int slots_done = 0, numbered = 0;
+  SlotState slot_state;
   {
     /* the choice must be the same on every rank (the slot construction has
        its own exchanges): nothing rank-local enters the condition */
     const char *mode = getenv("TMR_B200_NODES");
     if (gorder == 2 && !general && nd.nfmt.lbits == 0 && (comm || E > 0) &&
         !(mode && strcmp(mode, "sort") == 0)) {
-      slots_done = build_nodes_slots(f, nd, fmask.get(), k_first, k_last, om_n, &Nn);
+      slots_done = build_nodes_slots(f, nd, fmask.get(), k_first, k_last, om_n, &Nn,
+                                     slot_state);
       if (slots_done < 0) return 1;
       numbered = slots_done;
       if (getenv("TMR_B200_NODES_VERBOSE")) {
@@ -3004,9 +3033,14 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     nd.dep_weights.alloc(ctx, (i64)nnz);
     DBuf<u32> node_index_store;
     DepFillData fill;
-    fill.node_ix = build_key_index(ctx, nd.node_keys.get(), nd.node_keys.size(),
-                                   (u64)f.nblocks << nd.nfmt.pos_bits(),
-                                   node_index_store);
+    fill.sl = slot_state.lookup;
+    if (!fill.sl.on) {
+      fill.node_ix = build_key_index(ctx, nd.node_keys.get(), nd.node_keys.size(),
+                                     (u64)f.nblocks << nd.nfmt.pos_bits(),
+                                     node_index_store);
+    } else {
+      fill.node_ix = KeyIndex();
+    }
     fill.keys = f.keys.get();
     fill.fmt = f.fmt;
     fill.nfmt = nd.nfmt;

@@ -586,9 +586,6 @@ struct SlotKeyEmit {
 
 
 /* one rank: nodes and dependent nodes counted together, lo | hi << 31 */
-struct SlotInfo2 {
-  u32 node_off, mask, dep_off, dmask;
-};
 struct SlotCount2Fn {
   const u32 *mask;
   const u32 *dmask;
@@ -628,6 +625,22 @@ TMR_HD SlotInfo2 load_slotinfo2(const SlotInfo2 *p) {
   return *p;
 #endif
 }
+
+/* one rank: number of the node at a canonical position, straight from the
+   slots (rank index + per-leaf prefix counts) -- no node key array needed */
+struct SlotLookup {
+  int on;
+  SlotView v;
+  const SlotInfo2 *si;
+  TMR_HD int number(i32 b, i32 x, i32 y, i32 z) const {
+    const u64 loc = v.locate_xyz(b, x, y, z);
+    if (loc >= kLocFail) return 0;
+    const i64 leaf = (i64)(loc >> 5);
+    const int ord = (int)(loc & 31);
+    const SlotInfo2 s = load_slotinfo2(si + leaf);
+    return ((s.mask >> ord) & 1u) ? slot_node_number(s, ord) : 0;
+  }
+};
 
 /* key (NodeFmt at Dn = D) of slot c6 of the leaf `key` */
 TMR_HD u64 slot_node_key(u64 key, int D, int c6) {

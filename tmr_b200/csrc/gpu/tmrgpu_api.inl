@@ -384,6 +384,7 @@ int tmrgpu_download_nodes(tmrgpu_forest *F, int *conn, int *node_numbers,
              (size_t)(nd.num_elements * npe) * sizeof(int));
   }
   if (node_numbers) {
+    if (ensure_node_arrays(f)) return 1;
     copy_d2h(ctx, node_numbers, nd.node_num.get(),
              (size_t)nd.num_local_nodes * sizeof(int));
   }
@@ -407,8 +408,9 @@ int tmrgpu_node_device_views(tmrgpu_forest *F, const int **conn,
                              const uint64_t **element_keys, int *key_depth,
                              int *block_bits) {
   Forest &f = F->f;
-  const NodeData &nd = f.nodes;
+  NodeData &nd = f.nodes;
   if (conn) *conn = nd.conn.get();
+  if (node_numbers && nd.valid && ensure_node_arrays(f)) return 1;
   if (node_numbers) *node_numbers = nd.node_num.get();
   if (dep_ptr) *dep_ptr = nd.dep_ptr.get();
   if (dep_conn) *dep_conn = nd.dep_conn.get();
@@ -430,6 +432,7 @@ int tmrgpu_assembler_views(tmrgpu_forest *F, tmrgpu_assembler_view *out) {
   NodeData &nd = f.nodes;
   if (!out || !nd.valid) return 1;
   const int npe = nd.order * nd.order * nd.order;
+  if (ensure_node_arrays(f)) return 1;
   if (nd.elem_ptr.size() != nd.num_elements + 1) {
     nd.elem_ptr.alloc(*f.ctx, nd.num_elements + 1);
     ElemPtrFn ep = {npe, nd.elem_ptr.get()};
