@@ -548,6 +548,31 @@ def main():
     global_checksum = (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
     value = total_octants * args.steps / (ms * 1e-3)
 
+    # per phase of one cycle: synchronised wall time, kernel launches, blocking
+    # host round trips (rank 0's view; the phases are collective)
+    phases = {}
+    if True:
+        lib.tmrgpu_profile_reset(ctx)
+
+        def phase(name, fn):
+            barrier()
+            l0, s0 = lib.tmrgpu_launch_count(ctx), lib.tmrgpu_sync_count(ctx)
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            phases[name] = {"ms": round(1e3 * (time.perf_counter() - t0), 3),
+                            "launches": int(lib.tmrgpu_launch_count(ctx) - l0),
+                            "host_round_trips": int(lib.tmrgpu_sync_count(ctx) - s0)}
+
+        pw = base.duplicate()
+        pdev = P(lib.tmr_b200_device_forest(pw._ptr))
+        phase("refine", lambda: lib.tmrgpu_refine_device(pdev, d_flags, 0, 30))
+        phase("balance", lambda: lib.tmrgpu_balance(pdev, cfg["corner"]))
+        if world > 1:
+            phase("repartition", lambda: lib.tmrgpu_repartition(pdev, -1))
+        phase("createNodes", lambda: lib.tmrgpu_create_nodes(pdev, cfg["order"], 1, knots))
+        del pw
+
     # the same cycle with the H2D of the flags inside the timed region
     def step_device_h2d():
         lib.tmrgpu_copy_h2d(ctx, d_flags, h_flags.ctypes.data, 4 * e_in)
@@ -752,6 +777,7 @@ def main():
             "kernel_launches_per_step": launches / args.steps,
             "blocking_host_round_trips_per_step": host_syncs / args.steps,
             "kernel_ms_per_step": sum(v["ms"] for v in prof.values()) / args.steps,
+            "phases_of_one_cycle": phases,
             "clocks": clocks,
             "roofline": roof,
             "cycle_compulsory_bytes": int(b_alg),

@@ -1038,6 +1038,11 @@ struct DepWinnerFn {
   u64 *win_edge;
   u64 *win_face;
   TMR_HD void operator()(i64 e) const {
+    const int n = kOrder ? kOrder : order;
+    run(e, conn + e * (n * n * n));
+  }
+  /* c: the element's node numbers (its conn row, possibly still in registers) */
+  TMR_HD void run(i64 e, const int *c) const {
     const int inf = info[e];
     if (!inf) return;
     const int n = kOrder ? kOrder : order;
@@ -1048,7 +1053,6 @@ struct DepWinnerFn {
     int fm, em;
     decode_info(id, inf, &fm, &em);
     const int bx = id & 1, by = (id >> 1) & 1, bz = id >> 2;
-    const int *c = conn + e * (n * n * n);
     TMR_UNROLL
     for (int kk = 0; kk < n; kk++) {
       TMR_UNROLL
@@ -1090,6 +1094,41 @@ struct DepWinnerFn {
   }
 };
 
+/* slot resolve with the winner pass of the dependent CSR fused in: the
+   element's node numbers go from registers straight into DepWinnerFn, which
+   saves a second 2.8 GB read of the connectivity */
+struct SlotResolveWin2Fn {
+  SlotResolve2Fn rs;
+  DepWinnerFn<2> win;
+  TMR_HD void operator()(i64 e) const {
+    u32 leaf[8];
+    rs.row(e, leaf);
+    win.run(e, reinterpret_cast<const int *>(leaf));
+  }
+};
+/* several ranks: elements with a corner outside the rank's range get their
+   last numbers from the B pass and are revisited by DepWinnerBFn */
+struct SlotResolveWin3Fn {
+  SlotResolve3Fn rs;
+  DepWinnerFn<2> win;
+  unsigned char *pending;
+  TMR_HD void operator()(i64 e) const {
+    u32 leaf[8];
+    if (rs.row(e, leaf)) {
+      win.run(e, reinterpret_cast<const int *>(leaf));
+    } else {
+      pending[e] = 1;
+    }
+  }
+};
+struct PendingWinnerFn { /* after BPlaceFn: the elements with a B corner */
+  const unsigned char *pending;
+  DepWinnerFn<2> win;
+  TMR_HD void operator()(i64 e) const {
+    if (pending[e]) win(e);
+  }
+};
+
 struct DepLenFn {
   const u64 *win_edge;
   const u64 *win_face;
@@ -1098,16 +1137,6 @@ struct DepLenFn {
     if (win_edge[d]) return (u32)order;
     if (win_face[d]) return (u32)(order * order);
     return 0;
-  }
-};
-
-struct DepPtrFn {
-  const u32 *off;
-  i64 nd;
-  u32 total;
-  int *dep_ptr;
-  TMR_HD void operator()(i64 d) const {
-    dep_ptr[d] = (d < nd) ? (int)off[d] : (int)total;
   }
 };
 
@@ -1267,6 +1296,7 @@ struct DepFillData {
   int *dep_conn;
   double *dep_weights;
   unsigned short *dep_code; /* compact form of ptr + weights (DepExpandJob) */
+  const double *wtab;       /* 1-D weight rows (DepWeightTableFn) */
   SlotLookup sl; /* one rank, slot construction: node numbers by position */
 
   KeyIndex node_ix;
@@ -1438,13 +1468,12 @@ struct DepFillFn : DepFillData {
       }
       const int bit = (id >> (ed >> 2)) & 1;
       dep_code[d] = (unsigned short)(kDepCodeEdge | (bit << 4) | k);
-      if (bernstein) {
-        /* reference :5364-5374 */
-        bernstein_subdivision_weights(order, (order - 1) * (bit - 1) + k,
-                                      dep_weights + ptr);
-      } else {
-        const double u = 1.0 * (bit - 1) + 0.5 * (1.0 + knots[k]);
-        lagrange_basis(order, u, knots, dep_weights + ptr);
+      {
+        /* the row was evaluated once by DepWeightTableFn (reference :5364-5374:
+           Lagrange values at u = (bit - 1) + (1 + knot[k]) / 2, or the Bernstein
+           subdivision row) */
+        const double *row = wtab + (size_t)(bit * order + k) * order;
+        for (int j = 0; j < order; j++) dep_weights[ptr + j] = row[j];
       }
     } else if (win_face[d]) {
       const u64 code = win_face[d] - 1;
@@ -1492,21 +1521,13 @@ struct DepFillFn : DepFillData {
       const int b1 = (f < 2) ? by : bx;
       const int b2 = (f < 4) ? bz : by;
       dep_code[d] = (unsigned short)((b1 << 9) | (ii << 5) | (b2 << 4) | jj);
-      double Nu[kOrder ? kOrder : kMaxOrder], Nv[kOrder ? kOrder : kMaxOrder];
-      if (bernstein) {
-        /* reference :5453-5473 */
-        bernstein_subdivision_weights(order, -(order - 1) + ii + (order - 1) * b1, Nu);
-        bernstein_subdivision_weights(order, -(order - 1) + jj + (order - 1) * b2, Nv);
-      } else {
-        double u = -1.0 + 0.5 * (1.0 + knots[ii]);
-        double v = -1.0 + 0.5 * (1.0 + knots[jj]);
-        u += 1.0 * b1;
-        v += 1.0 * b2;
-        lagrange_basis(order, u, knots, Nu);
-        lagrange_basis(order, v, knots, Nv);
-      }
-      for (int j = 0; j < order * order; j++) {
-        dep_weights[ptr + j] = Nu[j % order] * Nv[j / order];
+      /* tensor product of two tabulated rows (reference :5453-5473) */
+      const double *Nu = wtab + (size_t)((2 + b1) * order + ii) * order;
+      const double *Nv = wtab + (size_t)((2 + b2) * order + jj) * order;
+      for (int q = 0; q < order; q++) {
+        for (int p = 0; p < order; p++) {
+          dep_weights[ptr + p + q * order] = Nu[p] * Nv[q];
+        }
       }
     }
   }
@@ -2218,7 +2239,11 @@ struct SlotState { /* outlives build_nodes_slots: the dependent CSR looks nodes 
   DBuf<RankEntry> rank_tab;
   DBuf<u32> rank_cells;
   SlotLookup lookup;
-  SlotState() { lookup.on = 0; }
+  /* winners of the dependent stencils (DepWinnerFn), found while the
+     connectivity was resolved */
+  DBuf<u64> win_edge, win_face;
+  int winner_done;
+  SlotState() : winner_done(0) { lookup.on = 0; }
 };
 
 inline int build_nodes_slots(Forest &f, NodeData &nd,
@@ -2298,7 +2323,15 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     const i64 Nn = (i64)(tot & 0x7fffffffULL), Nd = (i64)(tot >> 31);
     SlotResolve2Fn rs = {slotinfo.get(), slot8.get(),
                          reinterpret_cast<u32 *>(nd.conn.get())};
-    launch(ctx, E, rs, "nodes_slot_resolve");
+    st.win_edge.alloc(ctx, Nd);
+    st.win_face.alloc(ctx, Nd);
+    dev_zero(ctx, st.win_edge.get(), (size_t)Nd * sizeof(u64));
+    dev_zero(ctx, st.win_face.get(), (size_t)Nd * sizeof(u64));
+    DepWinnerFn<2> win = {f.keys.get(), f.info.get(), f.fmt, 2, nd.conn.get(),
+                          st.win_edge.get(), st.win_face.get()};
+    SlotResolveWin2Fn rw = {rs, win};
+    launch(ctx, E, rw, "nodes_slot_resolve");
+    st.winner_done = 1;
     /* node_keys / node_num (1.5 GB at 86 M octants) are not needed by anything
        createNodes produces: they are written on first request from the
        per-leaf counts kept here (ensure_node_arrays) */
@@ -2490,12 +2523,24 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
                     nd.node_num.get(), nlow};
   launch(ctx, E, kf, "nodes_slot_keys");
   SlotResolve3Fn rs = {sn, slot8.get(), reinterpret_cast<u32 *>(nd.conn.get())};
-  launch(ctx, E, rs, "nodes_slot_resolve");
+  st.win_edge.alloc(ctx, Nd);
+  st.win_face.alloc(ctx, Nd);
+  dev_zero(ctx, st.win_edge.get(), (size_t)Nd * sizeof(u64));
+  dev_zero(ctx, st.win_face.get(), (size_t)Nd * sizeof(u64));
+  DepWinnerFn<2> win = {f.keys.get(), f.info.get(), f.fmt, 2, nd.conn.get(),
+                        st.win_edge.get(), st.win_face.get()};
+  DBuf<unsigned char> pending(ctx, E);
+  dev_zero(ctx, pending.get(), (size_t)E);
+  SlotResolveWin3Fn rw = {rs, win, pending.get()};
+  launch(ctx, E, rw, "nodes_slot_resolve");
   if (nb > 0) {
     BPlaceFn bp = {b_key.get(), b_pay.get(), b_run.get(), b_num.get(), nlow, NA,
                    nd.node_keys.get(), nd.node_num.get(), nd.conn.get()};
     launch(ctx, nb, bp, "nodes_b_place");
+    PendingWinnerFn pw = {pending.get(), win};
+    launch(ctx, E, pw, "nodes_dep_winner_b");
   }
+  st.winner_done = 1;
   nd.num_candidates = nb;
   *Nn_out = Nn;
   return 1;
@@ -3007,10 +3052,19 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   /* 5. dependent-node CSR */
   nd.dep_ptr.alloc(ctx, Nd + 1);
   if (Nd > 0) {
-    DBuf<u64> win_edge(ctx, Nd), win_face(ctx, Nd);
-    dev_zero(ctx, win_edge.get(), (size_t)Nd * sizeof(u64));
-    dev_zero(ctx, win_face.get(), (size_t)Nd * sizeof(u64));
-    if (order == 2) {
+    DBuf<u64> win_edge, win_face;
+    if (slot_state.winner_done) {
+      win_edge.swap(slot_state.win_edge);
+      win_face.swap(slot_state.win_face);
+    } else {
+      win_edge.alloc(ctx, Nd);
+      win_face.alloc(ctx, Nd);
+      dev_zero(ctx, win_edge.get(), (size_t)Nd * sizeof(u64));
+      dev_zero(ctx, win_face.get(), (size_t)Nd * sizeof(u64));
+    }
+    if (slot_state.winner_done) {
+      /* done inside the slot resolve */
+    } else if (order == 2) {
       DepWinnerFn<2> win = {f.keys.get(), f.info.get(),   f.fmt,         order,
                             nd.conn.get(), win_edge.get(), win_face.get()};
       launch(ctx, E, win, "nodes_dep_winner");
@@ -3023,11 +3077,12 @@ inline int create_nodes(Forest &f, int order, int interp_type,
                             nd.conn.get(), win_edge.get(), win_face.get()};
       launch(ctx, E, win, "nodes_dep_winner");
     }
-    DBuf<u32> off(ctx, Nd);
+    /* stencil lengths -> dep_ptr, written by the scan itself */
     DepLenFn len = {win_edge.get(), win_face.get(), order};
-    const u64 nnz = scan_counts(ctx, Nd, len, off.get(), "nodes_dep_len_scan");
-    DepPtrFn dp = {off.get(), Nd, (u32)nnz, nd.dep_ptr.get()};
-    launch(ctx, Nd + 1, dp, "nodes_dep_ptr");
+    const u64 nnz = scan_counts(ctx, Nd, len, reinterpret_cast<u32 *>(nd.dep_ptr.get()),
+                                "nodes_dep_len_scan");
+    FillIntFn last = {nd.dep_ptr.get() + Nd, (int)nnz};
+    launch(ctx, 1, last, "nodes_dep_ptr");
     nd.dep_nnz = (i64)nnz;
     nd.dep_conn.alloc(ctx, (i64)nnz);
     nd.dep_weights.alloc(ctx, (i64)nnz);
@@ -3068,9 +3123,10 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     fill.dep_weights = nd.dep_weights.get();
     nd.dep_code.alloc(ctx, Nd);
     fill.dep_code = nd.dep_code.get();
-    /* the 1-D weight rows the codes index, computed by the same device
-       arithmetic as the stencils themselves */
+    /* the 1-D weight rows of the stencils (and of the codes' host-side
+       expansion), evaluated once */
     nd.dep_wtab.alloc(ctx, (i64)4 * order * order);
+    fill.wtab = nd.dep_wtab.get();
     {
       DepWeightTableFn wt = {order, bernstein, {0}, nd.dep_wtab.get()};
       for (int i = 0; i < kMaxOrder; i++) wt.knots[i] = nd.knots[i];

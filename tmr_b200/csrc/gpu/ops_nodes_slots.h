@@ -689,8 +689,8 @@ struct SlotResolve2Fn {
   const SlotInfo2 *slotinfo;
   const unsigned char *slot8;
   u32 *conn;
-  TMR_HD void operator()(i64 e) const {
-    u32 leaf[8];
+  /* the element's 8 node numbers, also left in `leaf` for a fused consumer */
+  TMR_HD void row(i64 e, u32 *leaf) const {
     load8_u32(conn + e * 8, leaf);
     const u64 ords = *reinterpret_cast<const u64 *>(slot8 + e * 8);
     TMR_UNROLL
@@ -699,6 +699,10 @@ struct SlotResolve2Fn {
       leaf[c] = (u32)slot_node_number(si, (int)((ords >> (8 * c)) & 31));
     }
     store8_u32(conn + e * 8, leaf);
+  }
+  TMR_HD void operator()(i64 e) const {
+    u32 leaf[8];
+    row(e, leaf);
   }
 };
 
@@ -937,17 +941,26 @@ struct SlotResolve3Fn {
   SlotNumbers sn;
   const unsigned char *slot8;
   u32 *conn;
-  TMR_HD void operator()(i64 e) const {
-    u32 leaf[8];
+  /* returns false when a corner is still to be placed by the B pass */
+  TMR_HD bool row(i64 e, u32 *leaf) const {
     load8_u32(conn + e * 8, leaf);
     const u64 ords = *reinterpret_cast<const u64 *>(slot8 + e * 8);
+    bool complete = true;
     TMR_UNROLL
     for (int c = 0; c < 8; c++) {
-      if (leaf[c] == kConnB) continue;
+      if (leaf[c] == kConnB) {
+        complete = false;
+        continue;
+      }
       const SlotInfoM s = load_slotinfom(sn.si + leaf[c]);
       leaf[c] = (u32)sn.number(s, (i64)leaf[c], (int)((ords >> (8 * c)) & 31));
     }
     store8_u32(conn + e * 8, leaf);
+    return complete;
+  }
+  TMR_HD void operator()(i64 e) const {
+    u32 leaf[8];
+    row(e, leaf);
   }
 };
 
