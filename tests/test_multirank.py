@@ -170,3 +170,31 @@ def test_find_enclosing_names_the_owner_of_a_miss(ranks, emu_lib, ref_lib):
     a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
     b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
     multirank.compare_find_enclosing(a, b, ranks)
+
+
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_multirank_device_views(ranks, emu_lib):
+    """Several ranks: the node arrays rebuilt on request from the slot state
+    (node numbers by local node, tmrgpu_assembler_views) agree with what the
+    getters return, which test_multirank_matches_reference pins to the oracle."""
+    conn = util.box_conn()
+
+    def body(lib, rank):
+        f = multirank.OctForest(order=2, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(1)
+        f.repartition()
+        for p in range(2):
+            f.refine(util.synth_flags(f.getOctants().as_array(), 2024 + p, 30))
+            f.balance(1)
+            f.repartition()
+        res = util.node_results(f)
+        v = f.assemblerViews()
+        assert np.array_equal(np.sort(v["node_numbers"]), res["node_numbers"])
+        assert np.array_equal(v["conn"].reshape(-1, 8), res["conn"].reshape(-1, 8))
+        assert np.array_equal(v["dep_ptr"], res["dep"][0])
+        assert np.array_equal(v["dep_conn"], res["dep"][1])
+        return len(v["node_numbers"])
+
+    out = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    assert all(n > 0 for n in out)

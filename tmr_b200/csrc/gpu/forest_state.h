@@ -101,6 +101,9 @@ struct NodeData {
      node_num are then built on first request (ensure_node_arrays): createNodes itself
      and the host getters never need them */
   DBuf<SlotInfo2> slot_info;
+  /* several ranks, slot construction: what node_keys / node_num are rebuilt from
+     (SlotMulti, ops_nodes.h) */
+  std::shared_ptr<void> slot_multi;
   DBuf<int> elem_ptr;   /* [num_elements + 1] order^3 * i, built on request (tmrgpu_assembler_views) */
   DBuf<double> dep_weights;
   DBuf<unsigned short> dep_code; /* [num_dep_nodes] stencil codes (DepExpandJob) */
@@ -164,6 +167,7 @@ struct NodeData {
     dep_wtab.reset();
     elem_ptr.reset();
     slot_info.reset();
+    slot_multi.reset();
     ext_numbers.reset();
     ext_numbers_valid = false;
     node_range.clear();

@@ -1298,6 +1298,7 @@ struct DepFillData {
   unsigned short *dep_code; /* compact form of ptr + weights (DepExpandJob) */
   const double *wtab;       /* 1-D weight rows (DepWeightTableFn) */
   SlotLookup sl; /* one rank, slot construction: node numbers by position */
+  SlotLookupM slm; /* the same on several ranks */
 
   KeyIndex node_ix;
   /* order 2 shortcut: in a complete family the parent's corner c is corner c
@@ -1405,6 +1406,7 @@ struct DepFillFn : DepFillData {
   TMR_HD int lookup(i32 block, i32 x, i32 y, i32 z, int label) const {
     transform_node(t, &block, &x, &y, &z, -1, NULL, NULL);
     if (sl.on) return sl.number(block, x, y, z);
+    if (slm.on) return slm.number(block, x, y, z);
     const i64 idx = node_ix.find(node_keys, nfmt.encode(block, x, y, z, label));
     return idx >= 0 ? node_num[idx] : 0;
   }
@@ -1569,6 +1571,8 @@ struct NumberRangeFn {
   TMR_HD void operator()(i64 i) const { out[i] = first + (int)i; }
 };
 
+inline int ensure_node_arrays(Forest &f);
+
 /* every local node number, ascending, in a device array */
 inline int build_sorted_numbers(Forest &f, DBuf<int> &out) {
   Ctx &ctx = *f.ctx;
@@ -1584,6 +1588,7 @@ inline int build_sorted_numbers(Forest &f, DBuf<int> &out) {
     launch(ctx, n, r, "nodes_number_range");
     return 0;
   }
+  if (ensure_node_arrays(f)) return 1;
   DBuf<u64> k(ctx, n), k_alt(ctx, n);
   DBuf<u32> v0, v1;
   NumToKeyFn a = {nd.node_num.get(), k.get()};
@@ -2184,25 +2189,15 @@ struct BLowCountFn {
   i64 *out;
   TMR_HD void operator()(i64) const { out[0] = lower_bound_u64(ukeys, n, first_key); }
 };
-/* B nodes below the rank's range keep their run index, the others follow the
-   NA slot nodes; their connectivity entries get the final numbers */
+/* connectivity entries of the corners outside the rank's range: the final
+   numbers of their B nodes */
 struct BPlaceFn {
-  const u64 *k;
   const u32 *pay;
   const u32 *run_of;
   const int *unum; /* number of every unique B node */
-  i64 nlow, NA;
-  u64 *node_keys;
-  int *node_num;
   int *conn;
   TMR_HD void operator()(i64 i) const {
-    const i64 run = (i64)run_of[i];
-    const i64 idx = run < nlow ? run : run + NA;
-    if (i == 0 || k[i] != k[i - 1]) {
-      node_keys[idx] = k[i];
-      node_num[idx] = unum[run];
-    }
-    if (pay[i] != kConnB) conn[pay[i] & ~kPayDep] = unum[run];
+    if (pay[i] != kConnB) conn[pay[i] & ~kPayDep] = unum[run_of[i]];
   }
 };
 struct OwnerFromReplyFn {
@@ -2220,12 +2215,37 @@ struct BHomeDestFn {
    connectivity comes out as final node NUMBERS (node_keys, node_num, the
    counts and node_range of `nd` are filled too).  Several ranks: `om_n` maps
    node positions to their home rank. */
-/* node_keys and node_num on request (one rank, slot construction) */
+/* several ranks: the state of the slot construction node_keys / node_num are
+   rebuilt from on request, and the dependent stencils look nodes up in */
+struct SlotMulti {
+  DBuf<u64> mc, slotinfo1, xref, b_ukeys;
+  DBuf<SlotInfoM> slotinfo;
+  DBuf<int> xnum, b_num;
+  DBuf<RankEntry> rank_tab;
+  DBuf<u32> rank_cells;
+  SlotNumbers sn;
+  SlotView v;
+  i64 nbu, nlow, NA;
+};
+
+/* node_keys and node_num on request (slot construction) */
 inline int ensure_node_arrays(Forest &f) {
   NodeData &nd = f.nodes;
   Ctx &ctx = *f.ctx;
   if (!nd.valid) return 1;
   if (nd.num_local_nodes == 0 || nd.node_num.size() == nd.num_local_nodes) return 0;
+  if (nd.slot_multi) {
+    const SlotMulti &sm = *static_cast<const SlotMulti *>(nd.slot_multi.get());
+    nd.node_keys.alloc(ctx, nd.num_local_nodes);
+    nd.node_num.alloc(ctx, nd.num_local_nodes);
+    SlotKeys3Fn kf = {f.keys.get(), f.fmt, sm.slotinfo1.get(), sm.sn, nd.node_keys.get(),
+                      nd.node_num.get(), sm.nlow};
+    launch(ctx, f.n, kf, "nodes_slot_keys");
+    BNodeArraysFn bf = {sm.b_ukeys.get(), sm.b_num.get(), sm.nlow, sm.NA,
+                        nd.node_keys.get(), nd.node_num.get()};
+    launch(ctx, sm.nbu, bf, "nodes_b_keys");
+    return 0;
+  }
   if (nd.slot_info.size() != f.n) return 1;
   nd.node_keys.alloc(ctx, nd.num_local_nodes);
   nd.node_num.alloc(ctx, nd.num_local_nodes);
@@ -2239,11 +2259,15 @@ struct SlotState { /* outlives build_nodes_slots: the dependent CSR looks nodes 
   DBuf<RankEntry> rank_tab;
   DBuf<u32> rank_cells;
   SlotLookup lookup;
+  SlotLookupM lookup_m;
   /* winners of the dependent stencils (DepWinnerFn), found while the
      connectivity was resolved */
   DBuf<u64> win_edge, win_face;
   int winner_done;
-  SlotState() : winner_done(0) { lookup.on = 0; }
+  SlotState() : winner_done(0) {
+    lookup.on = 0;
+    lookup_m.on = 0;
+  }
 };
 
 inline int build_nodes_slots(Forest &f, NodeData &nd,
@@ -2516,12 +2540,8 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     nd.ext_numbers.set_size(nx + nxb);
     nd.ext_numbers_valid = (Nd + nown + nx + nxb == Nn);
   }
-  /* ---- node keys, numbers, connectivity ---- */
-  nd.node_keys.alloc(ctx, Nn);
-  nd.node_num.alloc(ctx, Nn);
-  SlotKeys3Fn kf = {f.keys.get(), f.fmt, slotinfo1.get(), sn, nd.node_keys.get(),
-                    nd.node_num.get(), nlow};
-  launch(ctx, E, kf, "nodes_slot_keys");
+  /* ---- connectivity (node_keys / node_num follow on request:
+     ensure_node_arrays) ---- */
   SlotResolve3Fn rs = {sn, slot8.get(), reinterpret_cast<u32 *>(nd.conn.get())};
   st.win_edge.alloc(ctx, Nd);
   st.win_face.alloc(ctx, Nd);
@@ -2534,13 +2554,40 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
   SlotResolveWin3Fn rw = {rs, win, pending.get()};
   launch(ctx, E, rw, "nodes_slot_resolve");
   if (nb > 0) {
-    BPlaceFn bp = {b_key.get(), b_pay.get(), b_run.get(), b_num.get(), nlow, NA,
-                   nd.node_keys.get(), nd.node_num.get(), nd.conn.get()};
+    BPlaceFn bp = {b_pay.get(), b_run.get(), b_num.get(), nd.conn.get()};
     launch(ctx, nb, bp, "nodes_b_place");
     PendingWinnerFn pw = {pending.get(), win};
     launch(ctx, E, pw, "nodes_dep_winner_b");
   }
   st.winner_done = 1;
+  /* keep what the node arrays and the stencil look-ups are built from */
+  {
+    std::shared_ptr<SlotMulti> keep(new SlotMulti());
+    SlotMulti &sm = *keep;
+    sm.mc.swap(mc);
+    sm.slotinfo1.swap(slotinfo1);
+    sm.slotinfo.swap(slotinfo);
+    sm.xref.swap(xref);
+    sm.xnum.swap(xnum);
+    sm.b_ukeys.swap(b_ukeys);
+    sm.b_num.swap(b_num);
+    sm.rank_tab.swap(st.rank_tab);
+    sm.rank_cells.swap(st.rank_cells);
+    sm.sn = sn;
+    sm.v = v;
+    sm.v.fail = NULL;
+    sm.nbu = nbu;
+    sm.nlow = nlow;
+    sm.NA = NA;
+    st.lookup_m.on = 1;
+    st.lookup_m.v = sm.v;
+    st.lookup_m.sn = sm.sn;
+    st.lookup_m.nfmt = nd.nfmt;
+    st.lookup_m.b_ukeys = sm.b_ukeys.get();
+    st.lookup_m.nbu = nbu;
+    st.lookup_m.b_num = sm.b_num.get();
+    nd.slot_multi = keep;
+  }
   nd.num_candidates = nb;
   *Nn_out = Nn;
   return 1;
@@ -3089,7 +3136,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     DBuf<u32> node_index_store;
     DepFillData fill;
     fill.sl = slot_state.lookup;
-    if (!fill.sl.on) {
+    fill.slm = slot_state.lookup_m;
+    if (!fill.sl.on && !fill.slm.on) {
       fill.node_ix = build_key_index(ctx, nd.node_keys.get(), nd.node_keys.size(),
                                      (u64)f.nblocks << nd.nfmt.pos_bits(),
                                      node_index_store);

@@ -905,6 +905,45 @@ struct LookupSlotNumberFn {
     }
   }
 };
+/* several ranks: number of the node at a canonical position (the dependent
+   stencils' parent nodes), from the slots or, outside the rank's range, from
+   the B nodes */
+struct SlotLookupM {
+  int on;
+  SlotView v;
+  SlotNumbers sn;
+  NodeFmt nfmt;
+  const u64 *b_ukeys;
+  i64 nbu;
+  const int *b_num;
+  TMR_HD int number(i32 b, i32 x, i32 y, i32 z) const {
+    const u64 loc = v.locate_xyz(b, x, y, z);
+    if (loc < kLocFail) {
+      const i64 leaf = (i64)(loc >> 5);
+      const int ord = (int)(loc & 31);
+      if (!(((u32)v.mc[leaf] >> ord) & 1u)) return 0;
+      return sn.number(load_slotinfom(sn.si + leaf), leaf, ord);
+    }
+    if (loc == kLocB) {
+      const i64 r = find_u64(b_ukeys, nbu, nfmt.encode(b, x, y, z, 0));
+      return r >= 0 ? b_num[r] : 0;
+    }
+    return 0;
+  }
+};
+/* keys and numbers of the B nodes, at their places in node order */
+struct BNodeArraysFn {
+  const u64 *b_ukeys;
+  const int *b_num;
+  i64 nlow, NA;
+  u64 *node_keys;
+  int *node_num;
+  TMR_HD void operator()(i64 r) const {
+    const i64 idx = r < nlow ? r : r + NA;
+    node_keys[idx] = b_ukeys[r];
+    node_num[idx] = b_num[r];
+  }
+};
 struct StoreBExternalFn {
   const u32 *node;
   const int *number;
