@@ -230,6 +230,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--passes", type=int, default=FULL["passes"],
                     help="refinement passes of the recipe (4 = the named ~86M config)")
+    ap.add_argument("--pct", type=int, default=None,
+                    help="refinement percentage of the recipe (default: 35 for c2, 30 for c4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the parity gate that runs before the timed region")
@@ -330,6 +332,8 @@ def main():
     if args.workload == "c4":
         cfg["corner"] = 1
         cfg["pct"] = 30
+    if args.pct is not None:
+        cfg["pct"] = args.pct
     knots = (ctypes.c_double * 2)(-1.0, 1.0)
 
     # ---- build-up: everything before the timed cycle, all on the device ----
@@ -517,6 +521,7 @@ def main():
     work, wdev = last
     fp_final = fingerprint(wdev)
     pinned = (args.workload == "c2" and cfg["passes"] == FULL["passes"] and
+              cfg["pct"] == FULL["pct"] and
               (world == 1 or args.strong) and args.nbz_per_gpu == 8)
     if pinned:
         ok = all(fp_final[k] == C2_PIN[k] for k in C2_PIN)

@@ -57,6 +57,7 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None, a
         coarse.createNodes()
         sync()
         t2 = time.perf_counter()
+        t_nodes_coarse = t2 - t1
         t_dev = None
         if device_interp is not None:
             # device-resident CSR only (no D2H, no per-row addInterp hand-off)
@@ -68,7 +69,7 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None, a
             t_dev = time.perf_counter() - t_a
             t2 = time.perf_counter()
         t_bulk = None
-        if api == "bulk" or api is True:
+        if (api == "bulk" or api is True) and hasattr(lib, "tmr_b200_create_interpolation_csr"):
             # the whole CSR in one hand-off (tmr_b200_create_interpolation_csr)
             tb = time.perf_counter()
             rows, rowp, cols, vals = fine.createInterpolationCSR(coarse)
@@ -81,7 +82,7 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None, a
             sync()
             t3 = time.perf_counter()
             rows, rowp, cols, vals = vec.get()
-        elif api == "bulk":
+        elif api == "bulk" and t_bulk is not None:
             t3 = t2
         else:
             t3 = t2
@@ -98,7 +99,7 @@ def hierarchy(lib, level, passes, pct, sync, device_flags, device_interp=None, a
             "level": k, "fine_order": fine.getMeshOrder(), "coarse_order": coarse.getMeshOrder(),
             "fine_octants": fine.getNumOctants(), "coarse_octants": coarse.getNumOctants(),
             "rows": int(len(rows)), "nnz": int(len(cols)),
-            "create_nodes_fine_s": t1 - t0, "create_nodes_coarse_s": t2 - t1,
+            "create_nodes_fine_s": t1 - t0, "create_nodes_coarse_s": t_nodes_coarse,
             "create_interp_s": (t3 - t2) if api is True else None,
             "rows_per_s": (len(rows) / max(t3 - t2, 1e-9)) if api is True else None,
             "device_csr_s": t_dev, "api_bulk_csr_s": t_bulk,

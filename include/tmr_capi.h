@@ -156,6 +156,18 @@ int tmrc_hash_exercise(const tmrc_octant *in, int n, int use_node_index,
    (reference src/TMROctForest.cpp:331-337) */
 tmrc_forest tmrc_forest_create_self(int mesh_order, int interp_type);
 
+/* ---- geometry without the CAD layer (node-location tests) --------------------
+   Attach a topology whose volumes are trilinear hexahedra through the given
+   corner points (xpts: num_nodes x (x,y,z)); edges and faces are numbered as
+   setConnectivity numbers them.  Implemented per backend: with the drop-in's
+   TMRTrilinearTopology (tmr_b200/csrc/host/tmr_b200_ext.cpp), and for the
+   reference with a stand-in topology in oracle/shim/stubs.cpp whose volumes
+   evaluate the same trilinear expression.  Returns 0 on success. */
+int tmrc_set_trilinear_topology(tmrc_forest f, int num_nodes, const int *conn,
+                                int num_blocks, const double *xpts);
+/* getPoints (reference :1476-1481): borrowed pointer to num x (x,y,z) */
+int tmrc_get_points(tmrc_forest f, const double **xyz);
+
 #ifdef __cplusplus
 }
 #endif

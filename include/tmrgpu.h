@@ -186,6 +186,15 @@ int tmrgpu_interp_device_views(tmrgpu_forest *fine, const int **rows,
                                const int **rowp, const int **cols,
                                const double **vals);
 
+/* evaluateNodeLocations (reference :5524-5675) for forests whose trees are
+   trilinear hexahedra: corners = [nblocks][8][3] (tree corner c: bit0 x, bit1
+   y, bit2 z), X = [num_local_nodes][3] in the order of the sorted node numbers.
+   Every node takes the location evaluated through the first element and local
+   slot (in element order) that reference it, exactly the reference's flags[]
+   rule, at the parametric point u + 0.5 d (1 + knot[i]) of that element. */
+int tmrgpu_eval_trilinear_points(tmrgpu_forest *f, const double *corners,
+                                 double *X);
+
 /* createInterpolation (reference :6611-6793) between two forests that both
    have nodes.  Builds the CSR on the device; rows are emitted in the
    reference's call order (first touch in element order). */

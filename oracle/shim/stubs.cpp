@@ -1,14 +1,26 @@
 /*
   oracle/shim/stubs.cpp -- TEST INFRASTRUCTURE ONLY.
-  Link stubs for symbols the reference forest sources reference but never
-  reach when the forest is driven through setConnectivity (no CAD topology):
-  TMRTopology getters (declared reference src/TMRTopology.h:383-400) and two
-  LAPACK routines (reference src/tmrlapack.h:28-47, Bernstein+topology branch
-  of evaluateNodeLocations only).
+  Link definitions for the CAD-layer symbols the reference forest sources
+  reference (reference src/TMRTopology.h:251-280,382-400; their own
+  definitions live in src/TMRTopology.cpp, which needs the whole geometry
+  layer and is not compiled here) and two LAPACK routines (reference
+  src/tmrlapack.h:28-47, Bernstein+topology branch of evaluateNodeLocations
+  only, never reached by the tests).
+
+  TMRTopology is served by a stand-in: a hexahedral super-mesh whose volumes
+  are trilinear images of the unit cube (tmrc_set_trilinear_topology,
+  include/tmr_capi.h), so that the UNMODIFIED reference
+  TMROctForest::evaluateNodeLocations (src/TMROctForest.cpp:5524-5675) can be
+  run as the oracle of the node-location path.  getFace/getEdge/getVertex (name
+  queries) stay unreachable.
 */
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <map>
+#include <vector>
+
+#include "TMROctForest.h"
 #include "TMRTopology.h"
 
 static void unreachable(const char *what) {
@@ -16,16 +28,131 @@ static void unreachable(const char *what) {
   abort();
 }
 
-void TMRTopology::getVolume(int, TMRVolume **) { unreachable("getVolume"); }
+/* ---- TMRVolume: the base-class members of reference src/TMRTopology.cpp:910-968
+   the vtable needs ---- */
+TMRVolume::TMRVolume(int, TMRFace **) {
+  num_faces = 0;
+  faces = NULL;
+  mesh = NULL;
+}
+TMRVolume::~TMRVolume() {}
+void TMRVolume::getRange(double *umin, double *vmin, double *wmin, double *umax,
+                         double *vmax, double *wmax) {
+  *umin = *vmin = *wmin = 0.0;
+  *umax = *vmax = *wmax = 0.0;
+}
+int TMRVolume::evalPoint(double, double, double, TMRPoint *X) {
+  X->zero();
+  return 1;
+}
+
+namespace {
+
+/* trilinear image of (u,v,w) through 8 corners (corner c: bit0 x, bit1 y, bit2
+   z); the same expression, in the same order, as tmrgpu::trilinear_point
+   (tmr_b200/csrc/gpu/common.h) -- the geometry is test input, both sides must
+   evaluate it identically for the comparison to be about the forest */
+class TestTrilinearVolume : public TMRVolume {
+ public:
+  explicit TestTrilinearVolume(const double *c) : TMRVolume(0, NULL) {
+    for (int i = 0; i < 24; i++) X[i] = c[i];
+  }
+  int evalPoint(double u, double v, double w, TMRPoint *P) {
+    const double a[2] = {1.0 - u, u}, b[2] = {1.0 - v, v}, c[2] = {1.0 - w, w};
+    double p[3] = {0.0, 0.0, 0.0};
+    for (int k = 0; k < 8; k++) {
+      const double n = (a[k & 1] * b[(k >> 1) & 1]) * c[k >> 2];
+      p[0] += n * X[3 * k];
+      p[1] += n * X[3 * k + 1];
+      p[2] += n * X[3 * k + 2];
+    }
+    P->x = p[0];
+    P->y = p[1];
+    P->z = p[2];
+    return 0;
+  }
+  double X[24];
+};
+
+struct TopoData {
+  int nn, ne, nf, nb;
+  std::vector<int> bc, bec, bfc;
+  std::vector<TMRVolume *> vols;
+};
+std::map<const TMRTopology *, TopoData *> g_topos;
+
+TopoData *data_of(const TMRTopology *t) {
+  std::map<const TMRTopology *, TopoData *>::iterator it = g_topos.find(t);
+  if (it == g_topos.end()) unreachable("TMRTopology without stand-in data");
+  return it->second;
+}
+
+}  // namespace
+
+/* the stand-in never touches the real class's members (geo, the volume / face
+   / edge maps): every getter below answers from TopoData */
+TMRTopology::TMRTopology(MPI_Comm, TMRModel *) {}
+TMRTopology::~TMRTopology() {
+  std::map<const TMRTopology *, TopoData *>::iterator it = g_topos.find(this);
+  if (it != g_topos.end()) {
+    for (size_t i = 0; i < it->second->vols.size(); i++) it->second->vols[i]->decref();
+    delete it->second;
+    g_topos.erase(it);
+  }
+}
+void TMRTopology::getVolume(int i, TMRVolume **v) { *v = data_of(this)->vols[i]; }
 void TMRTopology::getFace(int, TMRFace **) { unreachable("getFace"); }
 void TMRTopology::getEdge(int, TMREdge **) { unreachable("getEdge"); }
 void TMRTopology::getVertex(int, TMRVertex **) { unreachable("getVertex"); }
-void TMRTopology::getConnectivity(int *, int *, int *, int *, const int **,
-                                  const int **, const int **) {
-  unreachable("getConnectivity");
+void TMRTopology::getConnectivity(int *nnodes, int *nedges, int *nfaces, int *nvolumes,
+                                  const int **volume_nodes, const int **volume_edges,
+                                  const int **volume_faces) {
+  TopoData *d = data_of(this);
+  *nnodes = d->nn;
+  *nedges = d->ne;
+  *nfaces = d->nf;
+  *nvolumes = d->nb;
+  *volume_nodes = d->bc.data();
+  *volume_edges = d->bec.data();
+  *volume_faces = d->bfc.data();
 }
 
 extern "C" {
+/* include/tmr_capi.h */
+int tmrc_set_trilinear_topology(void *f, int num_nodes, const int *conn,
+                                int num_blocks, const double *xpts) {
+  TMROctForest *forest = static_cast<TMROctForest *>(f);
+  /* edge and face numbering as the reference's own setConnectivity derives it */
+  TMROctForest *tmp = new TMROctForest(MPI_COMM_SELF);
+  tmp->incref();
+  tmp->setConnectivity(num_nodes, conn, num_blocks);
+  int nb, nf, ne, nn;
+  const int *bc, *bfc, *bec, *ids;
+  tmp->getConnectivity(&nb, &nf, &ne, &nn, &bc, &bfc, &bec, &ids);
+  TopoData *d = new TopoData();
+  d->nn = nn;
+  d->ne = ne;
+  d->nf = nf;
+  d->nb = nb;
+  d->bc.assign(bc, bc + 8 * nb);
+  d->bec.assign(bec, bec + 12 * nb);
+  d->bfc.assign(bfc, bfc + 6 * nb);
+  for (int b = 0; b < nb; b++) {
+    double c[24];
+    for (int k = 0; k < 8; k++) {
+      for (int a = 0; a < 3; a++) c[3 * k + a] = xpts[3 * conn[8 * b + k] + a];
+    }
+    TMRVolume *v = new TestTrilinearVolume(c);
+    v->incref();
+    d->vols.push_back(v);
+  }
+  tmp->decref();
+  TMRTopology *topo = new TMRTopology(MPI_COMM_SELF, NULL);
+  g_topos[topo] = d;
+  forest->setTopology(topo);
+  return 0;
+}
+
 void dgetrf_(int *, int *, double *, int *, int *, int *) {
   unreachable("dgetrf_");
 }

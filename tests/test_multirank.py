@@ -198,3 +198,33 @@ def test_multirank_device_views(ranks, emu_lib):
 
     out = multirank.run_thread_ranks(emu_lib, ranks, body, False)
     assert all(n > 0 for n in out)
+
+
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_multirank_node_locations(ranks, emu_lib, ref_lib):
+    """getPoints on several ranks (evaluateNodeLocations, reference
+    src/TMROctForest.cpp:5524-5675): each rank's X array, in the order of its
+    own sorted node numbers, against the same rank of the reference."""
+    conn = util.box_conn()
+    n = int(np.max(conn)) + 1
+    xpts = (np.random.default_rng(3).uniform(-1, 1, (n, 3)) +
+            2.5 * np.arange(n)[:, None] * np.array([1.0, -0.4, 0.25]))
+
+    def body(lib, rank):
+        f = multirank.OctForest(order=2, lib=lib)
+        f.setTrilinearTopology(conn, xpts)
+        f.createTrees(1)
+        f.repartition()
+        for p in range(2):
+            f.refine(util.synth_flags(f.getOctants().as_array(), 2024 + p, 30))
+            f.balance(0)
+            f.repartition()
+        f.createNodes()
+        return f.getNodeNumbers().copy(), f.getPoints()
+
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    for r in range(ranks):
+        assert np.array_equal(a[r][0], b[r][0]), r
+        assert len(a[r][1]) == len(a[r][0]) > 0
+        assert np.array_equal(a[r][1], b[r][1]), r

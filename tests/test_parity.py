@@ -571,3 +571,50 @@ def test_device_views_hold_what_the_getters_return(order, impl, ref_lib):
     assert np.array_equal(rows_a, rows_b) and np.array_equal(rowp_a, rowp_b)
     assert np.array_equal(cols_a, cols_b)
     np.testing.assert_allclose(vals_b, vals_a, rtol=1e-12, atol=1e-300)
+
+
+def _warped_points(conn, seed=11):
+    """physical locations for the super-mesh nodes: the 7-tree box layout of
+    reference examples/parallel/octant_test.cpp:47-50 is only topological here;
+    any injective placement will do for a trilinear geometry"""
+    n = int(np.max(conn)) + 1
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, (n, 3)) + 3.0 * np.arange(n)[:, None] * np.array([1.0, 0.3, -0.2])
+
+
+@pytest.mark.parametrize("order,conn_name", [(2, "box7"), (3, "box7"), (4, "connector15"),
+                                             (2, "butterfly2")])
+def test_node_locations(order, conn_name, impl, ref_lib):
+    """getPoints with a topology = evaluateNodeLocations
+    (reference src/TMROctForest.cpp:5524-5675): every local node evaluated
+    through the FIRST element and slot that reference it.  The oracle runs the
+    unmodified reference loop over a stand-in topology of trilinear volumes
+    (oracle/shim/stubs.cpp); the drop-in evaluates the same volumes on the
+    device.  Bit-exact: both sides evaluate the identical trilinear expression
+    and the library is built without fused multiply-adds."""
+    conn = util.CONNS[conn_name]()
+    xpts = _warped_points(conn)
+    res = []
+    for lib in (ref_lib, impl):
+        f = OctForest(order=order, lib=lib)
+        f.setTrilinearTopology(conn, xpts)
+        f.createTrees(1)
+        for p in range(2):
+            f.refine(util.synth_flags(f.getOctants().as_array(), 2024 + p, 30))
+            f.balance(1)
+        f.createNodes()
+        res.append((f.getNodeNumbers().copy(), f.getPoints(), f.getMeshConn().copy()))
+    (na, xa, ca), (nb, xb, cb) = res
+    assert np.array_equal(na, nb) and np.array_equal(ca, cb)
+    assert xa.shape == xb.shape and len(xa) == len(na) and len(xa) > 100
+    assert np.abs(xa).max() > 1.0
+    assert np.array_equal(xa, xb)
+
+
+def test_node_locations_without_topology_are_zero(impl, ref_lib):
+    """no topology: X is all zeros in the reference (:5526-5527) and here"""
+    conn = util.box_conn()
+    for lib in (ref_lib, impl):
+        f = util.build_forest(lib, conn, 1, 1, 30, 0)
+        x = f.getPoints()
+        assert len(x) == len(f.getNodeNumbers()) and not x.any()

@@ -359,4 +359,11 @@ int tmrc_hash_exercise(const tmrc_octant *in, int n, int use_node_index,
   return size;
 }
 
+int tmrc_get_points(tmrc_forest f, const double **xyz) {
+  TMRPoint *X = NULL;
+  const int n = F(f)->getPoints(&X);
+  if (xyz) *xyz = reinterpret_cast<const double *>(X);
+  return X ? n : 0;
+}
+
 }  // extern "C"

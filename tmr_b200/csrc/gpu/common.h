@@ -242,6 +242,29 @@ TMR_HD int slot_label(int order, int i, int j, int k) {
   return 3 - ext;
 }
 
+/* parametric coordinate of an integer tree coordinate (reference
+   convert_to_coordinate, src/TMROctForest.cpp:298-308) */
+TMR_HD double param_coordinate(i32 x) {
+  if (x == 0) return 0.0;
+  if (x == kHmax - 1) return 1.0;
+  return 1.0 * x / kHmax;
+}
+
+/* trilinear image of (u,v,w) in [0,1]^3 through 8 corner points (corner c:
+   bit0 = x, bit1 = y, bit2 = z).  One fixed operation order, so the host class
+   (TMRTrilinearVolume::evalPoint), the test oracle's stand-in and the device
+   kernel produce the same bits (the library is built with -fmad=false). */
+TMR_HD void trilinear_point(const double *X, double u, double v, double w, double *p) {
+  const double a[2] = {1.0 - u, u}, b[2] = {1.0 - v, v}, c[2] = {1.0 - w, w};
+  p[0] = p[1] = p[2] = 0.0;
+  for (int k = 0; k < 8; k++) {
+    const double n = (a[k & 1] * b[(k >> 1) & 1]) * c[k >> 2];
+    p[0] += n * X[3 * k];
+    p[1] += n * X[3 * k + 1];
+    p[2] += n * X[3 * k + 2];
+  }
+}
+
 /* ---- super-mesh connectivity tables (device or host pointers) -----------
    Layout and meaning follow reference src/TMROctForest.h:323-410: inverse
    maps store 8*block+corner / 12*block+edge / 6*block+face with the owner

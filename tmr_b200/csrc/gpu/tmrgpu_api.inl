@@ -10,6 +10,7 @@
 #include "ops_interp.h"
 #include "ops_multi.h"
 #include "ops_nodes.h"
+#include "ops_points.h"
 #include "tmrgpu.h"
 
 using namespace tmrgpu;
@@ -466,6 +467,10 @@ int tmrgpu_interp_device_views(tmrgpu_forest *F, const int **rows,
 
 int tmrgpu_download_sorted_node_numbers(tmrgpu_forest *f, int *out) {
   return swept(*f->f.ctx, sorted_node_numbers(f->f, out), "sorted_node_numbers");
+}
+
+int tmrgpu_eval_trilinear_points(tmrgpu_forest *f, const double *corners, double *X) {
+  return swept(*f->f.ctx, eval_trilinear_points(f->f, corners, X), "eval_trilinear_points");
 }
 
 int tmrgpu_create_interp(tmrgpu_forest *fine, tmrgpu_forest *coarse,

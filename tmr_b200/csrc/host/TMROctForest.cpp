@@ -12,8 +12,10 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
+#include "TMRTrilinearVolume.h"
 #include "common.h" /* shared host/device geometry: transform_node, tables */
 #include "tmrgpu.h"
 
@@ -754,14 +756,147 @@ int TMROctForest::getExtPreOffset() {
   return ext_pre_offset;
 }
 
+/* Node locations (reference evaluateNodeLocations :5524-5675).  Without a
+   topology they are zero, as in the reference.  With one, every local node is
+   evaluated through the first element (in element order) and local slot that
+   reference it, at u + 0.5 d (1 + knot[i]): on the GPU when every volume is a
+   TMRTrilinearVolume, else through the volumes' virtual evalPoint on the host,
+   the reference's own loop. */
+void TMROctForest::evaluateNodeLocations() {
+  X = new TMRPoint[num_local_nodes + 1];
+  for (int i = 0; i <= num_local_nodes; i++) X[i].zero();
+  if (!topo || num_local_nodes == 0 || !tables) return;
+  const int nb = tables->num_blocks;
+  std::vector<TMRVolume *> vols(nb, (TMRVolume *)NULL);
+  bool trilinear = true;
+  for (int b = 0; b < nb; b++) {
+    topo->getVolume(b, &vols[b]);
+    trilinear = trilinear && dynamic_cast<TMRTrilinearVolume *>(vols[b]) != NULL;
+  }
+  if (trilinear && !(interp_type == TMR_BERNSTEIN_POINTS && mesh_order > 2)) {
+    std::vector<double> corners((size_t)nb * 24);
+    for (int b = 0; b < nb; b++) {
+      const double *c = static_cast<TMRTrilinearVolume *>(vols[b])->corners();
+      std::copy(c, c + 24, corners.begin() + (size_t)b * 24);
+    }
+    if (tmrgpu_eval_trilinear_points(dev, corners.data(),
+                                     reinterpret_cast<double *>(X)) == 0) {
+      return;
+    }
+    fprintf(stderr, "TMROctForest Error: node locations could not be "
+                    "evaluated on the device\n");
+    return;
+  }
+  /* general volumes: the reference's host loop */
+  TMROctant *octs;
+  int num_elements;
+  TMROctantArray *elems = NULL;
+  getOctants(&elems); /* materialises the host mirror of the elements */
+  if (!elems) return;
+  elems->getArray(&octs, &num_elements);
+  const int *c0;
+  getNodeConn(&c0);
+  fetchNodeNumbers();
+  if (!c0 || !node_numbers) return;
+  const int p = mesh_order, size = p * p * p;
+  const double *knots = interp_knots;
+  std::vector<char> flags(num_local_nodes, 0);
+  const bool bern = (interp_type == TMR_BERNSTEIN_POINTS && p > 2);
+  std::vector<double> inverse;
+  if (bern) {
+    /* interpolation matrix of the Bernstein basis at the knot points and its
+       inverse (reference :5539-5577, there through LAPACK dgetrf/dgetrs) */
+    std::vector<double> A((size_t)size * size);
+    for (int i = 0; i < size; i++) {
+      double pt[3];
+      pt[0] = knots[i % p];
+      pt[1] = knots[(i % p * p) / p]; /* as in the reference (:5546) */
+      pt[2] = knots[i / (p * p)];
+      evalInterp(pt, &A[(size_t)size * i]);
+    }
+    inverse.assign((size_t)size * size, 0.0);
+    for (int i = 0; i < size; i++) inverse[(size_t)(size + 1) * i] = 1.0;
+    /* column-major view of the row-major matrix = its transpose, as the
+       reference passes it: solve A^T Y = I by Gaussian elimination with
+       partial pivoting */
+    std::vector<double> M((size_t)size * size);
+    for (int r = 0; r < size; r++) {
+      for (int c = 0; c < size; c++) M[(size_t)r * size + c] = A[(size_t)c * size + r];
+    }
+    for (int k = 0; k < size; k++) {
+      int piv = k;
+      for (int r = k + 1; r < size; r++) {
+        if (fabs(M[(size_t)r * size + k]) > fabs(M[(size_t)piv * size + k])) piv = r;
+      }
+      if (piv != k) {
+        for (int c = 0; c < size; c++) {
+          std::swap(M[(size_t)k * size + c], M[(size_t)piv * size + c]);
+          std::swap(inverse[(size_t)c * size + k], inverse[(size_t)c * size + piv]);
+        }
+      }
+      for (int r = k + 1; r < size; r++) {
+        const double fct = M[(size_t)r * size + k] / M[(size_t)k * size + k];
+        if (fct == 0.0) continue;
+        for (int c = k; c < size; c++) M[(size_t)r * size + c] -= fct * M[(size_t)k * size + c];
+        for (int c = 0; c < size; c++) {
+          inverse[(size_t)c * size + r] -= fct * inverse[(size_t)c * size + k];
+        }
+      }
+    }
+    for (int c = 0; c < size; c++) { /* back substitution, column c of Y */
+      for (int r = size - 1; r >= 0; r--) {
+        double v = inverse[(size_t)c * size + r];
+        for (int q = r + 1; q < size; q++) v -= M[(size_t)r * size + q] * inverse[(size_t)c * size + q];
+        inverse[(size_t)c * size + r] = v / M[(size_t)r * size + r];
+      }
+    }
+  }
+  std::vector<TMRPoint> Xtmp(size);
+  for (int i = 0; i < num_elements; i++) {
+    TMRVolume *vol = vols[octs[i].block];
+    const int32_t h = 1 << (TMR_MAX_LEVEL - octs[i].level);
+    const double d = tmrgpu::param_coordinate(h);
+    const double u = tmrgpu::param_coordinate(octs[i].x);
+    const double v = tmrgpu::param_coordinate(octs[i].y);
+    const double w = tmrgpu::param_coordinate(octs[i].z);
+    const int *c = &c0[(size_t)size * i];
+    if (bern) {
+      for (int kk = 0; kk < p; kk++) {
+        for (int jj = 0; jj < p; jj++) {
+          for (int ii = 0; ii < p; ii++) {
+            vol->evalPoint(u + 0.5 * d * (1.0 + knots[ii]), v + 0.5 * d * (1.0 + knots[jj]),
+                           w + 0.5 * d * (1.0 + knots[kk]), &Xtmp[ii + jj * p + kk * p * p]);
+          }
+        }
+      }
+    }
+    for (int kk = 0; kk < p; kk++) {
+      for (int jj = 0; jj < p; jj++) {
+        for (int ii = 0; ii < p; ii++) {
+          const int local = ii + jj * p + kk * p * p;
+          const int index = getLocalNodeNumber(c[local]);
+          if (index < 0 || flags[index]) continue;
+          flags[index] = 1;
+          if (bern) {
+            X[index].zero();
+            for (int j = 0; j < size; j++) {
+              X[index].x += inverse[(size_t)local * size + j] * Xtmp[j].x;
+              X[index].y += inverse[(size_t)local * size + j] * Xtmp[j].y;
+              X[index].z += inverse[(size_t)local * size + j] * Xtmp[j].z;
+            }
+          } else {
+            vol->evalPoint(u + 0.5 * d * (1.0 + knots[ii]), v + 0.5 * d * (1.0 + knots[jj]),
+                           w + 0.5 * d * (1.0 + knots[kk]), &X[index]);
+          }
+        }
+      }
+    }
+  }
+}
+
 int TMROctForest::getPoints(TMRPoint **_X) {
   fetchNodeData();
-  if (!X && nodes_on_host) {
-    /* no CAD topology => node locations are zero (reference :5526-5539);
-       materialised on first request */
-    X = new TMRPoint[num_local_nodes + 1];
-    for (int i = 0; i < num_local_nodes; i++) X[i].zero();
-  }
+  if (!X && nodes_on_host) evaluateNodeLocations();
   if (_X) *_X = X;
   return num_local_nodes;
 }
@@ -797,6 +932,23 @@ int TMROctForest::createInterpolationCSR(TMROctForest *coarse, const int **rows,
   interp_rowp = new int[nrows + 2];
   interp_cols = new int[nnz + 1];
   interp_vals = new double[nnz + 1];
+  /* fresh pages: fault them in from several threads before the copy lands
+     (a 1.5e9-entry prolongation is 18 GB of first touches) */
+  {
+    const int T = 8;
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+      th.push_back(std::thread([=]() {
+        const int64_t a = nnz * t / T, b = nnz * (t + 1) / T;
+        memset(interp_cols + a, 0, (size_t)(b - a) * sizeof(int));
+        memset(interp_vals + a, 0, (size_t)(b - a) * sizeof(double));
+        const int64_t c = nrows * t / T, d = nrows * (t + 1) / T;
+        memset(interp_rows + c, 0, (size_t)(d - c) * sizeof(int));
+        memset(interp_rowp + c, 0, (size_t)(d - c) * sizeof(int));
+      }));
+    }
+    for (size_t k = 0; k < th.size(); k++) th[k].join();
+  }
   if (tmrgpu_download_interp(dev, interp_rows, interp_rowp, interp_cols,
                              interp_vals)) {
     return 0;

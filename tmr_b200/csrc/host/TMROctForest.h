@@ -151,6 +151,7 @@ class TMROctForest : public TMREntity {
   void octantsReplacedOnDevice();
   void fetchNodeData();
   void fetchNodeNumbers();
+  void evaluateNodeLocations();
   int ensureDevice();
 
   /* createInterpolationCSR results */

@@ -4,6 +4,8 @@
   the CUDA layer (include/tmrgpu.h) on device-resident inputs.
 */
 #include "TMROctForest.h"
+#include "TMRTrilinearVolume.h"
+#include "tmr_capi.h"
 #include "tmr_b200_ext.h"
 #include "tmrgpu.h"
 
@@ -36,6 +38,24 @@ int tmr_b200_create_interpolation_csr(void *fine, void *coarse, const int **rows
   if (rowp) *rowp = rp;
   if (nnz) *nnz = (rp && n > 0) ? rp[n] : 0;
   return n;
+}
+
+/* declared in tmr_capi.h: the drop-in's version builds a TMRTrilinearTopology */
+int tmrc_set_trilinear_topology(tmrc_forest f, int num_nodes, const int *conn,
+                                int num_blocks, const double *xpts) {
+  TMROctForest *forest = static_cast<TMROctForest *>(f);
+  /* edge and face numbering exactly as setConnectivity derives it */
+  TMROctForest *tmp = new TMROctForest(MPI_COMM_SELF);
+  tmp->incref();
+  tmp->setConnectivity(num_nodes, conn, num_blocks);
+  int nb, nf, ne, nn;
+  const int *bc, *bfc, *bec, *ids;
+  tmp->getConnectivity(&nb, &nf, &ne, &nn, &bc, &bfc, &bec, &ids);
+  TMRTrilinearTopology *topo =
+      new TMRTrilinearTopology(nn, ne, nf, nb, bc, bec, bfc, xpts);
+  tmp->decref();
+  forest->setTopology(topo);
+  return 0;
 }
 
 }  // extern "C"

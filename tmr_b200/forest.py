@@ -299,6 +299,31 @@ class OctForest:
         self._lib.tmrc_create_interpolation(self._ptr, coarse._ptr, vec._ptr)
         return vec
 
+    def setTrilinearTopology(self, block_conn, xpts):
+        """Attach a topology of trilinear hexahedra (one per tree) through the
+        super-mesh node locations `xpts` (tmrc_set_trilinear_topology): gives
+        the forest a geometry without the CAD layer, so that getPoints() runs
+        evaluateNodeLocations (reference src/TMROctForest.cpp:5524-5675)."""
+        conn = np.ascontiguousarray(block_conn, dtype=np.int32)
+        x = np.ascontiguousarray(xpts, dtype=np.float64)
+        self._lib.tmrc_set_trilinear_topology.argtypes = [
+            C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        rc = self._lib.tmrc_set_trilinear_topology(
+            self._ptr, len(x), conn.ctypes.data, len(conn), x.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("tmrc_set_trilinear_topology failed")
+
+    def getPoints(self):
+        """Node locations, one row per local node in the order of
+        getNodeNumbers() (reference getPoints :1476-1481)."""
+        ptr = C.POINTER(C.c_double)()
+        self._lib.tmrc_get_points.restype = C.c_int
+        self._lib.tmrc_get_points.argtypes = [C.c_void_p, C.c_void_p]
+        n = self._lib.tmrc_get_points(self._ptr, C.byref(ptr))
+        if n <= 0 or not ptr:
+            return np.zeros((0, 3))
+        return _capi.as_double_array(ptr, 3 * n).reshape(n, 3).copy()
+
     # ---- B200 extensions (include/tmr_b200_ext.h, include/tmrgpu.h) ----------
     def createInterpolationCSR(self, coarse):
         """The whole prolongation in one hand-off: (rows, rowp, cols, vals),
