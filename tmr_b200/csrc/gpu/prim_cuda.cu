@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <time.h>
 
+#include <mutex>
+
 #include "prim_cuda.cuh"
 
 namespace tmrgpu {
@@ -55,6 +57,14 @@ struct DevCache {
 };
 
 static std::map<Ctx *, DevCache> g_caches;
+/* contexts are per thread (host/TMROctant.cpp); the maps that find a
+   context's cache are shared: look-ups are serialised, the cache itself is
+   only ever used by its context's thread (std::map nodes do not move) */
+static std::mutex g_cache_mutex;
+static DevCache &cache_of(std::map<Ctx *, DevCache> &m, Ctx &ctx) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  return m[&ctx];
+}
 
 static void cache_release_all(DevCache &c) {
   for (std::multimap<size_t, void *>::iterator it = c.free_blocks.begin();
@@ -66,6 +76,7 @@ static void cache_release_all(DevCache &c) {
 }
 
 void dev_cache_destroy(Ctx &ctx) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
   std::map<Ctx *, DevCache>::iterator it = g_caches.find(&ctx);
   if (it == g_caches.end()) return;
   cudaStreamSynchronize((cudaStream_t)ctx.stream);
@@ -73,7 +84,7 @@ void dev_cache_destroy(Ctx &ctx) {
   g_caches.erase(it);
 }
 
-size_t dev_cache_peak_bytes(Ctx &ctx) { return g_caches[&ctx].peak_bytes; }
+size_t dev_cache_peak_bytes(Ctx &ctx) { return cache_of(g_caches, ctx).peak_bytes; }
 
 void *dev_alloc(Ctx &ctx, size_t bytes) {
   if (ctx.fail_alloc_in > 0 && --ctx.fail_alloc_in == 0) {
@@ -82,7 +93,7 @@ void *dev_alloc(Ctx &ctx, size_t bytes) {
     ctx.last_error = "device allocation failed";
     return NULL;
   }
-  DevCache &c = g_caches[&ctx];
+  DevCache &c = cache_of(g_caches, ctx);
   const size_t cls = size_class(bytes);
   void *p = NULL;
   std::multimap<size_t, void *>::iterator it = c.free_blocks.find(cls);
@@ -118,7 +129,7 @@ void *dev_alloc(Ctx &ctx, size_t bytes) {
 
 void dev_free(Ctx &ctx, void *p) {
   if (!p) return;
-  DevCache &c = g_caches[&ctx];
+  DevCache &c = cache_of(g_caches, ctx);
   std::map<void *, size_t>::iterator it = c.live.find(p);
   if (it == c.live.end()) return;
   const size_t cls = it->second;
@@ -132,7 +143,7 @@ void dev_free(Ctx &ctx, void *p) {
 static std::map<Ctx *, DevCache> g_host_caches;
 
 void *host_alloc(Ctx &ctx, size_t bytes) {
-  DevCache &c = g_host_caches[&ctx];
+  DevCache &c = cache_of(g_host_caches, ctx);
   const size_t cls = size_class(bytes);
   void *p = NULL;
   std::multimap<size_t, void *>::iterator it = c.free_blocks.find(cls);
@@ -152,7 +163,7 @@ void *host_alloc(Ctx &ctx, size_t bytes) {
 
 void host_free(Ctx &ctx, void *p) {
   if (!p) return;
-  DevCache &c = g_host_caches[&ctx];
+  DevCache &c = cache_of(g_host_caches, ctx);
   std::map<void *, size_t>::iterator it = c.live.find(p);
   if (it == c.live.end()) return;
   c.free_blocks.insert(std::make_pair(it->second, p));

@@ -311,7 +311,16 @@ struct StoreOffsetFn {
 template <class F>
 u64 scan_counts(Ctx &ctx, i64 n, F f, u32 *out, const char *name) {
   StoreOffsetFn g = {out};
-  return scan_apply(ctx, n, f, g, name);
+  const u64 total = scan_apply(ctx, n, f, g, name);
+  if (total >> 32) {
+    /* the offsets are 32-bit: a larger total has wrapped them.  Recorded, so
+       that the operation's closing check_errors fails instead of handing out
+       corrupt arrays */
+    fprintf(stderr, "TMROctForest Error: %s: %llu outputs exceed the 32-bit offsets "
+                    "of the CUDA path\n", name, (unsigned long long)total);
+    ctx.last_error = "scan total exceeds 32 bits";
+  }
+  return total;
 }
 
 }  // namespace tmrgpu

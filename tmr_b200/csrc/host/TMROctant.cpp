@@ -200,17 +200,27 @@ void TMROctantArray::sort() {
   is_sorted = 1;
 }
 
+/* One query against the sorted array: a binary search on the host with the
+   scalar comparators, as the reference's bsearch (src/TMROctant.cpp:404-424) --
+   O(log n) and no traffic.  (Uploading the array for a single probe made
+   per-octant callers O(n) each; batches go through tmrgpu_array_contains.) */
 TMROctant *TMROctantArray::contains(TMROctant *q, int use_position) {
   if (!is_sorted) sort();
-  if (size == 0) return NULL;
-  tmrgpu_ctx *ctx = tmr_b200_context();
-  if (!ctx) return NULL;
-  const int mode = use_node_index ? 2 : (use_position ? 1 : 0);
-  int index = -1;
-  tmrgpu_array_contains(ctx, reinterpret_cast<const tmrgpu_octant *>(array),
-                        size, reinterpret_cast<const tmrgpu_octant *>(q), 1,
-                        mode, &index);
-  return index >= 0 ? &array[index] : NULL;
+  int lo = 0, hi = size;
+  while (lo < hi) {
+    const int mid = lo + ((hi - lo) >> 1);
+    const int c = use_node_index
+                      ? q->compareNode(&array[mid])
+                      : (use_position ? q->comparePosition(&array[mid])
+                                      : q->compare(&array[mid]));
+    if (c == 0) return &array[mid];
+    if (c < 0) {
+      hi = mid;
+    } else {
+      lo = mid + 1;
+    }
+  }
+  return NULL;
 }
 
 void TMROctantArray::merge(TMROctantArray *list) {
