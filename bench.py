@@ -42,6 +42,9 @@ CPU_SAMPLE = dict(nb=8, level=3, passes=2, pct=35, order=2, corner=0, seed=2024)
 C1 = dict(nb=1, level=4, passes=4, pct=30, order=2, corner=0, seed=2024)
 # fingerprints of the reference on C2 / C1 (pinned by the oracle)
 C2_PIN = dict(octants=86278900, checksum="da1d7223d950ef5c", owned_nodes=53774081)
+# the ~1e9-octant forest of BASELINE configs[4] (8x8x96 trees): fingerprint of the
+# same forest built on 4 GPUs (profiles/bench_r02_1B_n4.json)
+NORTH_STAR_PIN = dict(octants=1037532543, checksum="b263cb130799478f", owned_nodes=644833973)
 C1_PIN = dict(octants=1027916, checksum="55e9487c98c7a2ff", owned_nodes=652025,
               dep_nodes=908576, dep_nnz=2441728)
 
@@ -233,6 +236,8 @@ def main():
     ap.add_argument("--pct", type=int, default=None,
                     help="refinement percentage of the recipe (default: 35 for c2, 30 for c4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true",
+                    help="N=8: skip the additional 1e9-octant measurement (BASELINE configs[4])")
     ap.add_argument("--no-parity", action="store_true",
                     help="skip the parity gate that runs before the timed region")
     ap.add_argument("--profiler-range", action="store_true",
@@ -615,6 +620,34 @@ def main():
         del b1
         lib.tmrgpu_dev_free(ctx, f1)
 
+    # BASELINE configs[4] / north_star: the ~1e9-octant forest (8x8x96 trees, 130 M
+    # octants per GPU) on 8 GPUs, measured inside the same run so that the driver's
+    # N=8 line carries it; its fingerprint must equal the one recorded from the
+    # same forest on 4 GPUs (profiles/scaling_r02.md)
+    north_star = None
+    ns_world = int(os.environ.get("TMR_B200_NORTH_STAR_WORLD", "8"))  # (test hook)
+    if (world == ns_world and world > 1 and args.workload == "c2" and not args.strong
+            and args.nbz_per_gpu == 8 and cfg["passes"] == FULL["passes"]
+            and cfg["pct"] == FULL["pct"] and not args.no_north_star):
+        nsb, _, nsf, _ = build_base(util.structured_conn(8, 8, 12 * world), cfg)
+        ns_ms, ns_fp = timed_cycles(nsb, nsf, cfg, 3, 2)
+        tt = torch.tensor([ns_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ns_ms = float(tt.item())
+        ns_ok = all(ns_fp[k] == NORTH_STAR_PIN[k] for k in NORTH_STAR_PIN)
+        if world == 8:
+            parity["north_star_matches_4_gpu_run"] = ns_ok
+            parity["ok"] = parity["ok"] and ns_ok
+        north_star = {"workload": "8x8x%d-tree box (BASELINE configs[4]), same recipe, one forest over %d GPUs"
+                                  % (12 * world, world),
+                      "octants": ns_fp["octants"], "ms_per_step": ns_ms,
+                      "value": ns_fp["octants"] / (ns_ms * 1e-3), "unit": UNIT,
+                      "fingerprint": ns_fp, "fingerprint_on_4_gpus": NORTH_STAR_PIN,
+                      "frac_of_aggregate_hbm_peak_by_compulsory_bytes":
+                          134.0 * ns_fp["octants"] / (ns_ms * 1e-3) / 1e9 / (world * load_peaks()[0])}
+        del nsb
+        lib.tmrgpu_dev_free(ctx, nsf)
+
     # ---- end-to-end arm --------------------------------------------------------
     # node arrays are copied to page-locked host memory on a second stream as
     # soon as each is final (conn after the renumbering, the dependent CSR at
@@ -776,6 +809,7 @@ def main():
             "value_with_flags_h2d": value_h2d,
             "parity": parity,
             "same_config": same_config,
+            "north_star_1e9_octants": north_star,
             "fingerprint": fp_final,
             "numa_bound_cpus": numa_cpus,
             "gpu_launches": int(launches),
