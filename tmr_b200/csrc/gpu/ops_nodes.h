@@ -26,6 +26,9 @@
 #define TMRGPU_OPS_NODES_H
 
 #include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -1694,14 +1697,30 @@ inline void dep_expand_host(const unsigned short *codes, const double *table, i6
       const i64 end = sum[t + 1];
       for (; d < b && o + 4 <= end; d++) {
         const int c = cls[codes[d]];
-        ptr[d] = (int)o;
         const double *r = r4 + 4 * c;
+#if defined(__x86_64__)
+        /* streaming stores: the arrays are written once and read by the
+           caller much later -- no read-for-ownership traffic next to the DMA
+           of conn that is landing in the same memory */
+        _mm_stream_si32(ptr + d, (int)o);
+        const long long *q = reinterpret_cast<const long long *>(r);
+        long long *dst = reinterpret_cast<long long *>(w + o);
+        _mm_stream_si64(dst, q[0]);
+        _mm_stream_si64(dst + 1, q[1]);
+        _mm_stream_si64(dst + 2, q[2]);
+        _mm_stream_si64(dst + 3, q[3]);
+#else
+        ptr[d] = (int)o;
         w[o] = r[0];
         w[o + 1] = r[1];
         w[o + 2] = r[2];
         w[o + 3] = r[3];
+#endif
         o += len[c];
       }
+#if defined(__x86_64__)
+      _mm_sfence();
+#endif
     }
     for (; d < b; d++) {
       const int c = cls[codes[d]];
