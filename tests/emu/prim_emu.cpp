@@ -22,8 +22,6 @@ void *copy_d2h_async(Ctx &, void *d, const void *s, size_t b, int) {
 }
 void copy_wait(Ctx &, void *) {}
 void copy_sync(Ctx &, void *) {}
-void l2_persist(Ctx &, const void *, size_t) {}
-void l2_persist_off(Ctx &) {}
 void copy_d2d(Ctx &, void *d, const void *s, size_t b) { memcpy(d, s, b); }
 void dev_zero(Ctx &, void *p, size_t b) { memset(p, 0, b); }
 void dev_fill_ff(Ctx &, void *p, size_t b) { memset(p, 0xff, b); }

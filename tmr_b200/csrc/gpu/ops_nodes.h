@@ -2341,9 +2341,6 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     dev_zero(ctx, ctl.get(), 2 * sizeof(unsigned long long));
     v.fail = reinterpret_cast<int *>(ctl.get() + 1);
     if (E > 0) {
-      /* the rank index (16 B per 64 finest cells, 21 MB at C2) answers every
-         predecessor search: persisting in L2 */
-      l2_persist(ctx, rank_tab.get(), (size_t)rank_tab.size() * sizeof(RankEntry));
       if (3 * D <= 30) {
         launch_slot_locate<u32>(ctx, f, nd, v, slot8.get(), dep_table.get(),
                                 b_key.get(), b_pay.get(), ctl.get(), cap, fmask);
@@ -2351,7 +2348,6 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
         launch_slot_locate<u64>(ctx, f, nd, v, slot8.get(), dep_table.get(),
                                 b_key.get(), b_pay.get(), ctl.get(), cap, fmask);
       }
-      l2_persist_off(ctx);
     }
     if (!comm) break;
     copy_d2h(ctx, h_ctl, ctl.get(), sizeof(h_ctl));
@@ -2752,11 +2748,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
                      fq_key.get(), fq_dest.get(), fq_code.get(), fq_count.get(),
                      cap};
       HangingFn hang = {ev, info32.get()};
-      /* the leaf bitmap (19 MB at C2) is probed 6 times per element while 0.7 GB
-         of keys stream past it: keep it in the persisting part of L2 */
-      if (leaf_bits.get()) l2_persist(ctx, leaf_bits.get(), (size_t)map_words * sizeof(u32));
       launch(ctx, E, hang, "nodes_hanging_info");
-      l2_persist_off(ctx);
       if (!comm) break;
       unsigned long long h_count = 0;
       copy_d2h(ctx, &h_count, fq_count.get(), sizeof(h_count));

@@ -83,11 +83,6 @@ void copy_wait(Ctx &ctx, void *handle); /* blocks until done, releases it */
 unsigned long long *mailbox_slot(Ctx &ctx);
 /* blocks until done, keeps the handle; callable from a worker thread */
 void copy_sync(Ctx &ctx, void *handle);
-/* keep [p, p + bytes) resident in L2 for the kernels launched next on the
-   context's stream (access-policy window, persisting on hit, everything else
-   streaming); l2_persist_off ends the window.  TMR_B200_L2_PERSIST=0 disables. */
-void l2_persist(Ctx &ctx, const void *p, size_t bytes);
-void l2_persist_off(Ctx &ctx);
 void dev_zero(Ctx &ctx, void *p, size_t bytes);
 void dev_fill_ff(Ctx &ctx, void *p, size_t bytes);
 void stream_sync(Ctx &ctx);

@@ -290,45 +290,6 @@ void copy_d2d(Ctx &ctx, void *dst, const void *src, size_t bytes) {
                               (cudaStream_t)ctx.stream));
 }
 
-static int l2_persist_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char *ev = getenv("TMR_B200_L2_PERSIST");
-    mode = ev ? atoi(ev) : 1;
-  }
-  return mode;
-}
-
-void l2_persist(Ctx &ctx, const void *p, size_t bytes) {
-  if (!p || bytes == 0 || !l2_persist_mode()) return;
-  static int max_window = -1, max_persist = -1;
-  if (max_window < 0) {
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx.device);
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx.device);
-    if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-  }
-  if (max_window <= 0 || max_persist <= 0) return;
-  cudaStreamAttrValue attr;
-  memset(&attr, 0, sizeof(attr));
-  const size_t win = bytes < (size_t)max_window ? bytes : (size_t)max_window;
-  attr.accessPolicyWindow.base_ptr = const_cast<void *>(p);
-  attr.accessPolicyWindow.num_bytes = win;
-  /* a window larger than the set-aside would thrash it: scale the hit ratio */
-  attr.accessPolicyWindow.hitRatio =
-      win <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)win;
-  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  cudaStreamSetAttribute((cudaStream_t)ctx.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-}
-
-void l2_persist_off(Ctx &ctx) {
-  if (!l2_persist_mode()) return;
-  cudaStreamAttrValue attr;
-  memset(&attr, 0, sizeof(attr));
-  attr.accessPolicyWindow.num_bytes = 0;
-  cudaStreamSetAttribute((cudaStream_t)ctx.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-}
-
 void dev_zero(Ctx &ctx, void *p, size_t bytes) {
   if (bytes == 0 || !p || !ctx.last_error.empty()) return;
   TMR_CUDA_OK(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)ctx.stream));
@@ -491,83 +452,6 @@ __global__ void __launch_bounds__(256)
       }
     } else if (tile_base + u * 256 + threadIdx.x < n) {
       atomicAdd(&s_h[d], 1u);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kRadix; i += 256) {
-    thist[(size_t)blockIdx.x * kRadix + i] = s_h[i];
-  }
-}
-
-/* Experiment (round 2): the same histogram with the tile brought into shared
-   memory by ONE bulk-async copy (cp.async.bulk.shared::cluster.global with an
-   mbarrier transaction count -- the 1-D TMA path of sm_90+/sm_100a) instead
-   of 16 coalesced 8-byte loads per thread.  Selected with TMR_B200_HIST=bulk;
-   measured in profiles/experiments_r02.md. */
-template <int kBits>
-__global__ void __launch_bounds__(256)
-    radix_tile_hist_bulk_kernel(const u64 *__restrict__ keys, i64 n, int shift,
-                                int bits, u32 *__restrict__ thist) {
-  const int kRadix = 1 << kBits;
-  __shared__ __align__(128) u64 s_keys[kSortTile];
-  __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ u32 s_h[kRadix];
-  for (int i = threadIdx.x; i < kRadix; i += 256) s_h[i] = 0;
-  const i64 tile_base = (i64)blockIdx.x * kSortTile;
-  const i64 rem = n - tile_base;
-  const int tile_n = rem < kSortTile ? (int)rem : kSortTile;
-  const bool full = tile_n == kSortTile;
-  const u32 bar = (u32)__cvta_generic_to_shared(&s_bar);
-  const u32 dst = (u32)__cvta_generic_to_shared(s_keys);
-  if (full) {
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const u32 bytes = (u32)(kSortTile * sizeof(u64));
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                   "r"(bytes)
-                   : "memory");
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-              "r"(dst),
-          "l"(keys + tile_base), "r"(bytes), "r"(bar)
-          : "memory");
-    }
-    /* every thread waits for the transaction to complete (phase 0) */
-    u32 done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(bar)
-          : "memory");
-    }
-  } else {
-    for (int i = threadIdx.x; i < tile_n; i += 256) s_keys[i] = keys[tile_base + i];
-    __syncthreads();
-  }
-  const u32 dmask = (1u << bits) - 1u;
-  const int lane = threadIdx.x & 31;
-  for (int u = 0; u < kSortTile / 256; u++) {
-    const int i = u * 256 + threadIdx.x;
-    if (i < tile_n) {
-      const u32 d = (u32)(s_keys[i] >> shift) & dmask;
-      if (full) {
-        int uniform;
-        __match_all_sync(0xffffffffu, d, &uniform);
-        if (uniform) {
-          if (lane == 0) atomicAdd(&s_h[d], 32u);
-        } else {
-          atomicAdd(&s_h[d], 1u);
-        }
-      } else {
-        atomicAdd(&s_h[d], 1u);
-      }
     }
   }
   __syncthreads();
@@ -864,18 +748,8 @@ static void launch_tile_offsets(Ctx &ctx, const u64 *keys, i64 n, i64 tiles,
                                 u32 *doff) {
   cudaStream_t st = (cudaStream_t)ctx.stream;
   const int chunks = (int)((tiles + kScanChunk - 1) / kScanChunk);
-  static int bulk = -1;
-  if (bulk < 0) {
-    const char *ev = getenv("TMR_B200_HIST");
-    bulk = (ev && strcmp(ev, "bulk") == 0) ? 1 : 0;
-  }
-  if (bulk) {
-    radix_tile_hist_bulk_kernel<kBits><<<(unsigned)tiles, 256, 0, st>>>(keys, n, shift,
-                                                                      bits, thist);
-  } else {
-    radix_tile_hist_kernel<kBits><<<(unsigned)tiles, 256, 0, st>>>(keys, n, shift,
-                                                                 bits, thist);
-  }
+  radix_tile_hist_kernel<kBits><<<(unsigned)tiles, 256, 0, st>>>(keys, n, shift,
+                                                               bits, thist);
   radix_tile_scan_kernel<kBits><<<chunks, 1 << kBits, 0, st>>>(thist, tiles, ctot);
   radix_chunk_scan_kernel<kBits><<<1, 1 << kBits, 0, st>>>(ctot, chunks, doff);
 }
