@@ -1132,6 +1132,18 @@ struct PendingWinnerFn { /* after BPlaceFn: the elements with a B corner */
   }
 };
 
+#if defined(__CUDACC__)
+/* gather-latency-bound bodies: occupancy over registers */
+template <>
+struct LaunchMinBlocks<SlotResolveWin2Fn> {
+  static const int value = 6;
+};
+template <>
+struct LaunchMinBlocks<SlotResolveWin3Fn> {
+  static const int value = 6;
+};
+#endif
+
 struct DepLenFn {
   const u64 *win_edge;
   const u64 *win_face;
@@ -1537,6 +1549,13 @@ struct DepFillFn : DepFillData {
     }
   }
 };
+
+#if defined(__CUDACC__)
+template <>
+struct LaunchMinBlocks<DepFillFn<2> > {
+  static const int value = 5;
+};
+#endif
 
 struct ConnRemapFn {
   const int *conn_local;
@@ -2174,6 +2193,12 @@ inline void launch_slot_locate(Ctx &ctx, Forest &f, NodeData &nd, const SlotView
                                i64 cap, const unsigned char *fmask) {
   NodeSlotFn<M> ns = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8, f.info.get(),
                       dep_table, nd.nfmt, b_key, b_pay, b_count, cap};
+  if (!v.multi) {
+    NodeSlotFn<M, false> ns1 = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8,
+                                f.info.get(), dep_table, nd.nfmt, b_key, b_pay, b_count, cap};
+    launch_block3(ctx, f.n, ns1, "nodes_slot_locate");
+    return;
+  }
   launch_block3(ctx, f.n, ns, "nodes_slot_locate");
   if (v.multi && fmask) {
     ParentNodeGen pg = {f.keys.get(), fmask, f.fmt, nd.nfmt, f.tables, 2, NULL};

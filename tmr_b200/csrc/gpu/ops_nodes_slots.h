@@ -332,7 +332,10 @@ struct DepTableFn {
    collect() classifies the element and queues the points that need a search,
    process() drains the queues with all lanes busy, finish() assembles the
    element's row.  M: Morton word (u32 up to depth 10, else u64). */
-template <class M>
+/* kMulti = false compiles the off-range ("B") corner path out: on one rank no
+   corner can lie outside the rank's range, and the path costs the kernel six
+   registers (46 instead of 40: five instead of six resident CTAs per SM) */
+template <class M, bool kMulti = true>
 struct NodeSlotFn {
   SlotView v;
   u32 *conn_leaf;       /* [E][8] leaf index of every corner (kConnB: B list) */
@@ -533,7 +536,7 @@ struct NodeSlotFn {
         *v.fail = 1;
         leaf[c] = 0;
         dm &= ~(1 << c);
-      } else if (val == kLocB) {
+      } else if (kMulti && val == kLocB) {
         i32 b, x, y, z;
         int L;
         v.fmt.decode(v.keys[i], &b, &x, &y, &z, &L);

@@ -24,9 +24,28 @@ namespace tmrgpu {
 
 static const int kLaunchThreads = 256;
 
+/* resident CTAs per SM a kernel body asks the compiler to make room for
+   (register cap = 65536 / (256 * value)); specialised next to the few bodies
+   whose occupancy is worth a tighter register budget */
+template <class F>
+struct LaunchMinBlocks {
+  static const int value = 1;
+};
+
 template <class F>
 __global__ void __launch_bounds__(kLaunchThreads)
     launch_kernel(F f, i64 n) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    f(i);
+  }
+}
+/* the same with a register budget for kMin resident CTAs per SM (a minimum of
+   1 is NOT the same as none: ptxas then spends registers freely -- measured:
+   HangingFn 40 -> 54, MapClosureFn 32 -> 72 registers) */
+template <class F, int kMin>
+__global__ void __launch_bounds__(kLaunchThreads, kMin)
+    launch_kernel_occ(F f, i64 n) {
   const i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     f(i);
@@ -54,7 +73,12 @@ void launch(Ctx &ctx, i64 n, F f, const char *name) {
   /* up to 8 resident CTAs of 256 threads per SM; 4 waves of grid-stride */
   const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
   prof_begin(ctx, name);
-  launch_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
+  if constexpr (LaunchMinBlocks<F>::value > 1) {
+    launch_kernel_occ<F, LaunchMinBlocks<F>::value>
+        <<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
+  } else {
+    launch_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
+  }
   prof_end(ctx);
   ctx.launch_count++;
 }
@@ -120,7 +144,7 @@ void expand_u64(Ctx &ctx, i64 n, const u32 *off, u64 total, F f, u64 *out,
    construction (ops_nodes_slots.h), where sibling elements share the point
    locations of their family's 27 nodes. */
 template <class F>
-__global__ void __launch_bounds__(kLaunchThreads)
+__global__ void __launch_bounds__(kLaunchThreads, 6) /* 6 CTAs per SM: <= 40 registers */
     block3_kernel(F f, i64 n) {
   __shared__ typename F::Shared sh;
   const i64 nblk = (n + kLaunchThreads - 1) / kLaunchThreads;
