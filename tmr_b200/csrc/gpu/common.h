@@ -87,6 +87,31 @@ unsigned long long fetch_add_u64(unsigned long long *p, unsigned long long v) {
 #endif
 }
 
+/* append `value` to a list whose length lives at *count: on the device the
+   lanes of a warp that append together take ONE atomic (the lowest active lane
+   reserves the range), so a list fed by millions of threads does not serialise
+   on its counter */
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+void append_u32(unsigned long long *count, uint32_t *list, long long cap, uint32_t value) {
+#if defined(__CUDA_ARCH__)
+  const unsigned m = __activemask();
+  const int lane = (int)(threadIdx.x & 31);
+  const int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+  if ((long long)pos < cap) list[pos] = value;
+#else
+  const unsigned long long pos = (*count)++;
+  if ((long long)pos < cap) list[pos] = value;
+#endif
+}
+
 /* fetch-and-add on an int (shared-memory task counters) */
 #if defined(__CUDACC__)
 __host__ __device__ __forceinline__

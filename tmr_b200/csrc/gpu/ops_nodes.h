@@ -239,6 +239,12 @@ struct LeafMapBuildFn {
 struct HangingFn {
   ElemView ev;
   int *info32; /* 32-bit accumulator per element (bits 0-5 info) */
+  /* elements with a probe that leaves their tree: the inter-tree path (face /
+     edge tables, orientation transforms) runs in a second, dense launch over
+     this list -- inline it made every warp with one such element execute it
+     (ncu: 17 of 32 lanes active on average) */
+  u32 *slow_list;
+  unsigned long long *slow_count;
 
   /* exact-leaf probe of a level-pl cell of this tree at levels the map does
      not cover */
@@ -303,17 +309,6 @@ struct HangingFn {
         nc[k] = (comp - 1) & am[k];
       }
     }
-    /* coordinates only for probes that leave the tree */
-    i32 px = 0, py = 0, pz = 0, hp = 0;
-    if (out[0] || out[1] || out[2]) {
-      u32 ux, uy, uz;
-      unmorton3(mp, &ux, &uy, &uz);
-      const int s = kMaxLevel - pl;
-      px = (i32)(ux << s);
-      py = (i32)(uy << s);
-      pz = (i32)(uz << s);
-      hp = 1 << s;
-    }
     /* the 6 neighbour cells: faces k = 0..2, then edges parallel to axis k */
     u64 cell[6];
     bool inside[6];
@@ -356,20 +351,58 @@ struct HangingFn {
         }
       }
     }
-    /* probes that leave the tree (boundary elements only) */
+    info32[i] = bits;
+    /* probes that leave the tree: second launch (HangingBoundaryFn) */
+    if (out[0] || out[1] || out[2]) append_u32(slow_count, slow_list, ev.n, (u32)i);
+  }
+};
+
+/* second pass over the elements whose parent touches a face of its tree: the
+   probes that leave the tree (reference checkAdjacentFaces / Edges through
+   the face and edge transforms, :3465-3605) */
+struct HangingBoundaryFn {
+  HangingFn h;
+  TMR_HD void operator()(i64 q) const {
+    const ElemView &ev = h.ev;
+    const i64 i = (i64)h.slow_list[q];
+    const u64 key = ev.keys[i];
+    const int level = (int)(key & 31);
+    const int D = ev.fmt.D;
+    const u64 pos = key >> 5;
+    const u64 m = pos & ((1ULL << (3 * D)) - 1);
+    const i32 block = (i32)(pos >> (3 * D));
+    const int sh = 3 * (D - level);
+    const int md = (int)((m >> sh) & 7);
+    const int id = ((md >> 2) & 1) | (md & 2) | ((md & 1) << 2);
+    const int pl = level - 1;
+    const u64 mp = m >> (sh + 3);
+    const u64 lmask = pl > 0 ? ((1ULL << (3 * pl)) - 1) : 0ULL;
+    bool out[3];
     TMR_UNROLL
     for (int k = 0; k < 3; k++) {
-      if (!inside[k] &&
-          outside_face(id, k, block, px, py, pz, hp, pl, ((u64)i << 3) | (u64)k)) {
+      const u64 am = (0x1249249249249249ULL << (2 - k)) & lmask;
+      const u64 comp = mp & am;
+      out[k] = ((id >> k) & 1) ? (comp == am) : (comp == 0);
+    }
+    u32 ux, uy, uz;
+    unmorton3(mp, &ux, &uy, &uz);
+    const int s = kMaxLevel - pl;
+    const i32 px = (i32)(ux << s), py = (i32)(uy << s), pz = (i32)(uz << s), hp = 1 << s;
+    int bits = 0;
+    TMR_UNROLL
+    for (int k = 0; k < 3; k++) {
+      const int a = (k == 0) ? 1 : 0, b = (k == 2) ? 1 : 2; /* the other axes */
+      if (out[k] &&
+          h.outside_face(id, k, block, px, py, pz, hp, pl, ((u64)i << 3) | (u64)k)) {
         bits |= 1 << k;
       }
-      if (!inside[k + 3] &&
-          outside_edge(id, k, block, px, py, pz, hp, pl,
-                       ((u64)i << 3) | (u64)(k + 3))) {
+      if ((out[a] || out[b]) &&
+          h.outside_edge(id, k, block, px, py, pz, hp, pl,
+                         ((u64)i << 3) | (u64)(k + 3))) {
         bits |= 1 << (k + 3);
       }
     }
-    info32[i] = bits;
+    if (bits) h.info32[i] |= bits;
   }
 };
 
@@ -2753,6 +2786,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       lmap.bits = leaf_bits.get();
     }
     DBuf<int> info32(ctx, E);
+    DBuf<u32> slow_list(ctx, E);
+    DBuf<unsigned long long> slow_count(ctx, 1);
     DBuf<u64> fq_key, fq_code;
     DBuf<u32> fq_dest;
     DBuf<unsigned long long> fq_count(ctx, 1);
@@ -2772,8 +2807,15 @@ inline int create_nodes(Forest &f, int order, int interp_type,
                      E > 0 ? (i32)(k_last >> (3 * f.fmt.D + 5)) : 0,
                      fq_key.get(), fq_dest.get(), fq_code.get(), fq_count.get(),
                      cap};
-      HangingFn hang = {ev, info32.get()};
+      dev_zero(ctx, slow_count.get(), sizeof(unsigned long long));
+      HangingFn hang = {ev, info32.get(), slow_list.get(), slow_count.get()};
       launch(ctx, E, hang, "nodes_hanging_info");
+      /* the launch covers the worst case (every element on a tree face); threads
+         beyond the list's length return at once */
+      unsigned long long h_slow = 0;
+      copy_d2h(ctx, &h_slow, slow_count.get(), sizeof(h_slow));
+      HangingBoundaryFn hb = {hang};
+      launch(ctx, (i64)h_slow, hb, "nodes_hanging_boundary");
       if (!comm) break;
       unsigned long long h_count = 0;
       copy_d2h(ctx, &h_count, fq_count.get(), sizeof(h_count));
