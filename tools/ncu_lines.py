@@ -26,8 +26,9 @@ for r in rows:
         try:
             ie = int(r[hdr.index('Instructions Executed')])
             smp = int(r[4])
-            wf = int(r[hdr.index('L1 Wavefronts Shared')])
-            wfi = int(r[hdr.index('L1 Wavefronts Shared Ideal')])
+            wf = int(r[hdr.index('L1 Wavefronts Shared')]) if 'L1 Wavefronts Shared' in hdr else 0
+            wfi = (int(r[hdr.index('L1 Wavefronts Shared Ideal')])
+                   if 'L1 Wavefronts Shared Ideal' in hdr else 0)
         except (ValueError, IndexError):
             continue
         a = agg[line]
