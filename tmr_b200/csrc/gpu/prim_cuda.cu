@@ -11,6 +11,8 @@
 
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "prim_cuda.cuh"
 
 namespace tmrgpu {
@@ -327,7 +329,16 @@ int check_errors(Ctx &ctx, const char *where) {
   return 0;
 }
 
+/* TMR_B200_NVTX=1: every named launch bracket is an NVTX range (shows up in
+   nsys timelines and lets ncu filter with --nvtx-include) */
+static int nvtx_mode() {
+  static int mode = -1;
+  if (mode < 0) mode = getenv("TMR_B200_NVTX") ? atoi(getenv("TMR_B200_NVTX")) : 0;
+  return mode;
+}
+
 void prof_begin(Ctx &ctx, const char *name) {
+  if (nvtx_mode()) nvtxRangePushA(name);
   if (!ctx.profile) return;
   if (ctx.launch_log) fprintf(ctx.launch_log, "%ld %s\n", ctx.launch_count, name);
   cudaEvent_t a, b;
@@ -340,6 +351,7 @@ void prof_begin(Ctx &ctx, const char *name) {
 }
 
 void prof_end(Ctx &ctx) {
+  if (nvtx_mode()) nvtxRangePop();
   if (!ctx.profile) return;
   cudaEventRecord((cudaEvent_t)ctx.ev_stop.back(), (cudaStream_t)ctx.stream);
 }
