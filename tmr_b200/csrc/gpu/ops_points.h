@@ -46,7 +46,7 @@ struct PointFirstFn {
   u32 *first;
   TMR_HD void operator()(i64 code) const {
     const i64 i = index(conn[code]);
-    if (i >= 0) TMR_ATOMIC_MIN_I32(&first[i], (int)code);
+    if (i >= 0) TMR_ATOMIC_MIN_I32(reinterpret_cast<int *>(&first[i]), (int)code);
   }
 };
 
