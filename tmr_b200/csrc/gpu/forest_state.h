@@ -123,7 +123,7 @@ struct NodeData {
   NodeData()
       : valid(false), order(2), interp_type(1), num_elements(0),
         num_local_nodes(0), num_dep_nodes(0), num_owned_nodes(0), dep_nnz(0),
-        num_candidates(0), node_range_start(0), ext_numbers_valid(false), mctx(NULL),
+        num_candidates(0), node_range_start(0), mctx(NULL), ext_numbers_valid(false),
         prefetch(0) {}
   ~NodeData() { drop_mirrors(); }
   /* the expansion job writes into the DepPtr / DepWeights mirrors: join it
