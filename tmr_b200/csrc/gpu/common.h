@@ -112,6 +112,22 @@ void append_u32(unsigned long long *count, uint32_t *list, long long cap, uint32
 #endif
 }
 
+/* fetch-and-or returning the previous value */
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+int fetch_or_i32(int *p, int v) {
+#if defined(__CUDA_ARCH__)
+  return atomicOr(p, v);
+#else
+  const int old = *p;
+  *p = old | v;
+  return old;
+#endif
+}
+
 /* fetch-and-add on an int (shared-memory task counters) */
 #if defined(__CUDACC__)
 __host__ __device__ __forceinline__

@@ -421,11 +421,17 @@ struct PatchProbeFn {
   const u64 *code;
   const unsigned char *ans;
   int *info32; /* bits 0-5 info, bits 8-13 foreign mask */
+  /* the elements that got a foreign bit, each once: the few whose parent
+     edge / face nodes must be created explicitly (ParentNodeGen) */
+  u32 *foreign_list;
+  unsigned long long *foreign_count;
+  i64 cap;
   TMR_HD void operator()(i64 i) const {
     if (ans[i]) {
       const u64 c = code[i];
       const int bit = (int)(c & 7);
-      TMR_ATOMIC_OR_I32(&info32[c >> 3], (1 << bit) | (1 << (bit + 8)));
+      const int old = fetch_or_i32(&info32[c >> 3], (1 << bit) | (1 << (bit + 8)));
+      if (!(old & 0x3f00)) append_u32(foreign_count, foreign_list, cap, (u32)(c >> 3));
     }
   }
 };
@@ -2301,9 +2307,12 @@ struct ParentSlotFn {
   ParentNodeGen g;
   SlotView v;
   NodeSlotFn<M> ns;
-  TMR_HD void operator()(i64 e) const {
+  const u32 *list; /* the elements with a foreign bit */
+  const unsigned long long *count;
+  TMR_HD void operator()(i64 q) const {
+    if ((unsigned long long)q >= *count) return;
     SlotKeyEmit<NodeSlotFn<M> > em = {&v, &ns.nfmt, &ns};
-    g.run(e, em);
+    g.run((i64)list[q], em);
   }
 };
 
@@ -2313,7 +2322,10 @@ template <class M>
 inline void launch_slot_locate(Ctx &ctx, Forest &f, NodeData &nd, const SlotView &v,
                                unsigned char *slot8, const unsigned char *dep_table,
                                u64 *b_key, u32 *b_pay, unsigned long long *b_count,
-                               i64 cap, const unsigned char *fmask) {
+                               i64 cap, const unsigned char *fmask,
+                               const u32 *foreign_list,
+                               const unsigned long long *foreign_count,
+                               i64 foreign_cap) {
   NodeSlotFn<M> ns = {v, reinterpret_cast<u32 *>(nd.conn.get()), slot8, f.info.get(),
                       dep_table, nd.nfmt, b_key, b_pay, b_count, cap};
   if (!v.multi) {
@@ -2323,10 +2335,10 @@ inline void launch_slot_locate(Ctx &ctx, Forest &f, NodeData &nd, const SlotView
     return;
   }
   launch_block3(ctx, f.n, ns, "nodes_slot_locate");
-  if (v.multi && fmask) {
+  if (v.multi && fmask && foreign_cap > 0) {
     ParentNodeGen pg = {f.keys.get(), fmask, f.fmt, nd.nfmt, f.tables, 2, NULL};
-    ParentSlotFn<M> ps = {pg, v, ns};
-    launch(ctx, f.n, ps, "nodes_slot_parents");
+    ParentSlotFn<M> ps = {pg, v, ns, foreign_list, foreign_count};
+    launch(ctx, foreign_cap, ps, "nodes_slot_parents");
   }
 }
 
@@ -2402,9 +2414,15 @@ inline int ensure_node_arrays(Forest &f) {
   if (!nd.valid) return 1;
   if (nd.num_local_nodes == 0 || nd.node_num.size() == nd.num_local_nodes) return 0;
   if (nd.slot_multi) {
-    const SlotMulti &sm = *static_cast<const SlotMulti *>(nd.slot_multi.get());
+    SlotMulti &sm = *static_cast<SlotMulti *>(nd.slot_multi.get());
     nd.node_keys.alloc(ctx, nd.num_local_nodes);
     nd.node_num.alloc(ctx, nd.num_local_nodes);
+    if (sm.slotinfo1.size() != f.n) {
+      sm.slotinfo1.alloc(ctx, f.n);
+      SlotCountMFn sc1 = {sm.mc.get()};
+      SlotInfoMFn si1 = {sm.mc.get(), sm.slotinfo1.get()};
+      scan_apply(ctx, f.n, sc1, si1, "nodes_slot_scan");
+    }
     SlotKeys3Fn kf = {f.keys.get(), f.fmt, sm.slotinfo1.get(), sm.sn, nd.node_keys.get(),
                       nd.node_num.get(), sm.nlow};
     launch(ctx, f.n, kf, "nodes_slot_keys");
@@ -2431,7 +2449,11 @@ struct SlotState { /* outlives build_nodes_slots: the dependent CSR looks nodes 
      connectivity was resolved */
   DBuf<u64> win_edge, win_face;
   int winner_done;
-  SlotState() : winner_done(0) {
+  /* in: elements with a remote coarse neighbour (PatchProbeFn) */
+  const u32 *foreign_list;
+  const unsigned long long *foreign_count;
+  i64 foreign_cap;
+  SlotState() : winner_done(0), foreign_list(NULL), foreign_count(NULL), foreign_cap(0) {
     lookup.on = 0;
     lookup_m.on = 0;
   }
@@ -2491,10 +2513,12 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     if (E > 0) {
       if (3 * D <= 30) {
         launch_slot_locate<u32>(ctx, f, nd, v, slot8.get(), dep_table.get(),
-                                b_key.get(), b_pay.get(), ctl.get(), cap, fmask);
+                                b_key.get(), b_pay.get(), ctl.get(), cap, fmask,
+                                st.foreign_list, st.foreign_count, st.foreign_cap);
       } else {
         launch_slot_locate<u64>(ctx, f, nd, v, slot8.get(), dep_table.get(),
-                                b_key.get(), b_pay.get(), ctl.get(), cap, fmask);
+                                b_key.get(), b_pay.get(), ctl.get(), cap, fmask,
+                                st.foreign_list, st.foreign_count, st.foreign_cap);
       }
     }
     if (!comm) break;
@@ -2572,11 +2596,12 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
       copy_d2h(ctx, &nlow, d_low.get(), sizeof(i64));
     }
   }
-  /* first scan: position of every leaf's nodes in node order */
-  DBuf<u64> slotinfo1(ctx, E);
+  /* number of slot nodes; their positions in node order (a second array of 8
+     bytes per leaf) are only needed for node_keys / node_num and are scanned
+     when those are asked for (ensure_node_arrays) */
   SlotCountMFn sc1 = {mc.get()};
-  SlotInfoMFn si1 = {mc.get(), slotinfo1.get()};
-  const i64 NA = (i64)scan_apply(ctx, E, sc1, si1, "nodes_slot_scan");
+  SlotNoStoreFn none;
+  const i64 NA = (i64)scan_apply(ctx, E, sc1, none, "nodes_slot_scan");
   const i64 Nn = NA + nbu;
   if (Nn >= (1LL << 31)) {
     fprintf(stderr, "TMROctForest Error: too many local nodes\n");
@@ -2732,7 +2757,6 @@ inline int build_nodes_slots(Forest &f, NodeData &nd,
     std::shared_ptr<SlotMulti> keep(new SlotMulti());
     SlotMulti &sm = *keep;
     sm.mc.swap(mc);
-    sm.slotinfo1.swap(slotinfo1);
     sm.slotinfo.swap(slotinfo);
     sm.xref.swap(xref);
     sm.xnum.swap(xnum);
@@ -2846,6 +2870,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
      :3287-3451; the answers are the same exact-leaf tests) */
   if (!f.info.get()) f.info.alloc(ctx, E);
   DBuf<unsigned char> fmask;
+  DBuf<u32> foreign_list; /* elements with a remote coarse neighbour (several ranks) */
+  DBuf<unsigned long long> foreign_count;
   DBuf<u32> elem_index_store;
   int ix_bits = 22;
   if (const char *ev = getenv("TMR_B200_IXBITS")) ix_bits = atoi(ev);
@@ -2924,7 +2950,11 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       launch(ctx, plan.nrecv, ap, "nodes_probe_answer");
       DBuf<unsigned char> got;
       route_back(ctx, *comm, plan, ans.get(), got);
-      PatchProbeFn pp = {fq_code.get(), got.get(), info32.get()};
+      foreign_list.alloc(ctx, nq + 1);
+      foreign_count.alloc(ctx, 1);
+      dev_zero(ctx, foreign_count.get(), sizeof(unsigned long long));
+      PatchProbeFn pp = {fq_code.get(), got.get(),           info32.get(),
+                         foreign_list.get(), foreign_count.get(), nq};
       launch(ctx, nq, pp, "nodes_probe_patch");
       fmask.alloc(ctx, E);
     }
@@ -2953,6 +2983,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     const char *mode = getenv("TMR_B200_NODES");
     if (gorder == 2 && !general && nd.nfmt.lbits == 0 && (comm || E > 0) &&
         !(mode && strcmp(mode, "sort") == 0)) {
+      slot_state.foreign_list = foreign_list.get();
+      slot_state.foreign_count = foreign_count.get();
+      slot_state.foreign_cap = foreign_list.size() > 0 ? foreign_list.size() - 1 : 0;
       slots_done = build_nodes_slots(f, nd, fmask.get(), k_first, k_last, om_n, &Nn,
                                      slot_state);
       if (slots_done < 0) return 1;

@@ -752,6 +752,9 @@ struct SlotCountMFn {
   const u64 *mc;
   TMR_HD u32 operator()(i64 i) const { return (u32)popc32((u32)mc[i]); }
 };
+struct SlotNoStoreFn { /* scan for the total only */
+  TMR_HD void operator()(i64, u32) const {}
+};
 struct SlotInfoMFn {
   const u64 *mc;
   u64 *slotinfo;
