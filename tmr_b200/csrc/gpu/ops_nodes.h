@@ -239,6 +239,16 @@ struct LeafMapBuildFn {
 struct HangingFn {
   ElemView ev;
   int *info32; /* 32-bit accumulator per element (bits 0-5 info) */
+  /* one rank: nothing is patched in afterwards, the 6 bits go straight into
+     the forest's int16 info array (no accumulator, no split pass) */
+  int16_t *info16;
+  TMR_HD void store_info(i64 i, int bits) const {
+    if (info16) {
+      info16[i] = (int16_t)bits;
+    } else {
+      info32[i] = bits;
+    }
+  }
   /* elements with a probe that leaves their tree: the inter-tree path (face /
      edge tables, orientation transforms) runs in a second, dense launch over
      this list -- inline it made every warp with one such element execute it
@@ -282,7 +292,7 @@ struct HangingFn {
     const u64 key = ev.keys[i];
     const int level = (int)(key & 31);
     if (level == 0) {
-      info32[i] = 0;
+      store_info(i, 0);
       return;
     }
     const int D = ev.fmt.D;
@@ -351,7 +361,7 @@ struct HangingFn {
         }
       }
     }
-    info32[i] = bits;
+    store_info(i, bits);
     /* probes that leave the tree: second launch (HangingBoundaryFn) */
     if (out[0] || out[1] || out[2]) append_u32(slow_count, slow_list, ev.n, (u32)i);
   }
@@ -402,7 +412,13 @@ struct HangingBoundaryFn {
         bits |= 1 << (k + 3);
       }
     }
-    if (bits) h.info32[i] |= bits;
+    if (bits) {
+      if (h.info16) {
+        h.info16[i] = (int16_t)(h.info16[i] | bits);
+      } else {
+        h.info32[i] |= bits;
+      }
+    }
   }
 };
 
@@ -2875,9 +2891,9 @@ inline int create_nodes(Forest &f, int order, int interp_type,
   DBuf<u32> elem_index_store;
   int ix_bits = 22;
   if (const char *ev = getenv("TMR_B200_IXBITS")) ix_bits = atoi(ev);
-  const KeyIndex elem_ix =
-      build_key_index(ctx, f.keys.get(), E, (u64)f.nblocks << (3 * f.fmt.D + 5),
-                      elem_index_store, ix_bits);
+  /* exact-leaf searches by key: only the levels the leaf bitmap does not
+     cover, and the probes other ranks ask about, need them */
+  KeyIndex elem_ix = KeyIndex();
   u64 k_first = 0, k_last = 0;
   {
     DBuf<u32> leaf_bits;
@@ -2894,6 +2910,10 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       map_nb = (i32)(k_last >> (3 * f.fmt.D + 5)) - map_b0 + 1;
     }
     LeafMap lmap = plan_leaf_map(f.fmt.D, map_b0, map_nb, &map_words);
+    if (comm || lmap.lmax < f.fmt.D - 1) {
+      elem_ix = build_key_index(ctx, f.keys.get(), E, (u64)f.nblocks << (3 * f.fmt.D + 5),
+                                elem_index_store, ix_bits);
+    }
     if (lmap.lmax >= 0) {
       leaf_bits.alloc(ctx, (i64)map_words);
       dev_zero(ctx, leaf_bits.get(), (size_t)map_words * sizeof(u32));
@@ -2901,7 +2921,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       launch(ctx, E, lb, "nodes_leaf_map");
       lmap.bits = leaf_bits.get();
     }
-    DBuf<int> info32(ctx, E);
+    DBuf<int> info32(ctx, comm ? E : 0);
     DBuf<u32> slow_list(ctx, E);
     DBuf<unsigned long long> slow_count(ctx, 1);
     DBuf<u64> fq_key, fq_code;
@@ -2924,7 +2944,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
                      fq_key.get(), fq_dest.get(), fq_code.get(), fq_count.get(),
                      cap};
       dev_zero(ctx, slow_count.get(), sizeof(unsigned long long));
-      HangingFn hang = {ev, info32.get(), slow_list.get(), slow_count.get()};
+      HangingFn hang = {ev, info32.get(), comm ? (int16_t *)NULL : f.info.get(),
+                        slow_list.get(), slow_count.get()};
       launch(ctx, E, hang, "nodes_hanging_info");
       /* the launch covers the worst case (every element on a tree face); threads
          beyond the list's length return at once */
@@ -2958,8 +2979,10 @@ inline int create_nodes(Forest &f, int order, int interp_type,
       launch(ctx, nq, pp, "nodes_probe_patch");
       fmask.alloc(ctx, E);
     }
-    Info32SplitFn sp = {info32.get(), f.info.get(), fmask.get()};
-    launch(ctx, E, sp, "nodes_info_split");
+    if (comm) {
+      Info32SplitFn sp = {info32.get(), f.info.get(), fmask.get()};
+      launch(ctx, E, sp, "nodes_info_split");
+    }
   }
   trace_mark(ctx, "nodes: hanging info");
 
