@@ -44,6 +44,27 @@ def main():
     print("prolongation: %d rows, %d non-zeros, max |row sum - 1| = %.1e"
           % (len(rows), len(cols), np.abs(np.add.reduceat(vals, rowp[:-1]) - 1).max()))
 
+    # ---- B200 extensions (include/tmr_b200_ext.h, include/tmrgpu.h) ------------------
+    # the whole prolongation in one hand-off instead of one addInterp call per row
+    rows2, rowp2, cols2, vals2 = forest.createInterpolationCSR(coarse)
+    assert np.array_equal(rows, rows2) and np.array_equal(cols, cols2)
+    # the arrays createTACS hands to TACSAssembler, as they sit on the device
+    view = forest.assemblerViews()
+    assert np.array_equal(view["conn"].reshape(conn.shape), conn)
+    print("device views: elem_ptr[-1] = %d, %d dependent stencil entries"
+          % (view["elem_ptr"][-1], len(view["dep_conn"])))
+    # a geometry without the CAD layer: one trilinear hexahedron per tree
+    block_conn = util.box_conn()
+    nodes = int(block_conn.max()) + 1
+    xpts = np.random.default_rng(0).uniform(-1.0, 1.0, (nodes, 3)) + 4.0 * np.arange(nodes)[:, None]
+    geo = tmr_b200.OctForest(order=2)
+    geo.setTrilinearTopology(block_conn, xpts)
+    geo.createTrees(2)
+    geo.createNodes()
+    X = geo.getPoints()           # evaluateNodeLocations on the GPU
+    print("node locations: %d points, bounding box %s .. %s"
+          % (len(X), np.round(X.min(axis=0), 2), np.round(X.max(axis=0), 2)))
+
 
 if __name__ == "__main__":
     main()
