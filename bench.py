@@ -651,7 +651,7 @@ def main():
     # ---- end-to-end arm --------------------------------------------------------
     # node arrays are copied to page-locked host memory on a second stream as
     # soon as each is final (conn after the renumbering, the dependent CSR at
-    # the end): the 5.9 GB read-back overlaps the rest of createNodes
+    # the end): the read-back overlaps the rest of createNodes
     lib.tmrgpu_set_node_prefetch(bdev, 7)
     for _ in range(max(1, args.warmup - 1)):
         w = step_e2e()
@@ -804,8 +804,12 @@ def main():
                     "ms_per_step": float(t.item()) / args.steps,
                     "host_ms_per_call": e2e_breakdown,
                     "what": "TMROctForest API: refine(host flags) + balance + createNodes + "
-                            "getNodeConn + getDepNodeConn + getNodeNumbers; read-back overlapped "
-                            "with createNodes on a copy stream"},
+                            "getNodeConn + getDepNodeConn + getNodeNumbers into host arrays; conn and "
+                            "dep_conn are copied on a second stream as soon as they are final, "
+                            "dep_ptr/dep_weights cross the bus as 2-byte stencil codes and are rebuilt "
+                            "by host threads, the sorted node numbers are ranges written on the host "
+                            "(d2h_bytes_per_step = what crossed the bus, host_array_bytes_per_step = "
+                            "what the caller holds afterwards)"},
             "value_with_flags_h2d": value_h2d,
             "parity": parity,
             "same_config": same_config,
