@@ -92,6 +92,14 @@ def as_int_array(ptr, n):
     return np.ctypeslib.as_array(ptr, shape=(n,)).astype(np.int32, copy=True)
 
 
+def view_array(ptr, n, dtype):
+    """Borrowed numpy view of n items behind a C pointer: NO copy; valid as long
+    as the owner keeps the array (None-safe)."""
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,))
+
+
 def as_double_array(ptr, n):
     if n <= 0 or not ptr:
         return np.zeros(0, dtype=np.float64)

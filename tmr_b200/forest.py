@@ -338,9 +338,11 @@ class OctForest:
         n = lib.tmr_b200_create_interpolation_csr(
             self._ptr, coarse._ptr, C.byref(rows), C.byref(rowp), C.byref(cols),
             C.byref(vals), C.byref(nnz))
-        return (_capi.as_int_array(rows, n).copy(), _capi.as_int_array(rowp, n + 1).copy(),
-                _capi.as_int_array(cols, nnz.value).copy(),
-                _capi.as_double_array(vals, nnz.value).copy())
+        # borrowed views into arrays owned by this forest (valid until its next
+        # createInterpolationCSR / destruction): no copy of what can be 18 GB
+        return (_capi.view_array(rows, n, np.int32), _capi.view_array(rowp, n + 1, np.int32),
+                _capi.view_array(cols, nnz.value, np.int32),
+                _capi.view_array(vals, nnz.value, np.float64))
 
     def assemblerViews(self):
         """Copies of the DEVICE arrays tmrgpu_assembler_views exposes (the
