@@ -1,26 +1,35 @@
 /*
-  ops_nodes.h -- createNodes on the device (single-rank numbering; the
-  multi-rank ownership exchange builds on the same arrays).
+  ops_nodes.h -- createNodes on the device, one rank or several.
 
-  Pipeline (replaces reference src/TMROctForest.cpp:4064-4268 and its helpers
+  Replaces reference src/TMROctForest.cpp:4064-4268 and its helpers
   computeDepFacesAndEdges :3619-3702, createLocalNodes :4290-4640,
   createLocalConn :4660-4867, labelDependentNodes :3711-3832,
-  createDependentConn :5157-5519):
+  createDependentConn :5157-5519.
 
-    hanging_info      per element: 3 face + 3 edge exact-leaf probes (binary
-                      search in the sorted key array, inter-tree transforms)
-    node_candidates   order^3 canonical node keys per element (transformNode)
-                      with payload = element*order^3 + slot
-    radix sort + run heads  -> unique node array, conn[payload] = run index
-                      (one sort instead of 8-27 bsearches per element)
-    dep_label         mark hanging nodes; scan -> dependent / independent
-                      numbering in node order
-    dep_winner        per dependent node: the LAST (element, edge|face) in the
-                      reference's loop order that writes its stencil
-                      (atomicMax), which is the writer whose data survives in
-                      the reference
-    dep_fill          one thread per dependent node: parent edge/face node
-                      numbers (binary search in the node keys) + fp64 weights
+    hanging info      per element the 3 face + 3 edge exact-leaf probes of its
+                      parent's neighbours against a per-level leaf bitmap
+                      (HangingFn); the probes that leave the tree run in a second
+                      dense launch over the compacted tree-face elements
+                      (HangingBoundaryFn); on several ranks a miss that belongs
+                      to another rank becomes a query answered by its owner
+    nodes + conn      order 2: (leaf, slot) naming, scans, no sort
+                      (ops_nodes_slots.h, build_nodes_slots; dependents are
+                      labelled and everything numbered in slot space, the
+                      connectivity comes out as final node numbers).
+                      General path (orders >= 3, label bits, unbalanced input):
+                      order^3 canonical node keys per element (transformNode)
+                      with payload (element, slot) -> radix sort -> run heads =
+                      unique nodes, conn[payload] = run index; dep_label, scans,
+                      numbering, remap
+    dep winner        per dependent node the LAST (element, edge|face) in the
+                      reference's loop order that writes its stencil (atomicMax;
+                      fused into the slot resolve on the order-2 path)
+    dep fill          one thread per dependent node: the parent edge / face
+                      node numbers (from the siblings' connectivity rows, or by
+                      position) and the tabulated fp64 weight rows
+    host mirrors      node_mirror_*: conn / dep_conn by DMA, dep_ptr + dep_weights
+                      as stencil codes rebuilt by host threads, node numbers as
+                      ranges
 */
 #ifndef TMRGPU_OPS_NODES_H
 #define TMRGPU_OPS_NODES_H
@@ -1165,7 +1174,7 @@ struct SlotResolveWin2Fn {
   }
 };
 /* several ranks: elements with a corner outside the rank's range get their
-   last numbers from the B pass and are revisited by DepWinnerBFn */
+   last numbers from the B pass and are revisited by PendingWinnerFn */
 struct SlotResolveWin3Fn {
   SlotResolve3Fn rs;
   DepWinnerFn<2> win;
