@@ -221,7 +221,10 @@ struct MapClosureFn {
         const int oz = o / 9, oy = (o - 9 * oz) / 3, ox = o - 9 * oz - 3 * oy;
         const u64 mc = comp[0][ox] | comp[1][oy] | comp[2][oz];
         const u64 c = base | mc;
-        TMR_ATOMIC_OR_I32(&words[c >> 5], 1u << (int)(c & 31));
+        /* neighbouring groups demand the same cells over and over: look before
+           the reduction (a cached load) -- most bits are set already */
+        const u32 bit = 1u << (int)(c & 31);
+        if (!(words[c >> 5] & bit)) TMR_ATOMIC_OR_I32(&words[c >> 5], bit);
         if (fwd) rm.forward(block, mc, l - 1);
       }
       return;
