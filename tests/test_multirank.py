@@ -228,3 +228,4 @@ def test_multirank_node_locations(ranks, emu_lib, ref_lib):
         assert np.array_equal(a[r][0], b[r][0]), r
         assert len(a[r][1]) == len(a[r][0]) > 0
         assert np.array_equal(a[r][1], b[r][1]), r
+

@@ -618,3 +618,22 @@ def test_node_locations_without_topology_are_zero(impl, ref_lib):
         f = util.build_forest(lib, conn, 1, 1, 30, 0)
         x = f.getPoints()
         assert len(x) == len(f.getNodeNumbers()) and not x.any()
+
+
+@pytest.mark.parametrize("order,conn_name", [(2, "box7"), (3, "box7"), (2, "connector15")])
+def test_create_nodes_after_bare_refine(order, conn_name, impl, ref_lib):
+    """createNodes on what refine() leaves behind -- not a complete tree: a
+    refined octant is replaced by ONE representative child with the same anchor
+    (reference :2169-2329) -- without a balance in between.  Eight consecutive
+    keys whose first and last are siblings 0 and 7 are then NOT necessarily a
+    family; the node construction must fall back from the (leaf, slot) scheme
+    and check every member."""
+    conn = util.CONNS[conn_name]()
+    res = []
+    for lib in (ref_lib, impl):
+        f = OctForest(order=order, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(1)
+        f.refine(util.synth_flags(f.getOctants().as_array(), 2024, 30))
+        res.append(util.node_results(f))
+    util.assert_nodes_equal(res[0], res[1], "bare refine")

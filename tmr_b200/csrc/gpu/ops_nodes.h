@@ -550,6 +550,11 @@ struct NodeEmit {
      can name (NULL = tree index as is); shortens the sort key so that the
      conn-slot payload still fits beside it */
   const u32 *dense;
+  /* check all 8 keys of a family, not only its first and last: needed when the
+     forest is not known to be a complete tree (after a bare refine a sibling
+     can be replaced by a deeper representative with the same anchor); the slot
+     construction has verified completeness where it succeeded */
+  int strict;
   TMR_HD u64 tree_id(i32 block) const {
     return dense ? (u64)dense[block] : (u64)(u32)block;
   }
@@ -564,7 +569,14 @@ struct NodeEmit {
     const u64 k = keys[e];
     const int L = (int)(k & 31);
     if (L == 0 || digit_of(k) != 0) return false;
-    return keys[e + 7] == k + (7ULL << (5 + 3 * (fmt.D - L)));
+    const int s = 5 + 3 * (fmt.D - L);
+    if (keys[e + 7] != k + (7ULL << s)) return false;
+    if (strict) {
+      for (int j = 1; j < 7; j++) {
+        if (keys[e + j] != k + ((u64)j << s)) return false;
+      }
+    }
+    return true;
   }
   /* is element e a member of a complete family? (m = its child digit) */
   TMR_HD bool in_family(i64 e, int *m) const {
@@ -3060,7 +3072,7 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     }
     /* candidate emission plan */
     NodeEmit emit_gen = {f.keys.get(), E,        f.fmt, nd.nfmt,
-                         f.tables,     gorder,   1,     tree_dense.get()};
+                         f.tables,     gorder,   1,     tree_dense.get(), 1};
     i64 nemit = ngc;
     DBuf<u32> eoff;
     if (emit_gen.families) {
@@ -3404,7 +3416,8 @@ inline int create_nodes(Forest &f, int order, int interp_type,
     }
     fill.conn = nd.conn.get();
     {
-      NodeEmit fg = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order, order == 2 ? 1 : 0};
+      NodeEmit fg = {f.keys.get(), E, f.fmt, nd.nfmt, f.tables, order, order == 2 ? 1 : 0,
+                     NULL, numbered ? 0 : 1};
       fill.fam = fg;
     }
     fill.dep_ptr = nd.dep_ptr.get();

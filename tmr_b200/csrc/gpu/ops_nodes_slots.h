@@ -555,8 +555,6 @@ struct NodeSlotFn {
         ords |= (val & 31) << (8 * c);
       }
     }
-    store8_u32(conn_leaf + i * 8, leaf);
-    *reinterpret_cast<u64 *>(slot8 + i * 8) = ords;
     if (dm) {
       TMR_UNROLL
       for (int c = 0; c < 8; c++) {
@@ -565,6 +563,8 @@ struct NodeSlotFn {
         }
       }
     }
+    *reinterpret_cast<u64 *>(slot8 + i * 8) = ords;
+    store8_u32(conn_leaf + i * 8, leaf);
   }
 };
 
