@@ -21,6 +21,13 @@ void launch(Ctx &ctx, i64 n, F f, const char *) {
   ctx.launch_count++;
 }
 
+/* the per-item form of a warp-cooperative body */
+template <class F>
+void launch_warp(Ctx &ctx, i64 n, F f, const char *) {
+  for (i64 i = 0; i < n; i++) f(i);
+  ctx.launch_count++;
+}
+
 struct DirectSink {
   u64 *p;
   void operator()(u64 v) { *p++ = v; }

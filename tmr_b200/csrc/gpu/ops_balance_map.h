@@ -341,6 +341,64 @@ struct MapFillFn {
       }
     }
   }
+#if defined(__CUDACC__)
+  /* warp form (launch_warp; ncu: 4-13 of 32 lanes active per item): the
+     refined cells of the warp's 32 groups are taken four at a time, eight
+     lanes per cell -- one lane per child, the children's leaf counts scanned
+     within the eight lanes */
+  __device__ __forceinline__ void warp(i64 base, int lane, i64 n) const {
+    const i64 g = base + lane;
+    if (l == 0) { /* trees: tiny, per item */
+      if (g < n) (*this)(g);
+      return;
+    }
+    const u32 byte = (g < n) ? mp.byte_of(l, g) : 0u;
+    const int L = l + 1;
+    const int q = lane >> 3, e = lane & 7;
+    for (int d = 0; d < 8; d++) {
+      unsigned mask = __ballot_sync(0xffffffffu, (byte >> d) & 1u);
+      while (mask) {
+        const int left = __popc(mask);
+        const int nsrc = left < 4 ? left : 4;
+        const bool on = q < nsrc;
+        u32 size = 0, r = 0, at0 = 0;
+        bool refined = false;
+        i64 cell = 0;
+        if (on) {
+          const int src = (int)__fns(mask, 0, q + 1);
+          cell = ((base + src) << 3) | d;
+          at0 = off[mp.rank_of(l, cell)];
+          const u32 kids = (L < mp.D) ? mp.byte_of(L, cell) : 0u;
+          refined = ((kids >> e) & 1u) != 0;
+          if (refined) {
+            r = mp.rank_of(L, (cell << 3) | e);
+            size = cnt[r];
+          } else {
+            size = 1;
+          }
+        }
+        u32 incl = size;
+#pragma unroll
+        for (int s = 1; s < 8; s <<= 1) {
+          const u32 up = __shfl_up_sync(0xffffffffu, incl, s, 8);
+          if (e >= s) incl += up;
+        }
+        if (on) {
+          const u32 at = at0 + incl - size;
+          if (refined) {
+            off[r] = at;
+          } else {
+            const u64 block = ((u64)cell >> (3 * l)) + (u64)mp.block0;
+            const u64 m = (u64)cell & low_mask(3 * l);
+            const u64 mD = ((m << 3) | (u64)e) << (3 * (fmt.D - L));
+            put(at, (block << (3 * fmt.D + 5)) | (mD << 5) | (u64)L);
+          }
+        }
+        for (int k = 0; k < nsrc; k++) mask &= mask - 1;
+      }
+    }
+  }
+#endif
 };
 
 /* number of leaves of the map's trees that lie before position `pos` (depth
@@ -443,8 +501,8 @@ inline int balance_map_leaves(Forest &f, CellMaps &mp, i64 words, DBuf<u32> &wra
   for (int l = 0; l < D; l++) {
     MapFillFn ff = {mp,       l,     cnt.get(), off.get(), toff.get(), root_flag,
                     f.fmt,    out.get(), first, last};
-    launch(ctx, l == 0 ? ((i64)mp.nblocks + 7) / 8 : mp.cells(l - 1), ff,
-           "balance_map_fill");
+    launch_warp(ctx, l == 0 ? ((i64)mp.nblocks + 7) / 8 : mp.cells(l - 1), ff,
+                "balance_map_fill");
   }
   /* a failed allocation above launched nothing: leave the forest as it was */
   if (!ctx_ok(ctx)) return check_errors(ctx, "balance");

@@ -83,6 +83,32 @@ void launch(Ctx &ctx, i64 n, F f, const char *name) {
   ctx.launch_count++;
 }
 
+/* ---- warp-cooperative launch ------------------------------------------------
+   f.warp(base, lane, n) is called by all 32 lanes of a warp together for the
+   32 consecutive items base .. base + 31 (items >= n are the lanes' own
+   business): bodies whose work sits in a few of many items (sparse bitmaps)
+   spread one item's inner loop over the lanes instead of leaving 28 of them
+   idle.  The same functor's operator()(i) is the per-item form (used by the
+   test-only emulation). */
+template <class F>
+__global__ void __launch_bounds__(kLaunchThreads, 4) /* up to 64 registers: no spills */
+    warp_kernel(F f, i64 n) {
+  const int lane = threadIdx.x & 31;
+  const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+  for (i64 base = warp0 * 32; base < n; base += nwarps * 32) f.warp(base, lane, n);
+}
+
+template <class F>
+void launch_warp(Ctx &ctx, i64 n, F f, const char *name) {
+  if (n <= 0 || !ctx_ok(ctx)) return;
+  const int grid = grid_for(ctx, n, kLaunchThreads, 8 * 4);
+  prof_begin(ctx, name);
+  warp_kernel<F><<<grid, kLaunchThreads, 0, (cudaStream_t)ctx.stream>>>(f, n);
+  prof_end(ctx);
+  ctx.launch_count++;
+}
+
 /* ---- expand: item i appends count(i) 64-bit outputs at off[i] -------------
    off is the exclusive scan of the counts (consecutive items own consecutive
    output ranges), total = off[n].  A thread writing its few outputs straight
