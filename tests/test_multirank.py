@@ -34,6 +34,20 @@ def test_multirank_interpolation(order, ranks, mode, emu_lib, ref_lib):
     assert sum(len(x[1]["interp"]) for x in b) > 0
 
 
+def test_multirank_interpolation_uneven_depths(emu_lib, ref_lib):
+    """A forest that is never repartitioned keeps whole trees per rank, so the
+    ranks' deepest levels differ; reading the octants after createNodes makes
+    the host class upload them again.  The keys a rank ships for remote
+    prolongation rows must still be at the depth every rank agreed on in
+    createNodes (found by the seeded fuzz runs: grid2, 5 ranks)."""
+    conn = util.CONNS["grid2"]()
+    body = multirank.adapt_body(conn, 1, 3, 30, 1, 2, False, seed=738575,
+                                with_interp="repartitioned")
+    a = multirank.run_thread_ranks(ref_lib, 5, body, True)
+    b = multirank.run_thread_ranks(emu_lib, 5, body, False)
+    multirank.compare_rank_results(a, b, "uneven depths")
+
+
 @pytest.mark.parametrize("ranks", [2, 3])
 def test_multirank_bernstein_order3(ranks, emu_lib, ref_lib):
     """Labelled node keys (order-3 Bernstein points) through the multi-rank

@@ -164,7 +164,11 @@ inline int upload_octants(Forest &f, const Oct24 *h_recs, i64 n) {
     return 1;
   }
   /* node data is deliberately left alone: writing octants through the
-     borrowed array does not invalidate nodes in the reference either */
+     borrowed array does not invalidate nodes in the reference either.  It was
+     built at the key depth all ranks agreed on (create_nodes), which this
+     rank's own deepest level may lie below: keep that depth, or the kept slot
+     tables and the keys other ranks send would no longer match these keys */
+  if (f.nodes.valid && f.fmt.D > D && key_budget_ok(f, f.fmt.D)) D = f.fmt.D;
   f.fmt.D = D;
   f.fmt.bbits = f.bbits;
   f.n = n;
