@@ -68,3 +68,135 @@ def test_fuzz_multi_rank(case, emu_lib, ref_lib):
     a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
     b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
     multirank.compare_rank_results(a, b, "fuzz %s" % (case,))
+
+
+def _apply_step(f, kind, pct, seed, corner):
+    """One randomly chosen forest operation; returns the forest to go on with."""
+    o = f.getOctants().as_array()
+    if kind == "refine":
+        f.refine(util.synth_flags(o, seed, pct))
+        f.balance(corner)
+    elif kind == "refine_neg":  # coarsen the flagged ones, refine a few others
+        fl = util.synth_flags(o, seed, pct)
+        fl = np.where(fl > 0, -1, np.where(util.synth_flags(o, seed + 1, 20) > 0, 1, 0))
+        f.refine(fl.astype(np.int32))
+        f.balance(corner)
+    elif kind == "refine_clamp":  # level limits (reference :1798-1816)
+        fl = np.where(util.synth_flags(o, seed, pct) > 0, 2, -2).astype(np.int32)
+        f.refine(fl, 1, 4)
+        f.balance(corner)
+    elif kind == "coarsen":
+        f = f.coarsen()
+        f.balance(corner)
+    elif kind == "dup":
+        f = f.duplicate()
+    elif kind == "repart":
+        f.repartition()
+    return f
+
+
+def _sequence_cases(n, seed, multi):
+    rng = random.Random(seed)
+    kinds = ["refine", "refine", "refine_neg", "coarsen", "dup", "refine_clamp"]
+    if multi:
+        kinds += ["repart", "repart"]
+    out = []
+    for _ in range(n):
+        cn = rng.choice(["box7", "connector15", "grid2", "butterfly2"] if multi else NAMES)
+        steps = tuple((rng.choice(kinds), rng.choice([15, 35, 60]), rng.randrange(1, 10 ** 6))
+                      for _ in range(rng.choice([2, 3, 4])))
+        out.append((cn, rng.choice([1, 2]) if multi else rng.choice([0, 1, 2]),
+                    rng.choice([2, 2, 3, 4]), rng.choice([0, 1]),
+                    rng.choice([2, 3, 4, 6]) if multi else 1, steps))
+    return out
+
+
+def _case_id(c):
+    return "-".join([c[0]] + [str(x) for x in c[1:5]] + [s[0] for s in c[5]])
+
+
+@pytest.mark.parametrize("case", _sequence_cases(6, 101, False), ids=_case_id)
+def test_fuzz_operation_sequences(case, emu_lib, ref_lib):
+    """Random chains of refine (positive, negative, clamped) / coarsen /
+    duplicate with a balance after each, every intermediate octant array and
+    the final node arrays against the oracle."""
+    cn, level, order, corner, _, steps = case
+    conn = util.CONNS[cn]()
+    res = []
+    for lib in (ref_lib, emu_lib):
+        f = util.build_forest(lib, conn, level, 0, 0, corner, order)
+        stages = []
+        for kind, pct, seed in steps:
+            if f.getOctants().as_array().shape[0] > 40000 and kind.startswith("refine"):
+                kind = "coarsen"
+            f = _apply_step(f, kind, pct, seed, corner)
+            stages.append(f.getOctants().as_array().copy())
+        res.append((stages, util.node_results(f)))
+    for k, (a, b) in enumerate(zip(res[0][0], res[1][0])):
+        util.assert_octants_equal(a, b, "%s stage %d" % (case, k))
+    util.assert_nodes_equal(res[0][1], res[1][1], "sequence %s" % (case,))
+
+
+@pytest.mark.parametrize("case", _sequence_cases(4, 21, True), ids=_case_id)
+def test_fuzz_operation_sequences_multi_rank(case, emu_lib, ref_lib):
+    cn, level, order, corner, ranks, steps = case
+    conn = util.CONNS[cn]()
+
+    def body(lib, rank):
+        from tmr_b200.forest import OctForest
+        f = OctForest(order=order, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(level)
+        f.repartition()
+        stages = []
+        for kind, pct, seed in steps:
+            f = _apply_step(f, kind, pct, seed, corner)
+            stages.append(f.getOctants().as_array().copy())
+        return stages, util.node_results(f)
+
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_rank_results(a, b, "sequence %s" % (case,))
+
+
+def _interp_cases(n, seed):
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        fo = rng.choice([2, 3, 4, 5])
+        co = min(fo, rng.choice([2, 3, 4]))
+        it = rng.choice([1, 1, 2])
+        if it == 2 and fo - co > 1:
+            co = fo - 1
+        out.append((rng.choice(NAMES), rng.choice([1, 2]), fo, co, it,
+                    rng.randrange(1, 10 ** 6), rng.randrange(1, 10 ** 6),
+                    rng.choice([20, 40, 60]), rng.choice([10, 30, 50]),
+                    rng.choice(["unrelated", "coarser2", "same"])))
+    return out
+
+
+@pytest.mark.parametrize("case", _interp_cases(6, 11), ids=lambda c: "-".join(map(str, c)))
+def test_fuzz_interpolation_pairs(case, emu_lib, ref_lib):
+    """createInterpolation between forests that are NOT one coarsening apart:
+    an independently refined 'coarse' forest, two coarsenings, or the same
+    elements at a lower order (any order pair the reference accepts)."""
+    cn, level, fo, co, it, sa, sb, pa, pb, mode = case
+    conn = util.CONNS[cn]()
+    res = []
+    for lib in (ref_lib, emu_lib):
+        f = util.build_forest(lib, conn, level, 2, pa, 1, fo, seed=sa)
+        f.setMeshOrder(fo, it)
+        if mode == "unrelated":
+            c = util.build_forest(lib, conn, level, 1, pb, 1, co, seed=sb)
+        elif mode == "coarser2":
+            c = f.coarsen()
+            c.balance(1)
+            c = c.coarsen()
+            c.balance(1)
+        else:
+            c = f.duplicate()
+        c.setMeshOrder(co, it)
+        res.append(f.createInterpolation(c).get())
+    for a, b in zip(res[0][:3], res[1][:3]):
+        assert np.array_equal(a, b)
+    np.testing.assert_allclose(res[1][3], res[0][3], rtol=1e-12, atol=1e-300)
