@@ -200,3 +200,48 @@ def test_fuzz_interpolation_pairs(case, emu_lib, ref_lib):
     for a, b in zip(res[0][:3], res[1][:3]):
         assert np.array_equal(a, b)
     np.testing.assert_allclose(res[1][3], res[0][3], rtol=1e-12, atol=1e-300)
+
+
+def _scrambled_cases(n, seed):
+    rng = random.Random(seed)
+    out = []
+    for k in range(n):
+        ranks = rng.choice([1, 1, 2, 3])
+        out.append((rng.choice([(2, 2, 2), (3, 2, 1), (2, 2, 1), (3, 3, 1), (2, 1, 1)]),
+                    rng.choice([1, 2]) if ranks > 1 else rng.choice([0, 1, 2]),
+                    rng.choice([1, 2]), rng.choice([20, 40, 60]), rng.choice([0, 1]),
+                    rng.choice([2, 2, 3, 4]), rng.randrange(1, 10 ** 6), ranks,
+                    rng.randrange(1, 10 ** 6)))
+    return out
+
+
+@pytest.mark.parametrize("case", _scrambled_cases(8, 5), ids=lambda c: "-".join(map(str, c)))
+def test_fuzz_scrambled_tree_orientations(case, emu_lib, ref_lib):
+    """Boxes of trees with randomly permuted and flipped local axes (all 48
+    cube symmetries, left-handed trees included): the inter-tree transforms of
+    balance and of the node construction across every face / edge pairing."""
+    dims, level, passes, pct, corner, order, seed, ranks, conn_seed = case
+    conn = util.scrambled_conn(*dims, random.Random(conn_seed))
+    if ranks == 1:
+        res = []
+        for lib in (ref_lib, emu_lib):
+            f = util.build_forest(lib, conn, level, passes, pct, corner, order, seed=seed)
+            r = util.node_results(f)
+            coarse = f.coarsen() if order == 2 else f.duplicate()
+            if order == 2:
+                coarse.balance(1)
+            else:
+                coarse.setMeshOrder(order - 1)
+            res.append((f.getOctants().as_array().copy(), r,
+                        f.createInterpolation(coarse).get()))
+        util.assert_octants_equal(res[0][0], res[1][0], "scrambled %s" % (case,))
+        util.assert_nodes_equal(res[0][1], res[1][1], "scrambled %s" % (case,))
+        for a, b in zip(res[0][2][:3], res[1][2][:3]):
+            assert np.array_equal(a, b)
+        np.testing.assert_allclose(res[1][2][3], res[0][2][3], rtol=1e-12, atol=1e-300)
+    else:
+        body = multirank.adapt_body(conn, level, passes, pct, corner, order, True, seed=seed,
+                                    with_interp="repartitioned")
+        a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+        b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+        multirank.compare_rank_results(a, b, "scrambled %s" % (case,))

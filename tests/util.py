@@ -109,6 +109,26 @@ def butterfly_conn(cx, cy, cz):
     return np.array(out, dtype=np.int32)
 
 
+def scrambled_conn(nx, ny, nz, rng):
+    """nx x ny x nz box of trees whose local corner numbering is, tree by tree,
+    one of the 48 symmetries of the cube (axis permutation and flips), in a
+    shuffled tree order: every relative orientation of two trees across a face
+    or an edge occurs."""
+    import itertools
+    sym = [(p, f) for p in itertools.permutations(range(3)) for f in range(8)]
+    conn = structured_conn(nx, ny, nz)
+    out = np.zeros_like(conn)
+    for b in range(conn.shape[0]):
+        p, f = rng.choice(sym)
+        for c in range(8):
+            bits = [(c >> a) & 1 for a in range(3)]
+            nb = [bits[p[a]] ^ ((f >> a) & 1) for a in range(3)]
+            out[b, nb[0] | (nb[1] << 1) | (nb[2] << 2)] = conn[b, c]
+    perm = list(range(conn.shape[0]))
+    rng.shuffle(perm)
+    return np.ascontiguousarray(out[perm])
+
+
 CONNS = {
     "single": single_conn,
     "rectangle": rectangle_conn,
