@@ -245,3 +245,89 @@ def test_fuzz_scrambled_tree_orientations(case, emu_lib, ref_lib):
         a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
         b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
         multirank.compare_rank_results(a, b, "scrambled %s" % (case,))
+
+
+def _query_cases(n, seed):
+    rng = random.Random(seed)
+    return [(rng.choice([(2, 2, 1), (2, 1, 1), (2, 2, 2), (3, 2, 1)]), rng.choice([2, 3, 4]),
+             rng.choice([1, 2, 3, 4]), rng.choice([0, 1]), rng.randrange(1, 10 ** 6),
+             rng.randrange(1, 10 ** 6), rng.choice([1, 2]), rng.choice([0, 1, 2]),
+             rng.choice([1, 2, 3]), rng.choice([True, False]), rng.randrange(1, 10 ** 6))
+            for _ in range(n)]
+
+
+@pytest.mark.parametrize("case", _query_cases(5, 8), ids=lambda c: "-".join(map(str, c)))
+def test_fuzz_find_enclosing(case, emu_lib, ref_lib):
+    """findEnclosing asked about the nodes of an UNRELATED forest (other
+    levels, other refinement): hits name the same local element, misses the
+    same owner rank (reference :6228-6377)."""
+    from tmr_b200.forest import OctForest
+    dims, order, ranks, corner, sa, sb, la, lb, passes_b, lobatto, conn_seed = case
+    conn = util.scrambled_conn(*dims, random.Random(conn_seed))
+    kn = (-np.cos(np.pi * np.arange(order) / (order - 1)) if lobatto
+          else np.linspace(-1, 1, order))
+    kn[0], kn[-1] = -1.0, 1.0
+    q = util.build_forest(ref_lib, conn, lb, passes_b, 40, corner,
+                          seed=sb).getOctants().as_array().copy()
+    q["info"] = np.random.default_rng(sb).integers(0, order ** 3, len(q))
+
+    def body(lib, rank):
+        f = OctForest(order=order, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(la)
+        f.repartition()
+        for p in range(2):
+            f.refine(util.synth_flags(f.getOctants().as_array(), sa + p, 35))
+            f.balance(corner)
+            f.repartition()
+        idx, own = f.findEnclosing(order, kn, q)
+        return idx.copy(), own.copy()
+
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    for r in range(ranks):
+        hit = a[r][0] >= 0
+        assert np.array_equal(hit, b[r][0] >= 0), "rank %d: hit/miss" % r
+        assert np.array_equal(a[r][0][hit], b[r][0][hit]), "rank %d: element" % r
+        if ranks > 1:
+            assert np.array_equal(a[r][1][~hit], b[r][1][~hit]), "rank %d: owner" % r
+
+
+def _location_cases(n, seed):
+    rng = random.Random(seed)
+    return [(rng.choice([(2, 2, 1), (2, 1, 1), (2, 2, 2), (3, 2, 1)]), rng.choice([2, 3, 4, 5]),
+             rng.choice([0, 1]), rng.choice([1, 1, 2, 3]), rng.choice([0, 1]),
+             rng.randrange(1, 10 ** 6), rng.randrange(1, 10 ** 6)) for _ in range(n)]
+
+
+@pytest.mark.parametrize("case", _location_cases(5, 9), ids=lambda c: "-".join(map(str, c)))
+def test_fuzz_node_locations(case, emu_lib, ref_lib):
+    """getPoints over randomly placed trilinear trees (re-oriented, some of
+    them inverted): bit-equal locations, one and several ranks."""
+    from tmr_b200.forest import OctForest
+    dims, order, it, ranks, corner, seed, conn_seed = case
+    conn = util.scrambled_conn(*dims, random.Random(conn_seed))
+    xpts = np.random.default_rng(seed).normal(size=(int(conn.max()) + 1, 3)) * 3.0
+
+    def body(lib, rank):
+        f = OctForest(order=order, interp=it, lib=lib)
+        f.setTrilinearTopology(conn, xpts)
+        f.createTrees(1)
+        if ranks > 1:
+            f.repartition()
+        for p in range(2):
+            f.refine(util.synth_flags(f.getOctants().as_array(), seed + p, 30))
+            f.balance(corner)
+            if ranks > 1:
+                f.repartition()
+        f.createNodes()
+        return f.getNodeNumbers().copy(), f.getPoints().copy()
+
+    if ranks == 1:
+        a, b = [body(ref_lib, 0)], [body(emu_lib, 0)]
+    else:
+        a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+        b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    for r in range(ranks):
+        assert np.array_equal(a[r][0], b[r][0])
+        assert np.array_equal(a[r][1], b[r][1])
