@@ -168,6 +168,20 @@ int tmrc_set_trilinear_topology(tmrc_forest f, int num_nodes, const int *conn,
 /* getPoints (reference :1476-1481): borrowed pointer to num x (x,y,z) */
 int tmrc_get_points(tmrc_forest f, const double **xyz);
 
+/* ---- name queries (boundary conditions are applied through these) -----------
+   Name one entity of the topology attached by tmrc_set_trilinear_topology:
+   kind 0 vertex, 1 edge, 2 face, 3 volume; index in the numbering of
+   tmrc_get_connectivity; name NULL clears it.  Per backend, like the topology. */
+int tmrc_set_entity_name(tmrc_forest f, int kind, int index, const char *name);
+/* getOctsWithName (reference :5747-5862): local octants of a named volume, or
+   touching a named face (info = the face index).  Writes min(count, cap)
+   records, returns count (-1: no topology / no octants). */
+int tmrc_get_octs_with_name(tmrc_forest f, const char *name, tmrc_octant *out,
+                            int cap);
+/* getNodesWithName (reference :5882-6203): sorted unique numbers of the local
+   nodes on named vertices / edges / faces.  Same return convention. */
+int tmrc_get_nodes_with_name(tmrc_forest f, const char *name, int *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -243,3 +243,42 @@ def test_multirank_node_locations(ranks, emu_lib, ref_lib):
         assert len(a[r][1]) == len(a[r][0]) > 0
         assert np.array_equal(a[r][1], b[r][1]), r
 
+
+
+@pytest.mark.parametrize("ranks,order", [(2, 2), (3, 3)])
+def test_multirank_name_queries(ranks, order, emu_lib, ref_lib):
+    """getOctsWithName / getNodesWithName answer for the LOCAL octants and
+    nodes of each rank (reference src/TMROctForest.cpp:5747-5862, 5882-6203)."""
+    import random
+    conn = util.box_conn()
+    xpts = np.random.default_rng(3).uniform(-1, 1, (int(np.max(conn)) + 1, 3))
+
+    def body(lib, rank):
+        f = multirank.OctForest(order=order, lib=lib)
+        f.setTrilinearTopology(conn, xpts)
+        c = f.getConnectivity()
+        r = random.Random(5)
+        for kind, count in ((0, c["nnodes"]), (1, c["nedges"]), (2, c["nfaces"]),
+                            (3, c["nblocks"])):
+            for i in range(count):
+                name = r.choice([None, "fixed", "free"])
+                if name:
+                    f.setEntityName(kind, i, name)
+        f.createTrees(1)
+        f.repartition()
+        for p in range(2):
+            f.refine(util.synth_flags(f.getOctants().as_array(), 2024 + p, 30))
+            f.balance(1)
+            f.repartition()
+        f.createNodes()
+        return (f.getOctsWithName("fixed"), f.getOctsWithName("free"),
+                f.getNodesWithName("fixed"), f.getNodesWithName("free"))
+
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    total = 0
+    for r in range(ranks):
+        for x, y in zip(a[r], b[r]):
+            assert np.array_equal(x, y), r
+        total += len(b[r][2])
+    assert total > 0

@@ -637,3 +637,62 @@ def test_create_nodes_after_bare_refine(order, conn_name, impl, ref_lib):
         f.refine(util.synth_flags(f.getOctants().as_array(), 2024, 30))
         res.append(util.node_results(f))
     util.assert_nodes_equal(res[0], res[1], "bare refine")
+
+
+def _name_entities(f, seed, choices=(None, "clamped", "load")):
+    """Give every vertex / edge / face / volume of the stand-in topology a
+    random name (or none), identically for every backend."""
+    import random
+    c = f.getConnectivity()
+    r = random.Random(seed)
+    for kind, count in ((OctForest.VERTEX, c["nnodes"]), (OctForest.EDGE, c["nedges"]),
+                        (OctForest.FACE, c["nfaces"]), (OctForest.VOLUME, c["nblocks"])):
+        for i in range(count):
+            name = r.choice(choices)
+            if name:
+                f.setEntityName(kind, i, name)
+
+
+@pytest.mark.parametrize("order,conn_name,level", [(2, "box7", 1), (3, "box7", 1),
+                                                   (4, "connector15", 0), (2, "butterfly2", 1),
+                                                   (2, "single", 0)])
+def test_name_queries(order, conn_name, level, impl, ref_lib):
+    """getOctsWithName / getNodesWithName (reference src/TMROctForest.cpp:
+    5747-5862, 5882-6203), the calls boundary conditions are applied through:
+    the unmodified reference over a stand-in topology with nameable entities
+    against the drop-in, including a level-0 forest (root octants touch all six
+    faces) and a name nothing carries."""
+    conn = util.CONNS[conn_name]()
+    xpts = _warped_points(conn)
+    res = []
+    for lib in (ref_lib, impl):
+        f = OctForest(order=order, lib=lib)
+        f.setTrilinearTopology(conn, xpts)
+        _name_entities(f, 7)
+        f.createTrees(level)
+        octs0 = [f.getOctsWithName(n) for n in ("clamped", "load")]
+        for p in range(2 if level else 1):
+            f.refine(util.synth_flags(f.getOctants().as_array(), 2024 + p, 30))
+            f.balance(1)
+        f.createNodes()
+        res.append(octs0 + [f.getOctsWithName(n) for n in ("clamped", "load", "nobody")]
+                   + [f.getNodesWithName(n) for n in ("clamped", "load", "nobody")])
+    for k, (a, b) in enumerate(zip(*res)):
+        assert np.array_equal(a, b), "query %d differs" % k
+    assert len(res[1][2]) > 0 and len(res[1][5]) > 0 and len(res[1][7]) == 0
+
+
+def test_name_queries_unnamed(impl, ref_lib):
+    """a NULL name asks for the entities that carry no name (:5785, :5991)"""
+    conn = util.box_conn()
+    res = []
+    for lib in (ref_lib, impl):
+        f = OctForest(order=2, lib=lib)
+        f.setTrilinearTopology(conn, _warped_points(conn))
+        f.createTrees(1)
+        f.refine(util.synth_flags(f.getOctants().as_array(), 9, 30))
+        f.balance(0)
+        f.createNodes()
+        res.append((f.getOctsWithName(None), f.getNodesWithName(None)))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert len(res[1][0]) == len(f.getOctants().as_array())  # every volume is unnamed

@@ -366,4 +366,27 @@ int tmrc_get_points(tmrc_forest f, const double **xyz) {
   return X ? n : 0;
 }
 
+int tmrc_get_octs_with_name(tmrc_forest f, const char *name, tmrc_octant *out,
+                            int cap) {
+  TMROctantArray *list = F(f)->getOctsWithName(name);
+  if (!list) return -1;
+  TMROctant *a;
+  int n;
+  list->getArray(&a, &n);
+  for (int i = 0; i < n && i < cap; i++) {
+    memcpy(&out[i], &a[i], sizeof(tmrc_octant));
+  }
+  delete list;
+  return n;
+}
+
+int tmrc_get_nodes_with_name(tmrc_forest f, const char *name, int *out, int cap) {
+  int *nodes = NULL;
+  const int n = F(f)->getNodesWithName(name, &nodes);
+  if (!nodes) return -1;
+  for (int i = 0; i < n && i < cap; i++) out[i] = nodes[i];
+  delete[] nodes;
+  return n;
+}
+
 }  // extern "C"

@@ -1339,27 +1339,166 @@ TMROctantArray *TMROctForest::sendOctants(TMROctantArray *list,
   return new TMROctantArray(recv, recv_size, use_node_index);
 }
 
-/* ---- CAD-name queries and writers: need the CAD layer (out of scope) -------------------------- */
+/* ---- name queries -------------------------------------------------------------
+   Boundary conditions and material regions are attached through the names of the
+   topology's volumes, faces, edges and vertices.  Both queries are host loops
+   over the octant mirror (and, for nodes, the conn mirror) like the reference's;
+   what an octant touches follows from its coordinates alone. */
+namespace {
+/* the reference's test: a NULL query matches unnamed entities */
+inline bool name_matches(const TMREntity *e, const char *name) {
+  const char *n = e ? e->getName() : NULL;
+  return name ? (n && strcmp(n, name) == 0) : (n == NULL);
+}
+/* which sides of its tree an octant touches: lo[a] / hi[a] per axis */
+struct TreeSides {
+  bool lo[3], hi[3];
+  TreeSides(const TMROctant &o) {
+    const int32_t hmax = 1 << TMR_MAX_LEVEL;
+    const int32_t h = 1 << (TMR_MAX_LEVEL - o.level);
+    const int32_t p[3] = {o.x, o.y, o.z};
+    for (int a = 0; a < 3; a++) {
+      lo[a] = (p[a] == 0);
+      hi[a] = (p[a] + h == hmax);
+    }
+  }
+  bool on(int a) const { return lo[a] || hi[a]; }
+  bool side(int a, int s) const { return s ? hi[a] : lo[a]; }
+};
+}  // namespace
+
+/* reference :5747-5862: octants of a named volume as they are; otherwise one
+   copy per named tree face the octant touches, info = the face index */
 TMROctantArray *TMROctForest::getOctsWithName(const char *name) {
-  (void)name;
   if (!topo) {
     fprintf(stderr,
-            "TMROctForest Error: getOctsWithName() requires a topology\n");
+            "TMROctForest Error: Must define topology to use "
+            "getOctsWithName()\n");
     return NULL;
   }
-  fprintf(stderr,
-          "TMROctForest Error: getOctsWithName() is not part of the B200 "
-          "hot-path build\n");
-  return NULL;
+  TMROctantArray *local = NULL;
+  if (tables) getOctants(&local);
+  if (!local) {
+    fprintf(stderr,
+            "TMROctForest: Must create octants to use getOctsWithName()\n");
+    return NULL;
+  }
+  TMROctant *array;
+  int size;
+  local->getArray(&array, &size);
+  std::vector<TMROctant> found;
+  for (int i = 0; i < size; i++) {
+    const TMROctant &o = array[i];
+    TMRVolume *vol = NULL;
+    topo->getVolume(o.block, &vol);
+    if (name_matches(vol, name)) {
+      found.push_back(o);
+      continue;
+    }
+    const TreeSides t(o);
+    for (int a = 0; a < 3; a++) {
+      for (int s = 0; s < 2; s++) {
+        /* a root octant touches both sides; below the root the reference
+           looks at the low side first and never at both (:5808-5853) */
+        if (!t.side(a, s) || (o.level > 0 && s == 1 && t.lo[a])) continue;
+        const int face_index = 2 * a + s;
+        TMRFace *face = NULL;
+        topo->getFace(tables->block_face_conn[6 * o.block + face_index], &face);
+        if (name_matches(face, name)) {
+          found.push_back(o);
+          found.back().info = face_index;
+        }
+      }
+    }
+  }
+  TMROctant *out = new TMROctant[found.empty() ? 1 : found.size()];
+  if (!found.empty()) memcpy(out, found.data(), found.size() * sizeof(TMROctant));
+  return new TMROctantArray(out, (int)found.size());
 }
 
+/* reference :5882-6203: sorted unique numbers of the nodes of every local
+   element that lie on a named vertex, edge or face of the element's tree.  (A
+   matching VOLUME name adds nothing there -- the loop at :6174-6181 never
+   advances its counter -- and nothing here.) */
 int TMROctForest::getNodesWithName(const char *name, int **_nodes) {
-  (void)name;
   if (_nodes) *_nodes = NULL;
-  fprintf(stderr,
-          "TMROctForest Error: getNodesWithName() requires the CAD topology "
-          "layer, which is not part of the B200 hot-path build\n");
-  return 0;
+  if (!topo) {
+    fprintf(stderr,
+            "TMROctForest Error: Must define topology to use "
+            "getNodesWithName()\n");
+    return 0;
+  }
+  const int *c_all = NULL;
+  int nelems = 0;
+  if (nodes_exist) getNodeConn(&c_all, &nelems);
+  if (!c_all) {
+    fprintf(stderr,
+            "TMROctForest Error: Nodes must be created before calling "
+            "getNodesWithName()\n");
+    return 0;
+  }
+  TMROctantArray *local = NULL;
+  getOctants(&local);
+  TMROctant *octs;
+  int size;
+  local->getArray(&octs, &size);
+  const int p = mesh_order, p2 = p * p, npe = p * p * p;
+  std::vector<int> list;
+  for (int i = 0; i < size; i++) {
+    const TMROctant &o = octs[i];
+    const TreeSides t(o);
+    const int non = (t.on(0) ? 1 : 0) + (t.on(1) ? 1 : 0) + (t.on(2) ? 1 : 0);
+    if (non == 0) continue;
+    const int *c = &c_all[(size_t)npe * o.tag];
+    const int stride[3] = {1, p, p2};
+    if (non == 3) {
+      for (int v = 0; v < 8; v++) {
+        if (!(t.side(0, v & 1) && t.side(1, (v >> 1) & 1) && t.side(2, v >> 2))) continue;
+        TMRVertex *vert = NULL;
+        topo->getVertex(tables->block_conn[8 * o.block + v], &vert);
+        if (name_matches(vert, name)) {
+          list.push_back(c[(p - 1) * ((v & 1) + p * ((v >> 1) & 1) + p2 * (v >> 2))]);
+        }
+      }
+    }
+    if (non >= 2) {
+      for (int e = 0; e < 12; e++) {
+        /* edge e runs along axis e/4; (e & 1, (e >> 1) & 1) are the sides of the
+           other two axes in ascending axis order (reference edge numbering) */
+        const int along = e / 4;
+        const int a1 = (along == 0) ? 1 : 0, a2 = (along == 2) ? 1 : 2;
+        const int s1 = e & 1, s2 = (e >> 1) & 1;
+        if (!(t.side(a1, s1) && t.side(a2, s2))) continue;
+        TMREdge *edge = NULL;
+        topo->getEdge(tables->block_edge_conn[12 * o.block + e], &edge);
+        if (!name_matches(edge, name)) continue;
+        const int base = (p - 1) * (s1 * stride[a1] + s2 * stride[a2]);
+        for (int q = 0; q < p; q++) list.push_back(c[base + q * stride[along]]);
+      }
+    }
+    for (int f = 0; f < 6; f++) {
+      const int a = f / 2;
+      if (!t.side(a, f & 1)) continue;
+      TMRFace *face = NULL;
+      topo->getFace(tables->block_face_conn[6 * o.block + f], &face);
+      if (!name_matches(face, name)) continue;
+      const int a1 = (a == 0) ? 1 : 0, a2 = (a == 2) ? 1 : 2;
+      const int base = (p - 1) * (f & 1) * stride[a];
+      for (int r = 0; r < p; r++) {
+        for (int q = 0; q < p; q++) list.push_back(c[base + q * stride[a1] + r * stride[a2]]);
+      }
+    }
+  }
+  std::sort(list.begin(), list.end());
+  list.erase(std::unique(list.begin(), list.end()), list.end());
+  int *out = new int[list.empty() ? 1 : list.size()];
+  if (!list.empty()) memcpy(out, list.data(), list.size() * sizeof(int));
+  if (_nodes) {
+    *_nodes = out;
+  } else {
+    delete[] out;
+  }
+  return (int)list.size();
 }
 
 void TMROctForest::writeToVTK(const char *filename) {

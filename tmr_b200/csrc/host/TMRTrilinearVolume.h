@@ -57,11 +57,30 @@ class TMRTrilinearTopology : public TMRTopology {
       v->incref();
       vols.push_back(v);
     }
+    /* one nameable entity per super-mesh vertex / edge / face (name queries) */
+    for (int i = 0; i < nn; i++) verts.push_back(held(new TMRVertex()));
+    for (int i = 0; i < ne; i++) edges.push_back(held(new TMREdge()));
+    for (int i = 0; i < nf; i++) faces.push_back(held(new TMRFace()));
   }
   ~TMRTrilinearTopology() {
     for (size_t i = 0; i < vols.size(); i++) vols[i]->decref();
+    for (size_t i = 0; i < verts.size(); i++) verts[i]->decref();
+    for (size_t i = 0; i < edges.size(); i++) edges[i]->decref();
+    for (size_t i = 0; i < faces.size(); i++) faces[i]->decref();
   }
   void getVolume(int vol_num, TMRVolume **volume) { *volume = vols[vol_num]; }
+  void getFace(int face_num, TMRFace **face) { *face = faces[face_num]; }
+  void getEdge(int edge_num, TMREdge **edge) { *edge = edges[edge_num]; }
+  void getVertex(int vertex_num, TMRVertex **vertex) { *vertex = verts[vertex_num]; }
+  /* kind 0 vertex, 1 edge, 2 face, 3 volume; NULL if out of range */
+  TMREntity *entity(int kind, int index) {
+    if (index < 0) return NULL;
+    if (kind == 0 && index < nn) return verts[index];
+    if (kind == 1 && index < ne) return edges[index];
+    if (kind == 2 && index < nf) return faces[index];
+    if (kind == 3 && index < nb) return vols[index];
+    return NULL;
+  }
   void getConnectivity(int *nnodes, int *nedges, int *nfaces, int *nvolumes,
                        const int **volume_nodes, const int **volume_edges,
                        const int **volume_faces) {
@@ -78,6 +97,14 @@ class TMRTrilinearTopology : public TMRTopology {
   int nn, ne, nf, nb;
   std::vector<int> bc, bec, bfc;
   std::vector<TMRTrilinearVolume *> vols;
+  std::vector<TMRVertex *> verts;
+  std::vector<TMREdge *> edges;
+  std::vector<TMRFace *> faces;
+  template <class T>
+  static T *held(T *e) {
+    e->incref();
+    return e;
+  }
 };
 
 #endif

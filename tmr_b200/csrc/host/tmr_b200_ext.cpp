@@ -58,4 +58,15 @@ int tmrc_set_trilinear_topology(tmrc_forest f, int num_nodes, const int *conn,
   return 0;
 }
 
+/* declared in tmr_capi.h */
+int tmrc_set_entity_name(tmrc_forest f, int kind, int index, const char *name) {
+  TMROctForest *forest = static_cast<TMROctForest *>(f);
+  TMRTrilinearTopology *topo =
+      dynamic_cast<TMRTrilinearTopology *>(forest->getTopology());
+  TMREntity *e = topo ? topo->entity(kind, index) : NULL;
+  if (!e) return 1;
+  e->setName(name);
+  return 0;
+}
+
 }  // extern "C"

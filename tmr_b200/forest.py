@@ -324,6 +324,47 @@ class OctForest:
             return np.zeros((0, 3))
         return _capi.as_double_array(ptr, 3 * n).reshape(n, 3).copy()
 
+    # ---- name queries -----------------------------------------------------------
+    VERTEX, EDGE, FACE, VOLUME = 0, 1, 2, 3
+
+    def setEntityName(self, kind, index, name):
+        """Name a vertex / edge / face / volume of the topology attached by
+        setTrilinearTopology (index in the numbering of getConnectivity)."""
+        self._lib.tmrc_set_entity_name.restype = C.c_int
+        self._lib.tmrc_set_entity_name.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        raw = None if name is None else name.encode()
+        if self._lib.tmrc_set_entity_name(self._ptr, kind, index, raw) != 0:
+            raise ValueError("no entity of kind %d with index %d" % (kind, index))
+
+    def getOctsWithName(self, name):
+        """Local octants of a named volume, or touching a named tree face
+        (info = face index) (reference getOctsWithName :5747-5862)."""
+        f = self._lib.tmrc_get_octs_with_name
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
+        raw = None if name is None else name.encode()
+        # at most three faces per octant (six for a root octant)
+        cap = 6 * max(1, self._lib.tmrc_num_octants(self._ptr))
+        out = np.zeros(cap, dtype=_capi.OCT_DTYPE)
+        n = f(self._ptr, raw, out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError("getOctsWithName: no topology or no octants")
+        return out[:n].copy()
+
+    def getNodesWithName(self, name):
+        """Sorted unique numbers of the local nodes on named vertices, edges
+        and faces (reference getNodesWithName :5882-6203)."""
+        f = self._lib.tmrc_get_nodes_with_name
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
+        raw = None if name is None else name.encode()
+        n = f(self._ptr, raw, None, 0)
+        if n < 0:
+            raise RuntimeError("getNodesWithName: no topology or no nodes")
+        out = np.zeros(max(n, 1), dtype=np.int32)
+        n = f(self._ptr, raw, out.ctypes.data, n)
+        return out[:n].copy()
+
     # ---- B200 extensions (include/tmr_b200_ext.h, include/tmrgpu.h) ----------
     def createInterpolationCSR(self, coarse):
         """The whole prolongation in one hand-off: (rows, rowp, cols, vals),
