@@ -182,6 +182,11 @@ int tmrc_get_octs_with_name(tmrc_forest f, const char *name, tmrc_octant *out,
    nodes on named vertices / edges / faces.  Same return convention. */
 int tmrc_get_nodes_with_name(tmrc_forest f, const char *name, int *out, int cap);
 
+/* ---- text writers (reference :1149-1384) --------------------------------------
+   which 0: writeToVTK (super-mesh), 1: writeToTecplot (super-mesh),
+   2: writeForestToVTK (every local octant as a brick) */
+void tmrc_write(tmrc_forest f, int which, const char *filename);
+
 #ifdef __cplusplus
 }
 #endif

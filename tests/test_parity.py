@@ -696,3 +696,27 @@ def test_name_queries_unnamed(impl, ref_lib):
         res.append((f.getOctsWithName(None), f.getNodesWithName(None)))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert len(res[1][0]) == len(f.getOctants().as_array())  # every volume is unnamed
+
+
+def test_text_writers(impl, ref_lib, tmp_path):
+    """writeToVTK / writeToTecplot (super-mesh) and writeForestToVTK (every
+    octant as a brick) (reference src/TMROctForest.cpp:1149-1384): the files
+    of the unmodified reference, byte for byte."""
+    conn = util.box_conn()
+    xpts = _warped_points(conn)
+    out = []
+    for tag, lib in (("ref", ref_lib), ("impl", impl)):
+        f = OctForest(order=2, lib=lib)
+        f.setTrilinearTopology(conn, xpts)
+        f.createTrees(1)
+        f.refine(util.synth_flags(f.getOctants().as_array(), 3, 30))
+        f.balance(1)
+        files = []
+        for name, write in (("mesh.vtk", f.writeToVTK), ("mesh.dat", f.writeToTecplot),
+                            ("forest.vtk", f.writeForestToVTK)):
+            path = tmp_path / (tag + "_" + name)
+            write(path)
+            files.append(path.read_bytes())
+        out.append(files)
+    for a, b in zip(*out):
+        assert len(a) > 200 and a == b

@@ -389,4 +389,10 @@ int tmrc_get_nodes_with_name(tmrc_forest f, const char *name, int *out, int cap)
   return n;
 }
 
+void tmrc_write(tmrc_forest f, int which, const char *filename) {
+  if (which == 0) F(f)->writeToVTK(filename);
+  if (which == 1) F(f)->writeToTecplot(filename);
+  if (which == 2) F(f)->writeForestToVTK(filename);
+}
+
 }  // extern "C"

@@ -1501,23 +1501,120 @@ int TMROctForest::getNodesWithName(const char *name, int **_nodes) {
   return (int)list.size();
 }
 
+/* ---- writers (reference :1149-1384): plain-text dumps of the super-mesh and of
+   the forest, for visual checks.  They need nothing from the CAD layer beyond
+   TMRVolume::evalPoint, so they work with any topology; the text is the
+   reference's, byte for byte. */
+namespace {
+/* VTK / Tecplot brick order of a tree's (or an octant's) 8 corners */
+const int kBrick[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+
+void vtk_cells(FILE *fp, int ncells, const int *conn /* NULL: 8 k + c */, int base) {
+  fprintf(fp, "\nCELLS %d %d\n", ncells, 9 * ncells);
+  for (int k = 0; k < ncells; k++) {
+    fprintf(fp, "8");
+    for (int c = 0; c < 8; c++) {
+      fprintf(fp, " %d", (conn ? conn[8 * k + kBrick[c]] : 8 * k + kBrick[c]) + base);
+    }
+    fprintf(fp, "\n");
+  }
+  fprintf(fp, "\nCELL_TYPES %d\n", ncells);
+  for (int k = 0; k < ncells; k++) fprintf(fp, "12\n");
+  fprintf(fp, "CELL_DATA %d\n", ncells);
+  fprintf(fp, "SCALARS entity_index float 1\n");
+  fprintf(fp, "LOOKUP_TABLE default\n");
+}
+}  // namespace
+
+/* location of every super-mesh node: the owning tree's volume evaluated at the
+   corner the node sits on (reference :1164-1196) */
+void TMROctForest::superMeshPoints(std::vector<TMRPoint> &X) {
+  X.assign(tables->num_nodes > 0 ? tables->num_nodes : 1, TMRPoint());
+  for (int k = 0; k < tables->num_nodes; k++) {
+    const int block = tables->node_block_owners[k];
+    int corner = 0;
+    while (corner < 8 && tables->block_conn[8 * block + corner] != k) corner++;
+    TMRVolume *vol = NULL;
+    topo->getVolume(block, &vol);
+    X[k].zero();
+    if (vol) vol->evalPoint(corner & 1 ? 1.0 : 0.0, corner & 2 ? 1.0 : 0.0,
+                            corner & 4 ? 1.0 : 0.0, &X[k]);
+  }
+}
+
 void TMROctForest::writeToVTK(const char *filename) {
-  (void)filename;
-  fprintf(stderr,
-          "TMROctForest Error: writeToVTK() requires node locations from the "
-          "CAD layer, which is not part of the B200 hot-path build\n");
+  if (mpi_rank != 0 || !topo || !tables) return;
+  FILE *fp = fopen(filename, "w");
+  if (!fp) return;
+  std::vector<TMRPoint> X;
+  superMeshPoints(X);
+  fprintf(fp, "# vtk DataFile Version 3.0\n");
+  fprintf(fp, "vtk output\nASCII\n");
+  fprintf(fp, "DATASET UNSTRUCTURED_GRID\n");
+  fprintf(fp, "POINTS %d float\n", tables->num_nodes);
+  for (int k = 0; k < tables->num_nodes; k++) {
+    fprintf(fp, "%e %e %e\n", X[k].x, X[k].y, X[k].z);
+  }
+  vtk_cells(fp, tables->num_blocks, tables->block_conn, 0);
+  for (int k = 0; k < tables->num_blocks; k++) fprintf(fp, "%e\n", 1.0 * k);
+  fclose(fp);
 }
 
 void TMROctForest::writeToTecplot(const char *filename) {
-  (void)filename;
-  fprintf(stderr,
-          "TMROctForest Error: writeToTecplot() requires node locations from "
-          "the CAD layer, which is not part of the B200 hot-path build\n");
+  if (mpi_rank != 0 || !topo || !tables) return;
+  FILE *fp = fopen(filename, "w");
+  if (!fp) return;
+  const int nn = tables->num_nodes, nb = tables->num_blocks;
+  std::vector<TMRPoint> X;
+  superMeshPoints(X);
+  fprintf(fp, "Variables = X,Y,Z,block\n");
+  fprintf(fp, "Zone N = %d E = %d ", nn, nb);
+  fprintf(fp, "DATAPACKING=BLOCK, ZONETYPE=FEBRICK\n");
+  fprintf(fp, "VARLOCATION = ([4]=CELLCENTERED)\n");
+  for (int k = 0; k < nn; k++) fprintf(fp, "%e\n", X[k].x);
+  for (int k = 0; k < nn; k++) fprintf(fp, "%e\n", X[k].y);
+  for (int k = 0; k < nn; k++) fprintf(fp, "%e\n", X[k].z);
+  for (int k = 0; k < nb; k++) fprintf(fp, "%e\n", 1.0 * k);
+  for (int k = 0; k < nb; k++) {
+    for (int c = 0; c < 8; c++) {
+      fprintf(fp, c ? " %d" : "%d", tables->block_conn[8 * k + kBrick[c]] + 1);
+    }
+    fprintf(fp, "\n");
+  }
+  fclose(fp);
 }
 
+/* every local octant as its own brick, coloured by tree (reference :1317-1384;
+   each rank writes the file it is given) */
 void TMROctForest::writeForestToVTK(const char *filename) {
-  (void)filename;
-  fprintf(stderr,
-          "TMROctForest Error: writeForestToVTK() requires the CAD topology "
-          "layer, which is not part of the B200 hot-path build\n");
+  if (!topo || !tables) return;
+  TMROctantArray *local = NULL;
+  getOctants(&local);
+  if (!local) return;
+  FILE *fp = fopen(filename, "w");
+  if (!fp) return;
+  TMROctant *octs;
+  int size;
+  local->getArray(&octs, &size);
+  fprintf(fp, "# vtk DataFile Version 3.0\n");
+  fprintf(fp, "vtk output\nASCII\n");
+  fprintf(fp, "DATASET UNSTRUCTURED_GRID\n");
+  fprintf(fp, "POINTS %d float\n", 8 * size);
+  const int32_t hmax = 1 << TMR_MAX_LEVEL;
+  for (int k = 0; k < size; k++) {
+    const int32_t h = 1 << (TMR_MAX_LEVEL - octs[k].level);
+    TMRVolume *vol = NULL;
+    topo->getVolume(octs[k].block, &vol);
+    for (int c = 0; c < 8; c++) {
+      TMRPoint p;
+      p.zero();
+      vol->evalPoint(1.0 * (octs[k].x + (c & 1) * h) / hmax,
+                     1.0 * (octs[k].y + ((c >> 1) & 1) * h) / hmax,
+                     1.0 * (octs[k].z + (c >> 2) * h) / hmax, &p);
+      fprintf(fp, "%e %e %e\n", p.x, p.y, p.z);
+    }
+  }
+  vtk_cells(fp, size, NULL, 0);
+  for (int k = 0; k < size; k++) fprintf(fp, "%e\n", 1.0 * octs[k].block);
+  fclose(fp);
 }

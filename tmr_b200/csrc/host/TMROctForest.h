@@ -11,6 +11,8 @@
 #ifndef TMR_OCTANT_FOREST_H
 #define TMR_OCTANT_FOREST_H
 
+#include <vector>
+
 #include "TACSBVecInterp.h"
 #include "TMROctant.h"
 #include "TMRTopology.h"
@@ -143,6 +145,7 @@ class TMROctForest : public TMREntity {
   };
 
   void dropTables();
+  void superMeshPoints(std::vector<TMRPoint> &X);
   void dropMeshData(int drop_octants, int drop_owners);
   void dropHostNodeMirrors();
   void pushTablesToDevice();

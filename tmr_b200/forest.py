@@ -365,6 +365,21 @@ class OctForest:
         n = f(self._ptr, raw, out.ctypes.data, n)
         return out[:n].copy()
 
+    # ---- text writers (reference :1149-1384) -------------------------------------
+    def _write(self, which, filename):
+        self._lib.tmrc_write.restype = None
+        self._lib.tmrc_write.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        self._lib.tmrc_write(self._ptr, which, str(filename).encode())
+
+    def writeToVTK(self, filename):
+        self._write(0, filename)
+
+    def writeToTecplot(self, filename):
+        self._write(1, filename)
+
+    def writeForestToVTK(self, filename):
+        self._write(2, filename)
+
     # ---- B200 extensions (include/tmr_b200_ext.h, include/tmrgpu.h) ----------
     def createInterpolationCSR(self, coarse):
         """The whole prolongation in one hand-off: (rows, rowp, cols, vals),
