@@ -64,6 +64,11 @@ def main():
     X = geo.getPoints()           # evaluateNodeLocations on the GPU
     print("node locations: %d points, bounding box %s .. %s"
           % (len(X), np.round(X.min(axis=0), 2), np.round(X.max(axis=0), 2)))
+    # boundary conditions go through names: clamp the nodes of one tree face
+    face = int(geo.getConnectivity()["block_face_conn"][0])
+    geo.setEntityName(tmr_b200.OctForest.FACE, face, "clamped")
+    print("face %d named 'clamped': %d octants touch it, %d nodes lie on it"
+          % (face, len(geo.getOctsWithName("clamped")), len(geo.getNodesWithName("clamped"))))
 
 
 if __name__ == "__main__":
