@@ -331,3 +331,48 @@ def test_fuzz_node_locations(case, emu_lib, ref_lib):
     for r in range(ranks):
         assert np.array_equal(a[r][0], b[r][0])
         assert np.array_equal(a[r][1], b[r][1])
+
+
+def _sparse_rank_cases(n, seed):
+    rng = random.Random(seed)
+    return [(rng.choice(["single", "rectangle", "single", "box7"]), rng.choice([0, 0, 1]),
+             rng.choice([2, 2, 3, 4]), rng.choice([0, 1]), rng.choice([3, 4, 5, 8]),
+             rng.choice([1, 2, 3]), rng.choice([20, 50, 80]), rng.randrange(1, 10 ** 6),
+             rng.choice(["always", "never", "end", "first"])) for _ in range(n)]
+
+
+@pytest.mark.parametrize("case", _sparse_rank_cases(6, 31), ids=lambda c: "-".join(map(str, c)))
+def test_fuzz_more_ranks_than_elements(case, emu_lib, ref_lib):
+    """Ranks that hold no element, own no node or receive nothing: forests of one
+    or two trees at level 0/1 on up to 8 ranks, repartitioned always / never /
+    once, through refine, balance, createNodes and a same-mesh prolongation."""
+    from tmr_b200.forest import OctForest
+    cn, level, order, corner, ranks, passes, pct, seed, repart = case
+    conn = util.CONNS[cn]()
+
+    def body(lib, rank):
+        f = OctForest(order=order, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(level)
+        if repart in ("always", "first"):
+            f.repartition()
+        stages = []
+        for p in range(passes):
+            f.refine(util.synth_flags(f.getOctants().as_array(), seed + p, pct))
+            f.balance(corner)
+            if repart == "always":
+                f.repartition()
+            stages.append(f.getOctants().as_array().copy())
+        if repart == "end":
+            f.repartition()
+        res = util.node_results(f)
+        c = f.duplicate()
+        if order > 2:
+            c.setMeshOrder(order - 1)
+        rows, d = util.interp_rows(f.createInterpolation(c))
+        res["interp"] = {k: (cc.copy(), w.copy()) for k, (cc, w) in d.items()}
+        return stages, res
+
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_rank_results(a, b, "sparse ranks %s" % (case,))

@@ -186,8 +186,12 @@ def assert_nodes_equal(a, b, what="", rtol=1e-12):
     assert np.array_equal(a["conn"], b["conn"]), what + ": conn differs"
     assert np.array_equal(a["node_numbers"], b["node_numbers"]), what + ": node numbers"
     assert np.array_equal(a["node_range"], b["node_range"]), what + ": node_range"
-    assert a["ext_pre"] == b["ext_pre"], what + ": ext_pre_offset"
     assert a["num_owned"] == b["num_owned"], what + ": owned count"
+    if a["num_owned"] > 0:
+        # a rank that owns no node: the reference's bsearch for node_range[rank]
+        # finds nothing and ext_pre_offset is the difference to a NULL pointer
+        # (src/TMROctForest.cpp:4260-4264); here it is the lower bound
+        assert a["ext_pre"] == b["ext_pre"], what + ": ext_pre_offset"
     pa, ca, wa = a["dep"]
     pb, cb, wb = b["dep"]
     assert np.array_equal(pa, pb), what + ": dep_ptr differs"
