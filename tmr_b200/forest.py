@@ -343,12 +343,11 @@ class OctForest:
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
         raw = None if name is None else name.encode()
-        # at most three faces per octant (six for a root octant)
-        cap = 6 * max(1, self._lib.tmrc_num_octants(self._ptr))
-        out = np.zeros(cap, dtype=_capi.OCT_DTYPE)
-        n = f(self._ptr, raw, out.ctypes.data, cap)
+        n = f(self._ptr, raw, None, 0)  # count, then fetch
         if n < 0:
             raise RuntimeError("getOctsWithName: no topology or no octants")
+        out = np.zeros(max(n, 1), dtype=_capi.OCT_DTYPE)
+        n = f(self._ptr, raw, out.ctypes.data, n)
         return out[:n].copy()
 
     def getNodesWithName(self, name):
