@@ -376,3 +376,41 @@ def test_fuzz_more_ranks_than_elements(case, emu_lib, ref_lib):
     a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
     b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
     multirank.compare_rank_results(a, b, "sparse ranks %s" % (case,))
+
+
+def _max_rank_cases(n, seed):
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        ranks = rng.choice([2, 3, 4, 6])
+        out.append((rng.choice(["box7", "grid2", "connector15", "butterfly2"]), ranks,
+                    rng.choice([2, 3]), rng.choice([0, 1]), rng.randrange(1, 10 ** 6),
+                    tuple(rng.choice([0, 1, 2, ranks, ranks - 1, ranks + 3]) for _ in range(3))))
+    return out
+
+
+@pytest.mark.parametrize("case", _max_rank_cases(4, 12), ids=lambda c: "-".join(map(str, c)))
+def test_fuzz_repartition_max_rank(case, emu_lib, ref_lib):
+    """repartition(max_rank) (reference :1922-2088): the elements are dealt to
+    the first max_rank ranks only; values below 1 and above the rank count
+    included, the node construction afterwards on ranks left empty."""
+    from tmr_b200.forest import OctForest
+    cn, ranks, order, corner, seed, max_rank = case
+    conn = util.CONNS[cn]()
+
+    def body(lib, rank):
+        f = OctForest(order=order, lib=lib)
+        f.setConnectivity(conn)
+        f.createTrees(1)
+        f.repartition(max_rank[0])
+        stages = []
+        for p in range(2):
+            f.refine(util.synth_flags(f.getOctants().as_array(), seed + p, 35))
+            f.balance(corner)
+            f.repartition(max_rank[1 + p])
+            stages.append(f.getOctants().as_array().copy())
+        return stages, util.node_results(f)
+
+    a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+    b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    multirank.compare_rank_results(a, b, "max_rank %s" % (case,))
