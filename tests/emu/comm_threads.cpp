@@ -7,6 +7,8 @@
   thread-ranks on the CPU-only build container.
 */
 #include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -23,15 +25,32 @@ struct ThreadWorld {
   pthread_barrier_t bar;
   std::vector<const void *> ptr;
   std::vector<const i64 *> off;
+  /* what each rank believes the current collective is (kind, element size):
+     ranks that drift apart in their collective sequence would deadlock NCCL;
+     here they are caught at the rendezvous */
+  std::vector<size_t> tag;
   ThreadWorld() : ready(false), size(0) {}
 };
 
 class ThreadComm : public Comm {
  public:
   ThreadWorld *w;
+  void check_same_collective(size_t mine) {
+    for (int r = 0; r < size; r++) {
+      if (w->tag[r] != mine) {
+        fprintf(stderr,
+                "emulated communicator: rank %d is in collective %zx while rank %d is in "
+                "%zx -- the ranks' collective sequences diverged\n",
+                rank, mine, r, w->tag[r]);
+        abort();
+      }
+    }
+  }
   void allgather_host(Ctx &, const void *send, void *recv, size_t bytes) override {
     w->ptr[rank] = send;
+    w->tag[rank] = ((size_t)1 << 60) | bytes;
     pthread_barrier_wait(&w->bar);
+    check_same_collective(((size_t)1 << 60) | bytes);
     for (int r = 0; r < size; r++) {
       memcpy((char *)recv + (size_t)r * bytes, w->ptr[r], bytes);
     }
@@ -44,7 +63,9 @@ class ThreadComm : public Comm {
                  const i64 *recv_off, size_t eb) override {
     w->ptr[rank] = send;
     w->off[rank] = send_off;
+    w->tag[rank] = ((size_t)2 << 60) | eb;
     pthread_barrier_wait(&w->bar);
+    check_same_collective(((size_t)2 << 60) | eb);
     for (int p = 0; p < size; p++) {
       const i64 cnt = w->off[p][rank + 1] - w->off[p][rank];
       if (cnt > 0) {
@@ -75,6 +96,7 @@ Comm *comm_create(Ctx &, int rank, int size, const void *id_bytes) {
       pthread_barrier_init(&w->bar, NULL, size);
       w->ptr.assign(size, (const void *)0);
       w->off.assign(size, (const i64 *)0);
+      w->tag.assign(size, (size_t)0);
       w->ready = true;
     }
   }

@@ -48,6 +48,21 @@ def test_multirank_interpolation_uneven_depths(emu_lib, ref_lib):
     multirank.compare_rank_results(a, b, "uneven depths")
 
 
+def test_multirank_repartition_when_only_some_ranks_hold_info(emu_lib, ref_lib):
+    """16 elements on 8 ranks: after createNodes and a read of the octants some
+    ranks hold an `info` array and some do not; repartitioning the duplicate must
+    still run the SAME collectives on every rank (it used to exchange `info` only
+    where an array existed -- a deadlock under NCCL; the emulated communicator
+    aborts when the ranks' collective sequences diverge).  Found by the fuzz
+    runs."""
+    conn = util.CONNS["rectangle"]()
+    body = multirank.adapt_body(conn, 1, 1, 15, 0, 3, True, seed=673287,
+                                with_interp="repartitioned")
+    a = multirank.run_thread_ranks(ref_lib, 8, body, True)
+    b = multirank.run_thread_ranks(emu_lib, 8, body, False)
+    multirank.compare_rank_results(a, b, "partial info")
+
+
 @pytest.mark.parametrize("ranks", [2, 3])
 def test_multirank_bernstein_order3(ranks, emu_lib, ref_lib):
     """Labelled node keys (order-3 Bernstein points) through the multi-rank

@@ -86,10 +86,19 @@ inline int repartition(Forest &f, int max_rank) {
   const int R = comm->size, me = comm->rank;
   if (max_rank <= 0 || max_rank > R) max_rank = R;
   if (unify_depth(f)) return 1;
-  std::vector<i64> counts(R), ptr(R + 1, 0), nptr(R + 1, 0);
-  const i64 mine = f.n;
-  comm->allgather_host(ctx, &mine, counts.data(), sizeof(i64));
-  for (int k = 0; k < R; k++) ptr[k + 1] = ptr[k] + counts[k];
+  std::vector<i64> ptr(R + 1, 0), nptr(R + 1, 0);
+  /* element count and "carries an info array" of every rank in one gather: the
+     info exchange below is a collective, so whether it happens must not depend
+     on this rank alone (a rank without elements, or one whose octants were
+     uploaded with all-zero info, holds no array while its peers do) */
+  const i64 mine[2] = {f.n, f.info.get() ? 1 : 0};
+  std::vector<i64> all(2 * (size_t)R);
+  comm->allgather_host(ctx, mine, all.data(), sizeof(mine));
+  bool any_info = false;
+  for (int k = 0; k < R; k++) {
+    ptr[k + 1] = ptr[k] + all[2 * k];
+    any_info = any_info || all[2 * k + 1] != 0;
+  }
   const i64 total = ptr[R];
   const i64 avg = total / max_rank, rem = total - avg * max_rank;
   for (int k = 0; k < max_rank; k++) nptr[k + 1] = nptr[k] + avg + (k < rem ? 1 : 0);
@@ -108,7 +117,11 @@ inline int repartition(Forest &f, int max_rank) {
   DBuf<u64> nk(ctx, nnew);
   comm->alltoallv(ctx, f.keys.get(), send_off.data(), nk.get(), recv_off.data(),
                   sizeof(u64));
-  if (f.info.get()) {
+  if (any_info) {
+    if (!f.info.get() && f.n > 0) {
+      f.info.alloc(ctx, f.n);
+      dev_zero(ctx, f.info.get(), (size_t)f.n * sizeof(int16_t));
+    }
     DBuf<int16_t> ni(ctx, nnew);
     comm->alltoallv(ctx, f.info.get(), send_off.data(), ni.get(),
                     recv_off.data(), sizeof(int16_t));
