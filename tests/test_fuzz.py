@@ -414,3 +414,57 @@ def test_fuzz_repartition_max_rank(case, emu_lib, ref_lib):
     a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
     b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
     multirank.compare_rank_results(a, b, "max_rank %s" % (case,))
+
+
+def _name_cases(n, seed):
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        ranks = rng.choice([1, 1, 2, 3])
+        out.append((rng.choice([(2, 2, 1), (2, 1, 1), (2, 2, 2), (1, 1, 1)]), rng.randrange(1, 10 ** 6),
+                    rng.choice([2, 3, 4]), ranks, rng.choice([1, 2]) if ranks > 1 else rng.choice([0, 1, 2]),
+                    rng.choice([0, 1, 2]), rng.randrange(1, 10 ** 6), rng.randrange(1, 10 ** 6),
+                    rng.choice([(None, "a", "b"), (None, None, None, "a"), ("a", "b"), ("a",)])))
+    return out
+
+
+@pytest.mark.parametrize("case", _name_cases(5, 141), ids=lambda c: "-".join(map(str, c[:7])))
+def test_fuzz_name_queries(case, emu_lib, ref_lib):
+    """getOctsWithName / getNodesWithName with random names on every vertex,
+    edge, face and volume of re-oriented tree boxes: root octants (level 0, no
+    refinement), sparse and dense naming, a name nothing carries; 1-3 ranks."""
+    from tmr_b200.forest import OctForest
+    dims, conn_seed, order, ranks, level, passes, seed, name_seed, names = case
+    conn = util.scrambled_conn(*dims, random.Random(conn_seed))
+    xpts = np.random.default_rng(seed).normal(size=(int(conn.max()) + 1, 3))
+
+    def body(lib, rank):
+        f = OctForest(order=order, lib=lib)
+        f.setTrilinearTopology(conn, xpts)
+        c = f.getConnectivity()
+        r = random.Random(name_seed)
+        for kind, count in ((0, c["nnodes"]), (1, c["nedges"]), (2, c["nfaces"]), (3, c["nblocks"])):
+            for i in range(count):
+                name = r.choice(names)
+                if name:
+                    f.setEntityName(kind, i, name)
+        f.createTrees(level)
+        if ranks > 1:
+            f.repartition()
+        for p in range(passes):
+            f.refine(util.synth_flags(f.getOctants().as_array(), seed + p, 30))
+            f.balance(1)
+            if ranks > 1:
+                f.repartition()
+        f.createNodes()
+        return ([f.getOctsWithName(x) for x in ("a", "b", "c")] +
+                [f.getNodesWithName(x) for x in ("a", "b", "c")])
+
+    if ranks == 1:
+        a, b = [body(ref_lib, 0)], [body(emu_lib, 0)]
+    else:
+        a = multirank.run_thread_ranks(ref_lib, ranks, body, True)
+        b = multirank.run_thread_ranks(emu_lib, ranks, body, False)
+    for r in range(ranks):
+        for x, y in zip(a[r], b[r]):
+            assert np.array_equal(x, y), r
